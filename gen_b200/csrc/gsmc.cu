@@ -1,0 +1,930 @@
+// gsmc.cu -- host side of libgensmc.so: the C ABI of include/gen_b200.h.
+//
+// Owns the device-resident ParticleFilterState (src/inference/particle_filter.jl:18-24 of the
+// reference) as structure-of-arrays column slabs and enqueues the kernels of kernels.cuh on one
+// CUDA stream. There is no CPU fallback: every entry point either runs the CUDA path or fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gen_b200.h"
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define CK(expr)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess) return fail(GSMC_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define CKRC(expr)                \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != GSMC_OK) return rc__; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded at run time so that single-GPU use has no NCCL dependency
+// ------------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.lib) return GSMC_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) return fail(GSMC_E_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(NcclComm*, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllGather");
+  g_nccl.CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
+    return fail(GSMC_E_NCCL, "libnccl is missing required symbols");
+  g_nccl.lib = lib;
+  return GSMC_OK;
+}
+#define NK(expr)                                                                                         \
+  do {                                                                                                   \
+    int r__ = (expr);                                                                                    \
+    if (r__ != 0) return fail(GSMC_E_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?"); \
+  } while (0)
+enum { NCCL_UINT8 = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// the filter object
+// ------------------------------------------------------------------------------------------------
+enum KernelClass { KC_PROPAGATE = 0, KC_FINALIZE, KC_SCAN, KC_SPACINGS, KC_SEARCH, KC_OTHER, KC_COUNT };
+
+struct ProfEvent { cudaEvent_t a, b; int cls; };
+
+struct gsmc_filter {
+  gsmc_config cfg;
+  int model = 0, D = 0;
+  bool f32 = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int rank = 0, nranks = 1;
+  NcclComm comm = nullptr;
+  int64_t N = 0, n = 0, n_pad = 0, first = 0;   // global count, local count, padded local, first global index
+  int n_tiles = 0;
+  std::vector<double> params;
+  double* d_params = nullptr;
+  double* d_obs = nullptr;
+  size_t d_obs_cap = 0;
+  // column slabs
+  int64_t cap = 2;            // state/ancestor columns (ring of 2, or history_capacity)
+  int64_t flag_mod = 4;
+  void* state_slab = nullptr; // Real[cap][D][n_pad]
+  uint32_t* anc_slab = nullptr;  // uint32[cap][n_pad]
+  void* lw = nullptr;         // Real[n_pad]
+  uint64_t* cdf = nullptr;    // u64[n_pad]
+  uint64_t* cc = nullptr;     // residual: inclusive counts of deterministic copies
+  uint64_t* tile_a = nullptr; // per-tile sums / prefixes (weights)
+  uint64_t* tile_b = nullptr; // per-tile sums / prefixes (spacings; residual counts)
+  uint64_t* scratch_tot = nullptr;  // 4 u64 scratch totals
+  LseTriple* partials = nullptr;
+  DevScalars* ds = nullptr;
+  DevScalars* h_ds = nullptr; // pinned mirror
+  int* resampled = nullptr;   // device flags, index = step % flag_mod
+  double* d_f64 = nullptr;    // staging for f64 conversions / outputs
+  size_t d_f64_cap = 0;
+  // peers
+  const void* peer_slab[GSMC_MAX_RANKS] = {};
+  const uint32_t* peer_anc[GSMC_MAX_RANKS] = {};
+  const uint64_t* peer_cdf[GSMC_MAX_RANKS] = {};
+  // replay staging
+  double* d_zrep = nullptr; size_t zrep_n = 0, zrep_cap = 0;
+  double* d_urep = nullptr; size_t urep_n = 0, urep_cap = 0;
+  // logical state
+  int64_t T = 0;                 // time steps in the traces
+  bool decided_since_step = false;
+  bool pending = false;          // a resample has been decided but not yet applied by a propagate
+  bool stats_fresh = false;
+  bool is_importance = false;
+  int64_t last_resample_step = 0;
+  uint32_t n_sample_calls = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<ProfEvent> prof_live, prof_free;
+  double prof_ms[KC_COUNT] = {};
+  int64_t prof_n[KC_COUNT] = {};
+  int64_t n_prop_resampled = 0;
+  int64_t launches = 0;
+  cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+};
+
+static size_t real_size(const gsmc_filter* f) { return f->f32 ? 4 : 8; }
+static char* state_col(const gsmc_filter* f, const void* slab, int64_t step) {
+  return (char*)slab + (size_t)((step - 1) % f->cap) * f->D * f->n_pad * real_size(f);
+}
+static uint32_t* anc_col(const gsmc_filter* f, const uint32_t* slab, int64_t step) {
+  return (uint32_t*)slab + (size_t)((step - 1) % f->cap) * f->n_pad;
+}
+
+struct ProfScope {
+  gsmc_filter* f; ProfEvent ev; bool on;
+  ProfScope(gsmc_filter* f_, int cls) : f(f_), on(f_->profiling) {
+    f->launches += 1;
+    if (!on) return;
+    if (!f->prof_free.empty()) { ev = f->prof_free.back(); f->prof_free.pop_back(); }
+    else { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
+    ev.cls = cls;
+    cudaEventRecord(ev.a, f->stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(ev.b, f->stream);
+    f->prof_live.push_back(ev);
+  }
+};
+static void harvest_profile(gsmc_filter* f) {
+  for (ProfEvent& e : f->prof_live) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+      f->prof_ms[e.cls] += ms;
+      f->prof_n[e.cls] += 1;
+    }
+    f->prof_free.push_back(e);
+  }
+  f->prof_live.clear();
+}
+
+static int model_dim(int model) {
+  switch (model) {
+    case GSMC_MODEL_HMM: return HmmModel::D;
+    case GSMC_MODEL_LGSSM: return LgssmModel::D;
+    case GSMC_MODEL_SV: return SvModel::D;
+    case GSMC_MODEL_BEARINGS: return BearingsModel::D;
+    case GSMC_MODEL_REGRESSION: return RegressionModel::D;
+    case GSMC_MODEL_NORMAL_NORMAL: return NormalNormalModel::D;
+    default: return -1;
+  }
+}
+static bool model_is_importance(int model) { return model == GSMC_MODEL_REGRESSION || model == GSMC_MODEL_NORMAL_NORMAL; }
+
+static int check_params(int model, const double* p, size_t np) {
+  switch (model) {
+    case GSMC_MODEL_HMM: {
+      if (np < 2) return fail(GSMC_E_BADARG, "HMM params: [K, V, prior, trans, emis]");
+      const int K = (int)p[0], V = (int)p[1];
+      if (K < 1 || K > GSMC_HMM_MAX_K || V < 1) return fail(GSMC_E_BADARG, "HMM needs 1 <= K <= %d", GSMC_HMM_MAX_K);
+      if (np != (size_t)(2 + K + K * K + K * V)) return fail(GSMC_E_BADARG, "HMM params: expected %d values", 2 + K + K * K + K * V);
+      return GSMC_OK;
+    }
+    case GSMC_MODEL_LGSSM: return np == 7 ? GSMC_OK : fail(GSMC_E_BADARG, "LGSSM params: [m0, s0, a, b, q, c, r]");
+    case GSMC_MODEL_SV: return np == 3 ? GSMC_OK : fail(GSMC_E_BADARG, "SV params: [mu, phi, sigma]");
+    case GSMC_MODEL_BEARINGS: return np == 10 ? GSMC_OK : fail(GSMC_E_BADARG, "bearings params: [m[4], sd[4], sigma_w, sigma_theta]");
+    case GSMC_MODEL_REGRESSION:
+      if (np < 4 || np != (size_t)(4 + (int)p[0])) return fail(GSMC_E_BADARG, "regression params: [n, sd_slope, sd_intercept, sd_noise, xs[n]]");
+      return GSMC_OK;
+    case GSMC_MODEL_NORMAL_NORMAL: return np == 3 ? GSMC_OK : fail(GSMC_E_BADARG, "normal-normal params: [mu0, sd0, sd_y]");
+    default: return fail(GSMC_E_UNSUPPORTED, "unknown model id %d", model);
+  }
+}
+static int expected_obs(const gsmc_filter* f) {
+  if (f->model == GSMC_MODEL_REGRESSION) return (int)f->params[0];
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// allocation
+// ------------------------------------------------------------------------------------------------
+static int alloc_buffers(gsmc_filter* f) {
+  const size_t rs = real_size(f);
+  f->n_pad = (f->n + GSMC_TILE - 1) / GSMC_TILE * GSMC_TILE;
+  f->n_tiles = (int)(f->n_pad / GSMC_TILE);
+  if (f->n > (int64_t)GSMC_ANC_INDEX_MASK) return fail(GSMC_E_BADARG, "at most 2^28-1 particles per GPU");
+  f->cap = f->cfg.keep_history ? (f->cfg.history_capacity > 0 ? f->cfg.history_capacity : 128) : 2;
+  if (f->cap < 2) f->cap = 2;
+  f->flag_mod = f->cfg.keep_history ? f->cap + 2 : 4;
+  CK(cudaMalloc(&f->state_slab, (size_t)f->cap * f->D * f->n_pad * rs));
+  CK(cudaMalloc(&f->anc_slab, (size_t)f->cap * f->n_pad * sizeof(uint32_t)));
+  CK(cudaMalloc(&f->lw, f->n_pad * rs));
+  CK(cudaMalloc(&f->cdf, f->n_pad * sizeof(uint64_t)));
+  if (f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL) CK(cudaMalloc(&f->cc, f->n_pad * sizeof(uint64_t)));
+  CK(cudaMalloc(&f->tile_a, (size_t)f->n_tiles * sizeof(uint64_t)));
+  CK(cudaMalloc(&f->tile_b, (size_t)f->n_tiles * sizeof(uint64_t)));
+  CK(cudaMalloc(&f->scratch_tot, 4 * sizeof(uint64_t)));
+  CK(cudaMalloc(&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
+  CK(cudaMalloc(&f->ds, sizeof(DevScalars)));
+  CK(cudaMallocHost(&f->h_ds, sizeof(DevScalars)));
+  CK(cudaMalloc(&f->resampled, (size_t)f->flag_mod * sizeof(int)));
+  CK(cudaMemsetAsync(f->ds, 0, sizeof(DevScalars), f->stream));
+  CK(cudaMemsetAsync(f->resampled, 0, (size_t)f->flag_mod * sizeof(int), f->stream));
+  // pad lanes of the log-weight column are read by vector loads: keep them finite and harmless
+  CK(cudaMemsetAsync(f->lw, 0, f->n_pad * rs, f->stream));
+  CK(cudaMemsetAsync(f->anc_slab, 0, (size_t)f->cap * f->n_pad * sizeof(uint32_t), f->stream));
+  CK(cudaMemsetAsync(f->state_slab, 0, (size_t)f->cap * f->D * f->n_pad * rs, f->stream));
+  f->peer_slab[f->rank] = f->state_slab;
+  f->peer_anc[f->rank] = f->anc_slab;
+  f->peer_cdf[f->rank] = f->cdf;
+  return GSMC_OK;
+}
+static void free_buffers(gsmc_filter* f) {
+  for (int r = 0; r < f->nranks; ++r) {
+    if (r == f->rank) continue;
+    if (f->peer_slab[r]) cudaIpcCloseMemHandle((void*)f->peer_slab[r]);
+    if (f->peer_anc[r]) cudaIpcCloseMemHandle((void*)f->peer_anc[r]);
+    if (f->peer_cdf[r]) cudaIpcCloseMemHandle((void*)f->peer_cdf[r]);
+    f->peer_slab[r] = nullptr; f->peer_anc[r] = nullptr; f->peer_cdf[r] = nullptr;
+  }
+  cudaFree(f->state_slab); cudaFree(f->anc_slab); cudaFree(f->lw); cudaFree(f->cdf); cudaFree(f->cc);
+  cudaFree(f->tile_a); cudaFree(f->tile_b); cudaFree(f->scratch_tot); cudaFree(f->partials); cudaFree(f->ds);
+  cudaFree(f->resampled);
+  if (f->h_ds) cudaFreeHost(f->h_ds);
+  f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
+  f->tile_a = f->tile_b = f->scratch_tot = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
+  f->resampled = nullptr;
+}
+static int ensure_f64(gsmc_filter* f, size_t n) {
+  if (n <= f->d_f64_cap) return GSMC_OK;
+  cudaFree(f->d_f64);
+  f->d_f64 = nullptr; f->d_f64_cap = 0;
+  CK(cudaMalloc(&f->d_f64, n * sizeof(double)));
+  f->d_f64_cap = n;
+  return GSMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+template <class Model, typename Real, bool INIT, int PROP>
+static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
+  Model::prepare(a, INIT, PROP);
+  PropArgs<Real> g;
+  memset(&g, 0, sizeof g);
+  const int64_t new_step = f->T + 1;
+  for (int r = 0; r < f->nranks; ++r)
+    g.cur[r] = INIT ? nullptr : (const Real*)state_col(f, f->peer_slab[r], f->T);
+  g.nxt = (Real*)state_col(f, f->state_slab, new_step);
+  g.lw = (Real*)f->lw;
+  g.anc = anc_col(f, f->anc_slab, new_step);
+  g.resampled_flag = f->resampled + (new_step % f->flag_mod);
+  g.partials = f->partials;
+  g.n = f->n; g.stride = f->n_pad; g.first_global = (uint64_t)f->first; g.seed = f->cfg.seed;
+  g.t = (uint32_t)new_step;
+  g.use_anc = use_anc ? 1 : 0;
+  g.zrep = f->zrep_n ? f->d_zrep : nullptr;
+  g.urep = f->urep_n ? f->d_urep : nullptr;
+  const int nz = Model::nz(INIT, PROP), nu = Model::nu(INIT, PROP);
+  if (g.zrep && f->zrep_n != (size_t)(f->n * nz)) return fail(GSMC_E_BADARG, "replay normals: expected %lld values", (long long)(f->n * nz));
+  if (g.urep && nu && f->urep_n != (size_t)(f->n * nu)) return fail(GSMC_E_BADARG, "replay uniforms: expected %lld values", (long long)(f->n * nu));
+  if (!nu) g.urep = nullptr;
+  if (!nz) g.zrep = nullptr;
+  {
+    ProfScope ps(f, KC_PROPAGATE);
+    propagate_kernel<Model, Real, INIT, PROP><<<f->n_tiles, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream>>>(g, a);
+  }
+  CK(cudaGetLastError());
+  return GSMC_OK;
+}
+template <class Model, typename Real>
+static int launch_propagate_m(gsmc_filter* f, ModelArgs& a, bool init, int prop, bool use_anc) {
+  if (!Model::has_proposal(prop)) return fail(GSMC_E_UNSUPPORTED, "model %d has no proposal %d in the catalogue", f->model, prop);
+  if (init) return prop ? launch_propagate_t<Model, Real, true, 1>(f, a, use_anc) : launch_propagate_t<Model, Real, true, 0>(f, a, use_anc);
+  return prop ? launch_propagate_t<Model, Real, false, 1>(f, a, use_anc) : launch_propagate_t<Model, Real, false, 0>(f, a, use_anc);
+}
+template <typename Real>
+static int launch_propagate_r(gsmc_filter* f, ModelArgs& a, bool init, int prop, bool use_anc) {
+  switch (f->model) {
+    case GSMC_MODEL_HMM: return launch_propagate_m<HmmModel, Real>(f, a, init, prop, use_anc);
+    case GSMC_MODEL_LGSSM: return launch_propagate_m<LgssmModel, Real>(f, a, init, prop, use_anc);
+    case GSMC_MODEL_SV: return launch_propagate_m<SvModel, Real>(f, a, init, prop, use_anc);
+    case GSMC_MODEL_BEARINGS: return launch_propagate_m<BearingsModel, Real>(f, a, init, prop, use_anc);
+    case GSMC_MODEL_REGRESSION: return launch_propagate_m<RegressionModel, Real>(f, a, init, prop, use_anc);
+    case GSMC_MODEL_NORMAL_NORMAL: return launch_propagate_m<NormalNormalModel, Real>(f, a, init, prop, use_anc);
+  }
+  return fail(GSMC_E_UNSUPPORTED, "unknown model");
+}
+
+static int fill_model_args(gsmc_filter* f, ModelArgs& a, const double* obs, size_t n_obs, int prop, const double* pp, size_t npp) {
+  memset(&a, 0, sizeof a);
+  const int need = expected_obs(f);
+  if (!obs || (int)n_obs != need) return fail(GSMC_E_BADARG, "model %d needs %d observation value(s) per step, got %zu", f->model, need, n_obs);
+  if (npp > 8) return fail(GSMC_E_BADARG, "at most 8 proposal parameters");
+  if (prop != GSMC_PROPOSAL_DEFAULT && prop != GSMC_PROPOSAL_CUSTOM) return fail(GSMC_E_BADARG, "bad proposal id %d", prop);
+  a.n_p = (int)f->params.size(); a.n_obs = (int)n_obs;
+  for (size_t i = 0; i < f->params.size() && i < GSMC_MAX_INLINE_PARAMS; ++i) a.p[i] = f->params[i];
+  for (size_t i = 0; i < n_obs && i < GSMC_MAX_INLINE_OBS; ++i) a.obs[i] = obs[i];
+  for (size_t i = 0; i < npp; ++i) a.pp[i] = pp[i];
+  a.p_dev = f->d_params;
+  a.obs_dev = nullptr;
+  if (f->model == GSMC_MODEL_REGRESSION) {
+    if (prop == GSMC_PROPOSAL_CUSTOM && npp != 4) return fail(GSMC_E_BADARG, "regression proposal params: [mu_slope, sd_slope, mu_intercept, sd_intercept]");
+    if (n_obs > f->d_obs_cap) {
+      cudaFree(f->d_obs); f->d_obs = nullptr; f->d_obs_cap = 0;
+      CK(cudaMalloc(&f->d_obs, n_obs * sizeof(double)));
+      f->d_obs_cap = n_obs;
+    }
+    CK(cudaMemcpyAsync(f->d_obs, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    CK(cudaStreamSynchronize(f->stream));      // obs is a borrowed host pointer
+    a.obs_dev = f->d_obs;
+  }
+  if (f->model == GSMC_MODEL_NORMAL_NORMAL && prop == GSMC_PROPOSAL_CUSTOM && npp != 2)
+    return fail(GSMC_E_BADARG, "normal-normal proposal params: [mu_q, sd_q]");
+  if (f->model == GSMC_MODEL_HMM) {
+    const int V = (int)f->params[1];
+    if (!(obs[0] >= 1 && obs[0] <= V) || obs[0] != (double)(int)obs[0]) return fail(GSMC_E_BADARG, "HMM observation must be an integer in 1..%d", V);
+  }
+  return GSMC_OK;
+}
+
+static int launch_propagate(gsmc_filter* f, bool init, const double* obs, size_t n_obs, int prop, const double* pp, size_t npp, bool use_anc) {
+  ModelArgs a;
+  CKRC(fill_model_args(f, a, obs, n_obs, prop, pp, npp));
+  if (f->cfg.keep_history && f->T + 1 > f->cap) return fail(GSMC_E_BADARG, "history_capacity (%lld steps) exceeded", (long long)f->cap);
+  int rc = f->f32 ? launch_propagate_r<float>(f, a, init, prop, use_anc) : launch_propagate_r<double>(f, a, init, prop, use_anc);
+  f->zrep_n = 0; f->urep_n = 0;
+  return rc;
+}
+
+// finalize (+ decision when ess_threshold >= 0); leaves the statistics in f->ds
+static int launch_finalize(gsmc_filter* f, double ess_threshold) {
+  int* flag = ess_threshold >= 0.0 ? f->resampled + ((f->T + 1) % f->flag_mod) : nullptr;
+  {
+    ProfScope ps(f, KC_FINALIZE);
+    finalize_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_tiles, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag);
+  }
+  CK(cudaGetLastError());
+  if (f->nranks > 1) {
+    NK(g_nccl.AllGather((const char*)f->ds->triples + f->rank * sizeof(LseTriple), f->ds->triples, sizeof(LseTriple), NCCL_UINT8, f->comm, f->stream));
+    ProfScope ps(f, KC_FINALIZE);
+    decide_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, ess_threshold, (double)f->N, flag);
+    CK(cudaGetLastError());
+  }
+  return GSMC_OK;
+}
+static int fetch_scalars(gsmc_filter* f) {
+  CK(cudaMemcpyAsync(f->h_ds, f->ds, sizeof(DevScalars), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  return GSMC_OK;
+}
+
+__global__ void totals_kernel(DevScalars* ds, int nranks, uint64_t n_global, int set_draws, int conditional) {
+  if (threadIdx.x || blockIdx.x) return;
+  if (conditional && !ds->do_resample) return;
+  uint64_t s = 0;
+  for (int r = 0; r < nranks; ++r) s += ds->cdf_rank_total[r];
+  ds->cdf_total = s;
+  if (set_draws) { ds->n_draws = n_global; ds->n_det = 0; }
+}
+
+static CdfView make_cdf_view(const gsmc_filter* f) {
+  CdfView v;
+  memset(&v, 0, sizeof v);
+  for (int r = 0; r < f->nranks; ++r) v.seg[r] = f->peer_cdf[r];
+  v.n_per = f->n;
+  v.nranks = f->nranks;
+  return v;
+}
+
+template <typename Real>
+static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
+  const Real* lw = (const Real*)f->lw;
+  const double scale = gm_pow2([&] { int lg = 0; while (((uint64_t)1 << lg) < (uint64_t)f->N) ++lg; int k = 62 - lg; return k > 52 ? 52 : k; }());
+  const int nt = f->n_tiles;
+  const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
+  uint32_t* anc = anc_col(f, f->anc_slab, f->T + 1);
+  if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
+  // 1. integer weights -> tile sums -> tile prefixes and this rank's total
+  { ProfScope ps(f, KC_SCAN); qsum_kernel<Real><<<nt, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, conditional); }
+  { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[f->rank], nullptr, conditional); }
+  CK(cudaGetLastError());
+  if (f->nranks > 1)
+    NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+  { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, (uint64_t)f->N, residual ? 0 : 1, conditional); }
+  if (!residual) {
+    ProfScope ps(f, KC_SCAN);
+    cdf_kernel<Real><<<nt, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->cdf, conditional);
+  } else {
+    { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
+    { ProfScope ps(f, KC_SCAN); resid_sum_kernel<Real><<<nt, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, conditional); }
+    { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, f->tile_b, nt, f->ds, f->scratch_tot, f->scratch_tot + 1, conditional); }
+    { ProfScope ps(f, KC_OTHER); resid_totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->scratch_tot, f->scratch_tot + 1, (uint64_t)f->N); }
+    { ProfScope ps(f, KC_SCAN); resid_cdf_kernel<Real><<<nt, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, f->cc, f->cdf, conditional); }
+    { ProfScope ps(f, KC_SEARCH); det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(f->cc, f->n, f->ds, anc, conditional); }
+  }
+  CK(cudaGetLastError());
+  const CdfView v = make_cdf_view(f);
+  if (replay_iid) {
+    // one exported uniform per output slot (per multinomial draw in the residual scheme)
+    if (!residual && f->urep_n != (size_t)f->n) return fail(GSMC_E_BADARG, "replay uniforms for maybe_resample: expected %lld values", (long long)f->n);
+    ProfScope ps(f, KC_SEARCH);
+    search_iid_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(
+        v, f->ds, f->d_urep, 0, 0, 0, f->n, residual ? 1 : 0, anc, nullptr, conditional);
+    f->urep_n = 0;
+  } else {
+    // 2. sorted uniforms: spacing tile sums -> prefixes -> S_tot
+    const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
+    { ProfScope ps(f, KC_SPACINGS); spacing_sum_kernel<<<nt, GSMC_BLOCK, 0, f->stream>>>(f->cfg.seed, k_first, f->ds, f->tile_b, conditional); }
+    { ProfScope ps(f, KC_SPACINGS); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_b, nullptr, nt, f->ds, &f->ds->spacing_rank_total[f->rank], nullptr, conditional); }
+    CK(cudaGetLastError());
+    if (f->nranks > 1)
+      NK(g_nccl.AllGather((const char*)(f->ds->spacing_rank_total + f->rank), f->ds->spacing_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+    { ProfScope ps(f, KC_SPACINGS); spacing_total_kernel<<<1, 32, 0, f->stream>>>(f->cfg.seed, f->ds, f->nranks); }
+    // 3. ancestors
+    { ProfScope ps(f, KC_SEARCH);
+      search_sorted_kernel<<<nt, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, anc, f->n, residual ? 1 : 0, conditional); }
+  }
+  CK(cudaGetLastError());
+  return GSMC_OK;
+}
+static int launch_resample(gsmc_filter* f, int conditional, bool replay_iid) {
+  return f->f32 ? launch_resample_t<float>(f, conditional, replay_iid) : launch_resample_t<double>(f, conditional, replay_iid);
+}
+
+template <typename Real>
+static HistView<Real> make_hist_view(const gsmc_filter* f) {
+  HistView<Real> h;
+  memset(&h, 0, sizeof h);
+  for (int r = 0; r < f->nranks; ++r) { h.slab[r] = (const Real*)f->peer_slab[r]; h.anc_slab[r] = f->peer_anc[r]; }
+  h.resampled = f->resampled; h.stride = f->n_pad; h.D = f->D; h.cap = f->cap; h.flag_mod = f->flag_mod;
+  return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+GSMC_API const char* gsmc_version(void) { return "gen_b200 0.1.0 (sm_100a)"; }
+GSMC_API const char* gsmc_last_error(gsmc_handle) { return g_last_error.c_str(); }
+
+GSMC_API int gsmc_create(const gsmc_config* cfg, const double* params, size_t n_params, gsmc_handle* out) {
+  if (!cfg || !out || !params) return fail(GSMC_E_BADARG, "null argument");
+  if (cfg->struct_size != sizeof(gsmc_config)) return fail(GSMC_E_BADARG, "gsmc_config.struct_size mismatch (%u vs %zu)", cfg->struct_size, sizeof(gsmc_config));
+  *out = nullptr;
+  const int D = model_dim(cfg->model_id);
+  if (D < 0) return fail(GSMC_E_UNSUPPORTED, "unknown model id %d", cfg->model_id);
+  CKRC(check_params(cfg->model_id, params, n_params));
+  if (cfg->num_particles < 1) return fail(GSMC_E_BADARG, "num_particles must be >= 1");
+  if (cfg->dtype != GSMC_F64 && cfg->dtype != GSMC_F32) return fail(GSMC_E_BADARG, "bad dtype");
+  if (cfg->resample_scheme != GSMC_RESAMPLE_MULTINOMIAL && cfg->resample_scheme != GSMC_RESAMPLE_RESIDUAL) return fail(GSMC_E_BADARG, "bad resample_scheme");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1) return fail(GSMC_E_CUDA, "no CUDA device available (%s); libgensmc has no CPU path", cudaGetErrorString(e));
+  gsmc_filter* f = new gsmc_filter();
+  f->cfg = *cfg;
+  f->model = cfg->model_id; f->D = D; f->f32 = cfg->dtype == GSMC_F32;
+  f->is_importance = model_is_importance(cfg->model_id);
+  if (cfg->device >= 0) f->device = cfg->device; else cudaGetDevice(&f->device);
+  if (cudaSetDevice(f->device) != cudaSuccess) { delete f; return fail(GSMC_E_CUDA, "cannot select device %d", cfg->device); }
+  if (cfg->stream) f->stream = (cudaStream_t)cfg->stream;
+  else { if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess) { delete f; return fail(GSMC_E_CUDA, "stream creation failed"); } f->own_stream = true; }
+  f->params.assign(params, params + n_params);
+  f->N = (int64_t)cfg->num_particles; f->n = f->N; f->first = 0;
+  if (cudaMalloc(&f->d_params, n_params * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(f->d_params, params, n_params * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    gsmc_destroy(f);
+    return fail(GSMC_E_CUDA, "parameter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaEventCreate(&f->timer_a); cudaEventCreate(&f->timer_b);
+  *out = f;
+  return GSMC_OK;
+}
+
+GSMC_API void gsmc_destroy(gsmc_handle f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  harvest_profile(f);
+  for (ProfEvent& e : f->prof_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  free_buffers(f);
+  cudaFree(f->d_params); cudaFree(f->d_obs); cudaFree(f->d_zrep); cudaFree(f->d_urep); cudaFree(f->d_f64);
+  if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(f->comm);
+  if (f->timer_a) cudaEventDestroy(f->timer_a);
+  if (f->timer_b) cudaEventDestroy(f->timer_b);
+  if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+GSMC_API int gsmc_comm_unique_id(void* id_out, size_t nbytes) {
+  if (!id_out || nbytes < sizeof(NcclId)) return fail(GSMC_E_BADARG, "id buffer must hold 128 bytes");
+  CKRC(load_nccl());
+  NK(g_nccl.GetUniqueId((NcclId*)id_out));
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_comm_attach(gsmc_handle f, const void* unique_id, size_t nbytes, int rank, int nranks) {
+  if (!f || !unique_id || nbytes < sizeof(NcclId)) return fail(GSMC_E_BADARG, "bad arguments");
+  if (f->T != 0 || f->state_slab) return fail(GSMC_E_BADARG, "attach must precede gsmc_init");
+  if (nranks < 1 || nranks > GSMC_MAX_RANKS || rank < 0 || rank >= nranks) return fail(GSMC_E_BADARG, "1 <= nranks <= %d", GSMC_MAX_RANKS);
+  if (f->N % ((int64_t)nranks * GSMC_TILE) != 0) return fail(GSMC_E_BADARG, "num_particles must be a multiple of %d * nranks", GSMC_TILE);
+  CK(cudaSetDevice(f->device));
+  f->rank = rank; f->nranks = nranks;
+  f->n = f->N / nranks; f->first = f->n * rank;
+  if (nranks == 1) return GSMC_OK;
+  CKRC(load_nccl());
+  NcclId id;
+  memcpy(&id, unique_id, sizeof id);
+  NK(g_nccl.CommInitRank(&f->comm, nranks, id, rank));
+  // allocate now and exchange IPC handles of the slabs peers read (state, ancestors, CDF)
+  CKRC(alloc_buffers(f));
+  struct Handles { cudaIpcMemHandle_t slab, anc, cdf; };
+  Handles mine;
+  CK(cudaIpcGetMemHandle(&mine.slab, f->state_slab));
+  CK(cudaIpcGetMemHandle(&mine.anc, f->anc_slab));
+  CK(cudaIpcGetMemHandle(&mine.cdf, f->cdf));
+  Handles* d_all = nullptr;
+  CK(cudaMalloc(&d_all, sizeof(Handles) * nranks));
+  CK(cudaMemcpyAsync(d_all + rank, &mine, sizeof mine, cudaMemcpyHostToDevice, f->stream));
+  NK(g_nccl.AllGather(d_all + rank, d_all, sizeof(Handles), NCCL_UINT8, f->comm, f->stream));
+  std::vector<Handles> all(nranks);
+  CK(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * nranks, cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  cudaFree(d_all);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) continue;
+    void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+    CK(cudaIpcOpenMemHandle(&p0, all[r].slab, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&p1, all[r].anc, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&p2, all[r].cdf, cudaIpcMemLazyEnablePeerAccess));
+    f->peer_slab[r] = p0; f->peer_anc[r] = (const uint32_t*)p1; f->peer_cdf[r] = (const uint64_t*)p2;
+  }
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_set_replay(gsmc_handle f, const double* normals, size_t n_normals, const double* uniforms, size_t n_uniforms) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  CK(cudaSetDevice(f->device));
+  f->zrep_n = 0; f->urep_n = 0;
+  if (normals && n_normals) {
+    if (n_normals > f->zrep_cap) { cudaFree(f->d_zrep); f->d_zrep = nullptr; f->zrep_cap = 0; CK(cudaMalloc(&f->d_zrep, n_normals * sizeof(double))); f->zrep_cap = n_normals; }
+    CK(cudaMemcpyAsync(f->d_zrep, normals, n_normals * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    f->zrep_n = n_normals;
+  }
+  if (uniforms && n_uniforms) {
+    if (n_uniforms > f->urep_cap) { cudaFree(f->d_urep); f->d_urep = nullptr; f->urep_cap = 0; CK(cudaMalloc(&f->d_urep, n_uniforms * sizeof(double))); f->urep_cap = n_uniforms; }
+    CK(cudaMemcpyAsync(f->d_urep, uniforms, n_uniforms * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+    f->urep_n = n_uniforms;
+  }
+  CK(cudaStreamSynchronize(f->stream));   // host pointers are borrowed for this call only
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_init(gsmc_handle f, const double* obs, size_t n_obs, int prop, const double* pp, size_t npp) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  if (f->T != 0) return fail(GSMC_E_BADARG, "filter is already initialised");
+  CK(cudaSetDevice(f->device));
+  if (!f->state_slab) CKRC(alloc_buffers(f));
+  CKRC(launch_propagate(f, true, obs, n_obs, prop, pp, npp, false));
+  f->T = 1;
+  f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_step(gsmc_handle f, const double* obs, size_t n_obs, int prop, const double* pp, size_t npp) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (f->is_importance) return fail(GSMC_E_BADARG, "importance-sampling models have a single step");
+  CK(cudaSetDevice(f->device));
+  const bool gathered = f->pending;
+  CKRC(launch_propagate(f, false, obs, n_obs, prop, pp, npp, f->decided_since_step));
+  if (gathered) f->n_prop_resampled += 1;
+  f->T += 1;
+  f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_maybe_resample(gsmc_handle f, double ess_threshold, int* did_resample, double* ess_out) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (!(ess_threshold >= 0.0)) return fail(GSMC_E_BADARG, "ess_threshold must be >= 0");
+  CK(cudaSetDevice(f->device));
+  if (f->pending) {
+    // log weights are all zero after a resample: ESS = N exactly (particle_filter.jl:193)
+    if ((double)f->N < ess_threshold) return fail(GSMC_E_UNSUPPORTED, "two resampling events without a step in between");
+    if (did_resample) *did_resample = 0;
+    if (ess_out) *ess_out = (double)f->N;
+    return GSMC_OK;
+  }
+  CKRC(launch_finalize(f, ess_threshold));
+  CKRC(fetch_scalars(f));
+  f->stats_fresh = true;
+  f->decided_since_step = true;
+  if (f->h_ds->error) {
+    f->decided_since_step = false;
+    cudaMemsetAsync(&f->ds->error, 0, sizeof(int), f->stream);
+    return fail(GSMC_E_DEGENERATE, "total weight is zero or not finite (log_total = %g)", f->h_ds->log_total);
+  }
+  const int did = f->h_ds->do_resample;
+  if (did) {
+    const bool replay = f->urep_n > 0;
+    CKRC(launch_resample(f, 0, replay));
+    f->pending = true;
+    f->last_resample_step = f->T + 1;
+  }
+  f->urep_n = 0;
+  if (did_resample) *did_resample = did;
+  if (ess_out) *ess_out = f->h_ds->ess;
+  return GSMC_OK;
+}
+
+static int refresh_stats(gsmc_filter* f) {
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (!f->stats_fresh && !f->pending) {
+    CKRC(launch_finalize(f, -1.0));
+    CKRC(fetch_scalars(f));
+    f->stats_fresh = true;
+  } else if (!f->stats_fresh) {
+    CKRC(fetch_scalars(f));
+  }
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_log_ml_estimate(gsmc_handle f, double* out) {
+  if (!f || !out) return fail(GSMC_E_BADARG, "null argument");
+  CK(cudaSetDevice(f->device));
+  CKRC(refresh_stats(f));
+  // particle_filter.jl:52-55; after a resample the log weights are zero: logsumexp = log N
+  const double logn = gm_log((double)f->N);
+  *out = f->pending ? f->h_ds->log_ml_est + (logn - logn) : f->h_ds->log_ml_est + f->h_ds->log_total - logn;
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_get_log_weights(gsmc_handle f, double* host_dst, size_t n) {
+  if (!f || !host_dst) return fail(GSMC_E_BADARG, "null argument");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (n != (size_t)f->n) return fail(GSMC_E_BADARG, "expected a buffer of %lld values", (long long)f->n);
+  CK(cudaSetDevice(f->device));
+  if (f->pending) { for (size_t i = 0; i < n; ++i) host_dst[i] = 0.; return GSMC_OK; }   // particle_filter.jl:204
+  if (!f->f32) {
+    CK(cudaMemcpyAsync(host_dst, f->lw, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  } else {
+    CKRC(ensure_f64(f, n));
+    { ProfScope ps(f, KC_OTHER); column_to_f64_kernel<float><<<(int)((n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->d_f64, (int64_t)n); }
+    CK(cudaMemcpyAsync(host_dst, f->d_f64, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  }
+  CK(cudaStreamSynchronize(f->stream));
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_get_log_weights_device(gsmc_handle f, void** dev_ptr) {
+  if (!f || !dev_ptr) return fail(GSMC_E_BADARG, "null argument");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (f->pending) CK(cudaMemsetAsync(f->lw, 0, f->n_pad * real_size(f), f->stream));
+  *dev_ptr = f->lw;
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_get_state(gsmc_handle f, int64_t t, double* host_dst, size_t n_values) {
+  if (!f || !host_dst) return fail(GSMC_E_BADARG, "null argument");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (t == 0) t = f->T;
+  if (t < 1 || t > f->T) return fail(GSMC_E_BADARG, "time step %lld out of range 1..%lld", (long long)t, (long long)f->T);
+  if (t != f->T && !f->cfg.keep_history) return fail(GSMC_E_BADARG, "earlier time steps need keep_history=1");
+  if (n_values != (size_t)(f->D * f->n)) return fail(GSMC_E_BADARG, "expected a buffer of %lld values", (long long)(f->D * f->n));
+  CK(cudaSetDevice(f->device));
+  CKRC(ensure_f64(f, n_values));
+  const int grid = (int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK);
+  {
+    ProfScope ps(f, KC_OTHER);
+    if (f->f32) get_state_kernel<float><<<grid, GSMC_BLOCK, 0, f->stream>>>(make_hist_view<float>(f), f->rank, f->n, t, f->T, f->pending ? 1 : 0, f->d_f64);
+    else get_state_kernel<double><<<grid, GSMC_BLOCK, 0, f->stream>>>(make_hist_view<double>(f), f->rank, f->n, t, f->T, f->pending ? 1 : 0, f->d_f64);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host_dst, f->d_f64, n_values * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_get_trajectories(gsmc_handle f, const int64_t* idx, size_t n_idx, double* out, size_t n_values) {
+  if (!f || !idx || !out) return fail(GSMC_E_BADARG, "null argument");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (!f->cfg.keep_history && f->T > 1) return fail(GSMC_E_BADARG, "trajectories need keep_history=1");
+  if (n_values != n_idx * (size_t)f->T * f->D) return fail(GSMC_E_BADARG, "expected a buffer of %zu values", n_idx * (size_t)f->T * f->D);
+  for (size_t s = 0; s < n_idx; ++s) if (idx[s] < 0 || idx[s] >= f->n) return fail(GSMC_E_BADARG, "particle index %lld out of range", (long long)idx[s]);
+  if (n_idx == 0) return GSMC_OK;
+  CK(cudaSetDevice(f->device));
+  CKRC(ensure_f64(f, n_values + n_idx));
+  int64_t* d_idx = (int64_t*)(f->d_f64 + n_values);
+  CK(cudaMemcpyAsync(d_idx, idx, n_idx * sizeof(int64_t), cudaMemcpyHostToDevice, f->stream));
+  const int grid = (int)((n_idx + GSMC_BLOCK - 1) / GSMC_BLOCK);
+  {
+    ProfScope ps(f, KC_OTHER);
+    if (f->f32) trajectories_kernel<float><<<grid, GSMC_BLOCK, 0, f->stream>>>(make_hist_view<float>(f), f->rank, d_idx, (int64_t)n_idx, f->T, f->pending ? 1 : 0, f->d_f64);
+    else trajectories_kernel<double><<<grid, GSMC_BLOCK, 0, f->stream>>>(make_hist_view<double>(f), f->rank, d_idx, (int64_t)n_idx, f->T, f->pending ? 1 : 0, f->d_f64);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, f->d_f64, n_values * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_get_ancestors(gsmc_handle f, int64_t* host_dst, size_t n) {
+  if (!f || !host_dst) return fail(GSMC_E_BADARG, "null argument");
+  if (n != (size_t)f->n) return fail(GSMC_E_BADARG, "expected a buffer of %lld values", (long long)f->n);
+  CK(cudaSetDevice(f->device));
+  if (f->last_resample_step == 0) {         // parents = collect(1:num_particles), particle_filter.jl:90,107
+    for (size_t i = 0; i < n; ++i) host_dst[i] = f->first + (int64_t)i;
+    return GSMC_OK;
+  }
+  if (f->cfg.keep_history ? false : (f->last_resample_step < f->T)) return fail(GSMC_E_BADARG, "ancestor column has been recycled (keep_history=0)");
+  CKRC(ensure_f64(f, n));
+  { ProfScope ps(f, KC_OTHER);
+    anc_to_global_kernel<<<(int)((n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(anc_col(f, f->anc_slab, f->last_resample_step), (int64_t)n, f->n, (int64_t*)f->d_f64); }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host_dst, f->d_f64, n * sizeof(int64_t), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t* idx_out) {
+  if (!f || (!idx_out && num_samples)) return fail(GSMC_E_BADARG, "null argument");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "sample_unweighted is single-GPU in this version");
+  if (num_samples == 0) return GSMC_OK;
+  CK(cudaSetDevice(f->device));
+  CKRC(ensure_f64(f, num_samples));
+  int64_t* d_idx = (int64_t*)f->d_f64;
+  const int grid = (int)((num_samples + GSMC_BLOCK - 1) / GSMC_BLOCK);
+  if (f->pending) {
+    // uniform weights: the categorical draw over equal integer weights; build the CDF from zeros
+    CK(cudaMemsetAsync(f->lw, 0, f->n_pad * real_size(f), f->stream));
+  }
+  // statistics (max) of the current weights, then the integer CDF, unconditionally
+  if (f->pending) {
+    // partials still describe the pre-resample weights; recompute max = 0 directly
+    DevScalars z; memset(&z, 0, sizeof z);
+    CK(cudaMemcpyAsync(&f->ds->max_lw, &z.max_lw, sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  } else {
+    CKRC(launch_finalize(f, -1.0));
+  }
+  const bool residual_cfg = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
+  (void)residual_cfg;
+  {
+    const double scale = gm_pow2([&] { int lg = 0; while (((uint64_t)1 << lg) < (uint64_t)f->N) ++lg; int k = 62 - lg; return k > 52 ? 52 : k; }());
+    const int nt = f->n_tiles;
+    if (f->f32) {
+      { ProfScope ps(f, KC_SCAN); qsum_kernel<float><<<nt, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, 0); }
+      { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0); }
+      { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, 1, (uint64_t)f->N, 0, 0); }
+      { ProfScope ps(f, KC_SCAN); cdf_kernel<float><<<nt, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, 0); }
+    } else {
+      { ProfScope ps(f, KC_SCAN); qsum_kernel<double><<<nt, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, 0); }
+      { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0); }
+      { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, 1, (uint64_t)f->N, 0, 0); }
+      { ProfScope ps(f, KC_SCAN); cdf_kernel<double><<<nt, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, 0); }
+    }
+  }
+  CK(cudaGetLastError());
+  const double* urep = nullptr;
+  if (f->urep_n) {
+    if (f->urep_n != num_samples) return fail(GSMC_E_BADARG, "replay uniforms for sample_unweighted: expected %llu values", (unsigned long long)num_samples);
+    urep = f->d_urep;
+  }
+  { ProfScope ps(f, KC_SEARCH);
+    search_iid_kernel<<<grid, GSMC_BLOCK, 0, f->stream>>>(make_cdf_view(f), f->ds, urep, f->cfg.seed, f->n_sample_calls, GSMC_STREAM_SAMPLE,
+                                                         (int64_t)num_samples, 0, nullptr, d_idx, 0); }
+  CK(cudaGetLastError());
+  f->urep_n = 0;
+  f->n_sample_calls += 1;
+  CK(cudaMemcpyAsync(idx_out, d_idx, num_samples * sizeof(int64_t), cudaMemcpyDeviceToHost, f->stream));
+  CKRC(fetch_scalars(f));
+  if (!(f->h_ds->cdf_total > 0)) return fail(GSMC_E_DEGENERATE, "total weight is zero or not finite");
+  // sampling indexes the CURRENT particle order; with a pending resample that order is the ancestor column
+  if (f->pending) return fail(GSMC_E_UNSUPPORTED, "sample_unweighted between maybe_resample and the next step");
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_importance_sampling(const gsmc_config* cfg, const double* params, size_t n_params, const double* obs, size_t n_obs,
+                                      int prop, const double* pp, size_t npp, double* lml_out, gsmc_handle* out) {
+  if (!cfg || !out || !lml_out) return fail(GSMC_E_BADARG, "null argument");
+  if (!model_is_importance(cfg->model_id)) return fail(GSMC_E_UNSUPPORTED, "model %d is a state-space family: compose init/step instead", cfg->model_id);
+  gsmc_handle f = nullptr;
+  CKRC(gsmc_create(cfg, params, n_params, &f));
+  int rc = gsmc_init(f, obs, n_obs, prop, pp, npp);                       // importance.jl:25-28 / 41-47
+  if (rc == GSMC_OK) rc = launch_finalize(f, -1.0);                       // log_total_weight = logsumexp(log_weights)
+  if (rc == GSMC_OK) {
+    ProfScope ps(f, KC_OTHER);
+    const int grid = (int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK);
+    if (f->f32) normalize_lw_kernel<float><<<grid, GSMC_BLOCK, 0, f->stream>>>((float*)f->lw, f->n, f->ds);
+    else normalize_lw_kernel<double><<<grid, GSMC_BLOCK, 0, f->stream>>>((double*)f->lw, f->n, f->ds);
+  }
+  if (rc == GSMC_OK) rc = fetch_scalars(f);
+  if (rc != GSMC_OK) { std::string keep = g_last_error; gsmc_destroy(f); g_last_error = keep; return rc; }
+  *lml_out = f->h_ds->log_total - gm_log((double)f->N);                   // importance.jl:30,49
+  f->stats_fresh = true;
+  *out = f;
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, size_t n_obs, int prop, const double* pp, size_t npp,
+                            double ess_threshold) {
+  if (!f || !obs) return fail(GSMC_E_BADARG, "null argument");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (f->is_importance) return fail(GSMC_E_BADARG, "importance-sampling models have a single step");
+  if (f->pending) return fail(GSMC_E_BADARG, "call gsmc_step after gsmc_maybe_resample before gsmc_run_steps");
+  if (f->zrep_n || f->urep_n) return fail(GSMC_E_BADARG, "replay draws are consumed by the per-call API only");
+  if (!(ess_threshold >= 0.0)) return fail(GSMC_E_BADARG, "ess_threshold must be >= 0");
+  CK(cudaSetDevice(f->device));
+  for (size_t s = 0; s < n_steps; ++s) {
+    CKRC(launch_finalize(f, ess_threshold));
+    CKRC(launch_resample(f, 1, false));
+    CKRC(launch_propagate(f, false, obs + s * n_obs, n_obs, prop, pp, npp, true));
+    f->T += 1;
+  }
+  f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
+  f->last_resample_step = -1;
+  // surface a degenerate-weight error recorded on the device
+  CKRC(fetch_scalars(f));
+  if (f->h_ds->error) {
+    cudaMemsetAsync(&f->ds->error, 0, sizeof(int), f->stream);
+    return fail(GSMC_E_DEGENERATE, "total weight became zero or not finite during the run");
+  }
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_local_count(gsmc_handle f, uint64_t* n_local, uint64_t* first_global) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  if (n_local) *n_local = (uint64_t)f->n;
+  if (first_global) *first_global = (uint64_t)f->first;
+  return GSMC_OK;
+}
+GSMC_API int gsmc_state_dim(gsmc_handle f, int* dim) {
+  if (!f || !dim) return fail(GSMC_E_BADARG, "null argument");
+  *dim = f->D;
+  return GSMC_OK;
+}
+GSMC_API int gsmc_synchronize(gsmc_handle f) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  CK(cudaSetDevice(f->device));
+  CK(cudaStreamSynchronize(f->stream));
+  return GSMC_OK;
+}
+GSMC_API int gsmc_get_stats(gsmc_handle f, gsmc_stats* out) {
+  if (!f || !out) return fail(GSMC_E_BADARG, "null argument");
+  CK(cudaSetDevice(f->device));
+  memset(out, 0, sizeof *out);
+  if (f->ds) CKRC(fetch_scalars(f));
+  harvest_profile(f);
+  if (f->h_ds) {
+    out->last_ess = f->h_ds->ess; out->last_log_total = f->h_ds->log_total; out->log_ml_est = f->h_ds->log_ml_est;
+    out->num_resamples = f->h_ds->n_resamples;
+  }
+  out->num_steps = f->T;
+  out->kernel_launches = f->launches;
+  out->ms_propagate = f->prof_ms[KC_PROPAGATE]; out->n_propagate = f->prof_n[KC_PROPAGATE];
+  out->ms_finalize = f->prof_ms[KC_FINALIZE]; out->n_finalize = f->prof_n[KC_FINALIZE];
+  out->ms_scan = f->prof_ms[KC_SCAN]; out->n_scan = f->prof_n[KC_SCAN];
+  out->ms_spacings = f->prof_ms[KC_SPACINGS]; out->n_spacings = f->prof_n[KC_SPACINGS];
+  out->ms_search = f->prof_ms[KC_SEARCH]; out->n_search = f->prof_n[KC_SEARCH];
+  out->ms_other = f->prof_ms[KC_OTHER]; out->n_other = f->prof_n[KC_OTHER];
+  out->n_propagate_resampled = f->n_prop_resampled;
+  return GSMC_OK;
+}
+GSMC_API int gsmc_set_profiling(gsmc_handle f, int enabled) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  harvest_profile(f);
+  f->profiling = enabled != 0;
+  if (enabled) { for (int c = 0; c < KC_COUNT; ++c) { f->prof_ms[c] = 0; f->prof_n[c] = 0; } }
+  return GSMC_OK;
+}
+GSMC_API int gsmc_timer_start(gsmc_handle f) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  CK(cudaSetDevice(f->device));
+  CK(cudaEventRecord(f->timer_a, f->stream));
+  return GSMC_OK;
+}
+GSMC_API int gsmc_timer_stop(gsmc_handle f, double* elapsed_ms) {
+  if (!f || !elapsed_ms) return fail(GSMC_E_BADARG, "null argument");
+  CK(cudaSetDevice(f->device));
+  CK(cudaEventRecord(f->timer_b, f->stream));
+  CK(cudaEventSynchronize(f->timer_b));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, f->timer_a, f->timer_b));
+  *elapsed_ms = ms;
+  return GSMC_OK;
+}
+
+}  // extern "C"

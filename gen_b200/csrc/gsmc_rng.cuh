@@ -1,0 +1,80 @@
+// gsmc_rng.cuh -- counter-based Philox4x32-10 and the draw layout of the filter.
+//
+// Replaces the reference's global MersenneTwister (`randn()` in
+// src/modeling_library/distributions/normal.jl:96, `rand()` in bernoulli.jl:19 and
+// Distributions.jl's categorical sampler): every draw is a pure function of
+// (seed, global element index, time step, stream), so the result does not depend on
+// the thread/block/GPU that computes it.
+//
+// Layout (shared with the oracle's independent restatement, oracle/gsmc_oracle.c):
+//   call c of (seed, t, stream)    = Philox(ctr = {lo32(c), hi32(c), t, stream}, key = {lo32(seed), hi32(seed)})
+//   word a = out0 | out1<<32, word b = out2 | out3<<32
+//   normals  (stream 0): element e -> call e>>1; Box-Muller u1=((a>>11)+.5)2^-53, u2=(b>>11)2^-53,
+//                        r=sqrt(-2 log u1); e even -> r cos(2 pi u2), e odd -> r sin(2 pi u2)
+//   uniforms (stream 1,3): element e -> call e>>1; (e odd ? b : a)>>11 * 2^-53   in [0,1)
+//   spacings (stream 2): element e -> call e>>1; floor(-log(((w>>11)+.5)2^-53) * 2^32)
+// Particle i's j-th normal at a step that needs nz normals per particle is element i*nz + j.
+#ifndef GSMC_RNG_CUH
+#define GSMC_RNG_CUH
+
+#include <stdint.h>
+#include "gsmc_math.h"
+
+enum { GSMC_STREAM_NORMAL = 0, GSMC_STREAM_UNIFORM = 1, GSMC_STREAM_RESAMPLE = 2, GSMC_STREAM_SAMPLE = 3 };
+
+struct PhiloxOut { uint64_t a, b; };
+
+__host__ __device__ __forceinline__ uint32_t gsmc_mulhi32(uint32_t x, uint32_t y) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(x, y);
+#else
+  return (uint32_t)(((uint64_t)x * y) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ PhiloxOut philox_call(uint64_t seed, uint64_t call, uint32_t t, uint32_t stream) {
+  uint32_t c0 = (uint32_t)call, c1 = (uint32_t)(call >> 32), c2 = t, c3 = stream;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = gsmc_mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = gsmc_mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  PhiloxOut o;
+  o.a = (uint64_t)c0 | ((uint64_t)c1 << 32);
+  o.b = (uint64_t)c2 | ((uint64_t)c3 << 32);
+  return o;
+}
+
+// two standard normals from one call
+__host__ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t call, uint32_t t, double* z0, double* z1) {
+  const PhiloxOut o = philox_call(seed, call, t, GSMC_STREAM_NORMAL);
+  const double u1 = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
+  const double u2 = (double)(o.b >> 11) * 0x1p-53;
+  const double r = sqrt(-2.0 * gm_log(u1));
+  double s, c;
+  gm_sincospi(2.0 * u2, &s, &c);
+  *z0 = r * c;
+  *z1 = r * s;
+}
+
+__host__ __device__ __forceinline__ void uniform_pair(uint64_t seed, uint64_t call, uint32_t t, uint32_t stream, double* u0, double* u1) {
+  const PhiloxOut o = philox_call(seed, call, t, stream);
+  *u0 = (double)(o.a >> 11) * 0x1p-53;
+  *u1 = (double)(o.b >> 11) * 0x1p-53;
+}
+
+__host__ __device__ __forceinline__ uint64_t spacing_from_word(uint64_t w) {
+  const double u = ((double)(w >> 11) + 0.5) * 0x1p-53;
+  return (uint64_t)floor(-gm_log(u) * 4294967296.0);
+}
+__host__ __device__ __forceinline__ void spacing_pair(uint64_t seed, uint64_t call, uint32_t rho, uint64_t* e0, uint64_t* e1) {
+  const PhiloxOut o = philox_call(seed, call, rho, GSMC_STREAM_RESAMPLE);
+  *e0 = spacing_from_word(o.a);
+  *e1 = spacing_from_word(o.b);
+}
+
+#endif

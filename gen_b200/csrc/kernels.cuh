@@ -1,0 +1,709 @@
+// kernels.cuh -- hand-written sm_100a kernels of the SMC / importance-sampling hot path.
+//
+// All kernels are HBM-bound streaming passes over structure-of-arrays particle columns
+// (no tensor cores: nothing here is a dense contraction). One thread owns a PAIR of
+// neighbouring particles so that every global access is a 16-byte vector access, a warp
+// touches 512 contiguous bytes per column, and one Philox call feeds both particles.
+//
+//   propagate_kernel   particle_filter.jl:84-88,103-105 (init), :143-146,165-172 (step) fused with
+//                      the ancestor gather of :202-205 and with the block partials of logsumexp/ESS
+//   finalize_kernel    inference.jl:3-6 + particle_filter.jl:3-12 (normalize_weights, ESS) and the
+//                      `ess < ess_threshold` decision + `log_ml_est += log_total - log N` of :194,201
+//   qsum/cdf kernels   `weights = exp.(lnw)` + the CDF behind Categorical(weights/sum(weights)), :199-200,
+//                      in 64-bit fixed point so the prefix sum is associative (order/shard independent)
+//   spacing kernels    sorted uniforms from exponential spacings (the N iid draws of :200, generated
+//                      already sorted so that search + gather stream through memory)
+//   search kernels     parents[i] (:200) by binary search of the integer CDF
+#ifndef GSMC_KERNELS_CUH
+#define GSMC_KERNELS_CUH
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "gsmc_math.h"
+#include "gsmc_rng.cuh"
+#include "models.cuh"
+
+#define GSMC_BLOCK 256
+#define GSMC_TILE 1024            // particles (or thresholds) per block
+#define GSMC_MAX_RANKS 8
+#define GSMC_ANC_RANK_SHIFT 28    // ancestor word = (owner rank << 28) | local index
+#define GSMC_ANC_INDEX_MASK 0x0fffffffu
+
+struct LseTriple { double m, s1, s2; };   // max, sum exp(lw-m), sum exp(2(lw-m))
+
+// Device-resident scalars: the filter never needs a host round trip to take a decision.
+struct DevScalars {
+  double max_lw, log_total, ess;
+  double log_ml_est;
+  int do_resample;          // decision of the last finalize(decide)
+  int error;                // sticky: 1 = total weight zero / not finite at a resample
+  uint32_t n_resamples;     // resampling events so far
+  uint32_t rho;             // Philox event index of the resample being executed
+  uint64_t cdf_total;       // C_N over all ranks
+  uint64_t spacing_total;   // S_tot = sum of the M+1 spacings
+  uint64_t n_det;           // residual scheme: number of deterministic copies
+  uint64_t n_draws;         // M: number of multinomial draws of this event
+  double resid_scale;       // residual scheme: N * 2^32 / C_N
+  LseTriple triples[GSMC_MAX_RANKS];
+  uint64_t cdf_rank_total[GSMC_MAX_RANKS];      // per-rank integer weight totals (allgathered)
+  uint64_t spacing_rank_total[GSMC_MAX_RANKS];  // per-rank spacing totals (allgathered)
+};
+
+template <typename Real> struct Vec2T;
+template <> struct Vec2T<double> { typedef double2 type; };
+template <> struct Vec2T<float> { typedef float2 type; };
+
+// ------------------------------------------------------------------------------------------------
+// block-level helpers (256 threads = 8 warps)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {
+  return (uint64_t)__shfl_up_sync(0xffffffffu, (unsigned long long)v, d);
+}
+// inclusive scan of one u64 per thread over the block; returns inclusive value, *total = block sum.
+// sm must hold GSMC_BLOCK/32 + 1 u64.
+__device__ __forceinline__ uint64_t block_scan_u64(uint64_t v, uint64_t* sm, uint64_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t y = shfl_up_u64(x, d);
+    if (lane >= d) x += y;
+  }
+  __syncthreads();                  // protect sm reuse across calls
+  if (lane == 31) sm[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < GSMC_BLOCK / 32 ? sm[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < GSMC_BLOCK / 32; d <<= 1) {
+      const uint64_t y = shfl_up_u64(w, d);
+      if (lane >= d) w += y;
+    }
+    if (lane < GSMC_BLOCK / 32) sm[lane] = w;    // inclusive warp totals
+  }
+  __syncthreads();
+  const uint64_t warp_off = warp ? sm[warp - 1] : 0;
+  *total = sm[GSMC_BLOCK / 32 - 1];
+  return x + warp_off;
+}
+__device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t* sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, o);
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  uint64_t t = 0;
+#pragma unroll
+  for (int w = 0; w < GSMC_BLOCK / 32; ++w) t += sm[w];
+  return t;
+}
+
+// 128-bit comparison  a*b > c*d  for u64 operands
+__device__ __forceinline__ bool mul_gt(uint64_t a, uint64_t b, uint64_t chi, uint64_t clo) {
+  const uint64_t hi = __umul64hi(a, b), lo = a * b;
+  return hi > chi || (hi == chi && lo > clo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// propagate: init / step, fused with the ancestor gather and the logsumexp/ESS block partials
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+struct PropArgs {
+  const Real* cur[GSMC_MAX_RANKS];   // previous state column block of every rank (peer-mapped), [D][stride]
+  Real* nxt;                         // new state column block [D][stride]
+  Real* lw;                          // log weights (in place)
+  const uint32_t* anc;               // ancestor words of the pending resample
+  const int* resampled_flag;         // device flag: was a resample decided for this step?
+  LseTriple* partials;               // one per block
+  int64_t n;                         // local particle count
+  int64_t stride;                    // column stride (padded n)
+  uint64_t first_global;             // global index of local particle 0
+  uint64_t seed;
+  uint32_t t;                        // 1-based time index of the step being produced
+  int use_anc;                       // 0: read cur directly; 1: consult *resampled_flag
+  const double* zrep;                // replay normals [n][nz] or NULL
+  const double* urep;                // replay uniforms [n][nu] or NULL
+};
+
+template <class Model, typename Real, bool INIT, int PROP>
+__global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
+  typedef typename Vec2T<Real>::type Real2;
+  constexpr int D = Model::D;
+  constexpr int NZ_MAX = 4, NU_MAX = 1;
+  extern __shared__ double dyn_sm[];
+  __shared__ double red[3 * (GSMC_BLOCK / 32)];
+  if (Model::SMEM_DOUBLES > 0) {
+    Model::template prologue<INIT, PROP>(a, dyn_sm);
+    __syncthreads();
+  }
+  const int nz = Model::nz(INIT, PROP), nu = Model::nu(INIT, PROP);
+  const bool gather = !INIT && g.use_anc && (*g.resampled_flag != 0);
+
+  double lwv[4];        // up to 2 pairs per thread
+  bool val[4];
+  const int64_t tile0 = (int64_t)blockIdx.x * GSMC_TILE;
+#pragma unroll
+  for (int u = 0; u < GSMC_TILE / (2 * GSMC_BLOCK); ++u) {
+    const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK + 2 * threadIdx.x;   // first particle of the pair
+    const bool v0 = i < g.n, v1 = i + 1 < g.n;
+    val[2 * u] = v0; val[2 * u + 1] = v1;
+    lwv[2 * u] = lwv[2 * u + 1] = -gm_inf();
+    if (!v0) continue;
+    double prev0[D], prev1[D], lw0 = 0.0, lw1 = 0.0;
+    if (!INIT) {
+      if (gather) {
+        const uint2 aw = *reinterpret_cast<const uint2*>(g.anc + i);
+        const Real* c0 = g.cur[aw.x >> GSMC_ANC_RANK_SHIFT] + (aw.x & GSMC_ANC_INDEX_MASK);
+        const uint32_t ay = v1 ? aw.y : aw.x;    // the pad slot after an odd tail is not initialised
+        const Real* c1 = g.cur[ay >> GSMC_ANC_RANK_SHIFT] + (ay & GSMC_ANC_INDEX_MASK);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          prev0[d] = (double)__ldg(c0 + d * g.stride);
+          prev1[d] = v1 ? (double)__ldg(c1 + d * g.stride) : 0.0;
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const Real2 x = *reinterpret_cast<const Real2*>(g.cur[0] + d * g.stride + i);
+          prev0[d] = (double)x.x; prev1[d] = (double)x.y;
+        }
+        const Real2 l = *reinterpret_cast<const Real2*>(g.lw + i);
+        lw0 = (double)l.x; lw1 = (double)l.y;
+      }
+    }
+    // draws: elements [(first_global+i)*nz, +2nz) of the step's virtual normal array -> nz Philox calls
+    double zz[2 * NZ_MAX], uu[2 * NU_MAX];
+    if (nz > 0) {
+      if (g.zrep) {
+        for (int j = 0; j < 2 * nz; ++j) zz[j] = (j < nz || v1) ? g.zrep[i * nz + j] : 0.0;
+      } else {
+        const uint64_t c0 = ((g.first_global + (uint64_t)i) * (uint64_t)nz) >> 1;
+#pragma unroll
+        for (int m = 0; m < NZ_MAX; ++m)
+          if (m < nz) normal_pair(g.seed, c0 + m, g.t, &zz[2 * m], &zz[2 * m + 1]);
+      }
+    }
+    if (nu > 0) {
+      if (g.urep) {
+        for (int j = 0; j < 2 * nu; ++j) uu[j] = (j < nu || v1) ? g.urep[i * nu + j] : 0.0;
+      } else {
+        const uint64_t c0 = ((g.first_global + (uint64_t)i) * (uint64_t)nu) >> 1;
+#pragma unroll
+        for (int m = 0; m < NU_MAX; ++m)
+          if (m < nu) uniform_pair(g.seed, c0 + m, g.t, GSMC_STREAM_UNIFORM, &uu[2 * m], &uu[2 * m + 1]);
+      }
+    }
+    double out0[D], out1[D];
+    const double w0 = Model::template particle<INIT, PROP>(a, dyn_sm, prev0, zz, uu, out0);
+    double w1 = 0.0;
+    if (v1) w1 = Model::template particle<INIT, PROP>(a, dyn_sm, prev1, zz + nz, uu + nu, out1);
+    // log_weights[i] = weight (init) / += increment (step); after a resample they restart from 0.
+    const Real r0 = (Real)(INIT ? w0 : lw0 + w0), r1 = (Real)(INIT ? w1 : lw1 + w1);
+    if (v1) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        Real2 o; o.x = (Real)out0[d]; o.y = (Real)out1[d];
+        *reinterpret_cast<Real2*>(g.nxt + d * g.stride + i) = o;
+      }
+      Real2 l; l.x = r0; l.y = r1;
+      *reinterpret_cast<Real2*>(g.lw + i) = l;
+      lwv[2 * u + 1] = (double)r1;
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) g.nxt[d * g.stride + i] = (Real)out0[d];
+      g.lw[i] = r0;
+    }
+    lwv[2 * u] = (double)r0;
+  }
+
+  // block partial of (max, sum exp(lw-max), sum exp(2(lw-max))); NaN log weights poison s1/s2 on purpose.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double m = -gm_inf();
+  bool any_nan = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) if (val[j]) { if (lwv[j] != lwv[j]) any_nan = true; else m = fmax(m, lwv[j]); }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  double bm = red[0];
+#pragma unroll
+  for (int w = 1; w < GSMC_BLOCK / 32; ++w) bm = fmax(bm, red[w]);
+  double s1 = 0.0, s2 = 0.0;
+  if (bm > -gm_inf()) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (val[j]) { const double e = gm_exp(lwv[j] - bm); s1 += e; s2 += e * e; }
+  }
+  if (any_nan) { s1 = gm_nan(); s2 = gm_nan(); }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { red[GSMC_BLOCK / 32 + warp] = s1; red[2 * (GSMC_BLOCK / 32) + warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < GSMC_BLOCK / 32; ++w) { t1 += red[GSMC_BLOCK / 32 + w]; t2 += red[2 * (GSMC_BLOCK / 32) + w]; }
+    LseTriple tr; tr.m = bm; tr.s1 = t1; tr.s2 = t2;
+    g.partials[blockIdx.x] = tr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: combine block partials -> this rank's triple; single-rank runs also decide here.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ LseTriple lse_merge(LseTriple a, LseTriple b) {
+  if (!(b.m > -gm_inf()) && b.s1 == b.s1) return a;
+  if (!(a.m > -gm_inf()) && a.s1 == a.s1) return b;
+  LseTriple r;
+  r.m = fmax(a.m, b.m);
+  const double ea = gm_exp(a.m - r.m), eb = gm_exp(b.m - r.m);
+  r.s1 = a.s1 * ea + b.s1 * eb;
+  r.s2 = a.s2 * (ea * ea) + b.s2 * (eb * eb);
+  return r;
+}
+
+// Combine the per-rank triples in rank order and take the maybe_resample! decision.
+// ess_threshold < 0: statistics only. resampled_flag_out: flag slot of the NEXT step.
+__device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, double ess_threshold,
+                                                   double n_global, int* resampled_flag_out) {
+  LseTriple t = ds->triples[0];
+  for (int r = 1; r < nranks; ++r) t = lse_merge(t, ds->triples[r]);
+  const bool empty = !(t.m > -gm_inf()) && t.s1 == t.s1;
+  const double log_total = empty ? -gm_inf() : t.m + gm_log(t.s1);       // inference.jl:3-6
+  // particle_filter.jl:3-12 literally: lnw = lw - log_total; ess = exp(-logsumexp(2 lnw)) with
+  // logsumexp(2 lnw) = 2 lnw_max + log(sum exp(2 (lw - max))). Written this way (not s1^2/s2) the
+  // all-weights-equal case rounds exactly like the reference formula, where `ess < N` is a tie.
+  const double ess = empty ? gm_nan() : gm_exp(-(2.0 * (t.m - log_total) + gm_log(t.s2)));
+  ds->max_lw = t.m; ds->log_total = log_total; ds->ess = ess;
+  if (ess_threshold < 0.0) return;
+  int doit = ess < ess_threshold;                                        // particle_filter.jl:194
+  if (doit && !(log_total > -gm_inf() && log_total < gm_inf())) { ds->error = 1; doit = 0; }
+  ds->do_resample = doit;
+  if (resampled_flag_out) *resampled_flag_out = doit;
+  if (doit) {
+    ds->log_ml_est += log_total - gm_log(n_global);                      // particle_filter.jl:201
+    ds->rho = ds->n_resamples;
+    ds->n_resamples += 1;
+  }
+}
+
+__global__ void __launch_bounds__(1024) finalize_kernel(const LseTriple* partials, int nblk, DevScalars* ds,
+                                                        int rank, int nranks, double ess_threshold,
+                                                        double n_global, int* resampled_flag_out) {
+  __shared__ LseTriple sm[1024];
+  LseTriple t; t.m = -gm_inf(); t.s1 = 0.0; t.s2 = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 1024) t = lse_merge(t, partials[b]);
+  sm[threadIdx.x] = t;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] = lse_merge(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    ds->triples[rank] = sm[0];
+    if (nranks == 1) combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out);
+  }
+}
+// multi-rank: runs after the allgather of ds->triples
+__global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, double n_global, int* resampled_flag_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// integer weights: q_i = floor(exp(lw_i - max) * 2^k)
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, double mx, double scale, uint64_t q[4]) {
+  // i is a multiple of 4 and the columns are padded to a tile, so the vector loads stay inside the allocation
+  typedef typename Vec2T<Real>::type Real2;
+  const Real2 a = *reinterpret_cast<const Real2*>(lw + i);
+  const Real2 b = *reinterpret_cast<const Real2*>(lw + i + 2);
+  const double l[4] = {(double)a.x, (double)a.y, (double)b.x, (double)b.y};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(gm_exp(l[j] - mx) * scale) : 0;
+}
+
+// phase 1: per-tile sums of q
+template <typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) qsum_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
+                                                          uint64_t* tile_sums, int conditional) {
+  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+  if (conditional && !ds->do_resample) return;
+  const int64_t i = (int64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
+  uint64_t q[4];
+  load_q4(lw, i, n, ds->max_lw, scale, q);
+  const uint64_t t = block_sum_u64(q[0] + q[1] + q[2] + q[3], sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = t;
+}
+
+// phase 2: exclusive scan of up to 2 arrays of tile sums (one block); totals go to out_total[a]
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t* a1, int nt, const DevScalars* ds,
+                                                          uint64_t* total0, uint64_t* total1, int conditional) {
+  __shared__ uint64_t sm[33];
+  if (conditional && !ds->do_resample) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int arr = 0; arr < 2; ++arr) {
+    uint64_t* a = arr ? a1 : a0;
+    if (!a) continue;
+    uint64_t carry = 0;
+    for (int base = 0; base < nt; base += 1024) {
+      const int idx = base + threadIdx.x;
+      const uint64_t v = idx < nt ? a[idx] : 0;
+      uint64_t x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
+      __syncthreads();
+      if (lane == 31) sm[warp] = x;
+      __syncthreads();
+      if (warp == 0) {
+        uint64_t w = sm[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
+        sm[lane] = w;
+      }
+      __syncthreads();
+      const uint64_t incl = x + (warp ? sm[warp - 1] : 0);
+      if (idx < nt) a[idx] = carry + incl - v;      // exclusive
+      carry += sm[31];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { if (arr == 0) *total0 = carry; else *total1 = carry; }
+  }
+}
+
+// phase 3: local inclusive CDF  cdf[i] = tile_prefix[b] + inclusive scan within the tile
+template <typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
+                                                         const uint64_t* tile_prefix, uint64_t* cdf, int conditional) {
+  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+  if (conditional && !ds->do_resample) return;
+  const int64_t i = (int64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
+  uint64_t q[4];
+  load_q4(lw, i, n, ds->max_lw, scale, q);
+  uint64_t tot;
+  const uint64_t incl = block_scan_u64(q[0] + q[1] + q[2] + q[3], sm, &tot);
+  uint64_t c = tile_prefix[blockIdx.x] + incl - (q[0] + q[1] + q[2] + q[3]);
+  ulonglong2 o0, o1;
+  c += q[0]; o0.x = c; c += q[1]; o0.y = c; c += q[2]; o1.x = c; c += q[3]; o1.y = c;
+  *reinterpret_cast<ulonglong2*>(cdf + i) = o0;
+  *reinterpret_cast<ulonglong2*>(cdf + i + 2) = o1;
+}
+
+// residual scheme: e_i = floor(q_i * resid_scale); c_i = e_i >> 32 copies; r_i = e_i & (2^32-1)
+__device__ __forceinline__ void resid_split(uint64_t q, double scale, uint64_t* c, uint64_t* r) {
+  const uint64_t e = (uint64_t)floor((double)q * scale);
+  *c = e >> 32; *r = e & 0xffffffffULL;
+}
+__global__ void resid_scale_kernel(DevScalars* ds, double n_global) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample)
+    ds->resid_scale = (n_global * 4294967296.0) / (double)ds->cdf_total;
+}
+template <typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) resid_sum_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
+                                                               uint64_t* tile_c, uint64_t* tile_r, int conditional) {
+  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+  if (conditional && !ds->do_resample) return;
+  const int64_t i = (int64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
+  uint64_t q[4], cs = 0, rs = 0;
+  load_q4(lw, i, n, ds->max_lw, scale, q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { uint64_t c, r; resid_split(q[j], ds->resid_scale, &c, &r); if (i + j < n) { cs += c; rs += r; } }
+  const uint64_t tc = block_sum_u64(cs, sm);
+  const uint64_t tr = block_sum_u64(rs, sm);
+  if (threadIdx.x == 0) { tile_c[blockIdx.x] = tc; tile_r[blockIdx.x] = tr; }
+}
+template <typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
+                                                               const uint64_t* prefix_c, const uint64_t* prefix_r,
+                                                               uint64_t* cc, uint64_t* cdf, int conditional) {
+  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+  if (conditional && !ds->do_resample) return;
+  const int64_t i = (int64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
+  uint64_t q[4], c[4], r[4], cs = 0, rs = 0;
+  load_q4(lw, i, n, ds->max_lw, scale, q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    resid_split(q[j], ds->resid_scale, &c[j], &r[j]);
+    if (i + j >= n) { c[j] = 0; r[j] = 0; }
+    cs += c[j]; rs += r[j];
+  }
+  uint64_t tot;
+  uint64_t ic = prefix_c[blockIdx.x] + block_scan_u64(cs, sm, &tot) - cs;
+  uint64_t ir = prefix_r[blockIdx.x] + block_scan_u64(rs, sm, &tot) - rs;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { ic += c[j]; ir += r[j]; cc[i + j] = ic; cdf[i + j] = ir; }
+}
+// after the scans: n_det = sum c, n_draws = N - n_det, cdf_total = sum r (single rank)
+__global__ void resid_totals_kernel(DevScalars* ds, const uint64_t* total_c, const uint64_t* total_r, uint64_t n_global) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample) {
+    ds->n_det = *total_c;
+    ds->n_draws = n_global - *total_c;
+    ds->cdf_total = *total_r;
+    ds->cdf_rank_total[0] = *total_r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sorted uniforms from exponential spacings
+// ------------------------------------------------------------------------------------------------
+// spacings of the thresholds k = k0+4*tid .. +3 of tile b (global threshold index), masked to k < m_draws
+__device__ __forceinline__ void tile_spacings(uint64_t seed, uint32_t rho, uint64_t k, uint64_t m_draws, uint64_t e[4]) {
+  spacing_pair(seed, k >> 1, rho, &e[0], &e[1]);
+  spacing_pair(seed, (k >> 1) + 1, rho, &e[2], &e[3]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) if (k + j >= m_draws) e[j] = 0;
+}
+// per-tile sums of the spacings of this rank's thresholds [k_first, k_first + n_tiles*TILE)
+__global__ void __launch_bounds__(GSMC_BLOCK) spacing_sum_kernel(uint64_t seed, uint64_t k_first, const DevScalars* ds,
+                                                                 uint64_t* tile_sums, int conditional) {
+  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+  if (conditional && !ds->do_resample) return;
+  const uint64_t k = k_first + (uint64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
+  uint64_t e[4];
+  tile_spacings(seed, ds->rho, k, ds->n_draws, e);
+  const uint64_t t = block_sum_u64(e[0] + e[1] + e[2] + e[3], sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = t;
+}
+// S_tot = all ranks' spacing totals + the (M+1)-th spacing; runs on every rank after the allgather
+__global__ void spacing_total_kernel(uint64_t seed, DevScalars* ds, int nranks) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample) {
+    uint64_t s = 0;
+    for (int r = 0; r < nranks; ++r) s += ds->spacing_rank_total[r];
+    const uint64_t m = ds->n_draws;
+    uint64_t e0, e1;
+    spacing_pair(seed, m >> 1, ds->rho, &e0, &e1);
+    ds->spacing_total = s + ((m & 1) ? e1 : e0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// search: ancestor of every output slot
+// ------------------------------------------------------------------------------------------------
+struct CdfView {
+  const uint64_t* seg[GSMC_MAX_RANKS];   // local inclusive CDF of every rank (peer-mapped)
+  int64_t n_per;                         // particles per rank
+  int nranks;
+};
+// smallest (rank, j) in [lo, hi] of segment r with (off + seg[j]) * st > (chi,clo); returns hi+1 if none
+__device__ __forceinline__ int64_t seg_upper(const uint64_t* seg, uint64_t off, int64_t lo, int64_t hi, uint64_t st,
+                                             uint64_t chi, uint64_t clo) {
+  int64_t l = lo, h = hi + 1;
+  while (l < h) {
+    const int64_t mid = l + ((h - l) >> 1);
+    if (mul_gt(off + __ldg(seg + mid), st, chi, clo)) h = mid; else l = mid + 1;
+  }
+  return l;
+}
+// ancestor word of the threshold (S_k * C_N = chi:clo) against the global CDF, scaled by st = S_tot
+__device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, uint64_t st, uint64_t chi, uint64_t clo) {
+  uint64_t off = 0;
+  int r = 0;
+  for (; r < v.nranks - 1; ++r) {
+    if (mul_gt(off + ds->cdf_rank_total[r], st, chi, clo)) break;
+    off += ds->cdf_rank_total[r];
+  }
+  int64_t j = seg_upper(v.seg[r], off, 0, v.n_per - 1, st, chi, clo);
+  if (j > v.n_per - 1) j = v.n_per - 1;           // T == C_N can only happen when the last spacing is 0
+  return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
+}
+
+// Sorted mode. Tile b of this rank handles thresholds k_first + b*TILE + [0, TILE) and writes
+// anc[out_first + b*TILE + ...]. T_k = floor(S_k C_N / S_tot);  anc = min{i : C_i > T_k}
+// <=> C_i * S_tot > S_k * C_N (128-bit).
+__global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
+                                                                   const DevScalars* ds, const uint64_t* tile_prefix,
+                                                                   uint32_t* anc, int64_t n_out, int det_offset, int conditional) {
+  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+  __shared__ uint32_t win[2];
+  if (conditional && !ds->do_resample) return;
+  const uint64_t m_draws = ds->n_draws;
+  const uint64_t kt = k_first + (uint64_t)blockIdx.x * GSMC_TILE;
+  if (kt >= m_draws) return;
+  const uint64_t k = kt + 4 * threadIdx.x;
+  uint64_t e[4];
+  tile_spacings(seed, ds->rho, k, m_draws, e);
+  uint64_t tot;
+  const uint64_t tsum = e[0] + e[1] + e[2] + e[3];
+  uint64_t base = 0;
+  for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
+  uint64_t S = base + tile_prefix[blockIdx.x] + block_scan_u64(tsum, sm, &tot) - tsum;
+  const uint64_t st = ds->spacing_total, cn = ds->cdf_total;
+  // window of the tile: ancestors of its first and last threshold
+  uint32_t a[4];
+  bool have[4];
+  uint64_t chi[4], clo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    S += e[j];
+    have[j] = k + j < m_draws;
+    chi[j] = __umul64hi(S, cn); clo[j] = S * cn;
+  }
+  const uint64_t last_k = (kt + GSMC_TILE <= m_draws ? kt + GSMC_TILE : m_draws) - 1;
+  if (threadIdx.x == 0) win[0] = search_global(v, ds, st, chi[0], clo[0]);
+  if (k <= last_k && last_k < k + 4) win[1] = search_global(v, ds, st, chi[last_k - k], clo[last_k - k]);
+  __syncthreads();
+  const uint32_t w0 = win[0], w1 = win[1];
+  if ((w0 >> GSMC_ANC_RANK_SHIFT) == (w1 >> GSMC_ANC_RANK_SHIFT)) {
+    // common case: the whole tile maps into one rank's segment; search only inside the window
+    const int r = (int)(w0 >> GSMC_ANC_RANK_SHIFT);
+    uint64_t off = 0;
+    for (int q = 0; q < r; ++q) off += ds->cdf_rank_total[q];
+    const uint64_t* seg = v.seg[r];
+    int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK);
+    const int64_t hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!have[j]) { a[j] = 0; continue; }
+      if (j == 0) {
+        int64_t pos0 = seg_upper(seg, off, lo, hi, st, chi[0], clo[0]);
+        if (pos0 > hi) pos0 = hi;
+        lo = pos0;
+        a[0] = ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)pos0;
+        continue;
+      }
+      // gallop from the previous ancestor: thresholds are sorted, so ancestors are monotone
+      int64_t step = 1, l = lo, h = lo;
+      while (h <= hi && !mul_gt(off + __ldg(seg + h), st, chi[j], clo[j])) { l = h + 1; h += step; step <<= 1; }
+      if (h > hi) h = hi;
+      int64_t pos = (l <= h) ? seg_upper(seg, off, l, h, st, chi[j], clo[j]) : l;
+      if (pos > hi) pos = hi;
+      lo = pos;
+      a[j] = ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)pos;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, st, chi[j], clo[j]) : 0;
+  }
+  // output slot of threshold k: out_first + (k - k_first) [+ n_det for the residual scheme]
+  const int64_t o = (int64_t)(k - k_first) + (det_offset ? (int64_t)ds->n_det : 0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) if (have[j] && o + j < n_out) anc[o + j] = a[j];
+}
+
+// iid mode (replay / sample_unweighted): T_j = floor(floor(u_j 2^53) * C_N / 2^53)
+__global__ void __launch_bounds__(GSMC_BLOCK) search_iid_kernel(CdfView v, const DevScalars* ds, const double* u, uint64_t seed,
+                                                                uint32_t event, uint32_t stream, int64_t m, int64_t out_offset_det,
+                                                                uint32_t* anc32, int64_t* anc64, int conditional) {
+  if (conditional && !ds->do_resample) return;
+  const int64_t j = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  int64_t count = m;
+  if (out_offset_det) count = (int64_t)ds->n_draws;
+  if (j >= count) return;
+  double uj;
+  if (u) uj = u[j];
+  else { double u0, u1; uniform_pair(seed, (uint64_t)j >> 1, event, stream, &u0, &u1); uj = (j & 1) ? u1 : u0; }
+  const uint64_t t = (uint64_t)floor(uj * 9007199254740992.0);
+  const uint64_t cn = ds->cdf_total;
+  const uint64_t T = (__umul64hi(t, cn) << 11) | ((t * cn) >> 53);
+  // compare C > T via the same 128-bit helper with st = 1
+  uint64_t off = 0;
+  int r = 0;
+  for (; r < v.nranks - 1; ++r) {
+    if (off + ds->cdf_rank_total[r] > T) break;
+    off += ds->cdf_rank_total[r];
+  }
+  int64_t pos = seg_upper(v.seg[r], off, 0, v.n_per - 1, 1, 0, T);
+  if (pos > v.n_per - 1) pos = v.n_per - 1;
+  const int64_t o = j + (out_offset_det ? (int64_t)ds->n_det : 0);
+  if (anc32) anc32[o] = ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)pos;
+  if (anc64) anc64[o] = (int64_t)r * v.n_per + pos;
+}
+
+// residual scheme, deterministic part: slot o < n_det belongs to min{i : Cc_i > o}
+__global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* cc, int64_t n, const DevScalars* ds,
+                                                                uint32_t* anc, int conditional) {
+  if (conditional && !ds->do_resample) return;
+  const int64_t o = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  if (o >= (int64_t)ds->n_det || o >= n) return;
+  int64_t l = 0, h = n;
+  while (l < h) { const int64_t mid = l + ((h - l) >> 1); if (__ldg(cc + mid) > (uint64_t)o) h = mid; else l = mid + 1; }
+  anc[o] = (uint32_t)(l < n ? l : n - 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+// importance.jl:31,50: log_normalized_weights = log_weights .- log_total_weight
+template <typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) normalize_lw_kernel(Real* lw, int64_t n, const DevScalars* ds) {
+  const int64_t i = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  if (i < n) lw[i] = (Real)((double)lw[i] - ds->log_total);
+}
+template <typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) column_to_f64_kernel(const Real* src, double* dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+
+// get_traces view: value of time step t for the particle that is now at position i.
+// Walks the per-step ancestor columns back from the newest (anc_cols[s] was applied when step s
+// was produced from step s-1, if resampled[s]).
+template <typename Real>
+struct HistView {
+  const Real* slab[GSMC_MAX_RANKS];      // [cap][D][stride] per rank
+  const uint32_t* anc_slab[GSMC_MAX_RANKS];
+  const int* resampled;                  // [cap + 2], index = step
+  int64_t stride;
+  int D;
+  int64_t cap;                           // columns in the slabs; step t lives in column (t-1) % cap
+  int64_t flag_mod;                      // resampled[] is indexed by step % flag_mod
+};
+template <typename Real>
+__device__ __forceinline__ uint32_t walk_back(const HistView<Real>& h, uint32_t word, int64_t from_step, int64_t to_step) {
+  // word = (rank, index) position in the ordering that exists after step `from_step` ... down to `to_step`
+  for (int64_t s = from_step; s > to_step; --s) {
+    if (h.resampled[s % h.flag_mod]) {
+      const uint32_t* a = h.anc_slab[word >> GSMC_ANC_RANK_SHIFT] + ((s - 1) % h.cap) * h.stride;
+      word = a[word & GSMC_ANC_INDEX_MASK];
+    }
+  }
+  return word;
+}
+// out[d][i] (column-major, ld = n) of time step t for local particles i in [0, n); newest = newest existing step,
+// pending = 1 if a resample has been decided for step newest+1 but not yet applied
+template <typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) get_state_kernel(HistView<Real> h, int rank, int64_t n, int64_t t, int64_t newest,
+                                                               int pending, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  uint32_t word = ((uint32_t)rank << GSMC_ANC_RANK_SHIFT) | (uint32_t)i;
+  word = walk_back(h, word, newest + (pending ? 1 : 0), t);
+  const Real* col = h.slab[word >> GSMC_ANC_RANK_SHIFT] + ((t - 1) % h.cap) * h.D * h.stride + (word & GSMC_ANC_INDEX_MASK);
+  for (int d = 0; d < h.D; ++d) out[(int64_t)d * n + i] = (double)col[d * h.stride];
+}
+// out[s][t-1][d] for selected local particles idx[s]
+template <typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) trajectories_kernel(HistView<Real> h, int rank, const int64_t* idx, int64_t n_idx,
+                                                                  int64_t newest, int pending, double* out) {
+  const int64_t s = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  if (s >= n_idx) return;
+  uint32_t word = ((uint32_t)rank << GSMC_ANC_RANK_SHIFT) | (uint32_t)idx[s];
+  if (pending && h.resampled[(newest + 1) % h.flag_mod]) {
+    const uint32_t* a = h.anc_slab[rank] + (newest % h.cap) * h.stride;
+    word = a[word & GSMC_ANC_INDEX_MASK];
+  }
+  for (int64_t t = newest; t >= 1; --t) {
+    const Real* col = h.slab[word >> GSMC_ANC_RANK_SHIFT] + ((t - 1) % h.cap) * h.D * h.stride + (word & GSMC_ANC_INDEX_MASK);
+    for (int d = 0; d < h.D; ++d) out[(s * newest + (t - 1)) * h.D + d] = (double)col[d * h.stride];
+    if (t > 1 && h.resampled[t % h.flag_mod]) {
+      const uint32_t* a = h.anc_slab[word >> GSMC_ANC_RANK_SHIFT] + ((t - 1) % h.cap) * h.stride;
+      word = a[word & GSMC_ANC_INDEX_MASK];
+    }
+  }
+}
+// ancestor words -> global int64 indices (state.parents)
+__global__ void __launch_bounds__(GSMC_BLOCK) anc_to_global_kernel(const uint32_t* anc, int64_t n, int64_t n_per, int64_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  if (i < n) out[i] = (int64_t)(anc[i] >> GSMC_ANC_RANK_SHIFT) * n_per + (anc[i] & GSMC_ANC_INDEX_MASK);
+}
+
+#endif

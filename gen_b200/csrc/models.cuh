@@ -1,0 +1,352 @@
+// models.cuh -- the model catalogue as per-particle device functors.
+//
+// Each functor is the collapsed form of what the reference executes per particle per
+// time step through the GFI: Unfold's process_new! (src/modeling_library/unfold/update.jl:54-78)
+// calling generate() on a static-IR kernel (src/static_ir/generate.jl:24-43: constrained choice ->
+// weight += logpdf; unconstrained choice -> random()), and for custom proposals the
+// SimpleExtendingTraceTranslator (src/inference/trace_translators.jl:783-802: weight =
+// model_weight - proposal_score). Arithmetic follows the reference's distribution code
+// literally (normal.jl:56-60,96; categorical.jl:10-12) so that log weights agree bit for bit
+// with the CPU oracle; constants that do not depend on the particle (std*std, log(2 pi var))
+// are hoisted into ModelArgs::k by prepare() with the same IEEE operations.
+#ifndef GSMC_MODELS_CUH
+#define GSMC_MODELS_CUH
+
+#include "gsmc_math.h"
+
+#define GSMC_MAX_INLINE_PARAMS 32
+#define GSMC_MAX_INLINE_OBS 16
+#define GSMC_HMM_MAX_K 16
+
+struct ModelArgs {
+  double p[GSMC_MAX_INLINE_PARAMS];   // model parameters (prefix; all of them live at p_dev too)
+  double obs[GSMC_MAX_INLINE_OBS];    // this step's observations (prefix; obs_dev when longer)
+  double pp[8];                       // proposal parameters
+  double k[24];                       // per-launch derived constants (prepare())
+  const double* p_dev;
+  const double* obs_dev;
+  int n_p, n_obs;
+};
+
+// normal.jl:56-60 with var = std*std hoisted:  -(diff*diff)/(2.0*var) - 0.5*log(2.0*pi*var)
+struct NormC { double two_var, half_log; };
+GM_HD NormC make_normc(double std) {
+  NormC c;
+  const double var = std * std;
+  c.two_var = 2.0 * var;
+  c.half_log = 0.5 * gm_log(2.0 * GM_PI * var);
+  return c;
+}
+GM_HD double logpdf_normal_c(double x, double mu, NormC c) {
+  const double diff = x - mu;
+  return -(diff * diff) / c.two_var - c.half_log;
+}
+GM_HD double logpdf_normal(double x, double mu, double std) { return logpdf_normal_c(x, mu, make_normc(std)); }
+GM_HD double random_normal(double mu, double std, double z) { return mu + std * z; }   // normal.jl:96
+
+// ---------------------------------------------------------------------------------------------
+// LGSSM: x_init ~ normal(m0,s0); x ~ normal(x_prev*a + b, q); y ~ normal(c*x, r)
+// p = [m0, s0, a, b, q, c, r]; obs = [y]
+// k = [mean_sd, obs.two_var, obs.half_log, lat.two_var, lat.half_log, prop_var, prop_sd, q.two_var, q.half_log,
+//      c*c/(r*r) numerator terms ...]
+// ---------------------------------------------------------------------------------------------
+struct LgssmModel {
+  static constexpr int D = 1;
+  static constexpr int SMEM_DOUBLES = 0;
+  GM_HD static int nz(bool init, int) { (void)init; return 1; }
+  GM_HD static int nu(bool, int) { return 0; }
+  static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
+  static void prepare(ModelArgs& a, bool init, int prop) {
+    const double* p = a.p;
+    const double sd = init ? p[1] : p[4], c = p[5], r = p[6];
+    const NormC on = make_normc(r), ln = make_normc(sd);
+    a.k[0] = sd; a.k[1] = on.two_var; a.k[2] = on.half_log; a.k[3] = ln.two_var; a.k[4] = ln.half_log;
+    if (prop == 1) {
+      const double prec = 1.0 / (sd * sd) + (c * c) / (r * r);
+      const double var = 1.0 / prec;
+      const double sdq = sqrt(var);
+      const NormC qn = make_normc(sdq);
+      a.k[5] = var; a.k[6] = sdq; a.k[7] = qn.two_var; a.k[8] = qn.half_log;
+      a.k[9] = sd * sd; a.k[10] = r * r;
+    }
+  }
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static double particle(const ModelArgs& a, const double*, const double* prev,
+                                                    const double* z, const double*, double* out) {
+    const double* p = a.p;
+    const double mean = INIT ? p[0] : prev[0] * p[2] + p[3];
+    const double y = a.obs[0], c = p[5];
+    const NormC on = {a.k[1], a.k[2]};
+    if (PROP == 0) {
+      const double x = random_normal(mean, a.k[0], z[0]);
+      double w = 0.0;
+      w += logpdf_normal_c(y, c * x, on);
+      out[0] = x;
+      return w;
+    } else {
+      const double mu = a.k[5] * (mean / a.k[9] + (c * y) / a.k[10]);
+      const double x = random_normal(mu, a.k[6], z[0]);
+      const NormC qn = {a.k[7], a.k[8]}, ln = {a.k[3], a.k[4]};
+      const double q_score = logpdf_normal_c(x, mu, qn);
+      double mw = 0.0;
+      mw += logpdf_normal_c(x, mean, ln);
+      mw += logpdf_normal_c(y, c * x, on);
+      out[0] = x;
+      return mw - q_score;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Stochastic volatility: h_init ~ normal(mu, sigma/sqrt(1-phi*phi)); h ~ normal(mu + phi*(h_prev-mu), sigma);
+// y ~ normal(0, exp(h/2)).  p = [mu, phi, sigma]; obs = [y]
+// ---------------------------------------------------------------------------------------------
+struct SvModel {
+  static constexpr int D = 1;
+  static constexpr int SMEM_DOUBLES = 0;
+  GM_HD static int nz(bool, int) { return 1; }
+  GM_HD static int nu(bool, int) { return 0; }
+  static bool has_proposal(int prop) { return prop == 0; }
+  static void prepare(ModelArgs& a, bool init, int) {
+    const double phi = a.p[1], sigma = a.p[2];
+    a.k[0] = init ? sigma / sqrt(1.0 - phi * phi) : sigma;
+  }
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static double particle(const ModelArgs& a, const double*, const double* prev,
+                                                    const double* z, const double*, double* out) {
+    const double mu = a.p[0], phi = a.p[1];
+    const double mean = INIT ? mu : mu + phi * (prev[0] - mu);
+    const double h = random_normal(mean, a.k[0], z[0]);
+    double w = 0.0;
+    w += logpdf_normal(a.obs[0], 0.0, gm_exp(h / 2.0));
+    out[0] = h;
+    return w;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Bearings-only tracking, state (x, vx, y, vy).  p = [m[4], sd[4], sigma_w, sigma_theta]; obs=[bearing]
+// ---------------------------------------------------------------------------------------------
+struct BearingsModel {
+  static constexpr int D = 4;
+  static constexpr int SMEM_DOUBLES = 0;
+  GM_HD static int nz(bool init, int) { return init ? 4 : 2; }
+  GM_HD static int nu(bool, int) { return 0; }
+  static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
+  static void prepare(ModelArgs& a, bool, int) {
+    const double sw = a.p[8], st = a.p[9];
+    const NormC tn = make_normc(st), wn = make_normc(sw);
+    a.k[0] = tn.two_var; a.k[1] = tn.half_log; a.k[2] = wn.two_var; a.k[3] = wn.half_log;
+    a.k[4] = sw * sw; a.k[5] = st * st;
+  }
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static double particle(const ModelArgs& a, const double*, const double* sp,
+                                                    const double* z, const double*, double* out) {
+    const double* p = a.p;
+    const NormC tn = {a.k[0], a.k[1]};
+    const double obs = a.obs[0];
+    if (INIT) {
+      const double x = random_normal(p[0], p[4], z[0]);
+      const double vx = random_normal(p[1], p[5], z[1]);
+      const double y = random_normal(p[2], p[6], z[2]);
+      const double vy = random_normal(p[3], p[7], z[3]);
+      double w = 0.0;
+      w += logpdf_normal_c(obs, gm_atan2(y, x), tn);
+      out[0] = x; out[1] = vx; out[2] = y; out[3] = vy;
+      return w;
+    }
+    const double sw = p[8];
+    double wx, wy, q_score = 0.0, mw = 0.0;
+    if (PROP == 0) {
+      wx = random_normal(0.0, sw, z[0]);
+      wy = random_normal(0.0, sw, z[1]);
+    } else {
+      const double sw2 = a.k[4], st2 = a.k[5];
+      const double xb = sp[0] + sp[1], yb = sp[2] + sp[3];
+      const double rho2 = xb * xb + yb * yb;
+      const double nu = obs - gm_atan2(yb, xb);
+      const double hx = -yb / rho2, hy = xb / rho2;
+      const double S = 0.25 * sw2 * (hx * hx + hy * hy) + st2;
+      const double kx = 0.5 * sw2 * hx / S, ky = 0.5 * sw2 * hy / S;
+      const double mx = kx * nu, my = ky * nu;
+      const double sx = sqrt(sw2 * (1.0 - 0.5 * kx * hx)), sy = sqrt(sw2 * (1.0 - 0.5 * ky * hy));
+      wx = random_normal(mx, sx, z[0]);
+      wy = random_normal(my, sy, z[1]);
+      q_score += logpdf_normal(wx, mx, sx);
+      q_score += logpdf_normal(wy, my, sy);
+      const NormC wn = {a.k[2], a.k[3]};
+      mw += logpdf_normal_c(wx, 0.0, wn);
+      mw += logpdf_normal_c(wy, 0.0, wn);
+    }
+    const double x = sp[0] + sp[1] + 0.5 * wx;
+    const double vx = sp[1] + wx;
+    const double y = sp[2] + sp[3] + 0.5 * wy;
+    const double vy = sp[3] + wy;
+    mw += logpdf_normal_c(obs, gm_atan2(y, x), tn);
+    out[0] = x; out[1] = vx; out[2] = y; out[3] = vy;
+    return mw - q_score;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// HMM (test/inference/particle_filter.jl:52-78; proposals :104-127).
+// p = [K, V, prior[K], trans[K][K] (row z_prev), emis[K][V] (row z)]; obs = [x] (1-based); latent stored 1-based.
+// Shared-memory tables built per block by prologue():
+//   cum[zp][k]  running sums of the sampling distribution (prior / transition row, or the
+//               normalised locally-optimal proposal), exactly the `cp` sequence of the linear scan
+//   wt[zp][z]   the weight increment for choosing z from zp
+// ---------------------------------------------------------------------------------------------
+struct HmmModel {
+  static constexpr int D = 1;
+  static constexpr int SMEM_DOUBLES = 2 * GSMC_HMM_MAX_K * GSMC_HMM_MAX_K;
+  GM_HD static int nz(bool, int) { return 0; }
+  GM_HD static int nu(bool, int) { return 1; }
+  static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
+  static void prepare(ModelArgs&, bool, int) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static void prologue(const ModelArgs& a, double* sm) {
+    const double* p = a.p_dev;
+    const int K = (int)p[0], V = (int)p[1];
+    const double* prior = p + 2;
+    const double* trans = prior + K;
+    const double* emis = trans + K * K;
+    const int x = (int)a.obs[0];
+    double* cum = sm;
+    double* wt = sm + GSMC_HMM_MAX_K * GSMC_HMM_MAX_K;
+    const int rows = INIT ? 1 : K;
+    for (int zp = threadIdx.x; zp < rows; zp += blockDim.x) {
+      const double* pz = INIT ? prior : trans + zp * K;
+      double dist[GSMC_HMM_MAX_K];
+      if (PROP == 0) {
+        for (int k = 0; k < K; ++k) dist[k] = pz[k];
+      } else {
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) dist[k] = pz[k] * emis[k * V + (x - 1)];
+        for (int k = 0; k < K; ++k) s += dist[k];
+        for (int k = 0; k < K; ++k) dist[k] = dist[k] / s;
+      }
+      double cp = dist[0];
+      cum[zp * GSMC_HMM_MAX_K] = cp;
+      for (int k = 1; k < K; ++k) { cp += dist[k]; cum[zp * GSMC_HMM_MAX_K + k] = cp; }
+      for (int z = 0; z < K; ++z) {
+        const bool x_ok = (x > 0 && x <= V);
+        const double le = x_ok ? gm_log(emis[z * V + (x - 1)]) : -gm_inf();
+        double w;
+        if (PROP == 0) {
+          w = 0.0;
+          w += le;
+        } else {
+          const double q_score = gm_log(dist[z]);
+          double mw = 0.0;
+          mw += gm_log(pz[z]);
+          mw += le;
+          w = mw - q_score;
+        }
+        wt[zp * GSMC_HMM_MAX_K + z] = w;
+      }
+    }
+  }
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static double particle(const ModelArgs& a, const double* sm, const double* prev,
+                                                    const double*, const double* u, double* out) {
+    const int K = (int)a.p[0];
+    const int zp = INIT ? 0 : (int)prev[0] - 1;
+    const double* cum = sm + zp * GSMC_HMM_MAX_K;
+    // Distributions.jl linear scan: cp = p[1]; i = 1; while cp <= draw && i < n: cp += p[i += 1]
+    int i = 1;
+    while (cum[i - 1] <= u[0] && i < K) ++i;
+    out[0] = (double)i;
+    return sm[GSMC_HMM_MAX_K * GSMC_HMM_MAX_K + zp * GSMC_HMM_MAX_K + (i - 1)];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Importance-sampling families (run through the init kernel: one "time step", no resampling).
+// regression: p = [n, sd_s, sd_i, sd_n, xs[n]]; obs = ys[n]; pp = [mu_s, sd_s', mu_i, sd_i']
+// ---------------------------------------------------------------------------------------------
+struct RegressionModel {
+  static constexpr int D = 2;
+  static constexpr int SMEM_DOUBLES = 0;
+  GM_HD static int nz(bool, int) { return 2; }
+  GM_HD static int nu(bool, int) { return 0; }
+  static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
+  static void prepare(ModelArgs& a, bool, int prop) {
+    const NormC nn = make_normc(a.p[3]);
+    a.k[0] = nn.two_var; a.k[1] = nn.half_log;
+    if (prop == 1) {
+      const NormC a0 = make_normc(a.pp[1]), a1 = make_normc(a.pp[3]), b0 = make_normc(a.p[1]), b1 = make_normc(a.p[2]);
+      a.k[2] = a0.two_var; a.k[3] = a0.half_log; a.k[4] = a1.two_var; a.k[5] = a1.half_log;
+      a.k[6] = b0.two_var; a.k[7] = b0.half_log; a.k[8] = b1.two_var; a.k[9] = b1.half_log;
+    }
+  }
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static double particle(const ModelArgs& a, const double*, const double*,
+                                                    const double* z, const double*, double* out) {
+    const int n = (int)a.p[0];
+    const double* xs = a.p_dev + 4;
+    const double* ys = a.obs_dev;
+    double slope, intercept, pw = 0.0, mw = 0.0;
+    if (PROP == 0) {
+      slope = random_normal(0.0, a.p[1], z[0]);
+      intercept = random_normal(0.0, a.p[2], z[1]);
+    } else {
+      slope = random_normal(a.pp[0], a.pp[1], z[0]);
+      intercept = random_normal(a.pp[2], a.pp[3], z[1]);
+      const NormC a0 = {a.k[2], a.k[3]}, a1 = {a.k[4], a.k[5]}, b0 = {a.k[6], a.k[7]}, b1 = {a.k[8], a.k[9]};
+      pw += logpdf_normal_c(slope, a.pp[0], a0);
+      pw += logpdf_normal_c(intercept, a.pp[2], a1);
+      mw += logpdf_normal_c(slope, 0.0, b0);
+      mw += logpdf_normal_c(intercept, 0.0, b1);
+    }
+    const NormC nn = {a.k[0], a.k[1]};
+    for (int i = 0; i < n; ++i) mw += logpdf_normal_c(__ldg(ys + i), slope * __ldg(xs + i) + intercept, nn);
+    out[0] = slope; out[1] = intercept;
+    return mw - pw;
+  }
+};
+
+// normal-normal: x ~ normal(mu0, sd0); y ~ normal(x, sd_y). p = [mu0, sd0, sd_y]; obs = [y]; pp = [mu_q, sd_q]
+struct NormalNormalModel {
+  static constexpr int D = 1;
+  static constexpr int SMEM_DOUBLES = 0;
+  GM_HD static int nz(bool, int) { return 1; }
+  GM_HD static int nu(bool, int) { return 0; }
+  static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
+  static void prepare(ModelArgs& a, bool, int prop) {
+    const NormC yn = make_normc(a.p[2]);
+    a.k[0] = yn.two_var; a.k[1] = yn.half_log;
+    if (prop == 1) {
+      const NormC qn = make_normc(a.pp[1]), xn = make_normc(a.p[1]);
+      a.k[2] = qn.two_var; a.k[3] = qn.half_log; a.k[4] = xn.two_var; a.k[5] = xn.half_log;
+    }
+  }
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static double particle(const ModelArgs& a, const double*, const double*,
+                                                    const double* z, const double*, double* out) {
+    double x, pw = 0.0, mw = 0.0;
+    if (PROP == 0) {
+      x = random_normal(a.p[0], a.p[1], z[0]);
+    } else {
+      x = random_normal(a.pp[0], a.pp[1], z[0]);
+      const NormC qn = {a.k[2], a.k[3]}, xn = {a.k[4], a.k[5]};
+      pw += logpdf_normal_c(x, a.pp[0], qn);
+      mw += logpdf_normal_c(x, a.p[0], xn);
+    }
+    const NormC yn = {a.k[0], a.k[1]};
+    mw += logpdf_normal_c(a.obs[0], x, yn);
+    out[0] = x;
+    return mw - pw;
+  }
+};
+
+#endif

@@ -1,0 +1,377 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs. Integer/index results (ancestors) and, because device and oracle share IEEE-only
+transcendentals, log weights and states are compared BIT-EXACT in fp64; reductions (log_total, ESS,
+log-ML) to 1e-12 relative (BASELINE.json asks for 1e-5); fp32 storage to 1e-3."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import closed_forms as cf
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LG = [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0]
+SVP = [-1.0, 0.97, 0.2]
+
+
+def make_model(g, fam):
+    if fam == O.LGSSM:
+        return g.LinearGaussianSSM(*LG), np.array(LG), cf.simulate_lgssm(40, LG, 3)
+    if fam == O.SV:
+        return g.StochasticVolatility(*SVP), np.array(SVP), cf.simulate_sv(40, SVP, 4)
+    if fam == O.BEARINGS:
+        return g.BearingsOnly(), cf.BEARINGS_PARAMS, cf.simulate_bearings(40)
+    if fam == O.HMM:
+        obs = np.array([1, 1, 2, 3, 2, 1, 3, 3, 1, 2] * 4, dtype=np.float64)
+        return g.HMM(cf.HMM_PRIOR, cf.HMM_EMISSION, cf.HMM_TRANSITION), cf.hmm_params(), obs
+    raise ValueError(fam)
+
+
+def same_bits(a, b):
+    a, b = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(np.all(a.view(np.uint64) == b.view(np.uint64)))
+
+
+CASES = [(O.LGSSM, 0), (O.LGSSM, 1), (O.SV, 0), (O.BEARINGS, 0), (O.BEARINGS, 1), (O.HMM, 0), (O.HMM, 1)]
+
+
+@pytest.mark.parametrize("fam,prop", CASES)
+@pytest.mark.parametrize("N", [1, 2, 1023, 20011])
+def test_init_and_steps_bit_exact(gpu, orc, fam, prop, N):
+    """initialize_particle_filter + particle_filter_step! without resampling (Philox draws)."""
+    g = gpu
+    model, params, ys = make_model(g, fam)
+    st = g.ParticleFilterState(model, N, seed=11)
+    pf = orc.particle_filter(fam, params, N, seed=11)
+    proposal = model.custom_proposal() if prop else None
+    st.init([ys[0]], proposal)
+    pf.init([ys[0]], proposal=prop)
+    for t in range(1, 5):
+        assert same_bits(st.log_weights(), pf.log_weights()), "log weights differ at step %d" % t
+        assert same_bits(st.state(), pf.state()), "state differs at step %d" % t
+        st.step([ys[t]], proposal)
+        pf.step([ys[t]], proposal=prop)
+    assert same_bits(st.log_weights(), pf.log_weights())
+    assert same_bits(st.state(), pf.state())
+    assert st.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-12, abs=1e-12)
+
+
+@pytest.mark.parametrize("fam,prop", [(O.LGSSM, 0), (O.HMM, 1), (O.BEARINGS, 1)])
+def test_replay_mode_uses_exported_draws(gpu, orc, fam, prop):
+    """Fed the oracle's exported draws (replay mode), the GPU reproduces the oracle bit for bit."""
+    g = gpu
+    N = 5000
+    model, params, ys = make_model(g, fam)
+    st = g.ParticleFilterState(model, N, seed=999)       # seed must not matter in replay mode
+    pf = orc.particle_filter(fam, params, N, seed=5)
+    proposal = model.custom_proposal() if prop else None
+    rng = np.random.default_rng(0)
+    for t in range(4):
+        nz = orc.L.orc_pf_num_normals(pf.h, prop, int(t == 0))
+        nu = orc.L.orc_pf_num_uniforms(pf.h, prop, int(t == 0))
+        z = rng.standard_normal(N * nz) if nz else None
+        u = rng.random(N * nu) if nu else None
+        st.set_replay(z, u)
+        if t == 0:
+            st.init([ys[0]], proposal)
+            pf.init([ys[0]], proposal=prop, z_replay=z, u_replay=u)
+        else:
+            st.step([ys[t]], proposal)
+            pf.step([ys[t]], proposal=prop, z_replay=z, u_replay=u)
+        assert same_bits(st.log_weights(), pf.log_weights())
+        assert same_bits(st.state(), pf.state())
+
+
+@pytest.mark.parametrize("N", [7, 1024, 4097, 65536])
+def test_multinomial_resample_sorted_ancestors_bit_exact(gpu, orc, N):
+    g = gpu
+    model, params, ys = make_model(g, O.LGSSM)
+    st = g.ParticleFilterState(model, N, seed=3)
+    pf = orc.particle_filter(O.LGSSM, params, N, seed=3)
+    st.init([ys[0]])
+    pf.init([ys[0]])
+    st.step([ys[1]])
+    pf.step([ys[1]])
+    did_g = st.maybe_resample(N)            # ess < N always holds once weights differ
+    did_o = pf.maybe_resample(N)
+    assert did_g == did_o == (N > 1)
+    if N == 1:
+        return
+    assert st.last_ess == pytest.approx(pf.last_ess, rel=1e-12)
+    anc_g, anc_o = st.ancestors(), pf.parents()
+    assert np.array_equal(anc_g, anc_o)
+    assert np.all(np.diff(anc_g) >= 0), "sorted-uniform resampling must give monotone ancestors"
+    assert np.array_equal(st.log_weights(), np.zeros(N))
+    assert same_bits(st.state(), pf.state())                     # gather through ancestors
+    assert st.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    st.step([ys[2]])
+    pf.step([ys[2]])
+    assert same_bits(st.log_weights(), pf.log_weights())
+    assert same_bits(st.state(), pf.state())
+
+
+@pytest.mark.parametrize("scheme", ["multinomial", "residual"])
+def test_resample_with_exported_uniforms(gpu, orc, scheme):
+    """north_star protocol: fed exported iid uniforms (one per output slot), ancestor indices match bit-exact."""
+    g = gpu
+    N = 30000
+    model, params, ys = make_model(g, O.LGSSM)
+    st = g.ParticleFilterState(model, N, seed=8, resample=scheme)
+    pf = orc.particle_filter(O.LGSSM, params, N, seed=8)
+    st.init([ys[0]])
+    pf.init([ys[0]])
+    u = np.random.default_rng(5).random(N)
+    st.set_replay(None, u)
+    assert st.maybe_resample(N) is True
+    assert pf.maybe_resample(N, scheme=O.RESIDUAL if scheme == "residual" else O.MULTINOMIAL, u_replay=u) is True
+    assert np.array_equal(st.ancestors(), pf.parents())
+    assert same_bits(st.state(), pf.state())
+
+
+@pytest.mark.parametrize("fam,prop,scheme", [(O.LGSSM, 0, "multinomial"), (O.LGSSM, 1, "multinomial"), (O.SV, 0, "residual"),
+                                             (O.BEARINGS, 1, "multinomial"), (O.HMM, 0, "multinomial"), (O.HMM, 1, "residual")])
+def test_full_filter_loop_matches_oracle(gpu, orc, fam, prop, scheme):
+    """The canonical loop (test/inference/particle_filter.jl:130-137): maybe_resample! then step."""
+    g = gpu
+    N, T = 6000, 25
+    model, params, ys = make_model(g, fam)
+    st = g.ParticleFilterState(model, N, seed=21, resample=scheme, keep_history=True, history_capacity=T)
+    pf = orc.particle_filter(fam, params, N, seed=21, keep_history=True)
+    proposal = model.custom_proposal() if prop else None
+    sch = O.RESIDUAL if scheme == "residual" else O.MULTINOMIAL
+    st.init([ys[0]], proposal)
+    pf.init([ys[0]], proposal=prop)
+    n_res = 0
+    for t in range(1, T):
+        dg = st.maybe_resample(N * 0.8)
+        do = pf.maybe_resample(N * 0.8, scheme=sch)
+        assert dg == do, "resample decision differs at t=%d (ess %r vs %r)" % (t, st.last_ess, pf.last_ess)
+        assert st.last_ess == pytest.approx(pf.last_ess, rel=1e-11)
+        if dg:
+            n_res += 1
+            assert np.array_equal(st.ancestors(), pf.parents()), "ancestors differ at t=%d" % t
+        st.step([ys[t]], proposal)
+        pf.step([ys[t]], proposal=prop)
+        assert same_bits(st.log_weights(), pf.log_weights()), "log weights differ at t=%d" % t
+    assert n_res >= 3
+    assert same_bits(st.state(), pf.state())
+    assert st.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    assert st.stats()["num_resamples"] == n_res
+    # get_traces semantics: every earlier time step, in the current particle order (ancestor walk vs
+    # the oracle's physically permuted history)
+    for t in (1, 2, T // 2, T - 1, T):
+        assert same_bits(st.state(t), pf.history(t)), "history differs at t=%d" % t
+    idx = np.array([0, 1, N // 2, N - 1])
+    tr = st.trajectories(idx)
+    for t in range(1, T + 1):
+        assert same_bits(tr[:, t - 1, :].T, pf.history(t)[:, idx])
+
+
+def test_run_steps_equals_per_call_loop(gpu, orc):
+    """gsmc_run_steps enqueues the same loop without host round trips."""
+    g = gpu
+    N, T = 50000, 30
+    model, params, ys = make_model(g, O.LGSSM)
+    a = g.ParticleFilterState(model, N, seed=2, keep_history=False)
+    b = g.ParticleFilterState(model, N, seed=2, keep_history=False)
+    pf = orc.particle_filter(O.LGSSM, params, N, seed=2)
+    a.init([ys[0]])
+    b.init([ys[0]])
+    pf.init([ys[0]])
+    a.run_steps(ys[1:T], N / 2)
+    for t in range(1, T):
+        b.maybe_resample(N / 2)
+        b.step([ys[t]])
+        pf.maybe_resample(N / 2)
+        pf.step([ys[t]])
+    assert a.log_ml_estimate() == b.log_ml_estimate()
+    assert same_bits(a.log_weights(), b.log_weights())
+    assert same_bits(a.state(), pf.state())
+    assert a.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    assert a.stats()["num_resamples"] == b.stats()["num_resamples"] > 0
+
+
+@pytest.mark.parametrize("prop", [0, 1])
+def test_hmm_reference_test_case(gpu, orc, prop):
+    """test/inference/particle_filter.jl:96-168 through the mirrored API: N=10^4, ess_threshold=N,
+    both proposals, log-ML within atol 0.01 of the forward algorithm."""
+    g = gpu
+    model = g.HMM(cf.HMM_PRIOR, cf.HMM_EMISSION, cf.HMM_TRANSITION)
+    obs_x = cf.HMM_OBS
+    N = 10000
+    if prop:
+        state = g.initialize_particle_filter(model, (1,), g.choicemap(("x_init", obs_x[0])), model.custom_proposal(), (obs_x[0],), N, seed=0)
+    else:
+        state = g.initialize_particle_filter(model, (1,), g.choicemap(("x_init", obs_x[0])), N, seed=0)
+    pf = orc.particle_filter(O.HMM, cf.hmm_params(), N, seed=0)
+    pf.init([obs_x[0]], proposal=prop)
+    argdiffs = (g.UnknownChange(),)
+    for T in range(2, len(obs_x) + 1):
+        dg = g.maybe_resample_b(state, ess_threshold=N)
+        do = pf.maybe_resample(N)
+        assert dg == do
+        observations = g.choicemap((("chain", T - 1, "x"), obs_x[T - 1]))
+        if prop:
+            g.particle_filter_step_b(state, (T,), argdiffs, observations, model.custom_proposal(), (T, obs_x[T - 1]))
+        else:
+            g.particle_filter_step_b(state, (T,), argdiffs, observations)
+        pf.step([obs_x[T - 1]], proposal=prop)
+    expected = math.log(cf.hmm_forward_alg(cf.HMM_PRIOR, cf.HMM_EMISSION, cf.HMM_TRANSITION, obs_x))
+    assert expected == pytest.approx(cf.HMM_LOG_ML, abs=1e-12)
+    actual = g.log_ml_estimate(state)
+    assert abs(actual - expected) < 0.01                      # the reference's own bar
+    assert actual == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    tr = g.get_traces(state)[0]
+    ch = tr.get_choices()
+    assert ch["x_init"] == obs_x[0] and ch[("chain", 3, "x")] == obs_x[3]
+    assert ch["z_init"] in (1, 2, 3) and ch[("chain", 2, "z")] in (1, 2, 3)
+    assert int(pf.history(1)[0, 0]) == ch["z_init"]
+
+
+def test_importance_sampling_matches_oracle(gpu, orc):
+    g = gpu
+    n = 200000
+    xs, ys = cf.QUICKSTART_XS, cf.QUICKSTART_YS
+    model = g.LinearRegression()
+    obs = g.choicemap(*[("y-%d" % (i + 1), y) for i, y in enumerate(ys)])
+    for prop in (None, model.custom_proposal(-2.0, 0.5, 10.0, 2.0)):
+        traces, lnw, lml = g.importance_sampling(model, (xs,), obs, *((prop, ()) if prop else ()), n, seed=4)
+        lat, lnw_o, lml_o = orc.importance_sampling(O.REGRESSION, cf.regression_params(), ys, n, seed=4,
+                                                   proposal=1 if prop else 0, prop_params=prop.params if prop else None)
+        assert lml == pytest.approx(lml_o, rel=1e-12)
+        assert np.allclose(lnw, lnw_o, rtol=0, atol=1e-9)
+        assert abs(orc.logsumexp(lnw)) < 1e-10                 # test/inference/importance_sampling.jl:21
+        assert same_bits(traces._state.state(), lat)
+        assert len(traces) == n
+    assert lml == pytest.approx(cf.QUICKSTART_LOG_ML, abs=0.05)   # good proposal: close to the closed form
+    assert traces[0]["y-3"] == ys[2]
+
+
+def test_importance_sampling_reference_test(gpu, orc):
+    """test/inference/importance_sampling.jl:1-34 (n = 4)."""
+    g = gpu
+    model = g.NormalNormal(0.0, 1.0, 1.0)
+    y = 2.0
+    observations = g.choicemap()
+    observations.set_value("y", y)
+    n = 4
+    traces, lw, lml = g.importance_sampling(model, (), observations, n)
+    assert len(traces) == n and len(lw) == n
+    assert abs(orc.logsumexp(lw)) < 1e-14
+    assert not math.isnan(lml)
+    for tr in traces:
+        assert tr.get_choices()["y"] == y
+    traces, lw, lml = g.importance_sampling(model, (), observations, model.custom_proposal(0.0, 2.0), (), n)
+    assert len(traces) == n and len(lw) == n
+    assert abs(orc.logsumexp(lw)) < 1e-14
+    assert not math.isnan(lml)
+    lat, lnw_o, lml_o = orc.importance_sampling(O.NORMAL_NORMAL, [0, 1, 1], [y], n, seed=0, proposal=1, prop_params=[0, 2])
+    assert lml == pytest.approx(lml_o, rel=1e-13)
+    assert same_bits(traces._state.state(), lat)
+
+
+def test_importance_sampling_state_space_model(gpu, orc):
+    """importance_sampling on an Unfold model = generate() over all T steps, no resampling."""
+    g = gpu
+    model, params, ys = make_model(g, O.LGSSM)
+    T, n = 6, 40000
+    obs = g.choicemap(("y_init", ys[0]), *[(("chain", t, "y"), ys[t]) for t in range(1, T)])
+    traces, lnw, lml = g.importance_sampling(model, (T,), obs, n, seed=9)
+    pf = orc.particle_filter(O.LGSSM, params, n, seed=9)
+    pf.init([ys[0]])
+    for t in range(1, T):
+        pf.step([ys[t]])
+    assert lml == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    assert abs(orc.logsumexp(lnw)) < 1e-10
+    assert lml == pytest.approx(cf.kalman_log_ml(ys[:T], *LG), abs=0.3)
+
+
+def test_sample_unweighted_traces(gpu, orc):
+    g = gpu
+    N = 20000
+    model, params, ys = make_model(g, O.LGSSM)
+    st = g.ParticleFilterState(model, N, seed=6)
+    pf = orc.particle_filter(O.LGSSM, params, N, seed=6)
+    st.init([ys[0]])
+    pf.init([ys[0]])
+    st.step([ys[1]])
+    pf.step([ys[1]])
+    for _ in range(2):                                   # two calls use two different draw events
+        assert np.array_equal(st.sample_unweighted(777), pf.sample_unweighted(777))
+    u = np.random.default_rng(1).random(50)
+    st.set_replay(None, u)
+    assert np.array_equal(st.sample_unweighted(50), pf.sample_unweighted(50, u_replay=u))
+    trs = g.sample_unweighted_traces(st, 5)
+    assert len(trs) == 5 and trs[0].get_choices()["y_init"] == ys[0]
+
+
+def test_f32_storage_within_tolerance(gpu, orc):
+    """dtype f32 (storage) against the fp64 oracle: BASELINE.json's 1e-3 bar."""
+    g = gpu
+    N, T = 1 << 16, 20
+    model, params, ys = make_model(g, O.LGSSM)
+    st = g.ParticleFilterState(model, N, seed=1, dtype="f32")
+    pf = orc.particle_filter(O.LGSSM, params, N, seed=1)
+    st.init([ys[0]])
+    pf.init([ys[0]])
+    assert np.allclose(st.log_weights(), pf.log_weights(), rtol=1e-3, atol=1e-5)
+    for t in range(1, T):
+        st.maybe_resample(N / 2)
+        pf.maybe_resample(N / 2)
+        st.step([ys[t]])
+        pf.step([ys[t]])
+    assert st.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-3)
+
+
+def test_error_behaviour(gpu):
+    """Where the reference calls error(...), the C ABI returns a negative code and the wrapper raises."""
+    g = gpu
+    model = g.LinearGaussianSSM()
+    st = g.ParticleFilterState(model, 100)
+    with pytest.raises(g.GsmcError):
+        st.step([0.0])                                        # step before init
+    with pytest.raises(g.GsmcError):
+        st.log_ml_estimate()
+    st.init([0.1])
+    with pytest.raises(g.GsmcError):
+        st.init([0.1])                                        # already initialised
+    with pytest.raises(g.GsmcError):
+        st.step([0.1, 0.2])                                   # wrong number of observations
+    with pytest.raises(g.GsmcError):
+        g.particle_filter_step_b(st, (5,), (g.UnknownChange(),), g.choicemap((("chain", 1, "y"), 0.0)))   # not an extension by one
+    with pytest.raises(g.GsmcError):
+        g.particle_filter_step_b(st, (2,), (g.UnknownChange(),), g.choicemap((("chain", 7, "y"), 0.0)))   # unvisited constraint
+    sv = g.StochasticVolatility()
+    with pytest.raises(g.GsmcError):
+        g.ParticleFilterState(sv, 10).init([0.0], sv.custom_proposal())          # not in the catalogue
+    # degenerate weights: an observation so far away that every weight underflows to -inf never happens for
+    # a Gaussian likelihood in log space, so force it with NaN
+    st2 = g.ParticleFilterState(model, 64)
+    st2.init([float("nan")])
+    assert math.isnan(st2.log_ml_estimate())
+    assert st2.maybe_resample(32) is False                    # NaN ess: no resample, like the reference
+
+
+def test_large_n_properties(gpu):
+    """Size-independent properties at a size the oracle is too slow for: offspring counts sum to N,
+    ancestors sorted, log-ML close to the Kalman filter, run is reproducible."""
+    g = gpu
+    N, T = 1 << 22, 50
+    model = g.LinearGaussianSSM(*LG)
+    ys = cf.simulate_lgssm(T, LG, 0)
+    vals = []
+    for rep in range(2):
+        st = g.ParticleFilterState(model, N, seed=0, keep_history=False)
+        st.init([ys[0]])
+        st.step([ys[1]])
+        assert st.maybe_resample(N) is True
+        anc = st.ancestors()
+        assert anc.min() >= 0 and anc.max() < N and np.all(np.diff(anc) >= 0)
+        assert np.bincount(anc, minlength=N).sum() == N
+        st.step([ys[2]])
+        st.run_steps(ys[3:], N / 2)
+        vals.append(st.log_ml_estimate())
+    assert vals[0] == vals[1]
+    assert vals[0] == pytest.approx(cf.kalman_log_ml(ys, *LG), abs=0.05)

@@ -1,0 +1,47 @@
+"""CPU: gen_b200/csrc/gsmc_math.h (the IEEE-only transcendentals shared by device and oracle)
+against glibc, in ulps."""
+import math
+
+import numpy as np
+import pytest
+
+
+def ulps(ref, got):
+    ref, got = np.asarray(ref, dtype=np.float64), np.asarray(got, dtype=np.float64)
+    return np.abs(got - ref) / np.spacing(np.abs(ref))
+
+
+def test_exp_log_accuracy(orc):
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-700, 700, 20000), rng.uniform(-2, 2, 20000), [0.0, 1.0, -1.0, 709.0, -708.0]])
+    got = np.array([orc.L.orc_exp(float(x)) for x in xs])
+    assert ulps(np.exp(xs), got).max() <= 2.0
+    ys = np.concatenate([np.exp(rng.uniform(-700, 700, 20000)), 1 + rng.uniform(-1e-3, 1e-3, 20000), [1.0, 2.0, 0.5, 1e-310]])
+    got = np.array([orc.L.orc_log(float(y)) for y in ys])
+    assert ulps(np.log(ys), got)[np.log(ys) != 0].max() <= 2.5
+    assert orc.L.orc_log(1.0) == 0.0 and orc.L.orc_exp(0.0) == 1.0
+    assert orc.L.orc_exp(-math.inf) == 0.0 and orc.L.orc_exp(-750.0) == 0.0 and orc.L.orc_exp(800.0) == math.inf
+    assert orc.L.orc_log(0.0) == -math.inf and math.isnan(orc.L.orc_log(-1.0)) and math.isnan(orc.L.orc_exp(math.nan))
+
+
+def test_sincospi_atan2_accuracy(orc):
+    rng = np.random.default_rng(1)
+    for t in rng.uniform(0, 2, 5000):
+        s, c = orc.sincospi(float(t))
+        assert abs(s - math.sin(math.pi * t)) < 1e-15 and abs(c - math.cos(math.pi * t)) < 1e-15   # the reference side rounds pi*t too
+    assert orc.sincospi(0.0) == (0.0, 1.0)
+    assert orc.sincospi(0.5)[0] == 1.0 and orc.sincospi(1.5)[0] == -1.0
+    for _ in range(5000):
+        y, x = rng.uniform(-30, 30, 2)
+        assert ulps(math.atan2(y, x), orc.L.orc_atan2(float(y), float(x))) <= 4.0
+
+
+def test_box_muller_normals_are_standard(orc):
+    z = orc.normals(12345, 7, 0, 400000)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs(np.mean(z ** 3)) < 0.03 and abs(np.mean(z ** 4) - 3) < 0.06
+    assert np.array_equal(orc.normals(12345, 7, 1000, 10), z[1000:1010])          # counter-based: any slice
+    u = orc.uniforms(1, 2, 1, 0, 100000)
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    e = orc.spacings(3, 0, 0, 200000).astype(np.float64) / 2 ** 32
+    assert abs(e.mean() - 1) < 0.01 and abs(e.var() - 1) < 0.03

@@ -1,0 +1,234 @@
+"""CPU: the oracle against every golden value the reference's own tests hold for this path, against
+closed forms, and against committed fixtures (tests/golden). No GPU needed."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import closed_forms as cf
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_philox_known_answers(orc):
+    """Random123 kat_vectors for philox4x32-10."""
+    assert orc.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert orc.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert orc.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_forward_algorithm_hand_example():
+    """test/inference/particle_filter.jl:29-48."""
+    prior = np.array([0.4, 0.6])
+    E = np.array([[0.1, 0.9], [0.7, 0.3]]).T
+    Tm = np.array([[0.5, 0.5], [0.2, 0.8]]).T
+    obs = [2, 1]
+    exp = 0.0
+    for z1 in (1, 2):
+        for z2 in (1, 2):
+            exp += prior[z1 - 1] * Tm[z2 - 1, z1 - 1] * E[obs[0] - 1, z1 - 1] * E[obs[1] - 1, z2 - 1]
+    assert cf.hmm_forward_alg(prior, E, Tm, obs) == pytest.approx(exp, rel=1e-14)
+
+
+def test_hmm_fixture_log_ml():
+    v = math.log(cf.hmm_forward_alg(cf.HMM_PRIOR, cf.HMM_EMISSION, cf.HMM_TRANSITION, cf.HMM_OBS))
+    assert v == pytest.approx(-4.87645083351704, abs=1e-13)
+
+
+@pytest.mark.parametrize("prop", [0, 1])
+@pytest.mark.parametrize("libm", [False, True])
+def test_hmm_particle_filter_reference_test(orc, orc_libm, prop, libm):
+    """test/inference/particle_filter.jl:96-168: N=10^4, ess_threshold=N, atol 0.01."""
+    o = orc_libm if libm else orc
+    pf = o.particle_filter(O.HMM, cf.hmm_params(), 10000, seed=0)
+    pf.init([cf.HMM_OBS[0]], proposal=prop)
+    for T in range(2, 5):
+        pf.maybe_resample(ess_threshold=10000)
+        pf.step([cf.HMM_OBS[T - 1]], proposal=prop)
+    assert abs(pf.log_ml_estimate() - cf.HMM_LOG_ML) < 0.01
+
+
+def test_hmm_custom_proposal_weights_are_parent_marginals(orc):
+    """under the locally optimal proposal the increment is log sum_z Tr*E."""
+    N = 500
+    pf = orc.particle_filter(O.HMM, cf.hmm_params(), N, seed=3)
+    pf.init([1], proposal=1)
+    expect0 = math.log(float(np.sum(cf.HMM_PRIOR * cf.HMM_EMISSION[0, :])))
+    assert np.allclose(pf.log_weights(), expect0, atol=1e-14)
+    z0 = pf.state()[0].astype(int)
+    pf.step([2], proposal=1)
+    inc = pf.log_weights() - expect0
+    want = np.log(np.array([np.sum(cf.HMM_TRANSITION[:, z - 1] * cf.HMM_EMISSION[1, :]) for z in z0]))
+    assert np.allclose(inc, want, atol=1e-13)
+
+
+def test_unfold_extension_weight_identity(orc):
+    """test/modeling_library/unfold.jl:196-234: extending by a step whose observation is constrained
+    adds logpdf(obs | new latent) only; the new latent comes from the kernel's prior."""
+    alpha, beta, std, x_init = 0.2, 0.3, 1.0, 0.1
+    params = [x_init, 1e-300, alpha, beta, std, 1.0, 0.5]     # s0 ~ 0: x_1 = x_init exactly
+    N = 64
+    pf = orc.particle_filter(O.LGSSM, params, N, seed=1)
+    pf.init([0.0])
+    assert np.all(pf.state()[0] == x_init)
+    w0 = pf.log_weights()
+    z = np.random.default_rng(0).standard_normal(N)
+    pf.step([1.3], z_replay=z)
+    x = pf.state()[0]
+    assert np.array_equal(x, (x_init * alpha + beta) + std * z)             # normal.jl:96
+    inc = pf.log_weights() - w0
+    want = np.array([cf.normal_logpdf(1.3, 1.0 * xi, 0.5) for xi in x])      # logpdf of the constrained choice only
+    assert np.allclose(inc, want, rtol=0, atol=1e-13)
+
+
+def test_normal_logpdf_formula(orc):
+    """normal.jl:56-60 and support edge cases of test/modeling_library/distributions.jl:43,215."""
+    L = orc.L
+    assert L.orc_logpdf_normal(0.3, -0.1, 2.0) == pytest.approx(-(0.4 ** 2) / (2 * 4.0) - 0.5 * math.log(2 * math.pi * 4.0), rel=1e-15)
+    assert orc.logpdf_categorical(4, [0.2, 0.3, 0.5]) == -math.inf
+    assert orc.logpdf_categorical(0, [0.2, 0.3, 0.5]) == -math.inf
+    assert orc.logpdf_categorical(2, [0.2, 0.3, 0.5]) == pytest.approx(math.log(0.3), rel=1e-15)
+    assert L.orc_logpdf_uniform(-0.5, 0.0, 1.0) == -math.inf
+    assert L.orc_logpdf_uniform(0.5, 0.0, 2.0) == pytest.approx(-math.log(2.0))
+    assert L.orc_logpdf_bernoulli(1, 0.3) == pytest.approx(math.log(0.3))
+    assert L.orc_logpdf_bernoulli(0, 0.3) == pytest.approx(math.log(0.7))
+
+
+def test_logsumexp_and_ess(orc):
+    """inference.jl:3-11; particle_filter.jl:3-12."""
+    a = np.array([-1.0, -2.0, -0.5, -30.0])
+    assert orc.logsumexp(a) == pytest.approx(np.log(np.sum(np.exp(a))), rel=1e-15)
+    assert orc.logsumexp([-math.inf, -math.inf]) == -math.inf
+    assert orc.L.orc_logsumexp2(-1.0, -2.0) == pytest.approx(np.log(np.exp(-1) + np.exp(-2)), rel=1e-15)
+    assert orc.L.orc_logsumexp2(-math.inf, -math.inf) == -math.inf
+    lnw = a - orc.logsumexp(a)
+    p = np.exp(lnw)
+    assert orc.effective_sample_size(lnw) == pytest.approx(1.0 / np.sum(p * p), rel=1e-14)
+    assert orc.effective_sample_size(np.full(8, -math.log(8))) == pytest.approx(8.0, rel=1e-14)
+
+
+def test_importance_sampling_invariants(orc):
+    """test/inference/importance_sampling.jl:18-34 (n=4) and the closed form log N(2; 0, sqrt 2)."""
+    for prop, pp in ((0, None), (1, [0.0, 2.0])):
+        lat, lnw, lml = orc.importance_sampling(O.NORMAL_NORMAL, [0, 1, 1], [2.0], 4, seed=0, proposal=prop, prop_params=pp)
+        assert lat.shape == (1, 4) and lnw.shape == (4,)
+        assert abs(orc.logsumexp(lnw)) < 1e-14
+        assert not math.isnan(lml)
+    lat, lnw, lml = orc.importance_sampling(O.NORMAL_NORMAL, [0, 1, 1], [2.0], 400000, seed=1, proposal=1, prop_params=[1.0, 1.0])
+    assert lml == pytest.approx(-2.2655121234846454, abs=0.01)
+
+
+def test_regression_is_against_conjugate_closed_form(orc):
+    exact = cf.regression_log_ml(cf.QUICKSTART_XS, cf.QUICKSTART_YS, 2, 10, 1)
+    assert exact == pytest.approx(cf.QUICKSTART_LOG_ML, abs=1e-9)
+    lat, lnw, lml = orc.importance_sampling(O.REGRESSION, cf.regression_params(), cf.QUICKSTART_YS, 300000, seed=0,
+                                            proposal=1, prop_params=[-2.0, 0.3, 10.0, 1.5])
+    assert lml == pytest.approx(exact, abs=0.03)
+    assert abs(orc.logsumexp(lnw)) < 1e-10
+
+
+def test_lgssm_against_kalman(orc):
+    params = [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0]
+    ys = cf.simulate_lgssm(30, params, 0)
+    exact = cf.kalman_log_ml(ys, *params)
+    for prop in (0, 1):
+        pf = orc.particle_filter(O.LGSSM, params, 1 << 15, seed=5)
+        pf.init([ys[0]], proposal=prop)
+        for t in range(1, 30):
+            pf.maybe_resample()
+            pf.step([ys[t]], proposal=prop)
+        assert pf.log_ml_estimate() == pytest.approx(exact, abs=0.15 if prop == 0 else 0.03)
+
+
+def test_oracle_math_builds_agree(orc, orc_libm):
+    """The IEEE-only math build and the glibc build give the same filter up to rounding."""
+    params = [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0]
+    ys = cf.simulate_lgssm(10, params, 1)
+    outs = []
+    for o in (orc, orc_libm):
+        pf = o.particle_filter(O.LGSSM, params, 4096, seed=2)
+        pf.init([ys[0]])
+        for t in range(1, 10):
+            pf.step([ys[t]])
+        outs.append((pf.log_weights(), pf.log_ml_estimate()))
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-12, atol=1e-12)
+    assert outs[0][1] == pytest.approx(outs[1][1], rel=1e-13)
+
+
+def test_resampling_arithmetic(orc):
+    """Oracle-defined integer resampling: iid search == numpy searchsorted on the integer CDF; the
+    sorted-spacing thresholds are non-decreasing; residual copies are floor(N p)."""
+    rng = np.random.default_rng(0)
+    N = 5000
+    lw = rng.standard_normal(N) * 3
+    q, m = orc.quantise_weights(lw)
+    assert m == lw.max() and q.max() == 1 << orc.L.orc_weight_shift(N)
+    cdf = np.cumsum(q, dtype=np.uint64)
+    u = rng.random(N)
+    anc = orc.search_iid(cdf, u)
+    T = [(int(math.floor(x * 2 ** 53)) * int(cdf[-1])) >> 53 for x in u]
+    assert np.array_equal(anc, np.searchsorted(cdf, np.array(T, dtype=np.uint64), side="right"))
+    E = orc.spacings(7, 0, 0, N + 1)
+    anc_s = orc.search_sorted(cdf, E)
+    assert np.all(np.diff(anc_s) >= 0) and anc_s.min() >= 0 and anc_s.max() < N
+    S = np.cumsum([int(e) for e in E[:-1]], dtype=object)
+    stot = int(S[-1]) + int(E[-1])
+    Tk = np.array([(int(s) * int(cdf[-1])) // stot for s in S], dtype=np.uint64)
+    assert np.array_equal(anc_s, np.minimum(np.searchsorted(cdf, Tk, side="right"), N - 1))
+    # offspring counts follow the weights
+    counts = np.bincount(anc_s, minlength=N)
+    p = q / q.sum()
+    assert abs(np.sum(counts * p) / np.sum(N * p * p) - 1) < 0.1
+    # equal weights: ESS = N up to rounding, so `ess < N` is a tie the reference decides by rounding
+    pf = orc.particle_filter(O.LGSSM, [0, 1, 0.9, 0, 1, 1, 1], 1000, seed=0)
+    pf.init([0.0])
+    pf.set_log_weights(np.zeros(1000))
+    pf.maybe_resample(1000)
+    assert pf.last_ess == pytest.approx(1000.0, rel=1e-13)
+
+
+def test_residual_resampling_definition(orc):
+    N = 4000
+    pf = orc.particle_filter(O.LGSSM, [0, 1, 0.9, 0, 1, 1, 1], N, seed=0)
+    pf.init([0.5])
+    lw = pf.log_weights()
+    assert pf.maybe_resample(N, scheme=O.RESIDUAL) is True
+    anc = pf.parents()
+    p = np.exp(lw - orc.logsumexp(lw))
+    floor_counts = np.floor(N * p + 1e-9).astype(int)
+    counts = np.bincount(anc, minlength=N)
+    assert np.all(counts >= floor_counts - 1)          # -1: fixed-point truncation at exact integers
+    assert counts.sum() == N
+    det = int(floor_counts.sum())
+    assert np.all(np.diff(anc[:det - 5]) >= 0)          # deterministic copies are laid out in index order
+
+
+def test_history_is_permuted_like_the_reference(orc):
+    """particle_filter.jl:202-205 copies whole traces: history must follow the ancestors."""
+    N = 300
+    pf = orc.particle_filter(O.LGSSM, [0, 1, 0.9, 0, 1, 1, 1], N, seed=4, keep_history=True)
+    pf.init([0.2])
+    h1 = pf.history(1).copy()
+    pf.step([0.1])
+    assert pf.maybe_resample(N) is True
+    anc = pf.parents()
+    assert np.array_equal(pf.history(1), h1[:, anc])
+
+
+def test_golden_fixtures(orc):
+    """Committed outputs of the oracle (tests/golden/make_golden.py): guards the semantics the GPU
+    tests are compared against from drifting."""
+    with open(os.path.join(GOLD, "oracle_golden.json")) as fh:
+        gold = json.load(fh)
+    from tests.golden.make_golden import run_case
+    for case in gold["cases"]:
+        got = run_case(orc, case["spec"])
+        for key, val in case["expect"].items():
+            if isinstance(val, list):
+                assert list(got[key]) == val, (case["spec"], key)
+            else:
+                assert got[key] == pytest.approx(val, rel=1e-13, abs=1e-13), (case["spec"], key)
