@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/sec of the SMC hot path (BASELINE.json metric) on N B200s.
+
+A "step" (one of --steps K) is ONE COMPLETE FILTER RUN of the workload:
+    initialize_particle_filter + (T-1) x [maybe_resample!(ess < N/2) -> particle_filter_step!] + log_ml_estimate
+on the 1-D linear-Gaussian state-space model (BASELINE.json configs[2]: Unfold, T=100, 2^24 particles
+per GPU, fp64, multinomial resampling, full trace history kept), i.e. N*T particle-steps.
+
+  value      particle-steps/s, device-timed (CUDA events on the library's stream, max over ranks),
+             loop enqueued through gsmc_run_steps with no host round trip per step
+  e2e        the same run through the Gen-API mirror (initialize_particle_filter /
+             maybe_resample_b / particle_filter_step_b / log_ml_estimate): host observation choicemaps
+             in, Bool of every maybe_resample! and the log-ML estimate out, allocation included
+  roofline   dominant kernel (propagate: proposal + logpdf + ancestor gather + logsumexp partials),
+             algorithmic bytes per launch / CUDA-event duration of those launches, vs measured HBM peak
+  cpu_baseline   the CPU oracle (C restatement of the reference, 1 thread) on a bounded sample
+
+`--impl reference` times the reference's CPU algorithm (oracle port with all host threads; Julia/Gen.jl
+itself cannot run in this environment).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LG = [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0]           # m0, s0, a, b, q, c, r  (SURVEY.md 8(d) cfg 3)
+STATE_BYTES = 8                                     # S: one fp64 latent
+
+
+def make_observations(T):
+    from oracle import closed_forms as cf           # input generation only (numpy), not a compute path
+    return cf.simulate_lgssm(T, LG, 0)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.15 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def dist_setup(n_gpus):
+    """One process per GPU under torchrun; torch.distributed is plumbing (barrier, id broadcast, max)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        return rank, world, local, None
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def run_ours(args):
+    import gen_b200 as g
+    from gen_b200.distributed import Communicator
+    rank, world, local, dist = dist_setup(args.gpus)
+    n_per = 1 << args.log2n
+    N = n_per * world
+    T = args.T
+    ys = make_observations(T)
+    model = g.LinearGaussianSSM(*LG)
+    comm = Communicator(dist, rank, world, device=local) if world > 1 else None
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def new_state():
+        return g.ParticleFilterState(model, N, seed=0, dtype=args.dtype, keep_history=not args.no_history,
+                                     history_capacity=T, device=local, comm=comm)
+
+    # ---- device-timed value: K complete runs, inputs resident, no host round trip per step ------
+    st = new_state()
+
+    def one_run(s):
+        s.reset()
+        s.init([ys[0]])
+        s.run_steps(ys[1:], N / 2)
+        return s.log_ml_estimate()
+
+    for _ in range(args.warmup):
+        lml = one_run(st)
+    launches0 = st.stats()["kernel_launches"]
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.time()
+    st.synchronize()
+    st.timer_start()
+    for _ in range(args.steps):
+        lml = one_run(st)
+    ms = st.timer_stop()
+    st.synchronize()
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    stats = st.stats()
+    launches = stats["kernel_launches"] - launches0
+    n_resamples = stats["num_resamples"]
+    if dist is not None:
+        import torch
+        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = N * T * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel CUDA-event times (profiling pass through the per-call API, same workload) ----
+    st.set_profiling(True)
+    st.reset()
+    st.init([ys[0]])
+    for t in range(1, T):
+        st.maybe_resample(N / 2)
+        st.step([ys[t]])
+    st.log_ml_estimate()
+    prof = st.stats()
+    st.set_profiling(False)
+    st.close()
+
+    # ---- e2e through the Gen-API mirror, host buffers, allocation included --------------------------
+    def e2e_run():
+        state = g.initialize_particle_filter(model, (1,), g.choicemap(("y_init", float(ys[0]))), N, seed=0, dtype=args.dtype,
+                                             keep_history=not args.no_history, history_capacity=T, device=local, comm=comm)
+        for Tn in range(2, T + 1):
+            g.maybe_resample_b(state)
+            g.particle_filter_step_b(state, (Tn,), (g.UnknownChange(),), g.choicemap((("chain", Tn - 1, "y"), float(ys[Tn - 1]))))
+        out = g.log_ml_estimate(state)
+        state.close()
+        return out
+
+    e2e_run()
+    barrier()
+    e0 = time.perf_counter()
+    reps = max(1, min(args.steps, 3))
+    for _ in range(reps):
+        lml_e2e = e2e_run()
+    barrier()
+    e_ms = (time.perf_counter() - e0) * 1e3
+    if dist is not None:
+        import torch
+        tmax = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e_ms = float(tmax.item())
+    e2e_value = N * T * reps / (e_ms * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = measured_peak()
+    S = STATE_BYTES if args.dtype == "f64" else 4
+    LW = 8 if args.dtype == "f64" else 4
+    n_plain, n_gather = prof["n_propagate"], prof["n_propagate_gather"]
+    bytes_plain = n_per * (2 * S + 2 * LW)              # read x, lw; write x', lw'   (2S+16)
+    bytes_gather = n_per * (2 * S + LW + 4)             # read anc, x[anc]; write x', lw' (lw restarts from 0)
+    ms_prop = prof["ms_propagate"] + prof["ms_propagate_gather"]
+    alg_bytes = n_plain * bytes_plain + n_gather * bytes_gather
+    achieved = alg_bytes / (ms_prop * 1e-3) / 1e9 if ms_prop > 0 else 0.0
+    kernel_ms = {k[3:]: prof[k] for k in prof if k.startswith("ms_")}
+    total_kernel_ms = sum(kernel_ms.values())
+    # whole-run figure with SURVEY 8(d)'s accounting: 2S+16 per particle-step, 2S+36 per resample
+    run_bytes = n_per * (T * (2 * S + 2 * LW) + (n_gather) * (2 * S + 36))
+    line = {
+        "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "1D linear-Gaussian SSM (Unfold), T=%d, N=2^%d particles per GPU, bootstrap proposal, "
+                               "multinomial resampling at ESS<N/2, trace history %s" % (T, args.log2n, "dropped" if args.no_history else "kept"),
+                   "particles_total": N, "time_steps": T, "resamples_per_run": n_resamples,
+                   "parallelism": "particles sharded over %d GPU(s)" % world,
+                   "l2": "inputs larger than L2: each step streams >=3 columns of %d MiB (126 MB L2), history columns are never re-read" % (n_per * S >> 20)},
+        "log_ml": lml, "log_ml_kalman": kalman(ys), "log_ml_e2e": lml_e2e,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 8 * T,
+                "d2h_bytes_per_step": 8 + T * 408, "ms_per_step": e_ms / reps,
+                "note": "Gen-API mirror; includes cudaMalloc of the trace slabs, one D2H of the device scalars per maybe_resample!"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "propagate_kernel<LgssmModel>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
+                     "algorithmic_bytes_per_launch": {"plain": bytes_plain, "gather": bytes_gather},
+                     "launches": {"plain": n_plain, "gather": n_gather}, "avg_launch_ms": ms_prop / max(1, n_plain + n_gather)},
+        "roofline_whole_run": {"algorithmic_GBps": run_bytes * args.steps / (ms * 1e-3) / 1e9 / 1.0, "frac": run_bytes * args.steps / (ms * 1e-3) / 1e9 / peak,
+                               "accounting": "SURVEY 8(d): (2S+16) B per particle-step + (2S+36) B per particle per resample"},
+        "kernel_ms_profile_pass": kernel_ms, "kernel_share_propagate": ms_prop / total_kernel_ms if total_kernel_ms else None,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(1, args.cpu_log2n, T, ys)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def kalman(ys):
+    from oracle import closed_forms as cf
+    return cf.kalman_log_ml(ys, *LG)
+
+
+def oracle_run(orc, N, T, ys, threads):
+    from oracle import oracle as O
+    pf = orc.particle_filter(O.LGSSM, LG, N, seed=0, keep_history=False, num_threads=threads)
+    pf.init([ys[0]])
+    for t in range(1, T):
+        pf.maybe_resample()
+        pf.step([ys[t]])
+    return pf.log_ml_estimate()
+
+
+def cpu_baseline(threads, log2n, T, ys):
+    """The oracle (C port of the reference algorithm) on the host cores, bounded sample."""
+    from oracle import oracle as O
+    orc = O.Oracle()
+    N = 1 << log2n
+    t0 = time.perf_counter()
+    lml = oracle_run(orc, N, T, ys, threads)
+    dt = time.perf_counter() - t0
+    return {"value": N * T / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": "same model and loop, N=2^%d particles x T=%d steps, one run (%.1f s); C restatement of Gen.jl's "
+                      "algorithm without per-particle trace allocation, so it flatters Gen.jl" % (log2n, T, dt),
+            "log_ml": lml}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    T = args.T
+    ys = make_observations(T)
+    threads = os.cpu_count() or 1
+    orc = O.Oracle()
+    N = 1 << args.cpu_log2n
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle_run(orc, N, T, ys, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lml = oracle_run(orc, N, T, ys, threads)
+    dt = time.perf_counter() - t0
+    value = N * T * args.steps / dt
+    sample = "each step = one full filter run on a bounded sample: N=2^%d particles x T=%d (workload is 2^%d per GPU)" % (args.cpu_log2n, T, args.log2n)
+    line = {"impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "1D linear-Gaussian SSM (Unfold), T=%d, bootstrap proposal, multinomial resampling at ESS<N/2" % T,
+                       "note": "Gen.jl (Julia) cannot run here; this is the C port of its algorithm (oracle/) on all host threads"},
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "log_ml": lml, "log_ml_kalman": kalman(ys)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=24, help="log2 of particles per GPU")
+    ap.add_argument("--T", type=int, default=100)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-history", action="store_true")
+    ap.add_argument("--cpu-log2n", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

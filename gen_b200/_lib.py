@@ -31,11 +31,10 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("last_ess", C.c_double), ("last_log_total", C.c_double), ("log_ml_est", C.c_double),
                 ("num_steps", C.c_int64), ("num_resamples", C.c_int64), ("kernel_launches", C.c_int64),
-                ("ms_propagate", C.c_double), ("ms_finalize", C.c_double), ("ms_scan", C.c_double),
-                ("ms_spacings", C.c_double), ("ms_search", C.c_double), ("ms_other", C.c_double),
-                ("n_propagate", C.c_int64), ("n_finalize", C.c_int64), ("n_scan", C.c_int64),
-                ("n_spacings", C.c_int64), ("n_search", C.c_int64), ("n_other", C.c_int64),
-                ("n_propagate_resampled", C.c_int64)]
+                ("ms_propagate", C.c_double), ("ms_propagate_gather", C.c_double), ("ms_finalize", C.c_double),
+                ("ms_scan", C.c_double), ("ms_spacings", C.c_double), ("ms_search", C.c_double), ("ms_other", C.c_double),
+                ("n_propagate", C.c_int64), ("n_propagate_gather", C.c_int64), ("n_finalize", C.c_int64),
+                ("n_scan", C.c_int64), ("n_spacings", C.c_int64), ("n_search", C.c_int64), ("n_other", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -51,8 +50,11 @@ SIGNATURES = {
     "gsmc_last_error": (C.c_char_p, [_H]),
     "gsmc_create": (C.c_int, [C.POINTER(Config), _dp, C.c_size_t, C.POINTER(_H)]),
     "gsmc_destroy": (None, [_H]),
+    "gsmc_reset": (C.c_int, [_H]),
     "gsmc_comm_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
-    "gsmc_comm_attach": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
+    "gsmc_comm_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
+    "gsmc_comm_destroy": (None, [_H]),
+    "gsmc_comm_attach": (C.c_int, [_H, _H]),
     "gsmc_set_replay": (C.c_int, [_H, _dp, C.c_size_t, _dp, C.c_size_t]),
     "gsmc_init": (C.c_int, [_H, _dp, C.c_size_t, C.c_int, _dp, C.c_size_t]),
     "gsmc_step": (C.c_int, [_H, _dp, C.c_size_t, C.c_int, _dp, C.c_size_t]),

@@ -82,9 +82,14 @@ enum { NCCL_UINT8 = 1 };
 // ------------------------------------------------------------------------------------------------
 // the filter object
 // ------------------------------------------------------------------------------------------------
-enum KernelClass { KC_PROPAGATE = 0, KC_FINALIZE, KC_SCAN, KC_SPACINGS, KC_SEARCH, KC_OTHER, KC_COUNT };
+enum KernelClass { KC_PROPAGATE = 0, KC_PROPAGATE_GATHER, KC_FINALIZE, KC_SCAN, KC_SPACINGS, KC_SEARCH, KC_OTHER, KC_COUNT };
 
 struct ProfEvent { cudaEvent_t a, b; int cls; };
+
+struct gsmc_comm_s {
+  NcclComm comm = nullptr;
+  int rank = 0, nranks = 1, device = 0;
+};
 
 struct gsmc_filter {
   gsmc_config cfg;
@@ -112,6 +117,7 @@ struct gsmc_filter {
   uint64_t* tile_a = nullptr; // per-tile sums / prefixes (weights)
   uint64_t* tile_b = nullptr; // per-tile sums / prefixes (spacings; residual counts)
   uint64_t* scratch_tot = nullptr;  // 4 u64 scratch totals
+  uint32_t* win = nullptr;          // nt+1 window words of the sorted search
   LseTriple* partials = nullptr;
   DevScalars* ds = nullptr;
   DevScalars* h_ds = nullptr; // pinned mirror
@@ -138,7 +144,6 @@ struct gsmc_filter {
   std::vector<ProfEvent> prof_live, prof_free;
   double prof_ms[KC_COUNT] = {};
   int64_t prof_n[KC_COUNT] = {};
-  int64_t n_prop_resampled = 0;
   int64_t launches = 0;
   cudaEvent_t timer_a = nullptr, timer_b = nullptr;
 };
@@ -235,6 +240,7 @@ static int alloc_buffers(gsmc_filter* f) {
   CK(cudaMalloc(&f->tile_a, (size_t)f->n_tiles * sizeof(uint64_t)));
   CK(cudaMalloc(&f->tile_b, (size_t)f->n_tiles * sizeof(uint64_t)));
   CK(cudaMalloc(&f->scratch_tot, 4 * sizeof(uint64_t)));
+  CK(cudaMalloc(&f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t)));
   CK(cudaMalloc(&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
   CK(cudaMalloc(&f->ds, sizeof(DevScalars)));
   CK(cudaMallocHost(&f->h_ds, sizeof(DevScalars)));
@@ -243,8 +249,7 @@ static int alloc_buffers(gsmc_filter* f) {
   CK(cudaMemsetAsync(f->resampled, 0, (size_t)f->flag_mod * sizeof(int), f->stream));
   // pad lanes of the log-weight column are read by vector loads: keep them finite and harmless
   CK(cudaMemsetAsync(f->lw, 0, f->n_pad * rs, f->stream));
-  CK(cudaMemsetAsync(f->anc_slab, 0, (size_t)f->cap * f->n_pad * sizeof(uint32_t), f->stream));
-  CK(cudaMemsetAsync(f->state_slab, 0, (size_t)f->cap * f->D * f->n_pad * rs, f->stream));
+  // state / ancestor slabs are written before they are read (pad lanes are masked), so they are not cleared
   f->peer_slab[f->rank] = f->state_slab;
   f->peer_anc[f->rank] = f->anc_slab;
   f->peer_cdf[f->rank] = f->cdf;
@@ -259,11 +264,11 @@ static void free_buffers(gsmc_filter* f) {
     f->peer_slab[r] = nullptr; f->peer_anc[r] = nullptr; f->peer_cdf[r] = nullptr;
   }
   cudaFree(f->state_slab); cudaFree(f->anc_slab); cudaFree(f->lw); cudaFree(f->cdf); cudaFree(f->cc);
-  cudaFree(f->tile_a); cudaFree(f->tile_b); cudaFree(f->scratch_tot); cudaFree(f->partials); cudaFree(f->ds);
+  cudaFree(f->tile_a); cudaFree(f->tile_b); cudaFree(f->scratch_tot); cudaFree(f->win); cudaFree(f->partials); cudaFree(f->ds);
   cudaFree(f->resampled);
   if (f->h_ds) cudaFreeHost(f->h_ds);
   f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
-  f->tile_a = f->tile_b = f->scratch_tot = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
+  f->tile_a = f->tile_b = f->scratch_tot = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
   f->resampled = nullptr;
 }
 static int ensure_f64(gsmc_filter* f, size_t n) {
@@ -302,7 +307,7 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   if (!nu) g.urep = nullptr;
   if (!nz) g.zrep = nullptr;
   {
-    ProfScope ps(f, KC_PROPAGATE);
+    ProfScope ps(f, (use_anc && f->pending) ? KC_PROPAGATE_GATHER : KC_PROPAGATE);
     propagate_kernel<Model, Real, INIT, PROP><<<f->n_tiles, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream>>>(g, a);
   }
   CK(cudaGetLastError());
@@ -454,7 +459,9 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     { ProfScope ps(f, KC_SPACINGS); spacing_total_kernel<<<1, 32, 0, f->stream>>>(f->cfg.seed, f->ds, f->nranks); }
     // 3. ancestors
     { ProfScope ps(f, KC_SEARCH);
-      search_sorted_kernel<<<nt, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, anc, f->n, residual ? 1 : 0, conditional); }
+      partition_kernel<<<(nt + 1 + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, nt, f->win, conditional); }
+    { ProfScope ps(f, KC_SEARCH);
+      search_sorted_kernel<<<nt, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, f->win, anc, f->n, residual ? 1 : 0, conditional); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -521,11 +528,23 @@ GSMC_API void gsmc_destroy(gsmc_handle f) {
   for (ProfEvent& e : f->prof_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   free_buffers(f);
   cudaFree(f->d_params); cudaFree(f->d_obs); cudaFree(f->d_zrep); cudaFree(f->d_urep); cudaFree(f->d_f64);
-  if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(f->comm);
   if (f->timer_a) cudaEventDestroy(f->timer_a);
   if (f->timer_b) cudaEventDestroy(f->timer_b);
   if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
   delete f;
+}
+
+GSMC_API int gsmc_reset(gsmc_handle f) {
+  if (!f) return fail(GSMC_E_BADARG, "null handle");
+  if (f->is_importance && f->T > 0) return fail(GSMC_E_BADARG, "importance-sampling handles cannot be reset");
+  CK(cudaSetDevice(f->device));
+  f->T = 0; f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
+  f->last_resample_step = 0; f->n_sample_calls = 0; f->zrep_n = 0; f->urep_n = 0;
+  if (f->ds) {
+    CK(cudaMemsetAsync(f->ds, 0, sizeof(DevScalars), f->stream));
+    CK(cudaMemsetAsync(f->resampled, 0, (size_t)f->flag_mod * sizeof(int), f->stream));
+  }
+  return GSMC_OK;
 }
 
 GSMC_API int gsmc_comm_unique_id(void* id_out, size_t nbytes) {
@@ -535,19 +554,39 @@ GSMC_API int gsmc_comm_unique_id(void* id_out, size_t nbytes) {
   return GSMC_OK;
 }
 
-GSMC_API int gsmc_comm_attach(gsmc_handle f, const void* unique_id, size_t nbytes, int rank, int nranks) {
-  if (!f || !unique_id || nbytes < sizeof(NcclId)) return fail(GSMC_E_BADARG, "bad arguments");
-  if (f->T != 0 || f->state_slab) return fail(GSMC_E_BADARG, "attach must precede gsmc_init");
+GSMC_API int gsmc_comm_create(const void* unique_id, size_t nbytes, int rank, int nranks, int device, gsmc_comm* out) {
+  if (!unique_id || nbytes < sizeof(NcclId) || !out) return fail(GSMC_E_BADARG, "bad arguments");
   if (nranks < 1 || nranks > GSMC_MAX_RANKS || rank < 0 || rank >= nranks) return fail(GSMC_E_BADARG, "1 <= nranks <= %d", GSMC_MAX_RANKS);
-  if (f->N % ((int64_t)nranks * GSMC_TILE) != 0) return fail(GSMC_E_BADARG, "num_particles must be a multiple of %d * nranks", GSMC_TILE);
-  CK(cudaSetDevice(f->device));
-  f->rank = rank; f->nranks = nranks;
-  f->n = f->N / nranks; f->first = f->n * rank;
-  if (nranks == 1) return GSMC_OK;
   CKRC(load_nccl());
+  if (device < 0) CK(cudaGetDevice(&device));
+  CK(cudaSetDevice(device));
+  gsmc_comm_s* c = new gsmc_comm_s();
+  c->rank = rank; c->nranks = nranks; c->device = device;
   NcclId id;
   memcpy(&id, unique_id, sizeof id);
-  NK(g_nccl.CommInitRank(&f->comm, nranks, id, rank));
+  int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+  if (r != 0) { delete c; return fail(GSMC_E_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
+  *out = c;
+  return GSMC_OK;
+}
+
+GSMC_API void gsmc_comm_destroy(gsmc_comm c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  delete c;
+}
+
+GSMC_API int gsmc_comm_attach(gsmc_handle f, gsmc_comm c) {
+  if (!f || !c) return fail(GSMC_E_BADARG, "bad arguments");
+  if (f->T != 0 || f->state_slab) return fail(GSMC_E_BADARG, "attach must precede gsmc_init");
+  if (c->device != f->device) return fail(GSMC_E_BADARG, "communicator lives on device %d, filter on device %d", c->device, f->device);
+  const int rank = c->rank, nranks = c->nranks;
+  if (f->N % ((int64_t)nranks * GSMC_TILE) != 0) return fail(GSMC_E_BADARG, "num_particles must be a multiple of %d * nranks", GSMC_TILE);
+  CK(cudaSetDevice(f->device));
+  f->rank = rank; f->nranks = nranks; f->comm = c->comm;
+  f->n = f->N / nranks; f->first = f->n * rank;
+  if (nranks == 1) return GSMC_OK;
   // allocate now and exchange IPC handles of the slabs peers read (state, ancestors, CDF)
   CKRC(alloc_buffers(f));
   struct Handles { cudaIpcMemHandle_t slab, anc, cdf; };
@@ -608,9 +647,7 @@ GSMC_API int gsmc_step(gsmc_handle f, const double* obs, size_t n_obs, int prop,
   if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
   if (f->is_importance) return fail(GSMC_E_BADARG, "importance-sampling models have a single step");
   CK(cudaSetDevice(f->device));
-  const bool gathered = f->pending;
   CKRC(launch_propagate(f, false, obs, n_obs, prop, pp, npp, f->decided_since_step));
-  if (gathered) f->n_prop_resampled += 1;
   f->T += 1;
   f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
   return GSMC_OK;
@@ -900,7 +937,7 @@ GSMC_API int gsmc_get_stats(gsmc_handle f, gsmc_stats* out) {
   out->ms_spacings = f->prof_ms[KC_SPACINGS]; out->n_spacings = f->prof_n[KC_SPACINGS];
   out->ms_search = f->prof_ms[KC_SEARCH]; out->n_search = f->prof_n[KC_SEARCH];
   out->ms_other = f->prof_ms[KC_OTHER]; out->n_other = f->prof_n[KC_OTHER];
-  out->n_propagate_resampled = f->n_prop_resampled;
+  out->ms_propagate_gather = f->prof_ms[KC_PROPAGATE_GATHER]; out->n_propagate_gather = f->prof_n[KC_PROPAGATE_GATHER];
   return GSMC_OK;
 }
 GSMC_API int gsmc_set_profiling(gsmc_handle f, int enabled) {

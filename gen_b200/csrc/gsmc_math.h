@@ -29,6 +29,46 @@
 #define GM_TWO_PI 6.28318530717958623199592693708837032318115234375   /* 2.0*pi     */
 #define GM_INF_BITS 0x7ff0000000000000ULL
 
+
+// Polynomial coefficients live in __constant__ memory on the device so that DFMA takes them as
+// constant-bank operands (as 64-bit immediates they cost two UMOV issue slots each, 16% of the
+// propagate kernel's instructions in the first profile) and in a static table on the host.
+#define GM_EXP_COEFFS { 1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, \
+  2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, \
+  4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0 }
+#define GM_LOG_COEFFS { 4.7619047619047616e-02, 5.2631578947368418e-02, 5.8823529411764705e-02, 6.6666666666666666e-02, \
+  7.6923076923076927e-02, 9.0909090909090912e-02, 1.1111111111111110e-01, 1.4285714285714285e-01, 2.0000000000000001e-01, \
+  3.3333333333333331e-01 }
+#define GM_SIN_COEFFS { -8.2206352466243295e-18, 2.8114572543455206e-15, -7.6471637318198164e-13, 1.6059043836821613e-10, \
+  -2.5052108385441720e-08, 2.7557319223985893e-06, -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01 }
+#define GM_COS_COEFFS { -1.5619206968586225e-16, 4.7794773323873853e-14, -1.1470745597729725e-11, 2.0876756987868100e-09, \
+  -2.7557319223985888e-07, 2.4801587301587302e-05, -1.3888888888888889e-03, 4.1666666666666664e-02, -0.5 }
+#define GM_ATAN_COEFFS { -6.6666666666666666e-02, 7.6923076923076927e-02, -9.0909090909090912e-02, 1.1111111111111110e-01, \
+  -1.4285714285714285e-01, 2.0000000000000001e-01, -3.3333333333333331e-01 }
+#define GM_MISC_CONSTS { 1.44269504088896338700e+00, 6.93147180369123816490e-01, 1.90821492927058770002e-10 }
+static const double gm_exp_h[] = GM_EXP_COEFFS;
+static const double gm_log_h[] = GM_LOG_COEFFS;
+static const double gm_sin_h[] = GM_SIN_COEFFS;
+static const double gm_cos_h[] = GM_COS_COEFFS;
+static const double gm_atan_h[] = GM_ATAN_COEFFS;
+static const double gm_misc_h[] = GM_MISC_CONSTS;
+#if defined(__CUDACC__)
+static __constant__ double gm_exp_d[] = GM_EXP_COEFFS;
+static __constant__ double gm_log_d[] = GM_LOG_COEFFS;
+static __constant__ double gm_sin_d[] = GM_SIN_COEFFS;
+static __constant__ double gm_cos_d[] = GM_COS_COEFFS;
+static __constant__ double gm_atan_d[] = GM_ATAN_COEFFS;
+static __constant__ double gm_misc_d[] = GM_MISC_CONSTS;
+#endif
+#if defined(__CUDA_ARCH__)
+#define GM_C(tab, i) gm_##tab##_d[i]
+#else
+#define GM_C(tab, i) gm_##tab##_h[i]
+#endif
+#define GM_INV_LN2 GM_C(misc, 0)
+#define GM_LN2_HI GM_C(misc, 1)
+#define GM_LN2_LO GM_C(misc, 2)
+
 GM_HD double gm_from_bits(uint64_t b) {
 #if defined(__CUDA_ARCH__)
   return __longlong_as_double((long long)b);
@@ -53,29 +93,38 @@ GM_HD double gm_exp(double x) {
   if (x != x) return x;
   if (x > 709.782712893383973096) return gm_inf();
   if (x < -708.3964185322641) return 0.0;
-  const double kf = floor(x * 1.44269504088896338700e+00 + 0.5);
-  double r = fma(-kf, 6.93147180369123816490e-01, x);   /* ln2 hi (fdlibm split) */
-  r = fma(-kf, 1.90821492927058770002e-10, r);          /* ln2 lo */
-  double p = 1.6059043836821613e-10;                    /* 1/13! */
-  p = fma(p, r, 2.08767569878681e-09);                  /* 1/12! */
-  p = fma(p, r, 2.505210838544172e-08);                 /* 1/11! */
-  p = fma(p, r, 2.755731922398589e-07);                 /* 1/10! */
-  p = fma(p, r, 2.7557319223985893e-06);                /* 1/9!  */
-  p = fma(p, r, 2.48015873015873e-05);                  /* 1/8!  */
-  p = fma(p, r, 1.984126984126984e-04);                 /* 1/7!  */
-  p = fma(p, r, 1.388888888888889e-03);                 /* 1/6!  */
-  p = fma(p, r, 8.333333333333333e-03);                 /* 1/5!  */
-  p = fma(p, r, 4.1666666666666664e-02);                /* 1/4!  */
-  p = fma(p, r, 1.6666666666666666e-01);                /* 1/3!  */
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+  const double kf = floor(x * GM_INV_LN2 + 0.5);
+  double r = fma(-kf, GM_LN2_HI, x);                    /* ln2 hi (fdlibm split) */
+  r = fma(-kf, GM_LN2_LO, r);                           /* ln2 lo */
+  double p = GM_C(exp, 0);                              /* 1/13! ... 1/2!, 1, 1 */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < 14; ++i) p = fma(p, r, GM_C(exp, i));
   const int k = (int)kf;
   const int k1 = k / 2, k2 = k - k1;
   return (p * gm_pow2(k1)) * gm_pow2(k2);
 }
 
 // log(x). x = 2^e * m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = (m-1)/(m+1).
+// gm_log_core: x positive, finite and normal (no checks); e0 = exponent bias already applied.
+GM_HD double gm_log_core(uint64_t b, int e0) {
+  int e = e0 + (int)(b >> 52) - 1023;
+  double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+  if (m > 1.41421356237309514547) { m = m * 0.5; e += 1; }
+  const double f = m - 1.0;
+  const double s = f / (m + 1.0);
+  const double z = s * s;
+  double p = GM_C(log, 0);                   /* 1/21, 1/19, ..., 1/3 */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < 10; ++i) p = fma(p, z, GM_C(log, i));
+  const double s2 = s + s;
+  const double lm = fma(s2 * z, p, s2);      /* 2s + 2s^3 * P(z) */
+  const double ef = (double)e;
+  return fma(ef, GM_LN2_HI, fma(ef, GM_LN2_LO, lm));
+}
 GM_HD double gm_log(double x) {
   if (x != x) return x;
   if (x < 0.0) return gm_nan();
@@ -88,26 +137,26 @@ GM_HD double gm_log(double x) {
     b = gm_to_bits(x);
     e = -54;
   }
-  e += (int)(b >> 52) - 1023;
-  double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
-  if (m > 1.41421356237309514547) { m = m * 0.5; e += 1; }
-  const double f = m - 1.0;
-  const double s = f / (m + 1.0);
-  const double z = s * s;
-  double p = 4.7619047619047616e-02;         /* 1/21 */
-  p = fma(p, z, 5.2631578947368418e-02);     /* 1/19 */
-  p = fma(p, z, 5.8823529411764705e-02);     /* 1/17 */
-  p = fma(p, z, 6.6666666666666666e-02);     /* 1/15 */
-  p = fma(p, z, 7.6923076923076927e-02);     /* 1/13 */
-  p = fma(p, z, 9.0909090909090912e-02);     /* 1/11 */
-  p = fma(p, z, 1.1111111111111110e-01);     /* 1/9  */
-  p = fma(p, z, 1.4285714285714285e-01);     /* 1/7  */
-  p = fma(p, z, 2.0000000000000001e-01);     /* 1/5  */
-  p = fma(p, z, 3.3333333333333331e-01);     /* 1/3  */
-  const double s2 = s + s;
-  const double lm = fma(s2 * z, p, s2);      /* 2s + 2s^3 * P(z) */
-  const double ef = (double)e;
-  return fma(ef, 6.93147180369123816490e-01, fma(ef, 1.90821492927058770002e-10, lm));
+  return gm_log_core(b, e);
+}
+// same bits as gm_log(x) for positive, finite, normal x (e.g. a uniform in (0,1)); no special cases
+GM_HD double gm_log_pos(double x) { return gm_log_core(gm_to_bits(x), 0); }
+
+// x / c for a launch-invariant c with rc = 1.0 / c precomputed: Markstein's sequence
+//   q0 = RN(x rc); r = x - q0 c (exact, FMA); q = RN(q0 + r rc)
+// gives the correctly rounded quotient, i.e. the same bits as the IEEE division the reference
+// formula performs (tests/test_math.py checks 10^7 adversarial operand pairs). Outside the safe
+// magnitude range (zero, subnormal results, inf, nan) or when rc == 0 it falls back to x / c.
+GM_HD double gm_div_inv(double x, double c, double rc) {
+  const double ax = fabs(x);
+  if (!(ax > 1e-290 && ax < 1e290) || rc == 0.0) return x / c;
+  const double q0 = x * rc;
+  const double r = fma(-q0, c, x);
+  return fma(r, rc, q0);
+}
+GM_HD double gm_safe_recip(double c) {       /* rc for gm_div_inv; 0 = "use true division" */
+  const double ac = fabs(c);
+  return (ac > 1e-150 && ac < 1e150) ? 1.0 / c : 0.0;
 }
 
 // sin(pi*t), cos(pi*t) for finite t. Range reduction is exact; kernels are Taylor
@@ -117,25 +166,17 @@ GM_HD void gm_sincospi(double t, double* sn, double* cs) {
   const double r = fma(nf, -0.5, t);         /* exact: |r| <= 1/4 */
   const double x = r * GM_PI;
   const double z = x * x;
-  double ps = -8.2206352466243295e-18;       /* -1/19! */
-  ps = fma(ps, z, 2.8114572543455206e-15);   /*  1/17! */
-  ps = fma(ps, z, -7.6471637318198164e-13);  /* -1/15! */
-  ps = fma(ps, z, 1.6059043836821613e-10);   /*  1/13! */
-  ps = fma(ps, z, -2.5052108385441720e-08);  /* -1/11! */
-  ps = fma(ps, z, 2.7557319223985893e-06);   /*  1/9!  */
-  ps = fma(ps, z, -1.9841269841269841e-04);  /* -1/7!  */
-  ps = fma(ps, z, 8.3333333333333332e-03);   /*  1/5!  */
-  ps = fma(ps, z, -1.6666666666666666e-01);  /* -1/3!  */
+  double ps = GM_C(sin, 0);                  /* -1/19!, 1/17!, ..., -1/3! */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < 9; ++i) ps = fma(ps, z, GM_C(sin, i));
   const double s0 = fma(x * z, ps, x);
-  double pc = -1.5619206968586225e-16;       /* -1/18! */
-  pc = fma(pc, z, 4.7794773323873853e-14);   /*  1/16! */
-  pc = fma(pc, z, -1.1470745597729725e-11);  /* -1/14! */
-  pc = fma(pc, z, 2.0876756987868100e-09);   /*  1/12! */
-  pc = fma(pc, z, -2.7557319223985888e-07);  /* -1/10! */
-  pc = fma(pc, z, 2.4801587301587302e-05);   /*  1/8!  */
-  pc = fma(pc, z, -1.3888888888888889e-03);  /* -1/6!  */
-  pc = fma(pc, z, 4.1666666666666664e-02);   /*  1/4!  */
-  pc = fma(pc, z, -0.5);
+  double pc = GM_C(cos, 0);                  /* -1/18!, 1/16!, ..., -1/2! */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < 9; ++i) pc = fma(pc, z, GM_C(cos, i));
   const double c0 = fma(z, pc, 1.0);
   const long long n = (long long)nf;
   const int q = (int)(n & 3);
@@ -172,13 +213,11 @@ GM_HD double gm_atan(double x) {
   const double c = kf * 0.125;
   const double u = (t - c) / fma(t, c, 1.0);
   const double z = u * u;
-  double p = -6.6666666666666666e-02;        /* -1/15 */
-  p = fma(p, z, 7.6923076923076927e-02);     /*  1/13 */
-  p = fma(p, z, -9.0909090909090912e-02);    /* -1/11 */
-  p = fma(p, z, 1.1111111111111110e-01);     /*  1/9  */
-  p = fma(p, z, -1.4285714285714285e-01);    /* -1/7  */
-  p = fma(p, z, 2.0000000000000001e-01);     /*  1/5  */
-  p = fma(p, z, -3.3333333333333331e-01);    /* -1/3  */
+  double p = GM_C(atan, 0);                  /* -1/15, 1/13, ..., -1/3 */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < 7; ++i) p = fma(p, z, GM_C(atan, i));
   double a = gm_atan_tab((int)kf) + fma(u * z, p, u);
   if (inv) a = 1.57079632679489655800 - a;
   return x < 0.0 ? -a : a;

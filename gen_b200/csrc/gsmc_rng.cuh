@@ -24,23 +24,15 @@ enum { GSMC_STREAM_NORMAL = 0, GSMC_STREAM_UNIFORM = 1, GSMC_STREAM_RESAMPLE = 2
 
 struct PhiloxOut { uint64_t a, b; };
 
-__host__ __device__ __forceinline__ uint32_t gsmc_mulhi32(uint32_t x, uint32_t y) {
-#if defined(__CUDA_ARCH__)
-  return __umulhi(x, y);
-#else
-  return (uint32_t)(((uint64_t)x * y) >> 32);
-#endif
-}
-
 __host__ __device__ __forceinline__ PhiloxOut philox_call(uint64_t seed, uint64_t call, uint32_t t, uint32_t stream) {
   uint32_t c0 = (uint32_t)call, c1 = (uint32_t)(call >> 32), c2 = t, c3 = stream;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = gsmc_mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = gsmc_mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;     // one IMAD.WIDE.U32 each
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   PhiloxOut o;
@@ -54,7 +46,7 @@ __host__ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t cal
   const PhiloxOut o = philox_call(seed, call, t, GSMC_STREAM_NORMAL);
   const double u1 = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
   const double u2 = (double)(o.b >> 11) * 0x1p-53;
-  const double r = sqrt(-2.0 * gm_log(u1));
+  const double r = sqrt(-2.0 * gm_log_pos(u1));   // u1 in (0,1): no special cases
   double s, c;
   gm_sincospi(2.0 * u2, &s, &c);
   *z0 = r * c;
@@ -69,7 +61,7 @@ __host__ __device__ __forceinline__ void uniform_pair(uint64_t seed, uint64_t ca
 
 __host__ __device__ __forceinline__ uint64_t spacing_from_word(uint64_t w) {
   const double u = ((double)(w >> 11) + 0.5) * 0x1p-53;
-  return (uint64_t)floor(-gm_log(u) * 4294967296.0);
+  return (uint64_t)floor(-gm_log_pos(u) * 4294967296.0);
 }
 __host__ __device__ __forceinline__ void spacing_pair(uint64_t seed, uint64_t call, uint32_t rho, uint64_t* e0, uint64_t* e1) {
   const PhiloxOut o = philox_call(seed, call, rho, GSMC_STREAM_RESAMPLE);

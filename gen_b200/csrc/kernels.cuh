@@ -299,17 +299,33 @@ __device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, d
 __global__ void __launch_bounds__(1024) finalize_kernel(const LseTriple* partials, int nblk, DevScalars* ds,
                                                         int rank, int nranks, double ess_threshold,
                                                         double n_global, int* resampled_flag_out) {
-  __shared__ LseTriple sm[1024];
-  LseTriple t; t.m = -gm_inf(); t.s1 = 0.0; t.s2 = 0.0;
-  for (int b = threadIdx.x; b < nblk; b += 1024) t = lse_merge(t, partials[b]);
-  sm[threadIdx.x] = t;
+  __shared__ double sm[3][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // pass 1: global max of the block maxima
+  double m = -gm_inf();
+  for (int b = threadIdx.x; b < nblk; b += 1024) m = fmax(m, partials[b].m);
+  m = warp_max(m);
+  if (lane == 0) sm[0][warp] = m;
   __syncthreads();
-  for (int s = 512; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) sm[threadIdx.x] = lse_merge(sm[threadIdx.x], sm[threadIdx.x + s]);
-    __syncthreads();
+  double M = sm[0][0];
+#pragma unroll
+  for (int w = 1; w < 32; ++w) M = fmax(M, sm[0][w]);
+  // pass 2: rescaled sums, one exp per partial, fixed summation order (deterministic)
+  double a1 = 0.0, a2 = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 1024) {
+    const LseTriple p = partials[b];
+    const double e = (M > -gm_inf()) ? gm_exp(p.m - M) : 1.0;
+    a1 += p.s1 * e;
+    a2 += p.s2 * (e * e);
   }
+  a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) { sm[1][warp] = a1; sm[2][warp] = a2; }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    ds->triples[rank] = sm[0];
+    double t1 = 0.0, t2 = 0.0;
+    for (int w = 0; w < 32; ++w) { t1 += sm[1][w]; t2 += sm[2][w]; }
+    LseTriple tr; tr.m = M; tr.s1 = t1; tr.s2 = t2;
+    ds->triples[rank] = tr;
     if (nranks == 1) combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out);
   }
 }
@@ -516,14 +532,37 @@ __device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevSca
   return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
 }
 
-// Sorted mode. Tile b of this rank handles thresholds k_first + b*TILE + [0, TILE) and writes
-// anc[out_first + b*TILE + ...]. T_k = floor(S_k C_N / S_tot);  anc = min{i : C_i > T_k}
-// <=> C_i * S_tot > S_k * C_N (128-bit).
+// Sorted mode, step 1: ancestor word of the FIRST threshold of every tile (one thread per tile, all
+// binary searches in flight at once), win[b] for b in [0, nt]; win[nt] closes the last tile.
+__global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
+                                                               const DevScalars* ds, const uint64_t* tile_prefix, int nt,
+                                                               uint32_t* win, int conditional) {
+  if (conditional && !ds->do_resample) return;
+  const int b = blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  if (b > nt) return;
+  const uint64_t m_draws = ds->n_draws;
+  const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
+  if (kt >= m_draws) { win[b] = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1); return; }
+  uint64_t S = 0;
+  for (int r = 0; r < rank; ++r) S += ds->spacing_rank_total[r];
+  S += (b == nt) ? ds->spacing_rank_total[rank] : tile_prefix[b];
+  uint64_t e0, e1;
+  spacing_pair(seed, kt >> 1, ds->rho, &e0, &e1);     // kt is a multiple of the tile size: even element
+  S += e0;
+  const uint64_t cn = ds->cdf_total;
+  win[b] = search_global(v, ds, ds->spacing_total, __umul64hi(S, cn), S * cn);
+}
+
+// Sorted mode, step 2. Tile b of this rank handles thresholds k_first + b*TILE + [0, TILE) and writes
+// anc[b*TILE + ...]. T_k = floor(S_k C_N / S_tot);  anc = min{i : C_i > T_k}  <=>  C_i * S_tot > S_k * C_N
+// (128-bit). The CDF window [win[b], win[b+1]] the tile can map to is staged in shared memory.
+#define GSMC_WIN_CAP 3072
 __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
                                                                    const DevScalars* ds, const uint64_t* tile_prefix,
-                                                                   uint32_t* anc, int64_t n_out, int det_offset, int conditional) {
+                                                                   const uint32_t* win, uint32_t* anc, int64_t n_out,
+                                                                   int det_offset, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
-  __shared__ uint32_t win[2];
+  __shared__ uint64_t cwin[GSMC_WIN_CAP];
   if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws;
   const uint64_t kt = k_first + (uint64_t)blockIdx.x * GSMC_TILE;
@@ -537,7 +576,6 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
   for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
   uint64_t S = base + tile_prefix[blockIdx.x] + block_scan_u64(tsum, sm, &tot) - tsum;
   const uint64_t st = ds->spacing_total, cn = ds->cdf_total;
-  // window of the tile: ancestors of its first and last threshold
   uint32_t a[4];
   bool have[4];
   uint64_t chi[4], clo[4];
@@ -547,46 +585,49 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
     have[j] = k + j < m_draws;
     chi[j] = __umul64hi(S, cn); clo[j] = S * cn;
   }
-  const uint64_t last_k = (kt + GSMC_TILE <= m_draws ? kt + GSMC_TILE : m_draws) - 1;
-  if (threadIdx.x == 0) win[0] = search_global(v, ds, st, chi[0], clo[0]);
-  if (k <= last_k && last_k < k + 4) win[1] = search_global(v, ds, st, chi[last_k - k], clo[last_k - k]);
-  __syncthreads();
-  const uint32_t w0 = win[0], w1 = win[1];
-  if ((w0 >> GSMC_ANC_RANK_SHIFT) == (w1 >> GSMC_ANC_RANK_SHIFT)) {
-    // common case: the whole tile maps into one rank's segment; search only inside the window
-    const int r = (int)(w0 >> GSMC_ANC_RANK_SHIFT);
+  const uint32_t w0 = win[blockIdx.x], w1 = win[blockIdx.x + 1];
+  const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT);
+  const int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK), hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
+  if (r0 == (int)(w1 >> GSMC_ANC_RANK_SHIFT) && hi - lo + 1 <= GSMC_WIN_CAP) {
+    // common case: the whole tile maps into one rank's segment and the window fits in shared memory
     uint64_t off = 0;
-    for (int q = 0; q < r; ++q) off += ds->cdf_rank_total[q];
-    const uint64_t* seg = v.seg[r];
-    int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK);
-    const int64_t hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
+    for (int q = 0; q < r0; ++q) off += ds->cdf_rank_total[q];
+    const uint64_t* seg = v.seg[r0];
+    const int len = (int)(hi - lo + 1);
+    for (int j = threadIdx.x; j < len; j += GSMC_BLOCK) cwin[j] = off + __ldg(seg + lo + j);
+    __syncthreads();
+    int pos = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (!have[j]) { a[j] = 0; continue; }
-      if (j == 0) {
-        int64_t pos0 = seg_upper(seg, off, lo, hi, st, chi[0], clo[0]);
-        if (pos0 > hi) pos0 = hi;
-        lo = pos0;
-        a[0] = ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)pos0;
-        continue;
+      int l, h;
+      if (j == 0) { l = 0; h = len; }
+      else {
+        // gallop from the previous ancestor: thresholds are sorted, so ancestors are monotone
+        int step = 1;
+        l = pos; h = pos;
+        while (h < len && !mul_gt(cwin[h], st, chi[j], clo[j])) { l = h + 1; h += step; step <<= 1; }
+        if (h > len) h = len;
       }
-      // gallop from the previous ancestor: thresholds are sorted, so ancestors are monotone
-      int64_t step = 1, l = lo, h = lo;
-      while (h <= hi && !mul_gt(off + __ldg(seg + h), st, chi[j], clo[j])) { l = h + 1; h += step; step <<= 1; }
-      if (h > hi) h = hi;
-      int64_t pos = (l <= h) ? seg_upper(seg, off, l, h, st, chi[j], clo[j]) : l;
-      if (pos > hi) pos = hi;
-      lo = pos;
-      a[j] = ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)pos;
+      while (l < h) {                                   // min{p in [l, h) : pred(p)}, else h
+        const int mid = (l + h) >> 1;
+        if (mul_gt(cwin[mid], st, chi[j], clo[j])) h = mid; else l = mid + 1;
+      }
+      pos = l < len ? l : len - 1;
+      a[j] = ((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pos);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, st, chi[j], clo[j]) : 0;
   }
-  // output slot of threshold k: out_first + (k - k_first) [+ n_det for the residual scheme]
+  // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
   const int64_t o = (int64_t)(k - k_first) + (det_offset ? (int64_t)ds->n_det : 0);
+  if (!det_offset && have[3] && o + 3 < n_out) {
+    *reinterpret_cast<uint4*>(anc + o) = make_uint4(a[0], a[1], a[2], a[3]);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) if (have[j] && o + j < n_out) anc[o + j] = a[j];
+    for (int j = 0; j < 4; ++j) if (have[j] && o + j < n_out) anc[o + j] = a[j];
+  }
 }
 
 // iid mode (replay / sample_unweighted): T_j = floor(floor(u_j 2^53) * C_N / 2^53)

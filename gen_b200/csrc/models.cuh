@@ -18,30 +18,39 @@
 #define GSMC_MAX_INLINE_OBS 16
 #define GSMC_HMM_MAX_K 16
 
+struct NormC { double two_var, half_log, inv_two_var; };   // hoisted constants of one normal logpdf
+
 struct ModelArgs {
   double p[GSMC_MAX_INLINE_PARAMS];   // model parameters (prefix; all of them live at p_dev too)
   double obs[GSMC_MAX_INLINE_OBS];    // this step's observations (prefix; obs_dev when longer)
   double pp[8];                       // proposal parameters
-  double k[24];                       // per-launch derived constants (prepare())
+  double k[16];                       // per-launch derived constants (prepare())
+  NormC nc[6];                        // per-launch hoisted normal-logpdf constants (prepare())
   const double* p_dev;
   const double* obs_dev;
   int n_p, n_obs;
 };
 
 // normal.jl:56-60 with var = std*std hoisted:  -(diff*diff)/(2.0*var) - 0.5*log(2.0*pi*var)
-struct NormC { double two_var, half_log; };
 GM_HD NormC make_normc(double std) {
   NormC c;
   const double var = std * std;
   c.two_var = 2.0 * var;
   c.half_log = 0.5 * gm_log(2.0 * GM_PI * var);
+  c.inv_two_var = gm_safe_recip(c.two_var);
   return c;
 }
+// the division by the launch-invariant 2*var is done with gm_div_inv: same bits as `/`, 3 instructions
 GM_HD double logpdf_normal_c(double x, double mu, NormC c) {
   const double diff = x - mu;
-  return -(diff * diff) / c.two_var - c.half_log;
+  return gm_div_inv(-(diff * diff), c.two_var, c.inv_two_var) - c.half_log;
 }
-GM_HD double logpdf_normal(double x, double mu, double std) { return logpdf_normal_c(x, mu, make_normc(std)); }
+// per-particle std (nothing to hoist): the literal formula
+GM_HD double logpdf_normal(double x, double mu, double std) {
+  const double var = std * std;
+  const double diff = x - mu;
+  return -(diff * diff) / (2.0 * var) - 0.5 * gm_log(2.0 * GM_PI * var);
+}
 GM_HD double random_normal(double mu, double std, double z) { return mu + std * z; }   // normal.jl:96
 
 // ---------------------------------------------------------------------------------------------
@@ -59,14 +68,13 @@ struct LgssmModel {
   static void prepare(ModelArgs& a, bool init, int prop) {
     const double* p = a.p;
     const double sd = init ? p[1] : p[4], c = p[5], r = p[6];
-    const NormC on = make_normc(r), ln = make_normc(sd);
-    a.k[0] = sd; a.k[1] = on.two_var; a.k[2] = on.half_log; a.k[3] = ln.two_var; a.k[4] = ln.half_log;
+    a.k[0] = sd; a.nc[0] = make_normc(r); a.nc[1] = make_normc(sd);
     if (prop == 1) {
       const double prec = 1.0 / (sd * sd) + (c * c) / (r * r);
       const double var = 1.0 / prec;
       const double sdq = sqrt(var);
-      const NormC qn = make_normc(sdq);
-      a.k[5] = var; a.k[6] = sdq; a.k[7] = qn.two_var; a.k[8] = qn.half_log;
+      a.nc[2] = make_normc(sdq);
+      a.k[5] = var; a.k[6] = sdq;
       a.k[9] = sd * sd; a.k[10] = r * r;
     }
   }
@@ -78,7 +86,7 @@ struct LgssmModel {
     const double* p = a.p;
     const double mean = INIT ? p[0] : prev[0] * p[2] + p[3];
     const double y = a.obs[0], c = p[5];
-    const NormC on = {a.k[1], a.k[2]};
+    const NormC on = a.nc[0];
     if (PROP == 0) {
       const double x = random_normal(mean, a.k[0], z[0]);
       double w = 0.0;
@@ -88,7 +96,7 @@ struct LgssmModel {
     } else {
       const double mu = a.k[5] * (mean / a.k[9] + (c * y) / a.k[10]);
       const double x = random_normal(mu, a.k[6], z[0]);
-      const NormC qn = {a.k[7], a.k[8]}, ln = {a.k[3], a.k[4]};
+      const NormC qn = a.nc[2], ln = a.nc[1];
       const double q_score = logpdf_normal_c(x, mu, qn);
       double mw = 0.0;
       mw += logpdf_normal_c(x, mean, ln);
@@ -139,8 +147,7 @@ struct BearingsModel {
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs& a, bool, int) {
     const double sw = a.p[8], st = a.p[9];
-    const NormC tn = make_normc(st), wn = make_normc(sw);
-    a.k[0] = tn.two_var; a.k[1] = tn.half_log; a.k[2] = wn.two_var; a.k[3] = wn.half_log;
+    a.nc[0] = make_normc(st); a.nc[1] = make_normc(sw);
     a.k[4] = sw * sw; a.k[5] = st * st;
   }
   template <bool INIT, int PROP>
@@ -149,7 +156,7 @@ struct BearingsModel {
   __device__ __forceinline__ static double particle(const ModelArgs& a, const double*, const double* sp,
                                                     const double* z, const double*, double* out) {
     const double* p = a.p;
-    const NormC tn = {a.k[0], a.k[1]};
+    const NormC tn = a.nc[0];
     const double obs = a.obs[0];
     if (INIT) {
       const double x = random_normal(p[0], p[4], z[0]);
@@ -180,7 +187,7 @@ struct BearingsModel {
       wy = random_normal(my, sy, z[1]);
       q_score += logpdf_normal(wx, mx, sx);
       q_score += logpdf_normal(wy, my, sy);
-      const NormC wn = {a.k[2], a.k[3]};
+      const NormC wn = a.nc[1];
       mw += logpdf_normal_c(wx, 0.0, wn);
       mw += logpdf_normal_c(wy, 0.0, wn);
     }
@@ -277,12 +284,9 @@ struct RegressionModel {
   GM_HD static int nu(bool, int) { return 0; }
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs& a, bool, int prop) {
-    const NormC nn = make_normc(a.p[3]);
-    a.k[0] = nn.two_var; a.k[1] = nn.half_log;
+    a.nc[0] = make_normc(a.p[3]);
     if (prop == 1) {
-      const NormC a0 = make_normc(a.pp[1]), a1 = make_normc(a.pp[3]), b0 = make_normc(a.p[1]), b1 = make_normc(a.p[2]);
-      a.k[2] = a0.two_var; a.k[3] = a0.half_log; a.k[4] = a1.two_var; a.k[5] = a1.half_log;
-      a.k[6] = b0.two_var; a.k[7] = b0.half_log; a.k[8] = b1.two_var; a.k[9] = b1.half_log;
+      a.nc[1] = make_normc(a.pp[1]); a.nc[2] = make_normc(a.pp[3]); a.nc[3] = make_normc(a.p[1]); a.nc[4] = make_normc(a.p[2]);
     }
   }
   template <bool INIT, int PROP>
@@ -300,13 +304,13 @@ struct RegressionModel {
     } else {
       slope = random_normal(a.pp[0], a.pp[1], z[0]);
       intercept = random_normal(a.pp[2], a.pp[3], z[1]);
-      const NormC a0 = {a.k[2], a.k[3]}, a1 = {a.k[4], a.k[5]}, b0 = {a.k[6], a.k[7]}, b1 = {a.k[8], a.k[9]};
+      const NormC a0 = a.nc[1], a1 = a.nc[2], b0 = a.nc[3], b1 = a.nc[4];
       pw += logpdf_normal_c(slope, a.pp[0], a0);
       pw += logpdf_normal_c(intercept, a.pp[2], a1);
       mw += logpdf_normal_c(slope, 0.0, b0);
       mw += logpdf_normal_c(intercept, 0.0, b1);
     }
-    const NormC nn = {a.k[0], a.k[1]};
+    const NormC nn = a.nc[0];
     for (int i = 0; i < n; ++i) mw += logpdf_normal_c(__ldg(ys + i), slope * __ldg(xs + i) + intercept, nn);
     out[0] = slope; out[1] = intercept;
     return mw - pw;
@@ -321,12 +325,8 @@ struct NormalNormalModel {
   GM_HD static int nu(bool, int) { return 0; }
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs& a, bool, int prop) {
-    const NormC yn = make_normc(a.p[2]);
-    a.k[0] = yn.two_var; a.k[1] = yn.half_log;
-    if (prop == 1) {
-      const NormC qn = make_normc(a.pp[1]), xn = make_normc(a.p[1]);
-      a.k[2] = qn.two_var; a.k[3] = qn.half_log; a.k[4] = xn.two_var; a.k[5] = xn.half_log;
-    }
+    a.nc[0] = make_normc(a.p[2]);
+    if (prop == 1) { a.nc[1] = make_normc(a.pp[1]); a.nc[2] = make_normc(a.p[1]); }
   }
   template <bool INIT, int PROP>
   __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
@@ -338,11 +338,11 @@ struct NormalNormalModel {
       x = random_normal(a.p[0], a.p[1], z[0]);
     } else {
       x = random_normal(a.pp[0], a.pp[1], z[0]);
-      const NormC qn = {a.k[2], a.k[3]}, xn = {a.k[4], a.k[5]};
+      const NormC qn = a.nc[1], xn = a.nc[2];
       pw += logpdf_normal_c(x, a.pp[0], qn);
       mw += logpdf_normal_c(x, a.p[0], xn);
     }
-    const NormC yn = {a.k[0], a.k[1]};
+    const NormC yn = a.nc[0];
     mw += logpdf_normal_c(a.obs[0], x, yn);
     out[0] = x;
     return mw - pw;

@@ -94,6 +94,11 @@ class ParticleFilterState:
         self.T += 1
         self.observations.append(obs.copy())
 
+    def reset(self):
+        _lib.check(self.lib.gsmc_reset(self.handle), self.handle)
+        self.T = 0
+        self.observations = []
+
     def init(self, obs, proposal=None):
         self._propagate(self.lib.gsmc_init, obs, proposal)
 

@@ -76,10 +76,12 @@ typedef struct gsmc_stats {
   int64_t num_steps;         /* time steps in the traces (1 after init) */
   int64_t num_resamples;     /* resampling events so far */
   int64_t kernel_launches;   /* kernels launched by this handle so far */
-  /* per-kernel-class device time in ms and launch counts, filled while profiling is on */
-  double ms_propagate, ms_finalize, ms_scan, ms_spacings, ms_search, ms_other;
-  int64_t n_propagate, n_finalize, n_scan, n_spacings, n_search, n_other;
-  int64_t n_propagate_resampled;  /* propagate launches that gathered through ancestors */
+  /* per-kernel-class device time in ms and launch counts, filled while profiling is on.
+   * propagate = init/step launches that read the previous state directly; propagate_gather = step
+   * launches that read it through the ancestor column of a pending resample (per-call API only;
+   * gsmc_run_steps cannot tell them apart without a host round trip and books all as propagate). */
+  double ms_propagate, ms_propagate_gather, ms_finalize, ms_scan, ms_spacings, ms_search, ms_other;
+  int64_t n_propagate, n_propagate_gather, n_finalize, n_scan, n_spacings, n_search, n_other;
 } gsmc_stats;
 
 GSMC_API const char* gsmc_version(void);
@@ -90,12 +92,20 @@ GSMC_API const char* gsmc_last_error(gsmc_handle h);
  * params: model parameter vector in the catalogue layout. */
 GSMC_API int gsmc_create(const gsmc_config* cfg, const double* params, size_t n_params, gsmc_handle* out);
 GSMC_API void gsmc_destroy(gsmc_handle h);
+/* Back to the state right after gsmc_create (+ attach): no time steps, log_ml_est = 0, the resample
+ * event counter back to 0 so that a repeated run redraws the same Philox stream. Buffers are kept. */
+GSMC_API int gsmc_reset(gsmc_handle h);
 
-/* Multi-GPU (one process per GPU): rank 0 makes an id, every rank attaches before gsmc_init.
- * After attach the handle owns particles [rank*N/R, (rank+1)*N/R). No reference equivalent
- * (the reference is single-process); SURVEY.md section 8(e). */
+/* Multi-GPU (one process per GPU, NCCL over NVLink): rank 0 makes an id and hands it to every rank
+ * (the host does that, e.g. through torch.distributed); each rank creates one communicator and
+ * attaches its filters to it before gsmc_init. After attach the handle owns particles
+ * [rank*N/R, (rank+1)*N/R). No reference equivalent (the reference is single-process);
+ * SURVEY.md section 8(e). */
+typedef struct gsmc_comm_s* gsmc_comm;
 GSMC_API int gsmc_comm_unique_id(void* id_out, size_t nbytes /* >= 128 */);
-GSMC_API int gsmc_comm_attach(gsmc_handle h, const void* unique_id, size_t nbytes, int rank, int nranks);
+GSMC_API int gsmc_comm_create(const void* unique_id, size_t nbytes, int rank, int nranks, int device, gsmc_comm* out);
+GSMC_API void gsmc_comm_destroy(gsmc_comm c);
+GSMC_API int gsmc_comm_attach(gsmc_handle h, gsmc_comm c);
 
 /* Replay mode: the draws the next init/step/maybe_resample/sample_unweighted call consumes,
  * instead of Philox (this rank's slice). normals: n_local*n_norm values ordered

@@ -43,6 +43,28 @@ double orc_atan2(double y, double x) { return gm_atan2(y, x); }
 void orc_sincospi(double t, double* s, double* c) { gm_sincospi(t, s, c); }
 #endif
 
+/* checks of gsmc_math.h helpers the device uses (tests/test_math.py) */
+double orc_div_inv(double x, double c) { return gm_div_inv(x, c, gm_safe_recip(c)); }
+double orc_log_pos(double x) { return gm_log_pos(x); }
+/* number of operand pairs (adversarial mantissas included) where the Markstein sequence differs from x / c */
+int64_t orc_div_inv_mismatches(uint64_t seed, int64_t n) {
+  uint64_t s = seed ? seed : 88172645463325252ULL;
+  int64_t bad = 0;
+  for (int64_t it = 0; it < n; ++it) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17; uint64_t mc = s;
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17; uint64_t mx = s;
+    int mode = (int)(it & 7);
+    if (mode == 0) mc |= 0x000fffffffff0000ULL;
+    if (mode == 1) mc &= 0xfff0000000000fffULL;
+    if (mode == 2) mc |= 0x000fffffffffffffULL;
+    double c = gm_from_bits((mc & 0x000fffffffffffffULL) | ((uint64_t)(1023 - 40 + (mc >> 57)) << 52));
+    double x = gm_from_bits((mx & 0x000fffffffffffffULL) | ((uint64_t)(1023 - 60 + (mx >> 57)) << 52));
+    if (mx & (1ULL << 56)) x = -x;
+    if (gm_to_bits(orc_div_inv(x, c)) != gm_to_bits(x / c)) ++bad;
+  }
+  return bad;
+}
+
 /* ------------------------------------------------------------------------- */
 /* Philox4x32-10 (Salmon et al. 2011), written out independently of the       */
 /* product's device version; pinned by the Random123 known-answer vectors.    */

@@ -56,6 +56,9 @@ void orc_fill_normals(uint64_t seed, uint32_t t, uint64_t first, uint64_t count,
 void orc_fill_uniforms(uint64_t seed, uint32_t t, uint32_t stream, uint64_t first, uint64_t count, double* out);
 /* fixed-point Exp(1) spacings E_j = floor(-log(u_j) * 2^32), j in [first, first+count) of resample event rho */
 void orc_fill_spacings(uint64_t seed, uint32_t rho, uint64_t first, uint64_t count, uint64_t* out);
+double orc_div_inv(double x, double c);
+double orc_log_pos(double x);
+int64_t orc_div_inv_mismatches(uint64_t seed, int64_t n);
 double orc_exp(double x);
 double orc_log(double x);
 double orc_atan2(double y, double x);

@@ -47,6 +47,11 @@ class Oracle:
         L.orc_last_error.restype = C.c_char_p
         L.orc_exp.restype = L.orc_log.restype = C.c_double
         L.orc_exp.argtypes = L.orc_log.argtypes = [C.c_double]
+        L.orc_div_inv.restype = L.orc_log_pos.restype = C.c_double
+        L.orc_div_inv.argtypes = [C.c_double, C.c_double]
+        L.orc_log_pos.argtypes = [C.c_double]
+        L.orc_div_inv_mismatches.restype = C.c_int64
+        L.orc_div_inv_mismatches.argtypes = [C.c_uint64, C.c_int64]
         L.orc_atan2.restype = C.c_double
         L.orc_atan2.argtypes = [C.c_double, C.c_double]
         L.orc_sincospi.argtypes = [C.c_double, _dp, _dp]

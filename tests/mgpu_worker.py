@@ -1,0 +1,76 @@
+"""Worker of tests/test_multigpu.py: one process per GPU (torchrun), NCCL inside libgensmc.so.
+Every rank runs the full CPU oracle and compares its own shard bit for bit."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import gen_b200 as g
+    from gen_b200.distributed import Communicator
+    from oracle import closed_forms as cf
+    from oracle import oracle as O
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = Communicator(dist, rank, world, device=local)
+    orc = O.Oracle()
+
+    def bits(a):
+        return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+    for fam, model, params, ys, prop in (
+            (O.LGSSM, g.LinearGaussianSSM(0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0), [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0],
+             cf.simulate_lgssm(16, [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0], 3), 0),
+            (O.BEARINGS, g.BearingsOnly(), cf.BEARINGS_PARAMS, cf.simulate_bearings(16), 1)):
+        N, T = 1024 * 16 * world, 12
+        st = g.ParticleFilterState(model, N, seed=5, keep_history=True, history_capacity=T, device=local, comm=comm)
+        n, first = st.num_local, st.first_global
+        assert n == N // world and first == rank * n
+        pf = orc.particle_filter(fam, params, N, seed=5, keep_history=True)
+        proposal = model.custom_proposal() if prop else None
+        st.init([ys[0]], proposal)
+        pf.init([ys[0]], proposal=prop)
+        sl = slice(first, first + n)
+        n_res = 0
+        for t in range(1, T):
+            dg, do = st.maybe_resample(N * 0.8), pf.maybe_resample(N * 0.8)
+            assert dg == do, (t, st.last_ess, pf.last_ess)
+            assert abs(st.last_ess - pf.last_ess) <= 1e-10 * pf.last_ess
+            if dg:
+                n_res += 1
+                assert np.array_equal(st.ancestors(), pf.parents()[sl]), "ancestors differ at t=%d" % t
+                assert np.array_equal(bits(st.state()), bits(pf.state()[:, sl])), "gathered state differs at t=%d" % t
+            st.step([ys[t]], proposal)
+            pf.step([ys[t]], proposal=prop)
+            assert np.array_equal(bits(st.log_weights()), bits(pf.log_weights()[sl])), "log weights differ at t=%d" % t
+        assert n_res >= 2
+        assert np.array_equal(bits(st.state()), bits(pf.state()[:, sl]))
+        a, b = st.log_ml_estimate(), pf.log_ml_estimate()
+        assert abs(a - b) <= 1e-11 * abs(b), (a, b)
+        for t in (1, T // 2, T):
+            assert np.array_equal(bits(st.state(t)), bits(pf.history(t)[:, sl])), "history differs at t=%d" % t
+        # the sync-free loop gives the same answer
+        st2 = g.ParticleFilterState(model, N, seed=5, keep_history=False, device=local, comm=comm)
+        st2.init([ys[0]], proposal)
+        st2.run_steps(ys[1:T], N * 0.8, proposal)
+        assert st2.log_ml_estimate() == a
+        assert np.array_equal(bits(st2.log_weights()), bits(st.log_weights()))
+        st.close()
+        st2.close()
+        dist.barrier()
+        if rank == 0:
+            print("family %d ok on %d ranks: log_ml %.12f, %d resamples" % (fam, world, a, n_res), flush=True)
+    comm.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

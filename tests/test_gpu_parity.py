@@ -205,29 +205,41 @@ def test_hmm_reference_test_case(gpu, orc, prop):
         state = g.initialize_particle_filter(model, (1,), g.choicemap(("x_init", obs_x[0])), model.custom_proposal(), (obs_x[0],), N, seed=0)
     else:
         state = g.initialize_particle_filter(model, (1,), g.choicemap(("x_init", obs_x[0])), N, seed=0)
-    pf = orc.particle_filter(O.HMM, cf.hmm_params(), N, seed=0)
+    pf = orc.particle_filter(O.HMM, cf.hmm_params(), N, seed=0, keep_history=True)
     pf.init([obs_x[0]], proposal=prop)
     argdiffs = (g.UnknownChange(),)
+    in_step = True          # GPU and oracle still hold bit-identical particle sets
     for T in range(2, len(obs_x) + 1):
         dg = g.maybe_resample_b(state, ess_threshold=N)
         do = pf.maybe_resample(N)
-        assert dg == do
+        if dg != do:
+            # Under the locally optimal proposal all weights are equal up to rounding, ESS = N up to
+            # rounding, and `ess < N` (threshold = N as in the reference test) is a tie that the
+            # reference itself decides by summation order. Either decision is valid; the two runs are
+            # then only compared statistically.
+            assert prop == 1 and abs(state.last_ess - N) < 1e-6 and abs(pf.last_ess - N) < 1e-6
+            in_step = False
         observations = g.choicemap((("chain", T - 1, "x"), obs_x[T - 1]))
         if prop:
             g.particle_filter_step_b(state, (T,), argdiffs, observations, model.custom_proposal(), (T, obs_x[T - 1]))
         else:
             g.particle_filter_step_b(state, (T,), argdiffs, observations)
         pf.step([obs_x[T - 1]], proposal=prop)
+        if in_step:
+            assert same_bits(g.get_log_weights(state), pf.log_weights())
     expected = math.log(cf.hmm_forward_alg(cf.HMM_PRIOR, cf.HMM_EMISSION, cf.HMM_TRANSITION, obs_x))
     assert expected == pytest.approx(cf.HMM_LOG_ML, abs=1e-12)
     actual = g.log_ml_estimate(state)
     assert abs(actual - expected) < 0.01                      # the reference's own bar
-    assert actual == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    assert abs(pf.log_ml_estimate() - expected) < 0.01
+    if in_step:
+        assert actual == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
     tr = g.get_traces(state)[0]
     ch = tr.get_choices()
     assert ch["x_init"] == obs_x[0] and ch[("chain", 3, "x")] == obs_x[3]
     assert ch["z_init"] in (1, 2, 3) and ch[("chain", 2, "z")] in (1, 2, 3)
-    assert int(pf.history(1)[0, 0]) == ch["z_init"]
+    if in_step:
+        assert int(pf.history(1)[0, 0]) == ch["z_init"]
 
 
 def test_importance_sampling_matches_oracle(gpu, orc):

@@ -45,3 +45,20 @@ def test_box_muller_normals_are_standard(orc):
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
     e = orc.spacings(3, 0, 0, 200000).astype(np.float64) / 2 ** 32
     assert abs(e.mean() - 1) < 0.01 and abs(e.var() - 1) < 0.03
+
+
+def test_division_by_invariant_is_correctly_rounded(orc):
+    """gm_div_inv (Markstein sequence, used for -(diff^2)/(2 var) with a launch-invariant variance)
+    must give the bits of the IEEE division the reference formula performs (normal.jl:59)."""
+    assert orc.L.orc_div_inv_mismatches(1, 10_000_000) == 0
+    assert orc.L.orc_div_inv_mismatches(987654321, 10_000_000) == 0
+    for x, c in ((0.0, 2.0), (-0.0, 2.0), (1e-300, 3.0), (-1e300, 7.0), (math.inf, 2.0), (1.0, 1e-200), (1.0, 1e200)):
+        got, want = orc.L.orc_div_inv(x, c), x / c
+        assert (got == want and math.copysign(1, got) == math.copysign(1, want)) or (math.isnan(got) and math.isnan(want))
+    assert math.isnan(orc.L.orc_div_inv(math.nan, 2.0))
+
+
+def test_log_fast_path_has_the_same_bits(orc):
+    rng = np.random.default_rng(3)
+    for x in np.concatenate([rng.random(20000), np.exp(rng.uniform(-600, 600, 20000)), [2.0 ** -53 * 0.5, 1.0 - 2.0 ** -53]]):
+        assert orc.L.orc_log_pos(float(x)) == orc.L.orc_log(float(x))
