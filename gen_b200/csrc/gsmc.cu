@@ -299,6 +299,7 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   g.n = f->n; g.stride = f->n_pad; g.first_global = (uint64_t)f->first; g.seed = f->cfg.seed;
   g.t = (uint32_t)new_step;
   g.use_anc = use_anc ? 1 : 0;
+  g.rank = f->rank;
   g.zrep = f->zrep_n ? f->d_zrep : nullptr;
   g.urep = f->urep_n ? f->d_urep : nullptr;
   const int nz = Model::nz(INIT, PROP), nu = Model::nu(INIT, PROP);

@@ -132,6 +132,7 @@ struct PropArgs {
   uint64_t seed;
   uint32_t t;                        // 1-based time index of the step being produced
   int use_anc;                       // 0: read cur directly; 1: consult *resampled_flag
+  int rank;                          // this rank: cur[rank] is the local column
   const double* zrep;                // replay normals [n][nz] or NULL
   const double* urep;                // replay uniforms [n][nu] or NULL
 };
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Re
       } else {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          const Real2 x = *reinterpret_cast<const Real2*>(g.cur[0] + d * g.stride + i);
+          const Real2 x = *reinterpret_cast<const Real2*>(g.cur[g.rank] + d * g.stride + i);
           prev0[d] = (double)x.x; prev1[d] = (double)x.y;
         }
         const Real2 l = *reinterpret_cast<const Real2*>(g.lw + i);

@@ -26,6 +26,11 @@ def main():
     def bits(a):
         return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
+    def same(a, b, what):
+        a, b = bits(a).reshape(-1), bits(b).reshape(-1)
+        bad = np.nonzero(a != b)[0]
+        assert bad.size == 0, "[rank %d] %s: %d of %d values differ, first at %s" % (rank, what, bad.size, a.size, bad[:8])
+
     for fam, model, params, ys, prop in (
             (O.LGSSM, g.LinearGaussianSSM(0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0), [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0],
              cf.simulate_lgssm(16, [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0], 3), 0),
@@ -39,6 +44,8 @@ def main():
         st.init([ys[0]], proposal)
         pf.init([ys[0]], proposal=prop)
         sl = slice(first, first + n)
+        same(st.log_weights(), pf.log_weights()[sl], "init log weights")
+        same(st.state(), pf.state()[:, sl], "init state")
         n_res = 0
         for t in range(1, T):
             dg, do = st.maybe_resample(N * 0.8), pf.maybe_resample(N * 0.8)
@@ -47,10 +54,11 @@ def main():
             if dg:
                 n_res += 1
                 assert np.array_equal(st.ancestors(), pf.parents()[sl]), "ancestors differ at t=%d" % t
-                assert np.array_equal(bits(st.state()), bits(pf.state()[:, sl])), "gathered state differs at t=%d" % t
+                same(st.state(), pf.state()[:, sl], "gathered state at t=%d" % t)
             st.step([ys[t]], proposal)
             pf.step([ys[t]], proposal=prop)
-            assert np.array_equal(bits(st.log_weights()), bits(pf.log_weights()[sl])), "log weights differ at t=%d" % t
+            same(st.state(), pf.state()[:, sl], "state after step t=%d (resampled=%s)" % (t, dg))
+            same(st.log_weights(), pf.log_weights()[sl], "log weights after step t=%d (resampled=%s)" % (t, dg))
         assert n_res >= 2
         assert np.array_equal(bits(st.state()), bits(pf.state()[:, sl]))
         a, b = st.log_ml_estimate(), pf.log_ml_estimate()
