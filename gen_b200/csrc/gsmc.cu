@@ -101,7 +101,8 @@ struct gsmc_filter {
   int rank = 0, nranks = 1;
   NcclComm comm = nullptr;
   int64_t N = 0, n = 0, n_pad = 0, first = 0;   // global count, local count, padded local, first global index
-  int n_tiles = 0;
+  int n_tiles = 0;       // 1024-particle tiles of the scan / search kernels
+  int n_partials = 0;    // blocks (= logsumexp partials) of the last propagate launch
   std::vector<double> params;
   double* d_params = nullptr;
   double* d_obs = nullptr;
@@ -226,7 +227,7 @@ static int expected_obs(const gsmc_filter* f) {
 // ------------------------------------------------------------------------------------------------
 static int alloc_buffers(gsmc_filter* f) {
   const size_t rs = real_size(f);
-  f->n_pad = (f->n + GSMC_TILE - 1) / GSMC_TILE * GSMC_TILE;
+  f->n_pad = (f->n + GSMC_PAD - 1) / GSMC_PAD * GSMC_PAD;
   f->n_tiles = (int)(f->n_pad / GSMC_TILE);
   if (f->n > (int64_t)GSMC_ANC_INDEX_MASK) return fail(GSMC_E_BADARG, "at most 2^28-1 particles per GPU");
   f->cap = f->cfg.keep_history ? (f->cfg.history_capacity > 0 ? f->cfg.history_capacity : 128) : 2;
@@ -309,7 +310,8 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   if (!nz) g.zrep = nullptr;
   {
     ProfScope ps(f, (use_anc && f->pending) ? KC_PROPAGATE_GATHER : KC_PROPAGATE);
-    propagate_kernel<Model, Real, INIT, PROP><<<f->n_tiles, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream>>>(g, a);
+    f->n_partials = (int)(f->n_pad / PropTile<Model>::TILE);
+    propagate_kernel<Model, Real, INIT, PROP><<<f->n_partials, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream>>>(g, a);
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -379,7 +381,7 @@ static int launch_finalize(gsmc_filter* f, double ess_threshold) {
   int* flag = ess_threshold >= 0.0 ? f->resampled + ((f->T + 1) % f->flag_mod) : nullptr;
   {
     ProfScope ps(f, KC_FINALIZE);
-    finalize_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_tiles, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag);
+    finalize_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_partials, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag);
   }
   CK(cudaGetLastError());
   if (f->nranks > 1) {
@@ -583,7 +585,7 @@ GSMC_API int gsmc_comm_attach(gsmc_handle f, gsmc_comm c) {
   if (f->T != 0 || f->state_slab) return fail(GSMC_E_BADARG, "attach must precede gsmc_init");
   if (c->device != f->device) return fail(GSMC_E_BADARG, "communicator lives on device %d, filter on device %d", c->device, f->device);
   const int rank = c->rank, nranks = c->nranks;
-  if (f->N % ((int64_t)nranks * GSMC_TILE) != 0) return fail(GSMC_E_BADARG, "num_particles must be a multiple of %d * nranks", GSMC_TILE);
+  if (f->N % ((int64_t)nranks * GSMC_PAD) != 0) return fail(GSMC_E_BADARG, "num_particles must be a multiple of %d * nranks", GSMC_PAD);
   CK(cudaSetDevice(f->device));
   f->rank = rank; f->nranks = nranks; f->comm = c->comm;
   f->n = f->N / nranks; f->first = f->n * rank;

@@ -106,6 +106,24 @@ GM_HD double gm_exp(double x) {
   return (p * gm_pow2(k1)) * gm_pow2(k2);
 }
 
+// Same bits as gm_exp(x) for x <= 0 (finite or -inf); no overflow/NaN branches and the 2^k scaling
+// is one integer add on the exponent field (the result is normal or flushed to 0, never subnormal).
+// Used for exp(lw - max): logsumexp partials and the integer weights of the resampler.
+GM_HD double gm_exp_nonpos(double x) {
+  const double xc = x < -708.3964185322641 ? -708.0 : x;
+  const double kf = floor(xc * GM_INV_LN2 + 0.5);
+  double r = fma(-kf, GM_LN2_HI, xc);
+  r = fma(-kf, GM_LN2_LO, r);
+  double p = GM_C(exp, 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 1; i < 14; ++i) p = fma(p, r, GM_C(exp, i));
+  const long long k = (long long)kf;
+  const double v = gm_from_bits(gm_to_bits(p) + ((uint64_t)k << 52));
+  return x < -708.3964185322641 ? 0.0 : v;
+}
+
 // log(x). x = 2^e * m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = (m-1)/(m+1).
 // gm_log_core: x positive, finite and normal (no checks); e0 = exponent bias already applied.
 GM_HD double gm_log_core(uint64_t b, int e0) {
@@ -180,11 +198,12 @@ GM_HD void gm_sincospi(double t, double* sn, double* cs) {
   const double c0 = fma(z, pc, 1.0);
   const long long n = (long long)nf;
   const int q = (int)(n & 3);
-  double so, co;
-  if (q == 0) { so = s0; co = c0; }
-  else if (q == 1) { so = c0; co = -s0; }
-  else if (q == 2) { so = -s0; co = -c0; }
-  else { so = -c0; co = s0; }
+  // q=0: (s0, c0)  q=1: (c0, -s0)  q=2: (-s0, -c0)  q=3: (-c0, s0) -- selects, no divergent branches
+  const int swap = (q & 1) != 0;
+  double so = swap ? c0 : s0;
+  double co = swap ? s0 : c0;
+  so = (q & 2) ? -so : so;
+  co = ((q + 1) & 2) ? -co : co;
   *sn = so; *cs = co;
 }
 

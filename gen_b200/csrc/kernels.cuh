@@ -21,10 +21,12 @@
 #include <cuda_runtime.h>
 #include "gsmc_math.h"
 #include "gsmc_rng.cuh"
+#include "gsmc_fixed.h"
 #include "models.cuh"
 
 #define GSMC_BLOCK 256
-#define GSMC_TILE 1024            // particles (or thresholds) per block
+#define GSMC_TILE 1024            // particles (or thresholds) per block of the scan / search kernels
+#define GSMC_PAD 2048             // local columns are padded to this many particles
 #define GSMC_MAX_RANKS 8
 #define GSMC_ANC_RANK_SHIFT 28    // ancestor word = (owner rank << 28) | local index
 #define GSMC_ANC_INDEX_MASK 0x0fffffffu
@@ -44,6 +46,7 @@ struct DevScalars {
   uint64_t n_det;           // residual scheme: number of deterministic copies
   uint64_t n_draws;         // M: number of multinomial draws of this event
   double resid_scale;       // residual scheme: N * 2^32 / C_N
+  double thr_ratio, thr_inv;  // (double)C_N / (double)S_tot and 1 / (double)S_tot for muldiv_floor
   LseTriple triples[GSMC_MAX_RANKS];
   uint64_t cdf_rank_total[GSMC_MAX_RANKS];      // per-rank integer weight totals (allgathered)
   uint64_t spacing_rank_total[GSMC_MAX_RANKS];  // per-rank spacing totals (allgathered)
@@ -137,10 +140,17 @@ struct PropArgs {
   const double* urep;                // replay uniforms [n][nu] or NULL
 };
 
+// pairs of particles per thread: 4 (2048-particle tile) for 1-2 column models, 2 for wider states
+template <class Model> struct PropTile {
+  static constexpr int PAIRS = Model::D <= 2 ? 4 : 2;
+  static constexpr int TILE = 2 * GSMC_BLOCK * PAIRS;
+};
+
 template <class Model, typename Real, bool INIT, int PROP>
 __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
   typedef typename Vec2T<Real>::type Real2;
   constexpr int D = Model::D;
+  constexpr int PAIRS = PropTile<Model>::PAIRS;
   constexpr int NZ_MAX = 4, NU_MAX = 1;
   extern __shared__ double dyn_sm[];
   __shared__ double red[3 * (GSMC_BLOCK / 32)];
@@ -151,11 +161,11 @@ __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Re
   const int nz = Model::nz(INIT, PROP), nu = Model::nu(INIT, PROP);
   const bool gather = !INIT && g.use_anc && (*g.resampled_flag != 0);
 
-  double lwv[4];        // up to 2 pairs per thread
-  bool val[4];
-  const int64_t tile0 = (int64_t)blockIdx.x * GSMC_TILE;
+  double lwv[2 * PAIRS];
+  bool val[2 * PAIRS];
+  const int64_t tile0 = (int64_t)blockIdx.x * PropTile<Model>::TILE;
 #pragma unroll
-  for (int u = 0; u < GSMC_TILE / (2 * GSMC_BLOCK); ++u) {
+  for (int u = 0; u < PAIRS; ++u) {
     const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK + 2 * threadIdx.x;   // first particle of the pair
     const bool v0 = i < g.n, v1 = i + 1 < g.n;
     val[2 * u] = v0; val[2 * u + 1] = v1;
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Re
   double m = -gm_inf();
   bool any_nan = false;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) if (val[j]) { if (lwv[j] != lwv[j]) any_nan = true; else m = fmax(m, lwv[j]); }
+  for (int j = 0; j < 2 * PAIRS; ++j) if (val[j]) { if (lwv[j] != lwv[j]) any_nan = true; else m = fmax(m, lwv[j]); }
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Re
   double s1 = 0.0, s2 = 0.0;
   if (bm > -gm_inf()) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) if (val[j]) { const double e = gm_exp(lwv[j] - bm); s1 += e; s2 += e * e; }
+    for (int j = 0; j < 2 * PAIRS; ++j) if (val[j]) { const double e = gm_exp_nonpos(lwv[j] - bm); s1 += e; s2 += e * e; }
   }
   if (any_nan) { s1 = gm_nan(); s2 = gm_nan(); }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
@@ -304,7 +314,8 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const LseTriple* partial
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // pass 1: global max of the block maxima
   double m = -gm_inf();
-  for (int b = threadIdx.x; b < nblk; b += 1024) m = fmax(m, partials[b].m);
+#pragma unroll 8
+  for (int b = threadIdx.x; b < nblk; b += 1024) m = fmax(m, __ldg(&partials[b].m));
   m = warp_max(m);
   if (lane == 0) sm[0][warp] = m;
   __syncthreads();
@@ -313,9 +324,10 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const LseTriple* partial
   for (int w = 1; w < 32; ++w) M = fmax(M, sm[0][w]);
   // pass 2: rescaled sums, one exp per partial, fixed summation order (deterministic)
   double a1 = 0.0, a2 = 0.0;
+#pragma unroll 4
   for (int b = threadIdx.x; b < nblk; b += 1024) {
     const LseTriple p = partials[b];
-    const double e = (M > -gm_inf()) ? gm_exp(p.m - M) : 1.0;
+    const double e = (M > -gm_inf()) ? gm_exp_nonpos(p.m - M) : 1.0;
     a1 += p.s1 * e;
     a2 += p.s2 * (e * e);
   }
@@ -346,7 +358,7 @@ __device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, do
   const Real2 b = *reinterpret_cast<const Real2*>(lw + i + 2);
   const double l[4] = {(double)a.x, (double)a.y, (double)b.x, (double)b.y};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(gm_exp(l[j] - mx) * scale) : 0;
+  for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(gm_exp_nonpos(l[j] - mx) * scale) : 0;
 }
 
 // phase 1: per-tile sums of q
@@ -362,38 +374,37 @@ __global__ void __launch_bounds__(GSMC_BLOCK) qsum_kernel(const Real* lw, int64_
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = t;
 }
 
-// phase 2: exclusive scan of up to 2 arrays of tile sums (one block); totals go to out_total[a]
+// phase 2: exclusive scan of up to 2 arrays of tile sums (one block); totals go to total0/total1.
+// Each thread owns a run of consecutive elements (local serial scan), one block-wide scan of the run sums.
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t* a1, int nt, const DevScalars* ds,
                                                           uint64_t* total0, uint64_t* total1, int conditional) {
   __shared__ uint64_t sm[33];
   if (conditional && !ds->do_resample) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (nt + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(lo + per, nt);
   for (int arr = 0; arr < 2; ++arr) {
     uint64_t* a = arr ? a1 : a0;
     if (!a) continue;
-    uint64_t carry = 0;
-    for (int base = 0; base < nt; base += 1024) {
-      const int idx = base + threadIdx.x;
-      const uint64_t v = idx < nt ? a[idx] : 0;
-      uint64_t x = v;
+    uint64_t run = 0;
+    for (int i = lo; i < hi; ++i) run += a[i];
+    uint64_t x = run;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
-      __syncthreads();
-      if (lane == 31) sm[warp] = x;
-      __syncthreads();
-      if (warp == 0) {
-        uint64_t w = sm[lane];
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
+    __syncthreads();
+    if (lane == 31) sm[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t w = sm[lane];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
-        sm[lane] = w;
-      }
-      __syncthreads();
-      const uint64_t incl = x + (warp ? sm[warp - 1] : 0);
-      if (idx < nt) a[idx] = carry + incl - v;      // exclusive
-      carry += sm[31];
-      __syncthreads();
+      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
+      sm[lane] = w;
     }
-    if (threadIdx.x == 0) { if (arr == 0) *total0 = carry; else *total1 = carry; }
+    __syncthreads();
+    uint64_t acc = x - run + (warp ? sm[warp - 1] : 0);       // exclusive prefix of this thread's run
+    for (int i = lo; i < hi; ++i) { const uint64_t v = a[i]; a[i] = acc; acc += v; }
+    if (threadIdx.x == 0) { if (arr == 0) *total0 = sm[31]; else *total1 = sm[31]; }
+    __syncthreads();
   }
 }
 
@@ -498,7 +509,10 @@ __global__ void spacing_total_kernel(uint64_t seed, DevScalars* ds, int nranks) 
     const uint64_t m = ds->n_draws;
     uint64_t e0, e1;
     spacing_pair(seed, m >> 1, ds->rho, &e0, &e1);
-    ds->spacing_total = s + ((m & 1) ? e1 : e0);
+    const uint64_t stot = s + ((m & 1) ? e1 : e0);
+    ds->spacing_total = stot;
+    const MulDiv md = make_muldiv(ds->cdf_total, stot);
+    ds->thr_ratio = md.ratio; ds->thr_inv = md.inv_d;
   }
 }
 
@@ -510,27 +524,31 @@ struct CdfView {
   int64_t n_per;                         // particles per rank
   int nranks;
 };
-// smallest (rank, j) in [lo, hi] of segment r with (off + seg[j]) * st > (chi,clo); returns hi+1 if none
-__device__ __forceinline__ int64_t seg_upper(const uint64_t* seg, uint64_t off, int64_t lo, int64_t hi, uint64_t st,
-                                             uint64_t chi, uint64_t clo) {
+// smallest j in [lo, hi] of a segment with off + seg[j] > T; returns hi+1 if none
+__device__ __forceinline__ int64_t seg_upper(const uint64_t* seg, uint64_t off, int64_t lo, int64_t hi, uint64_t T) {
   int64_t l = lo, h = hi + 1;
   while (l < h) {
     const int64_t mid = l + ((h - l) >> 1);
-    if (mul_gt(off + __ldg(seg + mid), st, chi, clo)) h = mid; else l = mid + 1;
+    if (off + __ldg(seg + mid) > T) h = mid; else l = mid + 1;
   }
   return l;
 }
-// ancestor word of the threshold (S_k * C_N = chi:clo) against the global CDF, scaled by st = S_tot
-__device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, uint64_t st, uint64_t chi, uint64_t clo) {
+// ancestor word of threshold T against the global CDF: min{i : C_i > T}
+__device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, uint64_t T) {
   uint64_t off = 0;
   int r = 0;
   for (; r < v.nranks - 1; ++r) {
-    if (mul_gt(off + ds->cdf_rank_total[r], st, chi, clo)) break;
+    if (off + ds->cdf_rank_total[r] > T) break;
     off += ds->cdf_rank_total[r];
   }
-  int64_t j = seg_upper(v.seg[r], off, 0, v.n_per - 1, st, chi, clo);
+  int64_t j = seg_upper(v.seg[r], off, 0, v.n_per - 1, T);
   if (j > v.n_per - 1) j = v.n_per - 1;           // T == C_N can only happen when the last spacing is 0
   return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
+}
+__device__ __forceinline__ MulDiv threshold_muldiv(const DevScalars* ds) {
+  MulDiv md;
+  md.b = ds->cdf_total; md.d = ds->spacing_total; md.ratio = ds->thr_ratio; md.inv_d = ds->thr_inv;
+  return md;
 }
 
 // Sorted mode, step 1: ancestor word of the FIRST threshold of every tile (one thread per tile, all
@@ -550,8 +568,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
   uint64_t e0, e1;
   spacing_pair(seed, kt >> 1, ds->rho, &e0, &e1);     // kt is a multiple of the tile size: even element
   S += e0;
-  const uint64_t cn = ds->cdf_total;
-  win[b] = search_global(v, ds, ds->spacing_total, __umul64hi(S, cn), S * cn);
+  win[b] = search_global(v, ds, muldiv_floor(S, threshold_muldiv(ds)));
 }
 
 // Sorted mode, step 2. Tile b of this rank handles thresholds k_first + b*TILE + [0, TILE) and writes
@@ -576,15 +593,15 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
   uint64_t base = 0;
   for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
   uint64_t S = base + tile_prefix[blockIdx.x] + block_scan_u64(tsum, sm, &tot) - tsum;
-  const uint64_t st = ds->spacing_total, cn = ds->cdf_total;
+  const MulDiv md = threshold_muldiv(ds);
   uint32_t a[4];
   bool have[4];
-  uint64_t chi[4], clo[4];
+  uint64_t T[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     S += e[j];
     have[j] = k + j < m_draws;
-    chi[j] = __umul64hi(S, cn); clo[j] = S * cn;
+    T[j] = have[j] ? muldiv_floor(S, md) : 0;            // T_k = floor(S_k C_N / S_tot), exact
   }
   const uint32_t w0 = win[blockIdx.x], w1 = win[blockIdx.x + 1];
   const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT);
@@ -601,25 +618,20 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (!have[j]) { a[j] = 0; continue; }
-      int l, h;
-      if (j == 0) { l = 0; h = len; }
-      else {
-        // gallop from the previous ancestor: thresholds are sorted, so ancestors are monotone
-        int step = 1;
-        l = pos; h = pos;
-        while (h < len && !mul_gt(cwin[h], st, chi[j], clo[j])) { l = h + 1; h += step; step <<= 1; }
-        if (h > len) h = len;
+      if (j == 0) {
+        int l = 0, h = len;                               // min{p : cwin[p] > T}, else len
+        while (l < h) { const int mid = (l + h) >> 1; if (cwin[mid] > T[0]) h = mid; else l = mid + 1; }
+        pos = l;
+      } else {
+        // thresholds are sorted, so ancestors are monotone and on average one slot apart: walk
+        while (pos < len && cwin[pos] <= T[j]) ++pos;
       }
-      while (l < h) {                                   // min{p in [l, h) : pred(p)}, else h
-        const int mid = (l + h) >> 1;
-        if (mul_gt(cwin[mid], st, chi[j], clo[j])) h = mid; else l = mid + 1;
-      }
-      pos = l < len ? l : len - 1;
+      if (pos >= len) pos = len - 1;
       a[j] = ((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pos);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, st, chi[j], clo[j]) : 0;
+    for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, T[j]) : 0;
   }
   // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
   const int64_t o = (int64_t)(k - k_first) + (det_offset ? (int64_t)ds->n_det : 0);
@@ -646,18 +658,10 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_iid_kernel(CdfView v, const
   const uint64_t t = (uint64_t)floor(uj * 9007199254740992.0);
   const uint64_t cn = ds->cdf_total;
   const uint64_t T = (__umul64hi(t, cn) << 11) | ((t * cn) >> 53);
-  // compare C > T via the same 128-bit helper with st = 1
-  uint64_t off = 0;
-  int r = 0;
-  for (; r < v.nranks - 1; ++r) {
-    if (off + ds->cdf_rank_total[r] > T) break;
-    off += ds->cdf_rank_total[r];
-  }
-  int64_t pos = seg_upper(v.seg[r], off, 0, v.n_per - 1, 1, 0, T);
-  if (pos > v.n_per - 1) pos = v.n_per - 1;
+  const uint32_t w = search_global(v, ds, T);
   const int64_t o = j + (out_offset_det ? (int64_t)ds->n_det : 0);
-  if (anc32) anc32[o] = ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)pos;
-  if (anc64) anc64[o] = (int64_t)r * v.n_per + pos;
+  if (anc32) anc32[o] = w;
+  if (anc64) anc64[o] = (int64_t)(w >> GSMC_ANC_RANK_SHIFT) * v.n_per + (int64_t)(w & GSMC_ANC_INDEX_MASK);
 }
 
 // residual scheme, deterministic part: slot o < n_det belongs to min{i : Cc_i > o}

@@ -11,7 +11,7 @@ world_size>1 logic is testable on CPU with gloo.
 """
 import math
 
-TILE = 1024
+TILE = 2048
 
 
 def check_partition(num_particles, world_size):

@@ -14,6 +14,7 @@
  */
 #include "gsmc_oracle.h"
 #include "../gen_b200/csrc/gsmc_math.h"
+#include "../gen_b200/csrc/gsmc_fixed.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,6 +47,27 @@ void orc_sincospi(double t, double* s, double* c) { gm_sincospi(t, s, c); }
 /* checks of gsmc_math.h helpers the device uses (tests/test_math.py) */
 double orc_div_inv(double x, double c) { return gm_div_inv(x, c, gm_safe_recip(c)); }
 double orc_log_pos(double x) { return gm_log_pos(x); }
+double orc_exp_nonpos(double x) { return gm_exp_nonpos(x); }
+/* muldiv_floor vs unsigned __int128 division */
+int64_t orc_muldiv_mismatches(uint64_t seed, int64_t n) {
+  uint64_t s = seed ? seed : 1; int64_t bad = 0;
+  for (int64_t it = 0; it < n; ++it) {
+    uint64_t r[4];
+    for (int j = 0; j < 4; ++j) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; r[j] = s; }
+    int sb = 1 + (int)(r[0] % 62), sd = 1 + (int)(r[1] % 62);
+    uint64_t b = (r[2] >> (64 - sb)) | 1, d = (r[3] >> (64 - sd)) | 1;
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    uint64_t a = s % (d + 1);
+    int mode = (int)(it & 7);
+    if (mode == 0) a = d;
+    if (mode == 1) a = d - 1;
+    if (mode == 2) a = 0;
+    if (mode == 4) b = ((uint64_t)1 << 62) - (s % 1000);
+    if (mode == 5) { d = ((uint64_t)1 << 62) + (s % 100000); a = r[0] % (d + 1); }
+    if (muldiv_floor(a, make_muldiv(b, d)) != (uint64_t)(((u128)a * b) / d)) ++bad;
+  }
+  return bad;
+}
 /* number of operand pairs (adversarial mantissas included) where the Markstein sequence differs from x / c */
 int64_t orc_div_inv_mismatches(uint64_t seed, int64_t n) {
   uint64_t s = seed ? seed : 88172645463325252ULL;

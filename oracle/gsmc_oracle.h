@@ -58,6 +58,8 @@ void orc_fill_uniforms(uint64_t seed, uint32_t t, uint32_t stream, uint64_t firs
 void orc_fill_spacings(uint64_t seed, uint32_t rho, uint64_t first, uint64_t count, uint64_t* out);
 double orc_div_inv(double x, double c);
 double orc_log_pos(double x);
+double orc_exp_nonpos(double x);
+int64_t orc_muldiv_mismatches(uint64_t seed, int64_t n);
 int64_t orc_div_inv_mismatches(uint64_t seed, int64_t n);
 double orc_exp(double x);
 double orc_log(double x);

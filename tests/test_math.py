@@ -62,3 +62,16 @@ def test_log_fast_path_has_the_same_bits(orc):
     rng = np.random.default_rng(3)
     for x in np.concatenate([rng.random(20000), np.exp(rng.uniform(-600, 600, 20000)), [2.0 ** -53 * 0.5, 1.0 - 2.0 ** -53]]):
         assert orc.L.orc_log_pos(float(x)) == orc.L.orc_log(float(x))
+
+
+def test_exp_nonpos_has_the_same_bits(orc):
+    rng = np.random.default_rng(4)
+    xs = np.concatenate([-rng.random(20000) * 50, -np.exp(rng.uniform(-30, 6.56, 20000)), [0.0, -0.0, -708.39, -708.4, -745.0, -1e300, -math.inf]])
+    for x in xs:
+        assert orc.L.orc_exp_nonpos(float(x)) == orc.L.orc_exp(float(x)), x
+
+
+def test_muldiv_floor_is_exact(orc):
+    """gsmc_fixed.h: T_k = floor(S_k C_N / S_tot) against unsigned __int128 division."""
+    assert orc.L.orc_muldiv_mismatches(1, 5_000_000) == 0
+    assert orc.L.orc_muldiv_mismatches(2024, 5_000_000) == 0
