@@ -101,6 +101,7 @@ struct gsmc_filter {
   int rank = 0, nranks = 1;
   NcclComm comm = nullptr;
   int64_t N = 0, n = 0, n_pad = 0, first = 0;   // global count, local count, padded local, first global index
+  int sm_count = 148;
   int n_tiles = 0;       // 1024-particle tiles of the scan / search kernels
   int n_partials = 0;    // blocks (= logsumexp partials) of the last propagate launch
   std::vector<double> params;
@@ -421,11 +422,12 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   const Real* lw = (const Real*)f->lw;
   const double scale = gm_pow2([&] { int lg = 0; while (((uint64_t)1 << lg) < (uint64_t)f->N) ++lg; int k = 62 - lg; return k > 52 ? 52 : k; }());
   const int nt = f->n_tiles;
+  const int pg = nt < f->sm_count * 6 ? nt : f->sm_count * 6;     // persistent grid of the tile kernels
   const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
   uint32_t* anc = anc_col(f, f->anc_slab, f->T + 1);
   if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
   // 1. integer weights -> tile sums -> tile prefixes and this rank's total
-  { ProfScope ps(f, KC_SCAN); qsum_kernel<Real><<<nt, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, conditional); }
+  { ProfScope ps(f, KC_SCAN); qsum_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, nt, conditional); }
   { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[f->rank], nullptr, conditional); }
   CK(cudaGetLastError());
   if (f->nranks > 1)
@@ -433,13 +435,13 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, (uint64_t)f->N, residual ? 0 : 1, conditional); }
   if (!residual) {
     ProfScope ps(f, KC_SCAN);
-    cdf_kernel<Real><<<nt, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->cdf, conditional);
+    cdf_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, conditional);
   } else {
     { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
-    { ProfScope ps(f, KC_SCAN); resid_sum_kernel<Real><<<nt, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, conditional); }
+    { ProfScope ps(f, KC_SCAN); resid_sum_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, nt, conditional); }
     { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, f->tile_b, nt, f->ds, f->scratch_tot, f->scratch_tot + 1, conditional); }
     { ProfScope ps(f, KC_OTHER); resid_totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->scratch_tot, f->scratch_tot + 1, (uint64_t)f->N); }
-    { ProfScope ps(f, KC_SCAN); resid_cdf_kernel<Real><<<nt, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, f->cc, f->cdf, conditional); }
+    { ProfScope ps(f, KC_SCAN); resid_cdf_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, f->cc, f->cdf, nt, conditional); }
     { ProfScope ps(f, KC_SEARCH); det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(f->cc, f->n, f->ds, anc, conditional); }
   }
   CK(cudaGetLastError());
@@ -454,7 +456,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   } else {
     // 2. sorted uniforms: spacing tile sums -> prefixes -> S_tot
     const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
-    { ProfScope ps(f, KC_SPACINGS); spacing_sum_kernel<<<nt, GSMC_BLOCK, 0, f->stream>>>(f->cfg.seed, k_first, f->ds, f->tile_b, conditional); }
+    { ProfScope ps(f, KC_SPACINGS); spacing_sum_kernel<<<pg, GSMC_BLOCK, 0, f->stream>>>(f->cfg.seed, k_first, f->ds, f->tile_b, nt, conditional); }
     { ProfScope ps(f, KC_SPACINGS); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_b, nullptr, nt, f->ds, &f->ds->spacing_rank_total[f->rank], nullptr, conditional); }
     CK(cudaGetLastError());
     if (f->nranks > 1)
@@ -464,7 +466,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     { ProfScope ps(f, KC_SEARCH);
       partition_kernel<<<(nt + 1 + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, nt, f->win, conditional); }
     { ProfScope ps(f, KC_SEARCH);
-      search_sorted_kernel<<<nt, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, f->win, anc, f->n, residual ? 1 : 0, conditional); }
+      search_sorted_kernel<<<pg, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -511,6 +513,8 @@ GSMC_API int gsmc_create(const gsmc_config* cfg, const double* params, size_t n_
   if (cudaSetDevice(f->device) != cudaSuccess) { delete f; return fail(GSMC_E_CUDA, "cannot select device %d", cfg->device); }
   if (cfg->stream) f->stream = (cudaStream_t)cfg->stream;
   else { if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess) { delete f; return fail(GSMC_E_CUDA, "stream creation failed"); } f->own_stream = true; }
+  cudaDeviceGetAttribute(&f->sm_count, cudaDevAttrMultiProcessorCount, f->device);
+  if (f->sm_count < 1) f->sm_count = 148;
   f->params.assign(params, params + n_params);
   f->N = (int64_t)cfg->num_particles; f->n = f->N; f->first = 0;
   if (cudaMalloc(&f->d_params, n_params * sizeof(double)) != cudaSuccess ||
@@ -825,16 +829,17 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
   {
     const double scale = gm_pow2([&] { int lg = 0; while (((uint64_t)1 << lg) < (uint64_t)f->N) ++lg; int k = 62 - lg; return k > 52 ? 52 : k; }());
     const int nt = f->n_tiles;
+    const int pg = nt < f->sm_count * 6 ? nt : f->sm_count * 6;
     if (f->f32) {
-      { ProfScope ps(f, KC_SCAN); qsum_kernel<float><<<nt, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, 0); }
+      { ProfScope ps(f, KC_SCAN); qsum_kernel<float><<<pg, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, nt, 0); }
       { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0); }
       { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, 1, (uint64_t)f->N, 0, 0); }
-      { ProfScope ps(f, KC_SCAN); cdf_kernel<float><<<nt, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, 0); }
+      { ProfScope ps(f, KC_SCAN); cdf_kernel<float><<<pg, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, 0); }
     } else {
-      { ProfScope ps(f, KC_SCAN); qsum_kernel<double><<<nt, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, 0); }
+      { ProfScope ps(f, KC_SCAN); qsum_kernel<double><<<pg, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, nt, 0); }
       { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0); }
       { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, 1, (uint64_t)f->N, 0, 0); }
-      { ProfScope ps(f, KC_SCAN); cdf_kernel<double><<<nt, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, 0); }
+      { ProfScope ps(f, KC_SCAN); cdf_kernel<double><<<pg, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, 0); }
     }
   }
   CK(cudaGetLastError());

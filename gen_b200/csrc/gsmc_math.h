@@ -252,4 +252,91 @@ GM_HD double gm_atan2(double y, double x) {
   return y >= 0.0 ? a + GM_PI : a - GM_PI;
 }
 
+
+#if defined(__cplusplus)
+// ------------------------------------------------------------------------------------------------
+// Batch forms: K independent evaluations with the coefficient loop outside and the element loop
+// inside. Element by element the arithmetic is identical to the scalar functions above (same bits);
+// the batch form lets one constant load feed K FMAs and gives the scheduler K independent Horner
+// chains to interleave (the scalar chains stall on their own FMA latency).
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define GM_UNROLL _Pragma("unroll")
+#else
+#define GM_UNROLL
+#endif
+
+template <int K> GM_HD void gm_exp_nonpos_v(const double* x, double* out) {
+  double xc[K], kf[K], r[K], p[K];
+  GM_UNROLL for (int k = 0; k < K; ++k) {
+    xc[k] = x[k] < -708.3964185322641 ? -708.0 : x[k];
+    kf[k] = floor(xc[k] * GM_INV_LN2 + 0.5);
+    r[k] = fma(-kf[k], GM_LN2_HI, xc[k]);
+    r[k] = fma(-kf[k], GM_LN2_LO, r[k]);
+    p[k] = GM_C(exp, 0);
+  }
+  GM_UNROLL for (int i = 1; i < 14; ++i) {
+    const double c = GM_C(exp, i);
+    GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], c);
+  }
+  GM_UNROLL for (int k = 0; k < K; ++k) {
+    const long long kk = (long long)kf[k];
+    const double v = gm_from_bits(gm_to_bits(p[k]) + ((uint64_t)kk << 52));
+    out[k] = x[k] < -708.3964185322641 ? 0.0 : v;
+  }
+}
+
+// gm_log_pos for K positive, finite, normal arguments
+template <int K> GM_HD void gm_log_pos_v(const double* x, double* out) {
+  double s[K], z[K], p[K], ef[K];
+  GM_UNROLL for (int k = 0; k < K; ++k) {
+    const uint64_t b = gm_to_bits(x[k]);
+    int e = (int)(b >> 52) - 1023;
+    double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    if (m > 1.41421356237309514547) { m = m * 0.5; e += 1; }
+    const double f = m - 1.0;
+    s[k] = f / (m + 1.0);
+    z[k] = s[k] * s[k];
+    ef[k] = (double)e;
+    p[k] = GM_C(log, 0);
+  }
+  GM_UNROLL for (int i = 1; i < 10; ++i) {
+    const double c = GM_C(log, i);
+    GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], z[k], c);
+  }
+  GM_UNROLL for (int k = 0; k < K; ++k) {
+    const double s2 = s[k] + s[k];
+    const double lm = fma(s2 * z[k], p[k], s2);
+    out[k] = fma(ef[k], GM_LN2_HI, fma(ef[k], GM_LN2_LO, lm));
+  }
+}
+
+template <int K> GM_HD void gm_sincospi_v(const double* t, double* sn, double* cs) {
+  double nf[K], x[K], z[K], ps[K], pc[K];
+  GM_UNROLL for (int k = 0; k < K; ++k) {
+    nf[k] = floor(t[k] + t[k] + 0.5);
+    const double r = fma(nf[k], -0.5, t[k]);
+    x[k] = r * GM_PI;
+    z[k] = x[k] * x[k];
+    ps[k] = GM_C(sin, 0);
+    pc[k] = GM_C(cos, 0);
+  }
+  GM_UNROLL for (int i = 1; i < 9; ++i) {
+    const double a = GM_C(sin, i), b = GM_C(cos, i);
+    GM_UNROLL for (int k = 0; k < K; ++k) { ps[k] = fma(ps[k], z[k], a); pc[k] = fma(pc[k], z[k], b); }
+  }
+  GM_UNROLL for (int k = 0; k < K; ++k) {
+    const double s0 = fma(x[k] * z[k], ps[k], x[k]);
+    const double c0 = fma(z[k], pc[k], 1.0);
+    const int q = (int)((long long)nf[k] & 3);
+    const int swap = (q & 1) != 0;
+    double so = swap ? c0 : s0;
+    double co = swap ? s0 : c0;
+    so = (q & 2) ? -so : so;
+    co = ((q + 1) & 2) ? -co : co;
+    sn[k] = so; cs[k] = co;
+  }
+}
+#endif  /* __cplusplus */
+
 #endif  /* GSMC_MATH_H */

@@ -69,4 +69,41 @@ __host__ __device__ __forceinline__ void spacing_pair(uint64_t seed, uint64_t ca
   *e1 = spacing_from_word(o.b);
 }
 
+
+// Batch forms (same bits as the scalar functions, see gsmc_math.h "Batch forms").
+// K Philox calls -> 2K standard normals z[2m] (cos branch), z[2m+1] (sin branch)
+template <int K>
+__host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uint64_t* calls, uint32_t t, double* z) {
+  double u1[K], t2[K], l[K], sn[K], cs[K];
+#pragma unroll
+  for (int m = 0; m < K; ++m) {
+    const PhiloxOut o = philox_call(seed, calls[m], t, GSMC_STREAM_NORMAL);
+    u1[m] = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
+    const double u2 = (double)(o.b >> 11) * 0x1p-53;
+    t2[m] = 2.0 * u2;
+  }
+  gm_log_pos_v<K>(u1, l);
+  gm_sincospi_v<K>(t2, sn, cs);
+#pragma unroll
+  for (int m = 0; m < K; ++m) {
+    const double r = sqrt(-2.0 * l[m]);
+    z[2 * m] = r * cs[m];
+    z[2 * m + 1] = r * sn[m];
+  }
+}
+// 2K spacings of the calls c0, c0+1, ...
+template <int K>
+__host__ __device__ __forceinline__ void spacing_pairs_v(uint64_t seed, uint64_t c0, uint32_t rho, uint64_t* e) {
+  double u[2 * K], l[2 * K];
+#pragma unroll
+  for (int m = 0; m < K; ++m) {
+    const PhiloxOut o = philox_call(seed, c0 + m, rho, GSMC_STREAM_RESAMPLE);
+    u[2 * m] = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
+    u[2 * m + 1] = ((double)(o.b >> 11) + 0.5) * 0x1p-53;
+  }
+  gm_log_pos_v<2 * K>(u, l);
+#pragma unroll
+  for (int j = 0; j < 2 * K; ++j) e[j] = (uint64_t)floor(-l[j] * 4294967296.0);
+}
+
 #endif

@@ -150,100 +150,118 @@ template <class Model, typename Real, bool INIT, int PROP>
 __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
   typedef typename Vec2T<Real>::type Real2;
   constexpr int D = Model::D;
-  constexpr int PAIRS = PropTile<Model>::PAIRS;
-  constexpr int NZ_MAX = 4, NU_MAX = 1;
+  constexpr int PAIRS = PropTile<Model>::PAIRS, NP = 2 * PAIRS;
+  constexpr int NZ = Model::nz(INIT, PROP), NU = Model::nu(INIT, PROP);
+  constexpr int NZA = NZ > 0 ? NZ : 1, NUA = NU > 0 ? NU : 1;
   extern __shared__ double dyn_sm[];
   __shared__ double red[3 * (GSMC_BLOCK / 32)];
   if (Model::SMEM_DOUBLES > 0) {
     Model::template prologue<INIT, PROP>(a, dyn_sm);
     __syncthreads();
   }
-  const int nz = Model::nz(INIT, PROP), nu = Model::nu(INIT, PROP);
   const bool gather = !INIT && g.use_anc && (*g.resampled_flag != 0);
+  const int64_t tile0 = (int64_t)blockIdx.x * PropTile<Model>::TILE + 2 * threadIdx.x;
 
-  double lwv[2 * PAIRS];
-  bool val[2 * PAIRS];
-  const int64_t tile0 = (int64_t)blockIdx.x * PropTile<Model>::TILE;
+  // The columns are padded to the tile, so the pad lanes of the last tile are loaded, computed and
+  // stored like real particles (harmless garbage) and only masked out of the logsumexp partial.
+  // Stage A: previous state and log weights of all pairs (all loads in flight together).
+  double prev[NP][D], lwv[NP];
+  if (!INIT) {
+    if (gather) {
 #pragma unroll
-  for (int u = 0; u < PAIRS; ++u) {
-    const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK + 2 * threadIdx.x;   // first particle of the pair
-    const bool v0 = i < g.n, v1 = i + 1 < g.n;
-    val[2 * u] = v0; val[2 * u + 1] = v1;
-    lwv[2 * u] = lwv[2 * u + 1] = -gm_inf();
-    if (!v0) continue;
-    double prev0[D], prev1[D], lw0 = 0.0, lw1 = 0.0;
-    if (!INIT) {
-      if (gather) {
-        const uint2 aw = *reinterpret_cast<const uint2*>(g.anc + i);
+      for (int u = 0; u < PAIRS; ++u) {
+        const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
+        uint2 aw = *reinterpret_cast<const uint2*>(g.anc + i);
+        if (i >= g.n) aw.x = 0;                       // ancestor words of pad lanes are not initialised
+        if (i + 1 >= g.n) aw.y = 0;
         const Real* c0 = g.cur[aw.x >> GSMC_ANC_RANK_SHIFT] + (aw.x & GSMC_ANC_INDEX_MASK);
-        const uint32_t ay = v1 ? aw.y : aw.x;    // the pad slot after an odd tail is not initialised
-        const Real* c1 = g.cur[ay >> GSMC_ANC_RANK_SHIFT] + (ay & GSMC_ANC_INDEX_MASK);
+        const Real* c1 = g.cur[aw.y >> GSMC_ANC_RANK_SHIFT] + (aw.y & GSMC_ANC_INDEX_MASK);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          prev0[d] = (double)__ldg(c0 + d * g.stride);
-          prev1[d] = v1 ? (double)__ldg(c1 + d * g.stride) : 0.0;
+          prev[2 * u][d] = (double)__ldg(c0 + d * g.stride);
+          prev[2 * u + 1][d] = (double)__ldg(c1 + d * g.stride);
         }
-      } else {
+        lwv[2 * u] = 0.0; lwv[2 * u + 1] = 0.0;       // log_weights[i] = 0. after a resample (:204)
+      }
+    } else {
+      const Real* cur = g.cur[g.rank];
+#pragma unroll
+      for (int u = 0; u < PAIRS; ++u) {
+        const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          const Real2 x = *reinterpret_cast<const Real2*>(g.cur[g.rank] + d * g.stride + i);
-          prev0[d] = (double)x.x; prev1[d] = (double)x.y;
+          const Real2 x = *reinterpret_cast<const Real2*>(cur + d * g.stride + i);
+          prev[2 * u][d] = (double)x.x; prev[2 * u + 1][d] = (double)x.y;
         }
         const Real2 l = *reinterpret_cast<const Real2*>(g.lw + i);
-        lw0 = (double)l.x; lw1 = (double)l.y;
+        lwv[2 * u] = (double)l.x; lwv[2 * u + 1] = (double)l.y;
       }
     }
-    // draws: elements [(first_global+i)*nz, +2nz) of the step's virtual normal array -> nz Philox calls
-    double zz[2 * NZ_MAX], uu[2 * NU_MAX];
-    if (nz > 0) {
-      if (g.zrep) {
-        for (int j = 0; j < 2 * nz; ++j) zz[j] = (j < nz || v1) ? g.zrep[i * nz + j] : 0.0;
-      } else {
-        const uint64_t c0 = ((g.first_global + (uint64_t)i) * (uint64_t)nz) >> 1;
-#pragma unroll
-        for (int m = 0; m < NZ_MAX; ++m)
-          if (m < nz) normal_pair(g.seed, c0 + m, g.t, &zz[2 * m], &zz[2 * m + 1]);
-      }
-    }
-    if (nu > 0) {
-      if (g.urep) {
-        for (int j = 0; j < 2 * nu; ++j) uu[j] = (j < nu || v1) ? g.urep[i * nu + j] : 0.0;
-      } else {
-        const uint64_t c0 = ((g.first_global + (uint64_t)i) * (uint64_t)nu) >> 1;
-#pragma unroll
-        for (int m = 0; m < NU_MAX; ++m)
-          if (m < nu) uniform_pair(g.seed, c0 + m, g.t, GSMC_STREAM_UNIFORM, &uu[2 * m], &uu[2 * m + 1]);
-      }
-    }
-    double out0[D], out1[D];
-    const double w0 = Model::template particle<INIT, PROP>(a, dyn_sm, prev0, zz, uu, out0);
-    double w1 = 0.0;
-    if (v1) w1 = Model::template particle<INIT, PROP>(a, dyn_sm, prev1, zz + nz, uu + nu, out1);
-    // log_weights[i] = weight (init) / += increment (step); after a resample they restart from 0.
-    const Real r0 = (Real)(INIT ? w0 : lw0 + w0), r1 = (Real)(INIT ? w1 : lw1 + w1);
-    if (v1) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        Real2 o; o.x = (Real)out0[d]; o.y = (Real)out1[d];
-        *reinterpret_cast<Real2*>(g.nxt + d * g.stride + i) = o;
-      }
-      Real2 l; l.x = r0; l.y = r1;
-      *reinterpret_cast<Real2*>(g.lw + i) = l;
-      lwv[2 * u + 1] = (double)r1;
-    } else {
-#pragma unroll
-      for (int d = 0; d < D; ++d) g.nxt[d * g.stride + i] = (Real)out0[d];
-      g.lw[i] = r0;
-    }
-    lwv[2 * u] = (double)r0;
   }
 
-  // block partial of (max, sum exp(lw-max), sum exp(2(lw-max))); NaN log weights poison s1/s2 on purpose.
+  // Stage B: draws. Pair u needs elements [(first_global+i)*NZ, +2NZ) of the step's virtual normal
+  // array = NZ Philox calls; all PAIRS*NZ Box-Muller transforms are evaluated as one batch.
+  double zz[PAIRS][2 * NZA], uu[PAIRS][2 * NUA];
+  if (NZ > 0) {
+    if (g.zrep) {
+#pragma unroll
+      for (int u = 0; u < PAIRS; ++u) {
+        const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
+#pragma unroll
+        for (int j = 0; j < 2 * NZ; ++j) zz[u][j] = (i * NZ + j < g.n * NZ) ? g.zrep[i * NZ + j] : 0.0;
+      }
+    } else {
+      uint64_t calls[PAIRS * NZA];
+#pragma unroll
+      for (int u = 0; u < PAIRS; ++u) {
+        const uint64_t c0 = ((g.first_global + (uint64_t)(tile0 + (int64_t)u * 2 * GSMC_BLOCK)) * (uint64_t)NZ) >> 1;
+#pragma unroll
+        for (int m = 0; m < NZ; ++m) calls[u * NZ + m] = c0 + m;
+      }
+      normal_pairs_v<PAIRS * NZA>(g.seed, calls, g.t, &zz[0][0]);
+    }
+  }
+  if (NU > 0) {
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
+      if (g.urep) {
+#pragma unroll
+        for (int j = 0; j < 2 * NU; ++j) uu[u][j] = (i * NU + j < g.n * NU) ? g.urep[i * NU + j] : 0.0;
+      } else {
+        const uint64_t c0 = ((g.first_global + (uint64_t)i) * (uint64_t)NU) >> 1;
+#pragma unroll
+        for (int m = 0; m < NU; ++m) uniform_pair(g.seed, c0 + m, g.t, GSMC_STREAM_UNIFORM, &uu[u][2 * m], &uu[u][2 * m + 1]);
+      }
+    }
+  }
+
+  // Stage C: the model, per particle. log_weights[i] = weight (init) / += increment (step).
+  // Stage D: vector stores of the new state and log weights.
+#pragma unroll
+  for (int u = 0; u < PAIRS; ++u) {
+    const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
+    double out0[D], out1[D];
+    const double w0 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u], zz[u], uu[u], out0);
+    const double w1 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u + 1], zz[u] + NZ, uu[u] + NU, out1);
+    const Real r0 = (Real)(INIT ? w0 : lwv[2 * u] + w0), r1 = (Real)(INIT ? w1 : lwv[2 * u + 1] + w1);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      Real2 o; o.x = (Real)out0[d]; o.y = (Real)out1[d];
+      *reinterpret_cast<Real2*>(g.nxt + d * g.stride + i) = o;
+    }
+    Real2 l; l.x = r0; l.y = r1;
+    *reinterpret_cast<Real2*>(g.lw + i) = l;
+    lwv[2 * u] = (i < g.n) ? (double)r0 : -gm_inf();          // pad lanes drop out of the reduction
+    lwv[2 * u + 1] = (i + 1 < g.n) ? (double)r1 : -gm_inf();
+  }
+
+  // Stage E: block partial of (max, sum exp(lw-max), sum exp(2(lw-max))); NaN log weights poison s1/s2 on purpose.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double m = -gm_inf();
   bool any_nan = false;
 #pragma unroll
-  for (int j = 0; j < 2 * PAIRS; ++j) if (val[j]) { if (lwv[j] != lwv[j]) any_nan = true; else m = fmax(m, lwv[j]); }
+  for (int j = 0; j < NP; ++j) { if (lwv[j] != lwv[j]) any_nan = true; else m = fmax(m, lwv[j]); }
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
@@ -252,8 +270,12 @@ __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Re
   for (int w = 1; w < GSMC_BLOCK / 32; ++w) bm = fmax(bm, red[w]);
   double s1 = 0.0, s2 = 0.0;
   if (bm > -gm_inf()) {
+    double x[NP], e[NP];
 #pragma unroll
-    for (int j = 0; j < 2 * PAIRS; ++j) if (val[j]) { const double e = gm_exp_nonpos(lwv[j] - bm); s1 += e; s2 += e * e; }
+    for (int j = 0; j < NP; ++j) x[j] = lwv[j] - bm;           // -inf for pad lanes -> exp = 0
+    gm_exp_nonpos_v<NP>(x, e);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { s1 += e[j]; s2 += e[j] * e[j]; }
   }
   if (any_nan) { s1 = gm_nan(); s2 = gm_nan(); }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
@@ -356,22 +378,27 @@ __device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, do
   typedef typename Vec2T<Real>::type Real2;
   const Real2 a = *reinterpret_cast<const Real2*>(lw + i);
   const Real2 b = *reinterpret_cast<const Real2*>(lw + i + 2);
-  const double l[4] = {(double)a.x, (double)a.y, (double)b.x, (double)b.y};
+  const double x[4] = {(double)a.x - mx, (double)a.y - mx, (double)b.x - mx, (double)b.y - mx};
+  double e[4];
+  gm_exp_nonpos_v<4>(x, e);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(gm_exp_nonpos(l[j] - mx) * scale) : 0;
+  for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(e[j] * scale) : 0;
 }
 
 // phase 1: per-tile sums of q
 template <typename Real>
 __global__ void __launch_bounds__(GSMC_BLOCK) qsum_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                          uint64_t* tile_sums, int conditional) {
+                                                          uint64_t* tile_sums, int nt, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   if (conditional && !ds->do_resample) return;
-  const int64_t i = (int64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
-  uint64_t q[4];
-  load_q4(lw, i, n, ds->max_lw, scale, q);
-  const uint64_t t = block_sum_u64(q[0] + q[1] + q[2] + q[3], sm);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = t;
+  const double mx = ds->max_lw;
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {        // persistent: an early exit costs ~1k blocks, not n/1024
+    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+    uint64_t q[4];
+    load_q4(lw, i, n, mx, scale, q);
+    const uint64_t t = block_sum_u64(q[0] + q[1] + q[2] + q[3], sm);
+    if (threadIdx.x == 0) tile_sums[tile] = t;
+  }
 }
 
 // phase 2: exclusive scan of up to 2 arrays of tile sums (one block); totals go to total0/total1.
@@ -411,19 +438,22 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t
 // phase 3: local inclusive CDF  cdf[i] = tile_prefix[b] + inclusive scan within the tile
 template <typename Real>
 __global__ void __launch_bounds__(GSMC_BLOCK) cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                         const uint64_t* tile_prefix, uint64_t* cdf, int conditional) {
+                                                         const uint64_t* tile_prefix, uint64_t* cdf, int nt, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   if (conditional && !ds->do_resample) return;
-  const int64_t i = (int64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
-  uint64_t q[4];
-  load_q4(lw, i, n, ds->max_lw, scale, q);
-  uint64_t tot;
-  const uint64_t incl = block_scan_u64(q[0] + q[1] + q[2] + q[3], sm, &tot);
-  uint64_t c = tile_prefix[blockIdx.x] + incl - (q[0] + q[1] + q[2] + q[3]);
-  ulonglong2 o0, o1;
-  c += q[0]; o0.x = c; c += q[1]; o0.y = c; c += q[2]; o1.x = c; c += q[3]; o1.y = c;
-  *reinterpret_cast<ulonglong2*>(cdf + i) = o0;
-  *reinterpret_cast<ulonglong2*>(cdf + i + 2) = o1;
+  const double mx = ds->max_lw;
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+    uint64_t q[4];
+    load_q4(lw, i, n, mx, scale, q);
+    uint64_t tot;
+    const uint64_t incl = block_scan_u64(q[0] + q[1] + q[2] + q[3], sm, &tot);
+    uint64_t c = tile_prefix[tile] + incl - (q[0] + q[1] + q[2] + q[3]);
+    ulonglong2 o0, o1;
+    c += q[0]; o0.x = c; c += q[1]; o0.y = c; c += q[2]; o1.x = c; c += q[3]; o1.y = c;
+    *reinterpret_cast<ulonglong2*>(cdf + i) = o0;
+    *reinterpret_cast<ulonglong2*>(cdf + i + 2) = o1;
+  }
 }
 
 // residual scheme: e_i = floor(q_i * resid_scale); c_i = e_i >> 32 copies; r_i = e_i & (2^32-1)
@@ -437,38 +467,42 @@ __global__ void resid_scale_kernel(DevScalars* ds, double n_global) {
 }
 template <typename Real>
 __global__ void __launch_bounds__(GSMC_BLOCK) resid_sum_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                               uint64_t* tile_c, uint64_t* tile_r, int conditional) {
+                                                               uint64_t* tile_c, uint64_t* tile_r, int nt, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   if (conditional && !ds->do_resample) return;
-  const int64_t i = (int64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
-  uint64_t q[4], cs = 0, rs = 0;
-  load_q4(lw, i, n, ds->max_lw, scale, q);
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+    uint64_t q[4], cs = 0, rs = 0;
+    load_q4(lw, i, n, ds->max_lw, scale, q);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { uint64_t c, r; resid_split(q[j], ds->resid_scale, &c, &r); if (i + j < n) { cs += c; rs += r; } }
-  const uint64_t tc = block_sum_u64(cs, sm);
-  const uint64_t tr = block_sum_u64(rs, sm);
-  if (threadIdx.x == 0) { tile_c[blockIdx.x] = tc; tile_r[blockIdx.x] = tr; }
+    for (int j = 0; j < 4; ++j) { uint64_t c, r; resid_split(q[j], ds->resid_scale, &c, &r); if (i + j < n) { cs += c; rs += r; } }
+    const uint64_t tc = block_sum_u64(cs, sm);
+    const uint64_t tr = block_sum_u64(rs, sm);
+    if (threadIdx.x == 0) { tile_c[tile] = tc; tile_r[tile] = tr; }
+  }
 }
 template <typename Real>
 __global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
                                                                const uint64_t* prefix_c, const uint64_t* prefix_r,
-                                                               uint64_t* cc, uint64_t* cdf, int conditional) {
+                                                               uint64_t* cc, uint64_t* cdf, int nt, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   if (conditional && !ds->do_resample) return;
-  const int64_t i = (int64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
-  uint64_t q[4], c[4], r[4], cs = 0, rs = 0;
-  load_q4(lw, i, n, ds->max_lw, scale, q);
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+    uint64_t q[4], c[4], r[4], cs = 0, rs = 0;
+    load_q4(lw, i, n, ds->max_lw, scale, q);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    resid_split(q[j], ds->resid_scale, &c[j], &r[j]);
-    if (i + j >= n) { c[j] = 0; r[j] = 0; }
-    cs += c[j]; rs += r[j];
+    for (int j = 0; j < 4; ++j) {
+      resid_split(q[j], ds->resid_scale, &c[j], &r[j]);
+      if (i + j >= n) { c[j] = 0; r[j] = 0; }
+      cs += c[j]; rs += r[j];
+    }
+    uint64_t tot;
+    uint64_t ic = prefix_c[tile] + block_scan_u64(cs, sm, &tot) - cs;
+    uint64_t ir = prefix_r[tile] + block_scan_u64(rs, sm, &tot) - rs;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ic += c[j]; ir += r[j]; cc[i + j] = ic; cdf[i + j] = ir; }
   }
-  uint64_t tot;
-  uint64_t ic = prefix_c[blockIdx.x] + block_scan_u64(cs, sm, &tot) - cs;
-  uint64_t ir = prefix_r[blockIdx.x] + block_scan_u64(rs, sm, &tot) - rs;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { ic += c[j]; ir += r[j]; cc[i + j] = ic; cdf[i + j] = ir; }
 }
 // after the scans: n_det = sum c, n_draws = N - n_det, cdf_total = sum r (single rank)
 __global__ void resid_totals_kernel(DevScalars* ds, const uint64_t* total_c, const uint64_t* total_r, uint64_t n_global) {
@@ -485,21 +519,24 @@ __global__ void resid_totals_kernel(DevScalars* ds, const uint64_t* total_c, con
 // ------------------------------------------------------------------------------------------------
 // spacings of the thresholds k = k0+4*tid .. +3 of tile b (global threshold index), masked to k < m_draws
 __device__ __forceinline__ void tile_spacings(uint64_t seed, uint32_t rho, uint64_t k, uint64_t m_draws, uint64_t e[4]) {
-  spacing_pair(seed, k >> 1, rho, &e[0], &e[1]);
-  spacing_pair(seed, (k >> 1) + 1, rho, &e[2], &e[3]);
+  spacing_pairs_v<2>(seed, k >> 1, rho, e);
 #pragma unroll
   for (int j = 0; j < 4; ++j) if (k + j >= m_draws) e[j] = 0;
 }
 // per-tile sums of the spacings of this rank's thresholds [k_first, k_first + n_tiles*TILE)
 __global__ void __launch_bounds__(GSMC_BLOCK) spacing_sum_kernel(uint64_t seed, uint64_t k_first, const DevScalars* ds,
-                                                                 uint64_t* tile_sums, int conditional) {
+                                                                 uint64_t* tile_sums, int nt, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   if (conditional && !ds->do_resample) return;
-  const uint64_t k = k_first + (uint64_t)blockIdx.x * GSMC_TILE + 4 * threadIdx.x;
-  uint64_t e[4];
-  tile_spacings(seed, ds->rho, k, ds->n_draws, e);
-  const uint64_t t = block_sum_u64(e[0] + e[1] + e[2] + e[3], sm);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = t;
+  const uint32_t rho = ds->rho;
+  const uint64_t m_draws = ds->n_draws;
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+    const uint64_t k = k_first + (uint64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+    uint64_t e[4];
+    tile_spacings(seed, rho, k, m_draws, e);
+    const uint64_t t = block_sum_u64(e[0] + e[1] + e[2] + e[3], sm);
+    if (threadIdx.x == 0) tile_sums[tile] = t;
+  }
 }
 // S_tot = all ranks' spacing totals + the (M+1)-th spacing; runs on every rank after the allgather
 __global__ void spacing_total_kernel(uint64_t seed, DevScalars* ds, int nranks) {
@@ -577,69 +614,73 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
 #define GSMC_WIN_CAP 3072
 __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
                                                                    const DevScalars* ds, const uint64_t* tile_prefix,
-                                                                   const uint32_t* win, uint32_t* anc, int64_t n_out,
+                                                                   const uint32_t* win, uint32_t* anc, int64_t n_out, int nt,
                                                                    int det_offset, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   __shared__ uint64_t cwin[GSMC_WIN_CAP];
   if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws;
-  const uint64_t kt = k_first + (uint64_t)blockIdx.x * GSMC_TILE;
-  if (kt >= m_draws) return;
-  const uint64_t k = kt + 4 * threadIdx.x;
-  uint64_t e[4];
-  tile_spacings(seed, ds->rho, k, m_draws, e);
-  uint64_t tot;
-  const uint64_t tsum = e[0] + e[1] + e[2] + e[3];
+  const uint32_t rho = ds->rho;
+  const MulDiv md = threshold_muldiv(ds);
   uint64_t base = 0;
   for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
-  uint64_t S = base + tile_prefix[blockIdx.x] + block_scan_u64(tsum, sm, &tot) - tsum;
-  const MulDiv md = threshold_muldiv(ds);
-  uint32_t a[4];
-  bool have[4];
-  uint64_t T[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    S += e[j];
-    have[j] = k + j < m_draws;
-    T[j] = have[j] ? muldiv_floor(S, md) : 0;            // T_k = floor(S_k C_N / S_tot), exact
-  }
-  const uint32_t w0 = win[blockIdx.x], w1 = win[blockIdx.x + 1];
-  const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT);
-  const int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK), hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
-  if (r0 == (int)(w1 >> GSMC_ANC_RANK_SHIFT) && hi - lo + 1 <= GSMC_WIN_CAP) {
-    // common case: the whole tile maps into one rank's segment and the window fits in shared memory
-    uint64_t off = 0;
-    for (int q = 0; q < r0; ++q) off += ds->cdf_rank_total[q];
-    const uint64_t* seg = v.seg[r0];
-    const int len = (int)(hi - lo + 1);
-    for (int j = threadIdx.x; j < len; j += GSMC_BLOCK) cwin[j] = off + __ldg(seg + lo + j);
-    __syncthreads();
-    int pos = 0;
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+    const uint64_t kt = k_first + (uint64_t)tile * GSMC_TILE;
+    if (kt >= m_draws) break;                            // uniform per block
+    const uint64_t k = kt + 4 * threadIdx.x;
+    uint64_t e[4];
+    tile_spacings(seed, rho, k, m_draws, e);
+    uint64_t tot;
+    const uint64_t tsum = e[0] + e[1] + e[2] + e[3];
+    uint64_t S = base + tile_prefix[tile] + block_scan_u64(tsum, sm, &tot) - tsum;
+    uint32_t a[4];
+    bool have[4];
+    uint64_t T[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (!have[j]) { a[j] = 0; continue; }
-      if (j == 0) {
-        int l = 0, h = len;                               // min{p : cwin[p] > T}, else len
-        while (l < h) { const int mid = (l + h) >> 1; if (cwin[mid] > T[0]) h = mid; else l = mid + 1; }
-        pos = l;
-      } else {
-        // thresholds are sorted, so ancestors are monotone and on average one slot apart: walk
-        while (pos < len && cwin[pos] <= T[j]) ++pos;
-      }
-      if (pos >= len) pos = len - 1;
-      a[j] = ((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pos);
+      S += e[j];
+      have[j] = k + j < m_draws;
+      T[j] = have[j] ? muldiv_floor(S, md) : 0;          // T_k = floor(S_k C_N / S_tot), exact
     }
-  } else {
+    const uint32_t w0 = win[tile], w1 = win[tile + 1];
+    const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT);
+    const int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK), hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
+    if (r0 == (int)(w1 >> GSMC_ANC_RANK_SHIFT) && hi - lo + 1 <= GSMC_WIN_CAP) {
+      // common case: the whole tile maps into one rank's segment and the window fits in shared memory
+      uint64_t off = 0;
+      for (int q = 0; q < r0; ++q) off += ds->cdf_rank_total[q];
+      const uint64_t* seg = v.seg[r0];
+      const int len = (int)(hi - lo + 1);
+      __syncthreads();                                   // previous tile's readers are done with cwin
+      for (int j = threadIdx.x; j < len; j += GSMC_BLOCK) cwin[j] = off + __ldg(seg + lo + j);
+      __syncthreads();
+      int pos = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, T[j]) : 0;
-  }
-  // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
-  const int64_t o = (int64_t)(k - k_first) + (det_offset ? (int64_t)ds->n_det : 0);
-  if (!det_offset && have[3] && o + 3 < n_out) {
-    *reinterpret_cast<uint4*>(anc + o) = make_uint4(a[0], a[1], a[2], a[3]);
-  } else {
+      for (int j = 0; j < 4; ++j) {
+        if (!have[j]) { a[j] = 0; continue; }
+        if (j == 0) {
+          int l = 0, h = len;                             // min{p : cwin[p] > T}, else len
+          while (l < h) { const int mid = (l + h) >> 1; if (cwin[mid] > T[0]) h = mid; else l = mid + 1; }
+          pos = l;
+        } else {
+          // thresholds are sorted, so ancestors are monotone and on average one slot apart: walk
+          while (pos < len && cwin[pos] <= T[j]) ++pos;
+        }
+        if (pos >= len) pos = len - 1;
+        a[j] = ((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pos);
+      }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) if (have[j] && o + j < n_out) anc[o + j] = a[j];
+      for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, T[j]) : 0;
+    }
+    // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
+    const int64_t o = (int64_t)(k - k_first) + (det_offset ? (int64_t)ds->n_det : 0);
+    if (!det_offset && have[3] && o + 3 < n_out) {
+      *reinterpret_cast<uint4*>(anc + o) = make_uint4(a[0], a[1], a[2], a[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (have[j] && o + j < n_out) anc[o + j] = a[j];
+    }
   }
 }
 

@@ -62,8 +62,8 @@ GM_HD double random_normal(double mu, double std, double z) { return mu + std * 
 struct LgssmModel {
   static constexpr int D = 1;
   static constexpr int SMEM_DOUBLES = 0;
-  GM_HD static int nz(bool init, int) { (void)init; return 1; }
-  GM_HD static int nu(bool, int) { return 0; }
+  __host__ __device__ static constexpr int nz(bool, int) { return 1; }
+  __host__ __device__ static constexpr int nu(bool, int) { return 0; }
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs& a, bool init, int prop) {
     const double* p = a.p;
@@ -114,8 +114,8 @@ struct LgssmModel {
 struct SvModel {
   static constexpr int D = 1;
   static constexpr int SMEM_DOUBLES = 0;
-  GM_HD static int nz(bool, int) { return 1; }
-  GM_HD static int nu(bool, int) { return 0; }
+  __host__ __device__ static constexpr int nz(bool, int) { return 1; }
+  __host__ __device__ static constexpr int nu(bool, int) { return 0; }
   static bool has_proposal(int prop) { return prop == 0; }
   static void prepare(ModelArgs& a, bool init, int) {
     const double phi = a.p[1], sigma = a.p[2];
@@ -142,8 +142,8 @@ struct SvModel {
 struct BearingsModel {
   static constexpr int D = 4;
   static constexpr int SMEM_DOUBLES = 0;
-  GM_HD static int nz(bool init, int) { return init ? 4 : 2; }
-  GM_HD static int nu(bool, int) { return 0; }
+  __host__ __device__ static constexpr int nz(bool init, int) { return init ? 4 : 2; }
+  __host__ __device__ static constexpr int nu(bool, int) { return 0; }
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs& a, bool, int) {
     const double sw = a.p[8], st = a.p[9];
@@ -212,8 +212,8 @@ struct BearingsModel {
 struct HmmModel {
   static constexpr int D = 1;
   static constexpr int SMEM_DOUBLES = 2 * GSMC_HMM_MAX_K * GSMC_HMM_MAX_K;
-  GM_HD static int nz(bool, int) { return 0; }
-  GM_HD static int nu(bool, int) { return 1; }
+  __host__ __device__ static constexpr int nz(bool, int) { return 0; }
+  __host__ __device__ static constexpr int nu(bool, int) { return 1; }
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs&, bool, int) {}
   template <bool INIT, int PROP>
@@ -280,8 +280,8 @@ struct HmmModel {
 struct RegressionModel {
   static constexpr int D = 2;
   static constexpr int SMEM_DOUBLES = 0;
-  GM_HD static int nz(bool, int) { return 2; }
-  GM_HD static int nu(bool, int) { return 0; }
+  __host__ __device__ static constexpr int nz(bool, int) { return 2; }
+  __host__ __device__ static constexpr int nu(bool, int) { return 0; }
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs& a, bool, int prop) {
     a.nc[0] = make_normc(a.p[3]);
@@ -321,8 +321,8 @@ struct RegressionModel {
 struct NormalNormalModel {
   static constexpr int D = 1;
   static constexpr int SMEM_DOUBLES = 0;
-  GM_HD static int nz(bool, int) { return 1; }
-  GM_HD static int nu(bool, int) { return 0; }
+  __host__ __device__ static constexpr int nz(bool, int) { return 1; }
+  __host__ __device__ static constexpr int nu(bool, int) { return 0; }
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs& a, bool, int prop) {
     a.nc[0] = make_normc(a.p[2]);
