@@ -69,6 +69,7 @@ SIGNATURES = {
     "gsmc_importance_sampling": (C.c_int, [C.POINTER(Config), _dp, C.c_size_t, _dp, C.c_size_t, C.c_int, _dp,
                                            C.c_size_t, _dp, C.POINTER(_H)]),
     "gsmc_run_steps": (C.c_int, [_H, _dp, C.c_size_t, C.c_size_t, C.c_int, _dp, C.c_size_t, C.c_double]),
+    "gsmc_trim": (C.c_int, []),
     "gsmc_local_count": (C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gsmc_state_dim": (C.c_int, [_H, C.POINTER(C.c_int)]),
     "gsmc_synchronize": (C.c_int, [_H]),

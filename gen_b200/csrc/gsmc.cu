@@ -6,7 +6,9 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -80,6 +82,38 @@ static int load_nccl() {
 enum { NCCL_UINT8 = 1 };
 
 // ------------------------------------------------------------------------------------------------
+// slab pool: the big column slabs of a destroyed filter are kept (per device, keyed by size) and
+// handed to the next filter of the same shape, so that repeated initialize_particle_filter calls do not
+// pay cudaMalloc/cudaFree of tens of GB each time. gsmc_trim() / GSMC_NO_POOL=1 release / disable it.
+// ------------------------------------------------------------------------------------------------
+#include <map>
+#include <mutex>
+struct PoolKey { int device; size_t bytes; bool operator<(const PoolKey& o) const { return device != o.device ? device < o.device : bytes < o.bytes; } };
+static std::multimap<PoolKey, void*> g_pool;
+static std::mutex g_pool_mu;
+static bool pool_enabled() { static int on = getenv("GSMC_NO_POOL") ? 0 : 1; return on != 0; }
+static cudaError_t pool_alloc(int device, void** p, size_t bytes) {
+  if (pool_enabled() && bytes >= (1u << 20)) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool.find(PoolKey{device, bytes});
+    if (it != g_pool.end()) { *p = it->second; g_pool.erase(it); return cudaSuccess; }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess && pool_enabled()) {          // out of memory: drop the cache and retry once
+    cudaGetLastError();
+    { std::lock_guard<std::mutex> lk(g_pool_mu); for (auto& kv : g_pool) if (kv.first.device == device) cudaFree(kv.second);
+      for (auto it = g_pool.begin(); it != g_pool.end();) { if (it->first.device == device) it = g_pool.erase(it); else ++it; } }
+    e = cudaMalloc(p, bytes);
+  }
+  return e;
+}
+static void pool_free(int device, void* p, size_t bytes) {
+  if (!p) return;
+  if (pool_enabled() && bytes >= (1u << 20)) { std::lock_guard<std::mutex> lk(g_pool_mu); g_pool.insert({PoolKey{device, bytes}, p}); return; }
+  cudaFree(p);
+}
+
+// ------------------------------------------------------------------------------------------------
 // the filter object
 // ------------------------------------------------------------------------------------------------
 enum KernelClass { KC_PROPAGATE = 0, KC_PROPAGATE_GATHER, KC_FINALIZE, KC_SCAN, KC_SPACINGS, KC_SEARCH, KC_OTHER, KC_COUNT };
@@ -130,6 +164,10 @@ struct gsmc_filter {
   const void* peer_slab[GSMC_MAX_RANKS] = {};
   const uint32_t* peer_anc[GSMC_MAX_RANKS] = {};
   const uint64_t* peer_cdf[GSMC_MAX_RANKS] = {};
+  DevScalars* peer_ds[GSMC_MAX_RANKS] = {};
+  uint32_t xchg_seq = 0;        // sequence number of the fused peer exchanges (same on every rank)
+  bool use_nccl_scalars = false;  // GSMC_NCCL_SCALARS=1: exchange the per-step scalars with ncclAllGather instead
+  size_t bytes_state = 0, bytes_anc = 0, bytes_lw = 0, bytes_cdf = 0;
   // replay staging
   double* d_zrep = nullptr; size_t zrep_n = 0, zrep_cap = 0;
   double* d_urep = nullptr; size_t urep_n = 0, urep_cap = 0;
@@ -234,10 +272,12 @@ static int alloc_buffers(gsmc_filter* f) {
   f->cap = f->cfg.keep_history ? (f->cfg.history_capacity > 0 ? f->cfg.history_capacity : 128) : 2;
   if (f->cap < 2) f->cap = 2;
   f->flag_mod = f->cfg.keep_history ? f->cap + 2 : 4;
-  CK(cudaMalloc(&f->state_slab, (size_t)f->cap * f->D * f->n_pad * rs));
-  CK(cudaMalloc(&f->anc_slab, (size_t)f->cap * f->n_pad * sizeof(uint32_t)));
-  CK(cudaMalloc(&f->lw, f->n_pad * rs));
-  CK(cudaMalloc(&f->cdf, f->n_pad * sizeof(uint64_t)));
+  f->bytes_state = (size_t)f->cap * f->D * f->n_pad * rs; f->bytes_anc = (size_t)f->cap * f->n_pad * sizeof(uint32_t);
+  f->bytes_lw = f->n_pad * rs; f->bytes_cdf = f->n_pad * sizeof(uint64_t);
+  CK(pool_alloc(f->device, &f->state_slab, f->bytes_state));
+  CK(pool_alloc(f->device, (void**)&f->anc_slab, f->bytes_anc));
+  CK(pool_alloc(f->device, &f->lw, f->bytes_lw));
+  CK(pool_alloc(f->device, (void**)&f->cdf, f->bytes_cdf));
   if (f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL) CK(cudaMalloc(&f->cc, f->n_pad * sizeof(uint64_t)));
   CK(cudaMalloc(&f->tile_a, (size_t)f->n_tiles * sizeof(uint64_t)));
   CK(cudaMalloc(&f->tile_b, (size_t)f->n_tiles * sizeof(uint64_t)));
@@ -255,6 +295,7 @@ static int alloc_buffers(gsmc_filter* f) {
   f->peer_slab[f->rank] = f->state_slab;
   f->peer_anc[f->rank] = f->anc_slab;
   f->peer_cdf[f->rank] = f->cdf;
+  f->peer_ds[f->rank] = f->ds;
   return GSMC_OK;
 }
 static void free_buffers(gsmc_filter* f) {
@@ -263,9 +304,11 @@ static void free_buffers(gsmc_filter* f) {
     if (f->peer_slab[r]) cudaIpcCloseMemHandle((void*)f->peer_slab[r]);
     if (f->peer_anc[r]) cudaIpcCloseMemHandle((void*)f->peer_anc[r]);
     if (f->peer_cdf[r]) cudaIpcCloseMemHandle((void*)f->peer_cdf[r]);
-    f->peer_slab[r] = nullptr; f->peer_anc[r] = nullptr; f->peer_cdf[r] = nullptr;
+    if (f->peer_ds[r]) cudaIpcCloseMemHandle((void*)f->peer_ds[r]);
+    f->peer_slab[r] = nullptr; f->peer_anc[r] = nullptr; f->peer_cdf[r] = nullptr; f->peer_ds[r] = nullptr;
   }
-  cudaFree(f->state_slab); cudaFree(f->anc_slab); cudaFree(f->lw); cudaFree(f->cdf); cudaFree(f->cc);
+  pool_free(f->device, f->state_slab, f->bytes_state); pool_free(f->device, f->anc_slab, f->bytes_anc);
+  pool_free(f->device, f->lw, f->bytes_lw); pool_free(f->device, f->cdf, f->bytes_cdf); cudaFree(f->cc);
   cudaFree(f->tile_a); cudaFree(f->tile_b); cudaFree(f->scratch_tot); cudaFree(f->win); cudaFree(f->partials); cudaFree(f->ds);
   cudaFree(f->resampled);
   if (f->h_ds) cudaFreeHost(f->h_ds);
@@ -380,12 +423,17 @@ static int launch_propagate(gsmc_filter* f, bool init, const double* obs, size_t
 // finalize (+ decision when ess_threshold >= 0); leaves the statistics in f->ds
 static int launch_finalize(gsmc_filter* f, double ess_threshold) {
   int* flag = ess_threshold >= 0.0 ? f->resampled + ((f->T + 1) % f->flag_mod) : nullptr;
+  PeerScalars peers;
+  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
+  const int fused = (f->nranks > 1 && !f->use_nccl_scalars) ? 1 : 0;
+  if (fused) f->xchg_seq += 1;
   {
     ProfScope ps(f, KC_FINALIZE);
-    finalize_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_partials, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag);
+    finalize_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_partials, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag,
+                                               peers, f->xchg_seq, fused);
   }
   CK(cudaGetLastError());
-  if (f->nranks > 1) {
+  if (f->nranks > 1 && !fused) {
     NK(g_nccl.AllGather((const char*)f->ds->triples + f->rank * sizeof(LseTriple), f->ds->triples, sizeof(LseTriple), NCCL_UINT8, f->comm, f->stream));
     ProfScope ps(f, KC_FINALIZE);
     decide_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, ess_threshold, (double)f->N, flag);
@@ -393,6 +441,18 @@ static int launch_finalize(gsmc_filter* f, double ess_threshold) {
   }
   return GSMC_OK;
 }
+// All ranks have finished every kernel that reads this rank's slabs (needed before they are reused or freed).
+static int peer_barrier(gsmc_filter* f) {
+  if (f->nranks <= 1 || !f->ds || !f->peer_ds[(f->rank + 1) % f->nranks]) return GSMC_OK;
+  PeerScalars peers;
+  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
+  f->xchg_seq += 1;
+  { ProfScope ps(f, KC_OTHER); peer_barrier_kernel<<<1, 32, 0, f->stream>>>(peers, f->ds, f->rank, f->nranks, f->xchg_seq); }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(f->stream));
+  return GSMC_OK;
+}
+
 static int fetch_scalars(gsmc_filter* f) {
   CK(cudaMemcpyAsync(f->h_ds, f->ds, sizeof(DevScalars), cudaMemcpyDeviceToHost, f->stream));
   CK(cudaStreamSynchronize(f->stream));
@@ -428,9 +488,14 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
   // 1. integer weights -> tile sums -> tile prefixes and this rank's total
   { ProfScope ps(f, KC_SCAN); qsum_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, nt, conditional); }
-  { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[f->rank], nullptr, conditional); }
+  PeerScalars peers;
+  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
+  const bool fused = f->nranks > 1 && !f->use_nccl_scalars;
+  if (fused) f->xchg_seq += 1;
+  { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[f->rank], nullptr, conditional,
+                                                                          peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0); }
   CK(cudaGetLastError());
-  if (f->nranks > 1)
+  if (f->nranks > 1 && !fused)
     NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
   { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, (uint64_t)f->N, residual ? 0 : 1, conditional); }
   if (!residual) {
@@ -439,7 +504,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   } else {
     { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
     { ProfScope ps(f, KC_SCAN); resid_sum_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, nt, conditional); }
-    { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, f->tile_b, nt, f->ds, f->scratch_tot, f->scratch_tot + 1, conditional); }
+    { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, f->tile_b, nt, f->ds, f->scratch_tot, f->scratch_tot + 1, conditional, peers, 0, 1, 0, 0); }
     { ProfScope ps(f, KC_OTHER); resid_totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->scratch_tot, f->scratch_tot + 1, (uint64_t)f->N); }
     { ProfScope ps(f, KC_SCAN); resid_cdf_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, f->cc, f->cdf, nt, conditional); }
     { ProfScope ps(f, KC_SEARCH); det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(f->cc, f->n, f->ds, anc, conditional); }
@@ -457,14 +522,16 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     // 2. sorted uniforms: spacing tile sums -> prefixes -> S_tot
     const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
     { ProfScope ps(f, KC_SPACINGS); spacing_sum_kernel<<<pg, GSMC_BLOCK, 0, f->stream>>>(f->cfg.seed, k_first, f->ds, f->tile_b, nt, conditional); }
-    { ProfScope ps(f, KC_SPACINGS); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_b, nullptr, nt, f->ds, &f->ds->spacing_rank_total[f->rank], nullptr, conditional); }
+    if (fused) f->xchg_seq += 1;
+    { ProfScope ps(f, KC_SPACINGS); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_b, nullptr, nt, f->ds, &f->ds->spacing_rank_total[f->rank], nullptr, conditional,
+                                                                                peers, f->rank, f->nranks, f->xchg_seq, fused ? 2 : 0); }
     CK(cudaGetLastError());
-    if (f->nranks > 1)
+    if (f->nranks > 1 && !fused)
       NK(g_nccl.AllGather((const char*)(f->ds->spacing_rank_total + f->rank), f->ds->spacing_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
     { ProfScope ps(f, KC_SPACINGS); spacing_total_kernel<<<1, 32, 0, f->stream>>>(f->cfg.seed, f->ds, f->nranks); }
     // 3. ancestors
     { ProfScope ps(f, KC_SEARCH);
-      partition_kernel<<<(nt + 1 + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, nt, f->win, conditional); }
+      partition_kernel<<<(nt + 1 + GSMC_BLOCK / 32 - 1) / (GSMC_BLOCK / 32), GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, nt, f->win, conditional); }
     { ProfScope ps(f, KC_SEARCH);
       search_sorted_kernel<<<pg, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
   }
@@ -530,6 +597,7 @@ GSMC_API int gsmc_create(const gsmc_config* cfg, const double* params, size_t n_
 GSMC_API void gsmc_destroy(gsmc_handle f) {
   if (!f) return;
   cudaSetDevice(f->device);
+  peer_barrier(f);
   if (f->stream) cudaStreamSynchronize(f->stream);
   harvest_profile(f);
   for (ProfEvent& e : f->prof_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -547,8 +615,9 @@ GSMC_API int gsmc_reset(gsmc_handle f) {
   CK(cudaSetDevice(f->device));
   f->T = 0; f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
   f->last_resample_step = 0; f->n_sample_calls = 0; f->zrep_n = 0; f->urep_n = 0;
+  CKRC(peer_barrier(f));
   if (f->ds) {
-    CK(cudaMemsetAsync(f->ds, 0, sizeof(DevScalars), f->stream));
+    CK(cudaMemsetAsync(f->ds, 0, offsetof(DevScalars, mbox), f->stream));   // mailboxes keep their sequence tags
     CK(cudaMemsetAsync(f->resampled, 0, (size_t)f->flag_mod * sizeof(int), f->stream));
   }
   return GSMC_OK;
@@ -596,11 +665,13 @@ GSMC_API int gsmc_comm_attach(gsmc_handle f, gsmc_comm c) {
   if (nranks == 1) return GSMC_OK;
   // allocate now and exchange IPC handles of the slabs peers read (state, ancestors, CDF)
   CKRC(alloc_buffers(f));
-  struct Handles { cudaIpcMemHandle_t slab, anc, cdf; };
+  struct Handles { cudaIpcMemHandle_t slab, anc, cdf, ds; };
+  f->use_nccl_scalars = getenv("GSMC_NCCL_SCALARS") != nullptr;
   Handles mine;
   CK(cudaIpcGetMemHandle(&mine.slab, f->state_slab));
   CK(cudaIpcGetMemHandle(&mine.anc, f->anc_slab));
   CK(cudaIpcGetMemHandle(&mine.cdf, f->cdf));
+  CK(cudaIpcGetMemHandle(&mine.ds, f->ds));
   Handles* d_all = nullptr;
   CK(cudaMalloc(&d_all, sizeof(Handles) * nranks));
   CK(cudaMemcpyAsync(d_all + rank, &mine, sizeof mine, cudaMemcpyHostToDevice, f->stream));
@@ -611,11 +682,12 @@ GSMC_API int gsmc_comm_attach(gsmc_handle f, gsmc_comm c) {
   cudaFree(d_all);
   for (int r = 0; r < nranks; ++r) {
     if (r == rank) continue;
-    void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+    void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
     CK(cudaIpcOpenMemHandle(&p0, all[r].slab, cudaIpcMemLazyEnablePeerAccess));
     CK(cudaIpcOpenMemHandle(&p1, all[r].anc, cudaIpcMemLazyEnablePeerAccess));
     CK(cudaIpcOpenMemHandle(&p2, all[r].cdf, cudaIpcMemLazyEnablePeerAccess));
-    f->peer_slab[r] = p0; f->peer_anc[r] = (const uint32_t*)p1; f->peer_cdf[r] = (const uint64_t*)p2;
+    CK(cudaIpcOpenMemHandle(&p3, all[r].ds, cudaIpcMemLazyEnablePeerAccess));
+    f->peer_slab[r] = p0; f->peer_anc[r] = (const uint32_t*)p1; f->peer_cdf[r] = (const uint64_t*)p2; f->peer_ds[r] = (DevScalars*)p3;
   }
   return GSMC_OK;
 }
@@ -832,12 +904,12 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
     const int pg = nt < f->sm_count * 6 ? nt : f->sm_count * 6;
     if (f->f32) {
       { ProfScope ps(f, KC_SCAN); qsum_kernel<float><<<pg, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, nt, 0); }
-      { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0); }
+      { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0, PeerScalars(), 0, 1, 0, 0); }
       { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, 1, (uint64_t)f->N, 0, 0); }
       { ProfScope ps(f, KC_SCAN); cdf_kernel<float><<<pg, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, 0); }
     } else {
       { ProfScope ps(f, KC_SCAN); qsum_kernel<double><<<pg, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, nt, 0); }
-      { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0); }
+      { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0, PeerScalars(), 0, 1, 0, 0); }
       { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, 1, (uint64_t)f->N, 0, 0); }
       { ProfScope ps(f, KC_SCAN); cdf_kernel<double><<<pg, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, 0); }
     }
@@ -907,6 +979,15 @@ GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, si
     cudaMemsetAsync(&f->ds->error, 0, sizeof(int), f->stream);
     return fail(GSMC_E_DEGENERATE, "total weight became zero or not finite during the run");
   }
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_trim(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  int dev = 0; cudaGetDevice(&dev);
+  for (auto& kv : g_pool) { cudaSetDevice(kv.first.device); cudaFree(kv.second); }
+  g_pool.clear();
+  cudaSetDevice(dev);
   return GSMC_OK;
 }
 

@@ -50,7 +50,48 @@ struct DevScalars {
   LseTriple triples[GSMC_MAX_RANKS];
   uint64_t cdf_rank_total[GSMC_MAX_RANKS];      // per-rank integer weight totals (allgathered)
   uint64_t spacing_rank_total[GSMC_MAX_RANKS];  // per-rank spacing totals (allgathered)
+  // LL mailboxes for the fused peer-memory exchange: [parity][source rank][word]; a word is
+  // (payload 32 bit) | (sequence number << 32), written by the source rank with one 8-byte store.
+  unsigned long long mbox[2][GSMC_MAX_RANKS][8];
 };
+
+// Peer-memory exchange of a few scalars between the ranks (one kernel per GPU, each GPU's kernel only
+// waits for stores issued by the OTHER GPUs' kernels). Every rank writes its payload, 32 bits per
+// 8-byte word tagged with the sequence number, straight into every peer's mailbox over NVLink
+// (no fence needed: data and tag arrive in one atomic store, as in NCCL's LL protocol); a reader spins
+// on the tag. Mailboxes alternate by sequence parity, which is enough because a rank can be at most
+// one exchange ahead of any other. The spin is bounded (~2 s) so a lost peer cannot hang the GPU.
+struct PeerScalars { DevScalars* ds[GSMC_MAX_RANKS]; };
+__device__ __forceinline__ void ll_send(DevScalars* peer, int my_rank, uint32_t seq, const uint32_t* words, int n) {
+  volatile unsigned long long* box = peer->mbox[seq & 1][my_rank];
+  for (int w = 0; w < n; ++w) box[w] = (unsigned long long)words[w] | ((unsigned long long)seq << 32);
+}
+__device__ __forceinline__ bool ll_recv(DevScalars* self, int src, uint32_t seq, uint32_t* words, int n) {
+  volatile unsigned long long* box = self->mbox[seq & 1][src];
+  const long long t0 = clock64();
+  for (int w = 0; w < n; ++w) {
+    unsigned long long v;
+    while ((uint32_t)((v = box[w]) >> 32) != seq) {
+      if (clock64() - t0 > 4000000000LL) return false;
+    }
+    words[w] = (uint32_t)v;
+  }
+  return true;
+}
+// all ranks: send `n64` u64 values to everybody, receive everybody's into out[r*n64 ..]; threads 0..R-1 of one block
+__device__ __forceinline__ void ll_allgather_u64(const PeerScalars& peers, DevScalars* self, int my_rank, int nranks, uint32_t seq,
+                                                 const uint64_t* mine, int n64, uint64_t* out) {
+  const int r = threadIdx.x;
+  if (r < nranks) {
+    uint32_t w[8];
+    for (int j = 0; j < n64; ++j) { w[2 * j] = (uint32_t)mine[j]; w[2 * j + 1] = (uint32_t)(mine[j] >> 32); }
+    ll_send(peers.ds[r], my_rank, seq, w, 2 * n64);
+    uint32_t g[8];
+    if (!ll_recv(self, r, seq, g, 2 * n64)) { self->error = 2; return; }
+    for (int j = 0; j < n64; ++j) out[r * n64 + j] = (uint64_t)g[2 * j] | ((uint64_t)g[2 * j + 1] << 32);
+  }
+}
+
 
 template <typename Real> struct Vec2T;
 template <> struct Vec2T<double> { typedef double2 type; };
@@ -331,8 +372,10 @@ __device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, d
 
 __global__ void __launch_bounds__(1024) finalize_kernel(const LseTriple* partials, int nblk, DevScalars* ds,
                                                         int rank, int nranks, double ess_threshold,
-                                                        double n_global, int* resampled_flag_out) {
+                                                        double n_global, int* resampled_flag_out,
+                                                        PeerScalars peers, uint32_t seq, int fused_exchange) {
   __shared__ double sm[3][32];
+  __shared__ uint64_t mine[3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // pass 1: global max of the block maxima
   double m = -gm_inf();
@@ -362,8 +405,25 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const LseTriple* partial
     LseTriple tr; tr.m = M; tr.s1 = t1; tr.s2 = t2;
     ds->triples[rank] = tr;
     if (nranks == 1) combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out);
+    mine[0] = gm_to_bits(M); mine[1] = gm_to_bits(t1); mine[2] = gm_to_bits(t2);
+  }
+  if (nranks > 1 && fused_exchange) {
+    // logsumexp/ESS "allreduce": every rank gathers all triples over NVLink peer stores and merges
+    // them in rank order, so all ranks take the same decision without a separate collective.
+    __syncthreads();
+    ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 3, reinterpret_cast<uint64_t*>(ds->triples));
+    __syncthreads();
+    if (threadIdx.x == 0) combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out);
   }
 }
+// cross-GPU barrier (peer-memory exchange of one word): nobody passes until every rank has arrived
+__global__ void peer_barrier_kernel(PeerScalars peers, DevScalars* ds, int rank, int nranks, uint32_t seq) {
+  __shared__ uint64_t mine[1];
+  __shared__ uint64_t got[GSMC_MAX_RANKS];
+  mine[0] = seq;
+  ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 1, got);
+}
+
 // multi-rank: runs after the allgather of ds->triples
 __global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, double n_global, int* resampled_flag_out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out);
@@ -403,9 +463,17 @@ __global__ void __launch_bounds__(GSMC_BLOCK) qsum_kernel(const Real* lw, int64_
 
 // phase 2: exclusive scan of up to 2 arrays of tile sums (one block); totals go to total0/total1.
 // Each thread owns a run of consecutive elements (local serial scan), one block-wide scan of the run sums.
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t* a1, int nt, const DevScalars* ds,
-                                                          uint64_t* total0, uint64_t* total1, int conditional) {
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t* a1, int nt, DevScalars* ds,
+                                                          uint64_t* total0, uint64_t* total1, int conditional,
+                                                          PeerScalars peers, int rank, int nranks, uint32_t seq, int exchange_what) {
   __shared__ uint64_t sm[33];
+  __shared__ uint64_t mine[1];
+  // the exchange runs on every rank even when no resample was decided: peers are waiting for it
+  if (exchange_what && nranks > 1 && conditional && !ds->do_resample) {
+    mine[0] = 0;
+    ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 1, exchange_what == 1 ? ds->cdf_rank_total : ds->spacing_rank_total);
+    return;
+  }
   if (conditional && !ds->do_resample) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per = (nt + 1023) / 1024;
@@ -430,9 +498,11 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t
     __syncthreads();
     uint64_t acc = x - run + (warp ? sm[warp - 1] : 0);       // exclusive prefix of this thread's run
     for (int i = lo; i < hi; ++i) { const uint64_t v = a[i]; a[i] = acc; acc += v; }
-    if (threadIdx.x == 0) { if (arr == 0) *total0 = sm[31]; else *total1 = sm[31]; }
+    if (threadIdx.x == 0) { if (arr == 0) { *total0 = sm[31]; mine[0] = sm[31]; } else *total1 = sm[31]; }
     __syncthreads();
   }
+  if (exchange_what && nranks > 1)
+    ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 1, exchange_what == 1 ? ds->cdf_rank_total : ds->spacing_rank_total);
 }
 
 // phase 3: local inclusive CDF  cdf[i] = tile_prefix[b] + inclusive scan within the tile
@@ -582,6 +652,35 @@ __device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevSca
   if (j > v.n_per - 1) j = v.n_per - 1;           // T == C_N can only happen when the last spacing is 0
   return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
 }
+// Same result as search_global, computed by a full warp: 32 probes per round trip (32-ary search), so a
+// search over a peer's segment costs ~5 NVLink round trips instead of ~24.
+__device__ __forceinline__ uint32_t search_global_warp(const CdfView& v, const DevScalars* ds, uint64_t T) {
+  const int lane = threadIdx.x & 31;
+  uint64_t off = 0;
+  int r = 0;
+  for (; r < v.nranks - 1; ++r) {
+    if (off + ds->cdf_rank_total[r] > T) break;
+    off += ds->cdf_rank_total[r];
+  }
+  const uint64_t* seg = v.seg[r];
+  int64_t lo = 0, hi = v.n_per;                 // answer in [lo, hi]; hi = n_per means "none"
+  while (hi > lo) {
+    const int64_t step = (hi - lo + 31) >> 5;
+    const int64_t p = lo + (int64_t)lane * step;
+    const bool pred = (p >= hi) || (off + __ldg(seg + p) > T);
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    const int f = mask ? __ffs((int)mask) - 1 : 32;
+    const int64_t new_hi = (f == 32) ? hi : lo + (int64_t)f * step;
+    const int64_t new_lo = (f == 0) ? lo : lo + (int64_t)(f - 1) * step + 1;
+    hi = new_hi < hi ? new_hi : hi;
+    lo = new_lo;
+    if (f == 0) hi = lo;
+  }
+  int64_t j = lo;
+  if (j > v.n_per - 1) j = v.n_per - 1;
+  return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
+}
+
 __device__ __forceinline__ MulDiv threshold_muldiv(const DevScalars* ds) {
   MulDiv md;
   md.b = ds->cdf_total; md.d = ds->spacing_total; md.ratio = ds->thr_ratio; md.inv_d = ds->thr_inv;
@@ -594,18 +693,23 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
                                                                const DevScalars* ds, const uint64_t* tile_prefix, int nt,
                                                                uint32_t* win, int conditional) {
   if (conditional && !ds->do_resample) return;
-  const int b = blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (GSMC_BLOCK / 32) + (threadIdx.x >> 5);      // one warp per boundary
   if (b > nt) return;
   const uint64_t m_draws = ds->n_draws;
   const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
-  if (kt >= m_draws) { win[b] = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1); return; }
+  if (kt >= m_draws) {
+    if (lane == 0) win[b] = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
+    return;
+  }
   uint64_t S = 0;
   for (int r = 0; r < rank; ++r) S += ds->spacing_rank_total[r];
   S += (b == nt) ? ds->spacing_rank_total[rank] : tile_prefix[b];
   uint64_t e0, e1;
   spacing_pair(seed, kt >> 1, ds->rho, &e0, &e1);     // kt is a multiple of the tile size: even element
   S += e0;
-  win[b] = search_global(v, ds, muldiv_floor(S, threshold_muldiv(ds)));
+  const uint32_t w = search_global_warp(v, ds, muldiv_floor(S, threshold_muldiv(ds)));
+  if (lane == 0) win[b] = w;
 }
 
 // Sorted mode, step 2. Tile b of this rank handles thresholds k_first + b*TILE + [0, TILE) and writes
@@ -643,16 +747,21 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
       T[j] = have[j] ? muldiv_floor(S, md) : 0;          // T_k = floor(S_k C_N / S_tot), exact
     }
     const uint32_t w0 = win[tile], w1 = win[tile + 1];
-    const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT);
+    const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT), r1 = (int)(w1 >> GSMC_ANC_RANK_SHIFT);
     const int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK), hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
-    if (r0 == (int)(w1 >> GSMC_ANC_RANK_SHIFT) && hi - lo + 1 <= GSMC_WIN_CAP) {
-      // common case: the whole tile maps into one rank's segment and the window fits in shared memory
+    // window = [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the head [0, hi] of r0+1
+    const int64_t len_a = (r1 == r0) ? hi - lo + 1 : v.n_per - lo;
+    const int64_t len_b = (r1 == r0) ? 0 : hi + 1;
+    if ((r1 == r0 || r1 == r0 + 1) && len_a + len_b <= GSMC_WIN_CAP) {
       uint64_t off = 0;
       for (int q = 0; q < r0; ++q) off += ds->cdf_rank_total[q];
-      const uint64_t* seg = v.seg[r0];
-      const int len = (int)(hi - lo + 1);
+      const uint64_t off_b = off + ds->cdf_rank_total[r0];
+      const uint64_t* seg_a = v.seg[r0];
+      const uint64_t* seg_b = v.seg[r1];
+      const int la = (int)len_a, len = (int)(len_a + len_b);
       __syncthreads();                                   // previous tile's readers are done with cwin
-      for (int j = threadIdx.x; j < len; j += GSMC_BLOCK) cwin[j] = off + __ldg(seg + lo + j);
+      for (int j = threadIdx.x; j < len; j += GSMC_BLOCK)
+        cwin[j] = j < la ? off + __ldg(seg_a + lo + j) : off_b + __ldg(seg_b + (j - la));
       __syncthreads();
       int pos = 0;
 #pragma unroll
@@ -667,7 +776,8 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
           while (pos < len && cwin[pos] <= T[j]) ++pos;
         }
         if (pos >= len) pos = len - 1;
-        a[j] = ((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pos);
+        a[j] = pos < la ? (((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pos))
+                        : (((uint32_t)r1 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pos - la));
       }
     } else {
 #pragma unroll

@@ -100,7 +100,10 @@ GSMC_API int gsmc_reset(gsmc_handle h);
  * (the host does that, e.g. through torch.distributed); each rank creates one communicator and
  * attaches its filters to it before gsmc_init. After attach the handle owns particles
  * [rank*N/R, (rank+1)*N/R). No reference equivalent (the reference is single-process);
- * SURVEY.md section 8(e). */
+ * SURVEY.md section 8(e). NCCL creates the communicator and carries the one-time exchange of the
+ * CUDA-IPC handles; the per-step scalars (logsumexp triples, integer weight and spacing totals) travel
+ * as peer-memory stores fused into the finalize/scan kernels (set GSMC_NCCL_SCALARS=1 to use
+ * ncclAllGather for them instead), and remote ancestors are read with peer-memory loads. */
 typedef struct gsmc_comm_s* gsmc_comm;
 GSMC_API int gsmc_comm_unique_id(void* id_out, size_t nbytes /* >= 128 */);
 GSMC_API int gsmc_comm_create(const void* unique_id, size_t nbytes, int rank, int nranks, int device, gsmc_comm* out);
@@ -165,6 +168,9 @@ GSMC_API int gsmc_importance_sampling(const gsmc_config* cfg, const double* para
 GSMC_API int gsmc_run_steps(gsmc_handle h, const double* obs, size_t n_steps, size_t n_obs,
                             int proposal_id, const double* proposal_params, size_t n_proposal_params,
                             double ess_threshold);
+
+/* Release the slab pool (column slabs of destroyed filters are cached per device for reuse). */
+GSMC_API int gsmc_trim(void);
 
 GSMC_API int gsmc_local_count(gsmc_handle h, uint64_t* n_local, uint64_t* first_global);
 GSMC_API int gsmc_state_dim(gsmc_handle h, int* dim);
