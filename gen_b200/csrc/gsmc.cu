@@ -93,7 +93,7 @@ static std::multimap<PoolKey, void*> g_pool;
 static std::mutex g_pool_mu;
 static bool pool_enabled() { static int on = getenv("GSMC_NO_POOL") ? 0 : 1; return on != 0; }
 static cudaError_t pool_alloc(int device, void** p, size_t bytes) {
-  if (pool_enabled() && bytes >= (1u << 20)) {
+  if (pool_enabled()) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     auto it = g_pool.find(PoolKey{device, bytes});
     if (it != g_pool.end()) { *p = it->second; g_pool.erase(it); return cudaSuccess; }
@@ -107,9 +107,19 @@ static cudaError_t pool_alloc(int device, void** p, size_t bytes) {
   }
   return e;
 }
+static std::vector<DevScalars*> g_pinned_pool;
+static cudaError_t pinned_alloc(DevScalars** p) {
+  { std::lock_guard<std::mutex> lk(g_pool_mu); if (pool_enabled() && !g_pinned_pool.empty()) { *p = g_pinned_pool.back(); g_pinned_pool.pop_back(); return cudaSuccess; } }
+  return cudaMallocHost(p, sizeof(DevScalars));
+}
+static void pinned_free(DevScalars* p) {
+  if (!p) return;
+  if (pool_enabled()) { std::lock_guard<std::mutex> lk(g_pool_mu); g_pinned_pool.push_back(p); return; }
+  cudaFreeHost(p);
+}
 static void pool_free(int device, void* p, size_t bytes) {
   if (!p) return;
-  if (pool_enabled() && bytes >= (1u << 20)) { std::lock_guard<std::mutex> lk(g_pool_mu); g_pool.insert({PoolKey{device, bytes}, p}); return; }
+  if (pool_enabled()) { std::lock_guard<std::mutex> lk(g_pool_mu); g_pool.insert({PoolKey{device, bytes}, p}); return; }
   cudaFree(p);
 }
 
@@ -186,6 +196,7 @@ struct gsmc_filter {
   int64_t prof_n[KC_COUNT] = {};
   int64_t launches = 0;
   cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+  cudaEvent_t decision_ev = nullptr;   // recorded after the D2H copy of the decision
 };
 
 static size_t real_size(const gsmc_filter* f) { return f->f32 ? 4 : 8; }
@@ -278,15 +289,15 @@ static int alloc_buffers(gsmc_filter* f) {
   CK(pool_alloc(f->device, (void**)&f->anc_slab, f->bytes_anc));
   CK(pool_alloc(f->device, &f->lw, f->bytes_lw));
   CK(pool_alloc(f->device, (void**)&f->cdf, f->bytes_cdf));
-  if (f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL) CK(cudaMalloc(&f->cc, f->n_pad * sizeof(uint64_t)));
-  CK(cudaMalloc(&f->tile_a, (size_t)f->n_tiles * sizeof(uint64_t)));
-  CK(cudaMalloc(&f->tile_b, (size_t)f->n_tiles * sizeof(uint64_t)));
-  CK(cudaMalloc(&f->scratch_tot, 4 * sizeof(uint64_t)));
-  CK(cudaMalloc(&f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t)));
-  CK(cudaMalloc(&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
-  CK(cudaMalloc(&f->ds, sizeof(DevScalars)));
-  CK(cudaMallocHost(&f->h_ds, sizeof(DevScalars)));
-  CK(cudaMalloc(&f->resampled, (size_t)f->flag_mod * sizeof(int)));
+  if (f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL) CK(pool_alloc(f->device, (void**)&f->cc, f->n_pad * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->tile_a, (size_t)f->n_tiles * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->tile_b, (size_t)f->n_tiles * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->scratch_tot, 4 * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t)));
+  CK(pool_alloc(f->device, (void**)&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
+  CK(pool_alloc(f->device, (void**)&f->ds, sizeof(DevScalars)));
+  CK(pinned_alloc(&f->h_ds));
+  CK(pool_alloc(f->device, (void**)&f->resampled, (size_t)f->flag_mod * sizeof(int)));
   CK(cudaMemsetAsync(f->ds, 0, sizeof(DevScalars), f->stream));
   CK(cudaMemsetAsync(f->resampled, 0, (size_t)f->flag_mod * sizeof(int), f->stream));
   // pad lanes of the log-weight column are read by vector loads: keep them finite and harmless
@@ -308,10 +319,12 @@ static void free_buffers(gsmc_filter* f) {
     f->peer_slab[r] = nullptr; f->peer_anc[r] = nullptr; f->peer_cdf[r] = nullptr; f->peer_ds[r] = nullptr;
   }
   pool_free(f->device, f->state_slab, f->bytes_state); pool_free(f->device, f->anc_slab, f->bytes_anc);
-  pool_free(f->device, f->lw, f->bytes_lw); pool_free(f->device, f->cdf, f->bytes_cdf); cudaFree(f->cc);
-  cudaFree(f->tile_a); cudaFree(f->tile_b); cudaFree(f->scratch_tot); cudaFree(f->win); cudaFree(f->partials); cudaFree(f->ds);
-  cudaFree(f->resampled);
-  if (f->h_ds) cudaFreeHost(f->h_ds);
+  pool_free(f->device, f->lw, f->bytes_lw); pool_free(f->device, f->cdf, f->bytes_cdf); pool_free(f->device, f->cc, f->n_pad * sizeof(uint64_t));
+  pool_free(f->device, f->tile_a, (size_t)f->n_tiles * sizeof(uint64_t)); pool_free(f->device, f->tile_b, (size_t)f->n_tiles * sizeof(uint64_t));
+  pool_free(f->device, f->scratch_tot, 4 * sizeof(uint64_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
+  pool_free(f->device, f->partials, (size_t)f->n_tiles * sizeof(LseTriple)); pool_free(f->device, f->ds, sizeof(DevScalars));
+  pool_free(f->device, f->resampled, (size_t)f->flag_mod * sizeof(int));
+  pinned_free(f->h_ds);
   f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
   f->tile_a = f->tile_b = f->scratch_tot = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
   f->resampled = nullptr;
@@ -584,12 +597,13 @@ GSMC_API int gsmc_create(const gsmc_config* cfg, const double* params, size_t n_
   if (f->sm_count < 1) f->sm_count = 148;
   f->params.assign(params, params + n_params);
   f->N = (int64_t)cfg->num_particles; f->n = f->N; f->first = 0;
-  if (cudaMalloc(&f->d_params, n_params * sizeof(double)) != cudaSuccess ||
+  if (pool_alloc(f->device, (void**)&f->d_params, n_params * sizeof(double)) != cudaSuccess ||
       cudaMemcpy(f->d_params, params, n_params * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
     gsmc_destroy(f);
     return fail(GSMC_E_CUDA, "parameter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   cudaEventCreate(&f->timer_a); cudaEventCreate(&f->timer_b);
+  cudaEventCreateWithFlags(&f->decision_ev, cudaEventDisableTiming);
   *out = f;
   return GSMC_OK;
 }
@@ -602,9 +616,10 @@ GSMC_API void gsmc_destroy(gsmc_handle f) {
   harvest_profile(f);
   for (ProfEvent& e : f->prof_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   free_buffers(f);
-  cudaFree(f->d_params); cudaFree(f->d_obs); cudaFree(f->d_zrep); cudaFree(f->d_urep); cudaFree(f->d_f64);
+  pool_free(f->device, f->d_params, f->params.size() * sizeof(double)); cudaFree(f->d_obs); cudaFree(f->d_zrep); cudaFree(f->d_urep); cudaFree(f->d_f64);
   if (f->timer_a) cudaEventDestroy(f->timer_a);
   if (f->timer_b) cudaEventDestroy(f->timer_b);
+  if (f->decision_ev) cudaEventDestroy(f->decision_ev);
   if (f->own_stream && f->stream) cudaStreamDestroy(f->stream);
   delete f;
 }
@@ -744,8 +759,15 @@ GSMC_API int gsmc_maybe_resample(gsmc_handle f, double ess_threshold, int* did_r
     if (ess_out) *ess_out = (double)f->N;
     return GSMC_OK;
   }
+  const bool replay = f->urep_n > 0;
   CKRC(launch_finalize(f, ess_threshold));
-  CKRC(fetch_scalars(f));
+  // The decision lives on the device. Copy it out, and -- unless exported uniforms are being replayed --
+  // enqueue the resampling kernels right away in their conditional form (they exit at once when no
+  // resample was decided), so the GPU never idles while the host reads the Bool this call returns.
+  CK(cudaMemcpyAsync(f->h_ds, f->ds, sizeof(DevScalars), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaEventRecord(f->decision_ev, f->stream));
+  if (!replay) CKRC(launch_resample(f, 1, false));
+  CK(cudaEventSynchronize(f->decision_ev));
   f->stats_fresh = true;
   f->decided_since_step = true;
   if (f->h_ds->error) {
@@ -755,8 +777,7 @@ GSMC_API int gsmc_maybe_resample(gsmc_handle f, double ess_threshold, int* did_r
   }
   const int did = f->h_ds->do_resample;
   if (did) {
-    const bool replay = f->urep_n > 0;
-    CKRC(launch_resample(f, 0, replay));
+    if (replay) CKRC(launch_resample(f, 0, true));
     f->pending = true;
     f->last_resample_step = f->T + 1;
   }
@@ -987,6 +1008,8 @@ GSMC_API int gsmc_trim(void) {
   int dev = 0; cudaGetDevice(&dev);
   for (auto& kv : g_pool) { cudaSetDevice(kv.first.device); cudaFree(kv.second); }
   g_pool.clear();
+  for (DevScalars* p : g_pinned_pool) cudaFreeHost(p);
+  g_pinned_pool.clear();
   cudaSetDevice(dev);
   return GSMC_OK;
 }
