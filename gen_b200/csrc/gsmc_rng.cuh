@@ -12,7 +12,8 @@
 //   normals  (stream 0): element e -> call e>>1; Box-Muller u1=((a>>11)+.5)2^-53, u2=(b>>11)2^-53,
 //                        r=sqrt(-2 log u1); e even -> r cos(2 pi u2), e odd -> r sin(2 pi u2)
 //   uniforms (stream 1,3): element e -> call e>>1; (e odd ? b : a)>>11 * 2^-53   in [0,1)
-//   spacings (stream 2): element e -> call e>>1; floor(-log(((w>>11)+.5)2^-53) * 2^32)
+//   spacings (stream 2): element e -> call e>>2, 32-bit word e&3 (out0..out3); u = (w+.5)2^-32;
+//                        floor(-gm_log_tab(u) * 2^32)   (fixed-point Exp(1) variate)
 // Particle i's j-th normal at a step that needs nz normals per particle is element i*nz + j.
 #ifndef GSMC_RNG_CUH
 #define GSMC_RNG_CUH
@@ -59,16 +60,27 @@ __host__ __device__ __forceinline__ void uniform_pair(uint64_t seed, uint64_t ca
   *u1 = (double)(o.b >> 11) * 0x1p-53;
 }
 
-__host__ __device__ __forceinline__ uint64_t spacing_from_word(uint64_t w) {
-  const double u = ((double)(w >> 11) + 0.5) * 0x1p-53;
-  return (uint64_t)floor(-gm_log_pos(u) * 4294967296.0);
+__host__ __device__ __forceinline__ uint64_t spacing_from_word(uint32_t w, const double* tab) {
+  const double u = ((double)w + 0.5) * 0x1p-32;
+  return (uint64_t)floor(-gm_log_tab(u, tab) * 4294967296.0);
 }
-__host__ __device__ __forceinline__ void spacing_pair(uint64_t seed, uint64_t call, uint32_t rho, uint64_t* e0, uint64_t* e1) {
+// the four spacings 4c .. 4c+3 of call c
+__host__ __device__ __forceinline__ void spacing_quad(uint64_t seed, uint64_t call, uint32_t rho, const double* tab, uint64_t* e) {
   const PhiloxOut o = philox_call(seed, call, rho, GSMC_STREAM_RESAMPLE);
-  *e0 = spacing_from_word(o.a);
-  *e1 = spacing_from_word(o.b);
+  const uint32_t w[4] = {(uint32_t)o.a, (uint32_t)(o.a >> 32), (uint32_t)o.b, (uint32_t)(o.b >> 32)};
+  double u[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) u[j] = ((double)w[j] + 0.5) * 0x1p-32;
+  gm_log_tab_v<4>(u, tab, l);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e[j] = (uint64_t)floor(-l[j] * 4294967296.0);
 }
-
+// spacing of a single element (uniform across the calling warp / a single thread)
+__host__ __device__ __forceinline__ uint64_t spacing_one(uint64_t seed, uint64_t element, uint32_t rho, const double* tab) {
+  const PhiloxOut o = philox_call(seed, element >> 2, rho, GSMC_STREAM_RESAMPLE);
+  const uint32_t w[4] = {(uint32_t)o.a, (uint32_t)(o.a >> 32), (uint32_t)o.b, (uint32_t)(o.b >> 32)};
+  return spacing_from_word(w[element & 3], tab);
+}
 
 // Batch forms (same bits as the scalar functions, see gsmc_math.h "Batch forms").
 // K Philox calls -> 2K standard normals z[2m] (cos branch), z[2m+1] (sin branch)
@@ -91,19 +103,4 @@ __host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uin
     z[2 * m + 1] = r * sn[m];
   }
 }
-// 2K spacings of the calls c0, c0+1, ...
-template <int K>
-__host__ __device__ __forceinline__ void spacing_pairs_v(uint64_t seed, uint64_t c0, uint32_t rho, uint64_t* e) {
-  double u[2 * K], l[2 * K];
-#pragma unroll
-  for (int m = 0; m < K; ++m) {
-    const PhiloxOut o = philox_call(seed, c0 + m, rho, GSMC_STREAM_RESAMPLE);
-    u[2 * m] = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
-    u[2 * m + 1] = ((double)(o.b >> 11) + 0.5) * 0x1p-53;
-  }
-  gm_log_pos_v<2 * K>(u, l);
-#pragma unroll
-  for (int j = 0; j < 2 * K; ++j) e[j] = (uint64_t)floor(-l[j] * 4294967296.0);
-}
-
 #endif

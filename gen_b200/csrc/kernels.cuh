@@ -588,8 +588,8 @@ __global__ void resid_totals_kernel(DevScalars* ds, const uint64_t* total_c, con
 // sorted uniforms from exponential spacings
 // ------------------------------------------------------------------------------------------------
 // spacings of the thresholds k = k0+4*tid .. +3 of tile b (global threshold index), masked to k < m_draws
-__device__ __forceinline__ void tile_spacings(uint64_t seed, uint32_t rho, uint64_t k, uint64_t m_draws, uint64_t e[4]) {
-  spacing_pairs_v<2>(seed, k >> 1, rho, e);
+__device__ __forceinline__ void tile_spacings(uint64_t seed, uint32_t rho, uint64_t k, uint64_t m_draws, const double* tab, uint64_t e[4]) {
+  spacing_quad(seed, k >> 2, rho, tab, e);
 #pragma unroll
   for (int j = 0; j < 4; ++j) if (k + j >= m_draws) e[j] = 0;
 }
@@ -597,13 +597,16 @@ __device__ __forceinline__ void tile_spacings(uint64_t seed, uint32_t rho, uint6
 __global__ void __launch_bounds__(GSMC_BLOCK) spacing_sum_kernel(uint64_t seed, uint64_t k_first, const DevScalars* ds,
                                                                  uint64_t* tile_sums, int nt, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+  __shared__ double ltab[32];
   if (conditional && !ds->do_resample) return;
+  if (threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_d[threadIdx.x];
+  __syncthreads();
   const uint32_t rho = ds->rho;
   const uint64_t m_draws = ds->n_draws;
   for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
     const uint64_t k = k_first + (uint64_t)tile * GSMC_TILE + 4 * threadIdx.x;
     uint64_t e[4];
-    tile_spacings(seed, rho, k, m_draws, e);
+    tile_spacings(seed, rho, k, m_draws, ltab, e);
     const uint64_t t = block_sum_u64(e[0] + e[1] + e[2] + e[3], sm);
     if (threadIdx.x == 0) tile_sums[tile] = t;
   }
@@ -614,9 +617,7 @@ __global__ void spacing_total_kernel(uint64_t seed, DevScalars* ds, int nranks) 
     uint64_t s = 0;
     for (int r = 0; r < nranks; ++r) s += ds->spacing_rank_total[r];
     const uint64_t m = ds->n_draws;
-    uint64_t e0, e1;
-    spacing_pair(seed, m >> 1, ds->rho, &e0, &e1);
-    const uint64_t stot = s + ((m & 1) ? e1 : e0);
+    const uint64_t stot = s + spacing_one(seed, m, ds->rho, gm_logtab_d);
     ds->spacing_total = stot;
     const MulDiv md = make_muldiv(ds->cdf_total, stot);
     ds->thr_ratio = md.ratio; ds->thr_inv = md.inv_d;
@@ -705,9 +706,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
   uint64_t S = 0;
   for (int r = 0; r < rank; ++r) S += ds->spacing_rank_total[r];
   S += (b == nt) ? ds->spacing_rank_total[rank] : tile_prefix[b];
-  uint64_t e0, e1;
-  spacing_pair(seed, kt >> 1, ds->rho, &e0, &e1);     // kt is a multiple of the tile size: even element
-  S += e0;
+  S += spacing_one(seed, kt, ds->rho, gm_logtab_d);     // warp-uniform: constant-memory table
   const uint32_t w = search_global_warp(v, ds, muldiv_floor(S, threshold_muldiv(ds)));
   if (lane == 0) win[b] = w;
 }
@@ -722,7 +721,10 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
                                                                    int det_offset, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   __shared__ uint64_t cwin[GSMC_WIN_CAP];
+  __shared__ double ltab[32];
   if (conditional && !ds->do_resample) return;
+  if (threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_d[threadIdx.x];
+  __syncthreads();
   const uint64_t m_draws = ds->n_draws;
   const uint32_t rho = ds->rho;
   const MulDiv md = threshold_muldiv(ds);
@@ -733,7 +735,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
     if (kt >= m_draws) break;                            // uniform per block
     const uint64_t k = kt + 4 * threadIdx.x;
     uint64_t e[4];
-    tile_spacings(seed, rho, k, m_draws, e);
+    tile_spacings(seed, rho, k, m_draws, ltab, e);
     uint64_t tot;
     const uint64_t tsum = e[0] + e[1] + e[2] + e[3];
     uint64_t S = base + tile_prefix[tile] + block_scan_u64(tsum, sm, &tot) - tsum;

@@ -48,6 +48,7 @@ void orc_sincospi(double t, double* s, double* c) { gm_sincospi(t, s, c); }
 double orc_div_inv(double x, double c) { return gm_div_inv(x, c, gm_safe_recip(c)); }
 double orc_log_pos(double x) { return gm_log_pos(x); }
 double orc_exp_nonpos(double x) { return gm_exp_nonpos(x); }
+double orc_log_tab(double x) { return gm_log_tab(x, gm_logtab_h); }
 /* muldiv_floor vs unsigned __int128 division */
 int64_t orc_muldiv_mismatches(uint64_t seed, int64_t n) {
   uint64_t s = seed ? seed : 1; int64_t bad = 0;
@@ -145,12 +146,21 @@ void orc_fill_uniforms(uint64_t seed, uint32_t t, uint32_t stream, uint64_t firs
   }
 }
 
+/* Exp(1) spacings in 32.32 fixed point: element e uses 32-bit word e&3 of Philox call e>>2,
+ * u = (w + 1/2) 2^-32, E = floor(-log(u) 2^32) with the table-driven log of gsmc_math.h (the draw
+ * definition only needs a deterministic log; glibc's is used under -DORC_USE_LIBM). */
 void orc_fill_spacings(uint64_t seed, uint32_t rho, uint64_t first, uint64_t count, uint64_t* out) {
   for (uint64_t e = first; e < first + count; ++e) {
-    uint64_t a, b;
-    philox_pair(seed, e >> 1, rho, ORC_STREAM_RESAMPLE, &a, &b);
-    const double u = ((double)(((e & 1) ? b : a) >> 11) + 0.5) * 0x1p-53;
-    out[e - first] = (uint64_t)floor(-orc_log(u) * 4294967296.0);
+    uint32_t ctr[4] = { (uint32_t)(e >> 2), (uint32_t)((e >> 2) >> 32), rho, ORC_STREAM_RESAMPLE };
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t o[4];
+    orc_philox4x32_10(ctr, key, o);
+    const double u = ((double)o[e & 3] + 0.5) * 0x1p-32;
+#ifdef ORC_USE_LIBM
+    out[e - first] = (uint64_t)floor(-log(u) * 4294967296.0);
+#else
+    out[e - first] = (uint64_t)floor(-gm_log_tab(u, gm_logtab_h) * 4294967296.0);
+#endif
   }
 }
 

@@ -54,11 +54,13 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 /* element e of the virtual normal / uniform array of (seed, t, stream) */
 void orc_fill_normals(uint64_t seed, uint32_t t, uint64_t first, uint64_t count, double* out);
 void orc_fill_uniforms(uint64_t seed, uint32_t t, uint32_t stream, uint64_t first, uint64_t count, double* out);
-/* fixed-point Exp(1) spacings E_j = floor(-log(u_j) * 2^32), j in [first, first+count) of resample event rho */
+/* fixed-point Exp(1) spacings E_j = floor(-log(u_j) * 2^32), u_j = (32-bit Philox word + 1/2) 2^-32,
+ * j in [first, first+count) of resample event rho */
 void orc_fill_spacings(uint64_t seed, uint32_t rho, uint64_t first, uint64_t count, uint64_t* out);
 double orc_div_inv(double x, double c);
 double orc_log_pos(double x);
 double orc_exp_nonpos(double x);
+double orc_log_tab(double x);
 int64_t orc_muldiv_mismatches(uint64_t seed, int64_t n);
 int64_t orc_div_inv_mismatches(uint64_t seed, int64_t n);
 double orc_exp(double x);

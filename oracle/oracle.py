@@ -50,8 +50,8 @@ class Oracle:
         L.orc_div_inv.restype = L.orc_log_pos.restype = C.c_double
         L.orc_div_inv.argtypes = [C.c_double, C.c_double]
         L.orc_log_pos.argtypes = [C.c_double]
-        L.orc_exp_nonpos.restype = C.c_double
-        L.orc_exp_nonpos.argtypes = [C.c_double]
+        L.orc_exp_nonpos.restype = L.orc_log_tab.restype = C.c_double
+        L.orc_exp_nonpos.argtypes = L.orc_log_tab.argtypes = [C.c_double]
         L.orc_muldiv_mismatches.restype = C.c_int64
         L.orc_muldiv_mismatches.argtypes = [C.c_uint64, C.c_int64]
         L.orc_div_inv_mismatches.restype = C.c_int64

@@ -75,3 +75,12 @@ def test_muldiv_floor_is_exact(orc):
     """gsmc_fixed.h: T_k = floor(S_k C_N / S_tot) against unsigned __int128 division."""
     assert orc.L.orc_muldiv_mismatches(1, 5_000_000) == 0
     assert orc.L.orc_muldiv_mismatches(2024, 5_000_000) == 0
+
+
+def test_table_log_of_the_spacings(orc):
+    """gm_log_tab on the grid of 32-bit uniforms: absolute error far below the 2^-32 quantum."""
+    rng = np.random.default_rng(5)
+    ws = np.concatenate([rng.integers(0, 2 ** 32, 50000), [0, 1, 2, 2 ** 32 - 1, 2 ** 31, 2 ** 31 - 1]])
+    for w in ws:
+        u = (float(w) + 0.5) * 2.0 ** -32
+        assert abs(orc.L.orc_log_tab(u) - math.log(u)) < 2e-12
