@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
            "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"] + os.environ.get("GSMC_NVCC_EXTRA", "").split()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -495,7 +495,16 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   const Real* lw = (const Real*)f->lw;
   const double scale = gm_pow2([&] { int lg = 0; while (((uint64_t)1 << lg) < (uint64_t)f->N) ++lg; int k = 62 - lg; return k > 52 ? 52 : k; }());
   const int nt = f->n_tiles;
-  const int pg = nt < f->sm_count * 6 ? nt : f->sm_count * 6;     // persistent grid of the tile kernels
+  // persistent grids of the tile kernels: as many blocks as can be resident at once
+  auto grid_for = [&](const void* fn) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, GSMC_BLOCK, 0) != cudaSuccess || occ < 1) occ = 4;
+    const int g = f->sm_count * occ;
+    return nt < g ? nt : g;
+  };
+  const int pg_q = grid_for((const void*)qsum_kernel<Real>), pg_c = grid_for((const void*)cdf_kernel<Real>);
+  const int pg_s = grid_for((const void*)spacing_sum_kernel), pg_search = grid_for((const void*)search_sorted_kernel);
+  const int pg = pg_q;
   const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
   uint32_t* anc = anc_col(f, f->anc_slab, f->T + 1);
   if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
@@ -513,7 +522,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, (uint64_t)f->N, residual ? 0 : 1, conditional); }
   if (!residual) {
     ProfScope ps(f, KC_SCAN);
-    cdf_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, conditional);
+    cdf_kernel<Real><<<pg_c, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, conditional);
   } else {
     { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
     { ProfScope ps(f, KC_SCAN); resid_sum_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, nt, conditional); }
@@ -534,7 +543,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   } else {
     // 2. sorted uniforms: spacing tile sums -> prefixes -> S_tot
     const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
-    { ProfScope ps(f, KC_SPACINGS); spacing_sum_kernel<<<pg, GSMC_BLOCK, 0, f->stream>>>(f->cfg.seed, k_first, f->ds, f->tile_b, nt, conditional); }
+    { ProfScope ps(f, KC_SPACINGS); spacing_sum_kernel<<<pg_s, GSMC_BLOCK, 0, f->stream>>>(f->cfg.seed, k_first, f->ds, f->tile_b, nt, conditional); }
     if (fused) f->xchg_seq += 1;
     { ProfScope ps(f, KC_SPACINGS); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_b, nullptr, nt, f->ds, &f->ds->spacing_rank_total[f->rank], nullptr, conditional,
                                                                                 peers, f->rank, f->nranks, f->xchg_seq, fused ? 2 : 0); }
@@ -544,9 +553,9 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     { ProfScope ps(f, KC_SPACINGS); spacing_total_kernel<<<1, 32, 0, f->stream>>>(f->cfg.seed, f->ds, f->nranks); }
     // 3. ancestors
     { ProfScope ps(f, KC_SEARCH);
-      partition_kernel<<<(nt + 1 + GSMC_BLOCK / 32 - 1) / (GSMC_BLOCK / 32), GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, nt, f->win, conditional); }
+      partition_kernel<<<(nt + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, nt, f->win, conditional); }
     { ProfScope ps(f, KC_SEARCH);
-      search_sorted_kernel<<<pg, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
+      search_sorted_kernel<<<pg_search, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;

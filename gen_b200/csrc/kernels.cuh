@@ -476,29 +476,39 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t
   }
   if (conditional && !ds->do_resample) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per = (nt + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(lo + per, nt);
+  constexpr int IT = 16;                                   // consecutive elements per thread and pass
   for (int arr = 0; arr < 2; ++arr) {
     uint64_t* a = arr ? a1 : a0;
     if (!a) continue;
-    uint64_t run = 0;
-    for (int i = lo; i < hi; ++i) run += a[i];
-    uint64_t x = run;
+    uint64_t carry = 0;
+    for (int base = 0; base < nt; base += IT * 1024) {     // one pass for up to 16384 tiles (2^24 particles)
+      const int lo = base + threadIdx.x * IT;
+      uint64_t v[IT];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
-    __syncthreads();
-    if (lane == 31) sm[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint64_t w = sm[lane];
+      for (int j = 0; j < IT; ++j) v[j] = (lo + j < nt) ? a[lo + j] : 0;   // 16 independent loads in flight
+      uint64_t run = 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
-      sm[lane] = w;
+      for (int j = 0; j < IT; ++j) run += v[j];
+      uint64_t x = run;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
+      __syncthreads();
+      if (lane == 31) sm[warp] = x;
+      __syncthreads();
+      if (warp == 0) {
+        uint64_t w = sm[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
+        sm[lane] = w;
+      }
+      __syncthreads();
+      uint64_t acc = carry + x - run + (warp ? sm[warp - 1] : 0);     // exclusive prefix of this thread's run
+#pragma unroll
+      for (int j = 0; j < IT; ++j) { if (lo + j < nt) a[lo + j] = acc; acc += v[j]; }
+      carry += sm[31];
+      __syncthreads();
     }
-    __syncthreads();
-    uint64_t acc = x - run + (warp ? sm[warp - 1] : 0);       // exclusive prefix of this thread's run
-    for (int i = lo; i < hi; ++i) { const uint64_t v = a[i]; a[i] = acc; acc += v; }
-    if (threadIdx.x == 0) { if (arr == 0) { *total0 = sm[31]; mine[0] = sm[31]; } else *total1 = sm[31]; }
+    if (threadIdx.x == 0) { if (arr == 0) { *total0 = carry; mine[0] = carry; } else *total1 = carry; }
     __syncthreads();
   }
   if (exchange_what && nranks > 1)
@@ -690,32 +700,44 @@ __device__ __forceinline__ MulDiv threshold_muldiv(const DevScalars* ds) {
 
 // Sorted mode, step 1: ancestor word of the FIRST threshold of every tile (one thread per tile, all
 // binary searches in flight at once), win[b] for b in [0, nt]; win[nt] closes the last tile.
+__device__ __forceinline__ uint64_t boundary_threshold(uint64_t seed, uint64_t k_first, int rank, const DevScalars* ds,
+                                                      const uint64_t* tile_prefix, int nt, int b) {
+  const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
+  uint64_t S = 0;
+  for (int r = 0; r < rank; ++r) S += ds->spacing_rank_total[r];
+  S += (b == nt) ? ds->spacing_rank_total[rank] : tile_prefix[b];
+  S += spacing_one(seed, kt, ds->rho, gm_logtab_d);
+  return muldiv_floor(S, threshold_muldiv(ds));
+}
 __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
                                                                const DevScalars* ds, const uint64_t* tile_prefix, int nt,
                                                                uint32_t* win, int conditional) {
   if (conditional && !ds->do_resample) return;
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (GSMC_BLOCK / 32) + (threadIdx.x >> 5);      // one warp per boundary
-  if (b > nt) return;
   const uint64_t m_draws = ds->n_draws;
-  const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
-  if (kt >= m_draws) {
-    if (lane == 0) win[b] = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
-    return;
+  const uint32_t last = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
+  // boundaries 0..nt-1: one thread each (their ancestors are almost always in the local segment)
+  for (int b = blockIdx.x * GSMC_BLOCK + threadIdx.x; b < nt; b += gridDim.x * GSMC_BLOCK) {
+    const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
+    win[b] = kt >= m_draws ? last : search_global(v, ds, boundary_threshold(seed, k_first, rank, ds, tile_prefix, nt, b));
   }
-  uint64_t S = 0;
-  for (int r = 0; r < rank; ++r) S += ds->spacing_rank_total[r];
-  S += (b == nt) ? ds->spacing_rank_total[rank] : tile_prefix[b];
-  S += spacing_one(seed, kt, ds->rho, gm_logtab_d);     // warp-uniform: constant-memory table
-  const uint32_t w = search_global_warp(v, ds, muldiv_floor(S, threshold_muldiv(ds)));
-  if (lane == 0) win[b] = w;
+  // the closing boundary (first threshold of the next rank) lives in a peer's segment when there is one:
+  // searched by a whole warp, 32 probes per NVLink round trip
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    const uint64_t kt = k_first + (uint64_t)nt * GSMC_TILE;
+    uint32_t w = last;
+    if (kt < m_draws) w = search_global_warp(v, ds, boundary_threshold(seed, k_first, rank, ds, tile_prefix, nt, nt));
+    if (threadIdx.x == 0) win[nt] = w;
+  }
 }
 
 // Sorted mode, step 2. Tile b of this rank handles thresholds k_first + b*TILE + [0, TILE) and writes
 // anc[b*TILE + ...]. T_k = floor(S_k C_N / S_tot);  anc = min{i : C_i > T_k}  <=>  C_i * S_tot > S_k * C_N
 // (128-bit). The CDF window [win[b], win[b+1]] the tile can map to is staged in shared memory.
 #define GSMC_WIN_CAP 3072
-__global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
+#ifndef GSMC_SEARCH_MINBLOCKS
+#define GSMC_SEARCH_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_MINBLOCKS) search_sorted_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
                                                                    const DevScalars* ds, const uint64_t* tile_prefix,
                                                                    const uint32_t* win, uint32_t* anc, int64_t n_out, int nt,
                                                                    int det_offset, int conditional) {
@@ -730,9 +752,34 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
   const MulDiv md = threshold_muldiv(ds);
   uint64_t base = 0;
   for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
+  const uint64_t st = md.d, cn = md.b;
+  constexpr int PF = GSMC_WIN_CAP / GSMC_BLOCK;           // window elements per thread
   for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
     const uint64_t kt = k_first + (uint64_t)tile * GSMC_TILE;
     if (kt >= m_draws) break;                            // uniform per block
+    // window [win[tile], win[tile+1]]: [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the
+    // head [0, hi] of r0+1. Its CDF values are fetched into registers first, so the DRAM / NVLink latency
+    // overlaps the spacing arithmetic below.
+    const uint32_t w0 = win[tile], w1 = win[tile + 1];
+    const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT), r1 = (int)(w1 >> GSMC_ANC_RANK_SHIFT);
+    const int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK), hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
+    const int64_t len_a = (r1 == r0) ? hi - lo + 1 : v.n_per - lo;
+    const int64_t len_b = (r1 == r0) ? 0 : hi + 1;
+    const bool staged = (r1 == r0 || r1 == r0 + 1) && len_a + len_b <= GSMC_WIN_CAP;
+    const int la = (int)len_a, len = (int)(len_a + len_b);
+    uint64_t pre[PF];
+    if (staged) {
+      uint64_t off = 0;
+      for (int q = 0; q < r0; ++q) off += ds->cdf_rank_total[q];
+      const uint64_t off_b = off + ds->cdf_rank_total[r0];
+      const uint64_t* seg_a = v.seg[r0];
+      const uint64_t* seg_b = v.seg[r1];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int j = threadIdx.x + u * GSMC_BLOCK;
+        pre[u] = j < la ? off + __ldg(seg_a + lo + j) : (j < len ? off_b + __ldg(seg_b + (j - la)) : 0);
+      }
+    }
     const uint64_t k = kt + 4 * threadIdx.x;
     uint64_t e[4];
     tile_spacings(seed, rho, k, m_draws, ltab, e);
@@ -741,49 +788,40 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
     uint64_t S = base + tile_prefix[tile] + block_scan_u64(tsum, sm, &tot) - tsum;
     uint32_t a[4];
     bool have[4];
-    uint64_t T[4];
+    uint64_t Sk[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      S += e[j];
-      have[j] = k + j < m_draws;
-      T[j] = have[j] ? muldiv_floor(S, md) : 0;          // T_k = floor(S_k C_N / S_tot), exact
-    }
-    const uint32_t w0 = win[tile], w1 = win[tile + 1];
-    const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT), r1 = (int)(w1 >> GSMC_ANC_RANK_SHIFT);
-    const int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK), hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
-    // window = [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the head [0, hi] of r0+1
-    const int64_t len_a = (r1 == r0) ? hi - lo + 1 : v.n_per - lo;
-    const int64_t len_b = (r1 == r0) ? 0 : hi + 1;
-    if ((r1 == r0 || r1 == r0 + 1) && len_a + len_b <= GSMC_WIN_CAP) {
-      uint64_t off = 0;
-      for (int q = 0; q < r0; ++q) off += ds->cdf_rank_total[q];
-      const uint64_t off_b = off + ds->cdf_rank_total[r0];
-      const uint64_t* seg_a = v.seg[r0];
-      const uint64_t* seg_b = v.seg[r1];
-      const int la = (int)len_a, len = (int)(len_a + len_b);
+    for (int j = 0; j < 4; ++j) { S += e[j]; Sk[j] = S; have[j] = k + j < m_draws; }
+    if (staged) {
       __syncthreads();                                   // previous tile's readers are done with cwin
-      for (int j = threadIdx.x; j < len; j += GSMC_BLOCK)
-        cwin[j] = j < la ? off + __ldg(seg_a + lo + j) : off_b + __ldg(seg_b + (j - la));
+#pragma unroll
+      for (int u = 0; u < PF; ++u) { const int j = threadIdx.x + u * GSMC_BLOCK; if (j < len) cwin[j] = pre[u]; }
       __syncthreads();
+      // anc = min{p : C_p > T_k}, T_k = floor(S_k C_N / S_tot)  <=>  C_p * S_tot > S_k * C_N  (exact, 128 bit).
+      // Search with the double-precision estimate of T_k (cheap 64-bit compares), then settle the answer
+      // with the exact predicate: the estimate is within ~2^12 of T_k, so it can only be off across CDF
+      // steps smaller than that, and the two correction loops below almost never iterate.
       int pos = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (!have[j]) { a[j] = 0; continue; }
+        const uint64_t Ta = (uint64_t)((double)Sk[j] * md.ratio);
         if (j == 0) {
-          int l = 0, h = len;                             // min{p : cwin[p] > T}, else len
-          while (l < h) { const int mid = (l + h) >> 1; if (cwin[mid] > T[0]) h = mid; else l = mid + 1; }
+          int l = 0, h = len;
+          while (l < h) { const int mid = (l + h) >> 1; if (cwin[mid] > Ta) h = mid; else l = mid + 1; }
           pos = l;
         } else {
-          // thresholds are sorted, so ancestors are monotone and on average one slot apart: walk
-          while (pos < len && cwin[pos] <= T[j]) ++pos;
+          while (pos < len && cwin[pos] <= Ta) ++pos;    // thresholds are sorted: ancestors are monotone, ~1 apart
         }
-        if (pos >= len) pos = len - 1;
-        a[j] = pos < la ? (((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pos))
-                        : (((uint32_t)r1 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pos - la));
+        const uint64_t chi = __umul64hi(Sk[j], cn), clo = Sk[j] * cn;
+        while (pos < len && !mul_gt(cwin[pos], st, chi, clo)) ++pos;
+        while (pos > 0 && mul_gt(cwin[pos - 1], st, chi, clo)) --pos;
+        const int pc = pos < len ? pos : len - 1;
+        a[j] = pc < la ? (((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pc))
+                       : (((uint32_t)r1 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pc - la));
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, T[j]) : 0;
+      for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, muldiv_floor(Sk[j], md)) : 0;
     }
     // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
     const int64_t o = (int64_t)(k - k_first) + (det_offset ? (int64_t)ds->n_det : 0);

@@ -1,0 +1,10 @@
+mkdir -p gpurun_out
+for v in variants/*.so; do
+  cp $v gen_b200/libgensmc.so
+  python bench.py --no-cpu-baseline --steps 5 --warmup 3 > gpurun_out/var.json 2>/dev/null
+  python - <<PY
+import json
+d=json.load(open('gpurun_out/var.json')); k=d['kernel_ms_profile_pass']
+print("$v", round(d['ms_per_step'],2), 'search', round(k['search'],2), 'scan', round(k['scan'],2), 'spac', round(k['spacings'],2), 'prop', round(k['propagate']+k['propagate_gather'],2), 'lml', d['log_ml'])
+PY
+done
