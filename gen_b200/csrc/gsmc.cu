@@ -158,11 +158,12 @@ struct gsmc_filter {
   void* state_slab = nullptr; // Real[cap][D][n_pad]
   uint32_t* anc_slab = nullptr;  // uint32[cap][n_pad]
   void* lw = nullptr;         // Real[n_pad]
-  uint64_t* cdf = nullptr;    // u64[n_pad]
-  uint64_t* cc = nullptr;     // residual: inclusive counts of deterministic copies
-  uint64_t* tile_a = nullptr; // per-tile sums / prefixes (weights)
-  uint64_t* tile_b = nullptr; // per-tile sums / prefixes (spacings; residual counts)
-  uint64_t* scratch_tot = nullptr;  // 4 u64 scratch totals
+  uint64_t* cdf = nullptr;    // u64[n_pad] tile-local inclusive CDF of the integer weights, followed by tile_a
+  uint64_t* cc = nullptr;     // residual: tile-local inclusive counts of deterministic copies
+  uint64_t* tile_a = nullptr; // u64[nt+1] tile totals / exclusive prefixes of the weights (inside the cdf allocation: peers read it)
+  uint64_t* tile_b = nullptr; // u64[nt+1] residual scheme: tile prefixes of the residual fractions
+  uint64_t* tile_e = nullptr; // u64[nt+1] tile totals / exclusive prefixes of the spacings
+  uint32_t* esp = nullptr;    // u32[n_pad] exponential spacings of this rank's thresholds
   uint32_t* win = nullptr;          // nt+1 window words of the sorted search
   LseTriple* partials = nullptr;
   DevScalars* ds = nullptr;
@@ -284,15 +285,17 @@ static int alloc_buffers(gsmc_filter* f) {
   if (f->cap < 2) f->cap = 2;
   f->flag_mod = f->cfg.keep_history ? f->cap + 2 : 4;
   f->bytes_state = (size_t)f->cap * f->D * f->n_pad * rs; f->bytes_anc = (size_t)f->cap * f->n_pad * sizeof(uint32_t);
-  f->bytes_lw = f->n_pad * rs; f->bytes_cdf = f->n_pad * sizeof(uint64_t);
+  const size_t tile_words = ((size_t)f->n_tiles + 1 + 15) / 16 * 16;
+  f->bytes_lw = f->n_pad * rs; f->bytes_cdf = (f->n_pad + tile_words) * sizeof(uint64_t);
   CK(pool_alloc(f->device, &f->state_slab, f->bytes_state));
   CK(pool_alloc(f->device, (void**)&f->anc_slab, f->bytes_anc));
   CK(pool_alloc(f->device, &f->lw, f->bytes_lw));
   CK(pool_alloc(f->device, (void**)&f->cdf, f->bytes_cdf));
   if (f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL) CK(pool_alloc(f->device, (void**)&f->cc, f->n_pad * sizeof(uint64_t)));
-  CK(pool_alloc(f->device, (void**)&f->tile_a, (size_t)f->n_tiles * sizeof(uint64_t)));
-  CK(pool_alloc(f->device, (void**)&f->tile_b, (size_t)f->n_tiles * sizeof(uint64_t)));
-  CK(pool_alloc(f->device, (void**)&f->scratch_tot, 4 * sizeof(uint64_t)));
+  f->tile_a = f->cdf + f->n_pad;
+  CK(pool_alloc(f->device, (void**)&f->tile_b, tile_words * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->tile_e, tile_words * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->esp, f->n_pad * sizeof(uint32_t)));
   CK(pool_alloc(f->device, (void**)&f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t)));
   CK(pool_alloc(f->device, (void**)&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
   CK(pool_alloc(f->device, (void**)&f->ds, sizeof(DevScalars)));
@@ -320,13 +323,14 @@ static void free_buffers(gsmc_filter* f) {
   }
   pool_free(f->device, f->state_slab, f->bytes_state); pool_free(f->device, f->anc_slab, f->bytes_anc);
   pool_free(f->device, f->lw, f->bytes_lw); pool_free(f->device, f->cdf, f->bytes_cdf); pool_free(f->device, f->cc, f->n_pad * sizeof(uint64_t));
-  pool_free(f->device, f->tile_a, (size_t)f->n_tiles * sizeof(uint64_t)); pool_free(f->device, f->tile_b, (size_t)f->n_tiles * sizeof(uint64_t));
-  pool_free(f->device, f->scratch_tot, 4 * sizeof(uint64_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
+  const size_t tile_words = ((size_t)f->n_tiles + 1 + 15) / 16 * 16;
+  pool_free(f->device, f->tile_b, tile_words * sizeof(uint64_t)); pool_free(f->device, f->tile_e, tile_words * sizeof(uint64_t));
+  pool_free(f->device, f->esp, f->n_pad * sizeof(uint32_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
   pool_free(f->device, f->partials, (size_t)f->n_tiles * sizeof(LseTriple)); pool_free(f->device, f->ds, sizeof(DevScalars));
   pool_free(f->device, f->resampled, (size_t)f->flag_mod * sizeof(int));
   pinned_free(f->h_ds);
   f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
-  f->tile_a = f->tile_b = f->scratch_tot = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
+  f->tile_a = f->tile_b = f->tile_e = nullptr; f->esp = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
   f->resampled = nullptr;
 }
 static int ensure_f64(gsmc_filter* f, size_t n) {
@@ -472,67 +476,90 @@ static int fetch_scalars(gsmc_filter* f) {
   return GSMC_OK;
 }
 
-__global__ void totals_kernel(DevScalars* ds, int nranks, uint64_t n_global, int set_draws, int conditional) {
-  if (threadIdx.x || blockIdx.x) return;
-  if (conditional && !ds->do_resample) return;
-  uint64_t s = 0;
-  for (int r = 0; r < nranks; ++r) s += ds->cdf_rank_total[r];
-  ds->cdf_total = s;
-  if (set_draws) { ds->n_draws = n_global; ds->n_det = 0; }
-}
-
-static CdfView make_cdf_view(const gsmc_filter* f) {
+static CdfView make_cdf_view(const gsmc_filter* f, bool residual_fractions) {
   CdfView v;
   memset(&v, 0, sizeof v);
-  for (int r = 0; r < f->nranks; ++r) v.seg[r] = f->peer_cdf[r];
+  for (int r = 0; r < f->nranks; ++r) { v.seg[r] = f->peer_cdf[r]; v.tp[r] = f->peer_cdf[r] + f->n_pad; }
+  if (residual_fractions) v.tp[f->rank] = f->tile_b;      // single rank: the CDF of the residual fractions
   v.n_per = f->n;
+  v.nt = f->n_tiles;
   v.nranks = f->nranks;
   return v;
 }
+static double weight_scale(const gsmc_filter* f) {
+  int lg = 0;
+  while (((uint64_t)1 << lg) < (uint64_t)f->N) ++lg;
+  const int k = 62 - lg;
+  return gm_pow2(k > 52 ? 52 : k);
+}
+// persistent grid of a tile kernel: as many blocks as can be resident at once
+static int tile_grid(const gsmc_filter* f, const void* fn) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, GSMC_BLOCK, 0) != cudaSuccess || occ < 1) occ = 4;
+  const int g = f->sm_count * occ;
+  return f->n_tiles < g ? f->n_tiles : g;
+}
 
+// One-block scan of the tile totals + exchange of this rank's totals + the event's totals (see kernels.cuh).
+static int launch_scan(gsmc_filter* f, int cls, uint64_t* a0, uint64_t* a1, int what, int conditional) {
+  PeerScalars peers;
+  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
+  const bool multi = f->nranks > 1;
+  const bool fused = multi && !f->use_nccl_scalars;
+  if (fused) f->xchg_seq += 1;
+  { ProfScope ps(f, cls);
+    scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(a0, a1, f->n_tiles, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
+                                                 peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0); }
+  CK(cudaGetLastError());
+  if (multi && !fused) {
+    if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+    if (what & SCAN_E) NK(g_nccl.AllGather((const char*)(f->ds->spacing_rank_total + f->rank), f->ds->spacing_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+    ProfScope ps(f, KC_OTHER);
+    totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, f->cfg.seed, (uint64_t)f->N, what, conditional);
+    CK(cudaGetLastError());
+  }
+  return GSMC_OK;
+}
+
+// maybe_resample! (particle_filter.jl:199-200) on the device: integer CDF, sorted uniforms, ancestors.
+//   multinomial, Philox draws:  weights+spacings pass -> scan -> partition -> search          (4 launches)
+//   exported uniforms (replay): weights pass -> scan -> iid search
+//   residual: + the copy counts / residual fractions pass and the deterministic copies
 template <typename Real>
 static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   const Real* lw = (const Real*)f->lw;
-  const double scale = gm_pow2([&] { int lg = 0; while (((uint64_t)1 << lg) < (uint64_t)f->N) ++lg; int k = 62 - lg; return k > 52 ? 52 : k; }());
+  const double scale = weight_scale(f);
   const int nt = f->n_tiles;
-  // persistent grids of the tile kernels: as many blocks as can be resident at once
-  auto grid_for = [&](const void* fn) {
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, GSMC_BLOCK, 0) != cudaSuccess || occ < 1) occ = 4;
-    const int g = f->sm_count * occ;
-    return nt < g ? nt : g;
-  };
-  const int pg_q = grid_for((const void*)qsum_kernel<Real>), pg_c = grid_for((const void*)cdf_kernel<Real>);
-  const int pg_s = grid_for((const void*)spacing_sum_kernel), pg_search = grid_for((const void*)search_sorted_kernel);
-  const int pg = pg_q;
   const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
   uint32_t* anc = anc_col(f, f->anc_slab, f->T + 1);
   if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
-  // 1. integer weights -> tile sums -> tile prefixes and this rank's total
-  { ProfScope ps(f, KC_SCAN); qsum_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, nt, conditional); }
-  PeerScalars peers;
-  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
-  const bool fused = f->nranks > 1 && !f->use_nccl_scalars;
-  if (fused) f->xchg_seq += 1;
-  { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[f->rank], nullptr, conditional,
-                                                                          peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0); }
-  CK(cudaGetLastError());
-  if (f->nranks > 1 && !fused)
-    NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
-  { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, (uint64_t)f->N, residual ? 0 : 1, conditional); }
-  if (!residual) {
+  const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
+  const bool fuse_spacings = !residual && !replay_iid;
+  // 1. integer weights -> tile-local CDF + tile totals (and, fused, the spacings of the N draws)
+  if (fuse_spacings) {
     ProfScope ps(f, KC_SCAN);
-    cdf_kernel<Real><<<pg_c, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, conditional);
+    weights_kernel<Real, true, true><<<tile_grid(f, (const void*)weights_kernel<Real, true, true>), GSMC_BLOCK, 0, f->stream>>>(
+        lw, f->n, scale, f->ds, f->cdf, f->tile_a, f->cfg.seed, k_first, (uint64_t)f->N, f->esp, f->tile_e, nt, conditional);
   } else {
-    { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
-    { ProfScope ps(f, KC_SCAN); resid_sum_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, nt, conditional); }
-    { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, f->tile_b, nt, f->ds, f->scratch_tot, f->scratch_tot + 1, conditional, peers, 0, 1, 0, 0); }
-    { ProfScope ps(f, KC_OTHER); resid_totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->scratch_tot, f->scratch_tot + 1, (uint64_t)f->N); }
-    { ProfScope ps(f, KC_SCAN); resid_cdf_kernel<Real><<<pg, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->tile_a, f->tile_b, f->cc, f->cdf, nt, conditional); }
-    { ProfScope ps(f, KC_SEARCH); det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(f->cc, f->n, f->ds, anc, conditional); }
+    ProfScope ps(f, KC_SCAN);
+    weights_kernel<Real, true, false><<<tile_grid(f, (const void*)weights_kernel<Real, true, false>), GSMC_BLOCK, 0, f->stream>>>(
+        lw, f->n, scale, f->ds, f->cdf, f->tile_a, 0, 0, 0, nullptr, nullptr, nt, conditional);
   }
   CK(cudaGetLastError());
-  const CdfView v = make_cdf_view(f);
+  // 2. tile prefixes and the totals of the event
+  if (fuse_spacings) CKRC(launch_scan(f, KC_SCAN, f->tile_a, f->tile_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional));
+  else CKRC(launch_scan(f, KC_SCAN, f->tile_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional));
+  if (residual) {
+    { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
+    { ProfScope ps(f, KC_SCAN);
+      resid_cdf_kernel<Real><<<tile_grid(f, (const void*)resid_cdf_kernel<Real>), GSMC_BLOCK, 0, f->stream>>>(
+          lw, f->n, scale, f->ds, f->cc, f->tile_a, f->cdf, f->tile_b, nt, conditional); }
+    CKRC(launch_scan(f, KC_SCAN, f->tile_a, f->tile_b, SCAN_RESID, conditional));
+    { ProfScope ps(f, KC_SEARCH);
+      det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(f->cc, f->tile_a, nt, f->n, f->ds, anc, conditional); }
+    CK(cudaGetLastError());
+  }
+  const CdfView v = make_cdf_view(f, residual);
   if (replay_iid) {
     // one exported uniform per output slot (per multinomial draw in the residual scheme)
     if (!residual && f->urep_n != (size_t)f->n) return fail(GSMC_E_BADARG, "replay uniforms for maybe_resample: expected %lld values", (long long)f->n);
@@ -541,21 +568,19 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
         v, f->ds, f->d_urep, 0, 0, 0, f->n, residual ? 1 : 0, anc, nullptr, conditional);
     f->urep_n = 0;
   } else {
-    // 2. sorted uniforms: spacing tile sums -> prefixes -> S_tot
-    const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
-    { ProfScope ps(f, KC_SPACINGS); spacing_sum_kernel<<<pg_s, GSMC_BLOCK, 0, f->stream>>>(f->cfg.seed, k_first, f->ds, f->tile_b, nt, conditional); }
-    if (fused) f->xchg_seq += 1;
-    { ProfScope ps(f, KC_SPACINGS); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_b, nullptr, nt, f->ds, &f->ds->spacing_rank_total[f->rank], nullptr, conditional,
-                                                                                peers, f->rank, f->nranks, f->xchg_seq, fused ? 2 : 0); }
-    CK(cudaGetLastError());
-    if (f->nranks > 1 && !fused)
-      NK(g_nccl.AllGather((const char*)(f->ds->spacing_rank_total + f->rank), f->ds->spacing_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
-    { ProfScope ps(f, KC_SPACINGS); spacing_total_kernel<<<1, 32, 0, f->stream>>>(f->cfg.seed, f->ds, f->nranks); }
+    if (residual) {
+      // the number of draws M is only known now: spacings of the M thresholds
+      { ProfScope ps(f, KC_SPACINGS);
+        weights_kernel<Real, false, true><<<tile_grid(f, (const void*)weights_kernel<Real, false, true>), GSMC_BLOCK, 0, f->stream>>>(
+            lw, f->n, scale, f->ds, nullptr, nullptr, f->cfg.seed, k_first, 0, f->esp, f->tile_e, nt, conditional); }
+      CKRC(launch_scan(f, KC_SPACINGS, f->tile_e, nullptr, SCAN_E, conditional));
+    }
     // 3. ancestors
     { ProfScope ps(f, KC_SEARCH);
-      partition_kernel<<<(nt + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, nt, f->win, conditional); }
+      partition_kernel<<<(nt + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_e, f->esp, nt, f->win, conditional); }
     { ProfScope ps(f, KC_SEARCH);
-      search_sorted_kernel<<<pg_search, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_b, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
+      search_sorted_kernel<<<tile_grid(f, (const void*)search_sorted_kernel), GSMC_BLOCK, 0, f->stream>>>(
+          v, k_first, f->rank, f->ds, f->tile_e, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -926,23 +951,15 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
   } else {
     CKRC(launch_finalize(f, -1.0));
   }
-  const bool residual_cfg = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
-  (void)residual_cfg;
   {
-    const double scale = gm_pow2([&] { int lg = 0; while (((uint64_t)1 << lg) < (uint64_t)f->N) ++lg; int k = 62 - lg; return k > 52 ? 52 : k; }());
+    const double scale = weight_scale(f);
     const int nt = f->n_tiles;
-    const int pg = nt < f->sm_count * 6 ? nt : f->sm_count * 6;
-    if (f->f32) {
-      { ProfScope ps(f, KC_SCAN); qsum_kernel<float><<<pg, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, nt, 0); }
-      { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0, PeerScalars(), 0, 1, 0, 0); }
-      { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, 1, (uint64_t)f->N, 0, 0); }
-      { ProfScope ps(f, KC_SCAN); cdf_kernel<float><<<pg, GSMC_BLOCK, 0, f->stream>>>((const float*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, 0); }
-    } else {
-      { ProfScope ps(f, KC_SCAN); qsum_kernel<double><<<pg, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, nt, 0); }
-      { ProfScope ps(f, KC_SCAN); scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(f->tile_a, nullptr, nt, f->ds, &f->ds->cdf_rank_total[0], nullptr, 0, PeerScalars(), 0, 1, 0, 0); }
-      { ProfScope ps(f, KC_OTHER); totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, 1, (uint64_t)f->N, 0, 0); }
-      { ProfScope ps(f, KC_SCAN); cdf_kernel<double><<<pg, GSMC_BLOCK, 0, f->stream>>>((const double*)f->lw, f->n, scale, f->ds, f->tile_a, f->cdf, nt, 0); }
-    }
+    { ProfScope ps(f, KC_SCAN);
+      if (f->f32) weights_kernel<float, true, false><<<tile_grid(f, (const void*)weights_kernel<float, true, false>), GSMC_BLOCK, 0, f->stream>>>(
+          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->tile_a, 0, 0, 0, nullptr, nullptr, nt, 0);
+      else weights_kernel<double, true, false><<<tile_grid(f, (const void*)weights_kernel<double, true, false>), GSMC_BLOCK, 0, f->stream>>>(
+          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->tile_a, 0, 0, 0, nullptr, nullptr, nt, 0); }
+    CKRC(launch_scan(f, KC_SCAN, f->tile_a, nullptr, SCAN_Q, 0));
   }
   CK(cudaGetLastError());
   const double* urep = nullptr;
@@ -951,7 +968,7 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
     urep = f->d_urep;
   }
   { ProfScope ps(f, KC_SEARCH);
-    search_iid_kernel<<<grid, GSMC_BLOCK, 0, f->stream>>>(make_cdf_view(f), f->ds, urep, f->cfg.seed, f->n_sample_calls, GSMC_STREAM_SAMPLE,
+    search_iid_kernel<<<grid, GSMC_BLOCK, 0, f->stream>>>(make_cdf_view(f, false), f->ds, urep, f->cfg.seed, f->n_sample_calls, GSMC_STREAM_SAMPLE,
                                                          (int64_t)num_samples, 0, nullptr, d_idx, 0); }
   CK(cudaGetLastError());
   f->urep_n = 0;

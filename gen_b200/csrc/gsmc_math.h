@@ -261,6 +261,7 @@ GM_HD double gm_atan2(double y, double x) {
 // the spacings are quantised to 2^-32, so this is far more accurate than they need, and it is
 // deterministic (IEEE only), which is all the draw definition requires.
 // ------------------------------------------------------------------------------------------------
+#define GM_SPACING_SCALE 134217728.0    /* 2^27: spacings floor(-log(u) 2^27) fit in 32 bits */
 #define GM_LOGTAB_VALUES { \
   0.9696969696969697, 0.03077165866675366, 0.9142857142857143, 0.08961215868968717, \
   0.8648648648648649, 0.14518200984449783, 0.8205128205128205, 0.19782574332991992, \

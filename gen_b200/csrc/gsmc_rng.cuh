@@ -13,7 +13,8 @@
 //                        r=sqrt(-2 log u1); e even -> r cos(2 pi u2), e odd -> r sin(2 pi u2)
 //   uniforms (stream 1,3): element e -> call e>>1; (e odd ? b : a)>>11 * 2^-53   in [0,1)
 //   spacings (stream 2): element e -> call e>>2, 32-bit word e&3 (out0..out3); u = (w+.5)2^-32;
-//                        floor(-gm_log_tab(u) * 2^32)   (fixed-point Exp(1) variate)
+//                        floor(-gm_log_tab(u) * 2^27)   (fixed-point Exp(1) variate; < 2^32 because
+//                        -log u <= 33 ln 2, so a spacing is stored in 4 bytes)
 // Particle i's j-th normal at a step that needs nz normals per particle is element i*nz + j.
 #ifndef GSMC_RNG_CUH
 #define GSMC_RNG_CUH
@@ -60,12 +61,12 @@ __host__ __device__ __forceinline__ void uniform_pair(uint64_t seed, uint64_t ca
   *u1 = (double)(o.b >> 11) * 0x1p-53;
 }
 
-__host__ __device__ __forceinline__ uint64_t spacing_from_word(uint32_t w, const double* tab) {
+__host__ __device__ __forceinline__ uint32_t spacing_from_word(uint32_t w, const double* tab) {
   const double u = ((double)w + 0.5) * 0x1p-32;
-  return (uint64_t)floor(-gm_log_tab(u, tab) * 4294967296.0);
+  return (uint32_t)(int64_t)floor(-gm_log_tab(u, tab) * GM_SPACING_SCALE);
 }
 // the four spacings 4c .. 4c+3 of call c
-__host__ __device__ __forceinline__ void spacing_quad(uint64_t seed, uint64_t call, uint32_t rho, const double* tab, uint64_t* e) {
+__host__ __device__ __forceinline__ void spacing_quad(uint64_t seed, uint64_t call, uint32_t rho, const double* tab, uint32_t* e) {
   const PhiloxOut o = philox_call(seed, call, rho, GSMC_STREAM_RESAMPLE);
   const uint32_t w[4] = {(uint32_t)o.a, (uint32_t)(o.a >> 32), (uint32_t)o.b, (uint32_t)(o.b >> 32)};
   double u[4], l[4];
@@ -73,7 +74,7 @@ __host__ __device__ __forceinline__ void spacing_quad(uint64_t seed, uint64_t ca
   for (int j = 0; j < 4; ++j) u[j] = ((double)w[j] + 0.5) * 0x1p-32;
   gm_log_tab_v<4>(u, tab, l);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) e[j] = (uint64_t)floor(-l[j] * 4294967296.0);
+  for (int j = 0; j < 4; ++j) e[j] = (uint32_t)(int64_t)floor(-l[j] * GM_SPACING_SCALE);
 }
 // spacing of a single element (uniform across the calling warp / a single thread)
 __host__ __device__ __forceinline__ uint64_t spacing_one(uint64_t seed, uint64_t element, uint32_t rho, const double* tab) {

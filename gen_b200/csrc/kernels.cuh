@@ -26,6 +26,7 @@
 
 #define GSMC_BLOCK 256
 #define GSMC_TILE 1024            // particles (or thresholds) per block of the scan / search kernels
+#define GSMC_TILE_SHIFT 10
 #define GSMC_PAD 2048             // local columns are padded to this many particles
 #define GSMC_MAX_RANKS 8
 #define GSMC_ANC_RANK_SHIFT 28    // ancestor word = (owner rank << 28) | local index
@@ -430,7 +431,13 @@ __global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// integer weights: q_i = floor(exp(lw_i - max) * 2^k)
+// integer weights q_i = floor(exp(lw_i - max) * 2^k) and their CDF, stored in TWO LEVELS:
+//   cl[i]  = sum of q over the particles of i's 1024-tile up to and including i   (tile-local inclusive CDF)
+//   tp[b]  = sum of q over the tiles before b (exclusive tile prefix), tp[nt] = this rank's total
+// so that C_i = (rank offset) + tp[i / 1024] + cl[i]. One streaming pass writes cl and the tile totals, a
+// one-block scan turns the totals into prefixes; the global CDF is never materialised (no second read of
+// lw, no second exp). The exponential spacings of the sorted uniforms are generated by the same pass
+// and kept as 4-byte values, so the search pass neither re-runs Philox nor the log.
 // ------------------------------------------------------------------------------------------------
 template <typename Real>
 __device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, double mx, double scale, uint64_t q[4]) {
@@ -445,95 +452,188 @@ __device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, do
   for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(e[j] * scale) : 0;
 }
 
-// phase 1: per-tile sums of q
-template <typename Real>
-__global__ void __launch_bounds__(GSMC_BLOCK) qsum_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                          uint64_t* tile_sums, int nt, int conditional) {
-  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
-  if (conditional && !ds->do_resample) return;
-  const double mx = ds->max_lw;
-  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {        // persistent: an early exit costs ~1k blocks, not n/1024
-    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
-    uint64_t q[4];
-    load_q4(lw, i, n, mx, scale, q);
-    const uint64_t t = block_sum_u64(q[0] + q[1] + q[2] + q[3], sm);
-    if (threadIdx.x == 0) tile_sums[tile] = t;
-  }
+// spacings of the thresholds k .. k+3 (global threshold index, k a multiple of 4), masked to k < m_draws
+__device__ __forceinline__ void tile_spacings(uint64_t seed, uint32_t rho, uint64_t k, uint64_t m_draws, const double* tab, uint32_t e[4]) {
+  spacing_quad(seed, k >> 2, rho, tab, e);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) if (k + j >= m_draws) e[j] = 0;
 }
 
-// phase 2: exclusive scan of up to 2 arrays of tile sums (one block); totals go to total0/total1.
-// Each thread owns a run of consecutive elements (local serial scan), one block-wide scan of the run sums.
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t* a1, int nt, DevScalars* ds,
-                                                          uint64_t* total0, uint64_t* total1, int conditional,
-                                                          PeerScalars peers, int rank, int nranks, uint32_t seq, int exchange_what) {
-  __shared__ uint64_t sm[33];
-  __shared__ uint64_t mine[1];
-  // the exchange runs on every rank even when no resample was decided: peers are waiting for it
-  if (exchange_what && nranks > 1 && conditional && !ds->do_resample) {
-    mine[0] = 0;
-    ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 1, exchange_what == 1 ? ds->cdf_rank_total : ds->spacing_rank_total);
-    return;
-  }
-  if (conditional && !ds->do_resample) return;
+// Block-wide inclusive scan of v together with a block-wide sum of w, one barrier per call.
+// sm: [2 buffers][2][GSMC_BLOCK/32] u64, `buf` alternates between consecutive calls.
+__device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, uint64_t* sm, int buf, uint64_t* v_total, uint64_t* w_total) {
+  constexpr int NW = GSMC_BLOCK / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int IT = 16;                                   // consecutive elements per thread and pass
-  for (int arr = 0; arr < 2; ++arr) {
-    uint64_t* a = arr ? a1 : a0;
-    if (!a) continue;
-    uint64_t carry = 0;
-    for (int base = 0; base < nt; base += IT * 1024) {     // one pass for up to 16384 tiles (2^24 particles)
-      const int lo = base + threadIdx.x * IT;
-      uint64_t v[IT];
+  uint64_t x = v;
 #pragma unroll
-      for (int j = 0; j < IT; ++j) v[j] = (lo + j < nt) ? a[lo + j] : 0;   // 16 independent loads in flight
-      uint64_t run = 0;
+  for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
 #pragma unroll
-      for (int j = 0; j < IT; ++j) run += v[j];
-      uint64_t x = run;
+  for (int o = 16; o > 0; o >>= 1) w += (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)w, o);
+  uint64_t* sv = sm + buf * 2 * NW;
+  uint64_t* sw = sv + NW;
+  if (lane == 31) { sv[warp] = x; sw[warp] = w; }
+  __syncthreads();
+  uint64_t off = 0, vt = 0, wt = 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
-      __syncthreads();
-      if (lane == 31) sm[warp] = x;
-      __syncthreads();
-      if (warp == 0) {
-        uint64_t w = sm[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
-        sm[lane] = w;
-      }
-      __syncthreads();
-      uint64_t acc = carry + x - run + (warp ? sm[warp - 1] : 0);     // exclusive prefix of this thread's run
-#pragma unroll
-      for (int j = 0; j < IT; ++j) { if (lo + j < nt) a[lo + j] = acc; acc += v[j]; }
-      carry += sm[31];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) { if (arr == 0) { *total0 = carry; mine[0] = carry; } else *total1 = carry; }
+  for (int k = 0; k < NW; ++k) { const uint64_t a = sv[k]; if (k < warp) off += a; vt += a; wt += sw[k]; }
+  *v_total = vt; *w_total = wt;
+  return x + off;
+}
+
+// The streaming pass of a resampling event. WEIGHTS: lw -> q -> tile-local inclusive CDF + tile totals.
+// SPACINGS: Philox -> Exp(1) spacings of this rank's thresholds [k_first, k_first + nt*TILE) + tile totals.
+// m_draws_arg: number of draws M when the host knows it (multinomial: N), 0 = read ds->n_draws.
+template <typename Real, bool WEIGHTS, bool SPACINGS>
+__global__ void __launch_bounds__(GSMC_BLOCK) weights_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
+                                                             uint64_t* cl, uint64_t* tile_q, uint64_t seed, uint64_t k_first,
+                                                             uint64_t m_draws_arg, uint32_t* esp, uint64_t* tile_e, int nt, int conditional) {
+  __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
+  __shared__ double ltab[32];
+  if (conditional && !ds->do_resample) return;
+  if (SPACINGS) {
+    if (threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_d[threadIdx.x];
     __syncthreads();
   }
-  if (exchange_what && nranks > 1)
-    ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 1, exchange_what == 1 ? ds->cdf_rank_total : ds->spacing_rank_total);
+  const double mx = ds->max_lw;
+  const uint32_t rho = ds->rho;
+  const uint64_t m_draws = m_draws_arg ? m_draws_arg : ds->n_draws;
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, buf ^= 1) {   // persistent: an early exit costs a few hundred blocks
+    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+    uint64_t q[4] = {0, 0, 0, 0};
+    uint32_t e[4] = {0, 0, 0, 0};
+    if (WEIGHTS) load_q4(lw, i, n, mx, scale, q);
+    if (SPACINGS) tile_spacings(seed, rho, k_first + (uint64_t)i, m_draws, ltab, e);
+    const uint64_t qs = q[0] + q[1] + q[2] + q[3];
+    const uint64_t es = (uint64_t)e[0] + e[1] + e[2] + e[3];
+    uint64_t qt, et;
+    const uint64_t incl = block_scan_and_sum(qs, es, sm, buf, &qt, &et);
+    if (WEIGHTS) {
+      uint64_t c = incl - qs;
+      ulonglong2 o0, o1;
+      c += q[0]; o0.x = c; c += q[1]; o0.y = c; c += q[2]; o1.x = c; c += q[3]; o1.y = c;
+      *reinterpret_cast<ulonglong2*>(cl + i) = o0;
+      *reinterpret_cast<ulonglong2*>(cl + i + 2) = o1;
+      if (threadIdx.x == 0) tile_q[tile] = qt;
+    }
+    if (SPACINGS) {
+      *reinterpret_cast<uint4*>(esp + i) = make_uint4(e[0], e[1], e[2], e[3]);
+      if (threadIdx.x == 0) tile_e[tile] = et;
+    }
+  }
 }
 
-// phase 3: local inclusive CDF  cdf[i] = tile_prefix[b] + inclusive scan within the tile
-template <typename Real>
-__global__ void __launch_bounds__(GSMC_BLOCK) cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                         const uint64_t* tile_prefix, uint64_t* cdf, int nt, int conditional) {
-  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
-  if (conditional && !ds->do_resample) return;
-  const double mx = ds->max_lw;
-  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
-    uint64_t q[4];
-    load_q4(lw, i, n, mx, scale, q);
-    uint64_t tot;
-    const uint64_t incl = block_scan_u64(q[0] + q[1] + q[2] + q[3], sm, &tot);
-    uint64_t c = tile_prefix[tile] + incl - (q[0] + q[1] + q[2] + q[3]);
-    ulonglong2 o0, o1;
-    c += q[0]; o0.x = c; c += q[1]; o0.y = c; c += q[2]; o1.x = c; c += q[3]; o1.y = c;
-    *reinterpret_cast<ulonglong2*>(cdf + i) = o0;
-    *reinterpret_cast<ulonglong2*>(cdf + i + 2) = o1;
+// What a scan_tiles launch completes after the scans (bit set).
+enum { SCAN_Q = 1, SCAN_SET_DRAWS = 2, SCAN_E = 4, SCAN_RESID = 8 };
+
+// Totals of a resampling event once every rank's tile totals are known (thread 0 of one block):
+//   SCAN_Q      cdf_total = sum of the ranks' integer weight totals  [SCAN_SET_DRAWS: M = N draws, no copies]
+//   SCAN_E      S_tot = all ranks' spacing totals + the (M+1)-th spacing, and the constants of muldiv_floor
+//   SCAN_RESID  (single rank) n_det = sum c, M = N - n_det, cdf_total = sum of the residual fractions
+__device__ __forceinline__ void finish_totals(DevScalars* ds, int nranks, uint64_t seed, uint64_t n_global, int what,
+                                              uint64_t total0, uint64_t total1) {
+  if (what & SCAN_RESID) {
+    ds->n_det = total0;
+    ds->n_draws = n_global - total0;
+    ds->cdf_total = total1;
+    ds->cdf_rank_total[0] = total1;
   }
+  if (what & SCAN_Q) {
+    uint64_t s = 0;
+    for (int r = 0; r < nranks; ++r) s += ds->cdf_rank_total[r];
+    ds->cdf_total = s;
+    if (what & SCAN_SET_DRAWS) { ds->n_draws = n_global; ds->n_det = 0; }
+  }
+  if (what & SCAN_E) {
+    uint64_t s = 0;
+    for (int r = 0; r < nranks; ++r) s += ds->spacing_rank_total[r];
+    const uint64_t stot = s + spacing_one(seed, ds->n_draws, ds->rho, gm_logtab_d);
+    ds->spacing_total = stot;
+    const MulDiv md = make_muldiv(ds->cdf_total, stot);
+    ds->thr_ratio = md.ratio; ds->thr_inv = md.inv_d;
+  }
+}
+
+// One block: exclusive scans (in place) of up to two arrays of nt tile totals, a[nt] = total; then this
+// rank's totals go to ds, are exchanged with the peers (fused LL exchange over NVLink) and finish_totals
+// runs. With exchange == 0 on a multi-rank run the host performs the allgathers and launches totals_kernel.
+// Each thread owns a run of 16 consecutive elements (16 independent loads in flight), one block-wide scan of
+// the run sums per 16384 elements.
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t* a1, int nt, DevScalars* ds, int what,
+                                                          uint64_t seed, uint64_t n_global, int conditional,
+                                                          PeerScalars peers, int rank, int nranks, uint32_t seq, int exchange) {
+  __shared__ uint64_t sm[33];
+  __shared__ uint64_t mine[2];
+  __shared__ uint64_t got[2 * GSMC_MAX_RANKS];
+  const bool skip = conditional && !ds->do_resample;
+  const int n64 = ((what & SCAN_Q) ? 1 : 0) + ((what & SCAN_E) ? 1 : 0);
+  uint64_t totals[2] = {0, 0};
+  if (!skip) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int IT = 16;
+    for (int arr = 0; arr < 2; ++arr) {
+      uint64_t* a = arr ? a1 : a0;
+      if (!a) continue;
+      uint64_t carry = 0;
+      for (int base = 0; base < nt; base += IT * 1024) {
+        const int lo = base + threadIdx.x * IT;
+        uint64_t v[IT];
+#pragma unroll
+        for (int j = 0; j < IT; ++j) v[j] = (lo + j < nt) ? a[lo + j] : 0;
+        uint64_t run = 0;
+#pragma unroll
+        for (int j = 0; j < IT; ++j) run += v[j];
+        uint64_t x = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
+        __syncthreads();
+        if (lane == 31) sm[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+          uint64_t w = sm[lane];
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
+          sm[lane] = w;
+        }
+        __syncthreads();
+        uint64_t acc = carry + x - run + (warp ? sm[warp - 1] : 0);     // exclusive prefix of this thread's run
+#pragma unroll
+        for (int j = 0; j < IT; ++j) { if (lo + j < nt) a[lo + j] = acc; acc += v[j]; }
+        carry += sm[31];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) a[nt] = carry;
+      totals[arr] = carry;
+    }
+  }
+  // this rank's totals: the weights' first when both are present
+  if (threadIdx.x == 0) {
+    int k = 0;
+    if (what & SCAN_Q) { ds->cdf_rank_total[rank] = totals[0]; mine[k++] = totals[0]; }
+    if (what & SCAN_E) { const uint64_t t = (what & SCAN_Q) ? totals[1] : totals[0]; ds->spacing_rank_total[rank] = t; mine[k++] = t; }
+  }
+  __syncthreads();
+  if (nranks > 1) {
+    if (!exchange || n64 == 0) return;
+    // the exchange runs on every rank even when no resample was decided: the mailbox parity scheme
+    // needs every sequence number to be used by everybody
+    ll_allgather_u64(peers, ds, rank, nranks, seq, mine, n64, got);
+    __syncthreads();
+    if (threadIdx.x == 0 && !skip) {
+      for (int r = 0; r < nranks; ++r) {
+        int k = 0;
+        if (what & SCAN_Q) ds->cdf_rank_total[r] = got[r * n64 + k++];
+        if (what & SCAN_E) ds->spacing_rank_total[r] = got[r * n64 + k++];
+      }
+    }
+  }
+  if (threadIdx.x == 0 && !skip) finish_totals(ds, nranks, seed, n_global, what, totals[0], totals[1]);
+}
+// multi-rank runs that exchange the totals with ncclAllGather (GSMC_NCCL_SCALARS=1) finish here
+__global__ void totals_kernel(DevScalars* ds, int nranks, uint64_t seed, uint64_t n_global, int what, int conditional) {
+  if (threadIdx.x || blockIdx.x) return;
+  if (conditional && !ds->do_resample) return;
+  finish_totals(ds, nranks, seed, n_global, what, 0, 0);
 }
 
 // residual scheme: e_i = floor(q_i * resid_scale); c_i = e_i >> 32 copies; r_i = e_i & (2^32-1)
@@ -545,26 +645,11 @@ __global__ void resid_scale_kernel(DevScalars* ds, double n_global) {
   if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample)
     ds->resid_scale = (n_global * 4294967296.0) / (double)ds->cdf_total;
 }
-template <typename Real>
-__global__ void __launch_bounds__(GSMC_BLOCK) resid_sum_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                               uint64_t* tile_c, uint64_t* tile_r, int nt, int conditional) {
-  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
-  if (conditional && !ds->do_resample) return;
-  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
-    uint64_t q[4], cs = 0, rs = 0;
-    load_q4(lw, i, n, ds->max_lw, scale, q);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { uint64_t c, r; resid_split(q[j], ds->resid_scale, &c, &r); if (i + j < n) { cs += c; rs += r; } }
-    const uint64_t tc = block_sum_u64(cs, sm);
-    const uint64_t tr = block_sum_u64(rs, sm);
-    if (threadIdx.x == 0) { tile_c[tile] = tc; tile_r[tile] = tr; }
-  }
-}
+// tile-local inclusive CDFs of the copy counts (cc) and of the residual fractions (cl) + their tile totals
 template <typename Real>
 __global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                               const uint64_t* prefix_c, const uint64_t* prefix_r,
-                                                               uint64_t* cc, uint64_t* cdf, int nt, int conditional) {
+                                                               uint64_t* cc, uint64_t* tile_c, uint64_t* cl, uint64_t* tile_r,
+                                                               int nt, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   if (conditional && !ds->do_resample) return;
   for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
@@ -577,60 +662,12 @@ __global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, i
       if (i + j >= n) { c[j] = 0; r[j] = 0; }
       cs += c[j]; rs += r[j];
     }
-    uint64_t tot;
-    uint64_t ic = prefix_c[tile] + block_scan_u64(cs, sm, &tot) - cs;
-    uint64_t ir = prefix_r[tile] + block_scan_u64(rs, sm, &tot) - rs;
+    uint64_t ctot, rtot;
+    uint64_t ic = block_scan_u64(cs, sm, &ctot) - cs;
+    uint64_t ir = block_scan_u64(rs, sm, &rtot) - rs;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { ic += c[j]; ir += r[j]; cc[i + j] = ic; cdf[i + j] = ir; }
-  }
-}
-// after the scans: n_det = sum c, n_draws = N - n_det, cdf_total = sum r (single rank)
-__global__ void resid_totals_kernel(DevScalars* ds, const uint64_t* total_c, const uint64_t* total_r, uint64_t n_global) {
-  if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample) {
-    ds->n_det = *total_c;
-    ds->n_draws = n_global - *total_c;
-    ds->cdf_total = *total_r;
-    ds->cdf_rank_total[0] = *total_r;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// sorted uniforms from exponential spacings
-// ------------------------------------------------------------------------------------------------
-// spacings of the thresholds k = k0+4*tid .. +3 of tile b (global threshold index), masked to k < m_draws
-__device__ __forceinline__ void tile_spacings(uint64_t seed, uint32_t rho, uint64_t k, uint64_t m_draws, const double* tab, uint64_t e[4]) {
-  spacing_quad(seed, k >> 2, rho, tab, e);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) if (k + j >= m_draws) e[j] = 0;
-}
-// per-tile sums of the spacings of this rank's thresholds [k_first, k_first + n_tiles*TILE)
-__global__ void __launch_bounds__(GSMC_BLOCK) spacing_sum_kernel(uint64_t seed, uint64_t k_first, const DevScalars* ds,
-                                                                 uint64_t* tile_sums, int nt, int conditional) {
-  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
-  __shared__ double ltab[32];
-  if (conditional && !ds->do_resample) return;
-  if (threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_d[threadIdx.x];
-  __syncthreads();
-  const uint32_t rho = ds->rho;
-  const uint64_t m_draws = ds->n_draws;
-  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-    const uint64_t k = k_first + (uint64_t)tile * GSMC_TILE + 4 * threadIdx.x;
-    uint64_t e[4];
-    tile_spacings(seed, rho, k, m_draws, ltab, e);
-    const uint64_t t = block_sum_u64(e[0] + e[1] + e[2] + e[3], sm);
-    if (threadIdx.x == 0) tile_sums[tile] = t;
-  }
-}
-// S_tot = all ranks' spacing totals + the (M+1)-th spacing; runs on every rank after the allgather
-__global__ void spacing_total_kernel(uint64_t seed, DevScalars* ds, int nranks) {
-  if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample) {
-    uint64_t s = 0;
-    for (int r = 0; r < nranks; ++r) s += ds->spacing_rank_total[r];
-    const uint64_t m = ds->n_draws;
-    const uint64_t stot = s + spacing_one(seed, m, ds->rho, gm_logtab_d);
-    ds->spacing_total = stot;
-    const MulDiv md = make_muldiv(ds->cdf_total, stot);
-    ds->thr_ratio = md.ratio; ds->thr_inv = md.inv_d;
+    for (int j = 0; j < 4; ++j) { ic += c[j]; ir += r[j]; cc[i + j] = ic; cl[i + j] = ir; }
+    if (threadIdx.x == 0) { tile_c[tile] = ctot; tile_r[tile] = rtot; }
   }
 }
 
@@ -638,57 +675,80 @@ __global__ void spacing_total_kernel(uint64_t seed, DevScalars* ds, int nranks) 
 // search: ancestor of every output slot
 // ------------------------------------------------------------------------------------------------
 struct CdfView {
-  const uint64_t* seg[GSMC_MAX_RANKS];   // local inclusive CDF of every rank (peer-mapped)
+  const uint64_t* seg[GSMC_MAX_RANKS];   // tile-local inclusive CDF of every rank (peer-mapped)
+  const uint64_t* tp[GSMC_MAX_RANKS];    // exclusive tile prefixes of every rank, nt+1 entries (peer-mapped)
   int64_t n_per;                         // particles per rank
+  int nt;                                // tiles per rank
   int nranks;
 };
-// smallest j in [lo, hi] of a segment with off + seg[j] > T; returns hi+1 if none
-__device__ __forceinline__ int64_t seg_upper(const uint64_t* seg, uint64_t off, int64_t lo, int64_t hi, uint64_t T) {
-  int64_t l = lo, h = hi + 1;
+// smallest j in [0, len) with arr[j] > T; len if none
+__device__ __forceinline__ int upper_u64(const uint64_t* arr, int len, uint64_t T) {
+  int l = 0, h = len;
   while (l < h) {
-    const int64_t mid = l + ((h - l) >> 1);
-    if (off + __ldg(seg + mid) > T) h = mid; else l = mid + 1;
+    const int mid = (l + h) >> 1;
+    if (__ldg(arr + mid) > T) h = mid; else l = mid + 1;
   }
   return l;
 }
-// ancestor word of threshold T against the global CDF: min{i : C_i > T}
-__device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, uint64_t T) {
+// rank that owns threshold T and the offset of its segment
+__device__ __forceinline__ int owner_rank(const CdfView& v, const DevScalars* ds, uint64_t T, uint64_t* off_out) {
   uint64_t off = 0;
   int r = 0;
   for (; r < v.nranks - 1; ++r) {
     if (off + ds->cdf_rank_total[r] > T) break;
     off += ds->cdf_rank_total[r];
   }
-  int64_t j = seg_upper(v.seg[r], off, 0, v.n_per - 1, T);
-  if (j > v.n_per - 1) j = v.n_per - 1;           // T == C_N can only happen when the last spacing is 0
+  *off_out = off;
+  return r;
+}
+// ancestor word of threshold T against the global CDF: min{i : C_i > T}. Two levels: the tile whose
+// inclusive end exceeds T, then the position inside the tile.
+__device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, uint64_t T) {
+  uint64_t off;
+  const int r = owner_rank(v, ds, T, &off);
+  const uint64_t Tl = T - off;
+  const uint64_t* tp = v.tp[r];
+  const int t = upper_u64(tp + 1, v.nt, Tl);
+  int64_t j = v.n_per - 1;                        // T >= C_N can only happen when the last spacing is 0
+  if (t < v.nt) {
+    const uint64_t Tt = Tl - __ldg(tp + t);
+    j = (int64_t)t * GSMC_TILE + upper_u64(v.seg[r] + (int64_t)t * GSMC_TILE, GSMC_TILE, Tt);
+    if (j > v.n_per - 1) j = v.n_per - 1;
+  }
   return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
 }
-// Same result as search_global, computed by a full warp: 32 probes per round trip (32-ary search), so a
-// search over a peer's segment costs ~5 NVLink round trips instead of ~24.
-__device__ __forceinline__ uint32_t search_global_warp(const CdfView& v, const DevScalars* ds, uint64_t T) {
+// smallest j in [0, len) with arr[j] > T (len if none), by a full warp: 32 probes per round trip
+__device__ __forceinline__ int upper_u64_warp(const uint64_t* arr, int len, uint64_t T) {
   const int lane = threadIdx.x & 31;
-  uint64_t off = 0;
-  int r = 0;
-  for (; r < v.nranks - 1; ++r) {
-    if (off + ds->cdf_rank_total[r] > T) break;
-    off += ds->cdf_rank_total[r];
-  }
-  const uint64_t* seg = v.seg[r];
-  int64_t lo = 0, hi = v.n_per;                 // answer in [lo, hi]; hi = n_per means "none"
+  int lo = 0, hi = len;                           // answer in [lo, hi]; hi = len means "none"
   while (hi > lo) {
-    const int64_t step = (hi - lo + 31) >> 5;
-    const int64_t p = lo + (int64_t)lane * step;
-    const bool pred = (p >= hi) || (off + __ldg(seg + p) > T);
+    const int step = (hi - lo + 31) >> 5;
+    const int p = lo + lane * step;
+    const bool pred = (p >= hi) || (__ldg(arr + p) > T);
     const unsigned mask = __ballot_sync(0xffffffffu, pred);
     const int f = mask ? __ffs((int)mask) - 1 : 32;
-    const int64_t new_hi = (f == 32) ? hi : lo + (int64_t)f * step;
-    const int64_t new_lo = (f == 0) ? lo : lo + (int64_t)(f - 1) * step + 1;
+    const int new_hi = (f == 32) ? hi : lo + f * step;
+    const int new_lo = (f == 0) ? lo : lo + (f - 1) * step + 1;
     hi = new_hi < hi ? new_hi : hi;
     lo = new_lo;
     if (f == 0) hi = lo;
   }
-  int64_t j = lo;
-  if (j > v.n_per - 1) j = v.n_per - 1;
+  return lo;
+}
+// Same result as search_global, computed by a full warp (32-ary search), so that a search over a peer's
+// segment costs ~5 NVLink round trips instead of ~24.
+__device__ __forceinline__ uint32_t search_global_warp(const CdfView& v, const DevScalars* ds, uint64_t T) {
+  uint64_t off;
+  const int r = owner_rank(v, ds, T, &off);
+  const uint64_t Tl = T - off;
+  const uint64_t* tp = v.tp[r];
+  const int t = upper_u64_warp(tp + 1, v.nt, Tl);
+  int64_t j = v.n_per - 1;
+  if (t < v.nt) {
+    const uint64_t Tt = Tl - __ldg(tp + t);
+    j = (int64_t)t * GSMC_TILE + upper_u64_warp(v.seg[r] + (int64_t)t * GSMC_TILE, GSMC_TILE, Tt);
+    if (j > v.n_per - 1) j = v.n_per - 1;
+  }
   return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
 }
 
@@ -700,32 +760,35 @@ __device__ __forceinline__ MulDiv threshold_muldiv(const DevScalars* ds) {
 
 // Sorted mode, step 1: ancestor word of the FIRST threshold of every tile (one thread per tile, all
 // binary searches in flight at once), win[b] for b in [0, nt]; win[nt] closes the last tile.
-__device__ __forceinline__ uint64_t boundary_threshold(uint64_t seed, uint64_t k_first, int rank, const DevScalars* ds,
-                                                      const uint64_t* tile_prefix, int nt, int b) {
-  const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
-  uint64_t S = 0;
-  for (int r = 0; r < rank; ++r) S += ds->spacing_rank_total[r];
-  S += (b == nt) ? ds->spacing_rank_total[rank] : tile_prefix[b];
-  S += spacing_one(seed, kt, ds->rho, gm_logtab_d);
-  return muldiv_floor(S, threshold_muldiv(ds));
-}
+// tile_prefix: exclusive tile prefixes of the stored spacings esp.
 __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
-                                                               const DevScalars* ds, const uint64_t* tile_prefix, int nt,
-                                                               uint32_t* win, int conditional) {
+                                                               const DevScalars* ds, const uint64_t* tile_prefix,
+                                                               const uint32_t* esp, int nt, uint32_t* win, int conditional) {
   if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws;
   const uint32_t last = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
+  const MulDiv md = threshold_muldiv(ds);
+  uint64_t base = 0;
+  for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
   // boundaries 0..nt-1: one thread each (their ancestors are almost always in the local segment)
   for (int b = blockIdx.x * GSMC_BLOCK + threadIdx.x; b < nt; b += gridDim.x * GSMC_BLOCK) {
     const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
-    win[b] = kt >= m_draws ? last : search_global(v, ds, boundary_threshold(seed, k_first, rank, ds, tile_prefix, nt, b));
+    uint32_t w = last;
+    if (kt < m_draws) {
+      const uint64_t S = base + tile_prefix[b] + (uint64_t)esp[(int64_t)b * GSMC_TILE];
+      w = search_global(v, ds, muldiv_floor(S, md));
+    }
+    win[b] = w;
   }
   // the closing boundary (first threshold of the next rank) lives in a peer's segment when there is one:
   // searched by a whole warp, 32 probes per NVLink round trip
   if (blockIdx.x == 0 && threadIdx.x < 32) {
     const uint64_t kt = k_first + (uint64_t)nt * GSMC_TILE;
     uint32_t w = last;
-    if (kt < m_draws) w = search_global_warp(v, ds, boundary_threshold(seed, k_first, rank, ds, tile_prefix, nt, nt));
+    if (kt < m_draws) {
+      const uint64_t S = base + ds->spacing_rank_total[rank] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
+      w = search_global_warp(v, ds, muldiv_floor(S, md));
+    }
     if (threadIdx.x == 0) win[nt] = w;
   }
 }
@@ -737,18 +800,14 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
 #ifndef GSMC_SEARCH_MINBLOCKS
 #define GSMC_SEARCH_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_MINBLOCKS) search_sorted_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
-                                                                   const DevScalars* ds, const uint64_t* tile_prefix,
+__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_MINBLOCKS) search_sorted_kernel(CdfView v, uint64_t k_first, int rank,
+                                                                   const DevScalars* ds, const uint64_t* tile_prefix, const uint32_t* esp,
                                                                    const uint32_t* win, uint32_t* anc, int64_t n_out, int nt,
                                                                    int det_offset, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   __shared__ uint64_t cwin[GSMC_WIN_CAP];
-  __shared__ double ltab[32];
   if (conditional && !ds->do_resample) return;
-  if (threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_d[threadIdx.x];
-  __syncthreads();
   const uint64_t m_draws = ds->n_draws;
-  const uint32_t rho = ds->rho;
   const MulDiv md = threshold_muldiv(ds);
   uint64_t base = 0;
   for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
@@ -759,7 +818,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_MINBLOCKS) search_sort
     if (kt >= m_draws) break;                            // uniform per block
     // window [win[tile], win[tile+1]]: [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the
     // head [0, hi] of r0+1. Its CDF values are fetched into registers first, so the DRAM / NVLink latency
-    // overlaps the spacing arithmetic below.
+    // overlaps the spacing scan below.
     const uint32_t w0 = win[tile], w1 = win[tile + 1];
     const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT), r1 = (int)(w1 >> GSMC_ANC_RANK_SHIFT);
     const int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK), hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
@@ -774,17 +833,23 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_MINBLOCKS) search_sort
       const uint64_t off_b = off + ds->cdf_rank_total[r0];
       const uint64_t* seg_a = v.seg[r0];
       const uint64_t* seg_b = v.seg[r1];
+      const uint64_t* tp_a = v.tp[r0];
+      const uint64_t* tp_b = v.tp[r1];
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         const int j = threadIdx.x + u * GSMC_BLOCK;
-        pre[u] = j < la ? off + __ldg(seg_a + lo + j) : (j < len ? off_b + __ldg(seg_b + (j - la)) : 0);
+        uint64_t c = 0;
+        if (j < la) c = off + __ldg(tp_a + ((lo + j) >> GSMC_TILE_SHIFT)) + __ldg(seg_a + lo + j);
+        else if (j < len) c = off_b + __ldg(tp_b + ((j - la) >> GSMC_TILE_SHIFT)) + __ldg(seg_b + (j - la));
+        pre[u] = c;
       }
     }
-    const uint64_t k = kt + 4 * threadIdx.x;
-    uint64_t e[4];
-    tile_spacings(seed, rho, k, m_draws, ltab, e);
+    const int64_t o_local = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+    const uint64_t k = k_first + (uint64_t)o_local;
+    const uint4 ev = *reinterpret_cast<const uint4*>(esp + o_local);     // spacings beyond M were stored as 0
+    const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w};
     uint64_t tot;
-    const uint64_t tsum = e[0] + e[1] + e[2] + e[3];
+    const uint64_t tsum = (uint64_t)e[0] + e[1] + e[2] + e[3];
     uint64_t S = base + tile_prefix[tile] + block_scan_u64(tsum, sm, &tot) - tsum;
     uint32_t a[4];
     bool have[4];
@@ -824,7 +889,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_MINBLOCKS) search_sort
       for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, muldiv_floor(Sk[j], md)) : 0;
     }
     // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
-    const int64_t o = (int64_t)(k - k_first) + (det_offset ? (int64_t)ds->n_det : 0);
+    const int64_t o = o_local + (det_offset ? (int64_t)ds->n_det : 0);
     if (!det_offset && have[3] && o + 3 < n_out) {
       *reinterpret_cast<uint4*>(anc + o) = make_uint4(a[0], a[1], a[2], a[3]);
     } else {
@@ -855,15 +920,19 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_iid_kernel(CdfView v, const
   if (anc64) anc64[o] = (int64_t)(w >> GSMC_ANC_RANK_SHIFT) * v.n_per + (int64_t)(w & GSMC_ANC_INDEX_MASK);
 }
 
-// residual scheme, deterministic part: slot o < n_det belongs to min{i : Cc_i > o}
-__global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* cc, int64_t n, const DevScalars* ds,
-                                                                uint32_t* anc, int conditional) {
+// residual scheme, deterministic part: slot o < n_det belongs to min{i : Cc_i > o}, Cc in two levels
+__global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* cc, const uint64_t* tile_c, int nt, int64_t n,
+                                                                const DevScalars* ds, uint32_t* anc, int conditional) {
   if (conditional && !ds->do_resample) return;
   const int64_t o = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
   if (o >= (int64_t)ds->n_det || o >= n) return;
-  int64_t l = 0, h = n;
-  while (l < h) { const int64_t mid = l + ((h - l) >> 1); if (__ldg(cc + mid) > (uint64_t)o) h = mid; else l = mid + 1; }
-  anc[o] = (uint32_t)(l < n ? l : n - 1);
+  const int t = upper_u64(tile_c + 1, nt, (uint64_t)o);
+  int64_t l = n - 1;
+  if (t < nt) {
+    l = (int64_t)t * GSMC_TILE + upper_u64(cc + (int64_t)t * GSMC_TILE, GSMC_TILE, (uint64_t)o - __ldg(tile_c + t));
+    if (l > n - 1) l = n - 1;
+  }
+  anc[o] = (uint32_t)l;
 }
 
 // ------------------------------------------------------------------------------------------------

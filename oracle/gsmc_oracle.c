@@ -146,8 +146,8 @@ void orc_fill_uniforms(uint64_t seed, uint32_t t, uint32_t stream, uint64_t firs
   }
 }
 
-/* Exp(1) spacings in 32.32 fixed point: element e uses 32-bit word e&3 of Philox call e>>2,
- * u = (w + 1/2) 2^-32, E = floor(-log(u) 2^32) with the table-driven log of gsmc_math.h (the draw
+/* Exp(1) spacings in fixed point with 27 fractional bits (< 2^32): element e uses 32-bit word e&3 of Philox call e>>2,
+ * u = (w + 1/2) 2^-32, E = floor(-log(u) 2^27) with the table-driven log of gsmc_math.h (the draw
  * definition only needs a deterministic log; glibc's is used under -DORC_USE_LIBM). */
 void orc_fill_spacings(uint64_t seed, uint32_t rho, uint64_t first, uint64_t count, uint64_t* out) {
   for (uint64_t e = first; e < first + count; ++e) {
@@ -157,9 +157,9 @@ void orc_fill_spacings(uint64_t seed, uint32_t rho, uint64_t first, uint64_t cou
     orc_philox4x32_10(ctr, key, o);
     const double u = ((double)o[e & 3] + 0.5) * 0x1p-32;
 #ifdef ORC_USE_LIBM
-    out[e - first] = (uint64_t)floor(-log(u) * 4294967296.0);
+    out[e - first] = (uint64_t)floor(-log(u) * GM_SPACING_SCALE);
 #else
-    out[e - first] = (uint64_t)floor(-gm_log_tab(u, gm_logtab_h) * 4294967296.0);
+    out[e - first] = (uint64_t)floor(-gm_log_tab(u, gm_logtab_h) * GM_SPACING_SCALE);
 #endif
   }
 }

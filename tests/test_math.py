@@ -43,7 +43,7 @@ def test_box_muller_normals_are_standard(orc):
     assert np.array_equal(orc.normals(12345, 7, 1000, 10), z[1000:1010])          # counter-based: any slice
     u = orc.uniforms(1, 2, 1, 0, 100000)
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
-    e = orc.spacings(3, 0, 0, 200000).astype(np.float64) / 2 ** 32
+    e = orc.spacings(3, 0, 0, 200000).astype(np.float64) / 2 ** 27
     assert abs(e.mean() - 1) < 0.01 and abs(e.var() - 1) < 0.03
 
 
