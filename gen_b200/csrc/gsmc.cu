@@ -158,12 +158,14 @@ struct gsmc_filter {
   void* state_slab = nullptr; // Real[cap][D][n_pad]
   uint32_t* anc_slab = nullptr;  // uint32[cap][n_pad]
   void* lw = nullptr;         // Real[n_pad]
-  uint64_t* cdf = nullptr;    // u64[n_pad] tile-local inclusive CDF of the integer weights, followed by tile_a
-  uint64_t* cc = nullptr;     // residual: tile-local inclusive counts of deterministic copies
-  uint64_t* tile_a = nullptr; // u64[nt+1] tile totals / exclusive prefixes of the weights (inside the cdf allocation: peers read it)
-  uint64_t* tile_b = nullptr; // u64[nt+1] residual scheme: tile prefixes of the residual fractions
-  uint64_t* tile_e = nullptr; // u64[nt+1] tile totals / exclusive prefixes of the spacings
+  uint64_t* cdf = nullptr;    // u64[n_pad] segment-local inclusive CDF of the integer weights, followed by seg_a
+  uint64_t* cc = nullptr;     // residual: segment-local inclusive counts of deterministic copies
+  uint64_t* seg_a = nullptr;  // u64[n_segs+1] segment totals / exclusive prefixes of the weights (inside the cdf allocation: peers read it)
+  uint64_t* seg_b = nullptr;  // u64[n_segs+1] residual scheme: segment prefixes of the residual fractions
+  uint64_t* seg_e = nullptr;  // u64[n_segs+1] segment totals / exclusive prefixes of the spacings
+  uint64_t* tile_e = nullptr; // u64[nt] segment-local exclusive prefix of the spacings at every tile
   uint32_t* esp = nullptr;    // u32[n_pad] exponential spacings of this rank's thresholds
+  int seg_tiles = 1, n_segs = 0;  // tiles per segment (= per block of the streaming pass), segments per rank
   uint32_t* win = nullptr;          // nt+1 window words of the sorted search
   LseTriple* partials = nullptr;
   DevScalars* ds = nullptr;
@@ -285,16 +287,21 @@ static int alloc_buffers(gsmc_filter* f) {
   if (f->cap < 2) f->cap = 2;
   f->flag_mod = f->cfg.keep_history ? f->cap + 2 : 4;
   f->bytes_state = (size_t)f->cap * f->D * f->n_pad * rs; f->bytes_anc = (size_t)f->cap * f->n_pad * sizeof(uint32_t);
-  const size_t tile_words = ((size_t)f->n_tiles + 1 + 15) / 16 * 16;
-  f->bytes_lw = f->n_pad * rs; f->bytes_cdf = (f->n_pad + tile_words) * sizeof(uint64_t);
+  // segments: one per block of the streaming pass, 4 resident blocks per SM -> one wave
+  const int max_segs = f->sm_count * 4 < GSMC_MAX_SEGS ? f->sm_count * 4 : GSMC_MAX_SEGS;
+  f->seg_tiles = (f->n_tiles + max_segs - 1) / max_segs;
+  f->n_segs = (f->n_tiles + f->seg_tiles - 1) / f->seg_tiles;
+  const size_t seg_words = GSMC_MAX_SEGS + 16;
+  f->bytes_lw = f->n_pad * rs; f->bytes_cdf = (f->n_pad + seg_words) * sizeof(uint64_t);
   CK(pool_alloc(f->device, &f->state_slab, f->bytes_state));
   CK(pool_alloc(f->device, (void**)&f->anc_slab, f->bytes_anc));
   CK(pool_alloc(f->device, &f->lw, f->bytes_lw));
   CK(pool_alloc(f->device, (void**)&f->cdf, f->bytes_cdf));
   if (f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL) CK(pool_alloc(f->device, (void**)&f->cc, f->n_pad * sizeof(uint64_t)));
-  f->tile_a = f->cdf + f->n_pad;
-  CK(pool_alloc(f->device, (void**)&f->tile_b, tile_words * sizeof(uint64_t)));
-  CK(pool_alloc(f->device, (void**)&f->tile_e, tile_words * sizeof(uint64_t)));
+  f->seg_a = f->cdf + f->n_pad;
+  CK(pool_alloc(f->device, (void**)&f->seg_b, seg_words * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->seg_e, seg_words * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->esp, f->n_pad * sizeof(uint32_t)));
   CK(pool_alloc(f->device, (void**)&f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t)));
   CK(pool_alloc(f->device, (void**)&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
@@ -323,14 +330,15 @@ static void free_buffers(gsmc_filter* f) {
   }
   pool_free(f->device, f->state_slab, f->bytes_state); pool_free(f->device, f->anc_slab, f->bytes_anc);
   pool_free(f->device, f->lw, f->bytes_lw); pool_free(f->device, f->cdf, f->bytes_cdf); pool_free(f->device, f->cc, f->n_pad * sizeof(uint64_t));
-  const size_t tile_words = ((size_t)f->n_tiles + 1 + 15) / 16 * 16;
-  pool_free(f->device, f->tile_b, tile_words * sizeof(uint64_t)); pool_free(f->device, f->tile_e, tile_words * sizeof(uint64_t));
+  const size_t seg_words = GSMC_MAX_SEGS + 16;
+  pool_free(f->device, f->seg_b, seg_words * sizeof(uint64_t)); pool_free(f->device, f->seg_e, seg_words * sizeof(uint64_t));
+  pool_free(f->device, f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t));
   pool_free(f->device, f->esp, f->n_pad * sizeof(uint32_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
   pool_free(f->device, f->partials, (size_t)f->n_tiles * sizeof(LseTriple)); pool_free(f->device, f->ds, sizeof(DevScalars));
   pool_free(f->device, f->resampled, (size_t)f->flag_mod * sizeof(int));
   pinned_free(f->h_ds);
   f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
-  f->tile_a = f->tile_b = f->tile_e = nullptr; f->esp = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
+  f->seg_a = f->seg_b = f->seg_e = f->tile_e = nullptr; f->esp = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
   f->resampled = nullptr;
 }
 static int ensure_f64(gsmc_filter* f, size_t n) {
@@ -479,10 +487,12 @@ static int fetch_scalars(gsmc_filter* f) {
 static CdfView make_cdf_view(const gsmc_filter* f, bool residual_fractions) {
   CdfView v;
   memset(&v, 0, sizeof v);
-  for (int r = 0; r < f->nranks; ++r) { v.seg[r] = f->peer_cdf[r]; v.tp[r] = f->peer_cdf[r] + f->n_pad; }
-  if (residual_fractions) v.tp[f->rank] = f->tile_b;      // single rank: the CDF of the residual fractions
+  for (int r = 0; r < f->nranks; ++r) { v.seg[r] = f->peer_cdf[r]; v.sp[r] = f->peer_cdf[r] + f->n_pad; }
+  if (residual_fractions) v.sp[f->rank] = f->seg_b;      // single rank: the CDF of the residual fractions
   v.n_per = f->n;
-  v.nt = f->n_tiles;
+  v.n_pad = (int)f->n_pad;
+  v.seg_len = f->seg_tiles * GSMC_TILE;
+  v.n_segs = f->n_segs;
   v.nranks = f->nranks;
   return v;
 }
@@ -500,7 +510,7 @@ static int tile_grid(const gsmc_filter* f, const void* fn) {
   return f->n_tiles < g ? f->n_tiles : g;
 }
 
-// One-block scan of the tile totals + exchange of this rank's totals + the event's totals (see kernels.cuh).
+// One-block scan of the segment totals + exchange of this rank's totals + the event's totals (see kernels.cuh).
 static int launch_scan(gsmc_filter* f, int cls, uint64_t* a0, uint64_t* a1, int what, int conditional) {
   PeerScalars peers;
   for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
@@ -508,8 +518,8 @@ static int launch_scan(gsmc_filter* f, int cls, uint64_t* a0, uint64_t* a1, int 
   const bool fused = multi && !f->use_nccl_scalars;
   if (fused) f->xchg_seq += 1;
   { ProfScope ps(f, cls);
-    scan_tiles_kernel<<<1, 1024, 0, f->stream>>>(a0, a1, f->n_tiles, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
-                                                 peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0); }
+    scan_segments_kernel<<<1, 1024, 0, f->stream>>>(a0, a1, f->n_segs, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
+                                                    peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0); }
   CK(cudaGetLastError());
   if (multi && !fused) {
     if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
@@ -529,34 +539,34 @@ template <typename Real>
 static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   const Real* lw = (const Real*)f->lw;
   const double scale = weight_scale(f);
-  const int nt = f->n_tiles;
+  const int nt = f->n_tiles, ns = f->n_segs, st = f->seg_tiles;
   const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
   uint32_t* anc = anc_col(f, f->anc_slab, f->T + 1);
   if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
   const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
   const bool fuse_spacings = !residual && !replay_iid;
-  // 1. integer weights -> tile-local CDF + tile totals (and, fused, the spacings of the N draws)
+  // 1. integer weights -> segment-local CDF + segment totals (and, fused, the spacings of the N draws)
   if (fuse_spacings) {
     ProfScope ps(f, KC_SCAN);
-    weights_kernel<Real, true, true><<<tile_grid(f, (const void*)weights_kernel<Real, true, true>), GSMC_BLOCK, 0, f->stream>>>(
-        lw, f->n, scale, f->ds, f->cdf, f->tile_a, f->cfg.seed, k_first, (uint64_t)f->N, f->esp, f->tile_e, nt, conditional);
+    weights_kernel<Real, true, true><<<ns, GSMC_BLOCK, 0, f->stream>>>(
+        lw, f->n, scale, f->ds, f->cdf, f->seg_a, f->cfg.seed, k_first, (uint64_t)f->N, f->esp, f->tile_e, f->seg_e, nt, st, conditional);
   } else {
     ProfScope ps(f, KC_SCAN);
-    weights_kernel<Real, true, false><<<tile_grid(f, (const void*)weights_kernel<Real, true, false>), GSMC_BLOCK, 0, f->stream>>>(
-        lw, f->n, scale, f->ds, f->cdf, f->tile_a, 0, 0, 0, nullptr, nullptr, nt, conditional);
+    weights_kernel<Real, true, false><<<ns, GSMC_BLOCK, 0, f->stream>>>(
+        lw, f->n, scale, f->ds, f->cdf, f->seg_a, 0, 0, 0, nullptr, nullptr, nullptr, nt, st, conditional);
   }
   CK(cudaGetLastError());
-  // 2. tile prefixes and the totals of the event
-  if (fuse_spacings) CKRC(launch_scan(f, KC_SCAN, f->tile_a, f->tile_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional));
-  else CKRC(launch_scan(f, KC_SCAN, f->tile_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional));
+  // 2. segment prefixes and the totals of the event
+  if (fuse_spacings) CKRC(launch_scan(f, KC_SCAN, f->seg_a, f->seg_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional));
+  else CKRC(launch_scan(f, KC_SCAN, f->seg_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional));
   if (residual) {
     { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
     { ProfScope ps(f, KC_SCAN);
-      resid_cdf_kernel<Real><<<tile_grid(f, (const void*)resid_cdf_kernel<Real>), GSMC_BLOCK, 0, f->stream>>>(
-          lw, f->n, scale, f->ds, f->cc, f->tile_a, f->cdf, f->tile_b, nt, conditional); }
-    CKRC(launch_scan(f, KC_SCAN, f->tile_a, f->tile_b, SCAN_RESID, conditional));
+      resid_cdf_kernel<Real><<<ns, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->cc, f->seg_a, f->cdf, f->seg_b, nt, st, conditional); }
+    CKRC(launch_scan(f, KC_SCAN, f->seg_a, f->seg_b, SCAN_RESID, conditional));
     { ProfScope ps(f, KC_SEARCH);
-      det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(f->cc, f->tile_a, nt, f->n, f->ds, anc, conditional); }
+      det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(
+          f->cc, f->seg_a, ns, st * GSMC_TILE, (int)f->n_pad, f->n, f->ds, anc, conditional); }
     CK(cudaGetLastError());
   }
   const CdfView v = make_cdf_view(f, residual);
@@ -571,16 +581,17 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     if (residual) {
       // the number of draws M is only known now: spacings of the M thresholds
       { ProfScope ps(f, KC_SPACINGS);
-        weights_kernel<Real, false, true><<<tile_grid(f, (const void*)weights_kernel<Real, false, true>), GSMC_BLOCK, 0, f->stream>>>(
-            lw, f->n, scale, f->ds, nullptr, nullptr, f->cfg.seed, k_first, 0, f->esp, f->tile_e, nt, conditional); }
-      CKRC(launch_scan(f, KC_SPACINGS, f->tile_e, nullptr, SCAN_E, conditional));
+        weights_kernel<Real, false, true><<<ns, GSMC_BLOCK, 0, f->stream>>>(
+            lw, f->n, scale, f->ds, nullptr, nullptr, f->cfg.seed, k_first, 0, f->esp, f->tile_e, f->seg_e, nt, st, conditional); }
+      CKRC(launch_scan(f, KC_SPACINGS, f->seg_e, nullptr, SCAN_E, conditional));
     }
     // 3. ancestors
     { ProfScope ps(f, KC_SEARCH);
-      partition_kernel<<<(nt + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->tile_e, f->esp, nt, f->win, conditional); }
+      partition_kernel<<<(nt + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(
+          v, f->cfg.seed, k_first, f->rank, f->ds, f->seg_e, f->tile_e, st, f->esp, nt, f->win, conditional); }
     { ProfScope ps(f, KC_SEARCH);
       search_sorted_kernel<<<tile_grid(f, (const void*)search_sorted_kernel), GSMC_BLOCK, 0, f->stream>>>(
-          v, k_first, f->rank, f->ds, f->tile_e, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
+          v, k_first, f->rank, f->ds, f->seg_e, f->tile_e, st, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -953,13 +964,12 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
   }
   {
     const double scale = weight_scale(f);
-    const int nt = f->n_tiles;
     { ProfScope ps(f, KC_SCAN);
-      if (f->f32) weights_kernel<float, true, false><<<tile_grid(f, (const void*)weights_kernel<float, true, false>), GSMC_BLOCK, 0, f->stream>>>(
-          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->tile_a, 0, 0, 0, nullptr, nullptr, nt, 0);
-      else weights_kernel<double, true, false><<<tile_grid(f, (const void*)weights_kernel<double, true, false>), GSMC_BLOCK, 0, f->stream>>>(
-          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->tile_a, 0, 0, 0, nullptr, nullptr, nt, 0); }
-    CKRC(launch_scan(f, KC_SCAN, f->tile_a, nullptr, SCAN_Q, 0));
+      if (f->f32) weights_kernel<float, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
+          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->seg_a, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0);
+      else weights_kernel<double, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
+          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->seg_a, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
+    CKRC(launch_scan(f, KC_SCAN, f->seg_a, nullptr, SCAN_Q, 0));
   }
   CK(cudaGetLastError());
   const double* urep = nullptr;

@@ -29,6 +29,7 @@
 #define GSMC_TILE_SHIFT 10
 #define GSMC_PAD 2048             // local columns are padded to this many particles
 #define GSMC_MAX_RANKS 8
+#define GSMC_MAX_SEGS 1024          // segments (blocks of the streaming resample pass) per rank
 #define GSMC_ANC_RANK_SHIFT 28    // ancestor word = (owner rank << 28) | local index
 #define GSMC_ANC_INDEX_MASK 0x0fffffffu
 
@@ -47,7 +48,8 @@ struct DevScalars {
   uint64_t n_det;           // residual scheme: number of deterministic copies
   uint64_t n_draws;         // M: number of multinomial draws of this event
   double resid_scale;       // residual scheme: N * 2^32 / C_N
-  double thr_ratio, thr_inv;  // (double)C_N / (double)S_tot and 1 / (double)S_tot for muldiv_floor
+  double thr_ratio, thr_max;  // sorted thresholds: t_k = min((double)S_k * thr_ratio, thr_max); thr_ratio = (double)C_N / (double)S_tot,
+                              // thr_max = the largest double below (double)C_N (so every threshold has an ancestor)
   LseTriple triples[GSMC_MAX_RANKS];
   uint64_t cdf_rank_total[GSMC_MAX_RANKS];      // per-rank integer weight totals (allgathered)
   uint64_t spacing_rank_total[GSMC_MAX_RANKS];  // per-rank spacing totals (allgathered)
@@ -432,24 +434,31 @@ __global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, 
 
 // ------------------------------------------------------------------------------------------------
 // integer weights q_i = floor(exp(lw_i - max) * 2^k) and their CDF, stored in TWO LEVELS:
-//   cl[i]  = sum of q over the particles of i's 1024-tile up to and including i   (tile-local inclusive CDF)
-//   tp[b]  = sum of q over the tiles before b (exclusive tile prefix), tp[nt] = this rank's total
-// so that C_i = (rank offset) + tp[i / 1024] + cl[i]. One streaming pass writes cl and the tile totals, a
-// one-block scan turns the totals into prefixes; the global CDF is never materialised (no second read of
-// lw, no second exp). The exponential spacings of the sorted uniforms are generated by the same pass
-// and kept as 4-byte values, so the search pass neither re-runs Philox nor the log.
+//   cl[i]  = sum of q over the particles of i's SEGMENT up to and including i   (segment-local inclusive CDF)
+//   sp[s]  = sum of q over the segments before s (exclusive segment prefix), sp[n_segs] = this rank's total
+// so that C_i = (rank offset) + sp[segment(i)] + cl[i]. A segment is a run of seg_tiles consecutive
+// 1024-particle tiles owned by ONE block of the streaming pass, which carries the running sum in a
+// register: no inter-block dependency, no look-back, and only n_segs (a few hundred) totals are left to
+// scan. The global CDF is never materialised (lw is read once, exp evaluated once). The exponential
+// spacings of the sorted uniforms are generated by the same pass and kept as 4-byte values (plus their
+// segment-local tile prefixes), so the search pass neither re-runs Philox nor the log.
 // ------------------------------------------------------------------------------------------------
+template <typename Real>
+__device__ __forceinline__ void q_from_lw(typename Vec2T<Real>::type a, typename Vec2T<Real>::type b, int64_t i, int64_t n,
+                                          double mx, double scale, uint64_t q[4]) {
+  const double x[4] = {(double)a.x - mx, (double)a.y - mx, (double)b.x - mx, (double)b.y - mx};
+  double e[4];
+  gm_exp_nonpos_v<4>(x, e);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(e[j] * scale) : 0;
+}
 template <typename Real>
 __device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, double mx, double scale, uint64_t q[4]) {
   // i is a multiple of 4 and the columns are padded to a tile, so the vector loads stay inside the allocation
   typedef typename Vec2T<Real>::type Real2;
   const Real2 a = *reinterpret_cast<const Real2*>(lw + i);
   const Real2 b = *reinterpret_cast<const Real2*>(lw + i + 2);
-  const double x[4] = {(double)a.x - mx, (double)a.y - mx, (double)b.x - mx, (double)b.y - mx};
-  double e[4];
-  gm_exp_nonpos_v<4>(x, e);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(e[j] * scale) : 0;
+  q_from_lw<Real>(a, b, i, n, mx, scale, q);
 }
 
 // spacings of the thresholds k .. k+3 (global threshold index, k a multiple of 4), masked to k < m_draws
@@ -480,13 +489,17 @@ __device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, u
   return x + off;
 }
 
-// The streaming pass of a resampling event. WEIGHTS: lw -> q -> tile-local inclusive CDF + tile totals.
-// SPACINGS: Philox -> Exp(1) spacings of this rank's thresholds [k_first, k_first + nt*TILE) + tile totals.
+// The streaming pass of a resampling event; block s owns segment s = tiles [s*seg_tiles, (s+1)*seg_tiles).
+// WEIGHTS: lw -> q -> segment-local inclusive CDF cl + segment total seg_q[s].
+// SPACINGS: Philox -> Exp(1) spacings esp of this rank's thresholds [k_first, k_first + nt*TILE), the
+// segment-local exclusive prefix tile_e[tile] of every tile and the segment total seg_e[s].
 // m_draws_arg: number of draws M when the host knows it (multinomial: N), 0 = read ds->n_draws.
 template <typename Real, bool WEIGHTS, bool SPACINGS>
-__global__ void __launch_bounds__(GSMC_BLOCK) weights_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                             uint64_t* cl, uint64_t* tile_q, uint64_t seed, uint64_t k_first,
-                                                             uint64_t m_draws_arg, uint32_t* esp, uint64_t* tile_e, int nt, int conditional) {
+__global__ void __launch_bounds__(GSMC_BLOCK, 4) weights_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
+                                                             uint64_t* cl, uint64_t* seg_q, uint64_t seed, uint64_t k_first,
+                                                             uint64_t m_draws_arg, uint32_t* esp, uint64_t* tile_e, uint64_t* seg_e,
+                                                             int nt, int seg_tiles, int conditional) {
+  typedef typename Vec2T<Real>::type Real2;
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
   __shared__ double ltab[32];
   if (conditional && !ds->do_resample) return;
@@ -497,38 +510,57 @@ __global__ void __launch_bounds__(GSMC_BLOCK) weights_kernel(const Real* lw, int
   const double mx = ds->max_lw;
   const uint32_t rho = ds->rho;
   const uint64_t m_draws = m_draws_arg ? m_draws_arg : ds->n_draws;
+  const int t0 = blockIdx.x * seg_tiles, t1 = min(t0 + seg_tiles, nt);
+  uint64_t run_q = 0, run_e = 0;                          // sums over the tiles of this segment done so far
+  Real2 la, lb;
+  if (WEIGHTS) {
+    const int64_t i0 = (int64_t)t0 * GSMC_TILE + 4 * threadIdx.x;
+    la = *reinterpret_cast<const Real2*>(lw + i0);
+    lb = *reinterpret_cast<const Real2*>(lw + i0 + 2);
+  }
   int buf = 0;
-  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, buf ^= 1) {   // persistent: an early exit costs a few hundred blocks
+  for (int tile = t0; tile < t1; ++tile, buf ^= 1) {
     const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
     uint64_t q[4] = {0, 0, 0, 0};
     uint32_t e[4] = {0, 0, 0, 0};
-    if (WEIGHTS) load_q4(lw, i, n, mx, scale, q);
+    if (WEIGHTS) {
+      const Real2 ca = la, cb = lb;
+      if (tile + 1 < t1) {                                // next tile's log weights are in flight during the arithmetic
+        la = *reinterpret_cast<const Real2*>(lw + i + GSMC_TILE);
+        lb = *reinterpret_cast<const Real2*>(lw + i + GSMC_TILE + 2);
+      }
+      q_from_lw<Real>(ca, cb, i, n, mx, scale, q);
+    }
     if (SPACINGS) tile_spacings(seed, rho, k_first + (uint64_t)i, m_draws, ltab, e);
     const uint64_t qs = q[0] + q[1] + q[2] + q[3];
     const uint64_t es = (uint64_t)e[0] + e[1] + e[2] + e[3];
     uint64_t qt, et;
     const uint64_t incl = block_scan_and_sum(qs, es, sm, buf, &qt, &et);
     if (WEIGHTS) {
-      uint64_t c = incl - qs;
+      uint64_t c = run_q + incl - qs;
       ulonglong2 o0, o1;
       c += q[0]; o0.x = c; c += q[1]; o0.y = c; c += q[2]; o1.x = c; c += q[3]; o1.y = c;
       *reinterpret_cast<ulonglong2*>(cl + i) = o0;
       *reinterpret_cast<ulonglong2*>(cl + i + 2) = o1;
-      if (threadIdx.x == 0) tile_q[tile] = qt;
     }
     if (SPACINGS) {
       *reinterpret_cast<uint4*>(esp + i) = make_uint4(e[0], e[1], e[2], e[3]);
-      if (threadIdx.x == 0) tile_e[tile] = et;
+      if (threadIdx.x == 0) tile_e[tile] = run_e;
     }
+    run_q += qt; run_e += et;
+  }
+  if (threadIdx.x == 0) {
+    if (WEIGHTS) seg_q[blockIdx.x] = run_q;
+    if (SPACINGS) seg_e[blockIdx.x] = run_e;
   }
 }
 
-// What a scan_tiles launch completes after the scans (bit set).
+// What a scan_segments launch completes after the scans (bit set).
 enum { SCAN_Q = 1, SCAN_SET_DRAWS = 2, SCAN_E = 4, SCAN_RESID = 8 };
 
-// Totals of a resampling event once every rank's tile totals are known (thread 0 of one block):
+// Totals of a resampling event once every rank's totals are known (thread 0 of one block):
 //   SCAN_Q      cdf_total = sum of the ranks' integer weight totals  [SCAN_SET_DRAWS: M = N draws, no copies]
-//   SCAN_E      S_tot = all ranks' spacing totals + the (M+1)-th spacing, and the constants of muldiv_floor
+//   SCAN_E      S_tot = all ranks' spacing totals + the (M+1)-th spacing, and the threshold constants
 //   SCAN_RESID  (single rank) n_det = sum c, M = N - n_det, cdf_total = sum of the residual fractions
 __device__ __forceinline__ void finish_totals(DevScalars* ds, int nranks, uint64_t seed, uint64_t n_global, int what,
                                               uint64_t total0, uint64_t total1) {
@@ -549,20 +581,20 @@ __device__ __forceinline__ void finish_totals(DevScalars* ds, int nranks, uint64
     for (int r = 0; r < nranks; ++r) s += ds->spacing_rank_total[r];
     const uint64_t stot = s + spacing_one(seed, ds->n_draws, ds->rho, gm_logtab_d);
     ds->spacing_total = stot;
-    const MulDiv md = make_muldiv(ds->cdf_total, stot);
-    ds->thr_ratio = md.ratio; ds->thr_inv = md.inv_d;
+    const double cn = (double)ds->cdf_total;
+    ds->thr_ratio = cn / (double)stot;
+    ds->thr_max = cn > 0.0 ? gm_from_bits(gm_to_bits(cn) - 1) : 0.0;
   }
 }
 
-// One block: exclusive scans (in place) of up to two arrays of nt tile totals, a[nt] = total; then this
-// rank's totals go to ds, are exchanged with the peers (fused LL exchange over NVLink) and finish_totals
-// runs. With exchange == 0 on a multi-rank run the host performs the allgathers and launches totals_kernel.
-// Each thread owns a run of 16 consecutive elements (16 independent loads in flight), one block-wide scan of
-// the run sums per 16384 elements.
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t* a1, int nt, DevScalars* ds, int what,
-                                                          uint64_t seed, uint64_t n_global, int conditional,
-                                                          PeerScalars peers, int rank, int nranks, uint32_t seq, int exchange) {
-  __shared__ uint64_t sm[33];
+// One block: exclusive scans (in place) of up to two arrays of n_segs segment totals (n_segs <= 1024),
+// a[n_segs] = total; then this rank's totals go to ds, are exchanged with the peers (fused LL exchange over
+// NVLink) and finish_totals runs. With exchange == 0 on a multi-rank run the host performs the
+// allgathers and launches totals_kernel.
+__global__ void __launch_bounds__(1024) scan_segments_kernel(uint64_t* a0, uint64_t* a1, int n_segs, DevScalars* ds, int what,
+                                                             uint64_t seed, uint64_t n_global, int conditional,
+                                                             PeerScalars peers, int rank, int nranks, uint32_t seq, int exchange) {
+  __shared__ uint64_t sm[2][33];
   __shared__ uint64_t mine[2];
   __shared__ uint64_t got[2 * GSMC_MAX_RANKS];
   const bool skip = conditional && !ds->do_resample;
@@ -570,40 +602,33 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* a0, uint64_t
   uint64_t totals[2] = {0, 0};
   if (!skip) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int IT = 16;
+    const int i = threadIdx.x;
+    uint64_t v[2], x[2];
+#pragma unroll
+    for (int arr = 0; arr < 2; ++arr) {
+      const uint64_t* a = arr ? a1 : a0;
+      v[arr] = (a && i < n_segs) ? a[i] : 0;
+      x[arr] = v[arr];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x[arr], d); if (lane >= d) x[arr] += y; }
+      if (lane == 31) sm[arr][warp] = x[arr];
+    }
+    __syncthreads();
+    if (warp < 2) {
+      uint64_t w = sm[warp][lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
+      sm[warp][lane] = w;
+    }
+    __syncthreads();
+#pragma unroll
     for (int arr = 0; arr < 2; ++arr) {
       uint64_t* a = arr ? a1 : a0;
       if (!a) continue;
-      uint64_t carry = 0;
-      for (int base = 0; base < nt; base += IT * 1024) {
-        const int lo = base + threadIdx.x * IT;
-        uint64_t v[IT];
-#pragma unroll
-        for (int j = 0; j < IT; ++j) v[j] = (lo + j < nt) ? a[lo + j] : 0;
-        uint64_t run = 0;
-#pragma unroll
-        for (int j = 0; j < IT; ++j) run += v[j];
-        uint64_t x = run;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
-        __syncthreads();
-        if (lane == 31) sm[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-          uint64_t w = sm[lane];
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
-          sm[lane] = w;
-        }
-        __syncthreads();
-        uint64_t acc = carry + x - run + (warp ? sm[warp - 1] : 0);     // exclusive prefix of this thread's run
-#pragma unroll
-        for (int j = 0; j < IT; ++j) { if (lo + j < nt) a[lo + j] = acc; acc += v[j]; }
-        carry += sm[31];
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) a[nt] = carry;
-      totals[arr] = carry;
+      const uint64_t incl = x[arr] + (warp ? sm[arr][warp - 1] : 0);
+      if (i < n_segs) a[i] = incl - v[arr];
+      totals[arr] = sm[arr][31];
+      if (i == 0) a[n_segs] = totals[arr];
     }
   }
   // this rank's totals: the weights' first when both are present
@@ -645,14 +670,16 @@ __global__ void resid_scale_kernel(DevScalars* ds, double n_global) {
   if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample)
     ds->resid_scale = (n_global * 4294967296.0) / (double)ds->cdf_total;
 }
-// tile-local inclusive CDFs of the copy counts (cc) and of the residual fractions (cl) + their tile totals
+// segment-local inclusive CDFs of the copy counts (cc) and of the residual fractions (cl) + the segment totals
 template <typename Real>
 __global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                               uint64_t* cc, uint64_t* tile_c, uint64_t* cl, uint64_t* tile_r,
-                                                               int nt, int conditional) {
+                                                               uint64_t* cc, uint64_t* seg_c, uint64_t* cl, uint64_t* seg_r,
+                                                               int nt, int seg_tiles, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   if (conditional && !ds->do_resample) return;
-  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+  const int t0 = blockIdx.x * seg_tiles, t1 = min(t0 + seg_tiles, nt);
+  uint64_t run_c = 0, run_r = 0;
+  for (int tile = t0; tile < t1; ++tile) {
     const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
     uint64_t q[4], c[4], r[4], cs = 0, rs = 0;
     load_q4(lw, i, n, ds->max_lw, scale, q);
@@ -663,68 +690,52 @@ __global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, i
       cs += c[j]; rs += r[j];
     }
     uint64_t ctot, rtot;
-    uint64_t ic = block_scan_u64(cs, sm, &ctot) - cs;
-    uint64_t ir = block_scan_u64(rs, sm, &rtot) - rs;
+    uint64_t ic = run_c + block_scan_u64(cs, sm, &ctot) - cs;
+    uint64_t ir = run_r + block_scan_u64(rs, sm, &rtot) - rs;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { ic += c[j]; ir += r[j]; cc[i + j] = ic; cl[i + j] = ir; }
-    if (threadIdx.x == 0) { tile_c[tile] = ctot; tile_r[tile] = rtot; }
+    run_c += ctot; run_r += rtot;
   }
+  if (threadIdx.x == 0) { seg_c[blockIdx.x] = run_c; seg_r[blockIdx.x] = run_r; }
 }
 
 // ------------------------------------------------------------------------------------------------
 // search: ancestor of every output slot
 // ------------------------------------------------------------------------------------------------
 struct CdfView {
-  const uint64_t* seg[GSMC_MAX_RANKS];   // tile-local inclusive CDF of every rank (peer-mapped)
-  const uint64_t* tp[GSMC_MAX_RANKS];    // exclusive tile prefixes of every rank, nt+1 entries (peer-mapped)
+  const uint64_t* seg[GSMC_MAX_RANKS];   // segment-local inclusive CDF of every rank (peer-mapped)
+  const uint64_t* sp[GSMC_MAX_RANKS];    // exclusive segment prefixes of every rank, n_segs+1 entries (peer-mapped)
   int64_t n_per;                         // particles per rank
-  int nt;                                // tiles per rank
+  int n_pad;                             // padded particles per rank (the last segment ends here)
+  int seg_len;                           // particles per segment (a multiple of GSMC_TILE)
+  int n_segs;                            // segments per rank
   int nranks;
 };
-// smallest j in [0, len) with arr[j] > T; len if none
-__device__ __forceinline__ int upper_u64(const uint64_t* arr, int len, uint64_t T) {
+// The two threshold predicates "C > threshold" over integer CDF values C:
+//   GtU64  exact integers (iid / replay mode: T_j = floor(floor(u_j 2^53) C_N / 2^53))
+//   GtF64  double precision (sorted mode: t_k = min((double)S_k * ratio, t_max)); both are monotone in C
+struct GtU64 { uint64_t T; __device__ __forceinline__ bool operator()(uint64_t c) const { return c > T; } };
+struct GtF64 { double t; __device__ __forceinline__ bool operator()(uint64_t c) const { return (double)c > t; } };
+
+// smallest j in [0, len) with gt(add + arr[j]); len if none
+template <class P>
+__device__ __forceinline__ int upper_pred(const uint64_t* arr, int len, uint64_t add, const P gt) {
   int l = 0, h = len;
   while (l < h) {
     const int mid = (l + h) >> 1;
-    if (__ldg(arr + mid) > T) h = mid; else l = mid + 1;
+    if (gt(add + __ldg(arr + mid))) h = mid; else l = mid + 1;
   }
   return l;
 }
-// rank that owns threshold T and the offset of its segment
-__device__ __forceinline__ int owner_rank(const CdfView& v, const DevScalars* ds, uint64_t T, uint64_t* off_out) {
-  uint64_t off = 0;
-  int r = 0;
-  for (; r < v.nranks - 1; ++r) {
-    if (off + ds->cdf_rank_total[r] > T) break;
-    off += ds->cdf_rank_total[r];
-  }
-  *off_out = off;
-  return r;
-}
-// ancestor word of threshold T against the global CDF: min{i : C_i > T}. Two levels: the tile whose
-// inclusive end exceeds T, then the position inside the tile.
-__device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, uint64_t T) {
-  uint64_t off;
-  const int r = owner_rank(v, ds, T, &off);
-  const uint64_t Tl = T - off;
-  const uint64_t* tp = v.tp[r];
-  const int t = upper_u64(tp + 1, v.nt, Tl);
-  int64_t j = v.n_per - 1;                        // T >= C_N can only happen when the last spacing is 0
-  if (t < v.nt) {
-    const uint64_t Tt = Tl - __ldg(tp + t);
-    j = (int64_t)t * GSMC_TILE + upper_u64(v.seg[r] + (int64_t)t * GSMC_TILE, GSMC_TILE, Tt);
-    if (j > v.n_per - 1) j = v.n_per - 1;
-  }
-  return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
-}
-// smallest j in [0, len) with arr[j] > T (len if none), by a full warp: 32 probes per round trip
-__device__ __forceinline__ int upper_u64_warp(const uint64_t* arr, int len, uint64_t T) {
+// the same by a full warp: 32 probes per round trip (32-ary search)
+template <class P>
+__device__ __forceinline__ int upper_pred_warp(const uint64_t* arr, int len, uint64_t add, const P gt) {
   const int lane = threadIdx.x & 31;
   int lo = 0, hi = len;                           // answer in [lo, hi]; hi = len means "none"
   while (hi > lo) {
     const int step = (hi - lo + 31) >> 5;
     const int p = lo + lane * step;
-    const bool pred = (p >= hi) || (__ldg(arr + p) > T);
+    const bool pred = (p >= hi) || gt(add + __ldg(arr + p));
     const unsigned mask = __ballot_sync(0xffffffffu, pred);
     const int f = mask ? __ffs((int)mask) - 1 : 32;
     const int new_hi = (f == 32) ? hi : lo + f * step;
@@ -735,39 +746,44 @@ __device__ __forceinline__ int upper_u64_warp(const uint64_t* arr, int len, uint
   }
   return lo;
 }
-// Same result as search_global, computed by a full warp (32-ary search), so that a search over a peer's
-// segment costs ~5 NVLink round trips instead of ~24.
-__device__ __forceinline__ uint32_t search_global_warp(const CdfView& v, const DevScalars* ds, uint64_t T) {
-  uint64_t off;
-  const int r = owner_rank(v, ds, T, &off);
-  const uint64_t Tl = T - off;
-  const uint64_t* tp = v.tp[r];
-  const int t = upper_u64_warp(tp + 1, v.nt, Tl);
+// Ancestor word of a threshold against the global CDF: min{i : gt(C_i)}, clamped to the last particle.
+// Three levels: owner rank (its inclusive end passes the predicate), segment, position in the segment.
+template <bool WARP, class P>
+__device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, const P gt) {
+  uint64_t off = 0;
+  int r = 0;
+  for (; r < v.nranks - 1; ++r) {
+    if (gt(off + ds->cdf_rank_total[r])) break;
+    off += ds->cdf_rank_total[r];
+  }
+  const uint64_t* sp = v.sp[r];
+  const int s = WARP ? upper_pred_warp(sp + 1, v.n_segs, off, gt) : upper_pred(sp + 1, v.n_segs, off, gt);
   int64_t j = v.n_per - 1;
-  if (t < v.nt) {
-    const uint64_t Tt = Tl - __ldg(tp + t);
-    j = (int64_t)t * GSMC_TILE + upper_u64_warp(v.seg[r] + (int64_t)t * GSMC_TILE, GSMC_TILE, Tt);
+  if (s < v.n_segs) {
+    const int64_t first = (int64_t)s * v.seg_len;
+    const int len = (int)(first + v.seg_len <= v.n_pad ? v.seg_len : v.n_pad - first);
+    const uint64_t add = off + __ldg(sp + s);
+    j = first + (WARP ? upper_pred_warp(v.seg[r] + first, len, add, gt) : upper_pred(v.seg[r] + first, len, add, gt));
     if (j > v.n_per - 1) j = v.n_per - 1;
   }
   return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
 }
 
-__device__ __forceinline__ MulDiv threshold_muldiv(const DevScalars* ds) {
-  MulDiv md;
-  md.b = ds->cdf_total; md.d = ds->spacing_total; md.ratio = ds->thr_ratio; md.inv_d = ds->thr_inv;
-  return md;
+// sorted thresholds: t_k = min((double)S_k * ratio, t_max)
+__device__ __forceinline__ double sorted_threshold(uint64_t S, double ratio, double tmax) {
+  const double t = (double)S * ratio;
+  return t < tmax ? t : tmax;
 }
 
 // Sorted mode, step 1: ancestor word of the FIRST threshold of every tile (one thread per tile, all
 // binary searches in flight at once), win[b] for b in [0, nt]; win[nt] closes the last tile.
-// tile_prefix: exclusive tile prefixes of the stored spacings esp.
 __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
-                                                               const DevScalars* ds, const uint64_t* tile_prefix,
-                                                               const uint32_t* esp, int nt, uint32_t* win, int conditional) {
+                                                               const DevScalars* ds, const uint64_t* seg_e, const uint64_t* tile_e,
+                                                               int seg_tiles, const uint32_t* esp, int nt, uint32_t* win, int conditional) {
   if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws;
   const uint32_t last = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
-  const MulDiv md = threshold_muldiv(ds);
+  const double ratio = ds->thr_ratio, tmax = ds->thr_max;
   uint64_t base = 0;
   for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
   // boundaries 0..nt-1: one thread each (their ancestors are almost always in the local segment)
@@ -775,8 +791,9 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
     const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
     uint32_t w = last;
     if (kt < m_draws) {
-      const uint64_t S = base + tile_prefix[b] + (uint64_t)esp[(int64_t)b * GSMC_TILE];
-      w = search_global(v, ds, muldiv_floor(S, md));
+      const uint64_t S = base + seg_e[b / seg_tiles] + tile_e[b] + (uint64_t)esp[(int64_t)b * GSMC_TILE];
+      GtF64 gt; gt.t = sorted_threshold(S, ratio, tmax);
+      w = search_global<false>(v, ds, gt);
     }
     win[b] = w;
   }
@@ -787,106 +804,97 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
     uint32_t w = last;
     if (kt < m_draws) {
       const uint64_t S = base + ds->spacing_rank_total[rank] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
-      w = search_global_warp(v, ds, muldiv_floor(S, md));
+      GtF64 gt; gt.t = sorted_threshold(S, ratio, tmax);
+      w = search_global<true>(v, ds, gt);
     }
     if (threadIdx.x == 0) win[nt] = w;
   }
 }
 
 // Sorted mode, step 2. Tile b of this rank handles thresholds k_first + b*TILE + [0, TILE) and writes
-// anc[b*TILE + ...]. T_k = floor(S_k C_N / S_tot);  anc = min{i : C_i > T_k}  <=>  C_i * S_tot > S_k * C_N
-// (128-bit). The CDF window [win[b], win[b+1]] the tile can map to is staged in shared memory.
+// anc[b*TILE + ...]:  anc_k = min{i : (double)C_i > t_k}. The CDF window [win[b], win[b+1]] the tile can map
+// to is staged in shared memory as doubles; every thread binary-searches its first threshold (same number
+// of probes for the whole block) and walks to the next three (sorted thresholds: ~1 slot apart).
 #define GSMC_WIN_CAP 3072
-#ifndef GSMC_SEARCH_MINBLOCKS
-#define GSMC_SEARCH_MINBLOCKS 4
-#endif
-__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_MINBLOCKS) search_sorted_kernel(CdfView v, uint64_t k_first, int rank,
-                                                                   const DevScalars* ds, const uint64_t* tile_prefix, const uint32_t* esp,
-                                                                   const uint32_t* win, uint32_t* anc, int64_t n_out, int nt,
-                                                                   int det_offset, int conditional) {
-  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
-  __shared__ uint64_t cwin[GSMC_WIN_CAP];
+__global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, uint64_t k_first, int rank, const DevScalars* ds,
+                                                                   const uint64_t* seg_e, const uint64_t* tile_e, int seg_tiles,
+                                                                   const uint32_t* esp, const uint32_t* win, uint32_t* anc,
+                                                                   int64_t n_out, int nt, int det_offset, int conditional) {
+  __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
+  __shared__ double cwin[GSMC_WIN_CAP];
   if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws;
-  const MulDiv md = threshold_muldiv(ds);
+  const double ratio = ds->thr_ratio, tmax = ds->thr_max;
   uint64_t base = 0;
   for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
-  const uint64_t st = md.d, cn = md.b;
-  constexpr int PF = GSMC_WIN_CAP / GSMC_BLOCK;           // window elements per thread
-  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, buf ^= 1) {
     const uint64_t kt = k_first + (uint64_t)tile * GSMC_TILE;
     if (kt >= m_draws) break;                            // uniform per block
+    const int64_t o_local = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+    const uint4 ev = *reinterpret_cast<const uint4*>(esp + o_local);     // spacings beyond M were stored as 0
     // window [win[tile], win[tile+1]]: [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the
-    // head [0, hi] of r0+1. Its CDF values are fetched into registers first, so the DRAM / NVLink latency
-    // overlaps the spacing scan below.
+    // head [0, hi] of r0+1
     const uint32_t w0 = win[tile], w1 = win[tile + 1];
     const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT), r1 = (int)(w1 >> GSMC_ANC_RANK_SHIFT);
-    const int64_t lo = (int64_t)(w0 & GSMC_ANC_INDEX_MASK), hi = (int64_t)(w1 & GSMC_ANC_INDEX_MASK);
-    const int64_t len_a = (r1 == r0) ? hi - lo + 1 : v.n_per - lo;
-    const int64_t len_b = (r1 == r0) ? 0 : hi + 1;
+    const int lo = (int)(w0 & GSMC_ANC_INDEX_MASK), hi = (int)(w1 & GSMC_ANC_INDEX_MASK);
+    const int64_t len_a = (r1 == r0) ? (int64_t)hi - lo + 1 : v.n_per - lo;
+    const int64_t len_b = (r1 == r0) ? 0 : (int64_t)hi + 1;
     const bool staged = (r1 == r0 || r1 == r0 + 1) && len_a + len_b <= GSMC_WIN_CAP;
     const int la = (int)len_a, len = (int)(len_a + len_b);
-    uint64_t pre[PF];
     if (staged) {
       uint64_t off = 0;
       for (int q = 0; q < r0; ++q) off += ds->cdf_rank_total[q];
       const uint64_t off_b = off + ds->cdf_rank_total[r0];
       const uint64_t* seg_a = v.seg[r0];
       const uint64_t* seg_b = v.seg[r1];
-      const uint64_t* tp_a = v.tp[r0];
-      const uint64_t* tp_b = v.tp[r1];
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        const int j = threadIdx.x + u * GSMC_BLOCK;
-        uint64_t c = 0;
-        if (j < la) c = off + __ldg(tp_a + ((lo + j) >> GSMC_TILE_SHIFT)) + __ldg(seg_a + lo + j);
-        else if (j < len) c = off_b + __ldg(tp_b + ((j - la) >> GSMC_TILE_SHIFT)) + __ldg(seg_b + (j - la));
-        pre[u] = c;
+      const uint64_t* sp_a = v.sp[r0];
+      const uint64_t* sp_b = v.sp[r1];
+      // the window is shorter than 3 segments + 1: segment index by comparison with the next boundaries
+      const int s0 = lo / v.seg_len;
+      const int b1 = (s0 + 1) * v.seg_len, b2 = b1 + v.seg_len, b3 = b2 + v.seg_len;
+      for (int j = threadIdx.x; j < len; j += GSMC_BLOCK) {
+        uint64_t c;
+        if (j < la) {
+          const int idx = lo + j;
+          const int s = s0 + (idx >= b1) + (idx >= b2) + (idx >= b3);
+          c = off + __ldg(sp_a + s) + __ldg(seg_a + idx);
+        } else {
+          const int idx = j - la;
+          const int s = (idx >= v.seg_len) + (idx >= 2 * v.seg_len) + (idx >= 3 * v.seg_len);
+          c = off_b + __ldg(sp_b + s) + __ldg(seg_b + idx);
+        }
+        cwin[j] = (double)c;
       }
     }
-    const int64_t o_local = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
-    const uint64_t k = k_first + (uint64_t)o_local;
-    const uint4 ev = *reinterpret_cast<const uint4*>(esp + o_local);     // spacings beyond M were stored as 0
     const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w};
-    uint64_t tot;
     const uint64_t tsum = (uint64_t)e[0] + e[1] + e[2] + e[3];
-    uint64_t S = base + tile_prefix[tile] + block_scan_u64(tsum, sm, &tot) - tsum;
+    uint64_t tot, dummy;
+    // the barrier inside the scan also publishes the staged window
+    uint64_t S = base + seg_e[tile / seg_tiles] + tile_e[tile] + block_scan_and_sum(tsum, 0, sm, buf, &tot, &dummy) - tsum;
+    const uint64_t k = k_first + (uint64_t)o_local;
     uint32_t a[4];
     bool have[4];
-    uint64_t Sk[4];
+    double t[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { S += e[j]; Sk[j] = S; have[j] = k + j < m_draws; }
+    for (int j = 0; j < 4; ++j) { S += e[j]; t[j] = sorted_threshold(S, ratio, tmax); have[j] = k + j < m_draws; }
     if (staged) {
-      __syncthreads();                                   // previous tile's readers are done with cwin
-#pragma unroll
-      for (int u = 0; u < PF; ++u) { const int j = threadIdx.x + u * GSMC_BLOCK; if (j < len) cwin[j] = pre[u]; }
-      __syncthreads();
-      // anc = min{p : C_p > T_k}, T_k = floor(S_k C_N / S_tot)  <=>  C_p * S_tot > S_k * C_N  (exact, 128 bit).
-      // Search with the double-precision estimate of T_k (cheap 64-bit compares), then settle the answer
-      // with the exact predicate: the estimate is within ~2^12 of T_k, so it can only be off across CDF
-      // steps smaller than that, and the two correction loops below almost never iterate.
+      // pos = #{p : cwin[p] <= t}: branch-free binary search, the same probe count for every thread
       int pos = 0;
+      for (int step = 1 << (31 - __clz(len)); step > 0; step >>= 1) {
+        const int cand = pos + step;
+        if (cand <= len && cwin[cand - 1] <= t[0]) pos = cand;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (!have[j]) { a[j] = 0; continue; }
-        const uint64_t Ta = (uint64_t)((double)Sk[j] * md.ratio);
-        if (j == 0) {
-          int l = 0, h = len;
-          while (l < h) { const int mid = (l + h) >> 1; if (cwin[mid] > Ta) h = mid; else l = mid + 1; }
-          pos = l;
-        } else {
-          while (pos < len && cwin[pos] <= Ta) ++pos;    // thresholds are sorted: ancestors are monotone, ~1 apart
-        }
-        const uint64_t chi = __umul64hi(Sk[j], cn), clo = Sk[j] * cn;
-        while (pos < len && !mul_gt(cwin[pos], st, chi, clo)) ++pos;
-        while (pos > 0 && mul_gt(cwin[pos - 1], st, chi, clo)) --pos;
+        if (j > 0) { while (pos < len && cwin[pos] <= t[j]) ++pos; }
         const int pc = pos < len ? pos : len - 1;
         a[j] = pc < la ? (((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pc))
                        : (((uint32_t)r1 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pc - la));
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a[j] = have[j] ? search_global(v, ds, muldiv_floor(Sk[j], md)) : 0;
+      for (int j = 0; j < 4; ++j) { GtF64 gt; gt.t = t[j]; a[j] = have[j] ? search_global<false>(v, ds, gt) : 0; }
     }
     // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
     const int64_t o = o_local + (det_offset ? (int64_t)ds->n_det : 0);
@@ -896,6 +904,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_MINBLOCKS) search_sort
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (have[j] && o + j < n_out) anc[o + j] = a[j];
     }
+    __syncthreads();                                     // everybody is done with cwin before the next tile is staged
   }
 }
 
@@ -913,23 +922,26 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_iid_kernel(CdfView v, const
   else { double u0, u1; uniform_pair(seed, (uint64_t)j >> 1, event, stream, &u0, &u1); uj = (j & 1) ? u1 : u0; }
   const uint64_t t = (uint64_t)floor(uj * 9007199254740992.0);
   const uint64_t cn = ds->cdf_total;
-  const uint64_t T = (__umul64hi(t, cn) << 11) | ((t * cn) >> 53);
-  const uint32_t w = search_global(v, ds, T);
+  GtU64 gt; gt.T = (__umul64hi(t, cn) << 11) | ((t * cn) >> 53);
+  const uint32_t w = search_global<false>(v, ds, gt);
   const int64_t o = j + (out_offset_det ? (int64_t)ds->n_det : 0);
   if (anc32) anc32[o] = w;
   if (anc64) anc64[o] = (int64_t)(w >> GSMC_ANC_RANK_SHIFT) * v.n_per + (int64_t)(w & GSMC_ANC_INDEX_MASK);
 }
 
 // residual scheme, deterministic part: slot o < n_det belongs to min{i : Cc_i > o}, Cc in two levels
-__global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* cc, const uint64_t* tile_c, int nt, int64_t n,
-                                                                const DevScalars* ds, uint32_t* anc, int conditional) {
+__global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* cc, const uint64_t* seg_c, int n_segs, int seg_len, int n_pad,
+                                                                int64_t n, const DevScalars* ds, uint32_t* anc, int conditional) {
   if (conditional && !ds->do_resample) return;
   const int64_t o = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
   if (o >= (int64_t)ds->n_det || o >= n) return;
-  const int t = upper_u64(tile_c + 1, nt, (uint64_t)o);
+  GtU64 gt; gt.T = (uint64_t)o;
+  const int s = upper_pred(seg_c + 1, n_segs, 0, gt);
   int64_t l = n - 1;
-  if (t < nt) {
-    l = (int64_t)t * GSMC_TILE + upper_u64(cc + (int64_t)t * GSMC_TILE, GSMC_TILE, (uint64_t)o - __ldg(tile_c + t));
+  if (s < n_segs) {
+    const int64_t first = (int64_t)s * seg_len;
+    const int len = (int)(first + seg_len <= n_pad ? seg_len : n_pad - first);
+    l = first + upper_pred(cc + first, len, __ldg(seg_c + s), gt);
     if (l > n - 1) l = n - 1;
   }
   anc[o] = (uint32_t)l;

@@ -256,16 +256,25 @@ void orc_search_iid(const uint64_t* cdf, int64_t n, const double* u, int64_t m, 
     anc[j] = i < n ? i : n - 1;
   }
 }
+/* Sorted uniforms from the exponential spacings E[0..m]: S_k = E_0 + .. + E_k, threshold
+ * t_k = min((double)S_k * ratio, t_max) with ratio = (double)C_N / (double)S_tot and t_max the largest
+ * double below (double)C_N; anc_k = min{i : (double)C_i > t_k}. The comparison is made in double precision
+ * (like the reference's own weights/sum(weights) arithmetic, particle_filter.jl:199-200); both sides
+ * are monotone, and t_max guarantees that an ancestor with non-zero weight exists. */
 void orc_search_sorted(const uint64_t* cdf, int64_t n, const uint64_t* E, int64_t m, int64_t* anc) {
   const uint64_t total = cdf[n - 1];
   uint64_t stot = 0;
   for (int64_t j = 0; j <= m; ++j) stot += E[j];
+  const double cn = (double)total;
+  const double ratio = cn / (double)stot;
+  const double tmax = gm_from_bits(gm_to_bits(cn) - 1);
   uint64_t S = 0;
   int64_t i = 0;
   for (int64_t k = 0; k < m; ++k) {
     S += E[k];
-    uint64_t T = (uint64_t)(((u128)S * total) / stot);      /* T_k = floor(S_k C_N / S_tot) <= C_N */
-    while (i < n - 1 && cdf[i] <= T) ++i;                   /* min{i: C_i > T_k}; monotone in k */
+    double t = (double)S * ratio;
+    if (!(t < tmax)) t = tmax;
+    while (i < n - 1 && (double)cdf[i] <= t) ++i;             /* min{i: (double)C_i > t_k}; monotone in k */
     anc[k] = i;
   }
 }
