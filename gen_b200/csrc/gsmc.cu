@@ -525,7 +525,7 @@ static int launch_scan(gsmc_filter* f, int cls, uint64_t* a0, uint64_t* a1, int 
     if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
     if (what & SCAN_E) NK(g_nccl.AllGather((const char*)(f->ds->spacing_rank_total + f->rank), f->ds->spacing_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
     ProfScope ps(f, KC_OTHER);
-    totals_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, f->cfg.seed, (uint64_t)f->N, what, conditional);
+    totals_kernel<<<1, 1024, 0, f->stream>>>(a0, a1, f->n_segs, f->ds, f->nranks, f->rank, f->cfg.seed, (uint64_t)f->N, what, conditional);
     CK(cudaGetLastError());
   }
   return GSMC_OK;
@@ -589,9 +589,16 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     { ProfScope ps(f, KC_SEARCH);
       partition_kernel<<<(nt + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(
           v, f->cfg.seed, k_first, f->rank, f->ds, f->seg_e, f->tile_e, st, f->esp, nt, f->win, conditional); }
-    { ProfScope ps(f, KC_SEARCH);
-      search_sorted_kernel<<<tile_grid(f, (const void*)search_sorted_kernel), GSMC_BLOCK, 0, f->stream>>>(
-          v, k_first, f->rank, f->ds, f->seg_e, f->tile_e, st, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
+    { static bool attr_set = false;
+      if (!attr_set) { CK(cudaFuncSetAttribute((const void*)search_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMC_SEARCH_SMEM)); attr_set = true; }
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)search_sorted_kernel, GSMC_BLOCK, GSMC_SEARCH_SMEM) != cudaSuccess || occ < 1) occ = 2;
+      const int n_super = nt / (GSMC_SUPERTILE / GSMC_TILE);
+      const int grid = n_super < f->sm_count * occ ? n_super : f->sm_count * occ;
+      const uint32_t magic = st > 1 ? (uint32_t)(0x100000000ULL / (uint64_t)st) + 1u : 0u;
+      ProfScope ps(f, KC_SEARCH);
+      search_sorted_kernel<<<grid, GSMC_BLOCK, GSMC_SEARCH_SMEM, f->stream>>>(
+          v, k_first, f->ds, f->tile_e, (uint32_t)st, magic, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;

@@ -587,6 +587,19 @@ __device__ __forceinline__ void finish_totals(DevScalars* ds, int nranks, uint64
   }
 }
 
+// The segment prefixes are kept as GLOBAL prefixes: the totals of the lower ranks are added once here, so
+// that every consumer (and every peer) reads C_i = sp[segment] + cl[i] without a rank-offset loop.
+__device__ __forceinline__ void globalise_prefixes(uint64_t* a0, uint64_t* a1, int n_segs, const DevScalars* ds, int what, int rank) {
+  uint64_t off_q = 0, off_e = 0;
+  for (int r = 0; r < rank; ++r) { off_q += ds->cdf_rank_total[r]; off_e += ds->spacing_rank_total[r]; }
+  uint64_t* aq = (what & SCAN_Q) ? a0 : nullptr;
+  uint64_t* ae = (what & SCAN_E) ? ((what & SCAN_Q) ? a1 : a0) : nullptr;
+  for (int i = threadIdx.x; i <= n_segs; i += blockDim.x) {
+    if (aq) aq[i] += off_q;
+    if (ae) ae[i] += off_e;
+  }
+}
+
 // One block: exclusive scans (in place) of up to two arrays of n_segs segment totals (n_segs <= 1024),
 // a[n_segs] = total; then this rank's totals go to ds, are exchanged with the peers (fused LL exchange over
 // NVLink) and finish_totals runs. With exchange == 0 on a multi-rank run the host performs the
@@ -653,12 +666,18 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(uint64_t* a0, uint6
     }
   }
   if (threadIdx.x == 0 && !skip) finish_totals(ds, nranks, seed, n_global, what, totals[0], totals[1]);
+  if (nranks > 1 && !skip) {
+    __syncthreads();
+    globalise_prefixes(a0, a1, n_segs, ds, what, rank);
+  }
 }
 // multi-rank runs that exchange the totals with ncclAllGather (GSMC_NCCL_SCALARS=1) finish here
-__global__ void totals_kernel(DevScalars* ds, int nranks, uint64_t seed, uint64_t n_global, int what, int conditional) {
-  if (threadIdx.x || blockIdx.x) return;
+__global__ void __launch_bounds__(1024) totals_kernel(uint64_t* a0, uint64_t* a1, int n_segs, DevScalars* ds, int nranks, int rank,
+                                                      uint64_t seed, uint64_t n_global, int what, int conditional) {
   if (conditional && !ds->do_resample) return;
-  finish_totals(ds, nranks, seed, n_global, what, 0, 0);
+  if (threadIdx.x == 0) finish_totals(ds, nranks, seed, n_global, what, 0, 0);
+  __syncthreads();
+  if (nranks > 1) globalise_prefixes(a0, a1, n_segs, ds, what, rank);
 }
 
 // residual scheme: e_i = floor(q_i * resid_scale); c_i = e_i >> 32 copies; r_i = e_i & (2^32-1)
@@ -750,19 +769,19 @@ __device__ __forceinline__ int upper_pred_warp(const uint64_t* arr, int len, uin
 // Three levels: owner rank (its inclusive end passes the predicate), segment, position in the segment.
 template <bool WARP, class P>
 __device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, const P gt) {
-  uint64_t off = 0;
+  uint64_t end = 0;
   int r = 0;
   for (; r < v.nranks - 1; ++r) {
-    if (gt(off + ds->cdf_rank_total[r])) break;
-    off += ds->cdf_rank_total[r];
+    end += ds->cdf_rank_total[r];
+    if (gt(end)) break;
   }
-  const uint64_t* sp = v.sp[r];
-  const int s = WARP ? upper_pred_warp(sp + 1, v.n_segs, off, gt) : upper_pred(sp + 1, v.n_segs, off, gt);
+  const uint64_t* sp = v.sp[r];                   // global exclusive prefixes of rank r's segments
+  const int s = WARP ? upper_pred_warp(sp + 1, v.n_segs, 0, gt) : upper_pred(sp + 1, v.n_segs, 0, gt);
   int64_t j = v.n_per - 1;
   if (s < v.n_segs) {
     const int64_t first = (int64_t)s * v.seg_len;
     const int len = (int)(first + v.seg_len <= v.n_pad ? v.seg_len : v.n_pad - first);
-    const uint64_t add = off + __ldg(sp + s);
+    const uint64_t add = __ldg(sp + s);
     j = first + (WARP ? upper_pred_warp(v.seg[r] + first, len, add, gt) : upper_pred(v.seg[r] + first, len, add, gt));
     if (j > v.n_per - 1) j = v.n_per - 1;
   }
@@ -776,23 +795,23 @@ __device__ __forceinline__ double sorted_threshold(uint64_t S, double ratio, dou
 }
 
 // Sorted mode, step 1: ancestor word of the FIRST threshold of every tile (one thread per tile, all
-// binary searches in flight at once), win[b] for b in [0, nt]; win[nt] closes the last tile.
+// binary searches in flight at once), win[b] for b in [0, nt]; win[nt] closes the last tile. Also turns
+// tile_e[b] into the GLOBAL spacing prefix before tile b (adds its segment's prefix).
 __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
-                                                               const DevScalars* ds, const uint64_t* seg_e, const uint64_t* tile_e,
+                                                               const DevScalars* ds, const uint64_t* seg_e, uint64_t* tile_e,
                                                                int seg_tiles, const uint32_t* esp, int nt, uint32_t* win, int conditional) {
   if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws;
   const uint32_t last = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
   const double ratio = ds->thr_ratio, tmax = ds->thr_max;
-  uint64_t base = 0;
-  for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
   // boundaries 0..nt-1: one thread each (their ancestors are almost always in the local segment)
   for (int b = blockIdx.x * GSMC_BLOCK + threadIdx.x; b < nt; b += gridDim.x * GSMC_BLOCK) {
     const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
+    const uint64_t S0 = seg_e[b / seg_tiles] + tile_e[b];
+    tile_e[b] = S0;
     uint32_t w = last;
     if (kt < m_draws) {
-      const uint64_t S = base + seg_e[b / seg_tiles] + tile_e[b] + (uint64_t)esp[(int64_t)b * GSMC_TILE];
-      GtF64 gt; gt.t = sorted_threshold(S, ratio, tmax);
+      GtF64 gt; gt.t = sorted_threshold(S0 + (uint64_t)esp[(int64_t)b * GSMC_TILE], ratio, tmax);
       w = search_global<false>(v, ds, gt);
     }
     win[b] = w;
@@ -803,7 +822,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
     const uint64_t kt = k_first + (uint64_t)nt * GSMC_TILE;
     uint32_t w = last;
     if (kt < m_draws) {
-      const uint64_t S = base + ds->spacing_rank_total[rank] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
+      const uint64_t S = seg_e[v.n_segs] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
       GtF64 gt; gt.t = sorted_threshold(S, ratio, tmax);
       w = search_global<true>(v, ds, gt);
     }
@@ -811,31 +830,35 @@ __global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64
   }
 }
 
-// Sorted mode, step 2. Tile b of this rank handles thresholds k_first + b*TILE + [0, TILE) and writes
-// anc[b*TILE + ...]:  anc_k = min{i : (double)C_i > t_k}. The CDF window [win[b], win[b+1]] the tile can map
-// to is staged in shared memory as doubles; every thread binary-searches its first threshold (same number
-// of probes for the whole block) and walks to the next three (sorted thresholds: ~1 slot apart).
-#define GSMC_WIN_CAP 3072
-__global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, uint64_t k_first, int rank, const DevScalars* ds,
-                                                                   const uint64_t* seg_e, const uint64_t* tile_e, int seg_tiles,
-                                                                   const uint32_t* esp, const uint32_t* win, uint32_t* anc,
-                                                                   int64_t n_out, int nt, int det_offset, int conditional) {
+// Sorted mode, step 2. One block iteration handles a SUPERTILE of 2048 consecutive thresholds (8 per thread)
+// and writes their ancestors anc_k = min{i : (double)C_i > t_k}. The CDF window [win[2m], win[2m+2]] the
+// supertile can map to is staged in shared memory as doubles (+inf sentinel at the end); every thread finds
+// its first threshold with a bound-check-free binary search (same probe count for the whole block) and
+// walks to the next seven (sorted thresholds: ~1 slot apart).
+#define GSMC_SEARCH_TPT 8                                   // thresholds per thread
+#define GSMC_SUPERTILE (GSMC_BLOCK * GSMC_SEARCH_TPT)       // 2048
+#define GSMC_WIN_CAP 6144
+#define GSMC_SEARCH_SMEM ((GSMC_WIN_CAP + 1) * 8)
+__global__ void __launch_bounds__(GSMC_BLOCK, 4) search_sorted_kernel(CdfView v, uint64_t k_first, const DevScalars* ds,
+                                                                      const uint64_t* tile_e, uint32_t seg_tiles, uint32_t seg_magic,
+                                                                      const uint32_t* esp, const uint32_t* win, uint32_t* anc,
+                                                                      int64_t n_out, int nt, int det_offset, int conditional) {
+  extern __shared__ double cwin[];                        // GSMC_WIN_CAP + 1 doubles
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
-  __shared__ double cwin[GSMC_WIN_CAP];
   if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws;
   const double ratio = ds->thr_ratio, tmax = ds->thr_max;
-  uint64_t base = 0;
-  for (int r = 0; r < rank; ++r) base += ds->spacing_rank_total[r];
+  const int n_super = nt / (GSMC_SUPERTILE / GSMC_TILE);
   int buf = 0;
-  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, buf ^= 1) {
-    const uint64_t kt = k_first + (uint64_t)tile * GSMC_TILE;
+  for (int m = blockIdx.x; m < n_super; m += gridDim.x, buf ^= 1) {
+    const int tile = m * (GSMC_SUPERTILE / GSMC_TILE);
+    const uint64_t kt = k_first + (uint64_t)m * GSMC_SUPERTILE;
     if (kt >= m_draws) break;                            // uniform per block
-    const int64_t o_local = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
-    const uint4 ev = *reinterpret_cast<const uint4*>(esp + o_local);     // spacings beyond M were stored as 0
-    // window [win[tile], win[tile+1]]: [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the
-    // head [0, hi] of r0+1
-    const uint32_t w0 = win[tile], w1 = win[tile + 1];
+    const int64_t o_local = (int64_t)m * GSMC_SUPERTILE + GSMC_SEARCH_TPT * threadIdx.x;
+    const uint4 ev0 = *reinterpret_cast<const uint4*>(esp + o_local);     // spacings beyond M were stored as 0
+    const uint4 ev1 = *reinterpret_cast<const uint4*>(esp + o_local + 4);
+    // window [w0, w1]: [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the head [0, hi] of r0+1
+    const uint32_t w0 = win[tile], w1 = win[tile + GSMC_SUPERTILE / GSMC_TILE];
     const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT), r1 = (int)(w1 >> GSMC_ANC_RANK_SHIFT);
     const int lo = (int)(w0 & GSMC_ANC_INDEX_MASK), hi = (int)(w1 & GSMC_ANC_INDEX_MASK);
     const int64_t len_a = (r1 == r0) ? (int64_t)hi - lo + 1 : v.n_per - lo;
@@ -843,68 +866,67 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_sorted_kernel(CdfView v, ui
     const bool staged = (r1 == r0 || r1 == r0 + 1) && len_a + len_b <= GSMC_WIN_CAP;
     const int la = (int)len_a, len = (int)(len_a + len_b);
     if (staged) {
-      uint64_t off = 0;
-      for (int q = 0; q < r0; ++q) off += ds->cdf_rank_total[q];
-      const uint64_t off_b = off + ds->cdf_rank_total[r0];
-      const uint64_t* seg_a = v.seg[r0];
-      const uint64_t* seg_b = v.seg[r1];
+      // C_i = sp[segment(i)] + cl[i] with global segment prefixes; segment(i) = (i / 1024) / seg_tiles by multiply-high
+      const uint64_t* seg_a = v.seg[r0] + lo;
       const uint64_t* sp_a = v.sp[r0];
-      const uint64_t* sp_b = v.sp[r1];
-      // the window is shorter than 3 segments + 1: segment index by comparison with the next boundaries
-      const int s0 = lo / v.seg_len;
-      const int b1 = (s0 + 1) * v.seg_len, b2 = b1 + v.seg_len, b3 = b2 + v.seg_len;
-      for (int j = threadIdx.x; j < len; j += GSMC_BLOCK) {
-        uint64_t c;
-        if (j < la) {
-          const int idx = lo + j;
-          const int s = s0 + (idx >= b1) + (idx >= b2) + (idx >= b3);
-          c = off + __ldg(sp_a + s) + __ldg(seg_a + idx);
-        } else {
-          const int idx = j - la;
-          const int s = (idx >= v.seg_len) + (idx >= 2 * v.seg_len) + (idx >= 3 * v.seg_len);
-          c = off_b + __ldg(sp_b + s) + __ldg(seg_b + idx);
-        }
-        cwin[j] = (double)c;
+#pragma unroll 4
+      for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
+        const uint32_t t = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
+        const uint32_t sg = seg_tiles == 1 ? t : __umulhi(t, seg_magic);
+        cwin[j] = (double)(__ldg(sp_a + sg) + __ldg(seg_a + j));
       }
+      if (len_b) {
+        const uint64_t* seg_b = v.seg[r1];
+        const uint64_t* sp_b = v.sp[r1];
+        for (int j = threadIdx.x; j < (int)len_b; j += GSMC_BLOCK) {
+          const uint32_t t = (uint32_t)j >> GSMC_TILE_SHIFT;
+          const uint32_t sg = seg_tiles == 1 ? t : __umulhi(t, seg_magic);
+          cwin[la + j] = (double)(__ldg(sp_b + sg) + __ldg(seg_b + j));
+        }
+      }
+      if (threadIdx.x == 0) cwin[len] = gm_inf();        // sentinel: the walks below need no bound check
     }
-    const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w};
-    const uint64_t tsum = (uint64_t)e[0] + e[1] + e[2] + e[3];
+    const uint32_t e[GSMC_SEARCH_TPT] = {ev0.x, ev0.y, ev0.z, ev0.w, ev1.x, ev1.y, ev1.z, ev1.w};
+    uint64_t tsum = 0;
+#pragma unroll
+    for (int j = 0; j < GSMC_SEARCH_TPT; ++j) tsum += e[j];
     uint64_t tot, dummy;
     // the barrier inside the scan also publishes the staged window
-    uint64_t S = base + seg_e[tile / seg_tiles] + tile_e[tile] + block_scan_and_sum(tsum, 0, sm, buf, &tot, &dummy) - tsum;
+    uint64_t S = tile_e[tile] + block_scan_and_sum(tsum, 0, sm, buf, &tot, &dummy) - tsum;
     const uint64_t k = k_first + (uint64_t)o_local;
-    uint32_t a[4];
-    bool have[4];
-    double t[4];
+    uint32_t a[GSMC_SEARCH_TPT];
+    double t[GSMC_SEARCH_TPT];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { S += e[j]; t[j] = sorted_threshold(S, ratio, tmax); have[j] = k + j < m_draws; }
+    for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { S += e[j]; t[j] = sorted_threshold(S, ratio, tmax); }
     if (staged) {
-      // pos = #{p : cwin[p] <= t}: branch-free binary search, the same probe count for every thread
+      // pos = #{p : cwin[p] <= t[0]}: every probe is in bounds and the probe count depends on len only
       int pos = 0;
-      for (int step = 1 << (31 - __clz(len)); step > 0; step >>= 1) {
-        const int cand = pos + step;
-        if (cand <= len && cwin[cand - 1] <= t[0]) pos = cand;
+      for (int rem = len; rem > 1;) {
+        const int half = rem >> 1;
+        if (cwin[pos + half - 1] <= t[0]) pos += half;
+        rem -= half;
       }
+      if (cwin[pos] <= t[0]) ++pos;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j > 0) { while (pos < len && cwin[pos] <= t[j]) ++pos; }
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
+        if (j > 0) { while (cwin[pos] <= t[j]) ++pos; }
         const int pc = pos < len ? pos : len - 1;
-        a[j] = pc < la ? (((uint32_t)r0 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(lo + pc))
-                       : (((uint32_t)r1 << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pc - la));
+        a[j] = pc < la ? (w0 + (uint32_t)pc) : ((((uint32_t)r1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pc - la));
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { GtF64 gt; gt.t = t[j]; a[j] = have[j] ? search_global<false>(v, ds, gt) : 0; }
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { GtF64 gt; gt.t = t[j]; a[j] = (k + j < m_draws) ? search_global<false>(v, ds, gt) : 0; }
     }
     // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
     const int64_t o = o_local + (det_offset ? (int64_t)ds->n_det : 0);
-    if (!det_offset && have[3] && o + 3 < n_out) {
+    if (!det_offset && k + GSMC_SEARCH_TPT <= m_draws && o + GSMC_SEARCH_TPT <= n_out) {
       *reinterpret_cast<uint4*>(anc + o) = make_uint4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<uint4*>(anc + o + 4) = make_uint4(a[4], a[5], a[6], a[7]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (have[j] && o + j < n_out) anc[o + j] = a[j];
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (k + j < m_draws && o + j < n_out) anc[o + j] = a[j];
     }
-    __syncthreads();                                     // everybody is done with cwin before the next tile is staged
+    __syncthreads();                                     // everybody is done with cwin before the next supertile is staged
   }
 }
 
