@@ -37,8 +37,37 @@ STATE_BYTES = 8                                     # S: one fp64 latent
 
 
 def make_observations(T):
-    from oracle import closed_forms as cf           # input generation only (numpy), not a compute path
-    return cf.simulate_lgssm(T, LG, 0)
+    """Synthetic observations y_1:T simulated from the model itself (numpy, seed 0); inputs only."""
+    m0, s0, a, b, q, c, r = LG
+    rng = np.random.default_rng(0)
+    x = m0 + s0 * rng.standard_normal()
+    ys = []
+    for t in range(T):
+        if t > 0:
+            x = a * x + b + q * rng.standard_normal()
+        ys.append(c * x + r * rng.standard_normal())
+    return np.array(ys)
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout: libraries (NCCL banners, torch warnings) write to fd 1
+    too, so fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def emit(saved_fd, line):
+    os.write(saved_fd, (json.dumps(line) + "\n").encode())
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -59,7 +88,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -232,16 +261,30 @@ def run_ours(args):
                                "accounting": "SURVEY 8(d): (2S+16) B per particle-step + (2S+36) B per particle per resample"},
         "kernel_ms_profile_pass": kernel_ms, "kernel_share_propagate": ms_prop / total_kernel_ms if total_kernel_ms else None,
     }
+    tr = ncu_traffic()
+    if tr and args.dtype == "f64" and args.log2n == 24:
+        n_l = max(1, n_plain + n_gather)
+        line["roofline"]["traffic"] = (n_plain * tr["propagate_plain_bytes"] + n_gather * tr["propagate_gather_bytes"]) / n_l
+        line["roofline"]["traffic_source"] = tr.get("source")
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(1, args.cpu_log2n, T, ys)
-    print(json.dumps(line))
+    emit(args.out_fd, line)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def kalman(ys):
-    from oracle import closed_forms as cf
-    return cf.kalman_log_ml(ys, *LG)
+    """Exact log p(y_1:T) of the linear-Gaussian model (Kalman recursion): the external truth of log_ml."""
+    m0, s0, a, b, q, c, r = LG
+    m, P, ll = m0, s0 * s0, 0.0
+    for t, y in enumerate(ys):
+        if t > 0:
+            m, P = a * m + b, a * a * P + q * q
+        S = c * c * P + r * r
+        ll += -0.5 * (y - c * m) ** 2 / S - 0.5 * math.log(2 * math.pi * S)
+        K = c * P / S
+        m, P = m + K * (y - c * m), (1.0 - K * c) * P
+    return ll
 
 
 def oracle_run(orc, N, T, ys, threads):
@@ -294,7 +337,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "log_ml": lml, "log_ml_kalman": kalman(ys)}
-    print(json.dumps(line))
+    emit(args.out_fd, line)
 
 
 def main():
@@ -311,6 +354,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.out_fd = claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -162,7 +162,9 @@ struct gsmc_filter {
   uint64_t* cc = nullptr;     // residual: segment-local inclusive counts of deterministic copies
   uint64_t* seg_a = nullptr;  // u64[n_segs+1] segment totals / exclusive prefixes of the weights (inside the cdf allocation: peers read it)
   uint64_t* seg_b = nullptr;  // u64[n_segs+1] residual scheme: segment prefixes of the residual fractions
-  uint64_t* seg_e = nullptr;  // u64[n_segs+1] segment totals / exclusive prefixes of the spacings
+  uint64_t* seg_e = nullptr;  // u64[n_segs+1] exclusive prefixes of the spacings
+  uint64_t* raw0 = nullptr;   // u64[n_segs] raw segment totals written by the streaming passes (weights; residual: copies)
+  uint64_t* raw1 = nullptr;   // u64[n_segs] raw segment totals (spacings; residual: fractions)
   uint64_t* tile_e = nullptr; // u64[nt] segment-local exclusive prefix of the spacings at every tile
   uint32_t* esp = nullptr;    // u32[n_pad] exponential spacings of this rank's thresholds
   int seg_tiles = 1, n_segs = 0;  // tiles per segment (= per block of the streaming pass), segments per rank
@@ -288,7 +290,7 @@ static int alloc_buffers(gsmc_filter* f) {
   f->flag_mod = f->cfg.keep_history ? f->cap + 2 : 4;
   f->bytes_state = (size_t)f->cap * f->D * f->n_pad * rs; f->bytes_anc = (size_t)f->cap * f->n_pad * sizeof(uint32_t);
   // segments: one per block of the streaming pass, 4 resident blocks per SM -> one wave
-  const int max_segs = f->sm_count * 4 < GSMC_MAX_SEGS ? f->sm_count * 4 : GSMC_MAX_SEGS;
+  const int max_segs = f->sm_count * 4 < GSMC_MAX_SEGS - 1 ? f->sm_count * 4 : GSMC_MAX_SEGS - 1;   // n_segs + 1 <= 1024 threads
   f->seg_tiles = (f->n_tiles + max_segs - 1) / max_segs;
   f->n_segs = (f->n_tiles + f->seg_tiles - 1) / f->seg_tiles;
   const size_t seg_words = GSMC_MAX_SEGS + 16;
@@ -301,6 +303,8 @@ static int alloc_buffers(gsmc_filter* f) {
   f->seg_a = f->cdf + f->n_pad;
   CK(pool_alloc(f->device, (void**)&f->seg_b, seg_words * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->seg_e, seg_words * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->raw0, seg_words * sizeof(uint64_t)));
+  CK(pool_alloc(f->device, (void**)&f->raw1, seg_words * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->esp, f->n_pad * sizeof(uint32_t)));
   CK(pool_alloc(f->device, (void**)&f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t)));
@@ -332,13 +336,14 @@ static void free_buffers(gsmc_filter* f) {
   pool_free(f->device, f->lw, f->bytes_lw); pool_free(f->device, f->cdf, f->bytes_cdf); pool_free(f->device, f->cc, f->n_pad * sizeof(uint64_t));
   const size_t seg_words = GSMC_MAX_SEGS + 16;
   pool_free(f->device, f->seg_b, seg_words * sizeof(uint64_t)); pool_free(f->device, f->seg_e, seg_words * sizeof(uint64_t));
+  pool_free(f->device, f->raw0, seg_words * sizeof(uint64_t)); pool_free(f->device, f->raw1, seg_words * sizeof(uint64_t));
   pool_free(f->device, f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t));
   pool_free(f->device, f->esp, f->n_pad * sizeof(uint32_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
   pool_free(f->device, f->partials, (size_t)f->n_tiles * sizeof(LseTriple)); pool_free(f->device, f->ds, sizeof(DevScalars));
   pool_free(f->device, f->resampled, (size_t)f->flag_mod * sizeof(int));
   pinned_free(f->h_ds);
   f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
-  f->seg_a = f->seg_b = f->seg_e = f->tile_e = nullptr; f->esp = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
+  f->seg_a = f->seg_b = f->seg_e = f->tile_e = f->raw0 = f->raw1 = nullptr; f->esp = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
   f->resampled = nullptr;
 }
 static int ensure_f64(gsmc_filter* f, size_t n) {
@@ -510,29 +515,31 @@ static int tile_grid(const gsmc_filter* f, const void* fn) {
   return f->n_tiles < g ? f->n_tiles : g;
 }
 
-// One-block scan of the segment totals + exchange of this rank's totals + the event's totals (see kernels.cuh).
-static int launch_scan(gsmc_filter* f, int cls, uint64_t* a0, uint64_t* a1, int what, int conditional) {
+// One-block scan of the raw segment totals in0/in1 into the prefix arrays out0/out1 + exchange of this rank's
+// totals + the event's totals (see kernels.cuh).
+static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint64_t* in1, uint64_t* out0, uint64_t* out1, int what, int conditional) {
   PeerScalars peers;
   for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
   const bool multi = f->nranks > 1;
   const bool fused = multi && !f->use_nccl_scalars;
   if (fused) f->xchg_seq += 1;
   { ProfScope ps(f, cls);
-    scan_segments_kernel<<<1, 1024, 0, f->stream>>>(a0, a1, f->n_segs, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
+    scan_segments_kernel<<<1, 1024, 0, f->stream>>>(in0, in1, out0, out1, f->n_segs, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
                                                     peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0); }
   CK(cudaGetLastError());
   if (multi && !fused) {
     if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
     if (what & SCAN_E) NK(g_nccl.AllGather((const char*)(f->ds->spacing_rank_total + f->rank), f->ds->spacing_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
     ProfScope ps(f, KC_OTHER);
-    totals_kernel<<<1, 1024, 0, f->stream>>>(a0, a1, f->n_segs, f->ds, f->nranks, f->rank, f->cfg.seed, (uint64_t)f->N, what, conditional);
+    totals_kernel<<<1, 1024, 0, f->stream>>>(out0, out1, f->n_segs, f->ds, f->nranks, f->rank, f->cfg.seed, (uint64_t)f->N, what, conditional);
     CK(cudaGetLastError());
   }
   return GSMC_OK;
 }
 
 // maybe_resample! (particle_filter.jl:199-200) on the device: integer CDF, sorted uniforms, ancestors.
-//   multinomial, Philox draws:  weights+spacings pass -> scan -> partition -> search          (4 launches)
+//   multinomial, Philox draws, 1 GPU:  weights+spacings pass -> partition (with the scan fused) -> search   (3 launches)
+//   multinomial, Philox draws, R GPUs: weights+spacings pass -> scan + exchange -> partition -> search
 //   exported uniforms (replay): weights pass -> scan -> iid search
 //   residual: + the copy counts / residual fractions pass and the deterministic copies
 template <typename Real>
@@ -545,25 +552,26 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
   const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
   const bool fuse_spacings = !residual && !replay_iid;
+  const bool fuse_scan = fuse_spacings && f->nranks == 1;       // the partition kernel scans the segment totals itself
   // 1. integer weights -> segment-local CDF + segment totals (and, fused, the spacings of the N draws)
   if (fuse_spacings) {
     ProfScope ps(f, KC_SCAN);
     weights_kernel<Real, true, true><<<ns, GSMC_BLOCK, 0, f->stream>>>(
-        lw, f->n, scale, f->ds, f->cdf, f->seg_a, f->cfg.seed, k_first, (uint64_t)f->N, f->esp, f->tile_e, f->seg_e, nt, st, conditional);
+        lw, f->n, scale, f->ds, f->cdf, f->raw0, f->cfg.seed, k_first, (uint64_t)f->N, f->esp, f->tile_e, f->raw1, nt, st, conditional);
   } else {
     ProfScope ps(f, KC_SCAN);
     weights_kernel<Real, true, false><<<ns, GSMC_BLOCK, 0, f->stream>>>(
-        lw, f->n, scale, f->ds, f->cdf, f->seg_a, 0, 0, 0, nullptr, nullptr, nullptr, nt, st, conditional);
+        lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, nt, st, conditional);
   }
   CK(cudaGetLastError());
   // 2. segment prefixes and the totals of the event
-  if (fuse_spacings) CKRC(launch_scan(f, KC_SCAN, f->seg_a, f->seg_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional));
-  else CKRC(launch_scan(f, KC_SCAN, f->seg_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional));
+  if (fuse_spacings) { if (!fuse_scan) CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional)); }
+  else CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional));
   if (residual) {
     { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
     { ProfScope ps(f, KC_SCAN);
-      resid_cdf_kernel<Real><<<ns, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->cc, f->seg_a, f->cdf, f->seg_b, nt, st, conditional); }
-    CKRC(launch_scan(f, KC_SCAN, f->seg_a, f->seg_b, SCAN_RESID, conditional));
+      resid_cdf_kernel<Real><<<ns, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->cc, f->raw0, f->cdf, f->raw1, nt, st, conditional); }
+    CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_b, SCAN_RESID, conditional));
     { ProfScope ps(f, KC_SEARCH);
       det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(
           f->cc, f->seg_a, ns, st * GSMC_TILE, (int)f->n_pad, f->n, f->ds, anc, conditional); }
@@ -582,13 +590,18 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
       // the number of draws M is only known now: spacings of the M thresholds
       { ProfScope ps(f, KC_SPACINGS);
         weights_kernel<Real, false, true><<<ns, GSMC_BLOCK, 0, f->stream>>>(
-            lw, f->n, scale, f->ds, nullptr, nullptr, f->cfg.seed, k_first, 0, f->esp, f->tile_e, f->seg_e, nt, st, conditional); }
-      CKRC(launch_scan(f, KC_SPACINGS, f->seg_e, nullptr, SCAN_E, conditional));
+            lw, f->n, scale, f->ds, nullptr, nullptr, f->cfg.seed, k_first, 0, f->esp, f->tile_e, f->raw1, nt, st, conditional); }
+      CKRC(launch_scan(f, KC_SPACINGS, f->raw1, nullptr, f->seg_e, nullptr, SCAN_E, conditional));
     }
     // 3. ancestors
+    uint64_t* sp_q = residual ? f->seg_b : f->seg_a;
     { ProfScope ps(f, KC_SEARCH);
-      partition_kernel<<<(nt + GSMC_BLOCK - 1) / GSMC_BLOCK, GSMC_BLOCK, 0, f->stream>>>(
-          v, f->cfg.seed, k_first, f->rank, f->ds, f->seg_e, f->tile_e, st, f->esp, nt, f->win, conditional); }
+      const int need = (nt + 1 + 31) / 32;
+      const int grid = need < 2 * f->sm_count ? need : 2 * f->sm_count;      // one wave of 1024-thread blocks
+      if (fuse_scan) partition_kernel<true><<<grid, 1024, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
+                                                                          f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional);
+      else partition_kernel<false><<<grid, 1024, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, nullptr, nullptr, sp_q, f->seg_e,
+                                                                 f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional); }
     { static bool attr_set = false;
       if (!attr_set) { CK(cudaFuncSetAttribute((const void*)search_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMC_SEARCH_SMEM)); attr_set = true; }
       int occ = 0;
@@ -973,10 +986,10 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
     const double scale = weight_scale(f);
     { ProfScope ps(f, KC_SCAN);
       if (f->f32) weights_kernel<float, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
-          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->seg_a, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0);
+          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0);
       else weights_kernel<double, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
-          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->seg_a, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
-    CKRC(launch_scan(f, KC_SCAN, f->seg_a, nullptr, SCAN_Q, 0));
+          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
+    CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q, 0));
   }
   CK(cudaGetLastError());
   const double* urep = nullptr;

@@ -293,6 +293,71 @@ GM_HD double gm_log_tab(double x, const double* tab) {
   return fma(ef, GM_LN2_HI, fma(ef, GM_LN2_LO, fma(p, r, tab[2 * idx + 1])));
 }
 
+// ------------------------------------------------------------------------------------------------
+// gm_log_unit: table-driven log for x in (0, 1) with full double precision in absolute terms
+// (|error| < 3e-16 * max(1, |log x|)); the result is clamped to <= 0. x = 2^e m; the top 6 mantissa bits
+// pick a centre c_i = 1 + (i + 1/2)/64 from a 64-entry table {fl(1/c_i), -log(fl(1/c_i))};
+// r = m fl(1/c_i) - 1 with |r| <= 2^-7 and log1p(r) by a 7-term series (truncation 2e-18). No division and
+// no compare/select on the mantissa: about half the instructions of gm_log. Used for the radius of the
+// Box-Muller transform, sqrt(-2 log u1): close to u1 = 1 the RELATIVE error of the log grows (the absolute
+// error does not), which moves a normal that is itself < 1e-7 by < 1e-8.
+// ------------------------------------------------------------------------------------------------
+#define GM_LOGTAB64_VALUES { \
+  0.99224806201550386, 0.0077821404420549628, 0.97709923664122134, 0.023167059281534418, \
+  0.96240601503759393, 0.038318864302136657, 0.94814814814814818, 0.053244514518812243, \
+  0.93430656934306566, 0.067950661908507778, 0.92086330935251803, 0.082443669211074544, \
+  0.90780141843971629, 0.096729626458551141, 0.8951048951048951, 0.11081436634029011, \
+  0.88275862068965516, 0.12470347850095725, 0.87074829931972786, 0.13840232285911919, \
+  0.85906040268456374, 0.151916042025842, 0.84768211920529801, 0.16524957289530717, \
+  0.83660130718954251, 0.17840765747281825, 0.82580645161290323, 0.19139485299962947, \
+  0.8152866242038217, 0.20421554142869083, 0.80503144654088055, 0.2168739383006143, \
+  0.79503105590062106, 0.2293741010648459, 0.78527607361963192, 0.24171993688714513, \
+  0.77575757575757576, 0.25391520998096345, 0.76646706586826352, 0.26596354849713788, \
+  0.75739644970414199, 0.27786845100345631, 0.74853801169590639, 0.28963329258304271, \
+  0.73988439306358378, 0.30126133057816185, 0.73142857142857143, 0.3127557100038969, \
+  0.7231638418079096, 0.32411946865421198, 0.71508379888268159, 0.33535554192113781, \
+  0.70718232044198892, 0.34646676734620863, 0.69945355191256831, 0.3574558889218038, \
+  0.69189189189189193, 0.36832556115870757, 0.68449197860962563, 0.3790783529349695, \
+  0.67724867724867721, 0.38971675114002524, 0.67015706806282727, 0.40024316412701266, \
+  0.66321243523316065, 0.41065992498526832, 0.65641025641025641, 0.42096929464412963, \
+  0.64974619289340096, 0.43117346481837143, 0.64321608040201006, 0.4412745608048752, \
+  0.63681592039800994, 0.45127464413945861, 0.63054187192118227, 0.46117571512217015, \
+  0.62439024390243902, 0.47097971521879101, 0.61835748792270528, 0.48068852934575196, \
+  0.61244019138755978, 0.49030398804519387, 0.60663507109004744, 0.49982786955644926, \
+  0.60093896713615025, 0.5092619017898079, 0.59534883720930232, 0.51860776420804566, \
+  0.58986175115207373, 0.52786708962084239, 0.58447488584474883, 0.53704146589688373, \
+  0.579185520361991, 0.54613243759813557, 0.57399103139013452, 0.55514150754050162, \
+  0.56888888888888889, 0.56407013828480301, 0.56387665198237891, 0.57291975356178537, \
+  0.55895196506550215, 0.58169173963462251, 0.55411255411255411, 0.59038744660217635, \
+  0.54935622317596566, 0.59900818964608338, 0.5446808510638298, 0.60755525022454182, \
+  0.54008438818565396, 0.61602987721551405, 0.53556485355648531, 0.62443328801189357, \
+  0.53112033195020747, 0.63276666957103778, 0.52674897119341568, 0.64103117942093124, \
+  0.52244897959183678, 0.64922794662510974, 0.51821862348178138, 0.65735807270836, \
+  0.51405622489959835, 0.66542263254509049, 0.50996015936254979, 0.6734226752121667, \
+  0.50592885375494068, 0.68135922480790312, 0.50196078431372548, 0.689233281238809 }
+static const double gm_logtab64_h[128] = GM_LOGTAB64_VALUES;
+#if defined(__CUDACC__)
+static __constant__ double gm_logtab64_d[128] = GM_LOGTAB64_VALUES;
+#endif
+// tab: the 128-entry table (shared-memory copy on the device: lanes index it divergently)
+GM_HD double gm_log_unit(double x, const double* tab) {
+  const uint64_t b = gm_to_bits(x);
+  const int e = (int)(b >> 52) - 1023;
+  const int idx = (int)((b >> 46) & 63);
+  const double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+  const double r = fma(m, tab[2 * idx], -1.0);
+  double p = 1.4285714285714285e-01;                 /* 1/7 */
+  p = fma(p, r, -1.6666666666666666e-01);
+  p = fma(p, r, 2.0000000000000001e-01);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 3.3333333333333331e-01);
+  p = fma(p, r, -0.5);
+  p = fma(p, r, 1.0);
+  const double ef = (double)e;
+  const double l = fma(ef, GM_LN2_HI, fma(ef, GM_LN2_LO, fma(p, r, tab[2 * idx + 1])));
+  return l > 0.0 ? 0.0 : l;
+}
+
 #if defined(__cplusplus)
 // ------------------------------------------------------------------------------------------------
 // Batch forms: K independent evaluations with the coefficient loop outside and the element loop
@@ -369,6 +434,29 @@ template <int K> GM_HD void gm_log_tab_v(const double* x, const double* tab, dou
   GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -0.5);
   GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], 1.0);
   GM_UNROLL for (int k = 0; k < K; ++k) out[k] = fma(ef[k], GM_LN2_HI, fma(ef[k], GM_LN2_LO, fma(p[k], r[k], c[k])));
+}
+
+template <int K> GM_HD void gm_log_unit_v(const double* x, const double* tab, double* out) {
+  double r[K], p[K], c[K], ef[K];
+  GM_UNROLL for (int k = 0; k < K; ++k) {
+    const uint64_t b = gm_to_bits(x[k]);
+    const int idx = (int)((b >> 46) & 63);
+    const double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    ef[k] = (double)((int)(b >> 52) - 1023);
+    r[k] = fma(m, tab[2 * idx], -1.0);
+    c[k] = tab[2 * idx + 1];
+    p[k] = 1.4285714285714285e-01;
+  }
+  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -1.6666666666666666e-01);
+  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], 2.0000000000000001e-01);
+  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -0.25);
+  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], 3.3333333333333331e-01);
+  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -0.5);
+  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], 1.0);
+  GM_UNROLL for (int k = 0; k < K; ++k) {
+    const double l = fma(ef[k], GM_LN2_HI, fma(ef[k], GM_LN2_LO, fma(p[k], r[k], c[k])));
+    out[k] = l > 0.0 ? 0.0 : l;
+  }
 }
 
 template <int K> GM_HD void gm_sincospi_v(const double* t, double* sn, double* cs) {

@@ -10,7 +10,7 @@
 //   call c of (seed, t, stream)    = Philox(ctr = {lo32(c), hi32(c), t, stream}, key = {lo32(seed), hi32(seed)})
 //   word a = out0 | out1<<32, word b = out2 | out3<<32
 //   normals  (stream 0): element e -> call e>>1; Box-Muller u1=((a>>11)+.5)2^-53, u2=(b>>11)2^-53,
-//                        r=sqrt(-2 log u1); e even -> r cos(2 pi u2), e odd -> r sin(2 pi u2)
+//                        r=sqrt(-2 gm_log_unit(u1)); e even -> r cos(2 pi u2), e odd -> r sin(2 pi u2)
 //   uniforms (stream 1,3): element e -> call e>>1; (e odd ? b : a)>>11 * 2^-53   in [0,1)
 //   spacings (stream 2): element e -> call e>>2, 32-bit word e&3 (out0..out3); u = (w+.5)2^-32;
 //                        floor(-gm_log_tab(u) * 2^27)   (fixed-point Exp(1) variate; < 2^32 because
@@ -44,11 +44,11 @@ __host__ __device__ __forceinline__ PhiloxOut philox_call(uint64_t seed, uint64_
 }
 
 // two standard normals from one call
-__host__ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t call, uint32_t t, double* z0, double* z1) {
+__host__ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t call, uint32_t t, const double* ltab, double* z0, double* z1) {
   const PhiloxOut o = philox_call(seed, call, t, GSMC_STREAM_NORMAL);
   const double u1 = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
   const double u2 = (double)(o.b >> 11) * 0x1p-53;
-  const double r = sqrt(-2.0 * gm_log_pos(u1));   // u1 in (0,1): no special cases
+  const double r = sqrt(-2.0 * gm_log_unit(u1, ltab));   // u1 in (0,1): log <= 0
   double s, c;
   gm_sincospi(2.0 * u2, &s, &c);
   *z0 = r * c;
@@ -86,7 +86,7 @@ __host__ __device__ __forceinline__ uint64_t spacing_one(uint64_t seed, uint64_t
 // Batch forms (same bits as the scalar functions, see gsmc_math.h "Batch forms").
 // K Philox calls -> 2K standard normals z[2m] (cos branch), z[2m+1] (sin branch)
 template <int K>
-__host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uint64_t* calls, uint32_t t, double* z) {
+__host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uint64_t* calls, uint32_t t, const double* ltab, double* z) {
   double u1[K], t2[K], l[K], sn[K], cs[K];
 #pragma unroll
   for (int m = 0; m < K; ++m) {
@@ -95,7 +95,7 @@ __host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uin
     const double u2 = (double)(o.b >> 11) * 0x1p-53;
     t2[m] = 2.0 * u2;
   }
-  gm_log_pos_v<K>(u1, l);
+  gm_log_unit_v<K>(u1, ltab, l);
   gm_sincospi_v<K>(t2, sn, cs);
 #pragma unroll
   for (int m = 0; m < K; ++m) {

@@ -191,7 +191,7 @@ template <class Model> struct PropTile {
 };
 
 template <class Model, typename Real, bool INIT, int PROP>
-__global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
+__global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
   typedef typename Vec2T<Real>::type Real2;
   constexpr int D = Model::D;
   constexpr int PAIRS = PropTile<Model>::PAIRS, NP = 2 * PAIRS;
@@ -199,10 +199,10 @@ __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Re
   constexpr int NZA = NZ > 0 ? NZ : 1, NUA = NU > 0 ? NU : 1;
   extern __shared__ double dyn_sm[];
   __shared__ double red[3 * (GSMC_BLOCK / 32)];
-  if (Model::SMEM_DOUBLES > 0) {
-    Model::template prologue<INIT, PROP>(a, dyn_sm);
-    __syncthreads();
-  }
+  __shared__ double ltab[128];                       // table of gm_log_unit (Box-Muller radius)
+  if (NZ > 0 && threadIdx.x < 128) ltab[threadIdx.x] = gm_logtab64_d[threadIdx.x];
+  if (Model::SMEM_DOUBLES > 0) Model::template prologue<INIT, PROP>(a, dyn_sm);
+  if (NZ > 0 || Model::SMEM_DOUBLES > 0) __syncthreads();
   const bool gather = !INIT && g.use_anc && (*g.resampled_flag != 0);
   const int64_t tile0 = (int64_t)blockIdx.x * PropTile<Model>::TILE + 2 * threadIdx.x;
 
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK) propagate_kernel(const PropArgs<Re
 #pragma unroll
         for (int m = 0; m < NZ; ++m) calls[u * NZ + m] = c0 + m;
       }
-      normal_pairs_v<PAIRS * NZA>(g.seed, calls, g.t, &zz[0][0]);
+      normal_pairs_v<PAIRS * NZA>(g.seed, calls, g.t, ltab, &zz[0][0]);
     }
   }
   if (NU > 0) {
@@ -600,11 +600,47 @@ __device__ __forceinline__ void globalise_prefixes(uint64_t* a0, uint64_t* a1, i
   }
 }
 
-// One block: exclusive scans (in place) of up to two arrays of n_segs segment totals (n_segs <= 1024),
-// a[n_segs] = total; then this rank's totals go to ds, are exchanged with the peers (fused LL exchange over
-// NVLink) and finish_totals runs. With exchange == 0 on a multi-rank run the host performs the
-// allgathers and launches totals_kernel.
-__global__ void __launch_bounds__(1024) scan_segments_kernel(uint64_t* a0, uint64_t* a1, int n_segs, DevScalars* ds, int what,
+// Block-wide exclusive scans of up to two arrays of n_segs <= 1024 segment totals (one element per thread
+// of a 1024-thread block): out0/out1[i] = exclusive prefix, out[n_segs] = total. out may be shared or global.
+__device__ __forceinline__ void scan_segments_block(const uint64_t* in0, const uint64_t* in1, int n_segs, uint64_t* out0, uint64_t* out1,
+                                                    uint64_t (*sm)[33], uint64_t totals[2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = threadIdx.x;
+  uint64_t v[2], x[2];
+#pragma unroll
+  for (int arr = 0; arr < 2; ++arr) {
+    const uint64_t* a = arr ? in1 : in0;
+    v[arr] = (a && i < n_segs) ? a[i] : 0;
+    x[arr] = v[arr];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x[arr], d); if (lane >= d) x[arr] += y; }
+    if (lane == 31) sm[arr][warp] = x[arr];
+  }
+  __syncthreads();
+  if (warp < 2) {
+    uint64_t w = sm[warp][lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
+    sm[warp][lane] = w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int arr = 0; arr < 2; ++arr) {
+    uint64_t* o = arr ? out1 : out0;
+    totals[arr] = sm[arr][31];
+    if (!(arr ? in1 : in0) || !o) continue;
+    const uint64_t incl = x[arr] + (warp ? sm[arr][warp - 1] : 0);
+    if (i < n_segs) o[i] = incl - v[arr];
+    if (i == 0) o[n_segs] = totals[arr];
+  }
+}
+
+// One block: scans the raw segment totals in0/in1 into the prefix arrays out0/out1; then this rank's totals
+// go to ds, are exchanged with the peers (fused LL exchange over NVLink), finish_totals runs and the
+// prefixes are made global. With exchange == 0 on a multi-rank run the host performs the allgathers and
+// launches totals_kernel.
+__global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0, const uint64_t* in1, uint64_t* out0, uint64_t* out1,
+                                                             int n_segs, DevScalars* ds, int what,
                                                              uint64_t seed, uint64_t n_global, int conditional,
                                                              PeerScalars peers, int rank, int nranks, uint32_t seq, int exchange) {
   __shared__ uint64_t sm[2][33];
@@ -613,37 +649,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(uint64_t* a0, uint6
   const bool skip = conditional && !ds->do_resample;
   const int n64 = ((what & SCAN_Q) ? 1 : 0) + ((what & SCAN_E) ? 1 : 0);
   uint64_t totals[2] = {0, 0};
-  if (!skip) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = threadIdx.x;
-    uint64_t v[2], x[2];
-#pragma unroll
-    for (int arr = 0; arr < 2; ++arr) {
-      const uint64_t* a = arr ? a1 : a0;
-      v[arr] = (a && i < n_segs) ? a[i] : 0;
-      x[arr] = v[arr];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x[arr], d); if (lane >= d) x[arr] += y; }
-      if (lane == 31) sm[arr][warp] = x[arr];
-    }
-    __syncthreads();
-    if (warp < 2) {
-      uint64_t w = sm[warp][lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(w, d); if (lane >= d) w += y; }
-      sm[warp][lane] = w;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int arr = 0; arr < 2; ++arr) {
-      uint64_t* a = arr ? a1 : a0;
-      if (!a) continue;
-      const uint64_t incl = x[arr] + (warp ? sm[arr][warp - 1] : 0);
-      if (i < n_segs) a[i] = incl - v[arr];
-      totals[arr] = sm[arr][31];
-      if (i == 0) a[n_segs] = totals[arr];
-    }
-  }
+  if (!skip) scan_segments_block(in0, in1, n_segs, out0, out1, sm, totals);
   // this rank's totals: the weights' first when both are present
   if (threadIdx.x == 0) {
     int k = 0;
@@ -668,7 +674,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(uint64_t* a0, uint6
   if (threadIdx.x == 0 && !skip) finish_totals(ds, nranks, seed, n_global, what, totals[0], totals[1]);
   if (nranks > 1 && !skip) {
     __syncthreads();
-    globalise_prefixes(a0, a1, n_segs, ds, what, rank);
+    globalise_prefixes(out0, out1, n_segs, ds, what, rank);
   }
 }
 // multi-rank runs that exchange the totals with ncclAllGather (GSMC_NCCL_SCALARS=1) finish here
@@ -746,7 +752,7 @@ __device__ __forceinline__ int upper_pred(const uint64_t* arr, int len, uint64_t
   }
   return l;
 }
-// the same by a full warp: 32 probes per round trip (32-ary search)
+// the same by a full warp: 32 probes per round trip (32-ary search); arr may live in shared or global memory
 template <class P>
 __device__ __forceinline__ int upper_pred_warp(const uint64_t* arr, int len, uint64_t add, const P gt) {
   const int lane = threadIdx.x & 31;
@@ -754,7 +760,7 @@ __device__ __forceinline__ int upper_pred_warp(const uint64_t* arr, int len, uin
   while (hi > lo) {
     const int step = (hi - lo + 31) >> 5;
     const int p = lo + lane * step;
-    const bool pred = (p >= hi) || gt(add + __ldg(arr + p));
+    const bool pred = (p >= hi) || gt(add + arr[p]);
     const unsigned mask = __ballot_sync(0xffffffffu, pred);
     const int f = mask ? __ffs((int)mask) - 1 : 32;
     const int new_hi = (f == 32) ? hi : lo + f * step;
@@ -794,39 +800,82 @@ __device__ __forceinline__ double sorted_threshold(uint64_t S, double ratio, dou
   return t < tmax ? t : tmax;
 }
 
-// Sorted mode, step 1: ancestor word of the FIRST threshold of every tile (one thread per tile, all
-// binary searches in flight at once), win[b] for b in [0, nt]; win[nt] closes the last tile. Also turns
-// tile_e[b] into the GLOBAL spacing prefix before tile b (adds its segment's prefix).
-__global__ void __launch_bounds__(GSMC_BLOCK) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank,
-                                                               const DevScalars* ds, const uint64_t* seg_e, uint64_t* tile_e,
-                                                               int seg_tiles, const uint32_t* esp, int nt, uint32_t* win, int conditional) {
+// Sorted mode, step 1: ancestor word of the FIRST threshold of every tile, win[b] for b in [0, nt]; win[nt]
+// closes the last tile. One WARP per boundary (32-ary searches: 2 probe rounds over the segment prefixes
+// in shared memory, 3 over the segment in global/peer memory), 32 boundaries per 1024-thread block. Also
+// turns tile_e[b] into the GLOBAL spacing prefix before tile b.
+// FUSED_SCAN (single rank, multinomial): every block first scans the raw segment totals itself (identical
+// results in every block), which replaces the separate scan launch; block 0 publishes prefixes and totals.
+template <bool FUSED_SCAN>
+__global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank, DevScalars* ds,
+                                                         const uint64_t* raw_q, const uint64_t* raw_e, uint64_t* sp_q, uint64_t* sp_e,
+                                                         uint64_t* tile_e, int seg_tiles, const uint32_t* esp, int nt, uint32_t* win,
+                                                         uint64_t n_global, int conditional) {
+  __shared__ uint64_t spq[GSMC_MAX_SEGS + 1];
+  __shared__ uint64_t spe[GSMC_MAX_SEGS + 1];
+  __shared__ uint64_t sm[2][33];
+  __shared__ double s_thr[2];
+  __shared__ uint64_t s_draws;
   if (conditional && !ds->do_resample) return;
-  const uint64_t m_draws = ds->n_draws;
-  const uint32_t last = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
-  const double ratio = ds->thr_ratio, tmax = ds->thr_max;
-  // boundaries 0..nt-1: one thread each (their ancestors are almost always in the local segment)
-  for (int b = blockIdx.x * GSMC_BLOCK + threadIdx.x; b < nt; b += gridDim.x * GSMC_BLOCK) {
-    const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
-    const uint64_t S0 = seg_e[b / seg_tiles] + tile_e[b];
-    tile_e[b] = S0;
-    uint32_t w = last;
-    if (kt < m_draws) {
-      GtF64 gt; gt.t = sorted_threshold(S0 + (uint64_t)esp[(int64_t)b * GSMC_TILE], ratio, tmax);
-      w = search_global<false>(v, ds, gt);
+  const int n_segs = v.n_segs;
+  if (FUSED_SCAN) {
+    uint64_t totals[2];
+    scan_segments_block(raw_q, raw_e, n_segs, spq, spe, sm, totals);
+    if (threadIdx.x == 0) {
+      const uint64_t stot = totals[1] + spacing_one(seed, n_global, ds->rho, gm_logtab_d);
+      const double cn = (double)totals[0];
+      s_thr[0] = cn / (double)stot;
+      s_thr[1] = cn > 0.0 ? gm_from_bits(gm_to_bits(cn) - 1) : 0.0;
+      s_draws = n_global;
+      if (blockIdx.x == 0) {
+        ds->cdf_rank_total[0] = totals[0]; ds->spacing_rank_total[0] = totals[1];
+        ds->cdf_total = totals[0]; ds->n_draws = n_global; ds->n_det = 0;
+        ds->spacing_total = stot; ds->thr_ratio = s_thr[0]; ds->thr_max = s_thr[1];
+      }
     }
-    win[b] = w;
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x <= n_segs) { sp_q[threadIdx.x] = spq[threadIdx.x]; sp_e[threadIdx.x] = spe[threadIdx.x]; }
+  } else {
+    if (threadIdx.x <= n_segs) { spq[threadIdx.x] = sp_q[threadIdx.x]; spe[threadIdx.x] = sp_e[threadIdx.x]; }
+    if (threadIdx.x == 0) { s_thr[0] = ds->thr_ratio; s_thr[1] = ds->thr_max; s_draws = ds->n_draws; }
+    __syncthreads();
   }
-  // the closing boundary (first threshold of the next rank) lives in a peer's segment when there is one:
-  // searched by a whole warp, 32 probes per NVLink round trip
-  if (blockIdx.x == 0 && threadIdx.x < 32) {
-    const uint64_t kt = k_first + (uint64_t)nt * GSMC_TILE;
-    uint32_t w = last;
-    if (kt < m_draws) {
-      const uint64_t S = seg_e[v.n_segs] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
-      GtF64 gt; gt.t = sorted_threshold(S, ratio, tmax);
-      w = search_global<true>(v, ds, gt);
+  const int lane = threadIdx.x & 31;
+  const uint64_t m_draws = s_draws;
+  const double ratio = s_thr[0], tmax = s_thr[1];
+  for (int b = blockIdx.x * 32 + (threadIdx.x >> 5); b <= nt; b += gridDim.x * 32) {
+    const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
+    uint32_t w = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
+    uint64_t S;
+    if (b < nt) {
+      const uint64_t S0 = spe[b / seg_tiles] + tile_e[b];
+      __syncwarp();
+      if (lane == 0) tile_e[b] = S0;
+      S = S0 + (uint64_t)esp[(int64_t)b * GSMC_TILE];
+    } else {
+      // the closing boundary: first threshold of the next rank
+      S = spe[n_segs] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
     }
-    if (threadIdx.x == 0) win[nt] = w;
+    if (kt < m_draws) {
+      GtF64 gt; gt.t = sorted_threshold(S, ratio, tmax);
+      uint64_t end = 0;
+      int r = 0;
+      for (; r < v.nranks - 1; ++r) {
+        end += ds->cdf_rank_total[r];
+        if (gt(end)) break;
+      }
+      const uint64_t* sp = (r == rank) ? spq : v.sp[r];      // own prefixes from shared memory, a peer's over NVLink
+      const int sg = upper_pred_warp(sp + 1, n_segs, 0, gt);
+      int64_t j = v.n_per - 1;
+      if (sg < n_segs) {
+        const int64_t first = (int64_t)sg * v.seg_len;
+        const int len = (int)(first + v.seg_len <= v.n_pad ? v.seg_len : v.n_pad - first);
+        j = first + upper_pred_warp(v.seg[r] + first, len, sp[sg], gt);
+        if (j > v.n_per - 1) j = v.n_per - 1;
+      }
+      w = ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
+    }
+    if (lane == 0) win[b] = w;
   }
 }
 

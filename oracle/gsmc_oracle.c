@@ -47,6 +47,12 @@ void orc_sincospi(double t, double* s, double* c) { gm_sincospi(t, s, c); }
 /* checks of gsmc_math.h helpers the device uses (tests/test_math.py) */
 double orc_div_inv(double x, double c) { return gm_div_inv(x, c, gm_safe_recip(c)); }
 double orc_log_pos(double x) { return gm_log_pos(x); }
+/* log of a uniform in (0,1) for the Box-Muller radius: table-driven (gsmc_math.h), libm under -DORC_USE_LIBM */
+#ifdef ORC_USE_LIBM
+double orc_log_unit(double x) { return log(x); }
+#else
+double orc_log_unit(double x) { return gm_log_unit(x, gm_logtab64_h); }
+#endif
 double orc_exp_nonpos(double x) { return gm_exp_nonpos(x); }
 double orc_log_tab(double x) { return gm_log_tab(x, gm_logtab_h); }
 /* muldiv_floor vs unsigned __int128 division */
@@ -122,7 +128,7 @@ static void philox_pair(uint64_t seed, uint64_t call, uint32_t t, uint32_t strea
 static void box_muller(uint64_t a, uint64_t b, double* z0, double* z1) {
   const double u1 = ((double)(a >> 11) + 0.5) * 0x1p-53;   /* (0,1) */
   const double u2 = (double)(b >> 11) * 0x1p-53;           /* [0,1) */
-  const double r = sqrt(-2.0 * orc_log(u1));
+  const double r = sqrt(-2.0 * orc_log_unit(u1));
   double s, c;
   orc_sincospi(2.0 * u2, &s, &c);
   *z0 = r * c;

@@ -61,6 +61,7 @@ double orc_div_inv(double x, double c);
 double orc_log_pos(double x);
 double orc_exp_nonpos(double x);
 double orc_log_tab(double x);
+double orc_log_unit(double x);   /* gm_log_unit: log of a uniform in (0,1), Box-Muller radius */
 int64_t orc_muldiv_mismatches(uint64_t seed, int64_t n);
 int64_t orc_div_inv_mismatches(uint64_t seed, int64_t n);
 double orc_exp(double x);

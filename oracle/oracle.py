@@ -52,6 +52,8 @@ class Oracle:
         L.orc_log_pos.argtypes = [C.c_double]
         L.orc_exp_nonpos.restype = L.orc_log_tab.restype = C.c_double
         L.orc_exp_nonpos.argtypes = L.orc_log_tab.argtypes = [C.c_double]
+        L.orc_log_unit.restype = C.c_double
+        L.orc_log_unit.argtypes = [C.c_double]
         L.orc_muldiv_mismatches.restype = C.c_int64
         L.orc_muldiv_mismatches.argtypes = [C.c_uint64, C.c_int64]
         L.orc_div_inv_mismatches.restype = C.c_int64

@@ -84,3 +84,20 @@ def test_table_log_of_the_spacings(orc):
     for w in ws:
         u = (float(w) + 0.5) * 2.0 ** -32
         assert abs(orc.L.orc_log_tab(u) - math.log(u)) < 2e-12
+
+
+def test_table_log_of_the_box_muller_radius(orc):
+    """gm_log_unit on 53-bit uniforms in (0,1): absolute error at the level of one ulp of max(1, |log u|),
+    result never positive (the radius sqrt(-2 log u) is always defined)."""
+    rng = np.random.default_rng(6)
+    us = np.concatenate([
+        (rng.integers(0, 2 ** 53, 60000).astype(np.float64) + 0.5) * 2.0 ** -53,
+        [0.5 * 2.0 ** -53, 1.5 * 2.0 ** -53, 1.0 - 2.0 ** -54, 1.0 - 3 * 2.0 ** -54, 0.5, 0.25, 0.75, 2.0 ** -30],
+        1.0 - (rng.integers(0, 2 ** 20, 2000).astype(np.float64) + 0.5) * 2.0 ** -53,    # next to 1
+        (rng.integers(0, 2 ** 20, 2000).astype(np.float64) + 0.5) * 2.0 ** -53])          # next to 0
+    worst = 0.0
+    for u in us:
+        got, ref = orc.L.orc_log_unit(float(u)), math.log(float(u))
+        assert got <= 0.0
+        worst = max(worst, abs(got - ref) / max(1.0, abs(ref)))
+    assert worst < 4e-16, worst
