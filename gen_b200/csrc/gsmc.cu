@@ -123,6 +123,21 @@ static void pool_free(int device, void* p, size_t bytes) {
   cudaFree(p);
 }
 
+// Peer mappings of IPC handles are cached for the life of the process (or until gsmc_trim): the slabs come
+// from the pool above, so consecutive filters export the same allocations, and re-opening a multi-GB
+// mapping costs tens of milliseconds per peer.
+struct IpcKey { int device; char h[sizeof(cudaIpcMemHandle_t)]; bool operator<(const IpcKey& o) const { return device != o.device ? device < o.device : memcmp(h, o.h, sizeof h) < 0; } };
+static std::map<IpcKey, void*> g_ipc_cache;
+static cudaError_t ipc_open_cached(int device, const cudaIpcMemHandle_t& handle, void** p) {
+  IpcKey k; k.device = device; memcpy(k.h, &handle, sizeof k.h);
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_ipc_cache.find(k);
+  if (it != g_ipc_cache.end()) { *p = it->second; return cudaSuccess; }
+  cudaError_t e = cudaIpcOpenMemHandle(p, handle, cudaIpcMemLazyEnablePeerAccess);
+  if (e == cudaSuccess) g_ipc_cache[k] = *p;
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the filter object
 // ------------------------------------------------------------------------------------------------
@@ -326,10 +341,7 @@ static int alloc_buffers(gsmc_filter* f) {
 static void free_buffers(gsmc_filter* f) {
   for (int r = 0; r < f->nranks; ++r) {
     if (r == f->rank) continue;
-    if (f->peer_slab[r]) cudaIpcCloseMemHandle((void*)f->peer_slab[r]);
-    if (f->peer_anc[r]) cudaIpcCloseMemHandle((void*)f->peer_anc[r]);
-    if (f->peer_cdf[r]) cudaIpcCloseMemHandle((void*)f->peer_cdf[r]);
-    if (f->peer_ds[r]) cudaIpcCloseMemHandle((void*)f->peer_ds[r]);
+    // peer mappings stay open in g_ipc_cache
     f->peer_slab[r] = nullptr; f->peer_anc[r] = nullptr; f->peer_cdf[r] = nullptr; f->peer_ds[r] = nullptr;
   }
   pool_free(f->device, f->state_slab, f->bytes_state); pool_free(f->device, f->anc_slab, f->bytes_anc);
@@ -753,20 +765,20 @@ GSMC_API int gsmc_comm_attach(gsmc_handle f, gsmc_comm c) {
   CK(cudaIpcGetMemHandle(&mine.cdf, f->cdf));
   CK(cudaIpcGetMemHandle(&mine.ds, f->ds));
   Handles* d_all = nullptr;
-  CK(cudaMalloc(&d_all, sizeof(Handles) * nranks));
+  CK(pool_alloc(f->device, (void**)&d_all, sizeof(Handles) * GSMC_MAX_RANKS));
   CK(cudaMemcpyAsync(d_all + rank, &mine, sizeof mine, cudaMemcpyHostToDevice, f->stream));
   NK(g_nccl.AllGather(d_all + rank, d_all, sizeof(Handles), NCCL_UINT8, f->comm, f->stream));
   std::vector<Handles> all(nranks);
   CK(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * nranks, cudaMemcpyDeviceToHost, f->stream));
   CK(cudaStreamSynchronize(f->stream));
-  cudaFree(d_all);
+  pool_free(f->device, d_all, sizeof(Handles) * GSMC_MAX_RANKS);
   for (int r = 0; r < nranks; ++r) {
     if (r == rank) continue;
     void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
-    CK(cudaIpcOpenMemHandle(&p0, all[r].slab, cudaIpcMemLazyEnablePeerAccess));
-    CK(cudaIpcOpenMemHandle(&p1, all[r].anc, cudaIpcMemLazyEnablePeerAccess));
-    CK(cudaIpcOpenMemHandle(&p2, all[r].cdf, cudaIpcMemLazyEnablePeerAccess));
-    CK(cudaIpcOpenMemHandle(&p3, all[r].ds, cudaIpcMemLazyEnablePeerAccess));
+    CK(ipc_open_cached(f->device, all[r].slab, &p0));
+    CK(ipc_open_cached(f->device, all[r].anc, &p1));
+    CK(ipc_open_cached(f->device, all[r].cdf, &p2));
+    CK(ipc_open_cached(f->device, all[r].ds, &p3));
     f->peer_slab[r] = p0; f->peer_anc[r] = (const uint32_t*)p1; f->peer_cdf[r] = (const uint64_t*)p2; f->peer_ds[r] = (DevScalars*)p3;
   }
   return GSMC_OK;
@@ -1066,6 +1078,8 @@ GSMC_API int gsmc_trim(void) {
   g_pool.clear();
   for (DevScalars* p : g_pinned_pool) cudaFreeHost(p);
   g_pinned_pool.clear();
+  for (auto& kv : g_ipc_cache) { cudaSetDevice(kv.first.device); cudaIpcCloseMemHandle(kv.second); }
+  g_ipc_cache.clear();
   cudaSetDevice(dev);
   return GSMC_OK;
 }
