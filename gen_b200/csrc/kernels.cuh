@@ -879,6 +879,12 @@ __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t see
   }
 }
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 // Sorted mode, step 2. One block iteration handles a SUPERTILE of 2048 consecutive thresholds (8 per thread)
 // and writes their ancestors anc_k = min{i : (double)C_i > t_k}. The CDF window [win[2m], win[2m+2]] the
 // supertile can map to is staged in shared memory as doubles (+inf sentinel at the end); every thread finds
@@ -886,15 +892,16 @@ __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t see
 // walks to the next seven (sorted thresholds: ~1 slot apart).
 #define GSMC_SEARCH_TPT 8                                   // thresholds per thread
 #define GSMC_SUPERTILE (GSMC_BLOCK * GSMC_SEARCH_TPT)       // 2048
-#define GSMC_WIN_CAP 6144
+#define GSMC_WIN_CAP 5120                                   // 40 KB of window per block: 5 blocks per SM
 #define GSMC_SEARCH_SMEM ((GSMC_WIN_CAP + 1) * 8)
-__global__ void __launch_bounds__(GSMC_BLOCK, 4) search_sorted_kernel(CdfView v, uint64_t k_first, const DevScalars* ds,
+__global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v, uint64_t k_first, const DevScalars* ds,
                                                                       const uint64_t* tile_e, uint32_t seg_tiles, uint32_t seg_magic,
                                                                       const uint32_t* esp, const uint32_t* win, uint32_t* anc,
                                                                       int64_t n_out, int nt, int det_offset, int conditional) {
   extern __shared__ double cwin[];                        // GSMC_WIN_CAP + 1 doubles
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
   if (conditional && !ds->do_resample) return;
+  const uint32_t cwin_base = (uint32_t)__cvta_generic_to_shared(cwin);
   const uint64_t m_draws = ds->n_draws;
   const double ratio = ds->thr_ratio, tmax = ds->thr_max;
   const int n_super = nt / (GSMC_SUPERTILE / GSMC_TILE);
@@ -949,17 +956,20 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 4) search_sorted_kernel(CdfView v,
     for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { S += e[j]; t[j] = sorted_threshold(S, ratio, tmax); }
     if (staged) {
       // pos = #{p : cwin[p] <= t[0]}: every probe is in bounds and the probe count depends on len only
-      int pos = 0;
+      // (32-bit shared-memory addresses: one add per step instead of a 64-bit generic pointer)
+      uint32_t ad = cwin_base;
       for (int rem = len; rem > 1;) {
         const int half = rem >> 1;
-        if (cwin[pos + half - 1] <= t[0]) pos += half;
+        if (lds_f64(ad + (uint32_t)(half - 1) * 8u) <= t[0]) ad += (uint32_t)half * 8u;
         rem -= half;
       }
-      if (cwin[pos] <= t[0]) ++pos;
+      double c = lds_f64(ad);
+      if (c <= t[0]) { ad += 8u; c = lds_f64(ad); }
 #pragma unroll
       for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
-        if (j > 0) { while (cwin[pos] <= t[j]) ++pos; }
-        const int pc = pos < len ? pos : len - 1;
+        if (j > 0) { while (c <= t[j]) { ad += 8u; c = lds_f64(ad); } }
+        const int pj = (int)((ad - cwin_base) >> 3);
+        const int pc = pj < len ? pj : len - 1;
         a[j] = pc < la ? (w0 + (uint32_t)pc) : ((((uint32_t)r1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pc - la));
       }
     } else {
