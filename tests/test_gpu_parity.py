@@ -112,6 +112,32 @@ def test_multinomial_resample_sorted_ancestors_bit_exact(gpu, orc, N):
     assert same_bits(st.state(), pf.state())
 
 
+@pytest.mark.parametrize("N,y0", [(300_000, 8.0), (1_300_001, 3.0), (1_300_001, 9.0), (2_500_000, 25.0)])
+@pytest.mark.parametrize("scheme", ["multinomial", "residual"])
+def test_resample_skewed_weights_and_segments(gpu, orc, N, y0, scheme):
+    """Sizes with several tiles per CDF segment (N > 592 * 1024) and observations far in the tail: a few
+    particles carry all the weight, most integer weights are 0, so the search windows range from one entry
+    to far beyond the shared-memory window (global-search fallback). Ancestors stay bit-exact."""
+    g = gpu
+    model, params, ys = make_model(g, O.LGSSM)
+    st = g.ParticleFilterState(model, N, seed=11, resample=scheme)
+    pf = orc.particle_filter(O.LGSSM, params, N, seed=11)
+    st.init([y0])
+    pf.init([y0])
+    assert st.maybe_resample(N) is True
+    assert pf.maybe_resample(N, scheme=O.RESIDUAL if scheme == "residual" else O.MULTINOMIAL) is True
+    anc_g, anc_o = st.ancestors(), pf.parents()
+    assert np.array_equal(anc_g, anc_o)
+    if scheme == "multinomial":
+        assert np.all(np.diff(anc_g) >= 0)
+    st.step([ys[1]])
+    pf.step([ys[1]])
+    assert same_bits(st.log_weights(), pf.log_weights())
+    assert same_bits(st.state(), pf.state())
+    assert st.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    st.close()
+
+
 @pytest.mark.parametrize("scheme", ["multinomial", "residual"])
 def test_resample_with_exported_uniforms(gpu, orc, scheme):
     """north_star protocol: fed exported iid uniforms (one per output slot), ancestor indices match bit-exact."""
