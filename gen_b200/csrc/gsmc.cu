@@ -331,7 +331,10 @@ static int alloc_buffers(gsmc_filter* f) {
   CK(cudaMemsetAsync(f->resampled, 0, (size_t)f->flag_mod * sizeof(int), f->stream));
   // pad lanes of the log-weight column are read by vector loads: keep them finite and harmless
   CK(cudaMemsetAsync(f->lw, 0, f->n_pad * rs, f->stream));
-  // state / ancestor slabs are written before they are read (pad lanes are masked), so they are not cleared
+  // state slabs are written before they are read, so they are not cleared; the pad words of the ancestor columns
+  // are read (and used as indices) by the gathering propagate and never written by the search: zero them
+  if (f->n_pad > f->n)
+    CK(cudaMemset2DAsync(f->anc_slab + f->n, f->n_pad * sizeof(uint32_t), 0, (size_t)(f->n_pad - f->n) * sizeof(uint32_t), (size_t)f->cap, f->stream));
   f->peer_slab[f->rank] = f->state_slab;
   f->peer_anc[f->rank] = f->anc_slab;
   f->peer_cdf[f->rank] = f->cdf;
@@ -383,6 +386,7 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   g.anc = anc_col(f, f->anc_slab, new_step);
   g.resampled_flag = f->resampled + (new_step % f->flag_mod);
   g.partials = f->partials;
+  g.ds = f->ds; g.nranks = f->nranks;
   g.n = f->n; g.stride = f->n_pad; g.first_global = (uint64_t)f->first; g.seed = f->cfg.seed;
   g.t = (uint32_t)new_step;
   g.use_anc = use_anc ? 1 : 0;
@@ -396,7 +400,14 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   if (!nz) g.zrep = nullptr;
   {
     ProfScope ps(f, (use_anc && f->pending) ? KC_PROPAGATE_GATHER : KC_PROPAGATE);
-    f->n_partials = (int)(f->n_pad / PropTile<Model>::TILE);
+    // persistent grid: as many blocks as are resident at once (occupancy of this instantiation), at most one per tile
+    static int occ = 0;
+    if (occ == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)propagate_kernel<Model, Real, INIT, PROP>, GSMC_BLOCK,
+                                                        Model::SMEM_DOUBLES * sizeof(double)) != cudaSuccess || occ < 1) occ = 2;
+    }
+    g.n_tiles = (int)(f->n_pad / PropTile<Model>::TILE);
+    f->n_partials = g.n_tiles < f->sm_count * occ ? g.n_tiles : f->sm_count * occ;
     propagate_kernel<Model, Real, INIT, PROP><<<f->n_partials, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream>>>(g, a);
   }
   CK(cudaGetLastError());
@@ -471,8 +482,10 @@ static int launch_finalize(gsmc_filter* f, double ess_threshold) {
   if (fused) f->xchg_seq += 1;
   {
     ProfScope ps(f, KC_FINALIZE);
-    finalize_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_partials, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag,
-                                               peers, f->xchg_seq, fused);
+#if !GSMC_LASTBLOCK
+    reduce_partials_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_partials, f->ds, f->rank);
+#endif
+    finalize_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, peers, f->xchg_seq, fused);
   }
   CK(cudaGetLastError());
   if (f->nranks > 1 && !fused) {

@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#include "gsmc_tables.h"
 
 #if defined(__CUDACC__)
 #define GM_HD __host__ __device__ __forceinline__
@@ -33,19 +34,16 @@
 // Polynomial coefficients live in __constant__ memory on the device so that DFMA takes them as
 // constant-bank operands (as 64-bit immediates they cost two UMOV issue slots each, 16% of the
 // propagate kernel's instructions in the first profile) and in a static table on the host.
-#define GM_EXP_COEFFS { 1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, \
-  2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, \
-  4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0 }
+#define GM_EXP_COEFFS { 8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5 }   /* 1/5! .. 1/2! */
 #define GM_LOG_COEFFS { 4.7619047619047616e-02, 5.2631578947368418e-02, 5.8823529411764705e-02, 6.6666666666666666e-02, \
   7.6923076923076927e-02, 9.0909090909090912e-02, 1.1111111111111110e-01, 1.4285714285714285e-01, 2.0000000000000001e-01, \
   3.3333333333333331e-01 }
-#define GM_SIN_COEFFS { -8.2206352466243295e-18, 2.8114572543455206e-15, -7.6471637318198164e-13, 1.6059043836821613e-10, \
-  -2.5052108385441720e-08, 2.7557319223985893e-06, -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01 }
-#define GM_COS_COEFFS { -1.5619206968586225e-16, 4.7794773323873853e-14, -1.1470745597729725e-11, 2.0876756987868100e-09, \
-  -2.7557319223985888e-07, 2.4801587301587302e-05, -1.3888888888888889e-03, 4.1666666666666664e-02, -0.5 }
+#define GM_SIN_COEFFS { -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01 }   /* -1/7!, 1/5!, -1/3! */
+#define GM_COS_COEFFS { -1.3888888888888889e-03, 4.1666666666666664e-02, -0.5 }                       /* -1/6!, 1/4!, -1/2! */
 #define GM_ATAN_COEFFS { -6.6666666666666666e-02, 7.6923076923076927e-02, -9.0909090909090912e-02, 1.1111111111111110e-01, \
   -1.4285714285714285e-01, 2.0000000000000001e-01, -3.3333333333333331e-01 }
-#define GM_MISC_CONSTS { 1.44269504088896338700e+00, 6.93147180369123816490e-01, 1.90821492927058770002e-10 }
+#define GM_MISC_CONSTS { 1.44269504088896338700e+00, 6.93147180369123816490e-01, 1.90821492927058770002e-10, \
+  GM_EXP_INV_L, GM_EXP_L_HI, GM_EXP_L_LO }
 static const double gm_exp_h[] = GM_EXP_COEFFS;
 static const double gm_log_h[] = GM_LOG_COEFFS;
 static const double gm_sin_h[] = GM_SIN_COEFFS;
@@ -68,6 +66,26 @@ static __constant__ double gm_misc_d[] = GM_MISC_CONSTS;
 #define GM_INV_LN2 GM_C(misc, 0)
 #define GM_LN2_HI GM_C(misc, 1)
 #define GM_LN2_LO GM_C(misc, 2)
+#define GM_INV_L64 GM_C(misc, 3)
+#define GM_L64_HI GM_C(misc, 4)
+#define GM_L64_LO GM_C(misc, 5)
+
+// Lookup tables (gsmc_tables.h): 2^(j/64) and (sin, cos)(pi j/64). Lanes index them divergently, so on the
+// device the default copies live in global memory (L1/L2-cached) and the hot kernels stage them in shared
+// memory and pass that pointer to the batch forms.
+static const double gm_exp2tab_h[64] = GM_EXP2TAB_VALUES;
+static const double gm_sincostab_h[256] = GM_SINCOSTAB_VALUES;
+#if defined(__CUDACC__)
+static __device__ const double gm_exp2tab_g[64] = GM_EXP2TAB_VALUES;
+static __device__ const double gm_sincostab_g[256] = GM_SINCOSTAB_VALUES;
+#endif
+#if defined(__CUDA_ARCH__)
+#define GM_EXP2TAB gm_exp2tab_g
+#define GM_SINCOSTAB gm_sincostab_g
+#else
+#define GM_EXP2TAB gm_exp2tab_h
+#define GM_SINCOSTAB gm_sincostab_h
+#endif
 
 GM_HD double gm_from_bits(uint64_t b) {
 #if defined(__CUDA_ARCH__)
@@ -87,21 +105,32 @@ GM_HD double gm_inf(void) { return gm_from_bits(GM_INF_BITS); }
 GM_HD double gm_nan(void) { return gm_from_bits(0x7ff8000000000000ULL); }
 GM_HD double gm_pow2(int k) { return gm_from_bits((uint64_t)(k + 1023) << 52); }  /* -1022<=k<=1023 */
 
-// exp(x). Results below the smallest normal are flushed to 0 (x < -708.39) so no
-// denormal arithmetic is ever involved. 13th-order Taylor on |r| <= ln2/2.
+// exp(x) = 2^k 2^(j/64) e^r with x = (64 k + j) ln2/64 + r, |r| <= ln2/128: table value T_j times a
+// 5th-order Taylor polynomial, p = T + T (r + r^2 (1/2 + r (1/6 + r (1/24 + r/120)))) (truncation 3.5e-17,
+// total error < 1.3 ulp). Results below the smallest normal are flushed to 0 (x < -708.39) so no denormal
+// arithmetic is ever involved.
+// gm_exp_core: reduced evaluation shared by all variants; returns p in [0.99, 2) and the binary exponent k.
+GM_HD double gm_exp_core(double x, const double* tab, long long* k) {
+  const double kf = floor(x * GM_INV_L64 + 0.5);
+  double r = fma(-kf, GM_L64_HI, x);                    /* exact: L64_HI has 34 significant bits */
+  r = fma(-kf, GM_L64_LO, r);
+  double p = GM_C(exp, 0);
+  p = fma(p, r, GM_C(exp, 1));
+  p = fma(p, r, GM_C(exp, 2));
+  p = fma(p, r, GM_C(exp, 3));
+  const double q = fma(r * r, p, r);
+  const long long n = (long long)kf;
+  const double t = tab[(int)(n & 63)];
+  *k = n >> 6;
+  return fma(t, q, t);
+}
 GM_HD double gm_exp(double x) {
   if (x != x) return x;
   if (x > 709.782712893383973096) return gm_inf();
   if (x < -708.3964185322641) return 0.0;
-  const double kf = floor(x * GM_INV_LN2 + 0.5);
-  double r = fma(-kf, GM_LN2_HI, x);                    /* ln2 hi (fdlibm split) */
-  r = fma(-kf, GM_LN2_LO, r);                           /* ln2 lo */
-  double p = GM_C(exp, 0);                              /* 1/13! ... 1/2!, 1, 1 */
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 1; i < 14; ++i) p = fma(p, r, GM_C(exp, i));
-  const int k = (int)kf;
+  long long kk;
+  const double p = gm_exp_core(x, GM_EXP2TAB, &kk);
+  const int k = (int)kk;
   const int k1 = k / 2, k2 = k - k1;
   return (p * gm_pow2(k1)) * gm_pow2(k2);
 }
@@ -109,20 +138,14 @@ GM_HD double gm_exp(double x) {
 // Same bits as gm_exp(x) for x <= 0 (finite or -inf); no overflow/NaN branches and the 2^k scaling
 // is one integer add on the exponent field (the result is normal or flushed to 0, never subnormal).
 // Used for exp(lw - max): logsumexp partials and the integer weights of the resampler.
-GM_HD double gm_exp_nonpos(double x) {
+GM_HD double gm_exp_nonpos_t(double x, const double* tab) {
   const double xc = x < -708.3964185322641 ? -708.0 : x;
-  const double kf = floor(xc * GM_INV_LN2 + 0.5);
-  double r = fma(-kf, GM_LN2_HI, xc);
-  r = fma(-kf, GM_LN2_LO, r);
-  double p = GM_C(exp, 0);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 1; i < 14; ++i) p = fma(p, r, GM_C(exp, i));
-  const long long k = (long long)kf;
+  long long k;
+  const double p = gm_exp_core(xc, tab, &k);
   const double v = gm_from_bits(gm_to_bits(p) + ((uint64_t)k << 52));
   return x < -708.3964185322641 ? 0.0 : v;
 }
+GM_HD double gm_exp_nonpos(double x) { return gm_exp_nonpos_t(x, GM_EXP2TAB); }
 
 // log(x). x = 2^e * m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = (m-1)/(m+1).
 // gm_log_core: x positive, finite and normal (no checks); e0 = exponent bias already applied.
@@ -177,35 +200,30 @@ GM_HD double gm_safe_recip(double c) {       /* rc for gm_div_inv; 0 = "use true
   return (ac > 1e-150 && ac < 1e150) ? 1.0 / c : 0.0;
 }
 
-// sin(pi*t), cos(pi*t) for finite t. Range reduction is exact; kernels are Taylor
-// polynomials on |pi*r| <= pi/4.
-GM_HD void gm_sincospi(double t, double* sn, double* cs) {
-  const double nf = floor(t + t + 0.5);
-  const double r = fma(nf, -0.5, t);         /* exact: |r| <= 1/4 */
+// sin(pi*t), cos(pi*t) for finite t: t = j/64 + r (exact, |r| <= 1/128), table (S, C) = (sin, cos)(pi j/64)
+// with j taken mod 128, short Taylor kernels in x = pi r (|x| <= 0.0246: truncation < 4e-18) and the angle
+// addition written around the table value so that its rounding is the dominant error (<= 1 ulp of 1):
+//   sin = S + (S (cos x - 1) + C sin x),  cos = C + (C (cos x - 1) - S sin x).
+// No quadrant logic; exact at the multiples of 1/2 (the table holds exact 0 and +-1 there).
+GM_HD void gm_sincospi_t(double t, const double* tab, double* sn, double* cs) {
+  const double nf = floor(t * 64.0 + 0.5);
+  const double r = fma(nf, -0.015625, t);    /* exact */
   const double x = r * GM_PI;
   const double z = x * x;
-  double ps = GM_C(sin, 0);                  /* -1/19!, 1/17!, ..., -1/3! */
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 1; i < 9; ++i) ps = fma(ps, z, GM_C(sin, i));
-  const double s0 = fma(x * z, ps, x);
-  double pc = GM_C(cos, 0);                  /* -1/18!, 1/16!, ..., -1/2! */
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 1; i < 9; ++i) pc = fma(pc, z, GM_C(cos, i));
-  const double c0 = fma(z, pc, 1.0);
-  const long long n = (long long)nf;
-  const int q = (int)(n & 3);
-  // q=0: (s0, c0)  q=1: (c0, -s0)  q=2: (-s0, -c0)  q=3: (-c0, s0) -- selects, no divergent branches
-  const int swap = (q & 1) != 0;
-  double so = swap ? c0 : s0;
-  double co = swap ? s0 : c0;
-  so = (q & 2) ? -so : so;
-  co = ((q + 1) & 2) ? -co : co;
-  *sn = so; *cs = co;
+  double ps = GM_C(sin, 0);
+  ps = fma(ps, z, GM_C(sin, 1));
+  ps = fma(ps, z, GM_C(sin, 2));
+  const double sx = fma(x * z, ps, x);       /* sin x */
+  double pc = GM_C(cos, 0);
+  pc = fma(pc, z, GM_C(cos, 1));
+  pc = fma(pc, z, GM_C(cos, 2));
+  const double cm = z * pc;                  /* cos x - 1 */
+  const int j = (int)((long long)nf & 127);
+  const double S = tab[2 * j], C = tab[2 * j + 1];
+  *sn = S + fma(S, cm, C * sx);
+  *cs = C + fma(C, cm, -(S * sx));
 }
+GM_HD void gm_sincospi(double t, double* sn, double* cs) { gm_sincospi_t(t, GM_SINCOSTAB, sn, cs); }
 
 // atan(x) for any finite x and atan2(y, x). Reduction: |x|>1 -> pi/2 - atan(1/|x|);
 // then t in [0,1] is shifted by the nearest of atan(k/8), k=0..8, via
@@ -274,6 +292,7 @@ GM_HD double gm_atan2(double y, double x) {
 static const double gm_logtab_h[32] = GM_LOGTAB_VALUES;
 #if defined(__CUDACC__)
 static __constant__ double gm_logtab_d[32] = GM_LOGTAB_VALUES;
+static __device__ const double gm_logtab_g[32] = GM_LOGTAB_VALUES;      /* global-memory copy: coalesced staging into shared memory */
 #endif
 // tab: the 32-entry table (shared-memory copy on the device when lanes index it divergently)
 GM_HD double gm_log_tab(double x, const double* tab) {
@@ -338,6 +357,7 @@ GM_HD double gm_log_tab(double x, const double* tab) {
 static const double gm_logtab64_h[128] = GM_LOGTAB64_VALUES;
 #if defined(__CUDACC__)
 static __constant__ double gm_logtab64_d[128] = GM_LOGTAB64_VALUES;
+static __device__ const double gm_logtab64_g[128] = GM_LOGTAB64_VALUES;
 #endif
 // tab: the 128-entry table (shared-memory copy on the device: lanes index it divergently)
 GM_HD double gm_log_unit(double x, const double* tab) {
@@ -371,22 +391,24 @@ GM_HD double gm_log_unit(double x, const double* tab) {
 #define GM_UNROLL
 #endif
 
-template <int K> GM_HD void gm_exp_nonpos_v(const double* x, double* out) {
+template <int K> GM_HD void gm_exp_nonpos_v(const double* x, double* out, const double* tab) {
   double xc[K], kf[K], r[K], p[K];
   GM_UNROLL for (int k = 0; k < K; ++k) {
     xc[k] = x[k] < -708.3964185322641 ? -708.0 : x[k];
-    kf[k] = floor(xc[k] * GM_INV_LN2 + 0.5);
-    r[k] = fma(-kf[k], GM_LN2_HI, xc[k]);
-    r[k] = fma(-kf[k], GM_LN2_LO, r[k]);
+    kf[k] = floor(xc[k] * GM_INV_L64 + 0.5);
+    r[k] = fma(-kf[k], GM_L64_HI, xc[k]);
+    r[k] = fma(-kf[k], GM_L64_LO, r[k]);
     p[k] = GM_C(exp, 0);
   }
-  GM_UNROLL for (int i = 1; i < 14; ++i) {
+  GM_UNROLL for (int i = 1; i < 4; ++i) {
     const double c = GM_C(exp, i);
     GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], c);
   }
   GM_UNROLL for (int k = 0; k < K; ++k) {
-    const long long kk = (long long)kf[k];
-    const double v = gm_from_bits(gm_to_bits(p[k]) + ((uint64_t)kk << 52));
+    const double q = fma(r[k] * r[k], p[k], r[k]);
+    const long long n = (long long)kf[k];
+    const double t = tab[(int)(n & 63)];
+    const double v = gm_from_bits(gm_to_bits(fma(t, q, t)) + ((uint64_t)(n >> 6) << 52));
     out[k] = x[k] < -708.3964185322641 ? 0.0 : v;
   }
 }
@@ -459,30 +481,27 @@ template <int K> GM_HD void gm_log_unit_v(const double* x, const double* tab, do
   }
 }
 
-template <int K> GM_HD void gm_sincospi_v(const double* t, double* sn, double* cs) {
+template <int K> GM_HD void gm_sincospi_v(const double* t, double* sn, double* cs, const double* tab) {
   double nf[K], x[K], z[K], ps[K], pc[K];
   GM_UNROLL for (int k = 0; k < K; ++k) {
-    nf[k] = floor(t[k] + t[k] + 0.5);
-    const double r = fma(nf[k], -0.5, t[k]);
+    nf[k] = floor(t[k] * 64.0 + 0.5);
+    const double r = fma(nf[k], -0.015625, t[k]);
     x[k] = r * GM_PI;
     z[k] = x[k] * x[k];
     ps[k] = GM_C(sin, 0);
     pc[k] = GM_C(cos, 0);
   }
-  GM_UNROLL for (int i = 1; i < 9; ++i) {
+  GM_UNROLL for (int i = 1; i < 3; ++i) {
     const double a = GM_C(sin, i), b = GM_C(cos, i);
     GM_UNROLL for (int k = 0; k < K; ++k) { ps[k] = fma(ps[k], z[k], a); pc[k] = fma(pc[k], z[k], b); }
   }
   GM_UNROLL for (int k = 0; k < K; ++k) {
-    const double s0 = fma(x[k] * z[k], ps[k], x[k]);
-    const double c0 = fma(z[k], pc[k], 1.0);
-    const int q = (int)((long long)nf[k] & 3);
-    const int swap = (q & 1) != 0;
-    double so = swap ? c0 : s0;
-    double co = swap ? s0 : c0;
-    so = (q & 2) ? -so : so;
-    co = ((q + 1) & 2) ? -co : co;
-    sn[k] = so; cs[k] = co;
+    const double sx = fma(x[k] * z[k], ps[k], x[k]);
+    const double cm = z[k] * pc[k];
+    const int j = (int)((long long)nf[k] & 127);
+    const double S = tab[2 * j], C = tab[2 * j + 1];
+    sn[k] = S + fma(S, cm, C * sx);
+    cs[k] = C + fma(C, cm, -(S * sx));
   }
 }
 #endif  /* __cplusplus */

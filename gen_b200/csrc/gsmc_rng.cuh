@@ -86,7 +86,7 @@ __host__ __device__ __forceinline__ uint64_t spacing_one(uint64_t seed, uint64_t
 // Batch forms (same bits as the scalar functions, see gsmc_math.h "Batch forms").
 // K Philox calls -> 2K standard normals z[2m] (cos branch), z[2m+1] (sin branch)
 template <int K>
-__host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uint64_t* calls, uint32_t t, const double* ltab, double* z) {
+__host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uint64_t* calls, uint32_t t, const double* ltab, const double* sctab, double* z) {
   double u1[K], t2[K], l[K], sn[K], cs[K];
 #pragma unroll
   for (int m = 0; m < K; ++m) {
@@ -96,7 +96,7 @@ __host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uin
     t2[m] = 2.0 * u2;
   }
   gm_log_unit_v<K>(u1, ltab, l);
-  gm_sincospi_v<K>(t2, sn, cs);
+  gm_sincospi_v<K>(t2, sn, cs, sctab);
 #pragma unroll
   for (int m = 0; m < K; ++m) {
     const double r = sqrt(-2.0 * l[m]);

@@ -25,6 +25,9 @@
 #include "models.cuh"
 
 #define GSMC_BLOCK 256
+#ifndef GSMC_LASTBLOCK
+#define GSMC_LASTBLOCK 1
+#endif
 #define GSMC_TILE 1024            // particles (or thresholds) per block of the scan / search kernels
 #define GSMC_TILE_SHIFT 10
 #define GSMC_PAD 2048             // local columns are padded to this many particles
@@ -43,6 +46,8 @@ struct DevScalars {
   int error;                // sticky: 1 = total weight zero / not finite at a resample
   uint32_t n_resamples;     // resampling events so far
   uint32_t rho;             // Philox event index of the resample being executed
+  unsigned int blocks_done; // propagate: blocks that have published their logsumexp partial (the last one reduces them)
+  unsigned int pad0_;
   uint64_t cdf_total;       // C_N over all ranks
   uint64_t spacing_total;   // S_tot = sum of the M+1 spacings
   uint64_t n_det;           // residual scheme: number of deterministic copies
@@ -162,6 +167,21 @@ __device__ __forceinline__ bool mul_gt(uint64_t a, uint64_t b, uint64_t chi, uin
   return hi > chi || (hi == chi && lo > clo);
 }
 
+// Shared-memory copies of the lookup tables of gsmc_math.h (lanes index them divergently), staged with
+// coalesced loads from their global-memory copies.
+struct __align__(16) SmemTabs {
+  double sincos[256];   // (sin, cos)(pi j/64)
+  double log64[128];    // gm_log_unit
+  double exp2[64];      // 2^(j/64)
+};
+__device__ __forceinline__ void load_tabs(SmemTabs& t, bool normals) {
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) t.exp2[i] = gm_exp2tab_g[i];
+  if (normals) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) t.log64[i] = gm_logtab64_g[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) t.sincos[i] = gm_sincostab_g[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // propagate: init / step, fused with the ancestor gather and the logsumexp/ESS block partials
 // ------------------------------------------------------------------------------------------------
@@ -173,6 +193,9 @@ struct PropArgs {
   const uint32_t* anc;               // ancestor words of the pending resample
   const int* resampled_flag;         // device flag: was a resample decided for this step?
   LseTriple* partials;               // one per block
+  DevScalars* ds;                    // the last block to finish leaves this rank's (max, s1, s2) in ds->triples[rank]
+  int nranks;
+  int n_tiles;                       // tiles of PropTile<Model>::TILE particles (the grid is persistent)
   int64_t n;                         // local particle count
   int64_t stride;                    // column stride (padded n)
   uint64_t first_global;             // global index of local particle 0
@@ -190,43 +213,106 @@ template <class Model> struct PropTile {
   static constexpr int TILE = 2 * GSMC_BLOCK * PAIRS;
 };
 
+// merge of two (max, s1, s2) triples; NaN sums propagate, empty triples (max = -inf) drop out
+__device__ __forceinline__ LseTriple lse_merge_t(LseTriple a, LseTriple b, const double* etab) {
+  if (!(b.m > -gm_inf()) && b.s1 == b.s1) return a;
+  if (!(a.m > -gm_inf()) && a.s1 == a.s1) return b;
+  LseTriple r;
+  r.m = fmax(a.m, b.m);
+  const double ea = gm_exp_nonpos_t(a.m - r.m, etab), eb = gm_exp_nonpos_t(b.m - r.m, etab);
+  r.s1 = a.s1 * ea + b.s1 * eb;
+  r.s2 = a.s2 * (ea * ea) + b.s2 * (eb * eb);
+  return r;
+}
+
+// This rank's (max, s1, s2) from the block partials: the global max first, then the rescaled sums with one exp
+// per partial, in a fixed summation order (deterministic). Called by every thread of ONE block (any size up to
+// 1024); the result is valid in thread 0. sm: 96 doubles. The partials were written by other blocks: L2 loads.
+__device__ __forceinline__ LseTriple reduce_partials(const LseTriple* partials, int nblk, double* sm, const double* etab) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+  double m = -gm_inf();
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) m = fmax(m, __ldcg(&partials[b].m));
+  m = warp_max(m);
+  __syncthreads();
+  if (lane == 0) sm[warp] = m;
+  __syncthreads();
+  double M = sm[0];
+  for (int w = 1; w < nw; ++w) M = fmax(M, sm[w]);
+  double a1 = 0.0, a2 = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    const double pm = __ldcg(&partials[b].m), p1 = __ldcg(&partials[b].s1), p2 = __ldcg(&partials[b].s2);
+    const double e = (M > -gm_inf()) ? gm_exp_nonpos_t(pm - M, etab) : 1.0;
+    a1 += p1 * e;
+    a2 += p2 * (e * e);
+  }
+  a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) { sm[32 + warp] = a1; sm[64 + warp] = a2; }
+  __syncthreads();
+  LseTriple tr; tr.m = M; tr.s1 = 0.0; tr.s2 = 0.0;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < nw; ++w) { tr.s1 += sm[32 + w]; tr.s2 += sm[64 + w]; }
+  }
+  return tr;
+}
+
 template <class Model, typename Real, bool INIT, int PROP>
 __global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
   typedef typename Vec2T<Real>::type Real2;
   constexpr int D = Model::D;
-  constexpr int PAIRS = PropTile<Model>::PAIRS, NP = 2 * PAIRS;
+  constexpr int PAIRS = PropTile<Model>::PAIRS, NP = 2 * PAIRS, TILE = PropTile<Model>::TILE;
   constexpr int NZ = Model::nz(INIT, PROP), NU = Model::nu(INIT, PROP);
   constexpr int NZA = NZ > 0 ? NZ : 1, NUA = NU > 0 ? NU : 1;
   extern __shared__ double dyn_sm[];
-  __shared__ double red[3 * (GSMC_BLOCK / 32)];
-  __shared__ double ltab[128];                       // table of gm_log_unit (Box-Muller radius)
-  if (NZ > 0 && threadIdx.x < 128) ltab[threadIdx.x] = gm_logtab64_d[threadIdx.x];
+  __shared__ double red[96];
+  __shared__ SmemTabs tabs;
+  __shared__ int s_last;
+  load_tabs(tabs, NZ > 0);
   if (Model::SMEM_DOUBLES > 0) Model::template prologue<INIT, PROP>(a, dyn_sm);
-  if (NZ > 0 || Model::SMEM_DOUBLES > 0) __syncthreads();
+  __syncthreads();
   const bool gather = !INIT && g.use_anc && (*g.resampled_flag != 0);
-  const int64_t tile0 = (int64_t)blockIdx.x * PropTile<Model>::TILE + 2 * threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Persistent blocks: block b handles tiles b, b + gridDim.x, ...; thread 0 carries the block's running
+  // (max, s1, s2) over its tiles, so one partial, one fence and one atomic per BLOCK (not per tile) are left.
+  LseTriple run; run.m = -gm_inf(); run.s1 = 0.0; run.s2 = 0.0;
+  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+  const int64_t tile0 = (int64_t)tile * TILE + 2 * threadIdx.x;
+  // Only the last tile can hold pad lanes (the columns are padded to the tile): they are loaded, computed and
+  // stored like real particles (harmless garbage; the pad words of the ancestor columns are zero) and only
+  // masked out of the logsumexp partial. `lim` = real particles of this tile, block-uniform.
+  const int64_t lim64 = g.n - (int64_t)tile * TILE;
+  const int lim = lim64 < TILE ? (int)lim64 : TILE;
 
-  // The columns are padded to the tile, so the pad lanes of the last tile are loaded, computed and
-  // stored like real particles (harmless garbage) and only masked out of the logsumexp partial.
   // Stage A: previous state and log weights of all pairs (all loads in flight together).
   double prev[NP][D], lwv[NP];
   if (!INIT) {
     if (gather) {
+      uint2 aw[PAIRS];
 #pragma unroll
-      for (int u = 0; u < PAIRS; ++u) {
-        const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
-        uint2 aw = *reinterpret_cast<const uint2*>(g.anc + i);
-        if (i >= g.n) aw.x = 0;                       // ancestor words of pad lanes are not initialised
-        if (i + 1 >= g.n) aw.y = 0;
-        const Real* c0 = g.cur[aw.x >> GSMC_ANC_RANK_SHIFT] + (aw.x & GSMC_ANC_INDEX_MASK);
-        const Real* c1 = g.cur[aw.y >> GSMC_ANC_RANK_SHIFT] + (aw.y & GSMC_ANC_INDEX_MASK);
+      for (int u = 0; u < PAIRS; ++u) aw[u] = *reinterpret_cast<const uint2*>(g.anc + tile0 + (int64_t)u * 2 * GSMC_BLOCK);
+      if (g.nranks == 1) {
+        const Real* cur = g.cur[0];
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          prev[2 * u][d] = (double)__ldg(c0 + d * g.stride);
-          prev[2 * u + 1][d] = (double)__ldg(c1 + d * g.stride);
+        for (int u = 0; u < PAIRS; ++u) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            prev[2 * u][d] = (double)__ldg(cur + d * g.stride + aw[u].x);
+            prev[2 * u + 1][d] = (double)__ldg(cur + d * g.stride + aw[u].y);
+          }
         }
-        lwv[2 * u] = 0.0; lwv[2 * u + 1] = 0.0;       // log_weights[i] = 0. after a resample (:204)
+      } else {
+#pragma unroll
+        for (int u = 0; u < PAIRS; ++u) {
+          const Real* c0 = g.cur[aw[u].x >> GSMC_ANC_RANK_SHIFT] + (aw[u].x & GSMC_ANC_INDEX_MASK);
+          const Real* c1 = g.cur[aw[u].y >> GSMC_ANC_RANK_SHIFT] + (aw[u].y & GSMC_ANC_INDEX_MASK);
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            prev[2 * u][d] = (double)__ldg(c0 + d * g.stride);
+            prev[2 * u + 1][d] = (double)__ldg(c1 + d * g.stride);
+          }
+        }
       }
+#pragma unroll
+      for (int j = 0; j < NP; ++j) lwv[j] = 0.0;      // log_weights[i] = 0. after a resample (:204)
     } else {
       const Real* cur = g.cur[g.rank];
 #pragma unroll
@@ -262,7 +348,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs
 #pragma unroll
         for (int m = 0; m < NZ; ++m) calls[u * NZ + m] = c0 + m;
       }
-      normal_pairs_v<PAIRS * NZA>(g.seed, calls, g.t, ltab, &zz[0][0]);
+      normal_pairs_v<PAIRS * NZA>(g.seed, calls, g.t, tabs.log64, tabs.sincos, &zz[0][0]);
     }
   }
   if (NU > 0) {
@@ -296,12 +382,18 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs
     }
     Real2 l; l.x = r0; l.y = r1;
     *reinterpret_cast<Real2*>(g.lw + i) = l;
-    lwv[2 * u] = (i < g.n) ? (double)r0 : -gm_inf();          // pad lanes drop out of the reduction
-    lwv[2 * u + 1] = (i + 1 < g.n) ? (double)r1 : -gm_inf();
+    lwv[2 * u] = (double)r0; lwv[2 * u + 1] = (double)r1;
+  }
+  if (lim < TILE) {                                            // last tile only: pad lanes drop out of the reduction
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const int o = 2 * (int)threadIdx.x + u * 2 * GSMC_BLOCK;
+      if (o >= lim) lwv[2 * u] = -gm_inf();
+      if (o + 1 >= lim) lwv[2 * u + 1] = -gm_inf();
+    }
   }
 
   // Stage E: block partial of (max, sum exp(lw-max), sum exp(2(lw-max))); NaN log weights poison s1/s2 on purpose.
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double m = -gm_inf();
   bool any_nan = false;
 #pragma unroll
@@ -317,25 +409,52 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs
     double x[NP], e[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) x[j] = lwv[j] - bm;           // -inf for pad lanes -> exp = 0
-    gm_exp_nonpos_v<NP>(x, e);
+    gm_exp_nonpos_v<NP>(x, e, tabs.exp2);
 #pragma unroll
     for (int j = 0; j < NP; ++j) { s1 += e[j]; s2 += e[j] * e[j]; }
   }
   if (any_nan) { s1 = gm_nan(); s2 = gm_nan(); }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
-  if (lane == 0) { red[GSMC_BLOCK / 32 + warp] = s1; red[2 * (GSMC_BLOCK / 32) + warp] = s2; }
+  if (lane == 0) { red[32 + warp] = s1; red[64 + warp] = s2; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-    for (int w = 0; w < GSMC_BLOCK / 32; ++w) { t1 += red[GSMC_BLOCK / 32 + w]; t2 += red[2 * (GSMC_BLOCK / 32) + w]; }
+    for (int w = 0; w < GSMC_BLOCK / 32; ++w) { t1 += red[32 + w]; t2 += red[64 + w]; }
     LseTriple tr; tr.m = bm; tr.s1 = t1; tr.s2 = t2;
-    g.partials[blockIdx.x] = tr;
+    run = (tile == (int)blockIdx.x) ? tr : lse_merge_t(run, tr, tabs.exp2);
   }
+  }  // tiles
+  if (threadIdx.x == 0) {
+    g.partials[blockIdx.x] = run;
+#if GSMC_LASTBLOCK
+    // The last block to publish its partial reduces all of them (replaces a separate one-block launch).
+    __threadfence();
+    s_last = (atomicAdd(&g.ds->blocks_done, 1u) + 1u == gridDim.x) ? 1 : 0;
+#endif
+  }
+#if GSMC_LASTBLOCK
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const LseTriple tr = reduce_partials(g.partials, (int)gridDim.x, red, tabs.exp2);
+    if (threadIdx.x == 0) { g.ds->triples[g.rank] = tr; g.ds->blocks_done = 0; }
+  }
+#endif
 }
+#if !GSMC_LASTBLOCK
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const LseTriple* partials, int nblk, DevScalars* ds, int rank) {
+  __shared__ double red[96];
+  __shared__ double etab[64];
+  if (threadIdx.x < 64) etab[threadIdx.x] = gm_exp2tab_g[threadIdx.x];
+  __syncthreads();
+  const LseTriple tr = reduce_partials(partials, nblk, red, etab);
+  if (threadIdx.x == 0) ds->triples[rank] = tr;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
-// finalize: combine block partials -> this rank's triple; single-rank runs also decide here.
+// finalize: merge the ranks' triples and decide.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ LseTriple lse_merge(LseTriple a, LseTriple b) {
   if (!(b.m > -gm_inf()) && b.s1 == b.s1) return a;
@@ -373,50 +492,25 @@ __device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, d
   }
 }
 
-__global__ void __launch_bounds__(1024) finalize_kernel(const LseTriple* partials, int nblk, DevScalars* ds,
-                                                        int rank, int nranks, double ess_threshold,
-                                                        double n_global, int* resampled_flag_out,
-                                                        PeerScalars peers, uint32_t seq, int fused_exchange) {
-  __shared__ double sm[3][32];
+// The logsumexp/ESS statistics and the maybe_resample! decision from this rank's triple (left in ds->triples[rank]
+// by the last block of the propagate kernel). Multi-rank: every rank first gathers all triples over NVLink peer
+// stores (the logsumexp "allreduce") and merges them in rank order, so all ranks take the same decision
+// without a separate collective.
+__global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, int nranks, double ess_threshold,
+                                                      double n_global, int* resampled_flag_out,
+                                                      PeerScalars peers, uint32_t seq, int fused_exchange) {
   __shared__ uint64_t mine[3];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // pass 1: global max of the block maxima
-  double m = -gm_inf();
-#pragma unroll 8
-  for (int b = threadIdx.x; b < nblk; b += 1024) m = fmax(m, __ldg(&partials[b].m));
-  m = warp_max(m);
-  if (lane == 0) sm[0][warp] = m;
-  __syncthreads();
-  double M = sm[0][0];
-#pragma unroll
-  for (int w = 1; w < 32; ++w) M = fmax(M, sm[0][w]);
-  // pass 2: rescaled sums, one exp per partial, fixed summation order (deterministic)
-  double a1 = 0.0, a2 = 0.0;
-#pragma unroll 4
-  for (int b = threadIdx.x; b < nblk; b += 1024) {
-    const LseTriple p = partials[b];
-    const double e = (M > -gm_inf()) ? gm_exp_nonpos(p.m - M) : 1.0;
-    a1 += p.s1 * e;
-    a2 += p.s2 * (e * e);
-  }
-  a1 = warp_sum(a1); a2 = warp_sum(a2);
-  if (lane == 0) { sm[1][warp] = a1; sm[2][warp] = a2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t1 = 0.0, t2 = 0.0;
-    for (int w = 0; w < 32; ++w) { t1 += sm[1][w]; t2 += sm[2][w]; }
-    LseTriple tr; tr.m = M; tr.s1 = t1; tr.s2 = t2;
-    ds->triples[rank] = tr;
-    if (nranks == 1) combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out);
-    mine[0] = gm_to_bits(M); mine[1] = gm_to_bits(t1); mine[2] = gm_to_bits(t2);
-  }
   if (nranks > 1 && fused_exchange) {
-    // logsumexp/ESS "allreduce": every rank gathers all triples over NVLink peer stores and merges
-    // them in rank order, so all ranks take the same decision without a separate collective.
-    __syncthreads();
+    if (threadIdx.x == 0) {
+      const LseTriple tr = ds->triples[rank];
+      mine[0] = gm_to_bits(tr.m); mine[1] = gm_to_bits(tr.s1); mine[2] = gm_to_bits(tr.s2);
+    }
+    __syncwarp();
     ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 3, reinterpret_cast<uint64_t*>(ds->triples));
-    __syncthreads();
+    __syncwarp();
     if (threadIdx.x == 0) combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out);
+  } else if (nranks == 1) {
+    if (threadIdx.x == 0) combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out);
   }
 }
 // cross-GPU barrier (peer-memory exchange of one word): nobody passes until every rank has arrived
@@ -445,20 +539,20 @@ __global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, 
 // ------------------------------------------------------------------------------------------------
 template <typename Real>
 __device__ __forceinline__ void q_from_lw(typename Vec2T<Real>::type a, typename Vec2T<Real>::type b, int64_t i, int64_t n,
-                                          double mx, double scale, uint64_t q[4]) {
+                                          double mx, double scale, const double* etab, uint64_t q[4]) {
   const double x[4] = {(double)a.x - mx, (double)a.y - mx, (double)b.x - mx, (double)b.y - mx};
   double e[4];
-  gm_exp_nonpos_v<4>(x, e);
+  gm_exp_nonpos_v<4>(x, e, etab);
 #pragma unroll
   for (int j = 0; j < 4; ++j) q[j] = (i + j < n) ? (uint64_t)floor(e[j] * scale) : 0;
 }
 template <typename Real>
-__device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, double mx, double scale, uint64_t q[4]) {
+__device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, double mx, double scale, const double* etab, uint64_t q[4]) {
   // i is a multiple of 4 and the columns are padded to a tile, so the vector loads stay inside the allocation
   typedef typename Vec2T<Real>::type Real2;
   const Real2 a = *reinterpret_cast<const Real2*>(lw + i);
   const Real2 b = *reinterpret_cast<const Real2*>(lw + i + 2);
-  q_from_lw<Real>(a, b, i, n, mx, scale, q);
+  q_from_lw<Real>(a, b, i, n, mx, scale, etab, q);
 }
 
 // spacings of the thresholds k .. k+3 (global threshold index, k a multiple of 4), masked to k < m_draws
@@ -502,11 +596,11 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 4) weights_kernel(const Real* lw, 
   typedef typename Vec2T<Real>::type Real2;
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
   __shared__ double ltab[32];
+  __shared__ double etab[64];
   if (conditional && !ds->do_resample) return;
-  if (SPACINGS) {
-    if (threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_d[threadIdx.x];
-    __syncthreads();
-  }
+  if (SPACINGS && threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_g[threadIdx.x];
+  if (WEIGHTS && threadIdx.x >= 64 && threadIdx.x < 128) etab[threadIdx.x - 64] = gm_exp2tab_g[threadIdx.x - 64];
+  __syncthreads();
   const double mx = ds->max_lw;
   const uint32_t rho = ds->rho;
   const uint64_t m_draws = m_draws_arg ? m_draws_arg : ds->n_draws;
@@ -529,7 +623,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 4) weights_kernel(const Real* lw, 
         la = *reinterpret_cast<const Real2*>(lw + i + GSMC_TILE);
         lb = *reinterpret_cast<const Real2*>(lw + i + GSMC_TILE + 2);
       }
-      q_from_lw<Real>(ca, cb, i, n, mx, scale, q);
+      q_from_lw<Real>(ca, cb, i, n, mx, scale, etab, q);
     }
     if (SPACINGS) tile_spacings(seed, rho, k_first + (uint64_t)i, m_draws, ltab, e);
     const uint64_t qs = q[0] + q[1] + q[2] + q[3];
@@ -701,13 +795,16 @@ __global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, i
                                                                uint64_t* cc, uint64_t* seg_c, uint64_t* cl, uint64_t* seg_r,
                                                                int nt, int seg_tiles, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+  __shared__ double etab[64];
   if (conditional && !ds->do_resample) return;
+  if (threadIdx.x < 64) etab[threadIdx.x] = gm_exp2tab_g[threadIdx.x];
+  __syncthreads();
   const int t0 = blockIdx.x * seg_tiles, t1 = min(t0 + seg_tiles, nt);
   uint64_t run_c = 0, run_r = 0;
   for (int tile = t0; tile < t1; ++tile) {
     const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
     uint64_t q[4], c[4], r[4], cs = 0, rs = 0;
-    load_q4(lw, i, n, ds->max_lw, scale, q);
+    load_q4(lw, i, n, ds->max_lw, scale, etab, q);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       resid_split(q[j], ds->resid_scale, &c[j], &r[j]);

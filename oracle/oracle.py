@@ -25,7 +25,8 @@ def build(force=False):
     """Compile oracle/_build/liboracle{,_libm}.so with the committed Makefile."""
     out = os.path.join(_HERE, "_build", "liboracle.so")
     srcs = [os.path.join(_HERE, "gsmc_oracle.c"), os.path.join(_HERE, "gsmc_oracle.h"),
-            os.path.join(_HERE, "..", "gen_b200", "csrc", "gsmc_math.h")]
+            os.path.join(_HERE, "..", "gen_b200", "csrc", "gsmc_math.h"),
+            os.path.join(_HERE, "..", "gen_b200", "csrc", "gsmc_tables.h")]
     if force or not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "clean", "all"])
     return out
