@@ -636,7 +636,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
       const uint32_t magic = st > 1 ? (uint32_t)(0x100000000ULL / (uint64_t)st) + 1u : 0u;
       ProfScope ps(f, KC_SEARCH);
       search_sorted_kernel<<<grid, GSMC_BLOCK, GSMC_SEARCH_SMEM, f->stream>>>(
-          v, k_first, f->ds, f->tile_e, (uint32_t)st, magic, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional); }
+          v, k_first, f->ds, f->tile_e, (uint32_t)st, magic, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional, f->rank); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;

@@ -976,6 +976,28 @@ __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t see
   }
 }
 
+// ---- mbarrier + 1-D bulk copy (TMA) helpers: one thread moves a contiguous window global -> shared ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+// dst, src 16-byte aligned; bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -983,33 +1005,41 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 }
 
 // Sorted mode, step 2. One block iteration handles a SUPERTILE of 2048 consecutive thresholds (8 per thread)
-// and writes their ancestors anc_k = min{i : (double)C_i > t_k}. The CDF window [win[2m], win[2m+2]] the
-// supertile can map to is staged in shared memory as doubles (+inf sentinel at the end); every thread finds
-// its first threshold with a bound-check-free binary search (same probe count for the whole block) and
-// walks to the next seven (sorted thresholds: ~1 slot apart).
+// and writes their ancestors anc_k = min{i : (double)C_i > t_k}.
+//   1. one thread starts a bulk copy (TMA, mbarrier-tracked) of the CDF window [win[2m], win[2m+2]] the supertile
+//      can map to into shared memory; while it is in flight every thread turns its 8 spacings into thresholds
+//      (block scan of the spacing sums);
+//   2. the window is converted in place to doubles C_i = sp[segment(i)] + cl[i] (+inf sentinel at the end);
+//   3. every thread finds its first threshold with a bound-check-free binary search (same probe count for the
+//      whole block) and walks to the next seven (sorted thresholds: ~1 slot apart);
+//   4. positions -> ancestor words, 32-byte vector stores.
+// Windows that span more than two ranks or exceed the shared-memory capacity fall back to per-threshold
+// three-level searches in global memory; windows that touch a peer's CDF are staged with ordinary loads.
 #define GSMC_SEARCH_TPT 8                                   // thresholds per thread
 #define GSMC_SUPERTILE (GSMC_BLOCK * GSMC_SEARCH_TPT)       // 2048
-#define GSMC_WIN_CAP 5120                                   // 40 KB of window per block: 5 blocks per SM
-#define GSMC_SEARCH_SMEM ((GSMC_WIN_CAP + 1) * 8)
+#define GSMC_WIN_CAP 5120
+#define GSMC_SEARCH_SMEM ((GSMC_WIN_CAP + 4) * 8)           // 41 KB of window per block: 5 blocks per SM
 __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v, uint64_t k_first, const DevScalars* ds,
                                                                       const uint64_t* tile_e, uint32_t seg_tiles, uint32_t seg_magic,
                                                                       const uint32_t* esp, const uint32_t* win, uint32_t* anc,
-                                                                      int64_t n_out, int nt, int det_offset, int conditional) {
-  extern __shared__ double cwin[];                        // GSMC_WIN_CAP + 1 doubles
+                                                                      int64_t n_out, int nt, int det_offset, int conditional, int rank) {
+  extern __shared__ __align__(16) double dsm[];
+  double* cwin = dsm;                                              // GSMC_WIN_CAP + 4
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
+  __shared__ uint64_t mbar;
   if (conditional && !ds->do_resample) return;
-  const uint32_t cwin_base = (uint32_t)__cvta_generic_to_shared(cwin);
   const uint64_t m_draws = ds->n_draws;
   const double ratio = ds->thr_ratio, tmax = ds->thr_max;
   const int n_super = nt / (GSMC_SUPERTILE / GSMC_TILE);
+  if (threadIdx.x == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
   int buf = 0;
   for (int m = blockIdx.x; m < n_super; m += gridDim.x, buf ^= 1) {
     const int tile = m * (GSMC_SUPERTILE / GSMC_TILE);
     const uint64_t kt = k_first + (uint64_t)m * GSMC_SUPERTILE;
     if (kt >= m_draws) break;                            // uniform per block
     const int64_t o_local = (int64_t)m * GSMC_SUPERTILE + GSMC_SEARCH_TPT * threadIdx.x;
-    const uint4 ev0 = *reinterpret_cast<const uint4*>(esp + o_local);     // spacings beyond M were stored as 0
-    const uint4 ev1 = *reinterpret_cast<const uint4*>(esp + o_local + 4);
     // window [w0, w1]: [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the head [0, hi] of r0+1
     const uint32_t w0 = win[tile], w1 = win[tile + GSMC_SUPERTILE / GSMC_TILE];
     const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT), r1 = (int)(w1 >> GSMC_ANC_RANK_SHIFT);
@@ -1017,44 +1047,66 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
     const int64_t len_a = (r1 == r0) ? (int64_t)hi - lo + 1 : v.n_per - lo;
     const int64_t len_b = (r1 == r0) ? 0 : (int64_t)hi + 1;
     const bool staged = (r1 == r0 || r1 == r0 + 1) && len_a + len_b <= GSMC_WIN_CAP;
+    const bool bulk = staged && r1 == r0 && r0 == rank;
     const int la = (int)len_a, len = (int)(len_a + len_b);
-    if (staged) {
-      // C_i = sp[segment(i)] + cl[i] with global segment prefixes; segment(i) = (i / 1024) / seg_tiles by multiply-high
-      const uint64_t* seg_a = v.seg[r0] + lo;
-      const uint64_t* sp_a = v.sp[r0];
-#pragma unroll 4
-      for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
-        const uint32_t t = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
-        const uint32_t sg = seg_tiles == 1 ? t : __umulhi(t, seg_magic);
-        cwin[j] = (double)(__ldg(sp_a + sg) + __ldg(seg_a + j));
-      }
-      if (len_b) {
-        const uint64_t* seg_b = v.seg[r1];
-        const uint64_t* sp_b = v.sp[r1];
-        for (int j = threadIdx.x; j < (int)len_b; j += GSMC_BLOCK) {
-          const uint32_t t = (uint32_t)j >> GSMC_TILE_SHIFT;
-          const uint32_t sg = seg_tiles == 1 ? t : __umulhi(t, seg_magic);
-          cwin[la + j] = (double)(__ldg(sp_b + sg) + __ldg(seg_b + j));
-        }
-      }
-      if (threadIdx.x == 0) cwin[len] = gm_inf();        // sentinel: the walks below need no bound check
+    const int off = bulk ? (lo & 1) : 0;                 // the bulk copy starts at an even (16-byte aligned) element
+    if (bulk && threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)((off + len + 1) & ~1) * 8u;
+      fence_proxy_async();                               // earlier generic-proxy accesses of cwin come first
+      mbar_expect_tx(&mbar, bytes);
+      bulk_g2s(cwin, v.seg[r0] + (lo - off), bytes, &mbar);
     }
+    // thresholds of this thread: t_k = min((double)S_k * ratio, tmax); spacings beyond M were stored as 0
+    const uint4 ev0 = *reinterpret_cast<const uint4*>(esp + o_local);
+    const uint4 ev1 = *reinterpret_cast<const uint4*>(esp + o_local + 4);
     const uint32_t e[GSMC_SEARCH_TPT] = {ev0.x, ev0.y, ev0.z, ev0.w, ev1.x, ev1.y, ev1.z, ev1.w};
     uint64_t tsum = 0;
 #pragma unroll
     for (int j = 0; j < GSMC_SEARCH_TPT; ++j) tsum += e[j];
     uint64_t tot, dummy;
-    // the barrier inside the scan also publishes the staged window
     uint64_t S = tile_e[tile] + block_scan_and_sum(tsum, 0, sm, buf, &tot, &dummy) - tsum;
     const uint64_t k = k_first + (uint64_t)o_local;
-    uint32_t a[GSMC_SEARCH_TPT];
     double t[GSMC_SEARCH_TPT];
 #pragma unroll
     for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { S += e[j]; t[j] = sorted_threshold(S, ratio, tmax); }
+    uint32_t a[GSMC_SEARCH_TPT];
     if (staged) {
-      // pos = #{p : cwin[p] <= t[0]}: every probe is in bounds and the probe count depends on len only
+      // C_i = sp[segment(i)] + cl[i] with global segment prefixes; segment(i) = (i / 1024) / seg_tiles by multiply-high
+      const uint64_t* sp_a = v.sp[r0];
+      if (bulk) {
+        mbar_wait(&mbar, phase);
+        phase ^= 1;
+        const uint64_t* raw = reinterpret_cast<const uint64_t*>(cwin) + off;
+#pragma unroll 4
+        for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
+          const uint32_t tl = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
+          const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
+          cwin[off + j] = (double)(__ldg(sp_a + sg) + raw[j]);
+        }
+      } else {
+        const uint64_t* seg_a = v.seg[r0] + lo;
+#pragma unroll 4
+        for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
+          const uint32_t tl = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
+          const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
+          cwin[j] = (double)(__ldg(sp_a + sg) + __ldg(seg_a + j));
+        }
+        if (len_b) {
+          const uint64_t* seg_b = v.seg[r1];
+          const uint64_t* sp_b = v.sp[r1];
+          for (int j = threadIdx.x; j < (int)len_b; j += GSMC_BLOCK) {
+            const uint32_t tl = (uint32_t)j >> GSMC_TILE_SHIFT;
+            const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
+            cwin[la + j] = (double)(__ldg(sp_b + sg) + __ldg(seg_b + j));
+          }
+        }
+      }
+      if (threadIdx.x == 0) cwin[off + len] = gm_inf();  // sentinel
+      __syncthreads();
+      // pos = #{p : C_p <= t[0]}: every probe is in bounds and the probe count depends on len only
       // (32-bit shared-memory addresses: one add per step instead of a 64-bit generic pointer)
-      uint32_t ad = cwin_base;
+      const uint32_t cw_base = (uint32_t)__cvta_generic_to_shared(cwin + off);
+      uint32_t ad = cw_base;
       for (int rem = len; rem > 1;) {
         const int half = rem >> 1;
         if (lds_f64(ad + (uint32_t)(half - 1) * 8u) <= t[0]) ad += (uint32_t)half * 8u;
@@ -1065,9 +1117,9 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
 #pragma unroll
       for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
         if (j > 0) { while (c <= t[j]) { ad += 8u; c = lds_f64(ad); } }
-        const int pj = (int)((ad - cwin_base) >> 3);
-        const int pc = pj < len ? pj : len - 1;
-        a[j] = pc < la ? (w0 + (uint32_t)pc) : ((((uint32_t)r1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pc - la));
+        const int pj = (int)((ad - cw_base) >> 3);
+        const int pcl = pj < len ? pj : len - 1;
+        a[j] = pcl < la ? (w0 + (uint32_t)pcl) : ((((uint32_t)r1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pcl - la));
       }
     } else {
 #pragma unroll
@@ -1082,7 +1134,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
 #pragma unroll
       for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (k + j < m_draws && o + j < n_out) anc[o + j] = a[j];
     }
-    __syncthreads();                                     // everybody is done with cwin before the next supertile is staged
+    __syncthreads();                                     // everybody is done with the shared arrays before the next supertile
   }
 }
 
