@@ -304,8 +304,11 @@ static int alloc_buffers(gsmc_filter* f) {
   if (f->cap < 2) f->cap = 2;
   f->flag_mod = f->cfg.keep_history ? f->cap + 2 : 4;
   f->bytes_state = (size_t)f->cap * f->D * f->n_pad * rs; f->bytes_anc = (size_t)f->cap * f->n_pad * sizeof(uint32_t);
-  // segments: one per block of the streaming pass, 4 resident blocks per SM -> one wave
-  const int max_segs = f->sm_count * 4 < GSMC_MAX_SEGS - 1 ? f->sm_count * 4 : GSMC_MAX_SEGS - 1;   // n_segs + 1 <= 1024 threads
+  // segments: one per block of the streaming pass, all blocks resident at once -> one wave
+  int occ_w = 0;
+  const void* wk = f->f32 ? (const void*)weights_kernel<float, true, true> : (const void*)weights_kernel<double, true, true>;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, wk, GSMC_BLOCK, 0) != cudaSuccess || occ_w < 1) occ_w = 3;
+  const int max_segs = f->sm_count * occ_w < GSMC_MAX_SEGS - 1 ? f->sm_count * occ_w : GSMC_MAX_SEGS - 1;   // n_segs + 1 <= 1024 threads
   f->seg_tiles = (f->n_tiles + max_segs - 1) / max_segs;
   f->n_segs = (f->n_tiles + f->seg_tiles - 1) / f->seg_tiles;
   const size_t seg_words = GSMC_MAX_SEGS + 16;

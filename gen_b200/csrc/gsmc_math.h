@@ -27,6 +27,7 @@
 #endif
 
 #define GM_PI 3.141592653589793115997963468544185161590576171875      /* Float64(pi) */
+#define GM_RN_SHIFT 6755399441055744.0                               /* 1.5 * 2^52: x + SHIFT rounds x to an integer */
 #define GM_TWO_PI 6.28318530717958623199592693708837032318115234375   /* 2.0*pi     */
 #define GM_INF_BITS 0x7ff0000000000000ULL
 
@@ -101,6 +102,8 @@ GM_HD uint64_t gm_to_bits(double d) {
   uint64_t b; memcpy(&b, &d, 8); return b;
 #endif
 }
+/* (double)w for a 32-bit unsigned w, exactly, without an int->float conversion instruction: 2^52 + w has w in its low word */
+GM_HD double gm_u32_to_f64(uint32_t w) { return gm_from_bits(0x4330000000000000ULL | (uint64_t)w) - 4503599627370496.0; }
 GM_HD double gm_inf(void) { return gm_from_bits(GM_INF_BITS); }
 GM_HD double gm_nan(void) { return gm_from_bits(0x7ff8000000000000ULL); }
 GM_HD double gm_pow2(int k) { return gm_from_bits((uint64_t)(k + 1023) << 52); }  /* -1022<=k<=1023 */
@@ -111,7 +114,10 @@ GM_HD double gm_pow2(int k) { return gm_from_bits((uint64_t)(k + 1023) << 52); }
 // arithmetic is ever involved.
 // gm_exp_core: reduced evaluation shared by all variants; returns p in [0.99, 2) and the binary exponent k.
 GM_HD double gm_exp_core(double x, const double* tab, long long* k) {
-  const double kf = floor(x * GM_INV_L64 + 0.5);
+  /* kf = rn(x 64/ln2) by the shift trick: the sum lands in [2^52, 2^53), where doubles are the integers, so the
+     low word of z holds the integer (two's complement) and z - SHIFT is kf. No floor, no float->int conversion. */
+  const double z = fma(x, GM_INV_L64, GM_RN_SHIFT);
+  const double kf = z - GM_RN_SHIFT;
   double r = fma(-kf, GM_L64_HI, x);                    /* exact: L64_HI has 34 significant bits */
   r = fma(-kf, GM_L64_LO, r);
   double p = GM_C(exp, 0);
@@ -119,9 +125,9 @@ GM_HD double gm_exp_core(double x, const double* tab, long long* k) {
   p = fma(p, r, GM_C(exp, 2));
   p = fma(p, r, GM_C(exp, 3));
   const double q = fma(r * r, p, r);
-  const long long n = (long long)kf;
-  const double t = tab[(int)(n & 63)];
-  *k = n >> 6;
+  const int32_t n = (int32_t)(uint32_t)gm_to_bits(z);
+  const double t = tab[n & 63];
+  *k = (long long)(n >> 6);
   return fma(t, q, t);
 }
 GM_HD double gm_exp(double x) {
@@ -206,7 +212,8 @@ GM_HD double gm_safe_recip(double c) {       /* rc for gm_div_inv; 0 = "use true
 //   sin = S + (S (cos x - 1) + C sin x),  cos = C + (C (cos x - 1) - S sin x).
 // No quadrant logic; exact at the multiples of 1/2 (the table holds exact 0 and +-1 there).
 GM_HD void gm_sincospi_t(double t, const double* tab, double* sn, double* cs) {
-  const double nf = floor(t * 64.0 + 0.5);
+  const double zz = fma(t, 64.0, GM_RN_SHIFT);   /* nf = rn(64 t), |t| < 2^24 */
+  const double nf = zz - GM_RN_SHIFT;
   const double r = fma(nf, -0.015625, t);    /* exact */
   const double x = r * GM_PI;
   const double z = x * x;
@@ -218,7 +225,7 @@ GM_HD void gm_sincospi_t(double t, const double* tab, double* sn, double* cs) {
   pc = fma(pc, z, GM_C(cos, 1));
   pc = fma(pc, z, GM_C(cos, 2));
   const double cm = z * pc;                  /* cos x - 1 */
-  const int j = (int)((long long)nf & 127);
+  const int j = (int)((uint32_t)gm_to_bits(zz) & 127u);
   const double S = tab[2 * j], C = tab[2 * j + 1];
   *sn = S + fma(S, cm, C * sx);
   *cs = C + fma(C, cm, -(S * sx));
@@ -392,12 +399,13 @@ GM_HD double gm_log_unit(double x, const double* tab) {
 #endif
 
 template <int K> GM_HD void gm_exp_nonpos_v(const double* x, double* out, const double* tab) {
-  double xc[K], kf[K], r[K], p[K];
+  double xc[K], z[K], r[K], p[K];
   GM_UNROLL for (int k = 0; k < K; ++k) {
     xc[k] = x[k] < -708.3964185322641 ? -708.0 : x[k];
-    kf[k] = floor(xc[k] * GM_INV_L64 + 0.5);
-    r[k] = fma(-kf[k], GM_L64_HI, xc[k]);
-    r[k] = fma(-kf[k], GM_L64_LO, r[k]);
+    z[k] = fma(xc[k], GM_INV_L64, GM_RN_SHIFT);
+    const double kf = z[k] - GM_RN_SHIFT;
+    r[k] = fma(-kf, GM_L64_HI, xc[k]);
+    r[k] = fma(-kf, GM_L64_LO, r[k]);
     p[k] = GM_C(exp, 0);
   }
   GM_UNROLL for (int i = 1; i < 4; ++i) {
@@ -406,9 +414,9 @@ template <int K> GM_HD void gm_exp_nonpos_v(const double* x, double* out, const 
   }
   GM_UNROLL for (int k = 0; k < K; ++k) {
     const double q = fma(r[k] * r[k], p[k], r[k]);
-    const long long n = (long long)kf[k];
-    const double t = tab[(int)(n & 63)];
-    const double v = gm_from_bits(gm_to_bits(fma(t, q, t)) + ((uint64_t)(n >> 6) << 52));
+    const int32_t n = (int32_t)(uint32_t)gm_to_bits(z[k]);
+    const double t = tab[n & 63];
+    const double v = gm_from_bits(gm_to_bits(fma(t, q, t)) + ((uint64_t)(long long)(n >> 6) << 52));
     out[k] = x[k] < -708.3964185322641 ? 0.0 : v;
   }
 }
@@ -482,10 +490,10 @@ template <int K> GM_HD void gm_log_unit_v(const double* x, const double* tab, do
 }
 
 template <int K> GM_HD void gm_sincospi_v(const double* t, double* sn, double* cs, const double* tab) {
-  double nf[K], x[K], z[K], ps[K], pc[K];
+  double zz[K], x[K], z[K], ps[K], pc[K];
   GM_UNROLL for (int k = 0; k < K; ++k) {
-    nf[k] = floor(t[k] * 64.0 + 0.5);
-    const double r = fma(nf[k], -0.015625, t[k]);
+    zz[k] = fma(t[k], 64.0, GM_RN_SHIFT);
+    const double r = fma(zz[k] - GM_RN_SHIFT, -0.015625, t[k]);
     x[k] = r * GM_PI;
     z[k] = x[k] * x[k];
     ps[k] = GM_C(sin, 0);
@@ -498,7 +506,7 @@ template <int K> GM_HD void gm_sincospi_v(const double* t, double* sn, double* c
   GM_UNROLL for (int k = 0; k < K; ++k) {
     const double sx = fma(x[k] * z[k], ps[k], x[k]);
     const double cm = z[k] * pc[k];
-    const int j = (int)((long long)nf[k] & 127);
+    const int j = (int)((uint32_t)gm_to_bits(zz[k]) & 127u);
     const double S = tab[2 * j], C = tab[2 * j + 1];
     sn[k] = S + fma(S, cm, C * sx);
     cs[k] = C + fma(C, cm, -(S * sx));

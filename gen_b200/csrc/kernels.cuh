@@ -28,8 +28,8 @@
 #ifndef GSMC_LASTBLOCK
 #define GSMC_LASTBLOCK 1
 #endif
-#define GSMC_TILE 1024            // particles (or thresholds) per block of the scan / search kernels
-#define GSMC_TILE_SHIFT 10
+#define GSMC_TILE 2048            // particles (or thresholds) per block iteration of the scan / search kernels
+#define GSMC_TILE_SHIFT 11
 #define GSMC_PAD 2048             // local columns are padded to this many particles
 #define GSMC_MAX_RANKS 8
 #define GSMC_MAX_SEGS 1024          // segments (blocks of the streaming resample pass) per rank
@@ -570,8 +570,8 @@ __device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, u
   uint64_t x = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) w += (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)w, o);
+  // warp sum of w (< 2^40: a few 32-bit spacings per thread) by two hardware 32-bit reductions
+  w = (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(w & 0xfffffu)) + ((uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(w >> 20)) << 20);
   uint64_t* sv = sm + buf * 2 * NW;
   uint64_t* sw = sv + NW;
   if (lane == 31) { sv[warp] = x; sw[warp] = w; }
@@ -588,12 +588,17 @@ __device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, u
 // SPACINGS: Philox -> Exp(1) spacings esp of this rank's thresholds [k_first, k_first + nt*TILE), the
 // segment-local exclusive prefix tile_e[tile] of every tile and the segment total seg_e[s].
 // m_draws_arg: number of draws M when the host knows it (multinomial: N), 0 = read ds->n_draws.
+#ifndef GSMC_WK_OCC
+#define GSMC_WK_OCC 4
+#endif
+#define GSMC_WPT (GSMC_TILE / GSMC_BLOCK)     // elements per thread and tile of the streaming pass: 8
 template <typename Real, bool WEIGHTS, bool SPACINGS>
-__global__ void __launch_bounds__(GSMC_BLOCK, 4) weights_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
+__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
                                                              uint64_t* cl, uint64_t* seg_q, uint64_t seed, uint64_t k_first,
                                                              uint64_t m_draws_arg, uint32_t* esp, uint64_t* tile_e, uint64_t* seg_e,
                                                              int nt, int seg_tiles, int conditional) {
   typedef typename Vec2T<Real>::type Real2;
+  constexpr int W = GSMC_WPT;
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
   __shared__ double ltab[32];
   __shared__ double etab[64];
@@ -606,39 +611,61 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 4) weights_kernel(const Real* lw, 
   const uint64_t m_draws = m_draws_arg ? m_draws_arg : ds->n_draws;
   const int t0 = blockIdx.x * seg_tiles, t1 = min(t0 + seg_tiles, nt);
   uint64_t run_q = 0, run_e = 0;                          // sums over the tiles of this segment done so far
-  Real2 la, lb;
+  Real2 lv[W / 2];
   if (WEIGHTS) {
-    const int64_t i0 = (int64_t)t0 * GSMC_TILE + 4 * threadIdx.x;
-    la = *reinterpret_cast<const Real2*>(lw + i0);
-    lb = *reinterpret_cast<const Real2*>(lw + i0 + 2);
+    const int64_t i0 = (int64_t)t0 * GSMC_TILE + W * threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < W / 2; ++j) lv[j] = *reinterpret_cast<const Real2*>(lw + i0 + 2 * j);
   }
   int buf = 0;
   for (int tile = t0; tile < t1; ++tile, buf ^= 1) {
-    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
-    uint64_t q[4] = {0, 0, 0, 0};
-    uint32_t e[4] = {0, 0, 0, 0};
+    const int64_t i = (int64_t)tile * GSMC_TILE + W * threadIdx.x;
+    uint64_t q[W];
+    uint32_t e[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) { q[j] = 0; e[j] = 0; }
     if (WEIGHTS) {
-      const Real2 ca = la, cb = lb;
+      double x[W], ex[W];
+#pragma unroll
+      for (int j = 0; j < W / 2; ++j) { x[2 * j] = (double)lv[j].x - mx; x[2 * j + 1] = (double)lv[j].y - mx; }
       if (tile + 1 < t1) {                                // next tile's log weights are in flight during the arithmetic
-        la = *reinterpret_cast<const Real2*>(lw + i + GSMC_TILE);
-        lb = *reinterpret_cast<const Real2*>(lw + i + GSMC_TILE + 2);
+#pragma unroll
+        for (int j = 0; j < W / 2; ++j) lv[j] = *reinterpret_cast<const Real2*>(lw + i + GSMC_TILE + 2 * j);
       }
-      q_from_lw<Real>(ca, cb, i, n, mx, scale, etab, q);
+      gm_exp_nonpos_v<W>(x, ex, etab);
+#pragma unroll
+      for (int j = 0; j < W; ++j) q[j] = (uint64_t)(ex[j] * scale);          // = floor: the product is >= 0
+      if ((int64_t)(tile + 1) * GSMC_TILE > n) {                             // the tile that holds the pad lanes (block-uniform)
+#pragma unroll
+        for (int j = 0; j < W; ++j) if (i + j >= n) q[j] = 0;
+      }
     }
-    if (SPACINGS) tile_spacings(seed, rho, k_first + (uint64_t)i, m_draws, ltab, e);
-    const uint64_t qs = q[0] + q[1] + q[2] + q[3];
-    const uint64_t es = (uint64_t)e[0] + e[1] + e[2] + e[3];
+    if (SPACINGS) {
+      const uint64_t k = k_first + (uint64_t)i;
+      spacing_quad(seed, k >> 2, rho, ltab, e);
+      spacing_quad(seed, (k >> 2) + 1, rho, ltab, e + 4);
+      if (k_first + (uint64_t)(tile + 1) * GSMC_TILE > m_draws) {            // thresholds beyond the M draws (block-uniform)
+#pragma unroll
+        for (int j = 0; j < W; ++j) if (k + j >= m_draws) e[j] = 0;
+      }
+    }
+    uint64_t qs = 0, es = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) { qs += q[j]; es += e[j]; }
     uint64_t qt, et;
     const uint64_t incl = block_scan_and_sum(qs, es, sm, buf, &qt, &et);
     if (WEIGHTS) {
       uint64_t c = run_q + incl - qs;
-      ulonglong2 o0, o1;
-      c += q[0]; o0.x = c; c += q[1]; o0.y = c; c += q[2]; o1.x = c; c += q[3]; o1.y = c;
-      *reinterpret_cast<ulonglong2*>(cl + i) = o0;
-      *reinterpret_cast<ulonglong2*>(cl + i + 2) = o1;
+#pragma unroll
+      for (int j = 0; j < W; j += 2) {
+        ulonglong2 o;
+        c += q[j]; o.x = c; c += q[j + 1]; o.y = c;
+        *reinterpret_cast<ulonglong2*>(cl + i + j) = o;
+      }
     }
     if (SPACINGS) {
       *reinterpret_cast<uint4*>(esp + i) = make_uint4(e[0], e[1], e[2], e[3]);
+      *reinterpret_cast<uint4*>(esp + i + 4) = make_uint4(e[4], e[5], e[6], e[7]);
       if (threadIdx.x == 0) tile_e[tile] = run_e;
     }
     run_q += qt; run_e += et;
@@ -801,8 +828,8 @@ __global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, i
   __syncthreads();
   const int t0 = blockIdx.x * seg_tiles, t1 = min(t0 + seg_tiles, nt);
   uint64_t run_c = 0, run_r = 0;
-  for (int tile = t0; tile < t1; ++tile) {
-    const int64_t i = (int64_t)tile * GSMC_TILE + 4 * threadIdx.x;
+  for (int sub = t0 * (GSMC_TILE / 1024); sub < t1 * (GSMC_TILE / 1024); ++sub) {
+    const int64_t i = (int64_t)sub * 1024 + 4 * threadIdx.x;
     uint64_t q[4], c[4], r[4], cs = 0, rs = 0;
     load_q4(lw, i, n, ds->max_lw, scale, etab, q);
 #pragma unroll
