@@ -376,6 +376,20 @@ static int ensure_f64(gsmc_filter* f, size_t n) {
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
+// Hot-path kernels are launched with programmatic stream serialization (see pdl_wait in kernels.cuh): the
+// launch latency and the prologue of kernel k+1 overlap the tail of kernel k. GSMC_NO_PDL=1 turns it off.
+static bool pdl_enabled() { static int on = getenv("GSMC_NO_PDL") ? 0 : 1; return on != 0; }
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 template <class Model, typename Real, bool INIT, int PROP>
 static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   Model::prepare(a, INIT, PROP);
@@ -411,7 +425,7 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
     }
     g.n_tiles = (int)(f->n_pad / PropTile<Model>::TILE);
     f->n_partials = g.n_tiles < f->sm_count * occ ? g.n_tiles : f->sm_count * occ;
-    propagate_kernel<Model, Real, INIT, PROP><<<f->n_partials, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream>>>(g, a);
+    CK(launch_pdl(propagate_kernel<Model, Real, INIT, PROP>, f->n_partials, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream, g, a));
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -488,7 +502,7 @@ static int launch_finalize(gsmc_filter* f, double ess_threshold) {
 #if !GSMC_LASTBLOCK
     reduce_partials_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_partials, f->ds, f->rank);
 #endif
-    finalize_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, peers, f->xchg_seq, fused);
+    CK(launch_pdl(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, peers, f->xchg_seq, fused));
   }
   CK(cudaGetLastError());
   if (f->nranks > 1 && !fused) {
@@ -552,8 +566,8 @@ static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint6
   const bool fused = multi && !f->use_nccl_scalars;
   if (fused) f->xchg_seq += 1;
   { ProfScope ps(f, cls);
-    scan_segments_kernel<<<1, 1024, 0, f->stream>>>(in0, in1, out0, out1, f->n_segs, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
-                                                    peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0); }
+    CK(launch_pdl(scan_segments_kernel, 1, 1024, 0, f->stream, in0, in1, out0, out1, f->n_segs, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
+                  peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0)); }
   CK(cudaGetLastError());
   if (multi && !fused) {
     if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
@@ -584,25 +598,25 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   // 1. integer weights -> segment-local CDF + segment totals (and, fused, the spacings of the N draws)
   if (fuse_spacings) {
     ProfScope ps(f, KC_SCAN);
-    weights_kernel<Real, true, true><<<ns, GSMC_BLOCK, 0, f->stream>>>(
-        lw, f->n, scale, f->ds, f->cdf, f->raw0, f->cfg.seed, k_first, (uint64_t)f->N, f->esp, f->tile_e, f->raw1, nt, st, conditional);
+    CK(launch_pdl(weights_kernel<Real, true, true>, ns, GSMC_BLOCK, 0, f->stream,
+        lw, f->n, scale, f->ds, f->cdf, f->raw0, f->cfg.seed, k_first, (uint64_t)f->N, f->esp, f->tile_e, f->raw1, nt, st, conditional));
   } else {
     ProfScope ps(f, KC_SCAN);
-    weights_kernel<Real, true, false><<<ns, GSMC_BLOCK, 0, f->stream>>>(
-        lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, nt, st, conditional);
+    CK(launch_pdl(weights_kernel<Real, true, false>, ns, GSMC_BLOCK, 0, f->stream,
+        lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, nt, st, conditional));
   }
   CK(cudaGetLastError());
   // 2. segment prefixes and the totals of the event
   if (fuse_spacings) { if (!fuse_scan) CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional)); }
   else CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional));
   if (residual) {
-    { ProfScope ps(f, KC_OTHER); resid_scale_kernel<<<1, 32, 0, f->stream>>>(f->ds, (double)f->N); }
+    { ProfScope ps(f, KC_OTHER); CK(launch_pdl(resid_scale_kernel, 1, 32, 0, f->stream, f->ds, (double)f->N)); }
     { ProfScope ps(f, KC_SCAN);
-      resid_cdf_kernel<Real><<<ns, GSMC_BLOCK, 0, f->stream>>>(lw, f->n, scale, f->ds, f->cc, f->raw0, f->cdf, f->raw1, nt, st, conditional); }
+      CK(launch_pdl(resid_cdf_kernel<Real>, ns, GSMC_BLOCK, 0, f->stream, lw, f->n, scale, f->ds, f->cc, f->raw0, f->cdf, f->raw1, nt, st, conditional)); }
     CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_b, SCAN_RESID, conditional));
     { ProfScope ps(f, KC_SEARCH);
-      det_copies_kernel<<<(int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream>>>(
-          f->cc, f->seg_a, ns, st * GSMC_TILE, (int)f->n_pad, f->n, f->ds, anc, conditional); }
+      CK(launch_pdl(det_copies_kernel, (int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream,
+          f->cc, f->seg_a, ns, st * GSMC_TILE, (int)f->n_pad, f->n, f->ds, anc, conditional)); }
     CK(cudaGetLastError());
   }
   const CdfView v = make_cdf_view(f, residual);
@@ -617,8 +631,8 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     if (residual) {
       // the number of draws M is only known now: spacings of the M thresholds
       { ProfScope ps(f, KC_SPACINGS);
-        weights_kernel<Real, false, true><<<ns, GSMC_BLOCK, 0, f->stream>>>(
-            lw, f->n, scale, f->ds, nullptr, nullptr, f->cfg.seed, k_first, 0, f->esp, f->tile_e, f->raw1, nt, st, conditional); }
+        CK(launch_pdl(weights_kernel<Real, false, true>, ns, GSMC_BLOCK, 0, f->stream,
+            lw, f->n, scale, f->ds, nullptr, nullptr, f->cfg.seed, k_first, 0, f->esp, f->tile_e, f->raw1, nt, st, conditional)); }
       CKRC(launch_scan(f, KC_SPACINGS, f->raw1, nullptr, f->seg_e, nullptr, SCAN_E, conditional));
     }
     // 3. ancestors
@@ -626,10 +640,10 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     { ProfScope ps(f, KC_SEARCH);
       const int need = (nt + 1 + 31) / 32;
       const int grid = need < 2 * f->sm_count ? need : 2 * f->sm_count;      // one wave of 1024-thread blocks
-      if (fuse_scan) partition_kernel<true><<<grid, 1024, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
-                                                                          f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional);
-      else partition_kernel<false><<<grid, 1024, 0, f->stream>>>(v, f->cfg.seed, k_first, f->rank, f->ds, nullptr, nullptr, sp_q, f->seg_e,
-                                                                 f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional); }
+      if (fuse_scan) CK(launch_pdl(partition_kernel<true>, grid, 1024, 0, f->stream, v, f->cfg.seed, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
+                                   f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional));
+      else CK(launch_pdl(partition_kernel<false>, grid, 1024, 0, f->stream, v, f->cfg.seed, k_first, f->rank, f->ds, nullptr, nullptr, sp_q, f->seg_e,
+                         f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional)); }
     { static bool attr_set = false;
       if (!attr_set) { CK(cudaFuncSetAttribute((const void*)search_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMC_SEARCH_SMEM)); attr_set = true; }
       int occ = 0;
@@ -638,8 +652,8 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
       const int grid = n_super < f->sm_count * occ ? n_super : f->sm_count * occ;
       const uint32_t magic = st > 1 ? (uint32_t)(0x100000000ULL / (uint64_t)st) + 1u : 0u;
       ProfScope ps(f, KC_SEARCH);
-      search_sorted_kernel<<<grid, GSMC_BLOCK, GSMC_SEARCH_SMEM, f->stream>>>(
-          v, k_first, f->ds, f->tile_e, (uint32_t)st, magic, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional, f->rank); }
+      CK(launch_pdl(search_sorted_kernel, grid, GSMC_BLOCK, GSMC_SEARCH_SMEM, f->stream,
+          v, k_first, f->ds, f->tile_e, (uint32_t)st, magic, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional, f->rank)); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;

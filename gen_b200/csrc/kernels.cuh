@@ -36,6 +36,13 @@
 #define GSMC_ANC_RANK_SHIFT 28    // ancestor word = (owner rank << 28) | local index
 #define GSMC_ANC_INDEX_MASK 0x0fffffffu
 
+// Programmatic dependent launch: kernels launched with the programmatic-stream-serialization attribute may start
+// (block scheduling, shared-memory table staging) while the previous kernel of the stream drains; pdl_wait()
+// blocks until that kernel has completed and its writes are visible, so it precedes the first access of any
+// buffer another kernel writes or reads. pdl_trigger() lets the NEXT kernel's blocks be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct LseTriple { double m, s1, s2; };   // max, sum exp(lw-m), sum exp(2(lw-m))
 
 // Device-resident scalars: the filter never needs a host round trip to take a decision.
@@ -269,6 +276,8 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs
   load_tabs(tabs, NZ > 0);
   if (Model::SMEM_DOUBLES > 0) Model::template prologue<INIT, PROP>(a, dyn_sm);
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   const bool gather = !INIT && g.use_anc && (*g.resampled_flag != 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // Persistent blocks: block b handles tiles b, b + gridDim.x, ...; thread 0 carries the block's running
@@ -500,6 +509,8 @@ __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, 
                                                       double n_global, int* resampled_flag_out,
                                                       PeerScalars peers, uint32_t seq, int fused_exchange) {
   __shared__ uint64_t mine[3];
+  pdl_wait();
+  pdl_trigger();
   if (nranks > 1 && fused_exchange) {
     if (threadIdx.x == 0) {
       const LseTriple tr = ds->triples[rank];
@@ -602,10 +613,12 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const 
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
   __shared__ double ltab[32];
   __shared__ double etab[64];
-  if (conditional && !ds->do_resample) return;
   if (SPACINGS && threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_g[threadIdx.x];
   if (WEIGHTS && threadIdx.x >= 64 && threadIdx.x < 128) etab[threadIdx.x - 64] = gm_exp2tab_g[threadIdx.x - 64];
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  if (conditional && !ds->do_resample) return;
   const double mx = ds->max_lw;
   const uint32_t rho = ds->rho;
   const uint64_t m_draws = m_draws_arg ? m_draws_arg : ds->n_draws;
@@ -767,6 +780,8 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
   __shared__ uint64_t sm[2][33];
   __shared__ uint64_t mine[2];
   __shared__ uint64_t got[2 * GSMC_MAX_RANKS];
+  pdl_wait();
+  pdl_trigger();
   const bool skip = conditional && !ds->do_resample;
   const int n64 = ((what & SCAN_Q) ? 1 : 0) + ((what & SCAN_E) ? 1 : 0);
   uint64_t totals[2] = {0, 0};
@@ -813,6 +828,8 @@ __device__ __forceinline__ void resid_split(uint64_t q, double scale, uint64_t* 
   *c = e >> 32; *r = e & 0xffffffffULL;
 }
 __global__ void resid_scale_kernel(DevScalars* ds, double n_global) {
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample)
     ds->resid_scale = (n_global * 4294967296.0) / (double)ds->cdf_total;
 }
@@ -823,9 +840,11 @@ __global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, i
                                                                int nt, int seg_tiles, int conditional) {
   __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
   __shared__ double etab[64];
-  if (conditional && !ds->do_resample) return;
   if (threadIdx.x < 64) etab[threadIdx.x] = gm_exp2tab_g[threadIdx.x];
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  if (conditional && !ds->do_resample) return;
   const int t0 = blockIdx.x * seg_tiles, t1 = min(t0 + seg_tiles, nt);
   uint64_t run_c = 0, run_r = 0;
   for (int sub = t0 * (GSMC_TILE / 1024); sub < t1 * (GSMC_TILE / 1024); ++sub) {
@@ -940,6 +959,8 @@ __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t see
   __shared__ uint64_t sm[2][33];
   __shared__ double s_thr[2];
   __shared__ uint64_t s_draws;
+  pdl_wait();
+  pdl_trigger();
   if (conditional && !ds->do_resample) return;
   const int n_segs = v.n_segs;
   if (FUSED_SCAN) {
@@ -1054,6 +1075,8 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
   double* cwin = dsm;                                              // GSMC_WIN_CAP + 4
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
   __shared__ uint64_t mbar;
+  pdl_wait();
+  pdl_trigger();
   if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws;
   const double ratio = ds->thr_ratio, tmax = ds->thr_max;
@@ -1189,6 +1212,8 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_iid_kernel(CdfView v, const
 // residual scheme, deterministic part: slot o < n_det belongs to min{i : Cc_i > o}, Cc in two levels
 __global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* cc, const uint64_t* seg_c, int n_segs, int seg_len, int n_pad,
                                                                 int64_t n, const DevScalars* ds, uint32_t* anc, int conditional) {
+  pdl_wait();
+  pdl_trigger();
   if (conditional && !ds->do_resample) return;
   const int64_t o = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
   if (o >= (int64_t)ds->n_det || o >= n) return;

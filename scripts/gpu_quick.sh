@@ -10,3 +10,5 @@ print('ms_per_step',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'],'frac',d['roo
 print(d['kernel_ms_profile_pass'], d['log_ml'])
 PY
 tail -3 gpurun_out/bench_quick.err
+GSMC_NO_PDL=1 python bench.py --no-cpu-baseline > gpurun_out/bench_nopdl.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/bench_nopdl.json')); print('NO_PDL ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])"
