@@ -404,7 +404,7 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   g.resampled_flag = f->resampled + (new_step % f->flag_mod);
   g.partials = f->partials;
   g.ds = f->ds; g.nranks = f->nranks;
-  g.n = f->n; g.stride = f->n_pad; g.first_global = (uint64_t)f->first; g.seed = f->cfg.seed;
+  g.n = f->n; g.stride = f->n_pad; g.first_global = (uint64_t)f->first; g.seed = f->cfg.seed; g.keys = make_philox_keys(f->cfg.seed);
   g.t = (uint32_t)new_step;
   g.use_anc = use_anc ? 1 : 0;
   g.rank = f->rank;
@@ -599,11 +599,11 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   if (fuse_spacings) {
     ProfScope ps(f, KC_SCAN);
     CK(launch_pdl(weights_kernel<Real, true, true>, ns, GSMC_BLOCK, 0, f->stream,
-        lw, f->n, scale, f->ds, f->cdf, f->raw0, f->cfg.seed, k_first, (uint64_t)f->N, f->esp, f->tile_e, f->raw1, nt, st, conditional));
+        lw, f->n, scale, f->ds, f->cdf, f->raw0, make_philox_keys(f->cfg.seed), k_first, (uint64_t)f->N, f->esp, f->tile_e, f->raw1, nt, st, conditional));
   } else {
     ProfScope ps(f, KC_SCAN);
     CK(launch_pdl(weights_kernel<Real, true, false>, ns, GSMC_BLOCK, 0, f->stream,
-        lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, nt, st, conditional));
+        lw, f->n, scale, f->ds, f->cdf, f->raw0, make_philox_keys(0), 0, 0, nullptr, nullptr, nullptr, nt, st, conditional));
   }
   CK(cudaGetLastError());
   // 2. segment prefixes and the totals of the event
@@ -632,7 +632,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
       // the number of draws M is only known now: spacings of the M thresholds
       { ProfScope ps(f, KC_SPACINGS);
         CK(launch_pdl(weights_kernel<Real, false, true>, ns, GSMC_BLOCK, 0, f->stream,
-            lw, f->n, scale, f->ds, nullptr, nullptr, f->cfg.seed, k_first, 0, f->esp, f->tile_e, f->raw1, nt, st, conditional)); }
+            lw, f->n, scale, f->ds, nullptr, nullptr, make_philox_keys(f->cfg.seed), k_first, 0, f->esp, f->tile_e, f->raw1, nt, st, conditional)); }
       CKRC(launch_scan(f, KC_SPACINGS, f->raw1, nullptr, f->seg_e, nullptr, SCAN_E, conditional));
     }
     // 3. ancestors
@@ -1028,9 +1028,9 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
     const double scale = weight_scale(f);
     { ProfScope ps(f, KC_SCAN);
       if (f->f32) weights_kernel<float, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
-          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0);
+          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, make_philox_keys(0), 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0);
       else weights_kernel<double, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
-          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
+          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, make_philox_keys(0), 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
     CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q, 0));
   }
   CK(cudaGetLastError());

@@ -195,8 +195,10 @@ GM_HD double gm_log_pos(double x) { return gm_log_core(gm_to_bits(x), 0); }
 // formula performs (tests/test_math.py checks 10^7 adversarial operand pairs). Outside the safe
 // magnitude range (zero, subnormal results, inf, nan) or when rc == 0 it falls back to x / c.
 GM_HD double gm_div_inv(double x, double c, double rc) {
-  const double ax = fabs(x);
-  if (!(ax > 1e-290 && ax < 1e290) || rc == 0.0) return x / c;
+  /* safe range 2^-963 <= |x| < 2^963, tested on the exponent field with one integer compare
+     (0, subnormal, inf and nan fall outside) */
+  const uint32_t hx = (uint32_t)(gm_to_bits(x) >> 32) & 0x7fffffffu;
+  if (hx - 0x03c00000u >= 0x7c200000u - 0x03c00000u || rc == 0.0) return x / c;
   const double q0 = x * rc;
   const double r = fma(-q0, c, x);
   return fma(r, rc, q0);

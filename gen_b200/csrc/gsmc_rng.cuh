@@ -43,6 +43,30 @@ __host__ __device__ __forceinline__ PhiloxOut philox_call(uint64_t seed, uint64_
   return o;
 }
 
+// The ten round keys of a seed, precomputed on the host and passed as a kernel parameter: the rounds then take
+// them as constant-bank operands instead of recomputing k += W per round and call.
+struct PhiloxKeys { uint32_t k[20]; };
+static inline PhiloxKeys make_philox_keys(uint64_t seed) {
+  PhiloxKeys K;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  return K;
+}
+__device__ __forceinline__ PhiloxOut philox_call(const PhiloxKeys& K, uint64_t call, uint32_t t, uint32_t stream) {
+  uint32_t c0 = (uint32_t)call, c1 = (uint32_t)(call >> 32), c2 = t, c3 = stream;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[2 * r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[2 * r + 1];
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+  }
+  PhiloxOut o;
+  o.a = (uint64_t)c0 | ((uint64_t)c1 << 32);
+  o.b = (uint64_t)c2 | ((uint64_t)c3 << 32);
+  return o;
+}
+
 // two standard normals from one call
 __host__ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t call, uint32_t t, const double* ltab, double* z0, double* z1) {
   const PhiloxOut o = philox_call(seed, call, t, GSMC_STREAM_NORMAL);
@@ -66,7 +90,8 @@ __host__ __device__ __forceinline__ uint32_t spacing_from_word(uint32_t w, const
   return (uint32_t)(int64_t)floor(-gm_log_tab(u, tab) * GM_SPACING_SCALE);
 }
 // the four spacings 4c .. 4c+3 of call c
-__host__ __device__ __forceinline__ void spacing_quad(uint64_t seed, uint64_t call, uint32_t rho, const double* tab, uint32_t* e) {
+template <class Key>
+__host__ __device__ __forceinline__ void spacing_quad(const Key& seed, uint64_t call, uint32_t rho, const double* tab, uint32_t* e) {
   const PhiloxOut o = philox_call(seed, call, rho, GSMC_STREAM_RESAMPLE);
   const uint32_t w[4] = {(uint32_t)o.a, (uint32_t)(o.a >> 32), (uint32_t)o.b, (uint32_t)(o.b >> 32)};
   double u[4], l[4];
@@ -85,8 +110,8 @@ __host__ __device__ __forceinline__ uint64_t spacing_one(uint64_t seed, uint64_t
 
 // Batch forms (same bits as the scalar functions, see gsmc_math.h "Batch forms").
 // K Philox calls -> 2K standard normals z[2m] (cos branch), z[2m+1] (sin branch)
-template <int K>
-__host__ __device__ __forceinline__ void normal_pairs_v(uint64_t seed, const uint64_t* calls, uint32_t t, const double* ltab, const double* sctab, double* z) {
+template <int K, class Key>
+__host__ __device__ __forceinline__ void normal_pairs_v(const Key& seed, const uint64_t* calls, uint32_t t, const double* ltab, const double* sctab, double* z) {
   double u1[K], t2[K], l[K], sn[K], cs[K];
 #pragma unroll
   for (int m = 0; m < K; ++m) {

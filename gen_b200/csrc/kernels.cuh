@@ -25,6 +25,12 @@
 #include "models.cuh"
 
 #define GSMC_BLOCK 256
+#ifndef GSMC_PROP_PAIRS
+#define GSMC_PROP_PAIRS 4
+#endif
+#ifndef GSMC_PROP_OCC
+#define GSMC_PROP_OCC 3
+#endif
 #ifndef GSMC_LASTBLOCK
 #define GSMC_LASTBLOCK 1
 #endif
@@ -207,6 +213,7 @@ struct PropArgs {
   int64_t stride;                    // column stride (padded n)
   uint64_t first_global;             // global index of local particle 0
   uint64_t seed;
+  PhiloxKeys keys;                   // round keys of `seed`
   uint32_t t;                        // 1-based time index of the step being produced
   int use_anc;                       // 0: read cur directly; 1: consult *resampled_flag
   int rank;                          // this rank: cur[rank] is the local column
@@ -216,7 +223,7 @@ struct PropArgs {
 
 // pairs of particles per thread: 4 (2048-particle tile) for 1-2 column models, 2 for wider states
 template <class Model> struct PropTile {
-  static constexpr int PAIRS = Model::D <= 2 ? 4 : 2;
+  static constexpr int PAIRS = Model::D <= 2 ? GSMC_PROP_PAIRS : 2;
   static constexpr int TILE = 2 * GSMC_BLOCK * PAIRS;
 };
 
@@ -263,7 +270,7 @@ __device__ __forceinline__ LseTriple reduce_partials(const LseTriple* partials, 
 }
 
 template <class Model, typename Real, bool INIT, int PROP>
-__global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
+__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
   typedef typename Vec2T<Real>::type Real2;
   constexpr int D = Model::D;
   constexpr int PAIRS = PropTile<Model>::PAIRS, NP = 2 * PAIRS, TILE = PropTile<Model>::TILE;
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs
 #pragma unroll
         for (int m = 0; m < NZ; ++m) calls[u * NZ + m] = c0 + m;
       }
-      normal_pairs_v<PAIRS * NZA>(g.seed, calls, g.t, tabs.log64, tabs.sincos, &zz[0][0]);
+      normal_pairs_v<PAIRS * NZA>(g.keys, calls, g.t, tabs.log64, tabs.sincos, &zz[0][0]);
     }
   }
   if (NU > 0) {
@@ -403,10 +410,10 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs
   }
 
   // Stage E: block partial of (max, sum exp(lw-max), sum exp(2(lw-max))); NaN log weights poison s1/s2 on purpose.
+  // fmax drops NaNs, so the max needs no NaN test; a NaN log weight then turns into a NaN exp below
   double m = -gm_inf();
-  bool any_nan = false;
 #pragma unroll
-  for (int j = 0; j < NP; ++j) { if (lwv[j] != lwv[j]) any_nan = true; else m = fmax(m, lwv[j]); }
+  for (int j = 0; j < NP; ++j) m = fmax(m, lwv[j]);
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
@@ -421,8 +428,13 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 3) propagate_kernel(const PropArgs
     gm_exp_nonpos_v<NP>(x, e, tabs.exp2);
 #pragma unroll
     for (int j = 0; j < NP; ++j) { s1 += e[j]; s2 += e[j] * e[j]; }
+  } else {
+    // a tile of -inf / NaN log weights only: no exp is evaluated, so look for the NaNs explicitly
+    bool any_nan = false;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) any_nan = any_nan || (lwv[j] != lwv[j]);
+    if (any_nan) { s1 = gm_nan(); s2 = gm_nan(); }
   }
-  if (any_nan) { s1 = gm_nan(); s2 = gm_nan(); }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
   if (lane == 0) { red[32 + warp] = s1; red[64 + warp] = s2; }
   __syncthreads();
@@ -605,7 +617,7 @@ __device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, u
 #define GSMC_WPT (GSMC_TILE / GSMC_BLOCK)     // elements per thread and tile of the streaming pass: 8
 template <typename Real, bool WEIGHTS, bool SPACINGS>
 __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                             uint64_t* cl, uint64_t* seg_q, uint64_t seed, uint64_t k_first,
+                                                             uint64_t* cl, uint64_t* seg_q, const PhiloxKeys seed, uint64_t k_first,
                                                              uint64_t m_draws_arg, uint32_t* esp, uint64_t* tile_e, uint64_t* seg_e,
                                                              int nt, int seg_tiles, int conditional) {
   typedef typename Vec2T<Real>::type Real2;
