@@ -1139,11 +1139,19 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
         mbar_wait(&mbar, phase);
         phase ^= 1;
         const uint64_t* raw = reinterpret_cast<const uint64_t*>(cwin) + off;
+        const uint32_t tl0 = (uint32_t)lo >> GSMC_TILE_SHIFT, tl1 = (uint32_t)(lo + la - 1) >> GSMC_TILE_SHIFT;
+        const uint32_t sg0 = seg_tiles == 1 ? tl0 : __umulhi(tl0, seg_magic), sg1 = seg_tiles == 1 ? tl1 : __umulhi(tl1, seg_magic);
+        if (sg0 == sg1) {                                  // the usual case: the whole window lies in one segment
+          const uint64_t add = __ldg(sp_a + sg0);
 #pragma unroll 4
-        for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
-          const uint32_t tl = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
-          const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
-          cwin[off + j] = (double)(__ldg(sp_a + sg) + raw[j]);
+          for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) cwin[off + j] = (double)(add + raw[j]);
+        } else {
+#pragma unroll 4
+          for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
+            const uint32_t tl = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
+            const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
+            cwin[off + j] = (double)(__ldg(sp_a + sg) + raw[j]);
+          }
         }
       } else {
         const uint64_t* seg_a = v.seg[r0] + lo;
