@@ -967,7 +967,11 @@ GSMC_API int gsmc_get_trajectories(gsmc_handle f, const int64_t* idx, size_t n_i
   if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
   if (!f->cfg.keep_history && f->T > 1) return fail(GSMC_E_BADARG, "trajectories need keep_history=1");
   if (n_values != n_idx * (size_t)f->T * f->D) return fail(GSMC_E_BADARG, "expected a buffer of %zu values", n_idx * (size_t)f->T * f->D);
-  for (size_t s = 0; s < n_idx; ++s) if (idx[s] < 0 || idx[s] >= f->n) return fail(GSMC_E_BADARG, "particle index %lld out of range", (long long)idx[s]);
+  bool remote = false;
+  for (size_t s = 0; s < n_idx; ++s) {
+    if (idx[s] < 0 || idx[s] >= f->N) return fail(GSMC_E_BADARG, "particle index %lld out of range", (long long)idx[s]);
+    if (idx[s] < f->first || idx[s] >= f->first + f->n) remote = true;
+  }
   if (n_idx == 0) return GSMC_OK;
   CK(cudaSetDevice(f->device));
   CKRC(ensure_f64(f, n_values + n_idx));
@@ -976,12 +980,15 @@ GSMC_API int gsmc_get_trajectories(gsmc_handle f, const int64_t* idx, size_t n_i
   const int grid = (int)((n_idx + GSMC_BLOCK - 1) / GSMC_BLOCK);
   {
     ProfScope ps(f, KC_OTHER);
-    if (f->f32) trajectories_kernel<float><<<grid, GSMC_BLOCK, 0, f->stream>>>(make_hist_view<float>(f), f->rank, d_idx, (int64_t)n_idx, f->T, f->pending ? 1 : 0, f->d_f64);
-    else trajectories_kernel<double><<<grid, GSMC_BLOCK, 0, f->stream>>>(make_hist_view<double>(f), f->rank, d_idx, (int64_t)n_idx, f->T, f->pending ? 1 : 0, f->d_f64);
+    if (f->f32) trajectories_kernel<float><<<grid, GSMC_BLOCK, 0, f->stream>>>(make_hist_view<float>(f), f->n, d_idx, (int64_t)n_idx, f->T, f->pending ? 1 : 0, f->d_f64);
+    else trajectories_kernel<double><<<grid, GSMC_BLOCK, 0, f->stream>>>(make_hist_view<double>(f), f->n, d_idx, (int64_t)n_idx, f->T, f->pending ? 1 : 0, f->d_f64);
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, f->d_f64, n_values * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   CK(cudaStreamSynchronize(f->stream));
+  // rows of other ranks were read: the call is then collective (every rank asks for the same set, as after
+  // gsmc_sample_unweighted) and nobody moves on -- and overwrites rows -- while a peer may still be reading them
+  if (remote) CKRC(peer_barrier(f));
   return GSMC_OK;
 }
 
@@ -1006,8 +1013,8 @@ GSMC_API int gsmc_get_ancestors(gsmc_handle f, int64_t* host_dst, size_t n) {
 GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t* idx_out) {
   if (!f || (!idx_out && num_samples)) return fail(GSMC_E_BADARG, "null argument");
   if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
-  if (f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "sample_unweighted is single-GPU in this version");
-  if (num_samples == 0) return GSMC_OK;
+  if (num_samples == 0 && f->nranks == 1) return GSMC_OK;
+  if (num_samples == 0) return fail(GSMC_E_BADARG, "sample_unweighted is collective on a sharded filter: every rank passes the same num_samples > 0");
   CK(cudaSetDevice(f->device));
   CKRC(ensure_f64(f, num_samples));
   int64_t* d_idx = (int64_t*)f->d_f64;

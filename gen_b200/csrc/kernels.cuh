@@ -1302,13 +1302,15 @@ __global__ void __launch_bounds__(GSMC_BLOCK) get_state_kernel(HistView<Real> h,
 }
 // out[s][t-1][d] for selected local particles idx[s]
 template <typename Real>
-__global__ void __launch_bounds__(GSMC_BLOCK) trajectories_kernel(HistView<Real> h, int rank, const int64_t* idx, int64_t n_idx,
+__global__ void __launch_bounds__(GSMC_BLOCK) trajectories_kernel(HistView<Real> h, int64_t n_per, const int64_t* idx, int64_t n_idx,
                                                                   int64_t newest, int pending, double* out) {
   const int64_t s = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
   if (s >= n_idx) return;
-  uint32_t word = ((uint32_t)rank << GSMC_ANC_RANK_SHIFT) | (uint32_t)idx[s];
+  // idx holds GLOBAL particle indices: owner rank = idx / n_per; rows of other ranks are read through the peer mappings
+  const int owner = (int)(idx[s] / n_per);
+  uint32_t word = ((uint32_t)owner << GSMC_ANC_RANK_SHIFT) | (uint32_t)(idx[s] - (int64_t)owner * n_per);
   if (pending && h.resampled[(newest + 1) % h.flag_mod]) {
-    const uint32_t* a = h.anc_slab[rank] + (newest % h.cap) * h.stride;
+    const uint32_t* a = h.anc_slab[owner] + (newest % h.cap) * h.stride;
     word = a[word & GSMC_ANC_INDEX_MASK];
   }
   for (int64_t t = newest; t >= 1; --t) {

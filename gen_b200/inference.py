@@ -139,8 +139,11 @@ class ParticleFilterState:
         _lib.check(self.lib.gsmc_get_state(self.handle, int(t), _lib.dptr(out), out.size), self.handle)
         return out
 
-    def trajectories(self, idx):
+    def trajectories(self, idx, local=False):
+        """Trajectories of particles given by GLOBAL index (local=True: indices into this rank's shard)."""
         idx = np.ascontiguousarray(idx, dtype=np.int64)
+        if local:
+            idx = idx + self.first_global
         out = np.empty((idx.size, self.T, self.D), dtype=np.float64)
         _lib.check(self.lib.gsmc_get_trajectories(self.handle, _lib.iptr(idx), idx.size, _lib.dptr(out), out.size), self.handle)
         return out
@@ -217,14 +220,14 @@ class DeviceTraces:
     def __getitem__(self, i):
         if isinstance(i, slice):
             idx = np.arange(*i.indices(len(self)))
-            tr = self._state.trajectories(idx)
+            tr = self._state.trajectories(idx, local=True)
             return [DeviceTrace(self._state, int(j), tr[k]) for k, j in enumerate(idx)]
         i = int(i)
         if i < 0:
             i += len(self)
         if not 0 <= i < len(self):
             raise IndexError(i)
-        return DeviceTrace(self._state, i, self._state.trajectories([i])[0])
+        return DeviceTrace(self._state, i, self._state.trajectories([i], local=True)[0])
 
     def __iter__(self):
         for lo in range(0, len(self), 4096):

@@ -144,13 +144,16 @@ GSMC_API int gsmc_get_log_weights_device(gsmc_handle h, void** dev_ptr);
  * latent of time step t (1-based; 0 = current) for this rank's particles in their current
  * order, column-major [D][n_local], f64. t < current needs keep_history (walks ancestors). */
 GSMC_API int gsmc_get_state(gsmc_handle h, int64_t t, double* host_dst, size_t n_values);
-/* full trajectories of selected local particles: out[s][t][d], t = 1..num_steps */
+/* full trajectories of selected particles: out[s][t][d], t = 1..num_steps. idx holds GLOBAL particle indices
+ * (= local indices on an unsharded filter). Rows owned by other ranks of a sharded filter are read through the
+ * NVLink peer mappings; a call that asks for such rows is collective (every rank passes the same indices). */
 GSMC_API int gsmc_get_trajectories(gsmc_handle h, const int64_t* idx, size_t n_idx, double* out, size_t n_values);
 /* state.parents of the last resample (particle_filter.jl:200), global 0-based indices */
 GSMC_API int gsmc_get_ancestors(gsmc_handle h, int64_t* host_dst, size_t n);
 
 /* sample_unweighted_traces (src/inference/particle_filter.jl:62-70): num_samples categorical
- * draws from the normalised weights; returns local particle indices. */
+ * draws from the normalised weights; returns GLOBAL particle indices (every rank of a sharded filter makes
+ * the same call -- it is collective -- and receives the same indices). */
 GSMC_API int gsmc_sample_unweighted(gsmc_handle h, uint64_t num_samples, int64_t* idx_out);
 
 /* importance_sampling, both methods (src/inference/importance.jl:20-52). Returns a handle whose

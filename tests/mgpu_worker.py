@@ -65,6 +65,16 @@ def main():
         assert abs(a - b) <= 1e-11 * abs(b), (a, b)
         for t in (1, T // 2, T):
             assert np.array_equal(bits(st.state(t)), bits(pf.history(t)[:, sl])), "history differs at t=%d" % t
+        # sample_unweighted_traces (particle_filter.jl:62-70) on the sharded filter: collective, every rank gets the
+        # same GLOBAL indices as the oracle and reads the trajectories (its own rows and its peers') identically
+        ig, io = st.sample_unweighted(333), pf.sample_unweighted(333)
+        assert np.array_equal(ig, io), "sample_unweighted differs"
+        assert io.min() < n and io.max() >= (world - 1) * n, "the draw should touch the first and the last shard"
+        tr = st.trajectories(ig[:64])
+        for t in (1, T // 2, T):
+            assert np.array_equal(bits(tr[:, t - 1, :].T), bits(pf.history(t)[:, io[:64]])), "sampled trajectories differ at t=%d" % t
+        trs = g.sample_unweighted_traces(st, 7)
+        assert len(trs) == 7
         # the sync-free loop gives the same answer
         st2 = g.ParticleFilterState(model, N, seed=5, keep_history=False, device=local, comm=comm)
         st2.init([ys[0]], proposal)
