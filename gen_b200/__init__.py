@@ -4,7 +4,7 @@ include/gen_b200.h); this package is the Python mirror of the Julia host interfa
 from ._lib import GsmcError, load
 from .choicemap import ChoiceMap, NoChange, UnknownChange, choicemap, merge
 from .inference import (DeviceTrace, DeviceTraces, ParticleFilterState, get_log_weights, get_traces,
-                        importance_sampling, initialize_particle_filter, log_ml_estimate, maybe_resample_,
+                        importance_resampling, importance_sampling, initialize_particle_filter, log_ml_estimate, maybe_resample_,
                         maybe_resample_b, particle_filter_step_, particle_filter_step_b, sample_unweighted_traces)
 from .models import (HMM, BearingsOnly, DeviceModel, DeviceProposal, LinearGaussianSSM, LinearRegression, NormalNormal,
                      StochasticVolatility)

@@ -6,6 +6,7 @@ importance.jl; Python cannot spell `!`, so `particle_filter_step!` is `particle_
 The Julia spelling lives in julia/GenB200.jl.
 """
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -384,3 +385,59 @@ def importance_sampling(model, model_args, observations, *rest, **options):
     lw = state.log_weights()
     log_total = lml + float(np.log(num_samples))
     return DeviceTraces(state), lw - log_total, lml
+
+
+CHUNK_EVENT = 0xFFFFFFFF            # Philox event index of the chunk-merge draws of importance_resampling
+
+
+def chunk_seed(seed, c):
+    """Seed of chunk c of a chunked importance-sampling run (chunk 0 uses the seed itself)."""
+    return (int(seed) + c * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+
+def importance_resampling(model, model_args, observations, *rest, **options):
+    """(trace, lml_est) = importance_resampling(model, model_args, observations, num_samples, verbose=false)
+    (trace, lml_est) = importance_resampling(model, model_args, observations, proposal, proposal_args,
+                                             num_samples, verbose=false)                 (importance.jl:70-108)
+
+    Sampling importance resampling that returns ONE trace. The reference streams the samples one by one and keeps a
+    reservoir of size one (`bernoulli(exp(log_weight - log_total_weight))`), so its memory does not grow with
+    num_samples. Here the samples are generated `chunk_size` (option, default 2^24) at a time on the device; inside a
+    chunk the kept trace is one categorical draw from the chunk's weights (the distribution the reference's reservoir
+    has after the chunk), and chunks are merged with the reference's rule: the chunk's pick replaces the kept trace
+    with probability exp(chunk_log_total - log_total_so_far). Device memory is bounded by the chunk size."""
+    from . import philox
+    if len(rest) >= 3 and isinstance(rest[0], DeviceProposal):
+        head, num_samples = (rest[0], rest[1]), rest[2]
+        verbose = rest[3] if len(rest) > 3 else False
+    elif len(rest) >= 1:
+        head, num_samples = (), rest[0]
+        verbose = rest[1] if len(rest) > 1 else False
+    else:
+        raise TypeError("importance_resampling(model, model_args, observations[, proposal, proposal_args], num_samples, verbose=False)")
+    num_samples = int(num_samples)
+    if num_samples < 1:
+        raise _lib.GsmcError(_lib.E_BADARG, "num_samples must be >= 1")
+    options = dict(options)
+    chunk = int(options.pop("chunk_size", 1 << 24))
+    seed = int(options.pop("seed", 0))
+    options.pop("keep_history", None)
+    log_total, kept, done, c = -math.inf, None, 0, 0
+    while done < num_samples:
+        m = min(chunk, num_samples - done)
+        # state-space families: the kept trace is a whole trajectory, so the chunk keeps its history
+        extra = {} if model.family in (_lib.MODEL_REGRESSION, _lib.MODEL_NORMAL_NORMAL) else {"keep_history": True, "history_capacity": int(model_args[0])}
+        traces, _, lml_c = importance_sampling(model, model_args, observations, *head, m, seed=chunk_seed(seed, c), **extra, **options)
+        state = traces._state
+        lt_c = lml_c + math.log(m)
+        cand = traces[int(state.sample_unweighted(1)[0])]
+        new_total = lt_c if kept is None else float(np.logaddexp(log_total, lt_c))          # inference.jl:8-11
+        if kept is None or philox.uniform(seed, 2 * c, CHUNK_EVENT, philox.STREAM_SAMPLE) < math.exp(lt_c - new_total):
+            kept = cand
+        log_total = new_total
+        state.close()
+        done += m
+        c += 1
+        if verbose:
+            print("sample: %d of %d" % (done, num_samples))
+    return kept, log_total - math.log(num_samples)

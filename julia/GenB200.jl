@@ -226,6 +226,47 @@ function importance_sampling(model::DeviceSSM, model_args::Tuple, observations::
     (get_traces(state), get_log_weights(state) .- (lml + log(num_samples)), lml)
 end
 
-export LinearGaussianSSM, HMM, StochasticVolatility, DeviceProposal, DeviceParticleFilterState
+# importance.jl:70-87: sampling importance resampling that returns ONE trace. The reference keeps a reservoir of size
+# one while it streams the samples; here the samples are generated `chunk_size` at a time on the device, the kept trace
+# of a chunk is one categorical draw from the chunk's weights, and chunks are merged with the reference's rule
+# (`bernoulli(exp(log_weight - log_total_weight))` with the chunk's total in the place of one sample's weight).
+chunk_seed(seed::UInt64, c::Int) = seed + UInt64(c) * 0x9E3779B97F4A7C15
+function importance_resampling(model::DeviceSSM, model_args::Tuple, observations::ChoiceMap, num_samples::Int, verbose = false;
+                               seed::UInt64 = UInt64(0), chunk_size::Int = 1 << 24, kwargs...)
+    log_total, kept, done, c = -Inf, nothing, 0, 0
+    while done < num_samples
+        m = min(chunk_size, num_samples - done)
+        (traces, _, lml_c) = importance_sampling(model, model_args, observations, m; seed = chunk_seed(seed, c), keep_history = true, kwargs...)
+        lt_c = lml_c + log(m)
+        cand = sample_unweighted_traces(traces.state, 1)[1]
+        new_total = kept === nothing ? lt_c : logsumexp(log_total, lt_c)        # inference.jl:8-11
+        # the merge draw is host-side: Philox (seed, element 2c, event 0xffffffff, stream 3), see gen_b200/philox.py
+        if kept === nothing || philox_uniform(seed, 2 * c, 0xffffffff, 3) < exp(lt_c - new_total)
+            kept = cand
+        end
+        log_total = new_total
+        finalize(traces.state)                            # runs gsmc_destroy now: device memory stays bounded by one chunk
+        done += m
+        c += 1
+        verbose && println("sample: $done of $num_samples")
+    end
+    (kept, log_total - log(num_samples))
+end
+
+"Philox4x32-10 with the draw layout of gsmc_rng.cuh: element e of the uniform array of (seed, t, stream)."
+function philox_uniform(seed::UInt64, e::Int, t::Integer, stream::Integer)
+    call = UInt64(e >> 1)
+    c0, c1, c2, c3 = UInt32(call & 0xffffffff), UInt32(call >> 32), UInt32(t), UInt32(stream)
+    k0, k1 = UInt32(seed & 0xffffffff), UInt32(seed >> 32)
+    for _ in 1:10
+        p0, p1 = UInt64(0xD2511F53) * c0, UInt64(0xCD9E8D57) * c2
+        c0, c1, c2, c3 = UInt32(p1 >> 32) ⊻ c1 ⊻ k0, UInt32(p1 & 0xffffffff), UInt32(p0 >> 32) ⊻ c3 ⊻ k1, UInt32(p0 & 0xffffffff)
+        k0 += 0x9E3779B9; k1 += 0xBB67AE85
+    end
+    w = isodd(e) ? (UInt64(c2) | (UInt64(c3) << 32)) : (UInt64(c0) | (UInt64(c1) << 32))
+    Float64(w >> 11) * 2.0^-53
+end
+
+export LinearGaussianSSM, HMM, StochasticVolatility, DeviceProposal, DeviceParticleFilterState, importance_resampling
 
 end # module

@@ -439,3 +439,55 @@ def test_large_n_properties(gpu):
         vals.append(st.log_ml_estimate())
     assert vals[0] == vals[1]
     assert vals[0] == pytest.approx(cf.kalman_log_ml(ys, *LG), abs=0.05)
+
+
+def test_importance_resampling(gpu, orc):
+    """importance.jl:70-108 (SIR returning one trace). One chunk: the kept trace is the oracle's categorical draw
+    from the importance weights; several chunks: merged with the reference's reservoir rule, restated here with the
+    oracle's own Philox."""
+    import math
+    g = gpu
+    from gen_b200 import inference as inf
+    from gen_b200 import philox
+    T, n = 6, 5000
+    model, params, ys = make_model(g, O.LGSSM)
+    obs = g.choicemap(("y_init", float(ys[0])), *[(("chain", t, "y"), float(ys[t])) for t in range(1, T)])
+
+    def oracle_chunk(seed, m):
+        pf = orc.particle_filter(O.LGSSM, params, m, seed=seed, keep_history=True)
+        pf.init([ys[0]])
+        for t in range(1, T):
+            pf.step([ys[t]])
+        j = int(pf.sample_unweighted(1)[0])
+        traj = np.array([pf.history(t)[0, j] for t in range(1, T + 1)])
+        return pf.log_ml_estimate() + math.log(m), j, traj
+
+    # one chunk
+    tr, lml = g.importance_resampling(model, (T,), obs, n, seed=11)
+    lt, j, traj = oracle_chunk(11, n)
+    assert tr.index == j
+    assert np.array_equal(np.array([tr[("chain", t, "x")] if t > 0 else tr["x_init"] for t in range(T)]), traj)
+    assert lml == pytest.approx(lt - math.log(n), rel=1e-12)
+    assert tr[("chain", 2, "y")] == ys[2]
+    # three chunks of at most 2048 samples
+    tr3, lml3 = g.importance_resampling(model, (T,), obs, n, seed=11, chunk_size=2048)
+    total, kept = -math.inf, None
+    for c, m in enumerate((2048, 2048, n - 4096)):
+        lt, j, traj = oracle_chunk(inf.chunk_seed(11, c), m)
+        new_total = lt if kept is None else float(np.logaddexp(total, lt))
+        u = orc.uniforms(11, inf.CHUNK_EVENT, O.STREAM_SAMPLE, 2 * c, 1)[0]
+        assert u == philox.uniform(11, 2 * c, inf.CHUNK_EVENT, philox.STREAM_SAMPLE)
+        if kept is None or u < math.exp(lt - new_total):
+            kept = (j, traj)
+        total = new_total
+    assert tr3.index == kept[0]
+    assert np.array_equal(np.array([tr3[("chain", t, "x")] if t > 0 else tr3["x_init"] for t in range(T)]), kept[1])
+    assert lml3 == pytest.approx(total - math.log(n), rel=1e-12)
+    assert lml3 == pytest.approx(cf.kalman_log_ml(ys[:T], *LG), abs=0.2)
+    # custom proposal + a non-state-space family
+    reg = g.LinearRegression()
+    cm = g.choicemap(*[("y-%d" % (i + 1), v) for i, v in enumerate([-3.9, -2.1, 0.2, 1.8, 4.1])])
+    tr, lml = g.importance_resampling(reg, ([-2.0, -1.0, 0.0, 1.0, 2.0],), cm, 4000, seed=3)
+    assert math.isfinite(lml) and "slope" in tr.get_choices()
+    trq, lmlq = g.importance_resampling(reg, ([-2.0, -1.0, 0.0, 1.0, 2.0],), cm, reg.custom_proposal(2.0, 0.5, 0.0, 1.0), (), 4000, seed=3)
+    assert math.isfinite(lmlq) and abs(lmlq - lml) < 0.5

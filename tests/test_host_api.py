@@ -55,5 +55,5 @@ def test_regression_binding_and_observations():
 def test_api_surface_matches_reference_exports():
     """src/inference/particle_filter.jl:215-216 and importance.jl:110."""
     for name in ("initialize_particle_filter", "particle_filter_step_b", "maybe_resample_b", "get_traces",
-                 "get_log_weights", "log_ml_estimate", "sample_unweighted_traces", "importance_sampling"):
+                 "get_log_weights", "log_ml_estimate", "sample_unweighted_traces", "importance_sampling", "importance_resampling"):
         assert callable(getattr(g, name))
