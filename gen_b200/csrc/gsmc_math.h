@@ -78,7 +78,7 @@ static const double gm_exp2tab_h[64] = GM_EXP2TAB_VALUES;
 static const double gm_sincostab_h[256] = GM_SINCOSTAB_VALUES;
 #if defined(__CUDACC__)
 static __device__ const double gm_exp2tab_g[64] = GM_EXP2TAB_VALUES;
-static __device__ const double gm_sincostab_g[256] = GM_SINCOSTAB_VALUES;
+static __device__ __align__(16) const double gm_sincostab_g[256] = GM_SINCOSTAB_VALUES;
 #endif
 #if defined(__CUDA_ARCH__)
 #define GM_EXP2TAB gm_exp2tab_g
@@ -100,6 +100,15 @@ GM_HD uint64_t gm_to_bits(double d) {
   return (uint64_t)__double_as_longlong(d);
 #else
   uint64_t b; memcpy(&b, &d, 8); return b;
+#endif
+}
+/* the two adjacent table entries tab[2i], tab[2i+1] with ONE 16-byte load on the device (all pair tables are 16-byte aligned) */
+GM_HD void gm_tab_pair(const double* tab, int i, double* a, double* b) {
+#if defined(__CUDA_ARCH__)
+  const double2 v = *reinterpret_cast<const double2*>(tab + 2 * i);
+  *a = v.x; *b = v.y;
+#else
+  *a = tab[2 * i]; *b = tab[2 * i + 1];
 #endif
 }
 /* (double)w for a 32-bit unsigned w, exactly, without an int->float conversion instruction: 2^52 + w has w in its low word */
@@ -300,8 +309,8 @@ GM_HD double gm_atan2(double y, double x) {
   0.5245901639344263, 0.6451379613735847, 0.5079365079365079, 0.6773988235918061 }
 static const double gm_logtab_h[32] = GM_LOGTAB_VALUES;
 #if defined(__CUDACC__)
-static __constant__ double gm_logtab_d[32] = GM_LOGTAB_VALUES;
-static __device__ const double gm_logtab_g[32] = GM_LOGTAB_VALUES;      /* global-memory copy: coalesced staging into shared memory */
+static __constant__ __align__(16) double gm_logtab_d[32] = GM_LOGTAB_VALUES;
+static __device__ __align__(16) const double gm_logtab_g[32] = GM_LOGTAB_VALUES;      /* global-memory copy: coalesced staging into shared memory */
 #endif
 // tab: the 32-entry table (shared-memory copy on the device when lanes index it divergently)
 GM_HD double gm_log_tab(double x, const double* tab) {
@@ -365,8 +374,8 @@ GM_HD double gm_log_tab(double x, const double* tab) {
   0.50592885375494068, 0.68135922480790312, 0.50196078431372548, 0.689233281238809 }
 static const double gm_logtab64_h[128] = GM_LOGTAB64_VALUES;
 #if defined(__CUDACC__)
-static __constant__ double gm_logtab64_d[128] = GM_LOGTAB64_VALUES;
-static __device__ const double gm_logtab64_g[128] = GM_LOGTAB64_VALUES;
+static __constant__ __align__(16) double gm_logtab64_d[128] = GM_LOGTAB64_VALUES;
+static __device__ __align__(16) const double gm_logtab64_g[128] = GM_LOGTAB64_VALUES;
 #endif
 // tab: the 128-entry table (shared-memory copy on the device: lanes index it divergently)
 GM_HD double gm_log_unit(double x, const double* tab) {
@@ -455,8 +464,9 @@ template <int K> GM_HD void gm_log_tab_v(const double* x, const double* tab, dou
     const int idx = (int)((b >> 48) & 15);
     const double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
     ef[k] = (double)((int)(b >> 52) - 1023);
-    r[k] = fma(m, tab[2 * idx], -1.0);
-    c[k] = tab[2 * idx + 1];
+    double ic;
+    gm_tab_pair(tab, idx, &ic, &c[k]);
+    r[k] = fma(m, ic, -1.0);
     p[k] = 1.4285714285714285e-01;
   }
   GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -1.6666666666666666e-01);
@@ -475,8 +485,9 @@ template <int K> GM_HD void gm_log_unit_v(const double* x, const double* tab, do
     const int idx = (int)((b >> 46) & 63);
     const double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
     ef[k] = (double)((int)(b >> 52) - 1023);
-    r[k] = fma(m, tab[2 * idx], -1.0);
-    c[k] = tab[2 * idx + 1];
+    double ic;
+    gm_tab_pair(tab, idx, &ic, &c[k]);
+    r[k] = fma(m, ic, -1.0);
     p[k] = 1.4285714285714285e-01;
   }
   GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -1.6666666666666666e-01);
@@ -509,7 +520,8 @@ template <int K> GM_HD void gm_sincospi_v(const double* t, double* sn, double* c
     const double sx = fma(x[k] * z[k], ps[k], x[k]);
     const double cm = z[k] * pc[k];
     const int j = (int)((uint32_t)gm_to_bits(zz[k]) & 127u);
-    const double S = tab[2 * j], C = tab[2 * j + 1];
+    double S, C;
+    gm_tab_pair(tab, j, &S, &C);
     sn[k] = S + fma(S, cm, C * sx);
     cs[k] = C + fma(C, cm, -(S * sx));
   }

@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const 
   typedef typename Vec2T<Real>::type Real2;
   constexpr int W = GSMC_WPT;
   __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
-  __shared__ double ltab[32];
+  __shared__ __align__(16) double ltab[32];
   __shared__ double etab[64];
   if (SPACINGS && threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_g[threadIdx.x];
   if (WEIGHTS && threadIdx.x >= 64 && threadIdx.x < 128) etab[threadIdx.x - 64] = gm_exp2tab_g[threadIdx.x - 64];
