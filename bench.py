@@ -250,7 +250,8 @@ def run_ours(args):
         "log_ml": lml, "log_ml_kalman": kalman(ys), "log_ml_e2e": lml_e2e,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 8 * T,
-                "d2h_bytes_per_step": 8 + T * 1432, "ms_per_step": e_ms / reps,
+                "d2h_bytes_per_step": 8 + T * 432,   # one copy of the device scalars (432 B) per maybe_resample!, the log-ML double at the end
+                "ms_per_step": e_ms / reps,
                 "note": "Gen-API mirror; includes cudaMalloc of the trace slabs, one D2H of the device scalars per maybe_resample!"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "propagate_kernel<LgssmModel>", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -526,7 +526,7 @@ static int peer_barrier(gsmc_filter* f) {
 }
 
 static int fetch_scalars(gsmc_filter* f) {
-  CK(cudaMemcpyAsync(f->h_ds, f->ds, sizeof(DevScalars), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaMemcpyAsync(f->h_ds, f->ds, offsetof(DevScalars, mbox), cudaMemcpyDeviceToHost, f->stream));   // the scalars, not the mailboxes
   CK(cudaStreamSynchronize(f->stream));
   return GSMC_OK;
 }
@@ -594,7 +594,9 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
   const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
   const bool fuse_spacings = !residual && !replay_iid;
-  const bool fuse_scan = fuse_spacings && f->nranks == 1;       // the partition kernel scans the segment totals itself
+  // the partition kernel scans the segment totals itself and, on a sharded filter, exchanges the ranks' totals
+  // over the peer mailboxes; with GSMC_NCCL_SCALARS=1 the separate scan + ncclAllGather path is used instead
+  const bool fuse_scan = fuse_spacings && (f->nranks == 1 || !f->use_nccl_scalars);
   // 1. integer weights -> segment-local CDF + segment totals (and, fused, the spacings of the N draws)
   if (fuse_spacings) {
     ProfScope ps(f, KC_SCAN);
@@ -640,10 +642,13 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     { ProfScope ps(f, KC_SEARCH);
       const int need = (nt + 1 + 31) / 32;
       const int grid = need < 2 * f->sm_count ? need : 2 * f->sm_count;      // one wave of 1024-thread blocks
+      PeerScalars peers;
+      for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
+      if (fuse_scan && f->nranks > 1) f->xchg_seq += 1;
       if (fuse_scan) CK(launch_pdl(partition_kernel<true>, grid, 1024, 0, f->stream, v, f->cfg.seed, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
-                                   f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional));
+                                   f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq));
       else CK(launch_pdl(partition_kernel<false>, grid, 1024, 0, f->stream, v, f->cfg.seed, k_first, f->rank, f->ds, nullptr, nullptr, sp_q, f->seg_e,
-                         f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional)); }
+                         f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq)); }
     { static bool attr_set = false;
       if (!attr_set) { CK(cudaFuncSetAttribute((const void*)search_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMC_SEARCH_SMEM)); attr_set = true; }
       int occ = 0;
@@ -871,7 +876,7 @@ GSMC_API int gsmc_maybe_resample(gsmc_handle f, double ess_threshold, int* did_r
   // The decision lives on the device. Copy it out, and -- unless exported uniforms are being replayed --
   // enqueue the resampling kernels right away in their conditional form (they exit at once when no
   // resample was decided), so the GPU never idles while the host reads the Bool this call returns.
-  CK(cudaMemcpyAsync(f->h_ds, f->ds, sizeof(DevScalars), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaMemcpyAsync(f->h_ds, f->ds, offsetof(DevScalars, mbox), cudaMemcpyDeviceToHost, f->stream));   // the scalars, not the mailboxes
   CK(cudaEventRecord(f->decision_ev, f->stream));
   if (!replay) CKRC(launch_resample(f, 1, false));
   CK(cudaEventSynchronize(f->decision_ev));

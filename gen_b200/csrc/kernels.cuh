@@ -71,24 +71,25 @@ struct DevScalars {
   LseTriple triples[GSMC_MAX_RANKS];
   uint64_t cdf_rank_total[GSMC_MAX_RANKS];      // per-rank integer weight totals (allgathered)
   uint64_t spacing_rank_total[GSMC_MAX_RANKS];  // per-rank spacing totals (allgathered)
-  // LL mailboxes for the fused peer-memory exchange: [parity][source rank][word]; a word is
+  // LL mailboxes for the fused peer-memory exchange: [sequence mod 4][source rank][word]; a word is
   // (payload 32 bit) | (sequence number << 32), written by the source rank with one 8-byte store.
-  unsigned long long mbox[2][GSMC_MAX_RANKS][8];
+  unsigned long long mbox[4][GSMC_MAX_RANKS][8];
 };
 
 // Peer-memory exchange of a few scalars between the ranks (one kernel per GPU, each GPU's kernel only
 // waits for stores issued by the OTHER GPUs' kernels). Every rank writes its payload, 32 bits per
 // 8-byte word tagged with the sequence number, straight into every peer's mailbox over NVLink
 // (no fence needed: data and tag arrive in one atomic store, as in NCCL's LL protocol); a reader spins
-// on the tag. Mailboxes alternate by sequence parity, which is enough because a rank can be at most
-// one exchange ahead of any other. The spin is bounded (~2 s) so a lost peer cannot hang the GPU.
+// on the tag. Four mailboxes are used in turn (sequence number mod 4): every step has one exchange that nobody
+// skips (the logsumexp triples), so a rank is never more than two exchanges ahead of a peer that has not read
+// its words yet. The spin is bounded (~2 s) so a lost peer cannot hang the GPU.
 struct PeerScalars { DevScalars* ds[GSMC_MAX_RANKS]; };
 __device__ __forceinline__ void ll_send(DevScalars* peer, int my_rank, uint32_t seq, const uint32_t* words, int n) {
-  volatile unsigned long long* box = peer->mbox[seq & 1][my_rank];
+  volatile unsigned long long* box = peer->mbox[seq & 3][my_rank];
   for (int w = 0; w < n; ++w) box[w] = (unsigned long long)words[w] | ((unsigned long long)seq << 32);
 }
 __device__ __forceinline__ bool ll_recv(DevScalars* self, int src, uint32_t seq, uint32_t* words, int n) {
-  volatile unsigned long long* box = self->mbox[seq & 1][src];
+  volatile unsigned long long* box = self->mbox[seq & 3][src];
   const long long t0 = clock64();
   for (int w = 0; w < n; ++w) {
     unsigned long long v;
@@ -733,19 +734,9 @@ __device__ __forceinline__ void finish_totals(DevScalars* ds, int nranks, uint64
   }
 }
 
-// The segment prefixes are kept as GLOBAL prefixes: the totals of the lower ranks are added once here, so
-// that every consumer (and every peer) reads C_i = sp[segment] + cl[i] without a rank-offset loop.
-__device__ __forceinline__ void globalise_prefixes(uint64_t* a0, uint64_t* a1, int n_segs, const DevScalars* ds, int what, int rank) {
-  uint64_t off_q = 0, off_e = 0;
-  for (int r = 0; r < rank; ++r) { off_q += ds->cdf_rank_total[r]; off_e += ds->spacing_rank_total[r]; }
-  uint64_t* aq = (what & SCAN_Q) ? a0 : nullptr;
-  uint64_t* ae = (what & SCAN_E) ? ((what & SCAN_Q) ? a1 : a0) : nullptr;
-  for (int i = threadIdx.x; i <= n_segs; i += blockDim.x) {
-    if (aq) aq[i] += off_q;
-    if (ae) ae[i] += off_e;
-  }
-}
-
+// The segment prefixes stay RANK-LOCAL (they are final before a rank announces its totals, so a peer that has
+// received the totals can read them without a further handshake); consumers add the integer weight of the lower
+// ranks, off_r = sum of cdf_rank_total[0..r), themselves: C_i = off_r + sp[segment(i)] + cl[i].
 // Block-wide exclusive scans of up to two arrays of n_segs <= 1024 segment totals (one element per thread
 // of a 1024-thread block): out0/out1[i] = exclusive prefix, out[n_segs] = total. out may be shared or global.
 __device__ __forceinline__ void scan_segments_block(const uint64_t* in0, const uint64_t* in1, int n_segs, uint64_t* out0, uint64_t* out1,
@@ -798,6 +789,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
   const int n64 = ((what & SCAN_Q) ? 1 : 0) + ((what & SCAN_E) ? 1 : 0);
   uint64_t totals[2] = {0, 0};
   if (!skip) scan_segments_block(in0, in1, n_segs, out0, out1, sm, totals);
+  __threadfence_system();                            // the (rank-local) prefixes are visible to the peers before the totals are sent
   // this rank's totals: the weights' first when both are present
   if (threadIdx.x == 0) {
     int k = 0;
@@ -820,18 +812,12 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
     }
   }
   if (threadIdx.x == 0 && !skip) finish_totals(ds, nranks, seed, n_global, what, totals[0], totals[1]);
-  if (nranks > 1 && !skip) {
-    __syncthreads();
-    globalise_prefixes(out0, out1, n_segs, ds, what, rank);
-  }
 }
 // multi-rank runs that exchange the totals with ncclAllGather (GSMC_NCCL_SCALARS=1) finish here
 __global__ void __launch_bounds__(1024) totals_kernel(uint64_t* a0, uint64_t* a1, int n_segs, DevScalars* ds, int nranks, int rank,
                                                       uint64_t seed, uint64_t n_global, int what, int conditional) {
   if (conditional && !ds->do_resample) return;
   if (threadIdx.x == 0) finish_totals(ds, nranks, seed, n_global, what, 0, 0);
-  __syncthreads();
-  if (nranks > 1) globalise_prefixes(a0, a1, n_segs, ds, what, rank);
 }
 
 // residual scheme: e_i = floor(q_i * resid_scale); c_i = e_i >> 32 copies; r_i = e_i & (2^32-1)
@@ -926,23 +912,30 @@ __device__ __forceinline__ int upper_pred_warp(const uint64_t* arr, int len, uin
   }
   return lo;
 }
+// integer weight of the ranks before r
+__device__ __forceinline__ uint64_t rank_offset(const DevScalars* ds, int r) {
+  uint64_t off = 0;
+  for (int q = 0; q < r; ++q) off += ds->cdf_rank_total[q];
+  return off;
+}
 // Ancestor word of a threshold against the global CDF: min{i : gt(C_i)}, clamped to the last particle.
 // Three levels: owner rank (its inclusive end passes the predicate), segment, position in the segment.
 template <bool WARP, class P>
 __device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevScalars* ds, const P gt) {
-  uint64_t end = 0;
+  uint64_t off = 0;                               // integer weight of the ranks before r: C_i = off + sp[segment] + cl[i]
   int r = 0;
   for (; r < v.nranks - 1; ++r) {
-    end += ds->cdf_rank_total[r];
+    const uint64_t end = off + ds->cdf_rank_total[r];
     if (gt(end)) break;
+    off = end;
   }
-  const uint64_t* sp = v.sp[r];                   // global exclusive prefixes of rank r's segments
-  const int s = WARP ? upper_pred_warp(sp + 1, v.n_segs, 0, gt) : upper_pred(sp + 1, v.n_segs, 0, gt);
+  const uint64_t* sp = v.sp[r];                   // rank-local exclusive prefixes of rank r's segments
+  const int s = WARP ? upper_pred_warp(sp + 1, v.n_segs, off, gt) : upper_pred(sp + 1, v.n_segs, off, gt);
   int64_t j = v.n_per - 1;
   if (s < v.n_segs) {
     const int64_t first = (int64_t)s * v.seg_len;
     const int len = (int)(first + v.seg_len <= v.n_pad ? v.seg_len : v.n_pad - first);
-    const uint64_t add = __ldg(sp + s);
+    const uint64_t add = off + __ldg(sp + s);
     j = first + (WARP ? upper_pred_warp(v.seg[r] + first, len, add, gt) : upper_pred(v.seg[r] + first, len, add, gt));
     if (j > v.n_per - 1) j = v.n_per - 1;
   }
@@ -965,69 +958,99 @@ template <bool FUSED_SCAN>
 __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank, DevScalars* ds,
                                                          const uint64_t* raw_q, const uint64_t* raw_e, uint64_t* sp_q, uint64_t* sp_e,
                                                          uint64_t* tile_e, int seg_tiles, const uint32_t* esp, int nt, uint32_t* win,
-                                                         uint64_t n_global, int conditional) {
+                                                         uint64_t n_global, int conditional, PeerScalars peers, uint32_t seq) {
   __shared__ uint64_t spq[GSMC_MAX_SEGS + 1];
   __shared__ uint64_t spe[GSMC_MAX_SEGS + 1];
   __shared__ uint64_t sm[2][33];
   __shared__ double s_thr[2];
   __shared__ uint64_t s_draws;
+  __shared__ uint64_t off_q[GSMC_MAX_RANKS + 1], off_e[GSMC_MAX_RANKS + 1];   // exclusive prefixes of the ranks' totals, [R] = sum
+  __shared__ uint64_t tot_q[GSMC_MAX_RANKS], tot_e[GSMC_MAX_RANKS];
   pdl_wait();
   pdl_trigger();
-  if (conditional && !ds->do_resample) return;
-  const int n_segs = v.n_segs;
+  if (conditional && !ds->do_resample) return;          // every rank takes the same decision: nobody sends, nobody waits
+  const int n_segs = v.n_segs, R = v.nranks;
   if (FUSED_SCAN) {
     uint64_t totals[2];
     scan_segments_block(raw_q, raw_e, n_segs, spq, spe, sm, totals);
+    if (R > 1) {
+      // Block 0 publishes this rank's (rank-local) segment prefixes and then sends its two totals to every peer;
+      // every block of every rank reads all totals from its own mailboxes. A peer that has seen rank r's totals
+      // may read r's prefixes and CDF: they were complete (and fenced) before the send.
+      if (blockIdx.x == 0) {
+        if (threadIdx.x <= n_segs) { sp_q[threadIdx.x] = spq[threadIdx.x]; sp_e[threadIdx.x] = spe[threadIdx.x]; }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < R) {
+          const uint32_t w[4] = {(uint32_t)totals[0], (uint32_t)(totals[0] >> 32), (uint32_t)totals[1], (uint32_t)(totals[1] >> 32)};
+          __threadfence_system();
+          ll_send(peers.ds[threadIdx.x], rank, seq, w, 4);
+        }
+      }
+      if (threadIdx.x < R) {
+        uint32_t g[4];
+        if (!ll_recv(ds, threadIdx.x, seq, g, 4)) { ds->error = 2; g[0] = g[1] = g[2] = g[3] = 0; }
+        tot_q[threadIdx.x] = (uint64_t)g[0] | ((uint64_t)g[1] << 32);
+        tot_e[threadIdx.x] = (uint64_t)g[2] | ((uint64_t)g[3] << 32);
+      }
+    } else if (threadIdx.x == 0) { tot_q[0] = totals[0]; tot_e[0] = totals[1]; }
+    __syncthreads();
     if (threadIdx.x == 0) {
-      const uint64_t stot = totals[1] + spacing_one(seed, n_global, ds->rho, gm_logtab_d);
-      const double cn = (double)totals[0];
+      uint64_t aq = 0, ae = 0;
+      for (int r = 0; r < R; ++r) { off_q[r] = aq; off_e[r] = ae; aq += tot_q[r]; ae += tot_e[r]; }
+      off_q[R] = aq; off_e[R] = ae;
+      const uint64_t stot = ae + spacing_one(seed, n_global, ds->rho, gm_logtab_d);
+      const double cn = (double)aq;
       s_thr[0] = cn / (double)stot;
       s_thr[1] = cn > 0.0 ? gm_from_bits(gm_to_bits(cn) - 1) : 0.0;
       s_draws = n_global;
       if (blockIdx.x == 0) {
-        ds->cdf_rank_total[0] = totals[0]; ds->spacing_rank_total[0] = totals[1];
-        ds->cdf_total = totals[0]; ds->n_draws = n_global; ds->n_det = 0;
+        for (int r = 0; r < R; ++r) { ds->cdf_rank_total[r] = tot_q[r]; ds->spacing_rank_total[r] = tot_e[r]; }
+        ds->cdf_total = aq; ds->n_draws = n_global; ds->n_det = 0;
         ds->spacing_total = stot; ds->thr_ratio = s_thr[0]; ds->thr_max = s_thr[1];
       }
     }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x <= n_segs) { sp_q[threadIdx.x] = spq[threadIdx.x]; sp_e[threadIdx.x] = spe[threadIdx.x]; }
+    if (R == 1 && blockIdx.x == 0 && threadIdx.x <= n_segs) { sp_q[threadIdx.x] = spq[threadIdx.x]; sp_e[threadIdx.x] = spe[threadIdx.x]; }
   } else {
     if (threadIdx.x <= n_segs) { spq[threadIdx.x] = sp_q[threadIdx.x]; spe[threadIdx.x] = sp_e[threadIdx.x]; }
-    if (threadIdx.x == 0) { s_thr[0] = ds->thr_ratio; s_thr[1] = ds->thr_max; s_draws = ds->n_draws; }
+    if (threadIdx.x == 0) {
+      s_thr[0] = ds->thr_ratio; s_thr[1] = ds->thr_max; s_draws = ds->n_draws;
+      uint64_t aq = 0, ae = 0;
+      for (int r = 0; r < R; ++r) { off_q[r] = aq; off_e[r] = ae; aq += ds->cdf_rank_total[r]; ae += ds->spacing_rank_total[r]; }
+      off_q[R] = aq; off_e[R] = ae;
+    }
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
   const uint64_t m_draws = s_draws;
   const double ratio = s_thr[0], tmax = s_thr[1];
+  const uint64_t my_e = off_e[rank];
   for (int b = blockIdx.x * 32 + (threadIdx.x >> 5); b <= nt; b += gridDim.x * 32) {
     const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
-    uint32_t w = ((uint32_t)(v.nranks - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
+    uint32_t w = ((uint32_t)(R - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
     uint64_t S;
     if (b < nt) {
-      const uint64_t S0 = spe[b / seg_tiles] + tile_e[b];
+      const uint64_t S0 = my_e + spe[b / seg_tiles] + tile_e[b];
       __syncwarp();
-      if (lane == 0) tile_e[b] = S0;
+      if (lane == 0) tile_e[b] = S0;                     // tile_e becomes the GLOBAL spacing prefix before tile b
       S = S0 + (uint64_t)esp[(int64_t)b * GSMC_TILE];
     } else {
       // the closing boundary: first threshold of the next rank
-      S = spe[n_segs] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
+      S = my_e + spe[n_segs] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
     }
     if (kt < m_draws) {
       GtF64 gt; gt.t = sorted_threshold(S, ratio, tmax);
-      uint64_t end = 0;
       int r = 0;
-      for (; r < v.nranks - 1; ++r) {
-        end += ds->cdf_rank_total[r];
-        if (gt(end)) break;
-      }
+      for (; r < R - 1; ++r) if (gt(off_q[r + 1])) break;
+      const uint64_t off = off_q[r];
       const uint64_t* sp = (r == rank) ? spq : v.sp[r];      // own prefixes from shared memory, a peer's over NVLink
-      const int sg = upper_pred_warp(sp + 1, n_segs, 0, gt);
+      const int sg = upper_pred_warp(sp + 1, n_segs, off, gt);
       int64_t j = v.n_per - 1;
       if (sg < n_segs) {
         const int64_t first = (int64_t)sg * v.seg_len;
         const int len = (int)(first + v.seg_len <= v.n_pad ? v.seg_len : v.n_pad - first);
-        j = first + upper_pred_warp(v.seg[r] + first, len, sp[sg], gt);
+        j = first + upper_pred_warp(v.seg[r] + first, len, off + sp[sg], gt);
         if (j > v.n_per - 1) j = v.n_per - 1;
       }
       w = ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
@@ -1135,6 +1158,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
     if (staged) {
       // C_i = sp[segment(i)] + cl[i] with global segment prefixes; segment(i) = (i / 1024) / seg_tiles by multiply-high
       const uint64_t* sp_a = v.sp[r0];
+      const uint64_t roff_a = rank_offset(ds, r0);       // rank-local prefixes: C_i = roff + sp[segment(i)] + cl[i]
       if (bulk) {
         mbar_wait(&mbar, phase);
         phase ^= 1;
@@ -1142,7 +1166,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
         const uint32_t tl0 = (uint32_t)lo >> GSMC_TILE_SHIFT, tl1 = (uint32_t)(lo + la - 1) >> GSMC_TILE_SHIFT;
         const uint32_t sg0 = seg_tiles == 1 ? tl0 : __umulhi(tl0, seg_magic), sg1 = seg_tiles == 1 ? tl1 : __umulhi(tl1, seg_magic);
         if (sg0 == sg1) {                                  // the usual case: the whole window lies in one segment
-          const uint64_t add = __ldg(sp_a + sg0);
+          const uint64_t add = roff_a + __ldg(sp_a + sg0);
 #pragma unroll 4
           for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) cwin[off + j] = (double)(add + raw[j]);
         } else {
@@ -1150,7 +1174,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
           for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
             const uint32_t tl = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
             const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
-            cwin[off + j] = (double)(__ldg(sp_a + sg) + raw[j]);
+            cwin[off + j] = (double)(roff_a + __ldg(sp_a + sg) + raw[j]);
           }
         }
       } else {
@@ -1159,15 +1183,16 @@ __global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v,
         for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
           const uint32_t tl = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
           const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
-          cwin[j] = (double)(__ldg(sp_a + sg) + __ldg(seg_a + j));
+          cwin[j] = (double)(roff_a + __ldg(sp_a + sg) + __ldg(seg_a + j));
         }
         if (len_b) {
           const uint64_t* seg_b = v.seg[r1];
           const uint64_t* sp_b = v.sp[r1];
+          const uint64_t roff_b = rank_offset(ds, r1);
           for (int j = threadIdx.x; j < (int)len_b; j += GSMC_BLOCK) {
             const uint32_t tl = (uint32_t)j >> GSMC_TILE_SHIFT;
             const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
-            cwin[la + j] = (double)(__ldg(sp_b + sg) + __ldg(seg_b + j));
+            cwin[la + j] = (double)(roff_b + __ldg(sp_b + sg) + __ldg(seg_b + j));
           }
         }
       }
