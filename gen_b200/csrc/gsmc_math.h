@@ -115,6 +115,14 @@ GM_HD void gm_tab_pair(const double* tab, int i, double* a, double* b) {
 GM_HD double gm_u32_to_f64(uint32_t w) { return gm_from_bits(0x4330000000000000ULL | (uint64_t)w) - 4503599627370496.0; }
 GM_HD double gm_inf(void) { return gm_from_bits(GM_INF_BITS); }
 GM_HD double gm_nan(void) { return gm_from_bits(0x7ff8000000000000ULL); }
+/* p * 2^k by an integer add on the exponent field (the caller guarantees a normal result) */
+GM_HD double gm_scale_pow2(double p, int k) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+  return gm_from_bits(gm_to_bits(p) + ((uint64_t)(long long)k << 52));
+#endif
+}
 GM_HD double gm_pow2(int k) { return gm_from_bits((uint64_t)(k + 1023) << 52); }  /* -1022<=k<=1023 */
 
 // exp(x) = 2^k 2^(j/64) e^r with x = (64 k + j) ln2/64 + r, |r| <= ln2/128: table value T_j times a
@@ -154,10 +162,10 @@ GM_HD double gm_exp(double x) {
 // is one integer add on the exponent field (the result is normal or flushed to 0, never subnormal).
 // Used for exp(lw - max): logsumexp partials and the integer weights of the resampler.
 GM_HD double gm_exp_nonpos_t(double x, const double* tab) {
-  const double xc = x < -708.3964185322641 ? -708.0 : x;
+  /* below the flush threshold (down to -inf) the reduced evaluation yields garbage that is never used: no clamp */
   long long k;
-  const double p = gm_exp_core(xc, tab, &k);
-  const double v = gm_from_bits(gm_to_bits(p) + ((uint64_t)k << 52));
+  const double p = gm_exp_core(x, tab, &k);
+  const double v = gm_scale_pow2(p, (int)k);
   return x < -708.3964185322641 ? 0.0 : v;
 }
 GM_HD double gm_exp_nonpos(double x) { return gm_exp_nonpos_t(x, GM_EXP2TAB); }
@@ -203,11 +211,21 @@ GM_HD double gm_log_pos(double x) { return gm_log_core(gm_to_bits(x), 0); }
 // gives the correctly rounded quotient, i.e. the same bits as the IEEE division the reference
 // formula performs (tests/test_math.py checks 10^7 adversarial operand pairs). Outside the safe
 // magnitude range (zero, subnormal results, inf, nan) or when rc == 0 it falls back to x / c.
-GM_HD double gm_div_inv(double x, double c, double rc) {
+#define GM_DIV_SPAN (0x7c200000u - 0x03c00000u)
+/* span = GM_DIV_SPAN when rc is usable, 0 (= always take the true division) otherwise: gm_div_span(rc) */
+GM_HD double gm_div_inv_s(double x, double c, double rc, uint32_t span) {
   /* safe range 2^-963 <= |x| < 2^963, tested on the exponent field with one integer compare
      (0, subnormal, inf and nan fall outside) */
   const uint32_t hx = (uint32_t)(gm_to_bits(x) >> 32) & 0x7fffffffu;
-  if (hx - 0x03c00000u >= 0x7c200000u - 0x03c00000u || rc == 0.0) return x / c;
+  if (hx - 0x03c00000u >= span) return x / c;
+  const double q0 = x * rc;
+  const double r = fma(-q0, c, x);
+  return fma(r, rc, q0);
+}
+GM_HD uint32_t gm_div_span(double rc) { return rc == 0.0 ? 0u : GM_DIV_SPAN; }
+GM_HD double gm_div_inv(double x, double c, double rc) {
+  const uint32_t hx = (uint32_t)(gm_to_bits(x) >> 32) & 0x7fffffffu;
+  if (hx - 0x03c00000u >= GM_DIV_SPAN || rc == 0.0) return x / c;
   const double q0 = x * rc;
   const double r = fma(-q0, c, x);
   return fma(r, rc, q0);
@@ -410,12 +428,11 @@ GM_HD double gm_log_unit(double x, const double* tab) {
 #endif
 
 template <int K> GM_HD void gm_exp_nonpos_v(const double* x, double* out, const double* tab) {
-  double xc[K], z[K], r[K], p[K];
+  double z[K], r[K], p[K];
   GM_UNROLL for (int k = 0; k < K; ++k) {
-    xc[k] = x[k] < -708.3964185322641 ? -708.0 : x[k];
-    z[k] = fma(xc[k], GM_INV_L64, GM_RN_SHIFT);
+    z[k] = fma(x[k], GM_INV_L64, GM_RN_SHIFT);
     const double kf = z[k] - GM_RN_SHIFT;
-    r[k] = fma(-kf, GM_L64_HI, xc[k]);
+    r[k] = fma(-kf, GM_L64_HI, x[k]);
     r[k] = fma(-kf, GM_L64_LO, r[k]);
     p[k] = GM_C(exp, 0);
   }
@@ -427,7 +444,7 @@ template <int K> GM_HD void gm_exp_nonpos_v(const double* x, double* out, const 
     const double q = fma(r[k] * r[k], p[k], r[k]);
     const int32_t n = (int32_t)(uint32_t)gm_to_bits(z[k]);
     const double t = tab[n & 63];
-    const double v = gm_from_bits(gm_to_bits(fma(t, q, t)) + ((uint64_t)(long long)(n >> 6) << 52));
+    const double v = gm_scale_pow2(fma(t, q, t), n >> 6);
     out[k] = x[k] < -708.3964185322641 ? 0.0 : v;
   }
 }

@@ -18,7 +18,7 @@
 #define GSMC_MAX_INLINE_OBS 16
 #define GSMC_HMM_MAX_K 16
 
-struct NormC { double two_var, half_log, inv_two_var; };   // hoisted constants of one normal logpdf
+struct NormC { double two_var, half_log, inv_two_var; uint32_t span, pad_; };   // hoisted constants of one normal logpdf
 
 struct ModelArgs {
   double p[GSMC_MAX_INLINE_PARAMS];   // model parameters (prefix; all of them live at p_dev too)
@@ -38,12 +38,13 @@ GM_HD NormC make_normc(double std) {
   c.two_var = 2.0 * var;
   c.half_log = 0.5 * gm_log(2.0 * GM_PI * var);
   c.inv_two_var = gm_safe_recip(c.two_var);
+  c.span = gm_div_span(c.inv_two_var); c.pad_ = 0;
   return c;
 }
 // the division by the launch-invariant 2*var is done with gm_div_inv: same bits as `/`, 3 instructions
 GM_HD double logpdf_normal_c(double x, double mu, NormC c) {
   const double diff = x - mu;
-  return gm_div_inv(-(diff * diff), c.two_var, c.inv_two_var) - c.half_log;
+  return gm_div_inv_s(-(diff * diff), c.two_var, c.inv_two_var, c.span) - c.half_log;
 }
 // per-particle std (nothing to hoist): the literal formula
 GM_HD double logpdf_normal(double x, double mu, double std) {
