@@ -499,9 +499,6 @@ static int launch_finalize(gsmc_filter* f, double ess_threshold) {
   if (fused) f->xchg_seq += 1;
   {
     ProfScope ps(f, KC_FINALIZE);
-#if !GSMC_LASTBLOCK
-    reduce_partials_kernel<<<1, 1024, 0, f->stream>>>(f->partials, f->n_partials, f->ds, f->rank);
-#endif
     CK(launch_pdl(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, peers, f->xchg_seq, fused));
   }
   CK(cudaGetLastError());
@@ -549,14 +546,6 @@ static double weight_scale(const gsmc_filter* f) {
   const int k = 62 - lg;
   return gm_pow2(k > 52 ? 52 : k);
 }
-// persistent grid of a tile kernel: as many blocks as can be resident at once
-static int tile_grid(const gsmc_filter* f, const void* fn) {
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, GSMC_BLOCK, 0) != cudaSuccess || occ < 1) occ = 4;
-  const int g = f->sm_count * occ;
-  return f->n_tiles < g ? f->n_tiles : g;
-}
-
 // One-block scan of the raw segment totals in0/in1 into the prefix arrays out0/out1 + exchange of this rank's
 // totals + the event's totals (see kernels.cuh).
 static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint64_t* in1, uint64_t* out0, uint64_t* out1, int what, int conditional) {

@@ -31,9 +31,6 @@
 #ifndef GSMC_PROP_OCC
 #define GSMC_PROP_OCC 3
 #endif
-#ifndef GSMC_LASTBLOCK
-#define GSMC_LASTBLOCK 1
-#endif
 #define GSMC_TILE 2048            // particles (or thresholds) per block iteration of the scan / search kernels
 #define GSMC_TILE_SHIFT 11
 #define GSMC_PAD 2048             // local columns are padded to this many particles
@@ -162,25 +159,6 @@ __device__ __forceinline__ uint64_t block_scan_u64(uint64_t v, uint64_t* sm, uin
   *total = sm[GSMC_BLOCK / 32 - 1];
   return x + warp_off;
 }
-__device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t* sm) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)v, o);
-  __syncthreads();
-  if (lane == 0) sm[warp] = v;
-  __syncthreads();
-  uint64_t t = 0;
-#pragma unroll
-  for (int w = 0; w < GSMC_BLOCK / 32; ++w) t += sm[w];
-  return t;
-}
-
-// 128-bit comparison  a*b > c*d  for u64 operands
-__device__ __forceinline__ bool mul_gt(uint64_t a, uint64_t b, uint64_t chi, uint64_t clo) {
-  const uint64_t hi = __umul64hi(a, b), lo = a * b;
-  return hi > chi || (hi == chi && lo > clo);
-}
-
 // Shared-memory copies of the lookup tables of gsmc_math.h (lanes index them divergently), staged with
 // coalesced loads from their global-memory copies.
 struct __align__(16) SmemTabs {
@@ -449,31 +427,17 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
   }  // tiles
   if (threadIdx.x == 0) {
     g.partials[blockIdx.x] = run;
-#if GSMC_LASTBLOCK
     // The last block to publish its partial reduces all of them (replaces a separate one-block launch).
     __threadfence();
     s_last = (atomicAdd(&g.ds->blocks_done, 1u) + 1u == gridDim.x) ? 1 : 0;
-#endif
   }
-#if GSMC_LASTBLOCK
   __syncthreads();
   if (s_last) {
     __threadfence();
     const LseTriple tr = reduce_partials(g.partials, (int)gridDim.x, red, tabs.exp2);
     if (threadIdx.x == 0) { g.ds->triples[g.rank] = tr; g.ds->blocks_done = 0; }
   }
-#endif
 }
-#if !GSMC_LASTBLOCK
-__global__ void __launch_bounds__(1024) reduce_partials_kernel(const LseTriple* partials, int nblk, DevScalars* ds, int rank) {
-  __shared__ double red[96];
-  __shared__ double etab[64];
-  if (threadIdx.x < 64) etab[threadIdx.x] = gm_exp2tab_g[threadIdx.x];
-  __syncthreads();
-  const LseTriple tr = reduce_partials(partials, nblk, red, etab);
-  if (threadIdx.x == 0) ds->triples[rank] = tr;
-}
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // finalize: merge the ranks' triples and decide.
@@ -577,13 +541,6 @@ __device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, do
   const Real2 a = *reinterpret_cast<const Real2*>(lw + i);
   const Real2 b = *reinterpret_cast<const Real2*>(lw + i + 2);
   q_from_lw<Real>(a, b, i, n, mx, scale, etab, q);
-}
-
-// spacings of the thresholds k .. k+3 (global threshold index, k a multiple of 4), masked to k < m_draws
-__device__ __forceinline__ void tile_spacings(uint64_t seed, uint32_t rho, uint64_t k, uint64_t m_draws, const double* tab, uint32_t e[4]) {
-  spacing_quad(seed, k >> 2, rho, tab, e);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) if (k + j >= m_draws) e[j] = 0;
 }
 
 // Block-wide inclusive scan of v together with a block-wide sum of w, one barrier per call.
