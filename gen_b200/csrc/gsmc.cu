@@ -4,6 +4,8 @@
 // reference) as structure-of-arrays column slabs and enqueues the kernels of kernels.cuh on one
 // CUDA stream. There is no CPU fallback: every entry point either runs the CUDA path or fails.
 #include <cuda_runtime.h>
+#include <atomic>
+#include <chrono>
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stddef.h>
@@ -196,6 +198,7 @@ struct gsmc_filter {
   const uint64_t* peer_cdf[GSMC_MAX_RANKS] = {};
   DevScalars* peer_ds[GSMC_MAX_RANKS] = {};
   uint32_t xchg_seq = 0;        // sequence number of the fused peer exchanges (same on every rank)
+  uint32_t host_token = 0;      // token of the last decision published to the pinned host mirror
   bool use_nccl_scalars = false;  // GSMC_NCCL_SCALARS=1: exchange the per-step scalars with ncclAllGather instead
   size_t bytes_state = 0, bytes_anc = 0, bytes_lw = 0, bytes_cdf = 0;
   // replay staging
@@ -329,6 +332,8 @@ static int alloc_buffers(gsmc_filter* f) {
   CK(pool_alloc(f->device, (void**)&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
   CK(pool_alloc(f->device, (void**)&f->ds, sizeof(DevScalars)));
   CK(pinned_alloc(&f->h_ds));
+  memset(f->h_ds, 0, sizeof(DevScalars));          // pooled buffer: no stale decision token
+  f->host_token = 0;
   CK(pool_alloc(f->device, (void**)&f->resampled, (size_t)f->flag_mod * sizeof(int)));
   CK(cudaMemsetAsync(f->ds, 0, sizeof(DevScalars), f->stream));
   CK(cudaMemsetAsync(f->resampled, 0, (size_t)f->flag_mod * sizeof(int), f->stream));
@@ -491,23 +496,43 @@ static int launch_propagate(gsmc_filter* f, bool init, const double* obs, size_t
 }
 
 // finalize (+ decision when ess_threshold >= 0); leaves the statistics in f->ds
-static int launch_finalize(gsmc_filter* f, double ess_threshold) {
+static int launch_finalize(gsmc_filter* f, double ess_threshold, bool to_host = false) {
   int* flag = ess_threshold >= 0.0 ? f->resampled + ((f->T + 1) % f->flag_mod) : nullptr;
   PeerScalars peers;
   for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
   const int fused = (f->nranks > 1 && !f->use_nccl_scalars) ? 1 : 0;
   if (fused) f->xchg_seq += 1;
+  // to_host: the deciding thread also writes the decision into the pinned host mirror, tagged with a fresh token
+  DevScalars* host = to_host ? f->h_ds : nullptr;
+  if (to_host) { f->host_token += 1; if (f->host_token == 0) f->host_token = 1; }
   {
     ProfScope ps(f, KC_FINALIZE);
-    CK(launch_pdl(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, peers, f->xchg_seq, fused));
+    CK(launch_pdl(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, peers, f->xchg_seq, fused,
+                  (f->nranks > 1 && !fused) ? (DevScalars*)nullptr : host, f->host_token));
   }
   CK(cudaGetLastError());
   if (f->nranks > 1 && !fused) {
     NK(g_nccl.AllGather((const char*)f->ds->triples + f->rank * sizeof(LseTriple), f->ds->triples, sizeof(LseTriple), NCCL_UINT8, f->comm, f->stream));
     ProfScope ps(f, KC_FINALIZE);
-    decide_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, ess_threshold, (double)f->N, flag);
+    decide_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, ess_threshold, (double)f->N, flag, host, f->host_token);
     CK(cudaGetLastError());
   }
+  return GSMC_OK;
+}
+// Host side of publish_decision: spin on the token in the pinned mirror; falls back to a stream synchronisation +
+// copy if the token does not show up (e.g. a platform without device-mapped pinned memory).
+static int wait_decision(gsmc_filter* f) {
+  volatile unsigned int* tok = &f->h_ds->host_token;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (long spins = 0;; ++spins) {
+    if (*tok == f->host_token) { std::atomic_thread_fence(std::memory_order_acquire); return GSMC_OK; }
+    if ((spins & 0x3ff) == 0x3ff) {
+      if (cudaStreamQuery(f->stream) == cudaSuccess && *tok != f->host_token) break;          // all work done, no token: fall back
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) break;
+    }
+  }
+  CK(cudaMemcpyAsync(f->h_ds, f->ds, offsetof(DevScalars, mbox), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
   return GSMC_OK;
 }
 // All ranks have finished every kernel that reads this rank's slabs (needed before they are reused or freed).
@@ -861,14 +886,12 @@ GSMC_API int gsmc_maybe_resample(gsmc_handle f, double ess_threshold, int* did_r
     return GSMC_OK;
   }
   const bool replay = f->urep_n > 0;
-  CKRC(launch_finalize(f, ess_threshold));
-  // The decision lives on the device. Copy it out, and -- unless exported uniforms are being replayed --
-  // enqueue the resampling kernels right away in their conditional form (they exit at once when no
-  // resample was decided), so the GPU never idles while the host reads the Bool this call returns.
-  CK(cudaMemcpyAsync(f->h_ds, f->ds, offsetof(DevScalars, mbox), cudaMemcpyDeviceToHost, f->stream));   // the scalars, not the mailboxes
-  CK(cudaEventRecord(f->decision_ev, f->stream));
+  // The decision is taken on the device and written by the deciding thread into the pinned host mirror. Unless
+  // exported uniforms are being replayed, the resampling kernels are enqueued right away in their conditional form
+  // (they exit at once when no resample was decided), so the GPU never idles while the host reads the Bool.
+  CKRC(launch_finalize(f, ess_threshold, true));
   if (!replay) CKRC(launch_resample(f, 1, false));
-  CK(cudaEventSynchronize(f->decision_ev));
+  CKRC(wait_decision(f));
   f->stats_fresh = true;
   f->decided_since_step = true;
   if (f->h_ds->error) {

@@ -57,7 +57,7 @@ struct DevScalars {
   uint32_t n_resamples;     // resampling events so far
   uint32_t rho;             // Philox event index of the resample being executed
   unsigned int blocks_done; // propagate: blocks that have published their logsumexp partial (the last one reduces them)
-  unsigned int pad0_;
+  unsigned int host_token;  // pinned host mirror only: token of the last decision the device has written there
   uint64_t cdf_total;       // C_N over all ranks
   uint64_t spacing_total;   // S_tot = sum of the M+1 spacings
   uint64_t n_det;           // residual scheme: number of deterministic copies
@@ -478,13 +478,25 @@ __device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, d
   }
 }
 
+// maybe_resample! returns a Bool to the host: instead of a D2H copy + event, the deciding thread stores the few scalars
+// the host reads straight into the pinned (device-mapped) host mirror and then, after a system fence, the call's
+// token; the host spins on the token (a couple of microseconds instead of a DMA + event round trip).
+__device__ __forceinline__ void publish_decision(const DevScalars* ds, DevScalars* host, uint32_t token) {
+  if (!host) return;
+  host->max_lw = ds->max_lw; host->log_total = ds->log_total; host->ess = ds->ess; host->log_ml_est = ds->log_ml_est;
+  host->do_resample = ds->do_resample; host->error = ds->error; host->n_resamples = ds->n_resamples; host->rho = ds->rho;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned int*>(&host->host_token) = token;
+}
+
 // The logsumexp/ESS statistics and the maybe_resample! decision from this rank's triple (left in ds->triples[rank]
 // by the last block of the propagate kernel). Multi-rank: every rank first gathers all triples over NVLink peer
 // stores (the logsumexp "allreduce") and merges them in rank order, so all ranks take the same decision
 // without a separate collective.
 __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, int nranks, double ess_threshold,
                                                       double n_global, int* resampled_flag_out,
-                                                      PeerScalars peers, uint32_t seq, int fused_exchange) {
+                                                      PeerScalars peers, uint32_t seq, int fused_exchange,
+                                                      DevScalars* host, uint32_t token) {
   __shared__ uint64_t mine[3];
   pdl_wait();
   pdl_trigger();
@@ -496,9 +508,9 @@ __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, 
     __syncwarp();
     ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 3, reinterpret_cast<uint64_t*>(ds->triples));
     __syncwarp();
-    if (threadIdx.x == 0) combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out);
+    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out); publish_decision(ds, host, token); }
   } else if (nranks == 1) {
-    if (threadIdx.x == 0) combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out);
+    if (threadIdx.x == 0) { combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out); publish_decision(ds, host, token); }
   }
 }
 // cross-GPU barrier (peer-memory exchange of one word): nobody passes until every rank has arrived
@@ -510,8 +522,9 @@ __global__ void peer_barrier_kernel(PeerScalars peers, DevScalars* ds, int rank,
 }
 
 // multi-rank: runs after the allgather of ds->triples
-__global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, double n_global, int* resampled_flag_out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out);
+__global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, double n_global, int* resampled_flag_out,
+                              DevScalars* host, uint32_t token) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out); publish_decision(ds, host, token); }
 }
 
 // ------------------------------------------------------------------------------------------------
