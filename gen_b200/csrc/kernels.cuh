@@ -1070,9 +1070,14 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // three-level searches in global memory; windows that touch a peer's CDF are staged with ordinary loads.
 #define GSMC_SEARCH_TPT 8                                   // thresholds per thread
 #define GSMC_SUPERTILE (GSMC_BLOCK * GSMC_SEARCH_TPT)       // 2048
+#ifndef GSMC_WIN_CAP
 #define GSMC_WIN_CAP 5120
+#endif
+#ifndef GSMC_SEARCH_OCC
+#define GSMC_SEARCH_OCC 5
+#endif
 #define GSMC_SEARCH_SMEM ((GSMC_WIN_CAP + 4) * 8)           // 41 KB of window per block: 5 blocks per SM
-__global__ void __launch_bounds__(GSMC_BLOCK, 5) search_sorted_kernel(CdfView v, uint64_t k_first, const DevScalars* ds,
+__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_kernel(CdfView v, uint64_t k_first, const DevScalars* ds,
                                                                       const uint64_t* tile_e, uint32_t seg_tiles, uint32_t seg_magic,
                                                                       const uint32_t* esp, const uint32_t* win, uint32_t* anc,
                                                                       int64_t n_out, int nt, int det_offset, int conditional, int rank) {
