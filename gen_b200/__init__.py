@@ -6,6 +6,7 @@ from .choicemap import ChoiceMap, NoChange, UnknownChange, choicemap, merge
 from .inference import (DeviceTrace, DeviceTraces, ParticleFilterState, get_log_weights, get_traces,
                         importance_resampling, importance_sampling, initialize_particle_filter, log_ml_estimate, maybe_resample_,
                         maybe_resample_b, particle_filter_step_, particle_filter_step_b, sample_unweighted_traces)
+from .pmmh import ParticleFilterCombinator, PFCombinatorTrace, pmmh
 from .models import (HMM, BearingsOnly, DeviceModel, DeviceProposal, LinearGaussianSSM, LinearRegression, NormalNormal,
                      StochasticVolatility)
 

@@ -491,3 +491,37 @@ def test_importance_resampling(gpu, orc):
     assert math.isfinite(lml) and "slope" in tr.get_choices()
     trq, lmlq = g.importance_resampling(reg, ([-2.0, -1.0, 0.0, 1.0, 2.0],), cm, reg.custom_proposal(2.0, 0.5, 0.0, 1.0), (), 4000, seed=3)
     assert math.isfinite(lmlq) and abs(lmlq - lml) < 0.5
+
+
+def test_pmmh_recovers_the_exact_posterior(gpu):
+    """examples/pmmh (particle marginal MH): the chain over log q^2 of the linear-Gaussian model, driven by the device
+    filter's log-ML estimates, against the exact posterior from the Kalman likelihood on a grid."""
+    import math
+    g = gpu
+    T = 40
+    ys = cf.simulate_lgssm(T, LG, 9)
+    obs = g.choicemap(("y_init", float(ys[0])), *[(("chain", t, "y"), float(ys[t])) for t in range(1, T)])
+
+    def make(logq2):
+        return g.LinearGaussianSSM(LG[0], LG[1], LG[2], LG[3], math.exp(0.5 * logq2), LG[5], LG[6])
+
+    def log_prior(th):
+        return float(-0.5 * (th[0] / 2.0) ** 2)                       # log q^2 ~ normal(0, 2), example.jl:26-27
+
+    pf = g.ParticleFilterCombinator(make, 8192, seed=100)
+    tr, lml = pf.generate((T, 0.0), obs)
+    assert tr.get_score() == lml and tr.get_choices() is obs and tr.get_args() == (T, 0.0)
+    exact0 = cf.kalman_log_ml(ys, *LG)
+    assert lml == pytest.approx(exact0, abs=0.3)
+    tr2, w, _, _ = pf.update(tr, (T, 0.5))
+    assert w == pytest.approx(tr2.get_score() - lml)
+    samples, lmls, rate = g.pmmh(pf, T, obs, log_prior, [0.0], 400, [0.6], seed=1)
+    grid = np.linspace(-4, 4, 401)
+    lp = np.array([cf.kalman_log_ml(ys, LG[0], LG[1], LG[2], LG[3], math.exp(0.5 * v), LG[5], LG[6]) - 0.5 * (v / 2.0) ** 2 for v in grid])
+    w = np.exp(lp - lp.max())
+    mean = float((grid * w).sum() / w.sum())
+    sd = float(np.sqrt(((grid - mean) ** 2 * w).sum() / w.sum()))
+    chain = samples[100:, 0]
+    assert 0.1 < rate < 0.9
+    assert abs(chain.mean() - mean) < 0.5 * sd + 0.1, (chain.mean(), mean, sd)
+    assert 0.5 * sd < chain.std() < 2.0 * sd
