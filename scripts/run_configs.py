@@ -79,8 +79,19 @@ def filter_run(name, model, ys, N, S, resample="multinomial", proposal=None, kee
     ms = st.timer_stop() / reps
     n_res = st.stats()["num_resamples"]
     alg = N * (T * (2 * S + 16) + n_res * (2 * S + 36))
+    kernel_ms = None
+    if os.environ.get("GSMC_CFG_PROFILE"):             # per-kernel-class CUDA-event times (per-call API, same workload)
+        st.set_profiling(True)
+        st.reset()
+        st.init([ys[0]], proposal)
+        for t in range(1, T):
+            st.maybe_resample(thr)
+            st.step([ys[t]], proposal)
+        prof = st.stats()
+        kernel_ms = {k[3:]: round(prof[k], 3) for k in prof if k.startswith("ms_")}
+        st.set_profiling(False)
     st.close()
-    return {"config": name, "particles": N, "time_steps": T, "resample": resample, "resamples_per_run": n_res,
+    return {"kernel_ms_profile_pass": kernel_ms,"config": name, "particles": N, "time_steps": T, "resample": resample, "resamples_per_run": n_res,
             "ms_per_run": ms, "particle_steps_per_s": N * T / (ms * 1e-3), "log_ml": lml,
             "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": alg / (ms * 1e-3) / 1e9 / PEAK}
 
