@@ -31,6 +31,18 @@ def test_sharded_filter_matches_oracle(world):
     assert res.stdout.count(" ok on %d ranks" % world) == 2, res.stdout[-2000:]
 
 
+@pytest.mark.gpu
+def test_sharded_filter_with_nccl_scalar_exchanges():
+    """GSMC_NCCL_SCALARS=1: the per-step scalars travel by ncclAllGather instead of the fused peer-memory mailboxes."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, GSMC_NCCL_SCALARS="1"))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count(" ok on 2 ranks") == 2, res.stdout[-2000:]
+
+
 def _gloo_worker(rank, world, port, N, T, ret):
     """Each rank runs the oracle on ITS shard only, exchanging exactly what the CUDA library exchanges:
     logsumexp triples, per-rank integer weight totals (and, standing in for the peer-memory loads of
