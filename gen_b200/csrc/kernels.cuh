@@ -119,9 +119,12 @@ template <> struct Vec2T<float> { typedef float2 type; };
 // ------------------------------------------------------------------------------------------------
 // block-level helpers (256 threads = 8 warps)
 // ------------------------------------------------------------------------------------------------
+// max(a, b) that keeps a when b is NaN: one compare + select (fmax() costs ~8 instructions in fp64: NaN quieting and
+// signed-zero handling that the log-weight maxima do not need; a never is NaN here)
+__device__ __forceinline__ double max_nn(double a, double b) { return b > a ? b : a; }
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) v = max_nn(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ double warp_sum(double v) {
@@ -224,13 +227,13 @@ __device__ __forceinline__ LseTriple lse_merge_t(LseTriple a, LseTriple b, const
 __device__ __forceinline__ LseTriple reduce_partials(const LseTriple* partials, int nblk, double* sm, const double* etab) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
   double m = -gm_inf();
-  for (int b = threadIdx.x; b < nblk; b += blockDim.x) m = fmax(m, __ldcg(&partials[b].m));
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) m = max_nn(m, __ldcg(&partials[b].m));
   m = warp_max(m);
   __syncthreads();
   if (lane == 0) sm[warp] = m;
   __syncthreads();
   double M = sm[0];
-  for (int w = 1; w < nw; ++w) M = fmax(M, sm[w]);
+  for (int w = 1; w < nw; ++w) M = max_nn(M, sm[w]);
   double a1 = 0.0, a2 = 0.0;
   for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
     const double pm = __ldcg(&partials[b].m), p1 = __ldcg(&partials[b].s1), p2 = __ldcg(&partials[b].s2);
@@ -389,16 +392,22 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
   }
 
   // Stage E: block partial of (max, sum exp(lw-max), sum exp(2(lw-max))); NaN log weights poison s1/s2 on purpose.
-  // fmax drops NaNs, so the max needs no NaN test; a NaN log weight then turns into a NaN exp below
-  double m = -gm_inf();
+  // max_nn drops NaNs, so the max needs no NaN test; a NaN log weight then turns into a NaN exp below.
+  // Pairwise tree (independent compares) rather than one dependent chain.
+  double mt[NP];
 #pragma unroll
-  for (int j = 0; j < NP; ++j) m = fmax(m, lwv[j]);
-  m = warp_max(m);
+  for (int j = 0; j < NP; ++j) mt[j] = max_nn(-gm_inf(), lwv[j]);
+#pragma unroll
+  for (int w = NP / 2; w >= 1; w >>= 1) {
+#pragma unroll
+    for (int j = 0; j < w; ++j) mt[j] = max_nn(mt[j], mt[j + w]);
+  }
+  double m = warp_max(mt[0]);
   if (lane == 0) red[warp] = m;
   __syncthreads();
   double bm = red[0];
 #pragma unroll
-  for (int w = 1; w < GSMC_BLOCK / 32; ++w) bm = fmax(bm, red[w]);
+  for (int w = 1; w < GSMC_BLOCK / 32; ++w) bm = max_nn(bm, red[w]);
   double s1 = 0.0, s2 = 0.0;
   if (bm > -gm_inf()) {
     double x[NP], e[NP];
