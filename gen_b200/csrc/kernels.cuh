@@ -567,6 +567,7 @@ __device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, do
 
 // Block-wide inclusive scan of v together with a block-wide sum of w, one barrier per call.
 // sm: [2 buffers][2][GSMC_BLOCK/32] u64, `buf` alternates between consecutive calls.
+template <bool WITH_W>
 __device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, uint64_t* sm, int buf, uint64_t* v_total, uint64_t* w_total) {
   constexpr int NW = GSMC_BLOCK / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -574,16 +575,27 @@ __device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, u
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
   // warp sum of w (< 2^40: a few 32-bit spacings per thread) by two hardware 32-bit reductions
-  w = (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(w & 0xfffffu)) + ((uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(w >> 20)) << 20);
+  if (WITH_W) w = (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(w & 0xfffffu)) + ((uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(w >> 20)) << 20);
   uint64_t* sv = sm + buf * 2 * NW;
   uint64_t* sw = sv + NW;
-  if (lane == 31) { sv[warp] = x; sw[warp] = w; }
+  if (lane == 31) { sv[warp] = x; if (WITH_W) sw[warp] = w; }
   __syncthreads();
-  uint64_t off = 0, vt = 0, wt = 0;
+  // Every warp combines the NW warp totals with shuffles: lane k < NW holds total k, a 3-step inclusive scan gives the
+  // prefixes (instead of every thread reading and adding all NW totals itself).
+  uint64_t p = lane < NW ? sv[lane] : 0;
 #pragma unroll
-  for (int k = 0; k < NW; ++k) { const uint64_t a = sv[k]; if (k < warp) off += a; vt += a; wt += sw[k]; }
-  *v_total = vt; *w_total = wt;
-  return x + off;
+  for (int d = 1; d < NW; d <<= 1) { const uint64_t y = shfl_up_u64(p, d); if (lane >= d) p += y; }
+  *v_total = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)p, NW - 1);
+  const uint64_t off = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)p, warp ? warp - 1 : 0);
+  if (WITH_W) {
+    uint64_t q = lane < NW ? sw[lane] : 0;
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) q += (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)q, o);
+    *w_total = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)q, 0);
+  } else {
+    *w_total = 0;
+  }
+  return x + (warp ? off : 0);
 }
 
 // The streaming pass of a resampling event; block s owns segment s = tiles [s*seg_tiles, (s+1)*seg_tiles).
@@ -658,7 +670,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const 
 #pragma unroll
     for (int j = 0; j < W; ++j) { qs += q[j]; es += e[j]; }
     uint64_t qt, et;
-    const uint64_t incl = block_scan_and_sum(qs, es, sm, buf, &qt, &et);
+    const uint64_t incl = block_scan_and_sum<SPACINGS>(qs, es, sm, buf, &qt, &et);
     if (WEIGHTS) {
       uint64_t c = run_q + incl - qs;
 #pragma unroll
@@ -1133,7 +1145,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
 #pragma unroll
     for (int j = 0; j < GSMC_SEARCH_TPT; ++j) tsum += e[j];
     uint64_t tot, dummy;
-    uint64_t S = tile_e[tile] + block_scan_and_sum(tsum, 0, sm, buf, &tot, &dummy) - tsum;
+    uint64_t S = tile_e[tile] + block_scan_and_sum<false>(tsum, 0, sm, buf, &tot, &dummy) - tsum;
     const uint64_t k = k_first + (uint64_t)o_local;
     double t[GSMC_SEARCH_TPT];
 #pragma unroll
