@@ -405,9 +405,10 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
   double m = warp_max(mt[0]);
   if (lane == 0) red[warp] = m;
   __syncthreads();
-  double bm = red[0];
+  // block max: every group of 8 lanes loads the 8 warp maxima and folds them with a 3-step butterfly
+  double bm = red[lane & (GSMC_BLOCK / 32 - 1)];
 #pragma unroll
-  for (int w = 1; w < GSMC_BLOCK / 32; ++w) bm = max_nn(bm, red[w]);
+  for (int o = GSMC_BLOCK / 64; o > 0; o >>= 1) bm = max_nn(bm, __shfl_xor_sync(0xffffffffu, bm, o));
   double s1 = 0.0, s2 = 0.0;
   if (bm > -gm_inf()) {
     double x[NP], e[NP];
