@@ -113,6 +113,9 @@ GM_HD void gm_tab_pair(const double* tab, int i, double* a, double* b) {
 }
 /* (double)w for a 32-bit unsigned w, exactly, without an int->float conversion instruction: 2^52 + w has w in its low word */
 GM_HD double gm_u32_to_f64(uint32_t w) { return gm_from_bits(0x4330000000000000ULL | (uint64_t)w) - 4503599627370496.0; }
+/* (w + 0.5) 2^-32 for a 32-bit unsigned w with ONE subtraction: the bit pattern below is 2^20 + w 2^-32, and
+   2^20 - 2^-33 is a double (53 significant bits); every step is exact, so the bits equal ((double)w + 0.5) * 2^-32 */
+GM_HD double gm_u32_to_unit(uint32_t w) { return gm_from_bits(0x4130000000000000ULL | (uint64_t)w) - 0x1.fffffffffffffp+19; }
 GM_HD double gm_inf(void) { return gm_from_bits(GM_INF_BITS); }
 GM_HD double gm_nan(void) { return gm_from_bits(0x7ff8000000000000ULL); }
 /* p * 2^k by an integer add on the exponent field (the caller guarantees a normal result) */

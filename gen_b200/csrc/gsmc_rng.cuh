@@ -86,7 +86,7 @@ __host__ __device__ __forceinline__ void uniform_pair(uint64_t seed, uint64_t ca
 }
 
 __host__ __device__ __forceinline__ uint32_t spacing_from_word(uint32_t w, const double* tab) {
-  const double u = (gm_u32_to_f64(w) + 0.5) * 0x1p-32;
+  const double u = gm_u32_to_unit(w);                           // (w + 0.5) 2^-32
   return (uint32_t)(-gm_log_tab(u, tab) * GM_SPACING_SCALE);     // = floor: the product lies in (0, 2^32)
 }
 // the four spacings 4c .. 4c+3 of call c
@@ -96,7 +96,7 @@ __host__ __device__ __forceinline__ void spacing_quad(const Key& seed, uint64_t 
   const uint32_t w[4] = {(uint32_t)o.a, (uint32_t)(o.a >> 32), (uint32_t)o.b, (uint32_t)(o.b >> 32)};
   double u[4], l[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) u[j] = (gm_u32_to_f64(w[j]) + 0.5) * 0x1p-32;
+  for (int j = 0; j < 4; ++j) u[j] = gm_u32_to_unit(w[j]);        // (w + 0.5) 2^-32
   gm_log_tab_v<4>(u, tab, l);
 #pragma unroll
   for (int j = 0; j < 4; ++j) e[j] = (uint32_t)(-l[j] * GM_SPACING_SCALE);    // = floor: the product lies in (0, 2^32)

@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const 
     uint64_t q[W];
     uint32_t e[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) { q[j] = 0; e[j] = 0; }
+    for (int j = 0; j < W; ++j) { if (!WEIGHTS) q[j] = 0; if (!SPACINGS) e[j] = 0; }
     if (WEIGHTS) {
       double x[W], ex[W];
 #pragma unroll
