@@ -213,9 +213,12 @@ template <class Model> struct PropTile {
 __device__ __forceinline__ LseTriple lse_merge_t(LseTriple a, LseTriple b, const double* etab) {
   if (!(b.m > -gm_inf()) && b.s1 == b.s1) return a;
   if (!(a.m > -gm_inf()) && a.s1 == a.s1) return b;
+  // One of the two rescaling factors is exp(0) = 1 exactly: only the other one is evaluated (same bits as evaluating both).
   LseTriple r;
-  r.m = fmax(a.m, b.m);
-  const double ea = gm_exp_nonpos_t(a.m - r.m, etab), eb = gm_exp_nonpos_t(b.m - r.m, etab);
+  const bool a_big = a.m >= b.m;
+  r.m = a_big ? a.m : b.m;
+  const double e = gm_exp_nonpos_t(a_big ? b.m - a.m : a.m - b.m, etab);
+  const double ea = a_big ? 1.0 : e, eb = a_big ? e : 1.0;
   r.s1 = a.s1 * ea + b.s1 * eb;
   r.s2 = a.s2 * (ea * ea) + b.s2 * (eb * eb);
   return r;
