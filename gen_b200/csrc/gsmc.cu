@@ -163,7 +163,7 @@ struct gsmc_filter {
   NcclComm comm = nullptr;
   int64_t N = 0, n = 0, n_pad = 0, first = 0;   // global count, local count, padded local, first global index
   int sm_count = 148;
-  int n_tiles = 0;       // 1024-particle tiles of the scan / search kernels
+  int n_tiles = 0;       // GSMC_TILE (2048) particle tiles of the scan / search kernels
   int n_partials = 0;    // blocks (= logsumexp partials) of the last propagate launch
   std::vector<double> params;
   double* d_params = nullptr;

@@ -1,19 +1,24 @@
 // kernels.cuh -- hand-written sm_100a kernels of the SMC / importance-sampling hot path.
 //
-// All kernels are HBM-bound streaming passes over structure-of-arrays particle columns
-// (no tensor cores: nothing here is a dense contraction). One thread owns a PAIR of
-// neighbouring particles so that every global access is a 16-byte vector access, a warp
-// touches 512 contiguous bytes per column, and one Philox call feeds both particles.
+// All kernels are streaming passes over structure-of-arrays particle columns (no tensor cores: nothing here is a
+// dense contraction). One thread owns PAIRS of neighbouring particles so that every global access is a 16-byte vector
+// access, a warp touches 512 contiguous bytes per column, and one Philox call feeds both particles of a pair. The hot
+// kernels are persistent (one resident wave of blocks looping over 2048-particle tiles) and are launched with
+// programmatic dependent launch (pdl_wait / pdl_trigger below).
 //
-//   propagate_kernel   particle_filter.jl:84-88,103-105 (init), :143-146,165-172 (step) fused with
-//                      the ancestor gather of :202-205 and with the block partials of logsumexp/ESS
-//   finalize_kernel    inference.jl:3-6 + particle_filter.jl:3-12 (normalize_weights, ESS) and the
-//                      `ess < ess_threshold` decision + `log_ml_est += log_total - log N` of :194,201
-//   qsum/cdf kernels   `weights = exp.(lnw)` + the CDF behind Categorical(weights/sum(weights)), :199-200,
-//                      in 64-bit fixed point so the prefix sum is associative (order/shard independent)
-//   spacing kernels    sorted uniforms from exponential spacings (the N iid draws of :200, generated
-//                      already sorted so that search + gather stream through memory)
-//   search kernels     parents[i] (:200) by binary search of the integer CDF
+//   propagate_kernel   particle_filter.jl:84-88,103-105 (init), :143-146,165-172 (step) fused with the ancestor gather
+//                      of :202-205 and with logsumexp/ESS: per-tile partials -> per-block running triple -> the last
+//                      block to finish reduces the block partials into this rank's (max, sum e, sum e^2)
+//   finalize_kernel    inference.jl:3-6 + particle_filter.jl:3-12 (normalize_weights, ESS): merge of the ranks' triples
+//                      (fused NVLink mailbox exchange), the `ess < ess_threshold` decision and
+//                      `log_ml_est += log_total - log N` of :194,201; the Bool goes to the host through a pinned mirror
+//   weights_kernel     `weights = exp.(lnw)` + the CDF behind Categorical(weights/sum(weights)), :199-200, in 64-bit fixed
+//                      point so the prefix sum is associative (order/shard independent), as a two-level CDF; fused: the
+//                      exponential spacings of the sorted uniforms (the N iid draws of :200, generated already sorted so
+//                      that search + gather stream through memory)
+//   partition_kernel   scan of the segment totals (+ exchange of the ranks' totals) and the CDF window of every tile
+//   search_sorted_kernel  parents[i] (:200): TMA-staged CDF window, binary search + walks in shared memory
+//   search_iid_kernel  replay / sample_unweighted_traces (:62-70); resid_* / det_copies: the residual scheme
 #ifndef GSMC_KERNELS_CUH
 #define GSMC_KERNELS_CUH
 
@@ -545,7 +550,7 @@ __global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, 
 //   cl[i]  = sum of q over the particles of i's SEGMENT up to and including i   (segment-local inclusive CDF)
 //   sp[s]  = sum of q over the segments before s (exclusive segment prefix), sp[n_segs] = this rank's total
 // so that C_i = (rank offset) + sp[segment(i)] + cl[i]. A segment is a run of seg_tiles consecutive
-// 1024-particle tiles owned by ONE block of the streaming pass, which carries the running sum in a
+// 2048-particle tiles owned by ONE block of the streaming pass, which carries the running sum in a
 // register: no inter-block dependency, no look-back, and only n_segs (a few hundred) totals are left to
 // scan. The global CDF is never materialised (lw is read once, exp evaluated once). The exponential
 // spacings of the sorted uniforms are generated by the same pass and kept as 4-byte values (plus their
