@@ -199,6 +199,8 @@ struct gsmc_filter {
   DevScalars* peer_ds[GSMC_MAX_RANKS] = {};
   uint32_t xchg_seq = 0;        // sequence number of the fused peer exchanges (same on every rank)
   uint32_t host_token = 0;      // token of the last decision published to the pinned host mirror
+  bool fuse_next_decide = false;  // gsmc_run_steps: the propagate being launched also decides for the next step
+  double fuse_thr = -1.0;
   bool use_nccl_scalars = false;  // GSMC_NCCL_SCALARS=1: exchange the per-step scalars with ncclAllGather instead
   size_t bytes_state = 0, bytes_anc = 0, bytes_lw = 0, bytes_cdf = 0;
   // replay staging
@@ -409,6 +411,9 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   g.resampled_flag = f->resampled + (new_step % f->flag_mod);
   g.partials = f->partials;
   g.ds = f->ds; g.nranks = f->nranks;
+  g.fuse_decide = (f->fuse_next_decide && f->nranks == 1) ? 1 : 0;
+  g.fuse_threshold = f->fuse_thr; g.n_global = (double)f->N;
+  g.next_flag = f->resampled + ((new_step + 1) % f->flag_mod);
   g.n = f->n; g.stride = f->n_pad; g.first_global = (uint64_t)f->first; g.seed = f->cfg.seed; g.keys = make_philox_keys(f->cfg.seed);
   g.t = (uint32_t)new_step;
   g.use_anc = use_anc ? 1 : 0;
@@ -1108,10 +1113,18 @@ GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, si
   if (f->zrep_n || f->urep_n) return fail(GSMC_E_BADARG, "replay draws are consumed by the per-call API only");
   if (!(ess_threshold >= 0.0)) return fail(GSMC_E_BADARG, "ess_threshold must be >= 0");
   CK(cudaSetDevice(f->device));
+  // On one GPU the threshold of every decision is known here, so the last block of each propagate also takes the
+  // decision of the next step: only the first step of the call needs a finalize launch.
+  bool decided = false;
   for (size_t s = 0; s < n_steps; ++s) {
-    CKRC(launch_finalize(f, ess_threshold));
+    if (!decided) CKRC(launch_finalize(f, ess_threshold));
     CKRC(launch_resample(f, 1, false));
-    CKRC(launch_propagate(f, false, obs + s * n_obs, n_obs, prop, pp, npp, true));
+    f->fuse_next_decide = f->nranks == 1 && !f->profiling && s + 1 < n_steps;
+    f->fuse_thr = ess_threshold;
+    const int rc = launch_propagate(f, false, obs + s * n_obs, n_obs, prop, pp, npp, true);
+    decided = f->fuse_next_decide;
+    f->fuse_next_decide = false;
+    if (rc != GSMC_OK) return rc;
     f->T += 1;
   }
   f->decided_since_step = false; f->pending = false; f->stats_fresh = false;

@@ -196,6 +196,9 @@ struct PropArgs {
   DevScalars* ds;                    // the last block to finish leaves this rank's (max, s1, s2) in ds->triples[rank]
   int nranks;
   int n_tiles;                       // tiles of PropTile<Model>::TILE particles (the grid is persistent)
+  int fuse_decide;                   // single rank, threshold known in advance (gsmc_run_steps): the last block also takes
+  double fuse_threshold, n_global;   //   the maybe_resample! decision of the NEXT step (no finalize launch in between)
+  int* next_flag;                    //   resampled[] slot of the next step
   int64_t n;                         // local particle count
   int64_t stride;                    // column stride (padded n)
   uint64_t first_global;             // global index of local particle 0
@@ -213,6 +216,42 @@ template <class Model> struct PropTile {
   static constexpr int PAIRS = Model::D <= 2 ? GSMC_PROP_PAIRS : 2;
   static constexpr int TILE = 2 * GSMC_BLOCK * PAIRS;
 };
+
+__device__ __forceinline__ LseTriple lse_merge(LseTriple a, LseTriple b) {
+  if (!(b.m > -gm_inf()) && b.s1 == b.s1) return a;
+  if (!(a.m > -gm_inf()) && a.s1 == a.s1) return b;
+  LseTriple r;
+  r.m = fmax(a.m, b.m);
+  const double ea = gm_exp(a.m - r.m), eb = gm_exp(b.m - r.m);
+  r.s1 = a.s1 * ea + b.s1 * eb;
+  r.s2 = a.s2 * (ea * ea) + b.s2 * (eb * eb);
+  return r;
+}
+
+// Combine the per-rank triples in rank order and take the maybe_resample! decision.
+// ess_threshold < 0: statistics only. resampled_flag_out: flag slot of the NEXT step.
+__device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, double ess_threshold,
+                                                   double n_global, int* resampled_flag_out) {
+  LseTriple t = ds->triples[0];
+  for (int r = 1; r < nranks; ++r) t = lse_merge(t, ds->triples[r]);
+  const bool empty = !(t.m > -gm_inf()) && t.s1 == t.s1;
+  const double log_total = empty ? -gm_inf() : t.m + gm_log(t.s1);       // inference.jl:3-6
+  // particle_filter.jl:3-12 literally: lnw = lw - log_total; ess = exp(-logsumexp(2 lnw)) with
+  // logsumexp(2 lnw) = 2 lnw_max + log(sum exp(2 (lw - max))). Written this way (not s1^2/s2) the
+  // all-weights-equal case rounds exactly like the reference formula, where `ess < N` is a tie.
+  const double ess = empty ? gm_nan() : gm_exp(-(2.0 * (t.m - log_total) + gm_log(t.s2)));
+  ds->max_lw = t.m; ds->log_total = log_total; ds->ess = ess;
+  if (ess_threshold < 0.0) return;
+  int doit = ess < ess_threshold;                                        // particle_filter.jl:194
+  if (doit && !(log_total > -gm_inf() && log_total < gm_inf())) { ds->error = 1; doit = 0; }
+  ds->do_resample = doit;
+  if (resampled_flag_out) *resampled_flag_out = doit;
+  if (doit) {
+    ds->log_ml_est += log_total - gm_log(n_global);                      // particle_filter.jl:201
+    ds->rho = ds->n_resamples;
+    ds->n_resamples += 1;
+  }
+}
 
 // merge of two (max, s1, s2) triples; NaN sums propagate, empty triples (max = -inf) drop out
 __device__ __forceinline__ LseTriple lse_merge_t(LseTriple a, LseTriple b, const double* etab) {
@@ -453,49 +492,16 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
   if (s_last) {
     __threadfence();
     const LseTriple tr = reduce_partials(g.partials, (int)gridDim.x, red, tabs.exp2);
-    if (threadIdx.x == 0) { g.ds->triples[g.rank] = tr; g.ds->blocks_done = 0; }
+    if (threadIdx.x == 0) {
+      g.ds->triples[g.rank] = tr; g.ds->blocks_done = 0;
+      if (g.fuse_decide) combine_and_decide(g.ds, 1, g.fuse_threshold, g.n_global, g.next_flag);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // finalize: merge the ranks' triples and decide.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ LseTriple lse_merge(LseTriple a, LseTriple b) {
-  if (!(b.m > -gm_inf()) && b.s1 == b.s1) return a;
-  if (!(a.m > -gm_inf()) && a.s1 == a.s1) return b;
-  LseTriple r;
-  r.m = fmax(a.m, b.m);
-  const double ea = gm_exp(a.m - r.m), eb = gm_exp(b.m - r.m);
-  r.s1 = a.s1 * ea + b.s1 * eb;
-  r.s2 = a.s2 * (ea * ea) + b.s2 * (eb * eb);
-  return r;
-}
-
-// Combine the per-rank triples in rank order and take the maybe_resample! decision.
-// ess_threshold < 0: statistics only. resampled_flag_out: flag slot of the NEXT step.
-__device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, double ess_threshold,
-                                                   double n_global, int* resampled_flag_out) {
-  LseTriple t = ds->triples[0];
-  for (int r = 1; r < nranks; ++r) t = lse_merge(t, ds->triples[r]);
-  const bool empty = !(t.m > -gm_inf()) && t.s1 == t.s1;
-  const double log_total = empty ? -gm_inf() : t.m + gm_log(t.s1);       // inference.jl:3-6
-  // particle_filter.jl:3-12 literally: lnw = lw - log_total; ess = exp(-logsumexp(2 lnw)) with
-  // logsumexp(2 lnw) = 2 lnw_max + log(sum exp(2 (lw - max))). Written this way (not s1^2/s2) the
-  // all-weights-equal case rounds exactly like the reference formula, where `ess < N` is a tie.
-  const double ess = empty ? gm_nan() : gm_exp(-(2.0 * (t.m - log_total) + gm_log(t.s2)));
-  ds->max_lw = t.m; ds->log_total = log_total; ds->ess = ess;
-  if (ess_threshold < 0.0) return;
-  int doit = ess < ess_threshold;                                        // particle_filter.jl:194
-  if (doit && !(log_total > -gm_inf() && log_total < gm_inf())) { ds->error = 1; doit = 0; }
-  ds->do_resample = doit;
-  if (resampled_flag_out) *resampled_flag_out = doit;
-  if (doit) {
-    ds->log_ml_est += log_total - gm_log(n_global);                      // particle_filter.jl:201
-    ds->rho = ds->n_resamples;
-    ds->n_resamples += 1;
-  }
-}
-
 // maybe_resample! returns a Bool to the host: instead of a D2H copy + event, the deciding thread stores the few scalars
 // the host reads straight into the pinned (device-mapped) host mirror and then, after a system fence, the call's
 // token; the host spins on the token (a couple of microseconds instead of a DMA + event round trip).
