@@ -1164,7 +1164,11 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
     const uint64_t k = k_first + (uint64_t)o_local;
     double t[GSMC_SEARCH_TPT];
 #pragma unroll
-    for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { S += e[j]; t[j] = sorted_threshold(S, ratio, tmax); }
+    for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { S += e[j]; t[j] = (double)S * ratio; }
+    if (!(t[GSMC_SEARCH_TPT - 1] < tmax)) {               // thresholds ascend: the clamp to tmax can only matter if the last one needs it
+#pragma unroll
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) t[j] = t[j] < tmax ? t[j] : tmax;
+    }
     uint32_t a[GSMC_SEARCH_TPT];
     if (staged) {
       // C_i = sp[segment(i)] + cl[i] with global segment prefixes; segment(i) = (i / 1024) / seg_tiles by multiply-high
