@@ -1224,12 +1224,21 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
       }
       double c = lds_f64(ad);
       if (c <= t[0]) { ad += 8u; c = lds_f64(ad); }
+      if (len_b == 0) {                                    // the usual case (block-uniform): the window lies in one rank
+        const uint32_t last = (uint32_t)(len - 1);
 #pragma unroll
-      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
-        if (j > 0) { while (c <= t[j]) { ad += 8u; c = lds_f64(ad); } }
-        const int pj = (int)((ad - cw_base) >> 3);
-        const int pcl = pj < len ? pj : len - 1;
-        a[j] = pcl < la ? (w0 + (uint32_t)pcl) : ((((uint32_t)r1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pcl - la));
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
+          if (j > 0) { while (c <= t[j]) { ad += 8u; c = lds_f64(ad); } }
+          a[j] = w0 + min((ad - cw_base) >> 3, last);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
+          if (j > 0) { while (c <= t[j]) { ad += 8u; c = lds_f64(ad); } }
+          const int pj = (int)((ad - cw_base) >> 3);
+          const int pcl = pj < len ? pj : len - 1;
+          a[j] = pcl < la ? (w0 + (uint32_t)pcl) : ((((uint32_t)r1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pcl - la));
+        }
       }
     } else {
 #pragma unroll
