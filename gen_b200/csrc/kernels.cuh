@@ -958,8 +958,9 @@ __device__ __forceinline__ double sorted_threshold(uint64_t S, double ratio, dou
 // closes the last tile. One WARP per boundary (32-ary searches: 2 probe rounds over the segment prefixes
 // in shared memory, 3 over the segment in global/peer memory), 32 boundaries per 1024-thread block. Also
 // turns tile_e[b] into the GLOBAL spacing prefix before tile b.
-// FUSED_SCAN (single rank, multinomial): every block first scans the raw segment totals itself (identical
-// results in every block), which replaces the separate scan launch; block 0 publishes prefixes and totals.
+// FUSED_SCAN (multinomial, Philox draws): every block first scans the raw segment totals itself (identical
+// results in every block), which replaces the separate scan launch; block 0 publishes prefixes and totals and, on a
+// sharded filter, sends this rank's totals to the peers' mailboxes (every block reads all ranks' totals back).
 template <bool FUSED_SCAN>
 __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank, DevScalars* ds,
                                                          const uint64_t* raw_q, const uint64_t* raw_e, uint64_t* sp_q, uint64_t* sp_e,
@@ -1171,7 +1172,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
     }
     uint32_t a[GSMC_SEARCH_TPT];
     if (staged) {
-      // C_i = sp[segment(i)] + cl[i] with global segment prefixes; segment(i) = (i / 1024) / seg_tiles by multiply-high
+      // C_i = rank offset + sp[segment(i)] + cl[i] with rank-local segment prefixes; segment(i) = (i / GSMC_TILE) / seg_tiles by multiply-high
       const uint64_t* sp_a = v.sp[r0];
       const uint64_t roff_a = rank_offset(ds, r0);       // rank-local prefixes: C_i = roff + sp[segment(i)] + cl[i]
       if (bulk) {
