@@ -250,9 +250,12 @@ def run_ours(args):
         "log_ml": lml, "log_ml_kalman": kalman(ys), "log_ml_e2e": lml_e2e,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 8 * T,
-                "d2h_bytes_per_step": 8 + T * 432,   # one copy of the device scalars (432 B) per maybe_resample!, the log-ML double at the end
+                # per maybe_resample!: 52 B (decision, ESS, log-ML terms + token) stored by the deciding thread into the pinned
+                # host mirror; at the end one 432 B copy of the device scalars for log_ml_estimate
+                "d2h_bytes_per_step": (T - 1) * 52 + 432,
                 "ms_per_step": e_ms / reps,
-                "note": "Gen-API mirror; includes cudaMalloc of the trace slabs, one D2H of the device scalars per maybe_resample!"},
+                "note": "Gen-API mirror; includes allocation of the trace slabs (pooled after the first run); the Bool of every "
+                        "maybe_resample! reaches the host through the pinned mirror (device store + token), observations travel as kernel arguments"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "propagate_kernel<LgssmModel>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
