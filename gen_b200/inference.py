@@ -87,13 +87,28 @@ class ParticleFilterState:
                                             _lib.dptr(u), 0 if u is None else u.size), self.handle)
 
     def _propagate(self, fn, obs, proposal):
-        obs = np.ascontiguousarray(obs, dtype=np.float64)
-        pid, pp = _lib.PROPOSAL_DEFAULT, None
-        if proposal is not None:
-            pid, pp = proposal.proposal_id, np.ascontiguousarray(proposal.params, dtype=np.float64)
-        _lib.check(fn(self.handle, _lib.dptr(obs), obs.size, pid, _lib.dptr(pp), 0 if pp is None else pp.size), self.handle)
+        # per-step hot path of the host loop: short observation vectors go through a preallocated ctypes buffer
+        # (no numpy array + pointer cast per call); the library copies what it needs before returning
+        n = len(obs)
+        if n <= 16:
+            buf = self.__dict__.get("_obs_buf")
+            if buf is None:
+                buf = self._obs_buf = (C.c_double * 16)()
+            for i in range(n):
+                buf[i] = obs[i]
+            optr, kept = buf, np.array(buf[:n], dtype=np.float64)
+        else:
+            kept = np.ascontiguousarray(obs, dtype=np.float64).copy()
+            optr = _lib.dptr(kept)
+        if proposal is None:
+            rc = fn(self.handle, optr, n, _lib.PROPOSAL_DEFAULT, None, 0)
+        else:
+            pp = np.ascontiguousarray(proposal.params, dtype=np.float64)
+            rc = fn(self.handle, optr, n, proposal.proposal_id, _lib.dptr(pp), pp.size)
+        if rc:
+            _lib.check(rc, self.handle)
         self.T += 1
-        self.observations.append(obs.copy())
+        self.observations.append(kept)
 
     def reset(self):
         _lib.check(self.lib.gsmc_reset(self.handle), self.handle)
@@ -119,10 +134,15 @@ class ParticleFilterState:
         self.observations.extend(list(obs.copy()))
 
     def maybe_resample(self, ess_threshold):
-        did, ess = C.c_int(), C.c_double()
-        _lib.check(self.lib.gsmc_maybe_resample(self.handle, float(ess_threshold), C.byref(did), C.byref(ess)), self.handle)
-        self.last_ess = ess.value
-        return bool(did.value)
+        out = self.__dict__.get("_mr_out")
+        if out is None:
+            did, ess = C.c_int(), C.c_double()
+            out = self._mr_out = (did, ess, C.byref(did), C.byref(ess))
+        rc = self.lib.gsmc_maybe_resample(self.handle, float(ess_threshold), out[2], out[3])
+        if rc:
+            _lib.check(rc, self.handle)
+        self.last_ess = out[1].value
+        return bool(out[0].value)
 
     def log_ml_estimate(self):
         out = C.c_double()
