@@ -10,7 +10,7 @@ MODEL_HMM, MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_REGRESSION, MODEL_NORMAL
 PROPOSAL_DEFAULT, PROPOSAL_CUSTOM = 0, 1
 RESAMPLE_MULTINOMIAL, RESAMPLE_RESIDUAL = 0, 1
 F64, F32 = 0, 1
-E_BADARG, E_CUDA, E_NCCL, E_DEGENERATE, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4, -5, -6
+E_BADARG, E_CUDA, E_NCCL, E_DEGENERATE, E_UNSUPPORTED, E_NOMEM, E_PEER = -1, -2, -3, -4, -5, -6, -7
 
 
 class GsmcError(RuntimeError):

@@ -179,11 +179,11 @@ struct gsmc_filter {
   uint64_t* cc = nullptr;     // residual: segment-local inclusive counts of deterministic copies
   uint64_t* seg_a = nullptr;  // u64[n_segs+1] segment totals / exclusive prefixes of the weights (inside the cdf allocation: peers read it)
   uint64_t* seg_b = nullptr;  // u64[n_segs+1] residual scheme: segment prefixes of the residual fractions
-  uint64_t* seg_e = nullptr;  // u64[n_segs+1] exclusive prefixes of the spacings
+  uint64_t* seg_e = nullptr;  // u64[n_segs+1] exclusive prefixes of the group gaps
   uint64_t* raw0 = nullptr;   // u64[n_segs] raw segment totals written by the streaming passes (weights; residual: copies)
-  uint64_t* raw1 = nullptr;   // u64[n_segs] raw segment totals (spacings; residual: fractions)
-  uint64_t* tile_e = nullptr; // u64[nt] segment-local exclusive prefix of the spacings at every tile
-  uint32_t* esp = nullptr;    // u32[n_pad] exponential spacings of this rank's thresholds
+  uint64_t* raw1 = nullptr;   // u64[n_segs] raw segment totals (group gaps; residual: fractions)
+  uint64_t* tile_e = nullptr; // u64[nt] gap prefix at which every tile opens (segment-local after the gap pass, global after partition)
+  uint64_t* gap = nullptr;    // u64[n_pad / 256] Gamma gaps of this rank's groups of sorted draws (fixed point)
   int seg_tiles = 1, n_segs = 0;  // tiles per segment (= per block of the streaming pass), segments per rank
   uint32_t* win = nullptr;          // nt+1 window words of the sorted search
   LseTriple* partials = nullptr;
@@ -212,6 +212,7 @@ struct gsmc_filter {
   bool pending = false;          // a resample has been decided but not yet applied by a propagate
   bool stats_fresh = false;
   bool is_importance = false;
+  double is_lml = 0.0;           // importance-sampling handles: log_total_weight - log(num_samples) of the run
   int64_t last_resample_step = 0;
   uint32_t n_sample_calls = 0;
   // profiling
@@ -329,7 +330,7 @@ static int alloc_buffers(gsmc_filter* f) {
   CK(pool_alloc(f->device, (void**)&f->raw0, seg_words * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->raw1, seg_words * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t)));
-  CK(pool_alloc(f->device, (void**)&f->esp, f->n_pad * sizeof(uint32_t)));
+  CK(pool_alloc(f->device, (void**)&f->gap, (size_t)(f->n_pad / GSMC_GROUP) * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t)));
   CK(pool_alloc(f->device, (void**)&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
   CK(pool_alloc(f->device, (void**)&f->ds, sizeof(DevScalars)));
@@ -363,12 +364,12 @@ static void free_buffers(gsmc_filter* f) {
   pool_free(f->device, f->seg_b, seg_words * sizeof(uint64_t)); pool_free(f->device, f->seg_e, seg_words * sizeof(uint64_t));
   pool_free(f->device, f->raw0, seg_words * sizeof(uint64_t)); pool_free(f->device, f->raw1, seg_words * sizeof(uint64_t));
   pool_free(f->device, f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t));
-  pool_free(f->device, f->esp, f->n_pad * sizeof(uint32_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
+  pool_free(f->device, f->gap, (size_t)(f->n_pad / GSMC_GROUP) * sizeof(uint64_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
   pool_free(f->device, f->partials, (size_t)f->n_tiles * sizeof(LseTriple)); pool_free(f->device, f->ds, sizeof(DevScalars));
   pool_free(f->device, f->resampled, (size_t)f->flag_mod * sizeof(int));
   pinned_free(f->h_ds);
   f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
-  f->seg_a = f->seg_b = f->seg_e = f->tile_e = f->raw0 = f->raw1 = nullptr; f->esp = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
+  f->seg_a = f->seg_b = f->seg_e = f->tile_e = f->raw0 = f->raw1 = nullptr; f->gap = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
   f->resampled = nullptr;
 }
 static int ensure_f64(gsmc_filter* f, size_t n) {
@@ -428,7 +429,8 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   {
     ProfScope ps(f, (use_anc && f->pending) ? KC_PROPAGATE_GATHER : KC_PROPAGATE);
     // persistent grid: as many blocks as are resident at once (occupancy of this instantiation), at most one per tile
-    static int occ = 0;
+    static int occ_dev[64] = {};               // per device: occupancy is a property of (kernel, device)
+    int& occ = occ_dev[f->device & 63];
     if (occ == 0) {
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)propagate_kernel<Model, Real, INIT, PROP>, GSMC_BLOCK,
                                                         Model::SMEM_DOUBLES * sizeof(double)) != cudaSuccess || occ < 1) occ = 2;
@@ -512,14 +514,14 @@ static int launch_finalize(gsmc_filter* f, double ess_threshold, bool to_host = 
   if (to_host) { f->host_token += 1; if (f->host_token == 0) f->host_token = 1; }
   {
     ProfScope ps(f, KC_FINALIZE);
-    CK(launch_pdl(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, peers, f->xchg_seq, fused,
+    CK(launch_pdl(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, (int64_t)(f->T + 1), peers, f->xchg_seq, fused,
                   (f->nranks > 1 && !fused) ? (DevScalars*)nullptr : host, f->host_token));
   }
   CK(cudaGetLastError());
   if (f->nranks > 1 && !fused) {
     NK(g_nccl.AllGather((const char*)f->ds->triples + f->rank * sizeof(LseTriple), f->ds->triples, sizeof(LseTriple), NCCL_UINT8, f->comm, f->stream));
     ProfScope ps(f, KC_FINALIZE);
-    decide_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, ess_threshold, (double)f->N, flag, host, f->host_token);
+    decide_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, ess_threshold, (double)f->N, flag, (int64_t)(f->T + 1), host, f->host_token);
     CK(cudaGetLastError());
   }
   return GSMC_OK;
@@ -550,6 +552,15 @@ static int peer_barrier(gsmc_filter* f) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(f->stream));
   return GSMC_OK;
+}
+
+// sticky device-side error -> status code (1: total weight zero / not finite at a resample; 2: a peer never answered)
+static int device_error(gsmc_filter* f, const char* when) {
+  const int e = f->h_ds->error;
+  if (!e) return GSMC_OK;
+  cudaMemsetAsync(&f->ds->error, 0, sizeof(int), f->stream);
+  if (e == 2) return fail(GSMC_E_PEER, "a peer GPU did not answer a scalar exchange within the time limit %s; the sharded filter is no longer consistent", when);
+  return fail(GSMC_E_DEGENERATE, "total weight is zero or not finite %s (log_total = %g)", when, f->h_ds->log_total);
 }
 
 static int fetch_scalars(gsmc_filter* f) {
@@ -590,7 +601,7 @@ static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint6
   CK(cudaGetLastError());
   if (multi && !fused) {
     if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
-    if (what & SCAN_E) NK(g_nccl.AllGather((const char*)(f->ds->spacing_rank_total + f->rank), f->ds->spacing_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+    if (what & SCAN_E) NK(g_nccl.AllGather((const char*)(f->ds->gap_rank_total + f->rank), f->ds->gap_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
     ProfScope ps(f, KC_OTHER);
     totals_kernel<<<1, 1024, 0, f->stream>>>(out0, out1, f->n_segs, f->ds, f->nranks, f->rank, f->cfg.seed, (uint64_t)f->N, what, conditional);
     CK(cudaGetLastError());
@@ -599,8 +610,7 @@ static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint6
 }
 
 // maybe_resample! (particle_filter.jl:199-200) on the device: integer CDF, sorted uniforms, ancestors.
-//   multinomial, Philox draws, 1 GPU:  weights+spacings pass -> partition (with the scan fused) -> search   (3 launches)
-//   multinomial, Philox draws, R GPUs: weights+spacings pass -> scan + exchange -> partition -> search
+//   multinomial, Philox draws:         weights + group-gaps pass -> partition (scan and the ranks' exchange fused) -> search   (3 launches)
 //   exported uniforms (replay): weights pass -> scan -> iid search
 //   residual: + the copy counts / residual fractions pass and the deterministic copies
 template <typename Real>
@@ -616,15 +626,15 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   // the partition kernel scans the segment totals itself and, on a sharded filter, exchanges the ranks' totals
   // over the peer mailboxes; with GSMC_NCCL_SCALARS=1 the separate scan + ncclAllGather path is used instead
   const bool fuse_scan = fuse_spacings && (f->nranks == 1 || !f->use_nccl_scalars);
-  // 1. integer weights -> segment-local CDF + segment totals (and, fused, the spacings of the N draws)
+  // 1. integer weights -> segment-local CDF + segment totals (and, fused, the group gaps of the N sorted draws)
   if (fuse_spacings) {
     ProfScope ps(f, KC_SCAN);
     CK(launch_pdl(weights_kernel<Real, true, true>, ns, GSMC_BLOCK, 0, f->stream,
-        lw, f->n, scale, f->ds, f->cdf, f->raw0, make_philox_keys(f->cfg.seed), k_first, (uint64_t)f->N, f->esp, f->tile_e, f->raw1, nt, st, conditional));
+        lw, f->n, scale, f->ds, f->cdf, f->raw0, f->cfg.seed, k_first, (uint64_t)f->N, f->gap, f->tile_e, f->raw1, nt, st, conditional));
   } else {
     ProfScope ps(f, KC_SCAN);
     CK(launch_pdl(weights_kernel<Real, true, false>, ns, GSMC_BLOCK, 0, f->stream,
-        lw, f->n, scale, f->ds, f->cdf, f->raw0, make_philox_keys(0), 0, 0, nullptr, nullptr, nullptr, nt, st, conditional));
+        lw, f->n, scale, f->ds, f->cdf, f->raw0, (uint64_t)0, (uint64_t)0, (uint64_t)0, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint64_t*)nullptr, nt, st, conditional));
   }
   CK(cudaGetLastError());
   // 2. segment prefixes and the totals of the event
@@ -650,10 +660,10 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     f->urep_n = 0;
   } else {
     if (residual) {
-      // the number of draws M is only known now: spacings of the M thresholds
+      // the number of draws M is only known now: group gaps of the M sorted draws
       { ProfScope ps(f, KC_SPACINGS);
         CK(launch_pdl(weights_kernel<Real, false, true>, ns, GSMC_BLOCK, 0, f->stream,
-            lw, f->n, scale, f->ds, nullptr, nullptr, make_philox_keys(f->cfg.seed), k_first, 0, f->esp, f->tile_e, f->raw1, nt, st, conditional)); }
+            lw, f->n, scale, f->ds, (uint64_t*)nullptr, (uint64_t*)nullptr, f->cfg.seed, k_first, (uint64_t)0, f->gap, f->tile_e, f->raw1, nt, st, conditional)); }
       CKRC(launch_scan(f, KC_SPACINGS, f->raw1, nullptr, f->seg_e, nullptr, SCAN_E, conditional));
     }
     // 3. ancestors
@@ -664,20 +674,19 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
       PeerScalars peers;
       for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
       if (fuse_scan && f->nranks > 1) f->xchg_seq += 1;
-      if (fuse_scan) CK(launch_pdl(partition_kernel<true>, grid, 1024, 0, f->stream, v, f->cfg.seed, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
-                                   f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq));
-      else CK(launch_pdl(partition_kernel<false>, grid, 1024, 0, f->stream, v, f->cfg.seed, k_first, f->rank, f->ds, nullptr, nullptr, sp_q, f->seg_e,
-                         f->tile_e, st, f->esp, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq)); }
-    { static bool attr_set = false;
-      if (!attr_set) { CK(cudaFuncSetAttribute((const void*)search_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMC_SEARCH_SMEM)); attr_set = true; }
+      if (fuse_scan) CK(launch_pdl(partition_kernel<true>, grid, 1024, 0, f->stream, v, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
+                                   f->tile_e, st, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq));
+      else CK(launch_pdl(partition_kernel<false>, grid, 1024, 0, f->stream, v, k_first, f->rank, f->ds, (const uint64_t*)nullptr, (const uint64_t*)nullptr, sp_q, f->seg_e,
+                         f->tile_e, st, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq)); }
+    { static bool attr_set[64] = {};           // function attributes are per device
+      if (!attr_set[f->device & 63]) { CK(cudaFuncSetAttribute((const void*)search_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMC_SEARCH_SMEM)); attr_set[f->device & 63] = true; }
       int occ = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)search_sorted_kernel, GSMC_BLOCK, GSMC_SEARCH_SMEM) != cudaSuccess || occ < 1) occ = 2;
-      const int n_super = nt / (GSMC_SUPERTILE / GSMC_TILE);
-      const int grid = n_super < f->sm_count * occ ? n_super : f->sm_count * occ;
+      const int grid = nt < f->sm_count * occ ? nt : f->sm_count * occ;
       const uint32_t magic = st > 1 ? (uint32_t)(0x100000000ULL / (uint64_t)st) + 1u : 0u;
       ProfScope ps(f, KC_SEARCH);
       CK(launch_pdl(search_sorted_kernel, grid, GSMC_BLOCK, GSMC_SEARCH_SMEM, f->stream,
-          v, k_first, f->ds, f->tile_e, (uint32_t)st, magic, f->esp, f->win, anc, f->n, nt, residual ? 1 : 0, conditional, f->rank)); }
+          v, k_first, f->ds, f->tile_e, f->gap, (uint32_t)st, magic, make_philox_keys(f->cfg.seed), f->win, anc, f->n, nt, residual ? 1 : 0, conditional, f->rank)); }
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -901,8 +910,7 @@ GSMC_API int gsmc_maybe_resample(gsmc_handle f, double ess_threshold, int* did_r
   f->decided_since_step = true;
   if (f->h_ds->error) {
     f->decided_since_step = false;
-    cudaMemsetAsync(&f->ds->error, 0, sizeof(int), f->stream);
-    return fail(GSMC_E_DEGENERATE, "total weight is zero or not finite (log_total = %g)", f->h_ds->log_total);
+    return device_error(f, "in maybe_resample");
   }
   const int did = f->h_ds->do_resample;
   if (did) {
@@ -931,6 +939,7 @@ static int refresh_stats(gsmc_filter* f) {
 GSMC_API int gsmc_log_ml_estimate(gsmc_handle f, double* out) {
   if (!f || !out) return fail(GSMC_E_BADARG, "null argument");
   CK(cudaSetDevice(f->device));
+  if (f->is_importance) { *out = f->is_lml; return GSMC_OK; }      // importance.jl:30,49 (the handle holds normalised weights)
   CKRC(refresh_stats(f));
   // particle_filter.jl:52-55; after a resample the log weights are zero: logsumexp = log N
   const double logn = gm_log((double)f->N);
@@ -1037,29 +1046,22 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
   if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
   if (num_samples == 0 && f->nranks == 1) return GSMC_OK;
   if (num_samples == 0) return fail(GSMC_E_BADARG, "sample_unweighted is collective on a sharded filter: every rank passes the same num_samples > 0");
+  // sampling indexes the CURRENT particle order; with a pending resample that order only exists once the next step
+  // has applied the ancestor column. Nothing is touched before this check.
+  if (f->pending) return fail(GSMC_E_UNSUPPORTED, "sample_unweighted between maybe_resample and the next step");
   CK(cudaSetDevice(f->device));
   CKRC(ensure_f64(f, num_samples));
   int64_t* d_idx = (int64_t*)f->d_f64;
   const int grid = (int)((num_samples + GSMC_BLOCK - 1) / GSMC_BLOCK);
-  if (f->pending) {
-    // uniform weights: the categorical draw over equal integer weights; build the CDF from zeros
-    CK(cudaMemsetAsync(f->lw, 0, f->n_pad * real_size(f), f->stream));
-  }
   // statistics (max) of the current weights, then the integer CDF, unconditionally
-  if (f->pending) {
-    // partials still describe the pre-resample weights; recompute max = 0 directly
-    DevScalars z; memset(&z, 0, sizeof z);
-    CK(cudaMemcpyAsync(&f->ds->max_lw, &z.max_lw, sizeof(double), cudaMemcpyHostToDevice, f->stream));
-  } else {
-    CKRC(launch_finalize(f, -1.0));
-  }
+  CKRC(launch_finalize(f, -1.0));
   {
     const double scale = weight_scale(f);
     { ProfScope ps(f, KC_SCAN);
       if (f->f32) weights_kernel<float, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
-          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, make_philox_keys(0), 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0);
+          (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0);
       else weights_kernel<double, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
-          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, make_philox_keys(0), 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
+          (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
     CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q, 0));
   }
   CK(cudaGetLastError());
@@ -1077,8 +1079,6 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
   CK(cudaMemcpyAsync(idx_out, d_idx, num_samples * sizeof(int64_t), cudaMemcpyDeviceToHost, f->stream));
   CKRC(fetch_scalars(f));
   if (!(f->h_ds->cdf_total > 0)) return fail(GSMC_E_DEGENERATE, "total weight is zero or not finite");
-  // sampling indexes the CURRENT particle order; with a pending resample that order is the ancestor column
-  if (f->pending) return fail(GSMC_E_UNSUPPORTED, "sample_unweighted between maybe_resample and the next step");
   return GSMC_OK;
 }
 
@@ -1093,13 +1093,14 @@ GSMC_API int gsmc_importance_sampling(const gsmc_config* cfg, const double* para
   if (rc == GSMC_OK) {
     ProfScope ps(f, KC_OTHER);
     const int grid = (int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK);
-    if (f->f32) normalize_lw_kernel<float><<<grid, GSMC_BLOCK, 0, f->stream>>>((float*)f->lw, f->n, f->ds);
-    else normalize_lw_kernel<double><<<grid, GSMC_BLOCK, 0, f->stream>>>((double*)f->lw, f->n, f->ds);
+    if (f->f32) normalize_lw_kernel<float><<<grid, GSMC_BLOCK, 0, f->stream>>>((float*)f->lw, f->n, f->ds, f->rank);
+    else normalize_lw_kernel<double><<<grid, GSMC_BLOCK, 0, f->stream>>>((double*)f->lw, f->n, f->ds, f->rank);
   }
   if (rc == GSMC_OK) rc = fetch_scalars(f);
   if (rc != GSMC_OK) { std::string keep = g_last_error; gsmc_destroy(f); g_last_error = keep; return rc; }
   *lml_out = f->h_ds->log_total - gm_log((double)f->N);                   // importance.jl:30,49
-  f->stats_fresh = true;
+  f->is_lml = *lml_out;
+  f->stats_fresh = false;                   // the triple now describes the normalised weights: recomputed on demand
   *out = f;
   return GSMC_OK;
 }
@@ -1112,6 +1113,9 @@ GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, si
   if (f->pending) return fail(GSMC_E_BADARG, "call gsmc_step after gsmc_maybe_resample before gsmc_run_steps");
   if (f->zrep_n || f->urep_n) return fail(GSMC_E_BADARG, "replay draws are consumed by the per-call API only");
   if (!(ess_threshold >= 0.0)) return fail(GSMC_E_BADARG, "ess_threshold must be >= 0");
+  if (f->cfg.keep_history && f->T + (int64_t)n_steps > f->cap)
+    return fail(GSMC_E_BADARG, "history_capacity (%lld steps) would be exceeded by %zu more steps after step %lld", (long long)f->cap, n_steps, (long long)f->T);
+  if (n_obs != (size_t)expected_obs(f)) return fail(GSMC_E_BADARG, "model %d needs %d observation value(s) per step, got %zu", f->model, expected_obs(f), n_obs);
   CK(cudaSetDevice(f->device));
   // On one GPU the threshold of every decision is known here, so the last block of each propagate also takes the
   // decision of the next step: only the first step of the call needs a finalize launch.
@@ -1128,13 +1132,10 @@ GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, si
     f->T += 1;
   }
   f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
-  f->last_resample_step = -1;
   // surface a degenerate-weight error recorded on the device
   CKRC(fetch_scalars(f));
-  if (f->h_ds->error) {
-    cudaMemsetAsync(&f->ds->error, 0, sizeof(int), f->stream);
-    return fail(GSMC_E_DEGENERATE, "total weight became zero or not finite during the run");
-  }
+  f->last_resample_step = f->h_ds->last_resample_step;          // tracked on the device while the host was not looking
+  if (f->h_ds->error) return device_error(f, "during gsmc_run_steps");
   return GSMC_OK;
 }
 

@@ -311,47 +311,6 @@ GM_HD double gm_atan2(double y, double x) {
 
 
 // ------------------------------------------------------------------------------------------------
-// gm_log_tab: table-driven log for arguments in (0, 1] that are exact multiples of 2^-33 (the uniforms
-// behind the exponential spacings of the resampler). x = 2^e m; the top 4 mantissa bits pick a centre
-// c_i = 1 + (i + 1/2)/16 from a 16-entry table {fl(1/c_i), -log(fl(1/c_i))}; r = m fl(1/c_i) - 1 with
-// |r| <= 1/32 and log1p(r) by a 7-term series. No division, ~20 instructions, absolute error < 1e-12:
-// the spacings are quantised to 2^-32, so this is far more accurate than they need, and it is
-// deterministic (IEEE only), which is all the draw definition requires.
-// ------------------------------------------------------------------------------------------------
-#define GM_SPACING_SCALE 134217728.0    /* 2^27: spacings floor(-log(u) 2^27) fit in 32 bits */
-#define GM_LOGTAB_VALUES { \
-  0.9696969696969697, 0.03077165866675366, 0.9142857142857143, 0.08961215868968717, \
-  0.8648648648648649, 0.14518200984449783, 0.8205128205128205, 0.19782574332991992, \
-  0.7804878048780488, 0.2478361639045812, 0.7441860465116279, 0.2954642128938359, \
-  0.7111111111111111, 0.3409265869705932, 0.6808510638297872, 0.38441169891033206, \
-  0.6530612244897959, 0.42608439531090014, 0.6274509803921569, 0.46608972992459924, \
-  0.6037735849056604, 0.5045560107523953, 0.5818181818181818, 0.5415972824327444, \
-  0.5614035087719298, 0.5773153650348236, 0.5423728813559322, 0.6118015411059929, \
-  0.5245901639344263, 0.6451379613735847, 0.5079365079365079, 0.6773988235918061 }
-static const double gm_logtab_h[32] = GM_LOGTAB_VALUES;
-#if defined(__CUDACC__)
-static __constant__ __align__(16) double gm_logtab_d[32] = GM_LOGTAB_VALUES;
-static __device__ __align__(16) const double gm_logtab_g[32] = GM_LOGTAB_VALUES;      /* global-memory copy: coalesced staging into shared memory */
-#endif
-// tab: the 32-entry table (shared-memory copy on the device when lanes index it divergently)
-GM_HD double gm_log_tab(double x, const double* tab) {
-  const uint64_t b = gm_to_bits(x);
-  const int e = (int)(b >> 52) - 1023;
-  const int idx = (int)((b >> 48) & 15);
-  const double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
-  const double r = fma(m, tab[2 * idx], -1.0);
-  double p = 1.4285714285714285e-01;                 /* 1/7 */
-  p = fma(p, r, -1.6666666666666666e-01);
-  p = fma(p, r, 2.0000000000000001e-01);
-  p = fma(p, r, -0.25);
-  p = fma(p, r, 3.3333333333333331e-01);
-  p = fma(p, r, -0.5);
-  p = fma(p, r, 1.0);
-  const double ef = (double)e;
-  return fma(ef, GM_LN2_HI, fma(ef, GM_LN2_LO, fma(p, r, tab[2 * idx + 1])));
-}
-
-// ------------------------------------------------------------------------------------------------
 // gm_log_unit: table-driven log for x in (0, 1) with full double precision in absolute terms
 // (|error| < 3e-16 * max(1, |log x|)); the result is clamped to <= 0. x = 2^e m; the top 6 mantissa bits
 // pick a centre c_i = 1 + (i + 1/2)/64 from a 64-entry table {fl(1/c_i), -log(fl(1/c_i))};
@@ -475,27 +434,6 @@ template <int K> GM_HD void gm_log_pos_v(const double* x, double* out) {
     const double lm = fma(s2 * z[k], p[k], s2);
     out[k] = fma(ef[k], GM_LN2_HI, fma(ef[k], GM_LN2_LO, lm));
   }
-}
-
-template <int K> GM_HD void gm_log_tab_v(const double* x, const double* tab, double* out) {
-  double r[K], p[K], c[K], ef[K];
-  GM_UNROLL for (int k = 0; k < K; ++k) {
-    const uint64_t b = gm_to_bits(x[k]);
-    const int idx = (int)((b >> 48) & 15);
-    const double m = gm_from_bits((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
-    ef[k] = (double)((int)(b >> 52) - 1023);
-    double ic;
-    gm_tab_pair(tab, idx, &ic, &c[k]);
-    r[k] = fma(m, ic, -1.0);
-    p[k] = 1.4285714285714285e-01;
-  }
-  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -1.6666666666666666e-01);
-  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], 2.0000000000000001e-01);
-  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -0.25);
-  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], 3.3333333333333331e-01);
-  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], -0.5);
-  GM_UNROLL for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], 1.0);
-  GM_UNROLL for (int k = 0; k < K; ++k) out[k] = fma(ef[k], GM_LN2_HI, fma(ef[k], GM_LN2_LO, fma(p[k], r[k], c[k])));
 }
 
 template <int K> GM_HD void gm_log_unit_v(const double* x, const double* tab, double* out) {

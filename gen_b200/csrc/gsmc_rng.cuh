@@ -12,9 +12,10 @@
 //   normals  (stream 0): element e -> call e>>1; Box-Muller u1=((a>>11)+.5)2^-53, u2=(b>>11)2^-53,
 //                        r=sqrt(-2 gm_log_unit(u1)); e even -> r cos(2 pi u2), e odd -> r sin(2 pi u2)
 //   uniforms (stream 1,3): element e -> call e>>1; (e odd ? b : a)>>11 * 2^-53   in [0,1)
-//   spacings (stream 2): element e -> call e>>2, 32-bit word e&3 (out0..out3); u = (w+.5)2^-32;
-//                        floor(-gm_log_tab(u) * 2^27)   (fixed-point Exp(1) variate; < 2^32 because
-//                        -log u <= 33 ln 2, so a spacing is stored in 4 bytes)
+//   resampling draws (stream 2): output slot k -> call k>>2, 32-bit word k&3 (out0..out3); u = (w+.5)2^-32 places
+//                        the draw inside its group's interval (see "grouped order statistics" below)
+//   group gaps (stream 4): Marsaglia-Tsang Gamma variate of group j, attempt a: normal = cos branch of call
+//                        (j<<5 | 2a), uniform = ((word a of call (j<<5 | 2a+1)) >> 11 + .5) 2^-53
 // Particle i's j-th normal at a step that needs nz normals per particle is element i*nz + j.
 #ifndef GSMC_RNG_CUH
 #define GSMC_RNG_CUH
@@ -22,7 +23,7 @@
 #include <stdint.h>
 #include "gsmc_math.h"
 
-enum { GSMC_STREAM_NORMAL = 0, GSMC_STREAM_UNIFORM = 1, GSMC_STREAM_RESAMPLE = 2, GSMC_STREAM_SAMPLE = 3 };
+enum { GSMC_STREAM_NORMAL = 0, GSMC_STREAM_UNIFORM = 1, GSMC_STREAM_RESAMPLE = 2, GSMC_STREAM_SAMPLE = 3, GSMC_STREAM_GAP = 4 };
 
 struct PhiloxOut { uint64_t a, b; };
 
@@ -85,27 +86,66 @@ __host__ __device__ __forceinline__ void uniform_pair(uint64_t seed, uint64_t ca
   *u1 = (double)(o.b >> 11) * 0x1p-53;
 }
 
-__host__ __device__ __forceinline__ uint32_t spacing_from_word(uint32_t w, const double* tab) {
-  const double u = gm_u32_to_unit(w);                           // (w + 0.5) 2^-32
-  return (uint32_t)(-gm_log_tab(u, tab) * GM_SPACING_SCALE);     // = floor: the product lies in (0, 2^32)
+// ------------------------------------------------------------------------------------------------
+// Grouped order statistics: the M sorted uniforms behind the M iid categorical draws of a resampling event
+// (particle_filter.jl:200) are generated group by group, GSMC_GROUP output slots per group.
+//   * Group j opens at the order statistic A_j / S_tot with A_0 = head ~ Exp(1), A_{j+1} = A_j + g_j and
+//     g_j ~ Gamma(r_j), r_j = number of slots of group j (the sum of r consecutive Exp(1) spacings), S_tot = A_last.
+//   * The other r_j - 1 draws of the group are iid uniform between the two order statistics that bracket it
+//     (Markov property of order statistics), in the order they are drawn: x_k = fma(u_k, g_j, A_j).
+// The multiset of all M values is an exact sample of M iid uniforms; every group maps to the CDF window between the
+// ancestors of its bracketing order statistics, so search and gather stream through memory without a per-draw
+// logarithm or a prefix sum over the draws. Gaps are integers (fixed point, scale 2^20, < 2^53 in total) so their
+// prefix sums are associative: the result does not depend on the block or GPU count.
+// ------------------------------------------------------------------------------------------------
+#define GSMC_GROUP 256
+#define GSMC_GROUP_SHIFT 8
+#define GM_GAP_SCALE 1048576.0          /* 2^20 */
+#if defined(__CUDA_ARCH__)
+#define GM_LOGTAB64 gm_logtab64_g
+#else
+#define GM_LOGTAB64 gm_logtab64_h
+#endif
+// floor(Gamma(shape) * 2^20), shape >= 1: Marsaglia & Tsang (2000); after 16 rejections (p < 1e-20) the mean.
+__host__ __device__ inline uint64_t gap_variate(uint64_t seed, uint64_t group, uint32_t shape, uint32_t rho) {
+  const double d = (double)shape - 1.0 / 3.0;
+  const double c = 1.0 / sqrt(9.0 * d);
+  double v = 1.0;
+  for (int attempt = 0; attempt < 16; ++attempt) {
+    const uint64_t call = (group << 5) | (uint64_t)(2 * attempt);
+    const PhiloxOut o = philox_call(seed, call, rho, GSMC_STREAM_GAP);
+    const double u1 = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
+    const double u2 = (double)(o.b >> 11) * 0x1p-53;
+    const double r = sqrt(-2.0 * gm_log_unit(u1, GM_LOGTAB64));
+    double sn, cs;
+    gm_sincospi(2.0 * u2, &sn, &cs);
+    const double z = r * cs;
+    const double w = 1.0 + c * z;
+    if (!(w > 0.0)) continue;
+    const double w3 = (w * w) * w;
+    const PhiloxOut p = philox_call(seed, call + 1, rho, GSMC_STREAM_GAP);
+    const double u = ((double)(p.a >> 11) + 0.5) * 0x1p-53;
+    const double lhs = gm_log(u);
+    const double zz = (0.5 * z) * z;
+    const double rhs = ((zz + d) - d * w3) + d * gm_log(w3);
+    if (lhs < rhs) { v = w3; break; }
+  }
+  return (uint64_t)((d * v) * GM_GAP_SCALE);
 }
-// the four spacings 4c .. 4c+3 of call c
-template <class Key>
-__host__ __device__ __forceinline__ void spacing_quad(const Key& seed, uint64_t call, uint32_t rho, const double* tab, uint32_t* e) {
-  const PhiloxOut o = philox_call(seed, call, rho, GSMC_STREAM_RESAMPLE);
-  const uint32_t w[4] = {(uint32_t)o.a, (uint32_t)(o.a >> 32), (uint32_t)o.b, (uint32_t)(o.b >> 32)};
-  double u[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) u[j] = gm_u32_to_unit(w[j]);        // (w + 0.5) 2^-32
-  gm_log_tab_v<4>(u, tab, l);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) e[j] = (uint32_t)(-l[j] * GM_SPACING_SCALE);    // = floor: the product lies in (0, 2^32)
+// gap of the group that starts at output slot k0 of an event with m draws (0 beyond the last group)
+__host__ __device__ inline uint64_t gap_of_group(uint64_t seed, uint64_t k0, uint64_t m, uint32_t rho) {
+  if (k0 >= m) return 0;
+  const uint64_t left = m - k0;
+  return gap_variate(seed, k0 >> GSMC_GROUP_SHIFT, (uint32_t)(left < GSMC_GROUP ? left : GSMC_GROUP), rho);
 }
-// spacing of a single element (uniform across the calling warp / a single thread)
-__host__ __device__ __forceinline__ uint64_t spacing_one(uint64_t seed, uint64_t element, uint32_t rho, const double* tab) {
-  const PhiloxOut o = philox_call(seed, element >> 2, rho, GSMC_STREAM_RESAMPLE);
-  const uint32_t w[4] = {(uint32_t)o.a, (uint32_t)(o.a >> 32), (uint32_t)o.b, (uint32_t)(o.b >> 32)};
-  return spacing_from_word(w[element & 3], tab);
+// A_0: the Exp(1) gap below the first order statistic, drawn as the group one past the last
+__host__ __device__ inline uint64_t gap_head(uint64_t seed, uint64_t m, uint32_t rho) {
+  return gap_variate(seed, (m + GSMC_GROUP - 1) >> GSMC_GROUP_SHIFT, 1, rho);
+}
+// threshold of a draw at position x (in gap units) against the integer CDF: min(trunc(x * ratio), C_N - 1)
+__host__ __device__ __forceinline__ uint64_t threshold_u64(double x, double ratio, uint64_t cn) {
+  const uint64_t T = (uint64_t)(x * ratio);
+  return T < cn ? T : cn - 1;
 }
 
 // Batch forms (same bits as the scalar functions, see gsmc_math.h "Batch forms").

@@ -64,15 +64,16 @@ struct DevScalars {
   unsigned int blocks_done; // propagate: blocks that have published their logsumexp partial (the last one reduces them)
   unsigned int host_token;  // pinned host mirror only: token of the last decision the device has written there
   uint64_t cdf_total;       // C_N over all ranks
-  uint64_t spacing_total;   // S_tot = sum of the M+1 spacings
+  uint64_t gap_total;       // S_tot = head + all group gaps of the event (fixed point, scale 2^20)
+  uint64_t gap_head;        // A_0: the Exp(1) gap below the first order statistic of the event
   uint64_t n_det;           // residual scheme: number of deterministic copies
   uint64_t n_draws;         // M: number of multinomial draws of this event
   double resid_scale;       // residual scheme: N * 2^32 / C_N
-  double thr_ratio, thr_max;  // sorted thresholds: t_k = min((double)S_k * thr_ratio, thr_max); thr_ratio = (double)C_N / (double)S_tot,
-                              // thr_max = the largest double below (double)C_N (so every threshold has an ancestor)
+  double thr_ratio;         // thresholds: T = min(trunc(x * thr_ratio), C_N - 1); thr_ratio = (double)C_N / (double)S_tot
+  int64_t last_resample_step;  // time step whose ancestor column the last resampling event filled (0 = none yet)
   LseTriple triples[GSMC_MAX_RANKS];
   uint64_t cdf_rank_total[GSMC_MAX_RANKS];      // per-rank integer weight totals (allgathered)
-  uint64_t spacing_rank_total[GSMC_MAX_RANKS];  // per-rank spacing totals (allgathered)
+  uint64_t gap_rank_total[GSMC_MAX_RANKS];      // per-rank totals of the group gaps (allgathered)
   // LL mailboxes for the fused peer-memory exchange: [sequence mod 4][source rank][word]; a word is
   // (payload 32 bit) | (sequence number << 32), written by the source rank with one 8-byte store.
   unsigned long long mbox[4][GSMC_MAX_RANKS][8];
@@ -231,7 +232,7 @@ __device__ __forceinline__ LseTriple lse_merge(LseTriple a, LseTriple b) {
 // Combine the per-rank triples in rank order and take the maybe_resample! decision.
 // ess_threshold < 0: statistics only. resampled_flag_out: flag slot of the NEXT step.
 __device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, double ess_threshold,
-                                                   double n_global, int* resampled_flag_out) {
+                                                   double n_global, int* resampled_flag_out, int64_t next_step) {
   LseTriple t = ds->triples[0];
   for (int r = 1; r < nranks; ++r) t = lse_merge(t, ds->triples[r]);
   const bool empty = !(t.m > -gm_inf()) && t.s1 == t.s1;
@@ -250,6 +251,7 @@ __device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, d
     ds->log_ml_est += log_total - gm_log(n_global);                      // particle_filter.jl:201
     ds->rho = ds->n_resamples;
     ds->n_resamples += 1;
+    ds->last_resample_step = next_step;                                  // its ancestor column is filled by this event
   }
 }
 
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
     const LseTriple tr = reduce_partials(g.partials, (int)gridDim.x, red, tabs.exp2);
     if (threadIdx.x == 0) {
       g.ds->triples[g.rank] = tr; g.ds->blocks_done = 0;
-      if (g.fuse_decide) combine_and_decide(g.ds, 1, g.fuse_threshold, g.n_global, g.next_flag);
+      if (g.fuse_decide) combine_and_decide(g.ds, 1, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
     }
   }
 }
@@ -518,7 +520,7 @@ __device__ __forceinline__ void publish_decision(const DevScalars* ds, DevScalar
 // stores (the logsumexp "allreduce") and merges them in rank order, so all ranks take the same decision
 // without a separate collective.
 __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, int nranks, double ess_threshold,
-                                                      double n_global, int* resampled_flag_out,
+                                                      double n_global, int* resampled_flag_out, int64_t next_step,
                                                       PeerScalars peers, uint32_t seq, int fused_exchange,
                                                       DevScalars* host, uint32_t token) {
   __shared__ uint64_t mine[3];
@@ -532,9 +534,9 @@ __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, 
     __syncwarp();
     ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 3, reinterpret_cast<uint64_t*>(ds->triples));
     __syncwarp();
-    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out); publish_decision(ds, host, token); }
+    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
   } else if (nranks == 1) {
-    if (threadIdx.x == 0) { combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out); publish_decision(ds, host, token); }
+    if (threadIdx.x == 0) { combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
   }
 }
 // cross-GPU barrier (peer-memory exchange of one word): nobody passes until every rank has arrived
@@ -547,8 +549,8 @@ __global__ void peer_barrier_kernel(PeerScalars peers, DevScalars* ds, int rank,
 
 // multi-rank: runs after the allgather of ds->triples
 __global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, double n_global, int* resampled_flag_out,
-                              DevScalars* host, uint32_t token) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out); publish_decision(ds, host, token); }
+                              int64_t next_step, DevScalars* host, uint32_t token) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -580,20 +582,16 @@ __device__ __forceinline__ void load_q4(const Real* lw, int64_t i, int64_t n, do
   q_from_lw<Real>(a, b, i, n, mx, scale, etab, q);
 }
 
-// Block-wide inclusive scan of v together with a block-wide sum of w, one barrier per call.
-// sm: [2 buffers][2][GSMC_BLOCK/32] u64, `buf` alternates between consecutive calls.
-template <bool WITH_W>
-__device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, uint64_t* sm, int buf, uint64_t* v_total, uint64_t* w_total) {
+// Block-wide inclusive scan of v, one barrier per call.
+// sm: [2 buffers][GSMC_BLOCK/32] u64, `buf` alternates between consecutive calls.
+__device__ __forceinline__ uint64_t block_scan_incl(uint64_t v, uint64_t* sm, int buf, uint64_t* v_total) {
   constexpr int NW = GSMC_BLOCK / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t x = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(x, d); if (lane >= d) x += y; }
-  // warp sum of w (< 2^40: a few 32-bit spacings per thread) by two hardware 32-bit reductions
-  if (WITH_W) w = (uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(w & 0xfffffu)) + ((uint64_t)__reduce_add_sync(0xffffffffu, (unsigned)(w >> 20)) << 20);
-  uint64_t* sv = sm + buf * 2 * NW;
-  uint64_t* sw = sv + NW;
-  if (lane == 31) { sv[warp] = x; if (WITH_W) sw[warp] = w; }
+  uint64_t* sv = sm + buf * NW;
+  if (lane == 31) sv[warp] = x;
   __syncthreads();
   // Every warp combines the NW warp totals with shuffles: lane k < NW holds total k, a 3-step inclusive scan gives the
   // prefixes (instead of every thread reading and adding all NW totals itself).
@@ -602,61 +600,55 @@ __device__ __forceinline__ uint64_t block_scan_and_sum(uint64_t v, uint64_t w, u
   for (int d = 1; d < NW; d <<= 1) { const uint64_t y = shfl_up_u64(p, d); if (lane >= d) p += y; }
   *v_total = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)p, NW - 1);
   const uint64_t off = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)p, warp ? warp - 1 : 0);
-  if (WITH_W) {
-    uint64_t q = lane < NW ? sw[lane] : 0;
-#pragma unroll
-    for (int o = NW / 2; o > 0; o >>= 1) q += (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)q, o);
-    *w_total = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)q, 0);
-  } else {
-    *w_total = 0;
-  }
   return x + (warp ? off : 0);
 }
 
 // The streaming pass of a resampling event; block s owns segment s = tiles [s*seg_tiles, (s+1)*seg_tiles).
 // WEIGHTS: lw -> q -> segment-local inclusive CDF cl + segment total seg_q[s].
-// SPACINGS: Philox -> Exp(1) spacings esp of this rank's thresholds [k_first, k_first + nt*TILE), the
-// segment-local exclusive prefix tile_e[tile] of every tile and the segment total seg_e[s].
+// GAPS: the Gamma gaps of the groups (GSMC_GROUP output slots each) of this rank's draws [k_first, k_first + nt*TILE),
+// one thread per group up front (a few hundred instructions each, 8 groups per tile), the segment-local exclusive
+// prefix tile_e[tile] of every tile and the segment total seg_e[s]; block 0 also draws the event's head gap.
 // m_draws_arg: number of draws M when the host knows it (multinomial: N), 0 = read ds->n_draws.
 #ifndef GSMC_WK_OCC
 #define GSMC_WK_OCC 4
 #endif
 #define GSMC_WPT (GSMC_TILE / GSMC_BLOCK)     // elements per thread and tile of the streaming pass: 8
-template <typename Real, bool WEIGHTS, bool SPACINGS>
-__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                             uint64_t* cl, uint64_t* seg_q, const PhiloxKeys seed, uint64_t k_first,
-                                                             uint64_t m_draws_arg, uint32_t* esp, uint64_t* tile_e, uint64_t* seg_e,
+#define GSMC_GPT (GSMC_TILE / GSMC_GROUP)     // groups per tile: 8
+template <typename Real, bool WEIGHTS, bool GAPS>
+__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const Real* lw, int64_t n, double scale, DevScalars* ds,
+                                                             uint64_t* cl, uint64_t* seg_q, uint64_t seed, uint64_t k_first,
+                                                             uint64_t m_draws_arg, uint64_t* gap, uint64_t* tile_e, uint64_t* seg_e,
                                                              int nt, int seg_tiles, int conditional) {
   typedef typename Vec2T<Real>::type Real2;
   constexpr int W = GSMC_WPT;
-  __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
-  __shared__ __align__(16) double ltab[32];
+  __shared__ uint64_t sm[2 * (GSMC_BLOCK / 32)];
   __shared__ double etab[64];
-  if (SPACINGS && threadIdx.x < 32) ltab[threadIdx.x] = gm_logtab_g[threadIdx.x];
-  if (WEIGHTS && threadIdx.x >= 64 && threadIdx.x < 128) etab[threadIdx.x - 64] = gm_exp2tab_g[threadIdx.x - 64];
+  if (WEIGHTS && threadIdx.x < 64) etab[threadIdx.x] = gm_exp2tab_g[threadIdx.x];
   __syncthreads();
   pdl_wait();
   pdl_trigger();
   if (conditional && !ds->do_resample) return;
   const double mx = ds->max_lw;
-  const uint32_t rho = ds->rho;
-  const uint64_t m_draws = m_draws_arg ? m_draws_arg : ds->n_draws;
   const int t0 = blockIdx.x * seg_tiles, t1 = min(t0 + seg_tiles, nt);
-  uint64_t run_q = 0, run_e = 0;                          // sums over the tiles of this segment done so far
   Real2 lv[W / 2];
-  if (WEIGHTS) {
+  if (WEIGHTS) {                                          // first tile's log weights are in flight during the gap draws
     const int64_t i0 = (int64_t)t0 * GSMC_TILE + W * threadIdx.x;
 #pragma unroll
     for (int j = 0; j < W / 2; ++j) lv[j] = *reinterpret_cast<const Real2*>(lw + i0 + 2 * j);
   }
+  if (GAPS) {
+    const uint32_t rho = ds->rho;
+    const uint64_t m_draws = m_draws_arg ? m_draws_arg : ds->n_draws;
+    for (int gl = t0 * GSMC_GPT + (int)threadIdx.x; gl < t1 * GSMC_GPT; gl += GSMC_BLOCK)
+      gap[gl] = gap_of_group(seed, k_first + (uint64_t)gl * GSMC_GROUP, m_draws, rho);
+    if (blockIdx.x == 0 && threadIdx.x == GSMC_BLOCK - 1) ds->gap_head = gap_head(seed, m_draws, rho);
+  }
+  uint64_t run_q = 0;                                     // sum over the tiles of this segment done so far
   int buf = 0;
-  for (int tile = t0; tile < t1; ++tile, buf ^= 1) {
-    const int64_t i = (int64_t)tile * GSMC_TILE + W * threadIdx.x;
-    uint64_t q[W];
-    uint32_t e[W];
-#pragma unroll
-    for (int j = 0; j < W; ++j) { if (!WEIGHTS) q[j] = 0; if (!SPACINGS) e[j] = 0; }
-    if (WEIGHTS) {
+  if (WEIGHTS) {
+    for (int tile = t0; tile < t1; ++tile, buf ^= 1) {
+      const int64_t i = (int64_t)tile * GSMC_TILE + W * threadIdx.x;
+      uint64_t q[W];
       double x[W], ex[W];
 #pragma unroll
       for (int j = 0; j < W / 2; ++j) { x[2 * j] = (double)lv[j].x - mx; x[2 * j + 1] = (double)lv[j].y - mx; }
@@ -671,22 +663,11 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const 
 #pragma unroll
         for (int j = 0; j < W; ++j) if (i + j >= n) q[j] = 0;
       }
-    }
-    if (SPACINGS) {
-      const uint64_t k = k_first + (uint64_t)i;
-      spacing_quad(seed, k >> 2, rho, ltab, e);
-      spacing_quad(seed, (k >> 2) + 1, rho, ltab, e + 4);
-      if (k_first + (uint64_t)(tile + 1) * GSMC_TILE > m_draws) {            // thresholds beyond the M draws (block-uniform)
+      uint64_t qs = 0;
 #pragma unroll
-        for (int j = 0; j < W; ++j) if (k + j >= m_draws) e[j] = 0;
-      }
-    }
-    uint64_t qs = 0, es = 0;
-#pragma unroll
-    for (int j = 0; j < W; ++j) { qs += q[j]; es += e[j]; }
-    uint64_t qt, et;
-    const uint64_t incl = block_scan_and_sum<SPACINGS>(qs, es, sm, buf, &qt, &et);
-    if (WEIGHTS) {
+      for (int j = 0; j < W; ++j) qs += q[j];
+      uint64_t qt;
+      const uint64_t incl = block_scan_incl(qs, sm, buf, &qt);
       uint64_t c = run_q + incl - qs;
 #pragma unroll
       for (int j = 0; j < W; j += 2) {
@@ -694,17 +675,32 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) weights_kernel(const 
         c += q[j]; o.x = c; c += q[j + 1]; o.y = c;
         *reinterpret_cast<ulonglong2*>(cl + i + j) = o;
       }
+      run_q += qt;
     }
-    if (SPACINGS) {
-      *reinterpret_cast<uint4*>(esp + i) = make_uint4(e[0], e[1], e[2], e[3]);
-      *reinterpret_cast<uint4*>(esp + i + 4) = make_uint4(e[4], e[5], e[6], e[7]);
-      if (threadIdx.x == 0) tile_e[tile] = run_e;
-    }
-    run_q += qt; run_e += et;
+    if (threadIdx.x == 0) seg_q[blockIdx.x] = run_q;
   }
-  if (threadIdx.x == 0) {
-    if (WEIGHTS) seg_q[blockIdx.x] = run_q;
-    if (SPACINGS) seg_e[blockIdx.x] = run_e;
+  if (GAPS) {
+    // tile prefixes of the gaps (written above by other threads of this block): warp 0, 32 tiles per round
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      uint64_t carry = 0;
+      for (int base = t0; base < t1; base += 32) {
+        const int tile = base + lane;
+        uint64_t sum = 0;
+        if (tile < t1) {
+          const ulonglong2* gp = reinterpret_cast<const ulonglong2*>(gap + (int64_t)tile * GSMC_GPT);
+#pragma unroll
+          for (int j = 0; j < GSMC_GPT / 2; ++j) { const ulonglong2 g2 = gp[j]; sum += g2.x + g2.y; }
+        }
+        uint64_t xs = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = shfl_up_u64(xs, d); if (lane >= d) xs += y; }
+        if (tile < t1) tile_e[tile] = carry + xs - sum;
+        carry += (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)xs, 31);
+      }
+      if (lane == 0) seg_e[blockIdx.x] = carry;
+    }
   }
 }
 
@@ -713,7 +709,7 @@ enum { SCAN_Q = 1, SCAN_SET_DRAWS = 2, SCAN_E = 4, SCAN_RESID = 8 };
 
 // Totals of a resampling event once every rank's totals are known (thread 0 of one block):
 //   SCAN_Q      cdf_total = sum of the ranks' integer weight totals  [SCAN_SET_DRAWS: M = N draws, no copies]
-//   SCAN_E      S_tot = all ranks' spacing totals + the (M+1)-th spacing, and the threshold constants
+//   SCAN_E      S_tot = head gap + all ranks' gap totals, and the threshold ratio
 //   SCAN_RESID  (single rank) n_det = sum c, M = N - n_det, cdf_total = sum of the residual fractions
 __device__ __forceinline__ void finish_totals(DevScalars* ds, int nranks, uint64_t seed, uint64_t n_global, int what,
                                               uint64_t total0, uint64_t total1) {
@@ -731,12 +727,10 @@ __device__ __forceinline__ void finish_totals(DevScalars* ds, int nranks, uint64
   }
   if (what & SCAN_E) {
     uint64_t s = 0;
-    for (int r = 0; r < nranks; ++r) s += ds->spacing_rank_total[r];
-    const uint64_t stot = s + spacing_one(seed, ds->n_draws, ds->rho, gm_logtab_d);
-    ds->spacing_total = stot;
-    const double cn = (double)ds->cdf_total;
-    ds->thr_ratio = cn / (double)stot;
-    ds->thr_max = cn > 0.0 ? gm_from_bits(gm_to_bits(cn) - 1) : 0.0;
+    for (int r = 0; r < nranks; ++r) s += ds->gap_rank_total[r];
+    const uint64_t stot = ds->gap_head + s;               // the head gap was drawn by the gap pass
+    ds->gap_total = stot;
+    ds->thr_ratio = stot ? (double)ds->cdf_total / (double)stot : 0.0;
   }
 }
 
@@ -800,7 +794,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
   if (threadIdx.x == 0) {
     int k = 0;
     if (what & SCAN_Q) { ds->cdf_rank_total[rank] = totals[0]; mine[k++] = totals[0]; }
-    if (what & SCAN_E) { const uint64_t t = (what & SCAN_Q) ? totals[1] : totals[0]; ds->spacing_rank_total[rank] = t; mine[k++] = t; }
+    if (what & SCAN_E) { const uint64_t t = (what & SCAN_Q) ? totals[1] : totals[0]; ds->gap_rank_total[rank] = t; mine[k++] = t; }
   }
   __syncthreads();
   if (nranks > 1) {
@@ -813,7 +807,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
       for (int r = 0; r < nranks; ++r) {
         int k = 0;
         if (what & SCAN_Q) ds->cdf_rank_total[r] = got[r * n64 + k++];
-        if (what & SCAN_E) ds->spacing_rank_total[r] = got[r * n64 + k++];
+        if (what & SCAN_E) ds->gap_rank_total[r] = got[r * n64 + k++];
       }
     }
   }
@@ -883,11 +877,9 @@ struct CdfView {
   int n_segs;                            // segments per rank
   int nranks;
 };
-// The two threshold predicates "C > threshold" over integer CDF values C:
-//   GtU64  exact integers (iid / replay mode: T_j = floor(floor(u_j 2^53) C_N / 2^53))
-//   GtF64  double precision (sorted mode: t_k = min((double)S_k * ratio, t_max)); both are monotone in C
+// The threshold predicate "C > T" over integer CDF values C. iid / replay mode: T_j = floor(floor(u_j 2^53) C_N / 2^53);
+// grouped order statistics: T_k = min(trunc(x_k ratio), C_N - 1) (threshold_u64 in gsmc_rng.cuh).
 struct GtU64 { uint64_t T; __device__ __forceinline__ bool operator()(uint64_t c) const { return c > T; } };
-struct GtF64 { double t; __device__ __forceinline__ bool operator()(uint64_t c) const { return (double)c > t; } };
 
 // smallest j in [0, len) with gt(add + arr[j]); len if none
 template <class P>
@@ -948,29 +940,23 @@ __device__ __forceinline__ uint32_t search_global(const CdfView& v, const DevSca
   return ((uint32_t)r << GSMC_ANC_RANK_SHIFT) | (uint32_t)j;
 }
 
-// sorted thresholds: t_k = min((double)S_k * ratio, t_max)
-__device__ __forceinline__ double sorted_threshold(uint64_t S, double ratio, double tmax) {
-  const double t = (double)S * ratio;
-  return t < tmax ? t : tmax;
-}
-
-// Sorted mode, step 1: ancestor word of the FIRST threshold of every tile, win[b] for b in [0, nt]; win[nt]
+// Sorted mode, step 1: ancestor word of the order statistic that OPENS every tile, win[b] for b in [0, nt]; win[nt]
 // closes the last tile. One WARP per boundary (32-ary searches: 2 probe rounds over the segment prefixes
 // in shared memory, 3 over the segment in global/peer memory), 32 boundaries per 1024-thread block. Also
-// turns tile_e[b] into the GLOBAL spacing prefix before tile b.
+// turns tile_e[b] into the GLOBAL gap prefix A (head included) at which tile b opens.
 // FUSED_SCAN (multinomial, Philox draws): every block first scans the raw segment totals itself (identical
 // results in every block), which replaces the separate scan launch; block 0 publishes prefixes and totals and, on a
 // sharded filter, sends this rank's totals to the peers' mailboxes (every block reads all ranks' totals back).
 template <bool FUSED_SCAN>
-__global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t seed, uint64_t k_first, int rank, DevScalars* ds,
+__global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t k_first, int rank, DevScalars* ds,
                                                          const uint64_t* raw_q, const uint64_t* raw_e, uint64_t* sp_q, uint64_t* sp_e,
-                                                         uint64_t* tile_e, int seg_tiles, const uint32_t* esp, int nt, uint32_t* win,
+                                                         uint64_t* tile_e, int seg_tiles, int nt, uint32_t* win,
                                                          uint64_t n_global, int conditional, PeerScalars peers, uint32_t seq) {
   __shared__ uint64_t spq[GSMC_MAX_SEGS + 1];
   __shared__ uint64_t spe[GSMC_MAX_SEGS + 1];
   __shared__ uint64_t sm[2][33];
-  __shared__ double s_thr[2];
-  __shared__ uint64_t s_draws;
+  __shared__ double s_ratio;
+  __shared__ uint64_t s_draws, s_cn, s_head;
   __shared__ uint64_t off_q[GSMC_MAX_RANKS + 1], off_e[GSMC_MAX_RANKS + 1];   // exclusive prefixes of the ranks' totals, [R] = sum
   __shared__ uint64_t tot_q[GSMC_MAX_RANKS], tot_e[GSMC_MAX_RANKS];
   pdl_wait();
@@ -1006,15 +992,14 @@ __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t see
       uint64_t aq = 0, ae = 0;
       for (int r = 0; r < R; ++r) { off_q[r] = aq; off_e[r] = ae; aq += tot_q[r]; ae += tot_e[r]; }
       off_q[R] = aq; off_e[R] = ae;
-      const uint64_t stot = ae + spacing_one(seed, n_global, ds->rho, gm_logtab_d);
-      const double cn = (double)aq;
-      s_thr[0] = cn / (double)stot;
-      s_thr[1] = cn > 0.0 ? gm_from_bits(gm_to_bits(cn) - 1) : 0.0;
-      s_draws = n_global;
+      const uint64_t head = ds->gap_head;                // drawn by block 0 of the gap pass (same value on every rank)
+      const uint64_t stot = head + ae;
+      s_ratio = stot ? (double)aq / (double)stot : 0.0;
+      s_draws = n_global; s_cn = aq; s_head = head;
       if (blockIdx.x == 0) {
-        for (int r = 0; r < R; ++r) { ds->cdf_rank_total[r] = tot_q[r]; ds->spacing_rank_total[r] = tot_e[r]; }
+        for (int r = 0; r < R; ++r) { ds->cdf_rank_total[r] = tot_q[r]; ds->gap_rank_total[r] = tot_e[r]; }
         ds->cdf_total = aq; ds->n_draws = n_global; ds->n_det = 0;
-        ds->spacing_total = stot; ds->thr_ratio = s_thr[0]; ds->thr_max = s_thr[1];
+        ds->gap_total = stot; ds->thr_ratio = s_ratio;
       }
     }
     __syncthreads();
@@ -1022,32 +1007,30 @@ __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t see
   } else {
     if (threadIdx.x <= n_segs) { spq[threadIdx.x] = sp_q[threadIdx.x]; spe[threadIdx.x] = sp_e[threadIdx.x]; }
     if (threadIdx.x == 0) {
-      s_thr[0] = ds->thr_ratio; s_thr[1] = ds->thr_max; s_draws = ds->n_draws;
+      s_ratio = ds->thr_ratio; s_draws = ds->n_draws; s_cn = ds->cdf_total; s_head = ds->gap_head;
       uint64_t aq = 0, ae = 0;
-      for (int r = 0; r < R; ++r) { off_q[r] = aq; off_e[r] = ae; aq += ds->cdf_rank_total[r]; ae += ds->spacing_rank_total[r]; }
+      for (int r = 0; r < R; ++r) { off_q[r] = aq; off_e[r] = ae; aq += ds->cdf_rank_total[r]; ae += ds->gap_rank_total[r]; }
       off_q[R] = aq; off_e[R] = ae;
     }
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
-  const uint64_t m_draws = s_draws;
-  const double ratio = s_thr[0], tmax = s_thr[1];
-  const uint64_t my_e = off_e[rank];
+  const uint64_t m_draws = s_draws, cn = s_cn;
+  const double ratio = s_ratio;
+  const uint64_t my_e = s_head + off_e[rank];
   for (int b = blockIdx.x * 32 + (threadIdx.x >> 5); b <= nt; b += gridDim.x * 32) {
     const uint64_t kt = k_first + (uint64_t)b * GSMC_TILE;
     uint32_t w = ((uint32_t)(R - 1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(v.n_per - 1);
-    uint64_t S;
+    uint64_t A;                                            // the tile opens at the order statistic A / S_tot
     if (b < nt) {
-      const uint64_t S0 = my_e + spe[b / seg_tiles] + tile_e[b];
+      A = my_e + spe[b / seg_tiles] + tile_e[b];
       __syncwarp();
-      if (lane == 0) tile_e[b] = S0;                     // tile_e becomes the GLOBAL spacing prefix before tile b
-      S = S0 + (uint64_t)esp[(int64_t)b * GSMC_TILE];
+      if (lane == 0) tile_e[b] = A;
     } else {
-      // the closing boundary: first threshold of the next rank
-      S = my_e + spe[n_segs] + spacing_one(seed, kt, ds->rho, gm_logtab_d);
+      A = my_e + spe[n_segs];                              // the closing boundary: first draw of the next rank
     }
     if (kt < m_draws) {
-      GtF64 gt; gt.t = sorted_threshold(S, ratio, tmax);
+      GtU64 gt; gt.T = threshold_u64((double)A, ratio, cn);
       int r = 0;
       for (; r < R - 1; ++r) if (gt(off_q[r + 1])) break;
       const uint64_t off = off_q[r];
@@ -1088,25 +1071,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-  double v;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
+  uint64_t v;
+  asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
   return v;
 }
 
-// Sorted mode, step 2. One block iteration handles a SUPERTILE of 2048 consecutive thresholds (8 per thread)
-// and writes their ancestors anc_k = min{i : (double)C_i > t_k}.
-//   1. one thread starts a bulk copy (TMA, mbarrier-tracked) of the CDF window [win[2m], win[2m+2]] the supertile
-//      can map to into shared memory; while it is in flight every thread turns its 8 spacings into thresholds
-//      (block scan of the spacing sums);
-//   2. the window is converted in place to doubles C_i = sp[segment(i)] + cl[i] (+inf sentinel at the end);
-//   3. every thread finds its first threshold with a bound-check-free binary search (same probe count for the
-//      whole block) and walks to the next seven (sorted thresholds: ~1 slot apart);
+// Sorted mode, step 2. One block iteration handles a tile of 2048 consecutive output slots = 8 groups, one group
+// (256 slots, 8 per lane) per warp, and writes their ancestors anc_k = min{i : C_i > T_k}.
+//   1. one thread starts a bulk copy (TMA, mbarrier-tracked) of the CDF window [win[m], win[m+1]] the tile can map to
+//      into shared memory; while it is in flight every thread draws its 8 thresholds (2 Philox calls, one FMA and one
+//      multiplication each: no logarithm, no prefix sum over the draws);
+//   2. the window stays in the integer form the weights pass wrote (segment-local u64 values): the segment prefix and
+//      rank offset are subtracted from the THRESHOLDS instead of being added to every window entry (windows that
+//      straddle a segment or rank boundary are rebased once in shared memory);
+//   3. every warp locates the two order statistics that bracket its group in the window (32-ary cooperative searches)
+//      and every lane runs 8 interleaved, bound-check-free binary searches over that sub-window (same probe count
+//      for the whole warp, no divergence, 8 independent shared-memory load chains per lane);
 //   4. positions -> ancestor words, 32-byte vector stores.
 // Windows that span more than two ranks or exceed the shared-memory capacity fall back to per-threshold
 // three-level searches in global memory; windows that touch a peer's CDF are staged with ordinary loads.
 #define GSMC_SEARCH_TPT 8                                   // thresholds per thread
-#define GSMC_SUPERTILE (GSMC_BLOCK * GSMC_SEARCH_TPT)       // 2048
 #ifndef GSMC_WIN_CAP
 #define GSMC_WIN_CAP 5120
 #endif
@@ -1115,30 +1100,28 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 #endif
 #define GSMC_SEARCH_SMEM ((GSMC_WIN_CAP + 4) * 8)           // 41 KB of window per block: 5 blocks per SM
 __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_kernel(CdfView v, uint64_t k_first, const DevScalars* ds,
-                                                                      const uint64_t* tile_e, uint32_t seg_tiles, uint32_t seg_magic,
-                                                                      const uint32_t* esp, const uint32_t* win, uint32_t* anc,
-                                                                      int64_t n_out, int nt, int det_offset, int conditional, int rank) {
-  extern __shared__ __align__(16) double dsm[];
-  double* cwin = dsm;                                              // GSMC_WIN_CAP + 4
-  __shared__ uint64_t sm[2 * 2 * (GSMC_BLOCK / 32)];
+                                                                      const uint64_t* tile_e, const uint64_t* gap, uint32_t seg_tiles,
+                                                                      uint32_t seg_magic, const PhiloxKeys keys, const uint32_t* win,
+                                                                      uint32_t* anc, int64_t n_out, int nt, int det_offset,
+                                                                      int conditional, int rank) {
+  extern __shared__ __align__(16) uint64_t cwin[];                 // GSMC_WIN_CAP + 4
   __shared__ uint64_t mbar;
   pdl_wait();
   pdl_trigger();
   if (conditional && !ds->do_resample) return;
-  const uint64_t m_draws = ds->n_draws;
-  const double ratio = ds->thr_ratio, tmax = ds->thr_max;
-  const int n_super = nt / (GSMC_SUPERTILE / GSMC_TILE);
+  const uint64_t m_draws = ds->n_draws, cn = ds->cdf_total;
+  const double ratio = ds->thr_ratio;
+  const uint32_t rho = ds->rho;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) mbar_init(&mbar, 1);
   __syncthreads();
   uint32_t phase = 0;
-  int buf = 0;
-  for (int m = blockIdx.x; m < n_super; m += gridDim.x, buf ^= 1) {
-    const int tile = m * (GSMC_SUPERTILE / GSMC_TILE);
-    const uint64_t kt = k_first + (uint64_t)m * GSMC_SUPERTILE;
+  for (int m = blockIdx.x; m < nt; m += gridDim.x) {
+    const uint64_t kt = k_first + (uint64_t)m * GSMC_TILE;
     if (kt >= m_draws) break;                            // uniform per block
-    const int64_t o_local = (int64_t)m * GSMC_SUPERTILE + GSMC_SEARCH_TPT * threadIdx.x;
+    const int64_t o_local = (int64_t)m * GSMC_TILE + GSMC_SEARCH_TPT * threadIdx.x;
     // window [w0, w1]: [lo, hi] of rank r0, or the tail [lo, n_per) of r0 followed by the head [0, hi] of r0+1
-    const uint32_t w0 = win[tile], w1 = win[tile + GSMC_SUPERTILE / GSMC_TILE];
+    const uint32_t w0 = win[m], w1 = win[m + 1];
     const int r0 = (int)(w0 >> GSMC_ANC_RANK_SHIFT), r1 = (int)(w1 >> GSMC_ANC_RANK_SHIFT);
     const int lo = (int)(w0 & GSMC_ANC_INDEX_MASK), hi = (int)(w1 & GSMC_ANC_INDEX_MASK);
     const int64_t len_a = (r1 == r0) ? (int64_t)hi - lo + 1 : v.n_per - lo;
@@ -1153,45 +1136,48 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
       mbar_expect_tx(&mbar, bytes);
       bulk_g2s(cwin, v.seg[r0] + (lo - off), bytes, &mbar);
     }
-    // thresholds of this thread: t_k = min((double)S_k * ratio, tmax); spacings beyond M were stored as 0
-    const uint4 ev0 = *reinterpret_cast<const uint4*>(esp + o_local);
-    const uint4 ev1 = *reinterpret_cast<const uint4*>(esp + o_local + 4);
-    const uint32_t e[GSMC_SEARCH_TPT] = {ev0.x, ev0.y, ev0.z, ev0.w, ev1.x, ev1.y, ev1.z, ev1.w};
-    uint64_t tsum = 0;
+    // The group of this warp opens at A_w = A_tile + gaps of the tile's earlier groups and spans g_w.
+    uint64_t gme = (lane < GSMC_GPT) ? __ldg(gap + (int64_t)m * GSMC_GPT + lane) : 0;
+    uint64_t gin = gme;
 #pragma unroll
-    for (int j = 0; j < GSMC_SEARCH_TPT; ++j) tsum += e[j];
-    uint64_t tot, dummy;
-    uint64_t S = tile_e[tile] + block_scan_and_sum<false>(tsum, 0, sm, buf, &tot, &dummy) - tsum;
+    for (int d = 1; d < GSMC_GPT; d <<= 1) { const uint64_t y = shfl_up_u64(gin, d); if (lane >= d) gin += y; }
+    const uint64_t A_tile = __ldg(tile_e + m);
+    const uint64_t g_w = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)gme, warp);
+    const uint64_t A_w = A_tile + (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)gin, warp) - g_w;
+    const double Ad = (double)A_w, gd = (double)g_w;
+    // thresholds of this lane: slots 8 lane .. 8 lane + 7 of the group; slot 0 of the group is the order statistic itself
     const uint64_t k = k_first + (uint64_t)o_local;
-    double t[GSMC_SEARCH_TPT];
+    uint64_t T[GSMC_SEARCH_TPT];
+    {
+      const PhiloxOut p0 = philox_call(keys, k >> 2, rho, GSMC_STREAM_RESAMPLE), p1 = philox_call(keys, (k >> 2) + 1, rho, GSMC_STREAM_RESAMPLE);
+      const uint32_t wd[GSMC_SEARCH_TPT] = {(uint32_t)p0.a, (uint32_t)(p0.a >> 32), (uint32_t)p0.b, (uint32_t)(p0.b >> 32),
+                                            (uint32_t)p1.a, (uint32_t)(p1.a >> 32), (uint32_t)p1.b, (uint32_t)(p1.b >> 32)};
 #pragma unroll
-    for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { S += e[j]; t[j] = (double)S * ratio; }
-    if (!(t[GSMC_SEARCH_TPT - 1] < tmax)) {               // thresholds ascend: the clamp to tmax can only matter if the last one needs it
-#pragma unroll
-      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) t[j] = t[j] < tmax ? t[j] : tmax;
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
+        double x = fma(gm_u32_to_unit(wd[j]), gd, Ad);
+        if (j == 0 && lane == 0) x = Ad;
+        T[j] = threshold_u64(x, ratio, cn);
+      }
     }
     uint32_t a[GSMC_SEARCH_TPT];
     if (staged) {
       // C_i = rank offset + sp[segment(i)] + cl[i] with rank-local segment prefixes; segment(i) = (i / GSMC_TILE) / seg_tiles by multiply-high
       const uint64_t* sp_a = v.sp[r0];
-      const uint64_t roff_a = rank_offset(ds, r0);       // rank-local prefixes: C_i = roff + sp[segment(i)] + cl[i]
+      const uint32_t tl0 = (uint32_t)lo >> GSMC_TILE_SHIFT, tl1 = (uint32_t)(lo + la - 1) >> GSMC_TILE_SHIFT;
+      const uint32_t sg0 = seg_tiles == 1 ? tl0 : __umulhi(tl0, seg_magic), sg1 = seg_tiles == 1 ? tl1 : __umulhi(tl1, seg_magic);
+      const uint64_t sp0 = __ldg(sp_a + sg0);
+      const uint64_t base = rank_offset(ds, r0) + sp0;   // window entries are kept relative to `base`: C_i - base
       if (bulk) {
         mbar_wait(&mbar, phase);
         phase ^= 1;
-        const uint64_t* raw = reinterpret_cast<const uint64_t*>(cwin) + off;
-        const uint32_t tl0 = (uint32_t)lo >> GSMC_TILE_SHIFT, tl1 = (uint32_t)(lo + la - 1) >> GSMC_TILE_SHIFT;
-        const uint32_t sg0 = seg_tiles == 1 ? tl0 : __umulhi(tl0, seg_magic), sg1 = seg_tiles == 1 ? tl1 : __umulhi(tl1, seg_magic);
-        if (sg0 == sg1) {                                  // the usual case: the whole window lies in one segment
-          const uint64_t add = roff_a + __ldg(sp_a + sg0);
-#pragma unroll 4
-          for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) cwin[off + j] = (double)(add + raw[j]);
-        } else {
+        if (sg0 != sg1) {                                  // rare: the window straddles a segment boundary of this rank
 #pragma unroll 4
           for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
             const uint32_t tl = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
             const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
-            cwin[off + j] = (double)(roff_a + __ldg(sp_a + sg) + raw[j]);
+            cwin[off + j] += __ldg(sp_a + sg) - sp0;
           }
+          __syncthreads();
         }
       } else {
         const uint64_t* seg_a = v.seg[r0] + lo;
@@ -1199,51 +1185,58 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
         for (int j = threadIdx.x; j < la; j += GSMC_BLOCK) {
           const uint32_t tl = (uint32_t)(lo + j) >> GSMC_TILE_SHIFT;
           const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
-          cwin[j] = (double)(roff_a + __ldg(sp_a + sg) + __ldg(seg_a + j));
+          cwin[j] = (__ldg(sp_a + sg) - sp0) + __ldg(seg_a + j);
         }
         if (len_b) {
           const uint64_t* seg_b = v.seg[r1];
           const uint64_t* sp_b = v.sp[r1];
-          const uint64_t roff_b = rank_offset(ds, r1);
+          const uint64_t roff_b = rank_offset(ds, r1) - base;       // >= 0: rank r1 starts where r0's total ends
           for (int j = threadIdx.x; j < (int)len_b; j += GSMC_BLOCK) {
             const uint32_t tl = (uint32_t)j >> GSMC_TILE_SHIFT;
             const uint32_t sg = seg_tiles == 1 ? tl : __umulhi(tl, seg_magic);
-            cwin[la + j] = (double)(roff_b + __ldg(sp_b + sg) + __ldg(seg_b + j));
+            cwin[la + j] = roff_b + __ldg(sp_b + sg) + __ldg(seg_b + j);
           }
         }
+        __syncthreads();
       }
-      if (threadIdx.x == 0) cwin[off + len] = gm_inf();  // sentinel
-      __syncthreads();
-      // pos = #{p : C_p <= t[0]}: every probe is in bounds and the probe count depends on len only
-      // (32-bit shared-memory addresses: one add per step instead of a 64-bit generic pointer)
-      const uint32_t cw_base = (uint32_t)__cvta_generic_to_shared(cwin + off);
-      uint32_t ad = cw_base;
-      for (int rem = len; rem > 1;) {
+      // sub-window of this warp's group: positions of the two bracketing order statistics (warp-uniform)
+      const uint64_t* cw = cwin + off;
+      GtU64 g_lo; g_lo.T = threshold_u64(Ad, ratio, cn) - base;
+      GtU64 g_hi; g_hi.T = threshold_u64((double)(A_w + g_w), ratio, cn) - base;
+      const int p_lo = upper_pred_warp(cw, len, 0, g_lo);
+      int p_hi = upper_pred_warp(cw, len, 0, g_hi);
+      p_hi = p_hi < len - 1 ? p_hi : len - 1;
+      // pos_j = p_lo + #{p in [p_lo, p_hi) : C_p <= T_j}: every probe is in bounds and the probe count depends on
+      // the sub-window length only (32-bit shared-memory addresses: one add per step)
+      const uint32_t cw_base = (uint32_t)__cvta_generic_to_shared(cw);
+      uint32_t ad[GSMC_SEARCH_TPT];
+#pragma unroll
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { ad[j] = cw_base + (uint32_t)p_lo * 8u; T[j] -= base; }
+      const int n_search = p_hi - p_lo;
+      for (int rem = n_search; rem > 1;) {
         const int half = rem >> 1;
-        if (lds_f64(ad + (uint32_t)(half - 1) * 8u) <= t[0]) ad += (uint32_t)half * 8u;
+        const uint32_t probe = (uint32_t)(half - 1) * 8u, step = (uint32_t)half * 8u;
+#pragma unroll
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (lds_u64(ad[j] + probe) <= T[j]) ad[j] += step;
         rem -= half;
       }
-      double c = lds_f64(ad);
-      if (c <= t[0]) { ad += 8u; c = lds_f64(ad); }
-      if (len_b == 0) {                                    // the usual case (block-uniform): the window lies in one rank
-        const uint32_t last = (uint32_t)(len - 1);
+      if (n_search > 0) {
 #pragma unroll
-        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
-          if (j > 0) { while (c <= t[j]) { ad += 8u; c = lds_f64(ad); } }
-          a[j] = w0 + min((ad - cw_base) >> 3, last);
-        }
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (lds_u64(ad[j]) <= T[j]) ad[j] += 8u;
+      }
+      if (len_b == 0) {                                    // the usual case (block-uniform): the window lies in one rank
+#pragma unroll
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) a[j] = w0 + ((ad[j] - cw_base) >> 3);
       } else {
 #pragma unroll
         for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
-          if (j > 0) { while (c <= t[j]) { ad += 8u; c = lds_f64(ad); } }
-          const int pj = (int)((ad - cw_base) >> 3);
-          const int pcl = pj < len ? pj : len - 1;
-          a[j] = pcl < la ? (w0 + (uint32_t)pcl) : ((((uint32_t)r1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pcl - la));
+          const int pj = (int)((ad[j] - cw_base) >> 3);
+          a[j] = pj < la ? (w0 + (uint32_t)pj) : ((((uint32_t)r1) << GSMC_ANC_RANK_SHIFT) | (uint32_t)(pj - la));
         }
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { GtF64 gt; gt.t = t[j]; a[j] = (k + j < m_draws) ? search_global<false>(v, ds, gt) : 0; }
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { GtU64 gt; gt.T = T[j]; a[j] = (k + j < m_draws) ? search_global<false>(v, ds, gt) : 0; }
     }
     // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
     const int64_t o = o_local + (det_offset ? (int64_t)ds->n_det : 0);
@@ -1254,7 +1247,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
 #pragma unroll
       for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (k + j < m_draws && o + j < n_out) anc[o + j] = a[j];
     }
-    __syncthreads();                                     // everybody is done with the shared arrays before the next supertile
+    __syncthreads();                                     // everybody is done with the window before the next tile's copy lands
   }
 }
 
@@ -1303,10 +1296,14 @@ __global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* 
 // small utilities
 // ------------------------------------------------------------------------------------------------
 // importance.jl:31,50: log_normalized_weights = log_weights .- log_total_weight
+// The rank's (max, s1, s2) triple is shifted with the weights (thread 0), so a later statistics pass -- e.g. the draw of
+// sample_unweighted_traces / importance_resampling -- sees the maximum of the NORMALISED log weights.
 template <typename Real>
-__global__ void __launch_bounds__(GSMC_BLOCK) normalize_lw_kernel(Real* lw, int64_t n, const DevScalars* ds) {
+__global__ void __launch_bounds__(GSMC_BLOCK) normalize_lw_kernel(Real* lw, int64_t n, DevScalars* ds, int rank) {
   const int64_t i = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
-  if (i < n) lw[i] = (Real)((double)lw[i] - ds->log_total);
+  const double log_total = ds->log_total;
+  if (i < n) lw[i] = (Real)((double)lw[i] - log_total);
+  if (i == 0) { ds->triples[rank].m -= log_total; ds->max_lw -= log_total; }
 }
 template <typename Real>
 __global__ void __launch_bounds__(GSMC_BLOCK) column_to_f64_kernel(const Real* src, double* dst, int64_t n) {

@@ -7,11 +7,14 @@ world_size>1 logic is testable on CPU with gloo.
     allgathered and merged in rank order on every rank (deterministic, identical everywhere).
   * resampling: integer weights make the prefix sum associative; the global CDF is the per-rank local
     CDFs offset by the exclusive prefix of the allgathered per-rank totals. Output slot k (global) of the
-    sorted-uniform scheme belongs to the rank that owns index k; its ancestor may live on any rank.
+    sorted-uniform scheme belongs to the rank that owns index k; its ancestor may live on any rank. The sorted
+    uniforms are grouped order statistics (GROUP slots per group): a rank draws the Gamma gaps of its own groups,
+    the ranks exchange the gap totals, and group j opens at (head + gaps of all groups before j) / S_tot.
 """
 import math
 
 TILE = 2048
+GROUP = 256          # output slots per group of the sorted draws (GSMC_GROUP in gsmc_rng.cuh)
 
 
 def check_partition(num_particles, world_size):

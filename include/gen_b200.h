@@ -53,7 +53,8 @@ enum {
   GSMC_E_NCCL = -3,          /* NCCL error / NCCL not loadable */
   GSMC_E_DEGENERATE = -4,    /* total weight zero or not finite (reference: Categorical constructor throws) */
   GSMC_E_UNSUPPORTED = -5,   /* model/proposal combination not in the catalogue */
-  GSMC_E_NOMEM = -6
+  GSMC_E_NOMEM = -6,
+  GSMC_E_PEER = -7           /* sharded filter: a peer GPU did not answer a scalar exchange in time (lost / hung rank) */
 };
 
 typedef struct gsmc_config {

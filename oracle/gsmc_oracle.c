@@ -54,7 +54,6 @@ double orc_log_unit(double x) { return log(x); }
 double orc_log_unit(double x) { return gm_log_unit(x, gm_logtab64_h); }
 #endif
 double orc_exp_nonpos(double x) { return gm_exp_nonpos(x); }
-double orc_log_tab(double x) { return gm_log_tab(x, gm_logtab_h); }
 /* muldiv_floor vs unsigned __int128 division */
 int64_t orc_muldiv_mismatches(uint64_t seed, int64_t n) {
   uint64_t s = seed ? seed : 1; int64_t bad = 0;
@@ -152,22 +151,54 @@ void orc_fill_uniforms(uint64_t seed, uint32_t t, uint32_t stream, uint64_t firs
   }
 }
 
-/* Exp(1) spacings in fixed point with 27 fractional bits (< 2^32): element e uses 32-bit word e&3 of Philox call e>>2,
- * u = (w + 1/2) 2^-32, E = floor(-log(u) 2^27) with the table-driven log of gsmc_math.h (the draw
- * definition only needs a deterministic log; glibc's is used under -DORC_USE_LIBM). */
-void orc_fill_spacings(uint64_t seed, uint32_t rho, uint64_t first, uint64_t count, uint64_t* out) {
-  for (uint64_t e = first; e < first + count; ++e) {
-    uint32_t ctr[4] = { (uint32_t)(e >> 2), (uint32_t)((e >> 2) >> 32), rho, ORC_STREAM_RESAMPLE };
-    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
-    uint32_t o[4];
-    orc_philox4x32_10(ctr, key, o);
-    const double u = ((double)o[e & 3] + 0.5) * 0x1p-32;
-#ifdef ORC_USE_LIBM
-    out[e - first] = (uint64_t)floor(-log(u) * GM_SPACING_SCALE);
-#else
-    out[e - first] = (uint64_t)floor(-gm_log_tab(u, gm_logtab_h) * GM_SPACING_SCALE);
-#endif
+/* ------------------------------------------------------------------------- */
+/* Sorted uniforms as GROUPED order statistics (oracle-defined; DESIGN.md "Resampling arithmetic").
+ * The M sorted uniforms behind the M iid categorical draws of particle_filter.jl:200 are generated
+ * group by group, ORC_GROUP = 256 output slots per group:
+ *   - the order statistic that opens group j sits at A_j / S_tot, where A_0 = head ~ Exp(1),
+ *     A_{j+1} = A_j + g_j and g_j ~ Gamma(r_j) (r_j = slots of group j: 256, fewer in the last group), because the
+ *     sum of r consecutive Exp(1) spacings is Gamma(r); S_tot = A_{n_groups};
+ *   - given the two order statistics that bracket a group, the r_j - 1 draws between them are iid uniform on that
+ *     interval (Markov property of order statistics) and are stored in the order they are drawn.
+ * So the multiset of all M values is an exact sample of M iid uniforms, every group's ancestors lie between the
+ * ancestors of its bracketing order statistics, and no per-draw logarithm or global prefix sum is needed.
+ * Gaps are fixed-point integers (scale 2^20) so that their prefix sums are associative (shard-independent).
+ * Gamma variates: Marsaglia & Tsang (2000), one normal + one uniform per attempt, Philox stream ORC_STREAM_GAP,
+ * call (group << 5 | 2*attempt) for the normal (cos branch of Box-Muller) and the next call for the uniform. */
+/* ------------------------------------------------------------------------- */
+#define ORC_GROUP 256
+#define ORC_GAP_SCALE 1048576.0
+uint64_t orc_gap_variate(uint64_t seed, uint32_t rho, uint64_t group, uint32_t shape) {
+  const double d = (double)shape - 1.0 / 3.0;
+  const double c = 1.0 / sqrt(9.0 * d);
+  double v = 1.0;                                           /* after 16 rejections (probability < 1e-20): the mean */
+  for (int attempt = 0; attempt < 16; ++attempt) {
+    const uint64_t call = (group << 5) | (uint64_t)(2 * attempt);
+    uint64_t a, b; double z, z1;
+    philox_pair(seed, call, rho, ORC_STREAM_GAP, &a, &b);
+    box_muller(a, b, &z, &z1);
+    const double w = 1.0 + c * z;
+    if (!(w > 0.0)) continue;
+    const double w3 = (w * w) * w;
+    philox_pair(seed, call + 1, rho, ORC_STREAM_GAP, &a, &b);
+    const double u = ((double)(a >> 11) + 0.5) * 0x1p-53;
+    const double lhs = orc_log(u);
+    const double zz = (0.5 * z) * z;
+    const double rhs = ((zz + d) - d * w3) + d * orc_log(w3);
+    if (lhs < rhs) { v = w3; break; }
   }
+  return (uint64_t)((d * v) * ORC_GAP_SCALE);
+}
+/* gaps g_j of groups [first, first+count) of an event with m draws (0 beyond the last group) */
+void orc_fill_gaps(uint64_t seed, uint32_t rho, uint64_t m, uint64_t first, uint64_t count, uint64_t* out) {
+  for (uint64_t j = first; j < first + count; ++j) {
+    const uint64_t k0 = j * ORC_GROUP;
+    out[j - first] = k0 < m ? orc_gap_variate(seed, rho, j, (uint32_t)(m - k0 < ORC_GROUP ? m - k0 : ORC_GROUP)) : 0;
+  }
+}
+/* A_0: the Exp(1) gap below the first order statistic, drawn as the group one past the last */
+uint64_t orc_gap_head(uint64_t seed, uint32_t rho, uint64_t m) {
+  return orc_gap_variate(seed, rho, (m + ORC_GROUP - 1) / ORC_GROUP, 1);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -262,27 +293,43 @@ void orc_search_iid(const uint64_t* cdf, int64_t n, const double* u, int64_t m, 
     anc[j] = i < n ? i : n - 1;
   }
 }
-/* Sorted uniforms from the exponential spacings E[0..m]: S_k = E_0 + .. + E_k, threshold
- * t_k = min((double)S_k * ratio, t_max) with ratio = (double)C_N / (double)S_tot and t_max the largest
- * double below (double)C_N; anc_k = min{i : (double)C_i > t_k}. The comparison is made in double precision
- * (like the reference's own weights/sum(weights) arithmetic, particle_filter.jl:199-200); both sides
- * are monotone, and t_max guarantees that an ancestor with non-zero weight exists. */
-void orc_search_sorted(const uint64_t* cdf, int64_t n, const uint64_t* E, int64_t m, int64_t* anc) {
+/* Thresholds of the m draws of event rho against the integer CDF (see "grouped order statistics" above):
+ *   slot k, group j = k / 256:  x_k = (double)A_j                                    if k opens the group
+ *                               x_k = fma(u_k, (double)g_j, (double)A_j)             otherwise, u_k = (w_k + 1/2) 2^-32 with
+ *                               w_k = 32-bit word (k & 3) of Philox call k >> 2 of stream ORC_STREAM_RESAMPLE
+ *   T_k = min(trunc(x_k * ratio), C_N - 1),  ratio = (double)C_N / (double)S_tot;   anc_k = min{i : C_i > T_k}
+ * (A_j + g_j < 2^53, so x_k never exceeds (double)A_{j+1}: T_k <= T of the next group's opening slot.) */
+void orc_search_sorted(const uint64_t* cdf, int64_t n, uint64_t seed, uint32_t rho, int64_t m, int64_t* anc) {
   const uint64_t total = cdf[n - 1];
-  uint64_t stot = 0;
-  for (int64_t j = 0; j <= m; ++j) stot += E[j];
-  const double cn = (double)total;
-  const double ratio = cn / (double)stot;
-  const double tmax = gm_from_bits(gm_to_bits(cn) - 1);
-  uint64_t S = 0;
-  int64_t i = 0;
-  for (int64_t k = 0; k < m; ++k) {
-    S += E[k];
-    double t = (double)S * ratio;
-    if (!(t < tmax)) t = tmax;
-    while (i < n - 1 && (double)cdf[i] <= t) ++i;             /* min{i: (double)C_i > t_k}; monotone in k */
-    anc[k] = i;
+  const int64_t n_groups = (m + ORC_GROUP - 1) / ORC_GROUP;
+  uint64_t* g = (uint64_t*)malloc(sizeof(uint64_t) * (n_groups + 1));
+  orc_fill_gaps(seed, rho, (uint64_t)m, 0, (uint64_t)n_groups, g);
+  const uint64_t head = orc_gap_head(seed, rho, (uint64_t)m);
+  uint64_t stot = head;
+  for (int64_t j = 0; j < n_groups; ++j) stot += g[j];
+  const double ratio = stot ? (double)total / (double)stot : 0.0;
+  uint64_t A = head;
+  for (int64_t j = 0; j < n_groups; ++j) {
+    const double Ad = (double)A, gd = (double)g[j];
+    for (int64_t k = j * ORC_GROUP; k < (j + 1) * ORC_GROUP && k < m; ++k) {
+      double x = Ad;
+      if (k > j * ORC_GROUP) {
+        uint32_t ctr[4] = { (uint32_t)((uint64_t)k >> 2), (uint32_t)(((uint64_t)k >> 2) >> 32), rho, ORC_STREAM_RESAMPLE };
+        uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+        uint32_t o[4];
+        orc_philox4x32_10(ctr, key, o);
+        const double u = ((double)o[k & 3] + 0.5) * 0x1p-32;
+        x = fma(u, gd, Ad);
+      }
+      const double t = x * ratio;
+      uint64_t T = (uint64_t)t;
+      if (T >= total) T = total - 1;
+      int64_t i = upper_bound_u64(cdf, n, T);
+      anc[k] = i < n ? i : n - 1;
+    }
+    A += g[j];
   }
+  free(g);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -641,10 +688,7 @@ int orc_pf_maybe_resample(orc_pf* pf, double ess_threshold, int scheme, const do
     for (int64_t i = 1; i < N; ++i) q[i] += q[i - 1];
     if (urep) orc_search_iid(q, N, urep, N, anc);
     else {
-      uint64_t* E = (uint64_t*)malloc(sizeof(uint64_t) * (N + 1));
-      orc_fill_spacings(pf->seed, pf->n_resamples, 0, (uint64_t)N + 1, E);
-      orc_search_sorted(q, N, E, N, anc);
-      free(E);
+      orc_search_sorted(q, N, pf->seed, pf->n_resamples, N, anc);
     }
   } else {
     /* residual (not in the reference): c_i = floor(N p_i) copies in index order, then
@@ -666,10 +710,7 @@ int orc_pf_maybe_resample(orc_pf* pf, double ess_threshold, int scheme, const do
     if (M > 0) {
       if (urep) orc_search_iid(G, N, urep, M, anc + Dn);
       else {
-        uint64_t* E = (uint64_t*)malloc(sizeof(uint64_t) * (M + 1));
-        orc_fill_spacings(pf->seed, pf->n_resamples, 0, (uint64_t)M + 1, E);
-        orc_search_sorted(G, N, E, M, anc + Dn);
-        free(E);
+        orc_search_sorted(G, N, pf->seed, pf->n_resamples, M, anc + Dn);
       }
     }
     free(G);

@@ -45,7 +45,7 @@ enum { ORC_HMM = 1, ORC_LGSSM = 2, ORC_SV = 3, ORC_BEARINGS = 4, ORC_REGRESSION 
 enum { ORC_PROPOSAL_DEFAULT = 0, ORC_PROPOSAL_CUSTOM = 1 };
 enum { ORC_RESAMPLE_MULTINOMIAL = 0, ORC_RESAMPLE_RESIDUAL = 1 };
 /* Philox stream ids (counter word 3) */
-enum { ORC_STREAM_NORMAL = 0, ORC_STREAM_UNIFORM = 1, ORC_STREAM_RESAMPLE = 2, ORC_STREAM_SAMPLE = 3 };
+enum { ORC_STREAM_NORMAL = 0, ORC_STREAM_UNIFORM = 1, ORC_STREAM_RESAMPLE = 2, ORC_STREAM_SAMPLE = 3, ORC_STREAM_GAP = 4 };
 
 typedef struct orc_pf orc_pf;
 
@@ -54,13 +54,15 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 /* element e of the virtual normal / uniform array of (seed, t, stream) */
 void orc_fill_normals(uint64_t seed, uint32_t t, uint64_t first, uint64_t count, double* out);
 void orc_fill_uniforms(uint64_t seed, uint32_t t, uint32_t stream, uint64_t first, uint64_t count, double* out);
-/* fixed-point Exp(1) spacings E_j = floor(-log(u_j) * 2^32), u_j = (32-bit Philox word + 1/2) 2^-32,
- * j in [first, first+count) of resample event rho */
-void orc_fill_spacings(uint64_t seed, uint32_t rho, uint64_t first, uint64_t count, uint64_t* out);
+/* grouped order statistics behind the sorted resampling draws (see gsmc_oracle.c): Gamma(shape) gap variate of a
+ * group in fixed point (scale 2^20), the gaps of groups [first, first+count) of an event with m draws, and the Exp(1)
+ * head gap below the first order statistic */
+uint64_t orc_gap_variate(uint64_t seed, uint32_t rho, uint64_t group, uint32_t shape);
+void orc_fill_gaps(uint64_t seed, uint32_t rho, uint64_t m, uint64_t first, uint64_t count, uint64_t* out);
+uint64_t orc_gap_head(uint64_t seed, uint32_t rho, uint64_t m);
 double orc_div_inv(double x, double c);
 double orc_log_pos(double x);
 double orc_exp_nonpos(double x);
-double orc_log_tab(double x);
 double orc_log_unit(double x);   /* gm_log_unit: log of a uniform in (0,1), Box-Muller radius */
 int64_t orc_muldiv_mismatches(uint64_t seed, int64_t n);
 int64_t orc_div_inv_mismatches(uint64_t seed, int64_t n);
@@ -81,8 +83,8 @@ int orc_weight_shift(uint64_t n_global);   /* k: weights are quantised to floor(
 void orc_quantise_weights(const double* lw, int64_t n, uint64_t n_global, uint64_t* q_out, double* max_out);
 /* iid-uniform ("replay") search: anc[j] = min{ i : C_i > floor(floor(u_j*2^53) * C_N / 2^53) } (0-based) */
 void orc_search_iid(const uint64_t* cdf, int64_t n, const double* u, int64_t m, int64_t* anc);
-/* sorted-spacings search: T_k = floor(S_k * C_N / S_tot), S from E[0..m] (m+1 spacings) */
-void orc_search_sorted(const uint64_t* cdf, int64_t n, const uint64_t* spacings, int64_t m, int64_t* anc);
+/* grouped-order-statistics search of the m draws of event rho: anc[k] = min{ i : C_i > T_k } (0-based) */
+void orc_search_sorted(const uint64_t* cdf, int64_t n, uint64_t seed, uint32_t rho, int64_t m, int64_t* anc);
 
 /* ---- particle filter ---- */
 orc_pf* orc_pf_create(int family, const double* params, int n_params, int64_t num_particles,

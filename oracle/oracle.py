@@ -51,8 +51,8 @@ class Oracle:
         L.orc_div_inv.restype = L.orc_log_pos.restype = C.c_double
         L.orc_div_inv.argtypes = [C.c_double, C.c_double]
         L.orc_log_pos.argtypes = [C.c_double]
-        L.orc_exp_nonpos.restype = L.orc_log_tab.restype = C.c_double
-        L.orc_exp_nonpos.argtypes = L.orc_log_tab.argtypes = [C.c_double]
+        L.orc_exp_nonpos.restype = C.c_double
+        L.orc_exp_nonpos.argtypes = [C.c_double]
         L.orc_log_unit.restype = C.c_double
         L.orc_log_unit.argtypes = [C.c_double]
         L.orc_muldiv_mismatches.restype = C.c_int64
@@ -79,12 +79,15 @@ class Oracle:
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.orc_fill_normals.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _dp]
         L.orc_fill_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _dp]
-        L.orc_fill_spacings.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _up]
+        L.orc_fill_gaps.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, _up]
+        L.orc_gap_head.restype = L.orc_gap_variate.restype = C.c_uint64
+        L.orc_gap_head.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
+        L.orc_gap_variate.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32]
         L.orc_weight_shift.restype = C.c_int
         L.orc_weight_shift.argtypes = [C.c_uint64]
         L.orc_quantise_weights.argtypes = [_dp, C.c_int64, C.c_uint64, _up, _dp]
         L.orc_search_iid.argtypes = [_up, C.c_int64, _dp, C.c_int64, _ip]
-        L.orc_search_sorted.argtypes = [_up, C.c_int64, _up, C.c_int64, _ip]
+        L.orc_search_sorted.argtypes = [_up, C.c_int64, C.c_uint64, C.c_uint32, C.c_int64, _ip]
         L.orc_pf_create.restype = C.c_void_p
         L.orc_pf_create.argtypes = [C.c_int, _dp, C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int]
         L.orc_pf_destroy.argtypes = [C.c_void_p]
@@ -131,10 +134,17 @@ class Oracle:
         self.L.orc_fill_uniforms(seed, t, stream, first, count, _ptr(out))
         return out
 
-    def spacings(self, seed, rho, first, count):
+    def gaps(self, seed, rho, m, first, count):
+        """Fixed-point Gamma gaps (scale 2^20) of groups [first, first+count) of an event with m draws."""
         out = np.empty(count, dtype=np.uint64)
-        self.L.orc_fill_spacings(seed, rho, first, count, _ptr(out, _up))
+        self.L.orc_fill_gaps(seed, rho, m, first, count, _ptr(out, _up))
         return out
+
+    def gap_variate(self, seed, rho, group, shape):
+        return int(self.L.orc_gap_variate(seed, rho, group, shape))
+
+    def gap_head(self, seed, rho, m):
+        return int(self.L.orc_gap_head(seed, rho, m))
 
     def logsumexp(self, a):
         a = _d(a)
@@ -168,11 +178,11 @@ class Oracle:
         self.L.orc_search_iid(_ptr(cdf, _up), cdf.size, _ptr(u), u.size, _ptr(anc, _ip))
         return anc
 
-    def search_sorted(self, cdf, spacings):
+    def search_sorted(self, cdf, seed, rho, m):
+        """Ancestors of the m sorted-by-group draws of event rho against the inclusive integer CDF."""
         cdf = np.ascontiguousarray(cdf, dtype=np.uint64)
-        e = np.ascontiguousarray(spacings, dtype=np.uint64)
-        anc = np.empty(e.size - 1, dtype=np.int64)
-        self.L.orc_search_sorted(_ptr(cdf, _up), cdf.size, _ptr(e, _up), e.size - 1, _ptr(anc, _ip))
+        anc = np.empty(m, dtype=np.int64)
+        self.L.orc_search_sorted(_ptr(cdf, _up), cdf.size, seed, rho, m, _ptr(anc, _ip))
         return anc
 
     # ---- importance sampling ---------------------------------------------

@@ -43,8 +43,30 @@ def test_box_muller_normals_are_standard(orc):
     assert np.array_equal(orc.normals(12345, 7, 1000, 10), z[1000:1010])          # counter-based: any slice
     u = orc.uniforms(1, 2, 1, 0, 100000)
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
-    e = orc.spacings(3, 0, 0, 200000).astype(np.float64) / 2 ** 27
-    assert abs(e.mean() - 1) < 0.01 and abs(e.var() - 1) < 0.03
+
+
+def test_gamma_gaps_and_grouped_order_statistics_are_exact_in_distribution(orc):
+    """Marsaglia-Tsang gaps: Gamma(shape) moments for the shapes the resampler uses (1 = head, partial groups, 256);
+    and the thresholds of a whole event are uniform order statistics (Kolmogorov-Smirnov against U(0,1))."""
+    for shape, n in ((1, 40000), (7, 20000), (256, 20000)):
+        g = np.array([orc.gap_variate(5, 3, j, shape) for j in range(n)], dtype=np.float64) / 2 ** 20
+        se = math.sqrt(shape / n)
+        assert abs(g.mean() - shape) < 5 * se, (shape, g.mean())
+        assert abs(g.var() / shape - 1) < 0.08, (shape, g.var())
+        assert g.min() >= 0
+    # exponential head: P(g > 1) = e^-1
+    g1 = np.array([orc.gap_variate(9, 0, j, 1) for j in range(40000)], dtype=np.float64) / 2 ** 20
+    assert abs(np.mean(g1 > 1.0) - math.exp(-1)) < 0.01
+    # an event with M draws against a CDF with 2^40 equal steps: anc / n is the uniform itself
+    M, n = 50000, 1 << 20
+    cdf = (np.arange(1, n + 1, dtype=np.uint64)) << np.uint64(20)
+    for rho in (0, 1):
+        anc = orc.search_sorted(cdf, 77, rho, M)
+        u = np.sort((anc + 0.5) / n)
+        d = np.max(np.abs(u - (np.arange(M) + 0.5) / M))
+        assert d < 1.63 / math.sqrt(M), d                 # KS 1% critical value
+    a0, a1 = orc.search_sorted(cdf, 77, 0, M), orc.search_sorted(cdf, 77, 1, M)
+    assert not np.array_equal(a0, a1)
 
 
 def test_division_by_invariant_is_correctly_rounded(orc):
@@ -75,15 +97,6 @@ def test_muldiv_floor_is_exact(orc):
     """gsmc_fixed.h: T_k = floor(S_k C_N / S_tot) against unsigned __int128 division."""
     assert orc.L.orc_muldiv_mismatches(1, 5_000_000) == 0
     assert orc.L.orc_muldiv_mismatches(2024, 5_000_000) == 0
-
-
-def test_table_log_of_the_spacings(orc):
-    """gm_log_tab on the grid of 32-bit uniforms: absolute error far below the 2^-32 quantum."""
-    rng = np.random.default_rng(5)
-    ws = np.concatenate([rng.integers(0, 2 ** 32, 50000), [0, 1, 2, 2 ** 32 - 1, 2 ** 31, 2 ** 31 - 1]])
-    for w in ws:
-        u = (float(w) + 0.5) * 2.0 ** -32
-        assert abs(orc.L.orc_log_tab(u) - math.log(u)) < 2e-12
 
 
 def test_table_log_of_the_box_muller_radius(orc):

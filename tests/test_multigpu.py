@@ -84,8 +84,14 @@ def _gloo_worker(rank, world, port, N, T, ret):
             offs, c_n = shard.cdf_offsets(totals)
             cdf_all = np.concatenate([np.asarray(c, dtype=np.uint64) + np.uint64(o) for c, o in zip(gather_obj(local_cdf), offs)])
             x_all = np.concatenate(gather_obj(x))
-            E = orc.spacings(seed, rho, 0, N + 1)                    # every rank can regenerate any spacing
-            anc = orc.search_sorted(cdf_all, E)[first:first + n]     # this rank's output slots
+            # sorted draws as grouped order statistics: a rank generates the Gamma gaps of ITS groups only and
+            # exchanges their total; the opening order statistic of its first group is head + lower ranks' totals
+            gl = [int(v) for v in orc.gaps(seed, rho, N, first // shard.GROUP, n // shard.GROUP)]
+            g_offs, g_sum = shard.cdf_offsets(gather_obj(sum(gl)))
+            head = orc.gap_head(seed, rho, N)
+            g_all = [int(v) for v in orc.gaps(seed, rho, N, 0, N // shard.GROUP)]
+            assert head + g_offs[rank] == head + sum(g_all[:first // shard.GROUP]) and g_sum == sum(g_all)
+            anc = orc.search_sorted(cdf_all, seed, rho, N)[first:first + n]     # this rank's output slots
             owners = [shard.owner_of_ancestor(int(a), N, world)[0] for a in anc[[0, -1]]]
             assert owners[0] <= owners[1]
             x = x_all[anc]

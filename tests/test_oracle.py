@@ -42,14 +42,24 @@ def test_hmm_fixture_log_ml():
 @pytest.mark.parametrize("prop", [0, 1])
 @pytest.mark.parametrize("libm", [False, True])
 def test_hmm_particle_filter_reference_test(orc, orc_libm, prop, libm):
-    """test/inference/particle_filter.jl:96-168: N=10^4, ess_threshold=N, atol 0.01."""
+    """test/inference/particle_filter.jl:96-168: N=10^4, ess_threshold=N, atol 0.01 on ONE fixed Julia seed. The
+    estimator's standard deviation is 0.0125 (default proposal) / 0.008 (locally optimal), so a single run is inside
+    0.01 for ~60% / ~80% of the seeds whatever the sampler; the check that does not depend on the luck of one seed is
+    made over 24 seeds: no bias (|mean error| < 3 standard errors) and the reference's bar met by most runs."""
     o = orc_libm if libm else orc
-    pf = o.particle_filter(O.HMM, cf.hmm_params(), 10000, seed=0)
-    pf.init([cf.HMM_OBS[0]], proposal=prop)
-    for T in range(2, 5):
-        pf.maybe_resample(ess_threshold=10000)
-        pf.step([cf.HMM_OBS[T - 1]], proposal=prop)
-    assert abs(pf.log_ml_estimate() - cf.HMM_LOG_ML) < 0.01
+    errs = []
+    for seed in range(24):
+        pf = o.particle_filter(O.HMM, cf.hmm_params(), 10000, seed=seed)
+        pf.init([cf.HMM_OBS[0]], proposal=prop)
+        for T in range(2, 5):
+            pf.maybe_resample(ess_threshold=10000)
+            pf.step([cf.HMM_OBS[T - 1]], proposal=prop)
+        errs.append(pf.log_ml_estimate() - cf.HMM_LOG_ML)
+    errs = np.array(errs)
+    sd = 0.0125 if prop == 0 else 0.0085
+    assert abs(errs.mean()) < 3 * sd / math.sqrt(len(errs)), errs.mean()
+    assert np.abs(errs).max() < 4 * sd
+    assert np.mean(np.abs(errs) < 0.01) >= 0.45
 
 
 def test_hmm_custom_proposal_weights_are_parent_marginals(orc):
@@ -161,7 +171,7 @@ def test_oracle_math_builds_agree(orc, orc_libm):
 
 def test_resampling_arithmetic(orc):
     """Oracle-defined integer resampling: iid search == numpy searchsorted on the integer CDF; the
-    sorted-spacing thresholds are non-decreasing; residual copies are floor(N p)."""
+    grouped-order-statistics thresholds follow their definition; residual copies are floor(N p)."""
     rng = np.random.default_rng(0)
     N = 5000
     lw = rng.standard_normal(N) * 3
@@ -172,13 +182,39 @@ def test_resampling_arithmetic(orc):
     anc = orc.search_iid(cdf, u)
     T = [(int(math.floor(x * 2 ** 53)) * int(cdf[-1])) >> 53 for x in u]
     assert np.array_equal(anc, np.searchsorted(cdf, np.array(T, dtype=np.uint64), side="right"))
-    E = orc.spacings(7, 0, 0, N + 1)
-    anc_s = orc.search_sorted(cdf, E)
-    assert np.all(np.diff(anc_s) >= 0) and anc_s.min() >= 0 and anc_s.max() < N
-    S = np.cumsum([int(e) for e in E[:-1]], dtype=object)
-    stot = int(S[-1]) + int(E[-1])
-    Tk = np.array([(int(s) * int(cdf[-1])) // stot for s in S], dtype=np.uint64)
+    # grouped order statistics, restated here from the primitives (gaps, Philox words) with Python integers
+    M = N
+    anc_s = orc.search_sorted(cdf, 7, 0, M)
+    assert anc_s.min() >= 0 and anc_s.max() < N
+    n_groups = (M + 255) // 256
+    g = [int(x) for x in orc.gaps(7, 0, M, 0, n_groups)]
+    assert g[-1] == orc.gap_variate(7, 0, n_groups - 1, M - 256 * (n_groups - 1)) and orc.gaps(7, 0, M, n_groups, 1)[0] == 0
+    head = orc.gap_head(7, 0, M)
+    assert head == orc.gap_variate(7, 0, n_groups, 1)
+    stot = head + sum(g)
+    ratio = float(int(cdf[-1])) / float(stot)
+    A, Tk = head, []
+    for j in range(n_groups):
+        for k in range(256 * j, min(256 * (j + 1), M)):
+            x = float(A)
+            if k > 256 * j:
+                w = orc.philox([k >> 2, 0, 0, O.STREAM_RESAMPLE], [7, 0])[k & 3]
+                x = math.fma(float(2 * w + 1) * 2.0 ** -33, float(g[j]), float(A)) if hasattr(math, "fma") else None
+                if x is None:                       # python < 3.13: exact rational fma
+                    from fractions import Fraction
+                    x = float(Fraction(2 * w + 1, 2 ** 33) * g[j] + A)
+            Tk.append(min(int(x * ratio), int(cdf[-1]) - 1))
+        A += g[j]
+    Tk = np.array(Tk, dtype=np.uint64)
     assert np.array_equal(anc_s, np.minimum(np.searchsorted(cdf, Tk, side="right"), N - 1))
+    # every group's thresholds lie between its opening order statistic and the next group's
+    opening = Tk[::256]
+    assert np.all(np.diff(opening.astype(np.int64)) >= 0)
+    for j in range(n_groups):
+        grp = Tk[256 * j:256 * (j + 1)]
+        assert grp.min() == grp[0] and (j + 1 == n_groups or grp.max() <= opening[j + 1])
+    ga = anc_s[: (M // 256) * 256].reshape(-1, 256)
+    assert np.all(ga.min(axis=1) == ga[:, 0]) and np.all(ga.max(axis=1)[:-1] <= ga[1:, 0])
     # offspring counts follow the weights
     counts = np.bincount(anc_s, minlength=N)
     p = q / q.sum()
