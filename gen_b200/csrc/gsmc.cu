@@ -386,8 +386,15 @@ static int ensure_f64(gsmc_filter* f, size_t n) {
 // ------------------------------------------------------------------------------------------------
 // Hot-path kernels are launched with programmatic stream serialization (see pdl_wait in kernels.cuh): the
 // launch latency and the prologue of kernel k+1 overlap the tail of kernel k. GSMC_NO_PDL=1 turns it off.
-static bool pdl_enabled() { static int on = getenv("GSMC_NO_PDL") ? 0 : 1; return on != 0; }
-template <typename... KArgs, typename... Args>
+// GSMC_PDL_MASK=<bits> selects the kernel classes that may start early (bit 0 propagate, 1 finalize, 2 weights,
+// 3 partition, 4 search, 5 everything else). Default 0x3e: everything but propagate -- measured on B200 (cfg 3, ms per
+// run): all classes 24.97, none 23.02, all but propagate 22.38 (profiles/r2_pdl_masks.txt).
+enum { PDL_PROPAGATE = 0, PDL_FINALIZE, PDL_WEIGHTS, PDL_PARTITION, PDL_SEARCH, PDL_OTHER };
+static unsigned pdl_mask() {
+  static unsigned mask = getenv("GSMC_NO_PDL") ? 0u : (getenv("GSMC_PDL_MASK") ? (unsigned)strtoul(getenv("GSMC_PDL_MASK"), nullptr, 0) : 0x3eu);
+  return mask;
+}
+template <int CLS = PDL_OTHER, typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -395,7 +402,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = ((pdl_mask() >> CLS) & 1u) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 template <class Model, typename Real, bool INIT, int PROP>
@@ -437,7 +444,7 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
     }
     g.n_tiles = (int)(f->n_pad / PropTile<Model>::TILE);
     f->n_partials = g.n_tiles < f->sm_count * occ ? g.n_tiles : f->sm_count * occ;
-    CK(launch_pdl(propagate_kernel<Model, Real, INIT, PROP>, f->n_partials, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream, g, a));
+    CK(launch_pdl<PDL_PROPAGATE>(propagate_kernel<Model, Real, INIT, PROP>, f->n_partials, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream, g, a));
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -514,7 +521,7 @@ static int launch_finalize(gsmc_filter* f, double ess_threshold, bool to_host = 
   if (to_host) { f->host_token += 1; if (f->host_token == 0) f->host_token = 1; }
   {
     ProfScope ps(f, KC_FINALIZE);
-    CK(launch_pdl(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, (int64_t)(f->T + 1), peers, f->xchg_seq, fused,
+    CK(launch_pdl<PDL_FINALIZE>(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, (int64_t)(f->T + 1), peers, f->xchg_seq, fused,
                   (f->nranks > 1 && !fused) ? (DevScalars*)nullptr : host, f->host_token));
   }
   CK(cudaGetLastError());
@@ -629,11 +636,11 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   // 1. integer weights -> segment-local CDF + segment totals (and, fused, the group gaps of the N sorted draws)
   if (fuse_spacings) {
     ProfScope ps(f, KC_SCAN);
-    CK(launch_pdl(weights_kernel<Real, true, true>, ns, GSMC_BLOCK, 0, f->stream,
+    CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, true, true>, ns, GSMC_BLOCK, 0, f->stream,
         lw, f->n, scale, f->ds, f->cdf, f->raw0, f->cfg.seed, k_first, (uint64_t)f->N, f->gap, f->tile_e, f->raw1, nt, st, conditional));
   } else {
     ProfScope ps(f, KC_SCAN);
-    CK(launch_pdl(weights_kernel<Real, true, false>, ns, GSMC_BLOCK, 0, f->stream,
+    CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, true, false>, ns, GSMC_BLOCK, 0, f->stream,
         lw, f->n, scale, f->ds, f->cdf, f->raw0, (uint64_t)0, (uint64_t)0, (uint64_t)0, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint64_t*)nullptr, nt, st, conditional));
   }
   CK(cudaGetLastError());
@@ -662,7 +669,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     if (residual) {
       // the number of draws M is only known now: group gaps of the M sorted draws
       { ProfScope ps(f, KC_SPACINGS);
-        CK(launch_pdl(weights_kernel<Real, false, true>, ns, GSMC_BLOCK, 0, f->stream,
+        CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, false, true>, ns, GSMC_BLOCK, 0, f->stream,
             lw, f->n, scale, f->ds, (uint64_t*)nullptr, (uint64_t*)nullptr, f->cfg.seed, k_first, (uint64_t)0, f->gap, f->tile_e, f->raw1, nt, st, conditional)); }
       CKRC(launch_scan(f, KC_SPACINGS, f->raw1, nullptr, f->seg_e, nullptr, SCAN_E, conditional));
     }
@@ -674,9 +681,9 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
       PeerScalars peers;
       for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
       if (fuse_scan && f->nranks > 1) f->xchg_seq += 1;
-      if (fuse_scan) CK(launch_pdl(partition_kernel<true>, grid, 1024, 0, f->stream, v, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
+      if (fuse_scan) CK(launch_pdl<PDL_PARTITION>(partition_kernel<true>, grid, 1024, 0, f->stream, v, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
                                    f->tile_e, st, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq));
-      else CK(launch_pdl(partition_kernel<false>, grid, 1024, 0, f->stream, v, k_first, f->rank, f->ds, (const uint64_t*)nullptr, (const uint64_t*)nullptr, sp_q, f->seg_e,
+      else CK(launch_pdl<PDL_PARTITION>(partition_kernel<false>, grid, 1024, 0, f->stream, v, k_first, f->rank, f->ds, (const uint64_t*)nullptr, (const uint64_t*)nullptr, sp_q, f->seg_e,
                          f->tile_e, st, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq)); }
     { static bool attr_set[64] = {};           // function attributes are per device
       if (!attr_set[f->device & 63]) { CK(cudaFuncSetAttribute((const void*)search_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMC_SEARCH_SMEM)); attr_set[f->device & 63] = true; }
@@ -685,7 +692,7 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
       const int grid = nt < f->sm_count * occ ? nt : f->sm_count * occ;
       const uint32_t magic = st > 1 ? (uint32_t)(0x100000000ULL / (uint64_t)st) + 1u : 0u;
       ProfScope ps(f, KC_SEARCH);
-      CK(launch_pdl(search_sorted_kernel, grid, GSMC_BLOCK, GSMC_SEARCH_SMEM, f->stream,
+      CK(launch_pdl<PDL_SEARCH>(search_sorted_kernel, grid, GSMC_BLOCK, GSMC_SEARCH_SMEM, f->stream,
           v, k_first, f->ds, f->tile_e, f->gap, (uint32_t)st, magic, make_philox_keys(f->cfg.seed), f->win, anc, f->n, nt, residual ? 1 : 0, conditional, f->rank)); }
   }
   CK(cudaGetLastError());

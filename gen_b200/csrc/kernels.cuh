@@ -1077,21 +1077,63 @@ __device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
   return v;
 }
 
+// Key of a CDF entry inside a group's bracket [TL, TH): the largest 32-bit word that still selects a particle at or
+// before it, min(trunc((double)(C - TL) * 2^32 / (double)(TH - TL)), 2^32 - 1) (the conversion saturates).
+// (double)(u64) as fma(hi, 2^32, lo): one rounding of the exact value, i.e. the same bits as the direct conversion, with
+// two 32-bit conversions instead of the multi-instruction 64-bit one.
+__device__ __forceinline__ uint32_t bracket_key(uint64_t c_minus_tl, double r32) {
+  const double d = fma((double)(uint32_t)(c_minus_tl >> 32), 4294967296.0, (double)(uint32_t)c_minus_tl);
+  return __double2uint_rz(d * r32);
+}
+__device__ __forceinline__ double bracket_ratio(uint64_t tl, uint64_t th) { return th > tl ? 4294967296.0 / (double)(th - tl) : 0.0; }
+// global CDF value of the particle behind an ancestor word
+__device__ __forceinline__ uint64_t cdf_at(const CdfView& v, const DevScalars* ds, uint32_t word) {
+  const int r = (int)(word >> GSMC_ANC_RANK_SHIFT);
+  const uint32_t i = word & GSMC_ANC_INDEX_MASK;
+  return rank_offset(ds, r) + __ldg(v.sp[r] + i / (uint32_t)v.seg_len) + __ldg(v.seg[r] + i);
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// Bracket of a group on the global CDF, as global positions (rank * n_per + index): low word p_lo, high word p_hi.
+__device__ __noinline__ uint64_t bracket_global(const CdfView& v, const DevScalars* ds, uint64_t tl, uint64_t th) {
+  GtU64 g_lo; g_lo.T = tl;
+  GtU64 g_hi; g_hi.T = th;
+  const uint32_t wl = search_global<false>(v, ds, g_lo), wh = search_global<false>(v, ds, g_hi);
+  const uint64_t p_lo = (uint64_t)(wl >> GSMC_ANC_RANK_SHIFT) * (uint64_t)v.n_per + (wl & GSMC_ANC_INDEX_MASK);
+  const uint64_t p_hi = (uint64_t)(wh >> GSMC_ANC_RANK_SHIFT) * (uint64_t)v.n_per + (wh & GSMC_ANC_INDEX_MASK);
+  return p_lo | (p_hi << 32);
+}
+// Ancestor word of the draw with Philox word w in the bracket [p_lo, p_hi): p_lo + #{p : K_p < w}, keys evaluated per probe.
+__device__ __noinline__ uint32_t draw_global(const CdfView& v, const DevScalars* ds, uint32_t p_lo, uint32_t p_hi, uint64_t tl, double r32, uint32_t w) {
+  uint32_t l = p_lo, h = p_hi;
+  const uint32_t n_per = (uint32_t)v.n_per;
+  while (l < h) {
+    const uint32_t mid = l + ((h - l) >> 1);
+    const uint32_t word = ((mid / n_per) << GSMC_ANC_RANK_SHIFT) | (mid % n_per);
+    if (bracket_key(cdf_at(v, ds, word) - tl, r32) < w) l = mid + 1; else h = mid;
+  }
+  return ((l / n_per) << GSMC_ANC_RANK_SHIFT) | (l % n_per);
+}
+
 // Sorted mode, step 2. One block iteration handles a tile of 2048 consecutive output slots = 8 groups, one group
-// (256 slots, 8 per lane) per warp, and writes their ancestors anc_k = min{i : C_i > T_k}.
+// (256 slots, 8 per lane) per warp, and writes their ancestors.
 //   1. one thread starts a bulk copy (TMA, mbarrier-tracked) of the CDF window [win[m], win[m+1]] the tile can map to
-//      into shared memory; while it is in flight every thread draws its 8 thresholds (2 Philox calls, one FMA and one
-//      multiplication each: no logarithm, no prefix sum over the draws);
+//      into shared memory; while it is in flight every thread draws its 8 Philox words (2 calls);
 //   2. the window stays in the integer form the weights pass wrote (segment-local u64 values): the segment prefix and
 //      rank offset are subtracted from the THRESHOLDS instead of being added to every window entry (windows that
 //      straddle a segment or rank boundary are rebased once in shared memory);
-//   3. every warp locates the two order statistics that bracket its group in the window (32-ary cooperative searches)
-//      and every lane runs 8 interleaved, bound-check-free binary searches over that sub-window (same probe count
-//      for the whole warp, no divergence, 8 independent shared-memory load chains per lane);
-//   4. positions -> ancestor words, 32-byte vector stores.
-// Windows that span more than two ranks or exceed the shared-memory capacity fall back to per-threshold
-// three-level searches in global memory; windows that touch a peer's CDF are staged with ordinary loads.
-#define GSMC_SEARCH_TPT 8                                   // thresholds per thread
+//   3. every warp locates the order statistic that opens its group in the window (one 32-ary cooperative search; the
+//      closing one is the next warp's) and turns the entries of its bracket, in place, into 32-bit keys in the domain of
+//      the Philox words (one conversion per CDF entry, nothing per draw);
+//   4. every lane runs 8 interleaved, bound-check-free binary searches over the keys of the bracket (same probe count
+//      for the whole warp, no divergence, 8 independent 4-byte shared-memory load chains per lane);
+//   5. positions -> ancestor words, 32-byte vector stores.
+// Windows that span more than two ranks or exceed the shared-memory capacity fall back to per-draw searches in global
+// memory (same definition); windows that touch a peer's CDF are staged with ordinary loads.
+#define GSMC_SEARCH_TPT 8                                   // draws per thread
 #ifndef GSMC_WIN_CAP
 #define GSMC_WIN_CAP 5120
 #endif
@@ -1106,6 +1148,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
                                                                       int conditional, int rank) {
   extern __shared__ __align__(16) uint64_t cwin[];                 // GSMC_WIN_CAP + 4
   __shared__ uint64_t mbar;
+  __shared__ int s_pos[GSMC_GPT + 1];                              // window positions of the order statistics that bracket the tile's groups
   pdl_wait();
   pdl_trigger();
   if (conditional && !ds->do_resample) return;
@@ -1144,21 +1187,12 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
     const uint64_t A_tile = __ldg(tile_e + m);
     const uint64_t g_w = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)gme, warp);
     const uint64_t A_w = A_tile + (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)gin, warp) - g_w;
-    const double Ad = (double)A_w, gd = (double)g_w;
-    // thresholds of this lane: slots 8 lane .. 8 lane + 7 of the group; slot 0 of the group is the order statistic itself
+    const uint64_t TL_abs = threshold_u64((double)A_w, ratio, cn), TH_abs = threshold_u64((double)(A_w + g_w), ratio, cn);
+    // words of this lane: slots 8 lane .. 8 lane + 7 of the group; slot 0 of the group is the order statistic itself
     const uint64_t k = k_first + (uint64_t)o_local;
-    uint64_t T[GSMC_SEARCH_TPT];
-    {
-      const PhiloxOut p0 = philox_call(keys, k >> 2, rho, GSMC_STREAM_RESAMPLE), p1 = philox_call(keys, (k >> 2) + 1, rho, GSMC_STREAM_RESAMPLE);
-      const uint32_t wd[GSMC_SEARCH_TPT] = {(uint32_t)p0.a, (uint32_t)(p0.a >> 32), (uint32_t)p0.b, (uint32_t)(p0.b >> 32),
-                                            (uint32_t)p1.a, (uint32_t)(p1.a >> 32), (uint32_t)p1.b, (uint32_t)(p1.b >> 32)};
-#pragma unroll
-      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) {
-        double x = fma(gm_u32_to_unit(wd[j]), gd, Ad);
-        if (j == 0 && lane == 0) x = Ad;
-        T[j] = threshold_u64(x, ratio, cn);
-      }
-    }
+    const PhiloxOut p0 = philox_call(keys, k >> 2, rho, GSMC_STREAM_RESAMPLE), p1 = philox_call(keys, (k >> 2) + 1, rho, GSMC_STREAM_RESAMPLE);
+    const uint32_t wd[GSMC_SEARCH_TPT] = {(uint32_t)p0.a, (uint32_t)(p0.a >> 32), (uint32_t)p0.b, (uint32_t)(p0.b >> 32),
+                                          (uint32_t)p1.a, (uint32_t)(p1.a >> 32), (uint32_t)p1.b, (uint32_t)(p1.b >> 32)};
     uint32_t a[GSMC_SEARCH_TPT];
     if (staged) {
       // C_i = rank offset + sp[segment(i)] + cl[i] with rank-local segment prefixes; segment(i) = (i / GSMC_TILE) / seg_tiles by multiply-high
@@ -1199,31 +1233,53 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
         }
         __syncthreads();
       }
-      // sub-window of this warp's group: positions of the two bracketing order statistics (warp-uniform)
-      const uint64_t* cw = cwin + off;
-      GtU64 g_lo; g_lo.T = threshold_u64(Ad, ratio, cn) - base;
-      GtU64 g_hi; g_hi.T = threshold_u64((double)(A_w + g_w), ratio, cn) - base;
-      const int p_lo = upper_pred_warp(cw, len, 0, g_lo);
-      int p_hi = upper_pred_warp(cw, len, 0, g_hi);
+      // bracket of this warp's group: position of its opening order statistic (warp-uniform); the closing one is the
+      // next warp's opening one (the last warp also looks up the tile's closing one)
+      uint64_t* cw = cwin + off;
+      const uint64_t TL = TL_abs - base, TH = TH_abs - base;
+      {
+        GtU64 g_lo; g_lo.T = TL;
+        const int p = upper_pred_warp(cw, len, 0, g_lo);
+        if (lane == 0) s_pos[warp] = p;
+        if (warp == GSMC_GPT - 1) {
+          GtU64 g_hi; g_hi.T = TH;
+          const int q = upper_pred_warp(cw, len, 0, g_hi);
+          if (lane == 0) s_pos[GSMC_GPT] = q;
+        }
+      }
+      __syncthreads();                                     // all bracket searches read the u64 entries: done before any key is written
+      const int p_lo = s_pos[warp];
+      int p_hi = s_pos[warp + 1];
       p_hi = p_hi < len - 1 ? p_hi : len - 1;
-      // pos_j = p_lo + #{p in [p_lo, p_hi) : C_p <= T_j}: every probe is in bounds and the probe count depends on
-      // the sub-window length only (32-bit shared-memory addresses: one add per step)
-      const uint32_t cw_base = (uint32_t)__cvta_generic_to_shared(cw);
+      // keys of the bracket, in place (low word of each 8-byte entry); brackets of different warps are disjoint
+      const double r32 = bracket_ratio(TL, TH);
+      for (int p = p_lo + lane; p < p_hi; p += 32) {
+        const uint32_t key = bracket_key(cw[p] - TL, r32);
+        *reinterpret_cast<uint32_t*>(cw + p) = key;
+      }
+      __syncwarp();
+      // pos_j = p_lo + #{p in [p_lo, p_hi) : K_p < w_j}: every probe is in bounds and the probe count depends on
+      // the bracket length only (32-bit shared-memory addresses: one add per step)
+      uint32_t cw_base = (uint32_t)__cvta_generic_to_shared(cw);
+      asm volatile("" : "+r"(cw_base) :: "memory");        // the probes below (plain asm loads) stay behind the key stores
       uint32_t ad[GSMC_SEARCH_TPT];
 #pragma unroll
-      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { ad[j] = cw_base + (uint32_t)p_lo * 8u; T[j] -= base; }
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) ad[j] = cw_base + (uint32_t)p_lo * 8u;
+      // (halving by n/2, n/4, ... rather than a power-of-two ladder with immediate offsets: power-of-two strides put
+      // every lane's probe into the same shared-memory bank, measured 143 us against 107 us)
       const int n_search = p_hi - p_lo;
       for (int rem = n_search; rem > 1;) {
         const int half = rem >> 1;
         const uint32_t probe = (uint32_t)(half - 1) * 8u, step = (uint32_t)half * 8u;
 #pragma unroll
-        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (lds_u64(ad[j] + probe) <= T[j]) ad[j] += step;
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (lds_u32(ad[j] + probe) < wd[j]) ad[j] += step;
         rem -= half;
       }
       if (n_search > 0) {
 #pragma unroll
-        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (lds_u64(ad[j]) <= T[j]) ad[j] += 8u;
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (lds_u32(ad[j]) < wd[j]) ad[j] += 8u;
       }
+      if (lane == 0) ad[0] = cw_base + (uint32_t)p_lo * 8u;        // the order statistic that opens the group
       if (len_b == 0) {                                    // the usual case (block-uniform): the window lies in one rank
 #pragma unroll
         for (int j = 0; j < GSMC_SEARCH_TPT; ++j) a[j] = w0 + ((ad[j] - cw_base) >> 3);
@@ -1235,10 +1291,14 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
         }
       }
     } else {
+      // same definition on the global CDF (out of line: rare, and the hot loop stays small)
+      const uint64_t br = bracket_global(v, ds, TL_abs, TH_abs);
+      const double r32 = bracket_ratio(TL_abs, TH_abs);
 #pragma unroll
-      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) { GtU64 gt; gt.T = T[j]; a[j] = (k + j < m_draws) ? search_global<false>(v, ds, gt) : 0; }
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j)
+        a[j] = draw_global(v, ds, (uint32_t)br, (j == 0 && lane == 0) ? (uint32_t)br : (uint32_t)(br >> 32), TL_abs, r32, wd[j]);
     }
-    // output slot of threshold k: (k - k_first) [+ n_det for the residual scheme]
+    // output slot of draw k: (k - k_first) [+ n_det for the residual scheme]
     const int64_t o = o_local + (det_offset ? (int64_t)ds->n_det : 0);
     if (!det_offset && k + GSMC_SEARCH_TPT <= m_draws && o + GSMC_SEARCH_TPT <= n_out) {
       *reinterpret_cast<uint4*>(anc + o) = make_uint4(a[0], a[1], a[2], a[3]);

@@ -293,12 +293,25 @@ void orc_search_iid(const uint64_t* cdf, int64_t n, const double* u, int64_t m, 
     anc[j] = i < n ? i : n - 1;
   }
 }
-/* Thresholds of the m draws of event rho against the integer CDF (see "grouped order statistics" above):
- *   slot k, group j = k / 256:  x_k = (double)A_j                                    if k opens the group
- *                               x_k = fma(u_k, (double)g_j, (double)A_j)             otherwise, u_k = (w_k + 1/2) 2^-32 with
- *                               w_k = 32-bit word (k & 3) of Philox call k >> 2 of stream ORC_STREAM_RESAMPLE
- *   T_k = min(trunc(x_k * ratio), C_N - 1),  ratio = (double)C_N / (double)S_tot;   anc_k = min{i : C_i > T_k}
- * (A_j + g_j < 2^53, so x_k never exceeds (double)A_{j+1}: T_k <= T of the next group's opening slot.) */
+/* Ancestors of the m draws of event rho against the integer CDF (see "grouped order statistics" above).
+ * Position x (gap units) maps to the integer threshold thr(x) = min(trunc((double)x * ratio), C_N - 1),
+ * ratio = (double)C_N / (double)S_tot. Group j = slots [256 j, 256 j + r_j) is bracketed by TL = thr(A_j) and
+ * TH = thr(A_j + g_j), i.e. by the CDF positions p_lo = min{i : C_i > TL} and p_hi = min(min{i : C_i > TH}, n - 1).
+ *   slot k that opens the group:  anc_k = p_lo  (the order statistic itself)
+ *   any other slot: w_k = 32-bit word (k & 3) of Philox call k >> 2 of stream ORC_STREAM_RESAMPLE places the draw at
+ *                   TL + w_k (TH - TL) / 2^32; compared in the domain of the 32-bit words:
+ *                   anc_k = p_lo + #{p in [p_lo, p_hi) : K_p < w_k},
+ *                   K_p = min(trunc((double)(C_p - TL) * (2^32 / (double)(TH - TL))), 2^32 - 1)
+ * (K_p is the largest word that still selects a particle <= p; it is non-decreasing in p, so the count is a binary
+ * search. No per-draw floating-point arithmetic is left: one conversion per CDF entry of the bracket.) */
+static uint64_t thr_of(uint64_t x, double ratio, uint64_t total) {
+  uint64_t T = (uint64_t)((double)x * ratio);
+  return T < total ? T : total - 1;
+}
+uint32_t orc_bracket_key(uint64_t c_minus_tl, double r32) {
+  const double x = (double)c_minus_tl * r32;
+  return x >= 4294967295.0 ? 0xffffffffu : (uint32_t)x;
+}
 void orc_search_sorted(const uint64_t* cdf, int64_t n, uint64_t seed, uint32_t rho, int64_t m, int64_t* anc) {
   const uint64_t total = cdf[n - 1];
   const int64_t n_groups = (m + ORC_GROUP - 1) / ORC_GROUP;
@@ -310,22 +323,27 @@ void orc_search_sorted(const uint64_t* cdf, int64_t n, uint64_t seed, uint32_t r
   const double ratio = stot ? (double)total / (double)stot : 0.0;
   uint64_t A = head;
   for (int64_t j = 0; j < n_groups; ++j) {
-    const double Ad = (double)A, gd = (double)g[j];
+    const uint64_t TL = thr_of(A, ratio, total), TH = thr_of(A + g[j], ratio, total);
+    const int64_t p_lo = upper_bound_u64(cdf, n, TL);
+    int64_t p_hi = upper_bound_u64(cdf, n, TH);
+    if (p_hi > n - 1) p_hi = n - 1;
+    const double r32 = TH > TL ? 4294967296.0 / (double)(TH - TL) : 0.0;
     for (int64_t k = j * ORC_GROUP; k < (j + 1) * ORC_GROUP && k < m; ++k) {
-      double x = Ad;
+      int64_t pos = p_lo;
       if (k > j * ORC_GROUP) {
         uint32_t ctr[4] = { (uint32_t)((uint64_t)k >> 2), (uint32_t)(((uint64_t)k >> 2) >> 32), rho, ORC_STREAM_RESAMPLE };
         uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
         uint32_t o[4];
         orc_philox4x32_10(ctr, key, o);
-        const double u = ((double)o[k & 3] + 0.5) * 0x1p-32;
-        x = fma(u, gd, Ad);
+        const uint32_t w = o[k & 3];
+        int64_t lo = p_lo, hi = p_hi;                      /* first p in [p_lo, p_hi) with K_p >= w, else p_hi */
+        while (lo < hi) {
+          const int64_t mid = lo + ((hi - lo) >> 1);
+          if (orc_bracket_key(cdf[mid] - TL, r32) < w) lo = mid + 1; else hi = mid;
+        }
+        pos = lo;
       }
-      const double t = x * ratio;
-      uint64_t T = (uint64_t)t;
-      if (T >= total) T = total - 1;
-      int64_t i = upper_bound_u64(cdf, n, T);
-      anc[k] = i < n ? i : n - 1;
+      anc[k] = pos;
     }
     A += g[j];
   }

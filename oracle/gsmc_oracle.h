@@ -83,7 +83,9 @@ int orc_weight_shift(uint64_t n_global);   /* k: weights are quantised to floor(
 void orc_quantise_weights(const double* lw, int64_t n, uint64_t n_global, uint64_t* q_out, double* max_out);
 /* iid-uniform ("replay") search: anc[j] = min{ i : C_i > floor(floor(u_j*2^53) * C_N / 2^53) } (0-based) */
 void orc_search_iid(const uint64_t* cdf, int64_t n, const double* u, int64_t m, int64_t* anc);
-/* grouped-order-statistics search of the m draws of event rho: anc[k] = min{ i : C_i > T_k } (0-based) */
+/* grouped-order-statistics search of the m draws of event rho (0-based ancestors): the slot that opens a group takes
+ * the group's lower bracket position; every other slot counts the 32-bit bracket keys below its Philox word */
+uint32_t orc_bracket_key(uint64_t c_minus_tl, double r32);   /* min(trunc((double)(C_p - TL) * r32), 2^32 - 1) */
 void orc_search_sorted(const uint64_t* cdf, int64_t n, uint64_t seed, uint32_t rho, int64_t m, int64_t* anc);
 
 /* ---- particle filter ---- */

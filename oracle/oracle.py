@@ -87,6 +87,8 @@ class Oracle:
         L.orc_weight_shift.argtypes = [C.c_uint64]
         L.orc_quantise_weights.argtypes = [_dp, C.c_int64, C.c_uint64, _up, _dp]
         L.orc_search_iid.argtypes = [_up, C.c_int64, _dp, C.c_int64, _ip]
+        L.orc_bracket_key.restype = C.c_uint32
+        L.orc_bracket_key.argtypes = [C.c_uint64, C.c_double]
         L.orc_search_sorted.argtypes = [_up, C.c_int64, C.c_uint64, C.c_uint32, C.c_int64, _ip]
         L.orc_pf_create.restype = C.c_void_p
         L.orc_pf_create.argtypes = [C.c_int, _dp, C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int]

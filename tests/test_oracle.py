@@ -192,27 +192,35 @@ def test_resampling_arithmetic(orc):
     head = orc.gap_head(7, 0, M)
     assert head == orc.gap_variate(7, 0, n_groups, 1)
     stot = head + sum(g)
-    ratio = float(int(cdf[-1])) / float(stot)
-    A, Tk = head, []
+    total = int(cdf[-1])
+    ratio = float(total) / float(stot)
+    thr = lambda x: min(int(float(x) * ratio), total - 1)
+    cl = [int(c) for c in cdf]
+    A, exp_anc = head, []
     for j in range(n_groups):
+        TL, TH = thr(A), thr(A + g[j])
+        p_lo = int(np.searchsorted(cdf, np.uint64(TL), side="right"))
+        p_hi = min(int(np.searchsorted(cdf, np.uint64(TH), side="right")), N - 1)
+        r32 = 4294967296.0 / float(TH - TL) if TH > TL else 0.0
+        keys = [min(int(float(cl[p] - TL) * r32), 2 ** 32 - 1) for p in range(p_lo, p_hi)]
+        assert keys == sorted(keys) and all(orc.L.orc_bracket_key(cl[p] - TL, r32) == k for p, k in zip(range(p_lo, p_hi), keys))
         for k in range(256 * j, min(256 * (j + 1), M)):
-            x = float(A)
-            if k > 256 * j:
+            if k == 256 * j:
+                exp_anc.append(p_lo)
+            else:
                 w = orc.philox([k >> 2, 0, 0, O.STREAM_RESAMPLE], [7, 0])[k & 3]
-                x = math.fma(float(2 * w + 1) * 2.0 ** -33, float(g[j]), float(A)) if hasattr(math, "fma") else None
-                if x is None:                       # python < 3.13: exact rational fma
-                    from fractions import Fraction
-                    x = float(Fraction(2 * w + 1, 2 ** 33) * g[j] + A)
-            Tk.append(min(int(x * ratio), int(cdf[-1]) - 1))
+                exp_anc.append(p_lo + sum(1 for kk in keys if kk < w))
         A += g[j]
-    Tk = np.array(Tk, dtype=np.uint64)
-    assert np.array_equal(anc_s, np.minimum(np.searchsorted(cdf, Tk, side="right"), N - 1))
-    # every group's thresholds lie between its opening order statistic and the next group's
-    opening = Tk[::256]
-    assert np.all(np.diff(opening.astype(np.int64)) >= 0)
-    for j in range(n_groups):
-        grp = Tk[256 * j:256 * (j + 1)]
-        assert grp.min() == grp[0] and (j + 1 == n_groups or grp.max() <= opening[j + 1])
+    assert np.array_equal(anc_s, np.array(exp_anc))
+    # the draw of word w sits at TL + w (TH - TL) / 2^32: its ancestor is the exact integer search up to the rounding of one key
+    A = head
+    for j in range(min(n_groups, 3)):
+        TL, TH = thr(A), thr(A + g[j])
+        for k in range(256 * j + 1, 256 * j + 40):
+            w = orc.philox([k >> 2, 0, 0, O.STREAM_RESAMPLE], [7, 0])[k & 3]
+            exact = min(int(np.searchsorted(cdf, np.uint64(TL + (w * (TH - TL) >> 32)), side="right")), N - 1)
+            assert abs(int(anc_s[k]) - exact) <= 1
+        A += g[j]
     ga = anc_s[: (M // 256) * 256].reshape(-1, 256)
     assert np.all(ga.min(axis=1) == ga[:, 0]) and np.all(ga.max(axis=1)[:-1] <= ga[1:, 0])
     # offspring counts follow the weights
