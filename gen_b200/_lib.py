@@ -55,6 +55,13 @@ SIGNATURES = {
     "gsmc_comm_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
     "gsmc_comm_destroy": (None, [_H]),
     "gsmc_comm_attach": (C.c_int, [_H, _H]),
+    "gsmc_group_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_H)]),
+    "gsmc_group_destroy": (None, [_H]),
+    "gsmc_group_attach": (C.c_int, [_H, C.c_int, _H]),
+    "gsmc_group_init": (C.c_int, [_H, _dp, C.c_size_t, C.c_int, _dp, C.c_size_t]),
+    "gsmc_group_step": (C.c_int, [_H, _dp, C.c_size_t, C.c_int, _dp, C.c_size_t]),
+    "gsmc_group_maybe_resample": (C.c_int, [_H, C.c_double, C.POINTER(C.c_int), _dp]),
+    "gsmc_group_sample_unweighted": (C.c_int, [_H, C.c_uint64, _ip]),
     "gsmc_set_replay": (C.c_int, [_H, _dp, C.c_size_t, _dp, C.c_size_t]),
     "gsmc_init": (C.c_int, [_H, _dp, C.c_size_t, C.c_int, _dp, C.c_size_t]),
     "gsmc_step": (C.c_int, [_H, _dp, C.c_size_t, C.c_int, _dp, C.c_size_t]),

@@ -152,6 +152,17 @@ struct gsmc_comm_s {
   int rank = 0, nranks = 1, device = 0;
 };
 
+struct gsmc_filter;
+// Shard emulation: R logical ranks of one sharded filter in ONE process on ONE device, all on one stream. The scalar
+// exchanges become direct reads of the peers' DevScalars (XMODE_LOCAL); the group calls below enqueue every rank's
+// producer kernels before any rank's consumer kernels. Everything else (rank offsets, cross-shard CDF windows,
+// boundary gathers through the "peer" pointers) is the code that runs on R GPUs.
+struct gsmc_group_s {
+  int nranks = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  gsmc_filter* member[GSMC_MAX_RANKS] = {};
+};
+
 struct gsmc_filter {
   gsmc_config cfg;
   int model = 0, D = 0;
@@ -197,7 +208,7 @@ struct gsmc_filter {
   const uint32_t* peer_anc[GSMC_MAX_RANKS] = {};
   const uint64_t* peer_cdf[GSMC_MAX_RANKS] = {};
   DevScalars* peer_ds[GSMC_MAX_RANKS] = {};
-  uint32_t xchg_seq = 0;        // sequence number of the fused peer exchanges (same on every rank)
+  gsmc_group_s* group = nullptr;  // shard emulation (all ranks on this device and stream)
   uint32_t host_token = 0;      // token of the last decision published to the pinned host mirror
   bool fuse_next_decide = false;  // gsmc_run_steps: the propagate being launched also decides for the next step
   double fuse_thr = -1.0;
@@ -226,6 +237,16 @@ struct gsmc_filter {
 };
 
 static size_t real_size(const gsmc_filter* f) { return f->f32 ? 4 : 8; }
+static int xmode(const gsmc_filter* f) {
+  if (f->nranks <= 1) return XMODE_NONE;
+  if (f->group) return XMODE_LOCAL;
+  return f->use_nccl_scalars ? XMODE_NONE : XMODE_LL;
+}
+static PeerScalars peer_scalars(const gsmc_filter* f) {
+  PeerScalars peers;
+  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
+  return peers;
+}
 static char* state_col(const gsmc_filter* f, const void* slab, int64_t step) {
   return (char*)slab + (size_t)((step - 1) % f->cap) * f->D * f->n_pad * real_size(f);
 }
@@ -419,7 +440,8 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   g.resampled_flag = f->resampled + (new_step % f->flag_mod);
   g.partials = f->partials;
   g.ds = f->ds; g.nranks = f->nranks;
-  g.fuse_decide = (f->fuse_next_decide && f->nranks == 1) ? 1 : 0;
+  g.fuse_decide = (f->fuse_next_decide && (f->nranks == 1 || xmode(f) == XMODE_LL)) ? 1 : 0;
+  g.peers = peer_scalars(f);
   g.fuse_threshold = f->fuse_thr; g.n_global = (double)f->N;
   g.next_flag = f->resampled + ((new_step + 1) % f->flag_mod);
   g.n = f->n; g.stride = f->n_pad; g.first_global = (uint64_t)f->first; g.seed = f->cfg.seed; g.keys = make_philox_keys(f->cfg.seed);
@@ -512,20 +534,18 @@ static int launch_propagate(gsmc_filter* f, bool init, const double* obs, size_t
 // finalize (+ decision when ess_threshold >= 0); leaves the statistics in f->ds
 static int launch_finalize(gsmc_filter* f, double ess_threshold, bool to_host = false) {
   int* flag = ess_threshold >= 0.0 ? f->resampled + ((f->T + 1) % f->flag_mod) : nullptr;
-  PeerScalars peers;
-  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
-  const int fused = (f->nranks > 1 && !f->use_nccl_scalars) ? 1 : 0;
-  if (fused) f->xchg_seq += 1;
+  const int xm = xmode(f);
+  const bool nccl = f->nranks > 1 && xm == XMODE_NONE;
   // to_host: the deciding thread also writes the decision into the pinned host mirror, tagged with a fresh token
   DevScalars* host = to_host ? f->h_ds : nullptr;
   if (to_host) { f->host_token += 1; if (f->host_token == 0) f->host_token = 1; }
   {
     ProfScope ps(f, KC_FINALIZE);
-    CK(launch_pdl<PDL_FINALIZE>(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, (int64_t)(f->T + 1), peers, f->xchg_seq, fused,
-                  (f->nranks > 1 && !fused) ? (DevScalars*)nullptr : host, f->host_token));
+    CK(launch_pdl<PDL_FINALIZE>(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, (int64_t)(f->T + 1),
+                                peer_scalars(f), xm, nccl ? (DevScalars*)nullptr : host, f->host_token));
   }
   CK(cudaGetLastError());
-  if (f->nranks > 1 && !fused) {
+  if (nccl) {
     NK(g_nccl.AllGather((const char*)f->ds->triples + f->rank * sizeof(LseTriple), f->ds->triples, sizeof(LseTriple), NCCL_UINT8, f->comm, f->stream));
     ProfScope ps(f, KC_FINALIZE);
     decide_kernel<<<1, 32, 0, f->stream>>>(f->ds, f->nranks, ess_threshold, (double)f->N, flag, (int64_t)(f->T + 1), host, f->host_token);
@@ -552,10 +572,8 @@ static int wait_decision(gsmc_filter* f) {
 // All ranks have finished every kernel that reads this rank's slabs (needed before they are reused or freed).
 static int peer_barrier(gsmc_filter* f) {
   if (f->nranks <= 1 || !f->ds || !f->peer_ds[(f->rank + 1) % f->nranks]) return GSMC_OK;
-  PeerScalars peers;
-  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
-  f->xchg_seq += 1;
-  { ProfScope ps(f, KC_OTHER); peer_barrier_kernel<<<1, 32, 0, f->stream>>>(peers, f->ds, f->rank, f->nranks, f->xchg_seq); }
+  if (f->group) return GSMC_OK;                     // one stream: stream order is the barrier
+  { ProfScope ps(f, KC_OTHER); peer_barrier_kernel<<<1, 32, 0, f->stream>>>(peer_scalars(f), f->ds, f->rank, f->nranks); }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(f->stream));
   return GSMC_OK;
@@ -595,20 +613,28 @@ static double weight_scale(const gsmc_filter* f) {
   return gm_pow2(k > 52 ? 52 : k);
 }
 // One-block scan of the raw segment totals in0/in1 into the prefix arrays out0/out1 + exchange of this rank's
-// totals + the event's totals (see kernels.cuh).
-static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint64_t* in1, uint64_t* out0, uint64_t* out1, int what, int conditional) {
-  PeerScalars peers;
-  for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
+// totals + the event's totals (see kernels.cuh). phases: bit 0 = the scan (fused exchange included), bit 1 = what
+// follows it when the exchange is not fused (ncclAllGather, or the direct peer reads of the shard emulation).
+enum { PH_LOCAL = 1, PH_GLOBAL = 2, PH_ALL = 3 };
+static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint64_t* in1, uint64_t* out0, uint64_t* out1, int what, int conditional,
+                       int phases = PH_ALL) {
   const bool multi = f->nranks > 1;
-  const bool fused = multi && !f->use_nccl_scalars;
-  if (fused) f->xchg_seq += 1;
-  { ProfScope ps(f, cls);
+  const int xm = xmode(f);
+  const bool fused = multi && xm == XMODE_LL;
+  if (phases & PH_LOCAL) {
+    ProfScope ps(f, cls);
     CK(launch_pdl(scan_segments_kernel, 1, 1024, 0, f->stream, in0, in1, out0, out1, f->n_segs, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
-                  peers, f->rank, f->nranks, f->xchg_seq, fused ? 1 : 0)); }
-  CK(cudaGetLastError());
-  if (multi && !fused) {
-    if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
-    if (what & SCAN_E) NK(g_nccl.AllGather((const char*)(f->ds->gap_rank_total + f->rank), f->ds->gap_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+                  peer_scalars(f), f->rank, f->nranks, fused ? 1 : 0));
+    CK(cudaGetLastError());
+  }
+  if ((phases & PH_GLOBAL) && multi && !fused) {
+    if (xm == XMODE_LOCAL) {
+      ProfScope ps(f, KC_OTHER);
+      peer_copy_kernel<<<1, 32, 0, f->stream>>>(peer_scalars(f), f->ds, f->rank, f->nranks, ((what & SCAN_Q) ? PEER_COPY_CDF : 0) | ((what & SCAN_E) ? PEER_COPY_GAP : 0), conditional);
+    } else {
+      if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+      if (what & SCAN_E) NK(g_nccl.AllGather((const char*)(f->ds->gap_rank_total + f->rank), f->ds->gap_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+    }
     ProfScope ps(f, KC_OTHER);
     totals_kernel<<<1, 1024, 0, f->stream>>>(out0, out1, f->n_segs, f->ds, f->nranks, f->rank, f->cfg.seed, (uint64_t)f->N, what, conditional);
     CK(cudaGetLastError());
@@ -620,8 +646,10 @@ static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint6
 //   multinomial, Philox draws:         weights + group-gaps pass -> partition (scan and the ranks' exchange fused) -> search   (3 launches)
 //   exported uniforms (replay): weights pass -> scan -> iid search
 //   residual: + the copy counts / residual fractions pass and the deterministic copies
+// phases: PH_LOCAL = everything up to (and including) this rank's own totals, PH_GLOBAL = everything that needs the
+// other ranks' totals. A filter on its own runs both in one go; the shard emulation runs PH_LOCAL on every rank first.
 template <typename Real>
-static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
+static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid, int phases) {
   const Real* lw = (const Real*)f->lw;
   const double scale = weight_scale(f);
   const int nt = f->n_tiles, ns = f->n_segs, st = f->seg_tiles;
@@ -631,22 +659,25 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
   const bool fuse_spacings = !residual && !replay_iid;
   // the partition kernel scans the segment totals itself and, on a sharded filter, exchanges the ranks' totals
-  // over the peer mailboxes; with GSMC_NCCL_SCALARS=1 the separate scan + ncclAllGather path is used instead
-  const bool fuse_scan = fuse_spacings && (f->nranks == 1 || !f->use_nccl_scalars);
-  // 1. integer weights -> segment-local CDF + segment totals (and, fused, the group gaps of the N sorted draws)
-  if (fuse_spacings) {
-    ProfScope ps(f, KC_SCAN);
-    CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, true, true>, ns, GSMC_BLOCK, 0, f->stream,
-        lw, f->n, scale, f->ds, f->cdf, f->raw0, f->cfg.seed, k_first, (uint64_t)f->N, f->gap, f->tile_e, f->raw1, nt, st, conditional));
-  } else {
-    ProfScope ps(f, KC_SCAN);
-    CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, true, false>, ns, GSMC_BLOCK, 0, f->stream,
-        lw, f->n, scale, f->ds, f->cdf, f->raw0, (uint64_t)0, (uint64_t)0, (uint64_t)0, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint64_t*)nullptr, nt, st, conditional));
+  // over the peer mailboxes; with GSMC_NCCL_SCALARS=1 (and in the shard emulation) the separate scan + gather path is used
+  const bool fuse_scan = fuse_spacings && (f->nranks == 1 || xmode(f) == XMODE_LL);
+  if (phases & PH_LOCAL) {
+    // 1. integer weights -> segment-local CDF + segment totals (and, fused, the group gaps of the N sorted draws)
+    if (fuse_spacings) {
+      ProfScope ps(f, KC_SCAN);
+      CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, true, true>, ns, GSMC_BLOCK, 0, f->stream,
+          lw, f->n, scale, f->ds, f->cdf, f->raw0, f->cfg.seed, k_first, (uint64_t)f->N, f->gap, f->tile_e, f->raw1, nt, st, conditional));
+    } else {
+      ProfScope ps(f, KC_SCAN);
+      CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, true, false>, ns, GSMC_BLOCK, 0, f->stream,
+          lw, f->n, scale, f->ds, f->cdf, f->raw0, (uint64_t)0, (uint64_t)0, (uint64_t)0, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint64_t*)nullptr, nt, st, conditional));
+    }
+    CK(cudaGetLastError());
   }
-  CK(cudaGetLastError());
   // 2. segment prefixes and the totals of the event
-  if (fuse_spacings) { if (!fuse_scan) CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional)); }
-  else CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional));
+  if (fuse_spacings) { if (!fuse_scan) CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional, phases)); }
+  else CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional, phases));
+  if (!(phases & PH_GLOBAL)) return GSMC_OK;
   if (residual) {
     { ProfScope ps(f, KC_OTHER); CK(launch_pdl(resid_scale_kernel, 1, 32, 0, f->stream, f->ds, (double)f->N)); }
     { ProfScope ps(f, KC_SCAN);
@@ -678,17 +709,15 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
     { ProfScope ps(f, KC_SEARCH);
       const int need = (nt + 1 + 31) / 32;
       const int grid = need < 2 * f->sm_count ? need : 2 * f->sm_count;      // one wave of 1024-thread blocks
-      PeerScalars peers;
-      for (int r = 0; r < GSMC_MAX_RANKS; ++r) peers.ds[r] = f->peer_ds[r];
-      if (fuse_scan && f->nranks > 1) f->xchg_seq += 1;
       if (fuse_scan) CK(launch_pdl<PDL_PARTITION>(partition_kernel<true>, grid, 1024, 0, f->stream, v, k_first, f->rank, f->ds, f->raw0, f->raw1, sp_q, f->seg_e,
-                                   f->tile_e, st, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq));
+                                   f->tile_e, st, nt, f->win, (uint64_t)f->N, conditional, peer_scalars(f)));
       else CK(launch_pdl<PDL_PARTITION>(partition_kernel<false>, grid, 1024, 0, f->stream, v, k_first, f->rank, f->ds, (const uint64_t*)nullptr, (const uint64_t*)nullptr, sp_q, f->seg_e,
-                         f->tile_e, st, nt, f->win, (uint64_t)f->N, conditional, peers, f->xchg_seq)); }
+                         f->tile_e, st, nt, f->win, (uint64_t)f->N, conditional, peer_scalars(f))); }
     { static bool attr_set[64] = {};           // function attributes are per device
       if (!attr_set[f->device & 63]) { CK(cudaFuncSetAttribute((const void*)search_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMC_SEARCH_SMEM)); attr_set[f->device & 63] = true; }
-      int occ = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)search_sorted_kernel, GSMC_BLOCK, GSMC_SEARCH_SMEM) != cudaSuccess || occ < 1) occ = 2;
+      static int occ_dev[64] = {};
+      int& occ = occ_dev[f->device & 63];
+      if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)search_sorted_kernel, GSMC_BLOCK, GSMC_SEARCH_SMEM) != cudaSuccess || occ < 1)) occ = 2;
       const int grid = nt < f->sm_count * occ ? nt : f->sm_count * occ;
       const uint32_t magic = st > 1 ? (uint32_t)(0x100000000ULL / (uint64_t)st) + 1u : 0u;
       ProfScope ps(f, KC_SEARCH);
@@ -698,8 +727,8 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid) {
   CK(cudaGetLastError());
   return GSMC_OK;
 }
-static int launch_resample(gsmc_filter* f, int conditional, bool replay_iid) {
-  return f->f32 ? launch_resample_t<float>(f, conditional, replay_iid) : launch_resample_t<double>(f, conditional, replay_iid);
+static int launch_resample(gsmc_filter* f, int conditional, bool replay_iid, int phases = PH_ALL) {
+  return f->f32 ? launch_resample_t<float>(f, conditional, replay_iid, phases) : launch_resample_t<double>(f, conditional, replay_iid, phases);
 }
 
 template <typename Real>
@@ -779,7 +808,7 @@ GSMC_API int gsmc_reset(gsmc_handle f) {
   f->last_resample_step = 0; f->n_sample_calls = 0; f->zrep_n = 0; f->urep_n = 0;
   CKRC(peer_barrier(f));
   if (f->ds) {
-    CK(cudaMemsetAsync(f->ds, 0, offsetof(DevScalars, mbox), f->stream));   // mailboxes keep their sequence tags
+    CK(cudaMemsetAsync(f->ds, 0, offsetof(DevScalars, xseq), f->stream));   // the exchange sequence number and the mailboxes keep their tags
     CK(cudaMemsetAsync(f->resampled, 0, (size_t)f->flag_mod * sizeof(int), f->stream));
   }
   return GSMC_OK;
@@ -896,6 +925,7 @@ GSMC_API int gsmc_step(gsmc_handle f, const double* obs, size_t n_obs, int prop,
 
 GSMC_API int gsmc_maybe_resample(gsmc_handle f, double ess_threshold, int* did_resample, double* ess_out) {
   if (!f) return fail(GSMC_E_BADARG, "null handle");
+  if (f->group) return fail(GSMC_E_BADARG, "member of an emulated shard group: call gsmc_group_maybe_resample");
   if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
   if (!(ess_threshold >= 0.0)) return fail(GSMC_E_BADARG, "ess_threshold must be >= 0");
   CK(cudaSetDevice(f->device));
@@ -1048,7 +1078,7 @@ GSMC_API int gsmc_get_ancestors(gsmc_handle f, int64_t* host_dst, size_t n) {
   return GSMC_OK;
 }
 
-GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t* idx_out) {
+static int sample_unweighted_impl(gsmc_filter* f, uint64_t num_samples, int64_t* idx_out, int phases) {
   if (!f || (!idx_out && num_samples)) return fail(GSMC_E_BADARG, "null argument");
   if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
   if (num_samples == 0 && f->nranks == 1) return GSMC_OK;
@@ -1056,27 +1086,25 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
   // sampling indexes the CURRENT particle order; with a pending resample that order only exists once the next step
   // has applied the ancestor column. Nothing is touched before this check.
   if (f->pending) return fail(GSMC_E_UNSUPPORTED, "sample_unweighted between maybe_resample and the next step");
+  if (f->urep_n && f->urep_n != num_samples) return fail(GSMC_E_BADARG, "replay uniforms for sample_unweighted: expected %llu values", (unsigned long long)num_samples);
   CK(cudaSetDevice(f->device));
   CKRC(ensure_f64(f, num_samples));
   int64_t* d_idx = (int64_t*)f->d_f64;
   const int grid = (int)((num_samples + GSMC_BLOCK - 1) / GSMC_BLOCK);
-  // statistics (max) of the current weights, then the integer CDF, unconditionally
-  CKRC(launch_finalize(f, -1.0));
-  {
+  if (phases & PH_LOCAL) {
+    // statistics (max) of the current weights, then the integer CDF, unconditionally
+    CKRC(launch_finalize(f, -1.0));
     const double scale = weight_scale(f);
     { ProfScope ps(f, KC_SCAN);
       if (f->f32) weights_kernel<float, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
           (const float*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0);
       else weights_kernel<double, true, false><<<f->n_segs, GSMC_BLOCK, 0, f->stream>>>(
           (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
-    CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q, 0));
+    CK(cudaGetLastError());
   }
-  CK(cudaGetLastError());
-  const double* urep = nullptr;
-  if (f->urep_n) {
-    if (f->urep_n != num_samples) return fail(GSMC_E_BADARG, "replay uniforms for sample_unweighted: expected %llu values", (unsigned long long)num_samples);
-    urep = f->d_urep;
-  }
+  CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q, 0, phases));
+  if (!(phases & PH_GLOBAL)) return GSMC_OK;
+  const double* urep = f->urep_n ? f->d_urep : nullptr;
   { ProfScope ps(f, KC_SEARCH);
     search_iid_kernel<<<grid, GSMC_BLOCK, 0, f->stream>>>(make_cdf_view(f, false), f->ds, urep, f->cfg.seed, f->n_sample_calls, GSMC_STREAM_SAMPLE,
                                                          (int64_t)num_samples, 0, nullptr, d_idx, 0); }
@@ -1087,6 +1115,10 @@ GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t
   CKRC(fetch_scalars(f));
   if (!(f->h_ds->cdf_total > 0)) return fail(GSMC_E_DEGENERATE, "total weight is zero or not finite");
   return GSMC_OK;
+}
+GSMC_API int gsmc_sample_unweighted(gsmc_handle f, uint64_t num_samples, int64_t* idx_out) {
+  if (f && f->group) return fail(GSMC_E_BADARG, "member of an emulated shard group: call gsmc_group_sample_unweighted");
+  return sample_unweighted_impl(f, num_samples, idx_out, PH_ALL);
 }
 
 GSMC_API int gsmc_importance_sampling(const gsmc_config* cfg, const double* params, size_t n_params, const double* obs, size_t n_obs,
@@ -1124,13 +1156,15 @@ GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, si
     return fail(GSMC_E_BADARG, "history_capacity (%lld steps) would be exceeded by %zu more steps after step %lld", (long long)f->cap, n_steps, (long long)f->T);
   if (n_obs != (size_t)expected_obs(f)) return fail(GSMC_E_BADARG, "model %d needs %d observation value(s) per step, got %zu", f->model, expected_obs(f), n_obs);
   CK(cudaSetDevice(f->device));
-  // On one GPU the threshold of every decision is known here, so the last block of each propagate also takes the
-  // decision of the next step: only the first step of the call needs a finalize launch.
+  // The threshold of every decision is known here, so the last block of each propagate also takes the decision of the
+  // next step (on a sharded filter after exchanging the ranks' triples over the LL mailboxes): only the first step of
+  // the call needs a finalize launch.
+  if (f->group) return fail(GSMC_E_UNSUPPORTED, "gsmc_run_steps is not available on an emulated shard group");
   bool decided = false;
   for (size_t s = 0; s < n_steps; ++s) {
     if (!decided) CKRC(launch_finalize(f, ess_threshold));
     CKRC(launch_resample(f, 1, false));
-    f->fuse_next_decide = f->nranks == 1 && !f->profiling && s + 1 < n_steps;
+    f->fuse_next_decide = (f->nranks == 1 || xmode(f) == XMODE_LL) && !f->profiling && s + 1 < n_steps;
     f->fuse_thr = ess_threshold;
     const int rc = launch_propagate(f, false, obs + s * n_obs, n_obs, prop, pp, npp, true);
     decided = f->fuse_next_decide;
@@ -1143,6 +1177,112 @@ GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, si
   CKRC(fetch_scalars(f));
   f->last_resample_step = f->h_ds->last_resample_step;          // tracked on the device while the host was not looking
   if (f->h_ds->error) return device_error(f, "during gsmc_run_steps");
+  return GSMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shard emulation: R ranks of one sharded filter on one device (see gsmc_group_s)
+// ------------------------------------------------------------------------------------------------
+GSMC_API int gsmc_group_create(int nranks, int device, gsmc_group* out) {
+  if (!out) return fail(GSMC_E_BADARG, "null argument");
+  if (nranks < 2 || nranks > GSMC_MAX_RANKS) return fail(GSMC_E_BADARG, "2 <= nranks <= %d", GSMC_MAX_RANKS);
+  if (device < 0) CK(cudaGetDevice(&device));
+  CK(cudaSetDevice(device));
+  gsmc_group_s* g = new gsmc_group_s();
+  g->nranks = nranks; g->device = device;
+  if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) { delete g; return fail(GSMC_E_CUDA, "stream creation failed"); }
+  *out = g;
+  return GSMC_OK;
+}
+GSMC_API void gsmc_group_destroy(gsmc_group g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  for (int r = 0; r < g->nranks; ++r) if (g->member[r]) { g->member[r]->group = nullptr; gsmc_destroy(g->member[r]); }
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+GSMC_API int gsmc_group_attach(gsmc_group g, int rank, gsmc_handle f) {
+  if (!g || !f) return fail(GSMC_E_BADARG, "null argument");
+  if (rank < 0 || rank >= g->nranks || g->member[rank]) return fail(GSMC_E_BADARG, "rank %d out of range or already attached", rank);
+  if (f->T != 0 || f->state_slab) return fail(GSMC_E_BADARG, "attach must precede gsmc_init");
+  if (f->device != g->device) return fail(GSMC_E_BADARG, "group lives on device %d, filter on device %d", g->device, f->device);
+  if (f->N % ((int64_t)g->nranks * GSMC_PAD) != 0) return fail(GSMC_E_BADARG, "num_particles must be a multiple of %d * nranks", GSMC_PAD);
+  CK(cudaSetDevice(f->device));
+  if (f->own_stream && f->stream) { cudaStreamSynchronize(f->stream); cudaStreamDestroy(f->stream); }
+  f->stream = g->stream; f->own_stream = false;
+  f->rank = rank; f->nranks = g->nranks; f->group = g;
+  f->n = f->N / g->nranks; f->first = f->n * rank;
+  CKRC(alloc_buffers(f));
+  g->member[rank] = f;
+  for (int a = 0; a < g->nranks; ++a) for (int b = 0; b < g->nranks; ++b) {
+    gsmc_filter *x = g->member[a], *y = g->member[b];
+    if (!x || !y) continue;
+    x->peer_slab[b] = y->state_slab; x->peer_anc[b] = y->anc_slab; x->peer_cdf[b] = y->cdf; x->peer_ds[b] = y->ds;
+  }
+  return GSMC_OK;
+}
+static int group_ready(gsmc_group g) {
+  if (!g) return fail(GSMC_E_BADARG, "null group");
+  for (int r = 0; r < g->nranks; ++r) if (!g->member[r]) return fail(GSMC_E_BADARG, "rank %d of the group has no filter attached", r);
+  for (int r = 1; r < g->nranks; ++r)
+    if (g->member[r]->T != g->member[0]->T || g->member[r]->pending != g->member[0]->pending) return fail(GSMC_E_BADARG, "the ranks of the group are out of step");
+  return GSMC_OK;
+}
+GSMC_API int gsmc_group_init(gsmc_group g, const double* obs, size_t n_obs, int prop, const double* pp, size_t npp) {
+  CKRC(group_ready(g));
+  for (int r = 0; r < g->nranks; ++r) CKRC(gsmc_init(g->member[r], obs, n_obs, prop, pp, npp));
+  return GSMC_OK;
+}
+GSMC_API int gsmc_group_step(gsmc_group g, const double* obs, size_t n_obs, int prop, const double* pp, size_t npp) {
+  CKRC(group_ready(g));
+  for (int r = 0; r < g->nranks; ++r) CKRC(gsmc_step(g->member[r], obs, n_obs, prop, pp, npp));
+  return GSMC_OK;
+}
+GSMC_API int gsmc_group_maybe_resample(gsmc_group g, double ess_threshold, int* did_resample, double* ess_out) {
+  CKRC(group_ready(g));
+  gsmc_filter* f0 = g->member[0];
+  if (f0->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (!(ess_threshold >= 0.0)) return fail(GSMC_E_BADARG, "ess_threshold must be >= 0");
+  CK(cudaSetDevice(g->device));
+  if (f0->pending) {
+    if ((double)f0->N < ess_threshold) return fail(GSMC_E_UNSUPPORTED, "two resampling events without a step in between");
+    if (did_resample) *did_resample = 0;
+    if (ess_out) *ess_out = (double)f0->N;
+    return GSMC_OK;
+  }
+  const bool replay = f0->urep_n > 0;
+  const int R = g->nranks;
+  for (int r = 0; r < R; ++r) CKRC(launch_finalize(g->member[r], ess_threshold, true));
+  if (!replay) {
+    for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 1, false, PH_LOCAL));
+    for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 1, false, PH_GLOBAL));
+  }
+  int did = 0;
+  for (int r = 0; r < R; ++r) {
+    gsmc_filter* f = g->member[r];
+    CKRC(wait_decision(f));
+    f->stats_fresh = true; f->decided_since_step = true;
+    if (f->h_ds->error) { f->decided_since_step = false; return device_error(f, "in maybe_resample"); }
+    if (r == 0) did = f->h_ds->do_resample;
+    else if (f->h_ds->do_resample != did) return fail(GSMC_E_PEER, "the ranks of the group took different decisions");
+  }
+  if (did) {
+    if (replay) {
+      for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 0, true, PH_LOCAL));
+      for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 0, true, PH_GLOBAL));
+    }
+    for (int r = 0; r < R; ++r) { g->member[r]->pending = true; g->member[r]->last_resample_step = g->member[r]->T + 1; }
+  }
+  for (int r = 0; r < R; ++r) g->member[r]->urep_n = 0;
+  if (did_resample) *did_resample = did;
+  if (ess_out) *ess_out = f0->h_ds->ess;
+  return GSMC_OK;
+}
+GSMC_API int gsmc_group_sample_unweighted(gsmc_group g, uint64_t num_samples, int64_t* idx_out) {
+  CKRC(group_ready(g));
+  std::vector<int64_t> scratch(num_samples);
+  for (int r = 0; r < g->nranks; ++r) CKRC(sample_unweighted_impl(g->member[r], num_samples, scratch.data(), PH_LOCAL));
+  for (int r = 0; r < g->nranks; ++r) CKRC(sample_unweighted_impl(g->member[r], num_samples, r == 0 ? idx_out : scratch.data(), PH_GLOBAL));
   return GSMC_OK;
 }
 

@@ -74,6 +74,12 @@ struct DevScalars {
   LseTriple triples[GSMC_MAX_RANKS];
   uint64_t cdf_rank_total[GSMC_MAX_RANKS];      // per-rank integer weight totals (allgathered)
   uint64_t gap_rank_total[GSMC_MAX_RANKS];      // per-rank totals of the group gaps (allgathered)
+  // Sequence number of the peer exchanges, kept ON THE DEVICE (identical on every rank: all ranks run the same
+  // exchanges in the same order), so that a captured / replayed launch sequence never reuses a tag. The exchange of the
+  // logsumexp triples (and every other one-block exchange) advances it by 2 and uses the new value; the exchange of the
+  // resampling totals of the same step, read by every block of partition_kernel, uses that value + 1 without
+  // touching it. gsmc_reset leaves it (and the mailboxes) alone.
+  uint32_t xseq, xseq_pad;
   // LL mailboxes for the fused peer-memory exchange: [sequence mod 4][source rank][word]; a word is
   // (payload 32 bit) | (sequence number << 32), written by the source rank with one 8-byte store.
   unsigned long long mbox[4][GSMC_MAX_RANKS][8];
@@ -116,6 +122,12 @@ __device__ __forceinline__ void ll_allgather_u64(const PeerScalars& peers, DevSc
     for (int j = 0; j < n64; ++j) out[r * n64 + j] = (uint64_t)g[2 * j] | ((uint64_t)g[2 * j + 1] << 32);
   }
 }
+// How the ranks of a sharded filter exchange their per-step scalars.
+//   XMODE_NONE   single rank, or the host runs ncclAllGather between the kernels (GSMC_NCCL_SCALARS=1)
+//   XMODE_LL     fused: LL mailboxes in peer memory (the default on NVLink)
+//   XMODE_LOCAL  shard emulation: all ranks live on ONE device and ONE stream (gsmc_group_*); a rank reads its peers'
+//                scalars directly, the host having enqueued every rank's producer before any rank's consumer
+enum { XMODE_NONE = 0, XMODE_LL = 1, XMODE_LOCAL = 2 };
 
 
 template <typename Real> struct Vec2T;
@@ -197,9 +209,10 @@ struct PropArgs {
   DevScalars* ds;                    // the last block to finish leaves this rank's (max, s1, s2) in ds->triples[rank]
   int nranks;
   int n_tiles;                       // tiles of PropTile<Model>::TILE particles (the grid is persistent)
-  int fuse_decide;                   // single rank, threshold known in advance (gsmc_run_steps): the last block also takes
-  double fuse_threshold, n_global;   //   the maybe_resample! decision of the NEXT step (no finalize launch in between)
+  int fuse_decide;                   // threshold known in advance (gsmc_run_steps): the last block also takes the
+  double fuse_threshold, n_global;   //   maybe_resample! decision of the NEXT step (no finalize launch in between);
   int* next_flag;                    //   resampled[] slot of the next step
+  PeerScalars peers;                 //   sharded filter: it first exchanges the ranks' triples over the LL mailboxes
   int64_t n;                         // local particle count
   int64_t stride;                    // column stride (padded n)
   uint64_t first_global;             // global index of local particle 0
@@ -311,6 +324,8 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
   __shared__ double red[96];
   __shared__ SmemTabs tabs;
   __shared__ int s_last;
+  __shared__ uint32_t s_seq;
+  __shared__ uint64_t s_mine[3];
   load_tabs(tabs, NZ > 0);
   if (Model::SMEM_DOUBLES > 0) Model::template prologue<INIT, PROP>(a, dyn_sm);
   __syncthreads();
@@ -496,7 +511,19 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
     const LseTriple tr = reduce_partials(g.partials, (int)gridDim.x, red, tabs.exp2);
     if (threadIdx.x == 0) {
       g.ds->triples[g.rank] = tr; g.ds->blocks_done = 0;
-      if (g.fuse_decide) combine_and_decide(g.ds, 1, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
+      if (g.fuse_decide && g.nranks == 1) combine_and_decide(g.ds, 1, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
+    }
+    if (g.fuse_decide && g.nranks > 1) {
+      // Sharded filter: this block sends the rank's triple to every peer as soon as it is known and merges all of them
+      // in rank order (the logsumexp "allreduce"), so every rank takes the same decision without a finalize launch.
+      if (threadIdx.x == 0) {
+        s_mine[0] = gm_to_bits(tr.m); s_mine[1] = gm_to_bits(tr.s1); s_mine[2] = gm_to_bits(tr.s2);
+        s_seq = (g.ds->xseq += 2);
+      }
+      __syncthreads();
+      ll_allgather_u64(g.peers, g.ds, g.rank, g.nranks, s_seq, s_mine, 3, reinterpret_cast<uint64_t*>(g.ds->triples));
+      __syncthreads();
+      if (threadIdx.x == 0) combine_and_decide(g.ds, g.nranks, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
     }
   }
 }
@@ -521,18 +548,24 @@ __device__ __forceinline__ void publish_decision(const DevScalars* ds, DevScalar
 // without a separate collective.
 __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, int nranks, double ess_threshold,
                                                       double n_global, int* resampled_flag_out, int64_t next_step,
-                                                      PeerScalars peers, uint32_t seq, int fused_exchange,
-                                                      DevScalars* host, uint32_t token) {
+                                                      PeerScalars peers, int xmode, DevScalars* host, uint32_t token) {
   __shared__ uint64_t mine[3];
   pdl_wait();
   pdl_trigger();
-  if (nranks > 1 && fused_exchange) {
+  if (nranks > 1 && xmode == XMODE_LL) {
+    uint32_t seq = 0;
     if (threadIdx.x == 0) {
       const LseTriple tr = ds->triples[rank];
       mine[0] = gm_to_bits(tr.m); mine[1] = gm_to_bits(tr.s1); mine[2] = gm_to_bits(tr.s2);
+      seq = (ds->xseq += 2);
     }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
     __syncwarp();
     ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 3, reinterpret_cast<uint64_t*>(ds->triples));
+    __syncwarp();
+    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
+  } else if (nranks > 1 && xmode == XMODE_LOCAL) {
+    if ((int)threadIdx.x < nranks && (int)threadIdx.x != rank) ds->triples[threadIdx.x] = peers.ds[threadIdx.x]->triples[threadIdx.x];
     __syncwarp();
     if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
   } else if (nranks == 1) {
@@ -540,11 +573,23 @@ __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, 
   }
 }
 // cross-GPU barrier (peer-memory exchange of one word): nobody passes until every rank has arrived
-__global__ void peer_barrier_kernel(PeerScalars peers, DevScalars* ds, int rank, int nranks, uint32_t seq) {
+__global__ void peer_barrier_kernel(PeerScalars peers, DevScalars* ds, int rank, int nranks) {
   __shared__ uint64_t mine[1];
   __shared__ uint64_t got[GSMC_MAX_RANKS];
-  mine[0] = seq;
-  ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 1, got);
+  __shared__ uint32_t s_seq;
+  if (threadIdx.x == 0) { s_seq = (ds->xseq += 2); mine[0] = s_seq; }
+  __syncthreads();
+  ll_allgather_u64(peers, ds, rank, nranks, s_seq, mine, 1, got);
+}
+// shard emulation (XMODE_LOCAL): copy the peers' own entries of the per-rank scalars into this rank's arrays
+enum { PEER_COPY_TRIPLES = 1, PEER_COPY_CDF = 2, PEER_COPY_GAP = 4 };
+__global__ void peer_copy_kernel(PeerScalars peers, DevScalars* ds, int rank, int nranks, int what, int conditional) {
+  if (conditional && !ds->do_resample) return;
+  const int r = threadIdx.x;
+  if (r >= nranks || r == rank) return;
+  if (what & PEER_COPY_TRIPLES) ds->triples[r] = peers.ds[r]->triples[r];
+  if (what & PEER_COPY_CDF) ds->cdf_rank_total[r] = peers.ds[r]->cdf_rank_total[r];
+  if (what & PEER_COPY_GAP) ds->gap_rank_total[r] = peers.ds[r]->gap_rank_total[r];
 }
 
 // multi-rank: runs after the allgather of ds->triples
@@ -779,10 +824,11 @@ __device__ __forceinline__ void scan_segments_block(const uint64_t* in0, const u
 __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0, const uint64_t* in1, uint64_t* out0, uint64_t* out1,
                                                              int n_segs, DevScalars* ds, int what,
                                                              uint64_t seed, uint64_t n_global, int conditional,
-                                                             PeerScalars peers, int rank, int nranks, uint32_t seq, int exchange) {
+                                                             PeerScalars peers, int rank, int nranks, int exchange) {
   __shared__ uint64_t sm[2][33];
   __shared__ uint64_t mine[2];
   __shared__ uint64_t got[2 * GSMC_MAX_RANKS];
+  __shared__ uint32_t s_seq;
   pdl_wait();
   pdl_trigger();
   const bool skip = conditional && !ds->do_resample;
@@ -795,13 +841,13 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
     int k = 0;
     if (what & SCAN_Q) { ds->cdf_rank_total[rank] = totals[0]; mine[k++] = totals[0]; }
     if (what & SCAN_E) { const uint64_t t = (what & SCAN_Q) ? totals[1] : totals[0]; ds->gap_rank_total[rank] = t; mine[k++] = t; }
+    if (nranks > 1 && exchange && n64) s_seq = (ds->xseq += 2);
   }
   __syncthreads();
   if (nranks > 1) {
     if (!exchange || n64 == 0) return;
-    // the exchange runs on every rank even when no resample was decided: the mailbox parity scheme
-    // needs every sequence number to be used by everybody
-    ll_allgather_u64(peers, ds, rank, nranks, seq, mine, n64, got);
+    // the exchange runs on every rank even when no resample was decided (all ranks advance the sequence number alike)
+    ll_allgather_u64(peers, ds, rank, nranks, s_seq, mine, n64, got);
     __syncthreads();
     if (threadIdx.x == 0 && !skip) {
       for (int r = 0; r < nranks; ++r) {
@@ -951,7 +997,7 @@ template <bool FUSED_SCAN>
 __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t k_first, int rank, DevScalars* ds,
                                                          const uint64_t* raw_q, const uint64_t* raw_e, uint64_t* sp_q, uint64_t* sp_e,
                                                          uint64_t* tile_e, int seg_tiles, int nt, uint32_t* win,
-                                                         uint64_t n_global, int conditional, PeerScalars peers, uint32_t seq) {
+                                                         uint64_t n_global, int conditional, PeerScalars peers) {
   __shared__ uint64_t spq[GSMC_MAX_SEGS + 1];
   __shared__ uint64_t spe[GSMC_MAX_SEGS + 1];
   __shared__ uint64_t sm[2][33];
@@ -964,6 +1010,7 @@ __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t k_f
   if (conditional && !ds->do_resample) return;          // every rank takes the same decision: nobody sends, nobody waits
   const int n_segs = v.n_segs, R = v.nranks;
   if (FUSED_SCAN) {
+    const uint32_t seq = ds->xseq + 1;                    // the totals exchange of this step (see DevScalars::xseq)
     uint64_t totals[2];
     scan_segments_block(raw_q, raw_e, n_segs, spq, spe, sm, totals);
     if (R > 1) {

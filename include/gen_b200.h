@@ -111,6 +111,24 @@ GSMC_API int gsmc_comm_create(const void* unique_id, size_t nbytes, int rank, in
 GSMC_API void gsmc_comm_destroy(gsmc_comm c);
 GSMC_API int gsmc_comm_attach(gsmc_handle h, gsmc_comm c);
 
+/* Shard emulation: the R ranks of ONE sharded filter as R handles in one process on one device, sharing one stream.
+ * The data path is the multi-GPU code (rank offsets of the integer CDF and of the group gaps, CDF windows and ancestor
+ * gathers that cross shard boundaries, "peer" pointers); only the scalar exchanges differ: a rank reads its peers'
+ * scalars directly, and the gsmc_group_* calls enqueue every rank's producer kernels before any rank's consumers.
+ * Used by the 1-GPU parity tests of the sharded path; no reference equivalent.
+ * Attach every rank before gsmc_group_init; per-handle getters (log weights, state, ancestors, log-ML estimate,
+ * trajectories) work on the members as on any sharded handle. gsmc_group_destroy destroys the members too. */
+typedef struct gsmc_group_s* gsmc_group;
+GSMC_API int gsmc_group_create(int nranks, int device, gsmc_group* out);
+GSMC_API void gsmc_group_destroy(gsmc_group g);
+GSMC_API int gsmc_group_attach(gsmc_group g, int rank, gsmc_handle h);
+GSMC_API int gsmc_group_init(gsmc_group g, const double* obs, size_t n_obs,
+                             int proposal_id, const double* proposal_params, size_t n_proposal_params);
+GSMC_API int gsmc_group_step(gsmc_group g, const double* obs, size_t n_obs,
+                             int proposal_id, const double* proposal_params, size_t n_proposal_params);
+GSMC_API int gsmc_group_maybe_resample(gsmc_group g, double ess_threshold, int* did_resample, double* ess_out);
+GSMC_API int gsmc_group_sample_unweighted(gsmc_group g, uint64_t num_samples, int64_t* idx_out);
+
 /* Replay mode: the draws the next init/step/maybe_resample/sample_unweighted call consumes,
  * instead of Philox (this rank's slice). normals: n_local*n_norm values ordered
  * [particle][draw]; uniforms: n_local*n_unif for init/step, one per output slot for
