@@ -49,6 +49,35 @@ def make_observations(T):
     return np.array(ys)
 
 
+def make_bearings_observations(T, sw=0.001, st=0.005, truth=(-0.05, 0.001, 12.0, -0.055)):
+    """cfg 5: bearings of a constant-velocity target seen from the origin, simulated with numpy seed 0."""
+    rng = np.random.default_rng(0)
+    x, vx, y, vy = truth
+    obs = []
+    for t in range(T):
+        if t > 0:
+            wx, wy = sw * rng.standard_normal(2)
+            x, vx, y, vy = x + vx + 0.5 * wx, vx + wx, y + vy + 0.5 * wy, vy + wy
+        obs.append(math.atan2(y, x) + st * rng.standard_normal())
+    return np.array(obs)
+
+
+def workload(args):
+    """The configuration being timed. cfg3 (default) is the one BASELINE.json's metric is quoted on; cfg5 is
+    BASELINE.json configs[4] (bearings-only, custom proposal, T=200, 2^24 particles per GPU = 2^27 on 8 GPUs)."""
+    import gen_b200 as g
+    if args.config == "cfg5":
+        T = args.T or 200
+        model = g.BearingsOnly()
+        return {"name": "2D bearings-only tracking (Unfold), T=%d" % T, "model": model, "ys": make_bearings_observations(T), "T": T,
+                "proposal": model.custom_proposal(), "proposal_name": "custom (EKF-style) proposal", "S": 32, "kalman": None,
+                "kernel": "propagate_kernel<BearingsModel, PROP=1>"}
+    T = args.T or 100
+    ys = make_observations(T)
+    return {"name": "1D linear-Gaussian SSM (Unfold), T=%d" % T, "model": g.LinearGaussianSSM(*LG), "ys": ys, "T": T, "proposal": None,
+            "proposal_name": "bootstrap proposal", "S": STATE_BYTES, "kalman": kalman(ys), "kernel": "propagate_kernel<LgssmModel>"}
+
+
 def claim_stdout():
     """The contract is ONE JSON line on stdout: libraries (NCCL banners, torch warnings) write to fd 1
     too, so fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
@@ -134,9 +163,8 @@ def run_ours(args):
     rank, world, local, dist = dist_setup(args.gpus)
     n_per = 1 << args.log2n
     N = n_per * world
-    T = args.T
-    ys = make_observations(T)
-    model = g.LinearGaussianSSM(*LG)
+    wl = workload(args)
+    T, ys, model, proposal = wl["T"], wl["ys"], wl["model"], wl["proposal"]
     comm = Communicator(dist, rank, world, device=local) if world > 1 else None
 
     def barrier():
@@ -154,8 +182,8 @@ def run_ours(args):
 
     def one_run(s):
         s.reset()
-        s.init([ys[0]])
-        s.run_steps(ys[1:], N / 2)
+        s.init([ys[0]], proposal)
+        s.run_steps(ys[1:], N / 2, proposal)
         return s.log_ml_estimate()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -186,10 +214,16 @@ def run_ours(args):
     # ---- per-kernel CUDA-event times (profiling pass through the per-call API, same workload) ----
     st.set_profiling(True)
     st.reset()
-    st.init([ys[0]])
+    st.init([ys[0]], proposal)
+    remote_rows = None
     for t in range(1, T):
-        st.maybe_resample(N / 2)
-        st.step([ys[t]])
+        did = st.maybe_resample(N / 2)
+        if did and world > 1 and remote_rows is None and t > T // 2:
+            # rows this rank's gather reads over NVLink at one (late) resampling event: ancestors owned by another rank
+            anc = st.ancestors()
+            remote_rows = int(np.sum((anc < st.first_global) | (anc >= st.first_global + st.num_local)))
+            del anc
+        st.step([ys[t]], proposal)
     st.log_ml_estimate()
     prof = st.stats()
     st.set_profiling(False)
@@ -197,11 +231,14 @@ def run_ours(args):
 
     # ---- e2e through the Gen-API mirror, host buffers, allocation included --------------------------
     def e2e_run():
-        state = g.initialize_particle_filter(model, (1,), g.choicemap(("y_init", float(ys[0]))), N, seed=0, dtype=args.dtype,
-                                             keep_history=not args.no_history, history_capacity=T, device=local, comm=comm)
+        opts = dict(seed=0, dtype=args.dtype, keep_history=not args.no_history, history_capacity=T, device=local, comm=comm)
+        if proposal is None:
+            state = g.initialize_particle_filter(model, (1,), g.choicemap((model.obs_address(1), float(ys[0]))), N, **opts)
+        else:
+            state = g.initialize_particle_filter(model, (1,), g.choicemap((model.obs_address(1), float(ys[0]))), proposal, (), N, **opts)
         for Tn in range(2, T + 1):
             g.maybe_resample_b(state)
-            g.particle_filter_step_b(state, (Tn,), (g.UnknownChange(),), g.choicemap((("chain", Tn - 1, "y"), float(ys[Tn - 1]))))
+            g.particle_filter_step_b(state, (Tn,), (g.UnknownChange(),), g.choicemap((model.obs_address(Tn), float(ys[Tn - 1]))), proposal)
         out = g.log_ml_estimate(state)
         state.close()
         return out
@@ -221,12 +258,17 @@ def run_ours(args):
         e_ms = float(tmax.item())
     e2e_value = N * T * reps / (e_ms * 1e-3)
 
+    if dist is not None:
+        import torch
+        rr = torch.tensor([float(remote_rows or 0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(rr, op=dist.ReduceOp.MAX)
+        remote_rows = int(rr.item())
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     peak, peak_kind = measured_peak()
-    S = STATE_BYTES if args.dtype == "f64" else 4
+    S = wl["S"] if args.dtype == "f64" else wl["S"] // 2
     LW = 8 if args.dtype == "f64" else 4
     n_plain, n_gather = prof["n_propagate"], prof["n_propagate_gather"]
     bytes_plain = n_per * (2 * S + 2 * LW)              # read x, lw; write x', lw'   (2S+16)
@@ -242,12 +284,12 @@ def run_ours(args):
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "1D linear-Gaussian SSM (Unfold), T=%d, N=2^%d particles per GPU, bootstrap proposal, "
-                               "multinomial resampling at ESS<N/2, trace history %s" % (T, args.log2n, "dropped" if args.no_history else "kept"),
+        "config": {"workload": "%s, N=2^%d particles per GPU, %s, "
+                               "multinomial resampling at ESS<N/2, trace history %s" % (wl["name"], args.log2n, wl["proposal_name"], "dropped" if args.no_history else "kept"),
                    "particles_total": N, "time_steps": T, "resamples_per_run": n_resamples,
                    "parallelism": "particles sharded over %d GPU(s)" % world,
                    "l2": "inputs larger than L2: each step streams >=3 columns of %d MiB (126 MB L2), history columns are never re-read" % (n_per * S >> 20)},
-        "log_ml": lml, "log_ml_kalman": kalman(ys), "log_ml_e2e": lml_e2e,
+        "log_ml": lml, "log_ml_kalman": wl["kalman"], "log_ml_e2e": lml_e2e,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 8 * T,
                 # per maybe_resample!: 52 B (decision, ESS, log-ML terms + token) stored by the deciding thread into the pinned
@@ -257,7 +299,7 @@ def run_ours(args):
                 "note": "Gen-API mirror; includes allocation of the trace slabs (pooled after the first run); the Bool of every "
                         "maybe_resample! reaches the host through the pinned mirror (device store + token), observations travel as kernel arguments"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "propagate_kernel<LgssmModel>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": wl["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
                      "algorithmic_bytes_per_launch": {"plain": bytes_plain, "gather": bytes_gather},
                      "launches": {"plain": n_plain, "gather": n_gather}, "avg_launch_ms": ms_prop / max(1, n_plain + n_gather)},
@@ -265,13 +307,18 @@ def run_ours(args):
                                "accounting": "SURVEY 8(d): (2S+16) B per particle-step + (2S+36) B per particle per resample"},
         "kernel_ms_profile_pass": kernel_ms, "kernel_share_propagate": ms_prop / total_kernel_ms if total_kernel_ms else None,
     }
+    if world > 1:
+        line["nvlink"] = {"remote_rows_per_resample_max_rank": remote_rows, "rows_per_rank": n_per,
+                          "bytes_per_resample_est": (remote_rows or 0) * (S + 8),
+                          "note": "rows of the ancestor gather owned by another rank at one late resampling event (max over ranks); each costs S bytes of "
+                                  "state plus the CDF entries of boundary windows over NVLink. Outputs are in ancestor order, so only shard-boundary rows are remote"}
     tr = ncu_traffic()
-    if tr and args.dtype == "f64" and args.log2n == 24:
+    if tr and args.dtype == "f64" and args.log2n == 24 and args.config == "cfg3":
         n_l = max(1, n_plain + n_gather)
         line["roofline"]["traffic"] = (n_plain * tr["propagate_plain_bytes"] + n_gather * tr["propagate_gather_bytes"]) / n_l
         line["roofline"]["traffic_source"] = tr.get("source")
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(1, args.cpu_log2n, T, ys)
+        line["cpu_baseline"] = cpu_baseline(1, args.cpu_log2n, T, ys, args.config)
     emit(args.out_fd, line)
     if dist is not None:
         dist.destroy_process_group()
@@ -291,23 +338,25 @@ def kalman(ys):
     return ll
 
 
-def oracle_run(orc, N, T, ys, threads):
+def oracle_run(orc, N, T, ys, threads, config="cfg3"):
+    from oracle import closed_forms as cf
     from oracle import oracle as O
-    pf = orc.particle_filter(O.LGSSM, LG, N, seed=0, keep_history=False, num_threads=threads)
-    pf.init([ys[0]])
+    fam, params, prop = (O.BEARINGS, list(cf.BEARINGS_PARAMS), 1) if config == "cfg5" else (O.LGSSM, LG, 0)
+    pf = orc.particle_filter(fam, params, N, seed=0, keep_history=False, num_threads=threads)
+    pf.init([ys[0]], proposal=prop)
     for t in range(1, T):
         pf.maybe_resample()
-        pf.step([ys[t]])
+        pf.step([ys[t]], proposal=prop)
     return pf.log_ml_estimate()
 
 
-def cpu_baseline(threads, log2n, T, ys):
+def cpu_baseline(threads, log2n, T, ys, config="cfg3"):
     """The oracle (C port of the reference algorithm) on the host cores, bounded sample."""
     from oracle import oracle as O
     orc = O.Oracle()
     N = 1 << log2n
     t0 = time.perf_counter()
-    lml = oracle_run(orc, N, T, ys, threads)
+    lml = oracle_run(orc, N, T, ys, threads, config)
     dt = time.perf_counter() - t0
     return {"value": N * T / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
             "sample": "same model and loop, N=2^%d particles x T=%d steps, one run (%.1f s); C restatement of Gen.jl's "
@@ -320,27 +369,28 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
-    T = args.T
-    ys = make_observations(T)
+    T = args.T or (200 if args.config == "cfg5" else 100)
+    ys = make_bearings_observations(T) if args.config == "cfg5" else make_observations(T)
     threads = os.cpu_count() or 1
     orc = O.Oracle()
     N = 1 << args.cpu_log2n
     for _ in range(max(1, min(args.warmup, 1))):
-        oracle_run(orc, N, T, ys, threads)
+        oracle_run(orc, N, T, ys, threads, args.config)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        lml = oracle_run(orc, N, T, ys, threads)
+        lml = oracle_run(orc, N, T, ys, threads, args.config)
     dt = time.perf_counter() - t0
     value = N * T * args.steps / dt
     sample = "each step = one full filter run on a bounded sample: N=2^%d particles x T=%d (workload is 2^%d per GPU)" % (args.cpu_log2n, T, args.log2n)
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "1D linear-Gaussian SSM (Unfold), T=%d, bootstrap proposal, multinomial resampling at ESS<N/2" % T,
+            "config": {"workload": ("2D bearings-only tracking (Unfold), T=%d, custom proposal, multinomial resampling at ESS<N/2" if args.config == "cfg5" else
+                                    "1D linear-Gaussian SSM (Unfold), T=%d, bootstrap proposal, multinomial resampling at ESS<N/2") % T,
                        "note": "Gen.jl (Julia) cannot run here; this is the C port of its algorithm (oracle/) on all host threads"},
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "log_ml": lml, "log_ml_kalman": kalman(ys)}
+            "log_ml": lml, "log_ml_kalman": kalman(ys) if args.config == "cfg3" else None}
     emit(args.out_fd, line)
 
 
@@ -351,7 +401,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=24, help="log2 of particles per GPU")
-    ap.add_argument("--T", type=int, default=100)
+    ap.add_argument("--T", type=int, default=0, help="time steps (default: 100 for cfg3, 200 for cfg5)")
+    ap.add_argument("--config", default="cfg3", choices=["cfg3", "cfg5"], help="cfg3: LG-SSM (the headline); cfg5: bearings-only, custom proposal")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-history", action="store_true")
     ap.add_argument("--cpu-log2n", type=int, default=20)
