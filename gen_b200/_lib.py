@@ -76,6 +76,8 @@ SIGNATURES = {
     "gsmc_importance_sampling": (C.c_int, [C.POINTER(Config), _dp, C.c_size_t, _dp, C.c_size_t, C.c_int, _dp,
                                            C.c_size_t, _dp, C.POINTER(_H)]),
     "gsmc_run_steps": (C.c_int, [_H, _dp, C.c_size_t, C.c_size_t, C.c_int, _dp, C.c_size_t, C.c_double]),
+    "gsmc_save": (C.c_int, [_H, C.c_char_p]),
+    "gsmc_restore": (C.c_int, [_H, C.c_char_p]),
     "gsmc_trim": (C.c_int, []),
     "gsmc_local_count": (C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gsmc_state_dim": (C.c_int, [_H, C.POINTER(C.c_int)]),

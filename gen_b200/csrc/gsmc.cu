@@ -1197,7 +1197,7 @@ GSMC_API int gsmc_group_create(int nranks, int device, gsmc_group* out) {
 GSMC_API void gsmc_group_destroy(gsmc_group g) {
   if (!g) return;
   cudaSetDevice(g->device);
-  for (int r = 0; r < g->nranks; ++r) if (g->member[r]) { g->member[r]->group = nullptr; gsmc_destroy(g->member[r]); }
+  for (int r = 0; r < g->nranks; ++r) if (g->member[r]) gsmc_destroy(g->member[r]);      // (group stays set: no peer barrier kernel on one stream)
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -1283,6 +1283,120 @@ GSMC_API int gsmc_group_sample_unweighted(gsmc_group g, uint64_t num_samples, in
   std::vector<int64_t> scratch(num_samples);
   for (int r = 0; r < g->nranks; ++r) CKRC(sample_unweighted_impl(g->member[r], num_samples, scratch.data(), PH_LOCAL));
   for (int r = 0; r < g->nranks; ++r) CKRC(sample_unweighted_impl(g->member[r], num_samples, r == 0 ? idx_out : scratch.data(), PH_GLOBAL));
+  return GSMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// checkpoint / resume (the reference's analogue is saving Julia objects with JLD,
+// examples/planning/filtering.jl:822-829). One file per handle (per rank of a sharded filter): header, model
+// parameters, device scalars, the resample flags, the log weights and the state / ancestor columns that exist.
+// ------------------------------------------------------------------------------------------------
+struct CkptHeader {
+  char magic[8];                 // "GSMCCKP1"
+  uint32_t header_bytes, dev_scalars_bytes;
+  gsmc_config cfg;               // stream pointer zeroed
+  int32_t rank, nranks;
+  int64_t N, n, n_pad, cap, flag_mod, T, last_resample_step;
+  int32_t D, pending, decided_since_step, is_importance;
+  uint32_t n_sample_calls, n_params;
+  double is_lml;
+  int64_t n_cols;                // state / ancestor columns stored (steps T-n_cols+1 .. T)
+};
+static int write_dev(FILE* fp, gsmc_filter* f, const void* dev, size_t bytes, std::vector<char>& host) {
+  const size_t chunk = (size_t)64 << 20;
+  if (host.size() < (bytes < chunk ? bytes : chunk)) host.resize(bytes < chunk ? bytes : chunk);
+  for (size_t off = 0; off < bytes; off += chunk) {
+    const size_t len = bytes - off < chunk ? bytes - off : chunk;
+    CK(cudaMemcpyAsync(host.data(), (const char*)dev + off, len, cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    if (fwrite(host.data(), 1, len, fp) != len) return fail(GSMC_E_BADARG, "short write to the checkpoint file");
+  }
+  return GSMC_OK;
+}
+static int read_dev(FILE* fp, gsmc_filter* f, void* dev, size_t bytes, std::vector<char>& host) {
+  const size_t chunk = (size_t)64 << 20;
+  if (host.size() < (bytes < chunk ? bytes : chunk)) host.resize(bytes < chunk ? bytes : chunk);
+  for (size_t off = 0; off < bytes; off += chunk) {
+    const size_t len = bytes - off < chunk ? bytes - off : chunk;
+    if (fread(host.data(), 1, len, fp) != len) return fail(GSMC_E_BADARG, "checkpoint file is truncated");
+    CK(cudaMemcpyAsync((char*)dev + off, host.data(), len, cudaMemcpyHostToDevice, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+  }
+  return GSMC_OK;
+}
+GSMC_API int gsmc_save(gsmc_handle f, const char* path) {
+  if (!f || !path) return fail(GSMC_E_BADARG, "null argument");
+  if (f->T < 1 || !f->state_slab) return fail(GSMC_E_BADARG, "filter is not initialised");
+  CK(cudaSetDevice(f->device));
+  CK(cudaStreamSynchronize(f->stream));
+  FILE* fp = fopen(path, "wb");
+  if (!fp) return fail(GSMC_E_BADARG, "cannot open %s for writing", path);
+  CkptHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, "GSMCCKP1", 8);
+  h.header_bytes = (uint32_t)sizeof h; h.dev_scalars_bytes = (uint32_t)offsetof(DevScalars, mbox);
+  h.cfg = f->cfg; h.cfg.stream = nullptr;
+  h.rank = f->rank; h.nranks = f->nranks; h.N = f->N; h.n = f->n; h.n_pad = f->n_pad; h.cap = f->cap; h.flag_mod = f->flag_mod;
+  h.T = f->T; h.last_resample_step = f->last_resample_step; h.D = f->D;
+  h.pending = f->pending; h.decided_since_step = f->decided_since_step; h.is_importance = f->is_importance;
+  h.n_sample_calls = f->n_sample_calls; h.n_params = (uint32_t)f->params.size(); h.is_lml = f->is_lml;
+  // keep_history: every step so far; otherwise the current column and, with a resample pending, the column it fills
+  h.n_cols = f->cfg.keep_history ? f->T : 1;
+  std::vector<char> host;
+  int rc = GSMC_OK;
+  if (fwrite(&h, sizeof h, 1, fp) != 1 || fwrite(f->params.data(), sizeof(double), f->params.size(), fp) != f->params.size())
+    rc = fail(GSMC_E_BADARG, "short write to the checkpoint file");
+  if (rc == GSMC_OK) rc = write_dev(fp, f, f->ds, offsetof(DevScalars, mbox), host);
+  if (rc == GSMC_OK) rc = write_dev(fp, f, f->resampled, (size_t)f->flag_mod * sizeof(int), host);
+  if (rc == GSMC_OK) rc = write_dev(fp, f, f->lw, f->n_pad * real_size(f), host);
+  for (int64_t t = f->T - h.n_cols + 1; t <= f->T && rc == GSMC_OK; ++t) {
+    rc = write_dev(fp, f, state_col(f, f->state_slab, t), (size_t)f->D * f->n_pad * real_size(f), host);
+    if (rc == GSMC_OK) rc = write_dev(fp, f, anc_col(f, f->anc_slab, t), (size_t)f->n_pad * sizeof(uint32_t), host);
+  }
+  if (rc == GSMC_OK && f->pending) rc = write_dev(fp, f, anc_col(f, f->anc_slab, f->T + 1), (size_t)f->n_pad * sizeof(uint32_t), host);
+  if (fclose(fp) != 0 && rc == GSMC_OK) rc = fail(GSMC_E_BADARG, "closing %s failed", path);
+  return rc;
+}
+GSMC_API int gsmc_restore(gsmc_handle f, const char* path) {
+  if (!f || !path) return fail(GSMC_E_BADARG, "null argument");
+  CK(cudaSetDevice(f->device));
+  FILE* fp = fopen(path, "rb");
+  if (!fp) return fail(GSMC_E_BADARG, "cannot open %s", path);
+  CkptHeader h;
+  std::vector<double> params;
+  int rc = GSMC_OK;
+  if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "GSMCCKP1", 8) != 0 || h.header_bytes != sizeof h || h.dev_scalars_bytes != offsetof(DevScalars, mbox))
+    rc = fail(GSMC_E_BADARG, "%s is not a checkpoint of this library version", path);
+  if (rc == GSMC_OK) {
+    params.resize(h.n_params);
+    if (fread(params.data(), sizeof(double), params.size(), fp) != params.size()) rc = fail(GSMC_E_BADARG, "checkpoint file is truncated");
+  }
+  if (rc == GSMC_OK && (h.cfg.model_id != f->cfg.model_id || h.cfg.dtype != f->cfg.dtype || h.cfg.resample_scheme != f->cfg.resample_scheme ||
+                        h.cfg.num_particles != f->cfg.num_particles || h.cfg.seed != f->cfg.seed || h.cfg.keep_history != f->cfg.keep_history ||
+                        h.rank != f->rank || h.nranks != f->nranks || params != f->params))
+    rc = fail(GSMC_E_BADARG, "the checkpoint was written by a filter with another configuration (model, dtype, particles, seed, history, parameters or sharding)");
+  if (rc == GSMC_OK && !f->state_slab) rc = alloc_buffers(f);
+  if (rc == GSMC_OK && (h.cap > f->cap || h.n_pad != f->n_pad || h.flag_mod != f->flag_mod))
+    rc = fail(GSMC_E_BADARG, "the checkpoint needs history_capacity %lld, the handle has %lld", (long long)h.cap, (long long)f->cap);
+  std::vector<char> host;
+  if (rc == GSMC_OK) rc = peer_barrier(f);
+  if (rc == GSMC_OK) rc = read_dev(fp, f, f->ds, offsetof(DevScalars, xseq), host);       // the exchange sequence number and mailboxes stay
+  if (rc == GSMC_OK && fseek(fp, (long)(offsetof(DevScalars, mbox) - offsetof(DevScalars, xseq)), SEEK_CUR) != 0) rc = fail(GSMC_E_BADARG, "checkpoint file is truncated");
+  if (rc == GSMC_OK) rc = read_dev(fp, f, f->resampled, (size_t)f->flag_mod * sizeof(int), host);
+  if (rc == GSMC_OK) rc = read_dev(fp, f, f->lw, f->n_pad * real_size(f), host);
+  if (rc == GSMC_OK) {
+    f->T = h.T;                                         // the column helpers index by step
+    for (int64_t t = h.T - h.n_cols + 1; t <= h.T && rc == GSMC_OK; ++t) {
+      rc = read_dev(fp, f, state_col(f, f->state_slab, t), (size_t)f->D * f->n_pad * real_size(f), host);
+      if (rc == GSMC_OK) rc = read_dev(fp, f, anc_col(f, f->anc_slab, t), (size_t)f->n_pad * sizeof(uint32_t), host);
+    }
+    if (rc == GSMC_OK && h.pending) rc = read_dev(fp, f, anc_col(f, f->anc_slab, h.T + 1), (size_t)f->n_pad * sizeof(uint32_t), host);
+  }
+  fclose(fp);
+  if (rc != GSMC_OK) return rc;
+  f->last_resample_step = h.last_resample_step; f->pending = h.pending != 0; f->decided_since_step = h.decided_since_step != 0;
+  f->is_importance = h.is_importance != 0; f->n_sample_calls = h.n_sample_calls; f->is_lml = h.is_lml;
+  f->stats_fresh = false; f->zrep_n = 0; f->urep_n = 0;
   return GSMC_OK;
 }
 

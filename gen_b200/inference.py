@@ -179,6 +179,16 @@ class ParticleFilterState:
         _lib.check(self.lib.gsmc_sample_unweighted(self.handle, int(num_samples), _lib.iptr(out)), self.handle)
         return out
 
+    def save(self, path):
+        """Checkpoint (gsmc_save): one file per handle / per rank."""
+        _lib.check(self.lib.gsmc_save(self.handle, str(path).encode()), self.handle)
+
+    def restore(self, path, observations=()):
+        """Resume from a checkpoint written by a filter with the same configuration (gsmc_restore)."""
+        _lib.check(self.lib.gsmc_restore(self.handle, str(path).encode()), self.handle)
+        self.T = self.stats()["num_steps"]
+        self.observations = [np.atleast_1d(np.asarray(o, dtype=np.float64)) for o in observations]
+
     def stats(self):
         s = _lib.Stats()
         _lib.check(self.lib.gsmc_get_stats(self.handle, C.byref(s)), self.handle)
@@ -415,10 +425,11 @@ def chunk_seed(seed, c):
     return (int(seed) + c * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
 
 
-def importance_resampling(model, model_args, observations, *rest, **options):
-    """(trace, lml_est) = importance_resampling(model, model_args, observations, num_samples, verbose=false)
+def importance_resampling(model, model_args, observations, *rest, verbose=False, **options):
+    """(trace, lml_est) = importance_resampling(model, model_args, observations, num_samples; verbose=false)
     (trace, lml_est) = importance_resampling(model, model_args, observations, proposal, proposal_args,
-                                             num_samples, verbose=false)                 (importance.jl:70-108)
+                                             num_samples; verbose=false)                 (importance.jl:70-108)
+    `verbose` is keyword-only, as in the reference (importance.jl:72,89).
 
     Sampling importance resampling that returns ONE trace. The reference streams the samples one by one and keeps a
     reservoir of size one (`bernoulli(exp(log_weight - log_total_weight))`), so its memory does not grow with
@@ -427,14 +438,12 @@ def importance_resampling(model, model_args, observations, *rest, **options):
     has after the chunk), and chunks are merged with the reference's rule: the chunk's pick replaces the kept trace
     with probability exp(chunk_log_total - log_total_so_far). Device memory is bounded by the chunk size."""
     from . import philox
-    if len(rest) >= 3 and isinstance(rest[0], DeviceProposal):
+    if len(rest) == 3 and isinstance(rest[0], DeviceProposal):
         head, num_samples = (rest[0], rest[1]), rest[2]
-        verbose = rest[3] if len(rest) > 3 else False
-    elif len(rest) >= 1:
+    elif len(rest) == 1:
         head, num_samples = (), rest[0]
-        verbose = rest[1] if len(rest) > 1 else False
     else:
-        raise TypeError("importance_resampling(model, model_args, observations[, proposal, proposal_args], num_samples, verbose=False)")
+        raise TypeError("importance_resampling(model, model_args, observations[, proposal, proposal_args], num_samples; verbose=False)")
     num_samples = int(num_samples)
     if num_samples < 1:
         raise _lib.GsmcError(_lib.E_BADARG, "num_samples must be >= 1")

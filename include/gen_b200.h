@@ -191,6 +191,14 @@ GSMC_API int gsmc_run_steps(gsmc_handle h, const double* obs, size_t n_steps, si
                             int proposal_id, const double* proposal_params, size_t n_proposal_params,
                             double ess_threshold);
 
+/* Checkpoint / resume (the reference's analogue is saving Julia objects with JLD,
+ * examples/planning/filtering.jl:822-829). gsmc_save writes the filter behind h -- scalars, log weights, the state and
+ * ancestor columns that exist -- to one file (one per rank of a sharded filter). gsmc_restore loads it into a handle
+ * created with the same configuration and parameters (and attached to the same sharding); the run then continues
+ * bit-identically to one that was never interrupted. */
+GSMC_API int gsmc_save(gsmc_handle h, const char* path);
+GSMC_API int gsmc_restore(gsmc_handle h, const char* path);
+
 /* Release the slab pool (column slabs of destroyed filters are cached per device for reuse). */
 GSMC_API int gsmc_trim(void);
 

