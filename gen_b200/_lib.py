@@ -34,7 +34,8 @@ class Stats(C.Structure):
                 ("ms_propagate", C.c_double), ("ms_propagate_gather", C.c_double), ("ms_finalize", C.c_double),
                 ("ms_scan", C.c_double), ("ms_spacings", C.c_double), ("ms_search", C.c_double), ("ms_other", C.c_double),
                 ("n_propagate", C.c_int64), ("n_propagate_gather", C.c_int64), ("n_finalize", C.c_int64),
-                ("n_scan", C.c_int64), ("n_spacings", C.c_int64), ("n_search", C.c_int64), ("n_other", C.c_int64)]
+                ("n_scan", C.c_int64), ("n_spacings", C.c_int64), ("n_search", C.c_int64), ("n_other", C.c_int64),
+                ("graph_replays", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -209,6 +209,15 @@ struct gsmc_filter {
   const uint64_t* peer_cdf[GSMC_MAX_RANKS] = {};
   DevScalars* peer_ds[GSMC_MAX_RANKS] = {};
   gsmc_group_s* group = nullptr;  // shard emulation (all ranks on this device and stream)
+  // gsmc_run_steps as a CUDA graph (see run_steps_graph): the repeated call of one run shape is captured once
+  uint64_t graph_key = 0, graph_candidate = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_disabled = false;
+  int64_t graph_steps = 0;
+  cudaStream_t body_stream = nullptr;            // captures the bodies of the conditional nodes
+  unsigned long long cond_finalize = 0, cond_next = 0;   // conditional handles the next finalize / propagate launch sets
+  int64_t graph_launches = 0;
   uint32_t host_token = 0;      // token of the last decision published to the pinned host mirror
   bool fuse_next_decide = false;  // gsmc_run_steps: the propagate being launched also decides for the next step
   double fuse_thr = -1.0;
@@ -236,7 +245,13 @@ struct gsmc_filter {
   cudaEvent_t decision_ev = nullptr;   // recorded after the D2H copy of the decision
 };
 
+static void drop_graph(gsmc_filter* f) {
+  if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
+  if (f->graph) cudaGraphDestroy(f->graph);
+  f->graph_exec = nullptr; f->graph = nullptr; f->graph_key = 0;
+}
 static size_t real_size(const gsmc_filter* f) { return f->f32 ? 4 : 8; }
+static size_t partials_bytes(const gsmc_filter* f) { return (size_t)(f->n_pad / (2 * GSMC_BLOCK * 2)) * sizeof(LseTriple); }
 static int xmode(const gsmc_filter* f) {
   if (f->nranks <= 1) return XMODE_NONE;
   if (f->group) return XMODE_LOCAL;
@@ -353,7 +368,9 @@ static int alloc_buffers(gsmc_filter* f) {
   CK(pool_alloc(f->device, (void**)&f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->gap, (size_t)(f->n_pad / GSMC_GROUP) * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t)));
-  CK(pool_alloc(f->device, (void**)&f->partials, (size_t)f->n_tiles * sizeof(LseTriple)));
+  // one logsumexp partial per propagate block; the grid is at most one block per propagate tile, and the smallest
+  // propagate tile (wide states: 2 pairs per thread) is half a GSMC_TILE
+  CK(pool_alloc(f->device, (void**)&f->partials, partials_bytes(f)));
   CK(pool_alloc(f->device, (void**)&f->ds, sizeof(DevScalars)));
   CK(pinned_alloc(&f->h_ds));
   memset(f->h_ds, 0, sizeof(DevScalars));          // pooled buffer: no stale decision token
@@ -386,7 +403,7 @@ static void free_buffers(gsmc_filter* f) {
   pool_free(f->device, f->raw0, seg_words * sizeof(uint64_t)); pool_free(f->device, f->raw1, seg_words * sizeof(uint64_t));
   pool_free(f->device, f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t));
   pool_free(f->device, f->gap, (size_t)(f->n_pad / GSMC_GROUP) * sizeof(uint64_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
-  pool_free(f->device, f->partials, (size_t)f->n_tiles * sizeof(LseTriple)); pool_free(f->device, f->ds, sizeof(DevScalars));
+  pool_free(f->device, f->partials, partials_bytes(f)); pool_free(f->device, f->ds, sizeof(DevScalars));
   pool_free(f->device, f->resampled, (size_t)f->flag_mod * sizeof(int));
   pinned_free(f->h_ds);
   f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
@@ -415,6 +432,9 @@ static unsigned pdl_mask() {
   static unsigned mask = getenv("GSMC_NO_PDL") ? 0u : (getenv("GSMC_PDL_MASK") ? (unsigned)strtoul(getenv("GSMC_PDL_MASK"), nullptr, 0) : 0x3eu);
   return mask;
 }
+// While a run is being captured into a graph, the kernel that follows a conditional node (and the first kernel of a
+// conditional body) must not carry the programmatic-dependency attribute: its predecessor is not a kernel node.
+static thread_local bool g_pdl_suppress_next = false;
 template <int CLS = PDL_OTHER, typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -423,7 +443,8 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = ((pdl_mask() >> CLS) & 1u) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (((pdl_mask() >> CLS) & 1u) && !g_pdl_suppress_next) ? 1 : 0;
+  g_pdl_suppress_next = false;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 template <class Model, typename Real, bool INIT, int PROP>
@@ -442,6 +463,7 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   g.ds = f->ds; g.nranks = f->nranks;
   g.fuse_decide = (f->fuse_next_decide && (f->nranks == 1 || xmode(f) == XMODE_LL)) ? 1 : 0;
   g.peers = peer_scalars(f);
+  g.cond_handle = g.fuse_decide ? f->cond_next : 0;
   g.fuse_threshold = f->fuse_thr; g.n_global = (double)f->N;
   g.next_flag = f->resampled + ((new_step + 1) % f->flag_mod);
   g.n = f->n; g.stride = f->n_pad; g.first_global = (uint64_t)f->first; g.seed = f->cfg.seed; g.keys = make_philox_keys(f->cfg.seed);
@@ -464,6 +486,7 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)propagate_kernel<Model, Real, INIT, PROP>, GSMC_BLOCK,
                                                         Model::SMEM_DOUBLES * sizeof(double)) != cudaSuccess || occ < 1) occ = 2;
     }
+    static_assert(PropTile<Model>::TILE >= 2 * GSMC_BLOCK * 2, "partials_bytes() assumes at least 2 pairs per thread");
     g.n_tiles = (int)(f->n_pad / PropTile<Model>::TILE);
     f->n_partials = g.n_tiles < f->sm_count * occ ? g.n_tiles : f->sm_count * occ;
     CK(launch_pdl<PDL_PROPAGATE>(propagate_kernel<Model, Real, INIT, PROP>, f->n_partials, GSMC_BLOCK, Model::SMEM_DOUBLES * sizeof(double), f->stream, g, a));
@@ -542,7 +565,7 @@ static int launch_finalize(gsmc_filter* f, double ess_threshold, bool to_host = 
   {
     ProfScope ps(f, KC_FINALIZE);
     CK(launch_pdl<PDL_FINALIZE>(finalize_kernel, 1, 32, 0, f->stream, f->ds, f->rank, f->nranks, ess_threshold, (double)f->N, flag, (int64_t)(f->T + 1),
-                                peer_scalars(f), xm, nccl ? (DevScalars*)nullptr : host, f->host_token));
+                                peer_scalars(f), xm, nccl ? (DevScalars*)nullptr : host, f->host_token, f->cond_finalize));
   }
   CK(cudaGetLastError());
   if (nccl) {
@@ -791,6 +814,8 @@ GSMC_API void gsmc_destroy(gsmc_handle f) {
   if (f->stream) cudaStreamSynchronize(f->stream);
   harvest_profile(f);
   for (ProfEvent& e : f->prof_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  drop_graph(f);
+  if (f->body_stream) cudaStreamDestroy(f->body_stream);
   free_buffers(f);
   pool_free(f->device, f->d_params, f->params.size() * sizeof(double)); cudaFree(f->d_obs); cudaFree(f->d_zrep); cudaFree(f->d_urep); cudaFree(f->d_f64);
   if (f->timer_a) cudaEventDestroy(f->timer_a);
@@ -1144,6 +1169,138 @@ GSMC_API int gsmc_importance_sampling(const gsmc_config* cfg, const double* para
   return GSMC_OK;
 }
 
+// The loop of gsmc_run_steps, enqueued on f->stream. handles (captured run only): one conditional handle per step; the
+// resampling kernels of step s are then captured into the body of an IF node instead of being launched in their
+// early-exit form.
+static int enqueue_steps(gsmc_filter* f, const double* obs, size_t n_steps, size_t n_obs, int prop, const double* pp, size_t npp,
+                         double ess_threshold, const std::vector<cudaGraphConditionalHandle>* handles, std::vector<cudaGraph_t>* bodies) {
+  bool decided = false;
+  for (size_t s = 0; s < n_steps; ++s) {
+    if (!decided) {
+      f->cond_finalize = handles ? (*handles)[s] : 0;
+      const int rc = launch_finalize(f, ess_threshold);
+      f->cond_finalize = 0;
+      if (rc != GSMC_OK) return rc;
+    }
+    if (handles) {
+      // IF node on this step's handle, depending on everything captured so far; its body = the resampling kernels
+      cudaStreamCaptureStatus status;
+      cudaGraph_t graph = nullptr;
+      const cudaGraphNode_t* deps = nullptr;
+      size_t n_deps = 0;
+      CK(cudaStreamGetCaptureInfo_v2(f->stream, &status, nullptr, &graph, &deps, &n_deps));
+      cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = (*handles)[s];
+      np.conditional.type = cudaGraphCondTypeIf;
+      np.conditional.size = 1;
+      cudaGraphNode_t node;
+      CK(cudaGraphAddNode(&node, graph, deps, n_deps, &np));
+      cudaGraph_t body = np.conditional.phGraph_out[0];
+      cudaStream_t main_stream = f->stream;
+      CK(cudaStreamBeginCaptureToGraph(f->body_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+      f->stream = f->body_stream;
+      g_pdl_suppress_next = true;
+      int rc = launch_resample(f, 0, false);
+      f->stream = main_stream;
+      cudaGraph_t out = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(f->body_stream, &out);
+      if (rc != GSMC_OK) return rc;
+      CK(e);
+      bodies->push_back(body);
+      CK(cudaStreamUpdateCaptureDependencies(f->stream, &node, 1, cudaStreamSetCaptureDependencies));
+      g_pdl_suppress_next = true;                        // the propagate below follows the conditional node
+    } else {
+      CKRC(launch_resample(f, 1, false));
+    }
+    f->fuse_next_decide = (f->nranks == 1 || xmode(f) == XMODE_LL) && !f->profiling && s + 1 < n_steps;
+    f->fuse_thr = ess_threshold;
+    f->cond_next = (handles && s + 1 < n_steps) ? (*handles)[s + 1] : 0;
+    const int rc = launch_propagate(f, false, obs + s * n_obs, n_obs, prop, pp, npp, true);
+    g_pdl_suppress_next = false;
+    decided = f->fuse_next_decide;
+    f->fuse_next_decide = false;
+    f->cond_next = 0;
+    if (rc != GSMC_OK) return rc;
+    f->T += 1;
+  }
+  return GSMC_OK;
+}
+
+static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+  const unsigned char* c = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 0x100000001b3ULL; }
+  return h;
+}
+// A run shape that repeats (same first step, number of steps, observations, proposal and threshold on this handle --
+// e.g. reset + init + run_steps in a loop) is captured into ONE CUDA graph on its second occurrence and replayed from
+// then on: every step's resampling kernels sit in the body of a conditional (IF) node whose handle the deciding
+// kernel sets on the device, so the steps that do not resample launch nothing, and kernel-to-kernel gaps shrink to
+// graph edges. Returns 1 if the steps were enqueued through the graph, 0 if the caller should enqueue them itself.
+static int run_steps_graph(gsmc_filter* f, const double* obs, size_t n_steps, size_t n_obs, int prop, const double* pp, size_t npp,
+                           double ess_threshold, int* used) {
+  *used = 0;
+  // Measured on B200 (profiles/r2_graph.txt): a conditional node costs about as much as the three early-exit launches of
+  // the multinomial scheme (cfg 3: 22.9 ms with the graph, 22.6 without), but far less than the ten of the residual
+  // scheme (cfg 4: 98 ms against 130 ms). Default: residual only; GSMC_GRAPH=1 captures every scheme, GSMC_NO_GRAPH=1 none.
+  static int env_off = getenv("GSMC_NO_GRAPH") ? 1 : 0;
+  static int env_all = getenv("GSMC_GRAPH") ? 1 : 0;
+  const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
+  if (env_off || (!residual && !env_all) || f->graph_disabled || f->profiling || f->group || (f->nranks > 1 && xmode(f) != XMODE_LL) || n_steps < 2 ||
+      f->model == GSMC_MODEL_REGRESSION || (residual && f->nranks > 1)) return GSMC_OK;
+  uint64_t key = 0xcbf29ce484222325ULL;
+  const int64_t t0 = f->T;
+  key = fnv1a(key, &t0, sizeof t0); key = fnv1a(key, &n_steps, sizeof n_steps); key = fnv1a(key, &n_obs, sizeof n_obs);
+  key = fnv1a(key, &prop, sizeof prop); key = fnv1a(key, pp, npp * sizeof(double)); key = fnv1a(key, &ess_threshold, sizeof ess_threshold);
+  key = fnv1a(key, obs, n_steps * n_obs * sizeof(double));
+  if (key == 0) key = 1;
+  if (f->graph_exec && f->graph_key == key) {
+    CK(cudaGraphLaunch(f->graph_exec, f->stream));
+    f->T += (int64_t)n_steps;
+    f->graph_launches += 1; f->launches += f->graph_steps;
+    *used = 1;
+    return GSMC_OK;
+  }
+  if (f->graph_candidate != key) { f->graph_candidate = key; return GSMC_OK; }       // first occurrence: plain launches
+  // second occurrence: capture
+  drop_graph(f);
+  if (!f->body_stream && cudaStreamCreateWithFlags(&f->body_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); f->graph_disabled = true; return GSMC_OK; }
+  const int64_t launches0 = f->launches;
+  std::vector<cudaGraphConditionalHandle> handles(n_steps);
+  std::vector<cudaGraph_t> bodies;
+  cudaGraph_t graph = nullptr;
+  bool ok = cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  if (ok) {
+    cudaStreamCaptureStatus status;
+    cudaGraph_t g0 = nullptr;
+    ok = cudaStreamGetCaptureInfo_v2(f->stream, &status, nullptr, &g0, nullptr, nullptr) == cudaSuccess && g0;
+    for (size_t s = 0; ok && s < n_steps; ++s) ok = cudaGraphConditionalHandleCreate(&handles[s], g0, 0, cudaGraphCondAssignDefault) == cudaSuccess;
+    if (ok) ok = enqueue_steps(f, obs, n_steps, n_obs, prop, pp, npp, ess_threshold, &handles, &bodies) == GSMC_OK;
+    g_pdl_suppress_next = false;
+    cudaStreamCaptureStatus st2 = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(f->body_stream, &st2);
+    if (st2 != cudaStreamCaptureStatusNone) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(f->body_stream, &junk); }
+    const cudaError_t e = cudaStreamEndCapture(f->stream, &graph);
+    ok = ok && e == cudaSuccess && graph;
+  }
+  f->T = t0;                                              // nothing has run yet
+  f->zrep_n = 0; f->urep_n = 0;
+  if (ok) ok = cudaGraphInstantiate(&f->graph_exec, graph, 0) == cudaSuccess;
+  if (!ok) {
+    const cudaError_t e = cudaGetLastError();
+    if (getenv("GSMC_GRAPH_DEBUG")) fprintf(stderr, "libgensmc: graph capture of gsmc_run_steps failed (%s); using stream launches\n", cudaGetErrorString(e));
+    if (graph) cudaGraphDestroy(graph);
+    f->graph_exec = nullptr; f->graph_disabled = true; f->launches = launches0;
+    return GSMC_OK;
+  }
+  f->graph = graph; f->graph_key = key; f->graph_steps = f->launches - launches0; f->launches = launches0;
+  CK(cudaGraphLaunch(f->graph_exec, f->stream));
+  f->T += (int64_t)n_steps;
+  f->graph_launches += 1; f->launches += f->graph_steps;
+  *used = 1;
+  return GSMC_OK;
+}
+
 GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, size_t n_obs, int prop, const double* pp, size_t npp,
                             double ess_threshold) {
   if (!f || !obs) return fail(GSMC_E_BADARG, "null argument");
@@ -1155,23 +1312,19 @@ GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, si
   if (f->cfg.keep_history && f->T + (int64_t)n_steps > f->cap)
     return fail(GSMC_E_BADARG, "history_capacity (%lld steps) would be exceeded by %zu more steps after step %lld", (long long)f->cap, n_steps, (long long)f->T);
   if (n_obs != (size_t)expected_obs(f)) return fail(GSMC_E_BADARG, "model %d needs %d observation value(s) per step, got %zu", f->model, expected_obs(f), n_obs);
+  if (f->group) return fail(GSMC_E_UNSUPPORTED, "gsmc_run_steps is not available on an emulated shard group");
   CK(cudaSetDevice(f->device));
   // The threshold of every decision is known here, so the last block of each propagate also takes the decision of the
   // next step (on a sharded filter after exchanging the ranks' triples over the LL mailboxes): only the first step of
   // the call needs a finalize launch.
-  if (f->group) return fail(GSMC_E_UNSUPPORTED, "gsmc_run_steps is not available on an emulated shard group");
-  bool decided = false;
-  for (size_t s = 0; s < n_steps; ++s) {
-    if (!decided) CKRC(launch_finalize(f, ess_threshold));
-    CKRC(launch_resample(f, 1, false));
-    f->fuse_next_decide = (f->nranks == 1 || xmode(f) == XMODE_LL) && !f->profiling && s + 1 < n_steps;
-    f->fuse_thr = ess_threshold;
-    const int rc = launch_propagate(f, false, obs + s * n_obs, n_obs, prop, pp, npp, true);
-    decided = f->fuse_next_decide;
-    f->fuse_next_decide = false;
-    if (rc != GSMC_OK) return rc;
-    f->T += 1;
+  {
+    // validate the arguments of every step before anything is enqueued or captured
+    ModelArgs a;
+    for (size_t s = 0; s < n_steps; ++s) if (f->model != GSMC_MODEL_REGRESSION) CKRC(fill_model_args(f, a, obs + s * n_obs, n_obs, prop, pp, npp));
   }
+  int used = 0;
+  CKRC(run_steps_graph(f, obs, n_steps, n_obs, prop, pp, npp, ess_threshold, &used));
+  if (!used) CKRC(enqueue_steps(f, obs, n_steps, n_obs, prop, pp, npp, ess_threshold, nullptr, nullptr));
   f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
   // surface a degenerate-weight error recorded on the device
   CKRC(fetch_scalars(f));
@@ -1449,6 +1602,7 @@ GSMC_API int gsmc_get_stats(gsmc_handle f, gsmc_stats* out) {
   out->ms_search = f->prof_ms[KC_SEARCH]; out->n_search = f->prof_n[KC_SEARCH];
   out->ms_other = f->prof_ms[KC_OTHER]; out->n_other = f->prof_n[KC_OTHER];
   out->ms_propagate_gather = f->prof_ms[KC_PROPAGATE_GATHER]; out->n_propagate_gather = f->prof_n[KC_PROPAGATE_GATHER];
+  out->graph_replays = f->graph_launches;
   return GSMC_OK;
 }
 GSMC_API int gsmc_set_profiling(gsmc_handle f, int enabled) {

@@ -213,6 +213,7 @@ struct PropArgs {
   double fuse_threshold, n_global;   //   maybe_resample! decision of the NEXT step (no finalize launch in between);
   int* next_flag;                    //   resampled[] slot of the next step
   PeerScalars peers;                 //   sharded filter: it first exchanges the ranks' triples over the LL mailboxes
+  unsigned long long cond_handle;    //   captured run (CUDA graph): conditional handle of the next step's resampling block, 0 = none
   int64_t n;                         // local particle count
   int64_t stride;                    // column stride (padded n)
   uint64_t first_global;             // global index of local particle 0
@@ -511,7 +512,10 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
     const LseTriple tr = reduce_partials(g.partials, (int)gridDim.x, red, tabs.exp2);
     if (threadIdx.x == 0) {
       g.ds->triples[g.rank] = tr; g.ds->blocks_done = 0;
-      if (g.fuse_decide && g.nranks == 1) combine_and_decide(g.ds, 1, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
+      if (g.fuse_decide && g.nranks == 1) {
+        combine_and_decide(g.ds, 1, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
+        if (g.cond_handle) cudaGraphSetConditional(g.cond_handle, g.ds->do_resample ? 1u : 0u);
+      }
     }
     if (g.fuse_decide && g.nranks > 1) {
       // Sharded filter: this block sends the rank's triple to every peer as soon as it is known and merges all of them
@@ -523,7 +527,10 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
       __syncthreads();
       ll_allgather_u64(g.peers, g.ds, g.rank, g.nranks, s_seq, s_mine, 3, reinterpret_cast<uint64_t*>(g.ds->triples));
       __syncthreads();
-      if (threadIdx.x == 0) combine_and_decide(g.ds, g.nranks, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
+      if (threadIdx.x == 0) {
+        combine_and_decide(g.ds, g.nranks, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
+        if (g.cond_handle) cudaGraphSetConditional(g.cond_handle, g.ds->do_resample ? 1u : 0u);
+      }
     }
   }
 }
@@ -548,7 +555,8 @@ __device__ __forceinline__ void publish_decision(const DevScalars* ds, DevScalar
 // without a separate collective.
 __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, int nranks, double ess_threshold,
                                                       double n_global, int* resampled_flag_out, int64_t next_step,
-                                                      PeerScalars peers, int xmode, DevScalars* host, uint32_t token) {
+                                                      PeerScalars peers, int xmode, DevScalars* host, uint32_t token,
+                                                      unsigned long long cond_handle) {
   __shared__ uint64_t mine[3];
   pdl_wait();
   pdl_trigger();
@@ -563,13 +571,13 @@ __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, 
     __syncwarp();
     ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 3, reinterpret_cast<uint64_t*>(ds->triples));
     __syncwarp();
-    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
+    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
   } else if (nranks > 1 && xmode == XMODE_LOCAL) {
     if ((int)threadIdx.x < nranks && (int)threadIdx.x != rank) ds->triples[threadIdx.x] = peers.ds[threadIdx.x]->triples[threadIdx.x];
     __syncwarp();
-    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
+    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
   } else if (nranks == 1) {
-    if (threadIdx.x == 0) { combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
+    if (threadIdx.x == 0) { combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
   }
 }
 // cross-GPU barrier (peer-memory exchange of one word): nobody passes until every rank has arrived

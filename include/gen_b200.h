@@ -83,6 +83,7 @@ typedef struct gsmc_stats {
    * gsmc_run_steps cannot tell them apart without a host round trip and books all as propagate). */
   double ms_propagate, ms_propagate_gather, ms_finalize, ms_scan, ms_spacings, ms_search, ms_other;
   int64_t n_propagate, n_propagate_gather, n_finalize, n_scan, n_spacings, n_search, n_other;
+  int64_t graph_replays;     /* gsmc_run_steps calls served by the captured CUDA graph of a repeated run shape */
 } gsmc_stats;
 
 GSMC_API const char* gsmc_version(void);
@@ -186,7 +187,11 @@ GSMC_API int gsmc_importance_sampling(const gsmc_config* cfg, const double* para
 /* The canonical driver loop of test/inference/particle_filter.jl:130-137 enqueued without a host
  * round trip per step: for t in 1..T-1 { maybe_resample!(ess_frac*N); particle_filter_step!(obs[t]) }
  * starting from an initialised filter. obs is [T_steps][n_obs]. Results via gsmc_log_ml_estimate /
- * gsmc_get_stats. */
+ * gsmc_get_stats. With residual resampling (ten kernels per event), a run shape that repeats on a handle (same first
+ * step, step count, observations, proposal and threshold, e.g. reset + init + run_steps in a loop) is captured into one
+ * CUDA graph on its second occurrence and replayed afterwards; the resampling kernels of every step sit behind a
+ * conditional node that the deciding kernel sets on the device, so steps that do not resample launch nothing
+ * (GSMC_GRAPH=1: also for multinomial resampling, where it measured slightly slower; GSMC_NO_GRAPH=1: never). */
 GSMC_API int gsmc_run_steps(gsmc_handle h, const double* obs, size_t n_steps, size_t n_obs,
                             int proposal_id, const double* proposal_params, size_t n_proposal_params,
                             double ess_threshold);

@@ -72,6 +72,7 @@ def filter_run(name, model, ys, N, S, resample="multinomial", proposal=None, kee
         return st.log_ml_estimate()
 
     one()
+    one()                      # the second occurrence of a run shape is captured into a CUDA graph; later ones replay it
     st.synchronize()
     st.timer_start()
     for _ in range(reps):
@@ -135,7 +136,7 @@ def cfg3():
 def cfg4():
     p = [-1.0, 0.97, 0.2]
     return filter_run("cfg4 stochastic volatility T=1000 N=2^22, residual resampling at ESS<N/2", g.StochasticVolatility(*p), sim_sv(1000, p),
-                      1 << 22, 8, resample="residual", reps=1)
+                      1 << 22, 8, resample="residual", reps=2)
 
 
 def cfg5():

@@ -14,6 +14,9 @@ pytestmark = pytest.mark.gpu
 
 LG = [0.0, 1.0, 0.9, 0.0, 1.0, 1.0, 1.0]
 SVP = [-1.0, 0.97, 0.2]
+import os
+os.environ.setdefault("GSMC_GRAPH", "1")      # the library reads it once: capture every scheme so that the graph path is tested for all
+GRAPH_ALL = os.environ.get("GSMC_GRAPH") is not None and os.environ.get("GSMC_NO_GRAPH") is None
 
 
 def make_model(g, fam):
@@ -637,3 +640,51 @@ def test_ancestors_after_run_steps(gpu, orc):
         st.run_steps(ys[T:T + 3], N / 2)
     assert st.T == T and st.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
     st.close()
+
+
+@pytest.mark.parametrize("fam,prop,scheme", [(O.LGSSM, 0, "multinomial"), (O.BEARINGS, 1, "multinomial"), (O.SV, 0, "residual")])
+def test_run_steps_graph_replay_is_bit_identical(gpu, orc, fam, prop, scheme):
+    """A repeated run shape is captured into a CUDA graph on its second occurrence (conditional node per step around
+    the resampling kernels) and replayed afterwards: every repetition gives the bits of the per-call loop, and a
+    different shape or different observations fall back to plain launches / a new capture."""
+    g = gpu
+    N, T = 30000, 20
+    model, params, ys = make_model(g, fam)
+    proposal = model.custom_proposal() if prop else None
+    st = g.ParticleFilterState(model, N, seed=13, resample=scheme, keep_history=True, history_capacity=T)
+    ref = g.ParticleFilterState(model, N, seed=13, resample=scheme, keep_history=True, history_capacity=T)
+    graphs = 3 if scheme == "residual" or GRAPH_ALL else 0      # by default only the residual scheme is captured
+    ref.init([ys[0]], proposal)
+    anc_last = None
+    for t in range(1, T):
+        if ref.maybe_resample(N / 2):
+            anc_last = ref.ancestors()
+        ref.step([ys[t]], proposal)
+    lw_ref, x_ref, lml_ref, h_ref = ref.log_weights(), ref.state(), ref.log_ml_estimate(), ref.state(2)
+    assert ref.stats()["num_resamples"] > 0 and anc_last is not None
+    for rep in range(4):
+        st.reset()
+        st.init([ys[0]], proposal)
+        st.run_steps(ys[1:T], N / 2, proposal)
+        assert same_bits(st.log_weights(), lw_ref) and same_bits(st.state(), x_ref), "repetition %d" % rep
+        assert st.log_ml_estimate() == lml_ref, "repetition %d" % rep
+        for t in range(1, T + 1):
+            assert same_bits(st.state(t), ref.state(t)), "history of step %d differs in repetition %d (%d values)" % (
+                t, rep, int(np.sum(st.state(t).view(np.uint64) != ref.state(t).view(np.uint64))))
+        assert np.array_equal(st.ancestors(), anc_last)
+        assert st.stats()["num_resamples"] == ref.stats()["num_resamples"]
+    assert st.stats()["graph_replays"] == graphs     # captured on the second occurrence, replayed from then on
+    # other observations: not the captured run
+    ys2 = ys.copy()
+    ys2[3] += 0.125
+    st.reset()
+    st.init([ys2[0]], proposal)
+    st.run_steps(ys2[1:T], N / 2, proposal)
+    pf = orc.particle_filter(fam, params, N, seed=13)
+    pf.init([ys2[0]], proposal=prop)
+    for t in range(1, T):
+        pf.maybe_resample(N / 2, scheme=1 if scheme == "residual" else 0)
+        pf.step([ys2[t]], proposal=prop)
+    assert same_bits(st.log_weights(), pf.log_weights()) and st.stats()["graph_replays"] == graphs
+    st.close()
+    ref.close()
