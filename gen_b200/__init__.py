@@ -8,6 +8,6 @@ from .inference import (DeviceTrace, DeviceTraces, ParticleFilterState, get_log_
                         maybe_resample_b, particle_filter_step_, particle_filter_step_b, sample_unweighted_traces)
 from .pmmh import ParticleFilterCombinator, PFCombinatorTrace, pmmh
 from .models import (HMM, BearingsOnly, DeviceModel, DeviceProposal, LinearGaussianSSM, LinearRegression, NormalNormal,
-                     StochasticVolatility)
+                     OutlierRegression, StochasticVolatility, UniformNormal)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -7,6 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgensmc.so")
 
 MODEL_HMM, MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_REGRESSION, MODEL_NORMAL_NORMAL = 1, 2, 3, 4, 5, 6
+MODEL_OUTLIER_REGRESSION, MODEL_UNIFORM_NORMAL = 7, 8
+IS_FAMILIES = (MODEL_REGRESSION, MODEL_NORMAL_NORMAL, MODEL_OUTLIER_REGRESSION, MODEL_UNIFORM_NORMAL)
 PROPOSAL_DEFAULT, PROPOSAL_CUSTOM = 0, 1
 RESAMPLE_MULTINOMIAL, RESAMPLE_RESIDUAL = 0, 1
 F64, F32 = 0, 1

@@ -305,10 +305,15 @@ static int model_dim(int model) {
     case GSMC_MODEL_BEARINGS: return BearingsModel::D;
     case GSMC_MODEL_REGRESSION: return RegressionModel::D;
     case GSMC_MODEL_NORMAL_NORMAL: return NormalNormalModel::D;
+    case GSMC_MODEL_OUTLIER_REGRESSION: return OutlierRegressionModel::D;
+    case GSMC_MODEL_UNIFORM_NORMAL: return UniformNormalModel::D;
     default: return -1;
   }
 }
-static bool model_is_importance(int model) { return model == GSMC_MODEL_REGRESSION || model == GSMC_MODEL_NORMAL_NORMAL; }
+static bool model_is_importance(int model) {
+  return model == GSMC_MODEL_REGRESSION || model == GSMC_MODEL_NORMAL_NORMAL || model == GSMC_MODEL_OUTLIER_REGRESSION || model == GSMC_MODEL_UNIFORM_NORMAL;
+}
+static bool model_obs_on_device(int model) { return model == GSMC_MODEL_REGRESSION || model == GSMC_MODEL_OUTLIER_REGRESSION; }
 
 static int check_params(int model, const double* p, size_t np) {
   switch (model) {
@@ -326,11 +331,16 @@ static int check_params(int model, const double* p, size_t np) {
       if (np < 4 || np != (size_t)(4 + (int)p[0])) return fail(GSMC_E_BADARG, "regression params: [n, sd_slope, sd_intercept, sd_noise, xs[n]]");
       return GSMC_OK;
     case GSMC_MODEL_NORMAL_NORMAL: return np == 3 ? GSMC_OK : fail(GSMC_E_BADARG, "normal-normal params: [mu0, sd0, sd_y]");
+    case GSMC_MODEL_OUTLIER_REGRESSION:
+      if (np < 4 || np != (size_t)(3 + (int)p[0]) || (int)p[0] < 1 || (int)p[0] > 32 * GSMC_OUTLIER_ZWORDS)
+        return fail(GSMC_E_BADARG, "outlier regression params: [n, prob_outlier, prior_sd, xs[n]] with 1 <= n <= %d", 32 * GSMC_OUTLIER_ZWORDS);
+      return GSMC_OK;
+    case GSMC_MODEL_UNIFORM_NORMAL: return (np == 3 && p[1] > p[0]) ? GSMC_OK : fail(GSMC_E_BADARG, "uniform-normal params: [low, high, sd_y] with high > low");
     default: return fail(GSMC_E_UNSUPPORTED, "unknown model id %d", model);
   }
 }
 static int expected_obs(const gsmc_filter* f) {
-  if (f->model == GSMC_MODEL_REGRESSION) return (int)f->params[0];
+  if (model_obs_on_device(f->model)) return (int)f->params[0];
   return 1;
 }
 
@@ -472,7 +482,8 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   g.rank = f->rank;
   g.zrep = f->zrep_n ? f->d_zrep : nullptr;
   g.urep = f->urep_n ? f->d_urep : nullptr;
-  const int nz = Model::nz(INIT, PROP), nu = Model::nu(INIT, PROP);
+  // models that draw a run-time number of uniforms per particle (DrawCtx) take p[0] of them
+  const int nz = Model::nz(INIT, PROP), nu = model_ctx_uniforms<Model>::value ? (int)f->params[0] : Model::nu(INIT, PROP);
   if (g.zrep && f->zrep_n != (size_t)(f->n * nz)) return fail(GSMC_E_BADARG, "replay normals: expected %lld values", (long long)(f->n * nz));
   if (g.urep && nu && f->urep_n != (size_t)(f->n * nu)) return fail(GSMC_E_BADARG, "replay uniforms: expected %lld values", (long long)(f->n * nu));
   if (!nu) g.urep = nullptr;
@@ -509,6 +520,10 @@ static int launch_propagate_r(gsmc_filter* f, ModelArgs& a, bool init, int prop,
     case GSMC_MODEL_BEARINGS: return launch_propagate_m<BearingsModel, Real>(f, a, init, prop, use_anc);
     case GSMC_MODEL_REGRESSION: return launch_propagate_m<RegressionModel, Real>(f, a, init, prop, use_anc);
     case GSMC_MODEL_NORMAL_NORMAL: return launch_propagate_m<NormalNormalModel, Real>(f, a, init, prop, use_anc);
+    case GSMC_MODEL_OUTLIER_REGRESSION:
+      if (f->f32) return fail(GSMC_E_UNSUPPORTED, "the outlier-regression model packs its flags into exact f64 integers: dtype must be f64");
+      return launch_propagate_m<OutlierRegressionModel, Real>(f, a, init, prop, use_anc);
+    case GSMC_MODEL_UNIFORM_NORMAL: return launch_propagate_m<UniformNormalModel, Real>(f, a, init, prop, use_anc);
   }
   return fail(GSMC_E_UNSUPPORTED, "unknown model");
 }
@@ -525,8 +540,8 @@ static int fill_model_args(gsmc_filter* f, ModelArgs& a, const double* obs, size
   for (size_t i = 0; i < npp; ++i) a.pp[i] = pp[i];
   a.p_dev = f->d_params;
   a.obs_dev = nullptr;
-  if (f->model == GSMC_MODEL_REGRESSION) {
-    if (prop == GSMC_PROPOSAL_CUSTOM && npp != 4) return fail(GSMC_E_BADARG, "regression proposal params: [mu_slope, sd_slope, mu_intercept, sd_intercept]");
+  if (model_obs_on_device(f->model)) {
+    if (f->model == GSMC_MODEL_REGRESSION && prop == GSMC_PROPOSAL_CUSTOM && npp != 4) return fail(GSMC_E_BADARG, "regression proposal params: [mu_slope, sd_slope, mu_intercept, sd_intercept]");
     if (n_obs > f->d_obs_cap) {
       cudaFree(f->d_obs); f->d_obs = nullptr; f->d_obs_cap = 0;
       CK(cudaMalloc(&f->d_obs, n_obs * sizeof(double)));
@@ -538,6 +553,8 @@ static int fill_model_args(gsmc_filter* f, ModelArgs& a, const double* obs, size
   }
   if (f->model == GSMC_MODEL_NORMAL_NORMAL && prop == GSMC_PROPOSAL_CUSTOM && npp != 2)
     return fail(GSMC_E_BADARG, "normal-normal proposal params: [mu_q, sd_q]");
+  if (f->model == GSMC_MODEL_UNIFORM_NORMAL && prop == GSMC_PROPOSAL_CUSTOM && (npp != 2 || !(pp[1] > pp[0])))
+    return fail(GSMC_E_BADARG, "uniform-normal proposal params: [low_q, high_q] with high_q > low_q");
   if (f->model == GSMC_MODEL_HMM) {
     const int V = (int)f->params[1];
     if (!(obs[0] >= 1 && obs[0] <= V) || obs[0] != (double)(int)obs[0]) return fail(GSMC_E_BADARG, "HMM observation must be an integer in 1..%d", V);
@@ -1247,7 +1264,7 @@ static int run_steps_graph(gsmc_filter* f, const double* obs, size_t n_steps, si
   static int env_all = getenv("GSMC_GRAPH") ? 1 : 0;
   const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
   if (env_off || (!residual && !env_all) || f->graph_disabled || f->profiling || f->group || (f->nranks > 1 && xmode(f) != XMODE_LL) || n_steps < 2 ||
-      f->model == GSMC_MODEL_REGRESSION || (residual && f->nranks > 1)) return GSMC_OK;
+      model_obs_on_device(f->model) || (residual && f->nranks > 1)) return GSMC_OK;
   uint64_t key = 0xcbf29ce484222325ULL;
   const int64_t t0 = f->T;
   key = fnv1a(key, &t0, sizeof t0); key = fnv1a(key, &n_steps, sizeof n_steps); key = fnv1a(key, &n_obs, sizeof n_obs);
@@ -1320,7 +1337,7 @@ GSMC_API int gsmc_run_steps(gsmc_handle f, const double* obs, size_t n_steps, si
   {
     // validate the arguments of every step before anything is enqueued or captured
     ModelArgs a;
-    for (size_t s = 0; s < n_steps; ++s) if (f->model != GSMC_MODEL_REGRESSION) CKRC(fill_model_args(f, a, obs + s * n_obs, n_obs, prop, pp, npp));
+    for (size_t s = 0; s < n_steps; ++s) if (!model_obs_on_device(f->model)) CKRC(fill_model_args(f, a, obs + s * n_obs, n_obs, prop, pp, npp));
   }
   int used = 0;
   CKRC(run_steps_graph(f, obs, n_steps, n_obs, prop, pp, npp, ess_threshold, &used));

@@ -314,6 +314,10 @@ __device__ __forceinline__ LseTriple reduce_partials(const LseTriple* partials, 
   return tr;
 }
 
+// models that draw a run-time number of uniforms per particle declare `static constexpr bool CTX_UNIFORMS = true`
+template <class M, class = void> struct model_ctx_uniforms { static constexpr bool value = false; };
+template <class M> struct model_ctx_uniforms<M, decltype((void)M::CTX_UNIFORMS)> { static constexpr bool value = M::CTX_UNIFORMS; };
+
 template <class Model, typename Real, bool INIT, int PROP>
 __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
   typedef typename Vec2T<Real>::type Real2;
@@ -435,8 +439,20 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
   for (int u = 0; u < PAIRS; ++u) {
     const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
     double out0[D], out1[D];
-    const double w0 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u], zz[u], uu[u], out0);
-    const double w1 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u + 1], zz[u] + NZ, uu[u] + NU, out1);
+    double w0, w1;
+    if constexpr (model_ctx_uniforms<Model>::value) {
+      // run-time number of uniforms per particle: the model draws them itself from the same virtual array
+      const int nu_rt = (int)a.p[0];
+      DrawCtx c0, c1;
+      c0.seed = c1.seed = g.seed; c0.t = c1.t = g.t;
+      c0.global_index = g.first_global + (uint64_t)i; c1.global_index = c0.global_index + 1;
+      c0.urep = g.urep ? g.urep + i * nu_rt : nullptr; c1.urep = g.urep ? g.urep + (i + 1) * nu_rt : nullptr;
+      w0 = Model::template particle_ctx<INIT, PROP>(a, dyn_sm, prev[2 * u], zz[u], c0, out0);
+      w1 = Model::template particle_ctx<INIT, PROP>(a, dyn_sm, prev[2 * u + 1], zz[u] + NZ, c1, out1);
+    } else {
+      w0 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u], zz[u], uu[u], out0);
+      w1 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u + 1], zz[u] + NZ, uu[u] + NU, out1);
+    }
     const Real r0 = (Real)(INIT ? w0 : lwv[2 * u] + w0), r1 = (Real)(INIT ? w1 : lwv[2 * u + 1] + w1);
 #pragma unroll
     for (int d = 0; d < D; ++d) {

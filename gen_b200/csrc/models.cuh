@@ -53,6 +53,21 @@ GM_HD double logpdf_normal(double x, double mu, double std) {
   return -(diff * diff) / (2.0 * var) - 0.5 * gm_log(2.0 * GM_PI * var);
 }
 GM_HD double random_normal(double mu, double std, double z) { return mu + std * z; }   // normal.jl:96
+// bernoulli.jl:10-12,19: logpdf = x ? log(prob) : log(1. - prob); random = rand() < prob
+GM_HD double logpdf_bernoulli(bool x, double prob) { return x ? gm_log(prob) : gm_log(1. - prob); }
+GM_HD bool random_bernoulli(double prob, double u) { return u < prob; }
+// uniform_continuous.jl:12-14,21-23: logpdf = (x >= low && x <= high) ? -log(high-low) : -Inf; random = rand() * (high - low) + low
+GM_HD double logpdf_uniform(double x, double low, double high) { return (x >= low && x <= high) ? -gm_log(high - low) : -gm_inf(); }
+GM_HD double random_uniform(double low, double high, double u) { return u * (high - low) + low; }
+
+// What a model with a run-time number of uniform draws per particle needs to draw them itself: element
+// global_index * n + j of the step's virtual uniform array (same layout as the fixed-count path), or the replayed values.
+struct DrawCtx {
+  uint64_t seed;
+  uint64_t global_index;
+  uint32_t t;
+  const double* urep;       // this particle's replayed uniforms, or NULL
+};
 
 // ---------------------------------------------------------------------------------------------
 // LGSSM: x_init ~ normal(m0,s0); x ~ normal(x_prev*a + b, q); y ~ normal(c*x, r)
@@ -314,6 +329,93 @@ struct RegressionModel {
     const NormC nn = a.nc[0];
     for (int i = 0; i < n; ++i) mw += logpdf_normal_c(__ldg(ys + i), slope * __ldg(xs + i) + intercept, nn);
     out[0] = slope; out[1] = intercept;
+    return mw - pw;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Outlier regression, examples/regression/static_model.jl:3-23 (a static model over a Map of the static `datum`):
+//   log_inlier_std, log_outlier_std, slope, intercept ~ normal(0, sd); per datum z ~ bernoulli(prob),
+//   std = ifelse(z, inlier_std, outlier_std) [literally :6], y ~ normal(x * slope + intercept, std) (constrained).
+// p = [n, prob, sd, xs[n]]; obs = ys[n]. Latent columns: the four reals, then the flags packed 32 per column as exact
+// integers (GSMC_OUTLIER_ZWORDS columns: n <= 256). The n uniforms of a particle come through DrawCtx.
+// ---------------------------------------------------------------------------------------------
+#define GSMC_OUTLIER_ZWORDS 8
+struct OutlierRegressionModel {
+  static constexpr int D = 4 + GSMC_OUTLIER_ZWORDS;
+  static constexpr int SMEM_DOUBLES = 0;
+  static constexpr bool CTX_UNIFORMS = true;
+  __host__ __device__ static constexpr int nz(bool, int) { return 4; }
+  __host__ __device__ static constexpr int nu(bool, int) { return 0; }
+  static bool has_proposal(int prop) { return prop == 0; }
+  static void prepare(ModelArgs&, bool, int) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static double particle_ctx(const ModelArgs& a, const double*, const double*, const double* z,
+                                                        const DrawCtx& c, double* out) {
+    const int n = (int)a.p[0];
+    const double prob = a.p[1], sd = a.p[2];
+    const double* xs = a.p_dev + 3;
+    const double* ys = a.obs_dev;
+    const double inlier_log_std = random_normal(0.0, sd, z[0]);
+    const double outlier_log_std = random_normal(0.0, sd, z[1]);
+    const double inlier_std = gm_exp(inlier_log_std), outlier_std = gm_exp(outlier_log_std);
+    const double slope = random_normal(0.0, sd, z[2]);
+    const double intercept = random_normal(0.0, sd, z[3]);
+    double w = 0.0;
+    uint32_t words[GSMC_OUTLIER_ZWORDS];
+#pragma unroll
+    for (int k = 0; k < GSMC_OUTLIER_ZWORDS; ++k) words[k] = 0;
+    const uint64_t e0 = c.global_index * (uint64_t)n;
+    double ua = 0.0, ub = 0.0;
+    uint64_t have = ~(uint64_t)0;                        // Philox call whose two uniforms are in (ua, ub)
+    for (int i = 0; i < n; ++i) {
+      double u;
+      if (c.urep) u = c.urep[i];
+      else {
+        const uint64_t e = e0 + (uint64_t)i;
+        if ((e >> 1) != have) { have = e >> 1; uniform_pair(c.seed, have, c.t, GSMC_STREAM_UNIFORM, &ua, &ub); }
+        u = (e & 1) ? ub : ua;
+      }
+      const bool is_outlier = random_bernoulli(prob, u);
+      const double std = is_outlier ? inlier_std : outlier_std;
+      w += logpdf_normal(__ldg(ys + i), __ldg(xs + i) * slope + intercept, std);
+      // the flag goes into word i >> 5 without indexing the register array dynamically
+#pragma unroll
+      for (int k = 0; k < GSMC_OUTLIER_ZWORDS; ++k) if ((i >> 5) == k && is_outlier) words[k] |= 1u << (i & 31);
+    }
+    out[0] = inlier_log_std; out[1] = outlier_log_std; out[2] = slope; out[3] = intercept;
+#pragma unroll
+    for (int k = 0; k < GSMC_OUTLIER_ZWORDS; ++k) out[4 + k] = (double)words[k];
+    return w;
+  }
+};
+
+// uniform-normal: x ~ uniform(lo, hi); y ~ normal(x, sd_y). p = [lo, hi, sd_y]; obs = [y]; pp = [lo_q, hi_q]
+struct UniformNormalModel {
+  static constexpr int D = 1;
+  static constexpr int SMEM_DOUBLES = 0;
+  __host__ __device__ static constexpr int nz(bool, int) { return 0; }
+  __host__ __device__ static constexpr int nu(bool, int) { return 1; }
+  static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
+  static void prepare(ModelArgs& a, bool, int) { a.nc[0] = make_normc(a.p[2]); }
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
+  template <bool INIT, int PROP>
+  __device__ __forceinline__ static double particle(const ModelArgs& a, const double*, const double*,
+                                                    const double*, const double* u, double* out) {
+    double x, pw = 0.0, mw = 0.0;
+    if (PROP == 0) {
+      x = random_uniform(a.p[0], a.p[1], u[0]);
+    } else {
+      x = random_uniform(a.pp[0], a.pp[1], u[0]);
+      pw += logpdf_uniform(x, a.pp[0], a.pp[1]);
+      mw += logpdf_uniform(x, a.p[0], a.p[1]);
+    }
+    const NormC yn = a.nc[0];
+    mw += logpdf_normal_c(a.obs[0], x, yn);
+    out[0] = x;
     return mw - pw;
   }
 };

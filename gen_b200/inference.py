@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 from .choicemap import ChoiceMap, choicemap
-from .models import DeviceModel, DeviceProposal, LinearRegression
+from .models import DeviceModel, DeviceProposal, LinearRegression, OutlierRegression
 
 
 class ParticleFilterState:
@@ -218,6 +218,8 @@ class DeviceTrace:
 
     def get_choices(self):
         st, m = self._state, self._state.model
+        if isinstance(m, OutlierRegression):
+            return m.choices(self._traj[0], st.observations[0])
         cm = ChoiceMap()
         for t in range(1, self._traj.shape[0] + 1):
             for d, name in enumerate(m.state_names):
@@ -272,7 +274,7 @@ def _check_proposal(model, proposal):
 
 
 def _bind(model, model_args):
-    if isinstance(model, LinearRegression):
+    if isinstance(model, (LinearRegression, OutlierRegression)):
         if len(model_args) != 1:
             raise _lib.GsmcError(_lib.E_BADARG, "model_args must be (xs,)")
         return model.bind(model_args[0])
@@ -371,7 +373,7 @@ def importance_sampling(model, model_args, observations, *rest, **options):
     bound = _bind(model, model_args)
     if proposal is not None:
         proposal = DeviceProposal(bound, proposal.name, proposal.params)
-    if bound.family in (_lib.MODEL_REGRESSION, _lib.MODEL_NORMAL_NORMAL):
+    if bound.family in _lib.IS_FAMILIES:
         cfg = _lib.Config()
         cfg.struct_size = C.sizeof(_lib.Config)
         cfg.model_id = bound.family
@@ -455,7 +457,7 @@ def importance_resampling(model, model_args, observations, *rest, verbose=False,
     while done < num_samples:
         m = min(chunk, num_samples - done)
         # state-space families: the kept trace is a whole trajectory, so the chunk keeps its history
-        extra = {} if model.family in (_lib.MODEL_REGRESSION, _lib.MODEL_NORMAL_NORMAL) else {"keep_history": True, "history_capacity": int(model_args[0])}
+        extra = {} if model.family in _lib.IS_FAMILIES else {"keep_history": True, "history_capacity": int(model_args[0])}
         traces, _, lml_c = importance_sampling(model, model_args, observations, *head, m, seed=chunk_seed(seed, c), **extra, **options)
         state = traces._state
         lt_c = lml_c + math.log(m)

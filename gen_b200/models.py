@@ -203,3 +203,80 @@ class NormalNormal(DeviceModel):
 
     def latent_address(self, T, name):
         return name
+
+
+class OutlierRegression(DeviceModel):
+    """examples/regression/static_model.jl:3-23 (importance sampling; prior as proposal):
+
+        @gen (static) function datum(x, inlier_std, outlier_std, slope, intercept)
+            is_outlier = @trace(bernoulli(0.5), :z)
+            std = ifelse(is_outlier, inlier_std, outlier_std)
+            y = @trace(normal(x * slope + intercept, std), :y)
+        end
+        data = Map(datum)
+        @gen (static) function model(xs)
+            inlier_log_std = @trace(normal(0, 2), :log_inlier_std); outlier_log_std = @trace(normal(0, 2), :log_outlier_std)
+            slope = @trace(normal(0, 2), :slope); intercept = @trace(normal(0, 2), :intercept)
+            @trace(data(xs, fill(exp(inlier_log_std), n), ...), :data)
+        end
+
+    Observations constrain (:data, i, :y) for i = 1..n (n <= 256); the flags (:data, i, :z) are latent, stored bit-packed."""
+    family = _lib.MODEL_OUTLIER_REGRESSION
+    ZWORDS = 8
+    state_names = ("log_inlier_std", "log_outlier_std", "slope", "intercept") + tuple("z_word_%d" % k for k in range(8))
+
+    def __init__(self, prob_outlier=0.5, prior_sd=2.0):
+        self.prob, self.sd = float(prob_outlier), float(prior_sd)
+        self.xs = None
+
+    def bind(self, xs):
+        m = OutlierRegression(self.prob, self.sd)
+        m.xs = np.asarray(xs, dtype=np.float64)
+        return m
+
+    def params(self):
+        return np.concatenate([[self.xs.size, self.prob, self.sd], self.xs])
+
+    def latent_address(self, T, name):
+        return name
+
+    def extract_observations(self, T, observations):
+        n = self.xs.size
+        want = [("data", i + 1, "y") for i in range(n)]
+        extra = [k for k in observations.keys() if k not in want]
+        if extra:
+            raise _lib.GsmcError(_lib.E_BADARG, "constraints at addresses the model does not visit (or latent flags): %r" % (extra[:4],))
+        missing = [k for k in want if k not in observations]
+        if missing:
+            raise _lib.GsmcError(_lib.E_BADARG, "observations must constrain %r" % (missing[:4],))
+        return np.array([float(observations[k]) for k in want], dtype=np.float64)
+
+    def choices(self, latent_row, obs):
+        """Choice map of one trace from its latent row [4 reals + packed flag words] and the observations."""
+        from .choicemap import ChoiceMap
+        cm = ChoiceMap()
+        for d, name in enumerate(self.state_names[:4]):
+            cm[name] = float(latent_row[d])
+        for i in range(self.xs.size):
+            cm[("data", i + 1, "z")] = bool((int(latent_row[4 + (i >> 5)]) >> (i & 31)) & 1)
+            cm[("data", i + 1, "y")] = float(obs[i])
+        return cm
+
+
+class UniformNormal(DeviceModel):
+    """x ~ uniform(low, high); y ~ normal(x, sd_y) (uniform_continuous.jl:12-23 on the device path);
+    custom proposal x ~ uniform(low_q, high_q)."""
+    family = _lib.MODEL_UNIFORM_NORMAL
+    state_names = ("x",)
+
+    def __init__(self, low=0.0, high=1.0, sd_y=1.0):
+        self.p = np.array([low, high, sd_y], dtype=np.float64)
+
+    def params(self):
+        return self.p
+
+    def obs_address(self, T):
+        return "y"
+
+    def latent_address(self, T, name):
+        return name

@@ -40,7 +40,9 @@ enum {
   GSMC_MODEL_SV = 3,             /* stochastic volatility; SSM pattern of examples/pmmh/model.jl:40-50 */
   GSMC_MODEL_BEARINGS = 4,       /* bearings-only tracking; pattern of examples/planning/filtering.jl:79-91 */
   GSMC_MODEL_REGRESSION = 5,     /* examples/regression/quickstart.jl:3-9 (importance sampling) */
-  GSMC_MODEL_NORMAL_NORMAL = 6   /* test/inference/importance_sampling.jl:3-12 (importance sampling) */
+  GSMC_MODEL_NORMAL_NORMAL = 6,  /* test/inference/importance_sampling.jl:3-12 (importance sampling) */
+  GSMC_MODEL_OUTLIER_REGRESSION = 7, /* examples/regression/static_model.jl:3-23: bernoulli outlier flags, Map of a static kernel (importance sampling) */
+  GSMC_MODEL_UNIFORM_NORMAL = 8  /* x ~ uniform(low, high); y ~ normal(x, sd): uniform_continuous.jl:12-23 on the device (importance sampling) */
 };
 enum { GSMC_PROPOSAL_DEFAULT = 0, GSMC_PROPOSAL_CUSTOM = 1 };
 enum { GSMC_RESAMPLE_MULTINOMIAL = 0, GSMC_RESAMPLE_RESIDUAL = 1 };

@@ -380,6 +380,8 @@ static int family_dim(int family) {
     case ORC_HMM: case ORC_LGSSM: case ORC_SV: case ORC_NORMAL_NORMAL: return 1;
     case ORC_BEARINGS: return 4;
     case ORC_REGRESSION: return 2;
+    case ORC_OUTLIER_REGRESSION: return 4 + ORC_OUTLIER_ZWORDS;
+    case ORC_UNIFORM_NORMAL: return 1;
     default: return -1;
   }
 }
@@ -390,6 +392,8 @@ static int family_normals(int family, int proposal, int is_init) {
     case ORC_LGSSM: case ORC_SV: case ORC_NORMAL_NORMAL: return 1;
     case ORC_BEARINGS: return is_init ? 4 : 2;
     case ORC_REGRESSION: return 2;
+    case ORC_OUTLIER_REGRESSION: return 4;
+    case ORC_UNIFORM_NORMAL: return 0;
     default: return -1;
   }
 }
@@ -573,12 +577,58 @@ static double normal_normal_sample(const double* p, const double* obs, int propo
   return model_w - prop_w;
 }
 
+/* examples/regression/static_model.jl:3-23: a static model whose data points are a Map of the static `datum`:
+ *   inlier_log_std ~ normal(0, sd) :log_inlier_std; outlier_log_std ~ normal(0, sd) :log_outlier_std;
+ *   inlier_std = exp(inlier_log_std); outlier_std = exp(outlier_log_std); slope ~ normal(0, sd); intercept ~ normal(0, sd);
+ *   datum i (:data => i): is_outlier ~ bernoulli(prob) :z;  std = ifelse(is_outlier, inlier_std, outlier_std)  [literally :6];
+ *                         y ~ normal(x_i * slope + intercept, std) :y   (constrained)
+ * params = [n, prob, sd, xs[n]] (the reference: prob = 0.5, sd = 2). generate(): unconstrained choices are sampled in
+ * trace order (static_ir/generate.jl:36-42; Map visits the data points in order, map/generate.jl), the weight is the sum
+ * of the logpdfs of the constrained :y's. random(bernoulli, p) = rand() < p (bernoulli.jl:19).
+ * latents: [log_inlier_std, log_outlier_std, slope, intercept, z bits packed 32 per word as exact integers]. */
+static double outlier_regression_sample(const double* p, const double* ys, const double* z, const double* u, double* lat) {
+  const int n = (int)p[0];
+  const double prob = p[1], sd = p[2];
+  const double* xs = p + 3;
+  const double inlier_log_std = random_normal(0.0, sd, z[0]);
+  const double outlier_log_std = random_normal(0.0, sd, z[1]);
+  const double inlier_std = orc_exp(inlier_log_std), outlier_std = orc_exp(outlier_log_std);
+  const double slope = random_normal(0.0, sd, z[2]);
+  const double intercept = random_normal(0.0, sd, z[3]);
+  double w = 0.0;
+  uint32_t words[ORC_OUTLIER_ZWORDS] = {0};
+  for (int i = 0; i < n; ++i) {
+    const int is_outlier = u[i] < prob;                                        /* bernoulli.jl:19 */
+    const double std = is_outlier ? inlier_std : outlier_std;                  /* static_model.jl:6 */
+    w += orc_logpdf_normal(ys[i], xs[i] * slope + intercept, std);
+    if (is_outlier) words[i >> 5] |= 1u << (i & 31);
+  }
+  lat[0] = inlier_log_std; lat[1] = outlier_log_std; lat[2] = slope; lat[3] = intercept;
+  for (int k = 0; k < ORC_OUTLIER_ZWORDS; ++k) lat[4 + k] = (double)words[k];
+  return w;
+}
+/* x ~ uniform(lo, hi) (uniform_continuous.jl:12-23: random = rand() * (high - low) + low); y ~ normal(x, sd_y).
+ * params = [lo, hi, sd_y]; obs = [y]; custom proposal x ~ uniform(pp[0], pp[1]). */
+static double uniform_normal_sample(const double* p, const double* obs, int proposal, const double* pp, const double* u, double* lat) {
+  double x, prop_w = 0.0, model_w = 0.0;
+  if (proposal == ORC_PROPOSAL_DEFAULT) {
+    x = u[0] * (p[1] - p[0]) + p[0];
+  } else {
+    x = u[0] * (pp[1] - pp[0]) + pp[0];
+    prop_w += orc_logpdf_uniform(x, pp[0], pp[1]);
+    model_w += orc_logpdf_uniform(x, p[0], p[1]);
+  }
+  model_w += orc_logpdf_normal(obs[0], x, p[2]);
+  lat[0] = x;
+  return model_w - prop_w;
+}
+
 /* ------------------------------------------------------------------------- */
 /* particle filter                                                            */
 /* ------------------------------------------------------------------------- */
 orc_pf* orc_pf_create(int family, const double* params, int n_params, int64_t N, uint64_t seed, int keep_history, int nthreads) {
   int D = family_dim(family);
-  if (D < 0 || family == ORC_REGRESSION || family == ORC_NORMAL_NORMAL) { snprintf(g_err, sizeof g_err, "family %d is not a state-space family", family); return NULL; }
+  if (D < 0 || family == ORC_REGRESSION || family == ORC_NORMAL_NORMAL || family == ORC_OUTLIER_REGRESSION || family == ORC_UNIFORM_NORMAL) { snprintf(g_err, sizeof g_err, "family %d is not a state-space family", family); return NULL; }
   if (n_params > MAXP || N <= 0) { snprintf(g_err, sizeof g_err, "bad arguments"); return NULL; }
   orc_pf* pf = (orc_pf*)calloc(1, sizeof(orc_pf));
   pf->family = family; pf->n_params = n_params; memcpy(pf->params, params, sizeof(double) * n_params);
@@ -799,14 +849,18 @@ int orc_importance_sampling(int family, const double* params, int n_params, cons
                             const double* zrep, double* lat_out, double* lnw_out, double* lml_out, int nthreads) {
   (void)n_params; (void)npp;
   int D = family_dim(family);
-  if (family != ORC_REGRESSION && family != ORC_NORMAL_NORMAL) ORC_FAIL("family %d is not an importance-sampling family", family);
-  if (family == ORC_REGRESSION && n_obs != (int)params[0]) ORC_FAIL("need one observation per data point");
-  if (family == ORC_NORMAL_NORMAL && n_obs != 1) ORC_FAIL("need exactly one observation");
+  if (family != ORC_REGRESSION && family != ORC_NORMAL_NORMAL && family != ORC_OUTLIER_REGRESSION && family != ORC_UNIFORM_NORMAL)
+    ORC_FAIL("family %d is not an importance-sampling family", family);
+  if ((family == ORC_REGRESSION || family == ORC_OUTLIER_REGRESSION) && n_obs != (int)params[0]) ORC_FAIL("need one observation per data point");
+  if (family == ORC_OUTLIER_REGRESSION && ((int)params[0] < 1 || (int)params[0] > 32 * ORC_OUTLIER_ZWORDS)) ORC_FAIL("1 <= n <= %d data points", 32 * ORC_OUTLIER_ZWORDS);
+  if (family == ORC_OUTLIER_REGRESSION && proposal != ORC_PROPOSAL_DEFAULT) ORC_FAIL("the outlier model has no custom proposal in the catalogue");
+  if ((family == ORC_NORMAL_NORMAL || family == ORC_UNIFORM_NORMAL) && n_obs != 1) ORC_FAIL("need exactly one observation");
   if (proposal != ORC_PROPOSAL_DEFAULT && !pp) ORC_FAIL("custom proposal needs parameters");
   const int nz = family_normals(family, proposal, 1);
+  const int nu = family == ORC_OUTLIER_REGRESSION ? (int)params[0] : (family == ORC_UNIFORM_NORMAL ? 1 : 0);
   if (nthreads < 1) nthreads = 1;
   double* Z = (double*)zrep;
-  if (!zrep) {
+  if (!zrep && nz > 0) {
     Z = (double*)malloc(sizeof(double) * nz * n);
     #pragma omp parallel for num_threads(nthreads) schedule(static)
     for (int64_t blk = 0; blk < (nz * n + 4095) / 4096; ++blk) {
@@ -814,15 +868,23 @@ int orc_importance_sampling(int family, const double* params, int n_params, cons
       orc_fill_normals(seed, 1, f, c, Z + f);
     }
   }
+  double* U = NULL;
+  if (nu > 0) {                                            /* element i*nu + j of the step's virtual uniform array */
+    U = (double*)malloc(sizeof(double) * (size_t)nu * n);
+    orc_fill_uniforms(seed, 1, ORC_STREAM_UNIFORM, 0, (uint64_t)nu * n, U);
+  }
   double* lw = lnw_out;
   #pragma omp parallel for num_threads(nthreads) schedule(static)
   for (int64_t i = 0; i < n; ++i) {                       /* for i=1:num_samples  :25,41 */
-    double lat[4];
+    double lat[4 + ORC_OUTLIER_ZWORDS];
     if (family == ORC_REGRESSION) lw[i] = regression_sample(params, obs, proposal, pp, Z + (int64_t)nz * i, lat);
+    else if (family == ORC_OUTLIER_REGRESSION) lw[i] = outlier_regression_sample(params, obs, Z + (int64_t)nz * i, U + (int64_t)nu * i, lat);
+    else if (family == ORC_UNIFORM_NORMAL) lw[i] = uniform_normal_sample(params, obs, proposal, pp, U + i, lat);
     else lw[i] = normal_normal_sample(params, obs, proposal, pp, Z + (int64_t)nz * i, lat);
     for (int d = 0; d < D; ++d) lat_out[d * n + i] = lat[d];
   }
-  if (!zrep) free(Z);
+  if (!zrep && Z) free(Z);
+  free(U);
   double log_total = orc_logsumexp(lw, n);                /* :29,48 */
   *lml_out = log_total - orc_log((double)n);              /* :30,49 */
   for (int64_t i = 0; i < n; ++i) lnw_out[i] = lw[i] - log_total;   /* :31,50 */

@@ -41,7 +41,10 @@ extern "C" {
 #endif
 
 /* model families (same numbering as include/gen_b200.h) */
-enum { ORC_HMM = 1, ORC_LGSSM = 2, ORC_SV = 3, ORC_BEARINGS = 4, ORC_REGRESSION = 5, ORC_NORMAL_NORMAL = 6 };
+enum { ORC_HMM = 1, ORC_LGSSM = 2, ORC_SV = 3, ORC_BEARINGS = 4, ORC_REGRESSION = 5, ORC_NORMAL_NORMAL = 6,
+       ORC_OUTLIER_REGRESSION = 7,   /* examples/regression/static_model.jl:3-23 (bernoulli outlier flags, Map of `datum`) */
+       ORC_UNIFORM_NORMAL = 8 };     /* x ~ uniform(lo, hi); y ~ normal(x, sd): uniform_continuous.jl:12-23 on the path */
+#define ORC_OUTLIER_ZWORDS 8          /* outlier flags packed 32 per latent word: at most 256 data points */
 enum { ORC_PROPOSAL_DEFAULT = 0, ORC_PROPOSAL_CUSTOM = 1 };
 enum { ORC_RESAMPLE_MULTINOMIAL = 0, ORC_RESAMPLE_RESIDUAL = 1 };
 /* Philox stream ids (counter word 3) */

@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-HMM, LGSSM, SV, BEARINGS, REGRESSION, NORMAL_NORMAL = 1, 2, 3, 4, 5, 6
+HMM, LGSSM, SV, BEARINGS, REGRESSION, NORMAL_NORMAL, OUTLIER_REGRESSION, UNIFORM_NORMAL = 1, 2, 3, 4, 5, 6, 7, 8
 PROPOSAL_DEFAULT, PROPOSAL_CUSTOM = 0, 1
 MULTINOMIAL, RESIDUAL = 0, 1
 STREAM_NORMAL, STREAM_UNIFORM, STREAM_RESAMPLE, STREAM_SAMPLE = 0, 1, 2, 3
@@ -191,7 +191,7 @@ class Oracle:
     def importance_sampling(self, family, params, obs, num_samples, seed=0, proposal=PROPOSAL_DEFAULT,
                             prop_params=None, z_replay=None, num_threads=1):
         params, obs, pp, z = _d(params), _d(obs), _d(prop_params), _d(z_replay)
-        D = {REGRESSION: 2, NORMAL_NORMAL: 1}[family]
+        D = {REGRESSION: 2, NORMAL_NORMAL: 1, OUTLIER_REGRESSION: 12, UNIFORM_NORMAL: 1}[family]
         lat = np.empty((D, num_samples), dtype=np.float64)
         lnw = np.empty(num_samples, dtype=np.float64)
         lml = C.c_double()

@@ -688,3 +688,64 @@ def test_run_steps_graph_replay_is_bit_identical(gpu, orc, fam, prop, scheme):
     assert same_bits(st.log_weights(), pf.log_weights()) and st.stats()["graph_replays"] == graphs
     st.close()
     ref.close()
+
+
+def test_outlier_regression_bernoulli_on_device(gpu, orc):
+    """examples/regression/static_model.jl:3-23 (SURVEY cfg-2 secondary): bernoulli outlier flags (bernoulli.jl:10-12,19),
+    a Map of the static `datum` kernel, prior as proposal. Latents (incl. the bit-packed flags) bit-exact vs the oracle."""
+    g = gpu
+    n, ns = 200, 60000
+    xs = np.linspace(-5, 5, n)
+    rng = np.random.default_rng(1)
+    noise = np.where(rng.random(n) < 0.5, 0.5, 5.0) * rng.standard_normal(n)
+    ys = -xs + 2 + noise
+    model = g.OutlierRegression()
+    obs = g.choicemap(*[(("data", i + 1, "y"), float(y)) for i, y in enumerate(ys)])
+    traces, lnw, lml = g.importance_sampling(model, (xs,), obs, ns, seed=3)
+    lat, lnw_o, lml_o = orc.importance_sampling(O.OUTLIER_REGRESSION, np.concatenate([[n, 0.5, 2.0], xs]), ys, ns, seed=3)
+    assert same_bits(traces._state.state(), lat)
+    assert lml == pytest.approx(lml_o, rel=1e-12)
+    assert np.allclose(lnw, lnw_o, rtol=0, atol=1e-9) and abs(orc.logsumexp(lnw)) < 1e-10
+    # about half of the flags are set, and the trace exposes the reference's addresses
+    flags = lat[4:].astype(np.uint64)
+    frac = sum(int(bin(int(w)).count("1")) for w in flags[:, :500].reshape(-1)) / (500 * n)
+    assert 0.45 < frac < 0.55
+    best = int(np.argmax(lnw))
+    ch = traces[best].get_choices()
+    assert ch[("data", 7, "y")] == ys[6] and isinstance(ch[("data", 7, "z")], bool)
+    assert ch["slope"] == lat[2, best] and ch["log_inlier_std"] == lat[0, best]
+    assert abs(ch["slope"] + 1) < 1.0
+    with pytest.raises(g.GsmcError):                 # latent flags cannot be constrained through this path
+        g.importance_sampling(model, (xs,), g.choicemap((("data", 1, "z"), True)), 16)
+    traces._state.close()
+    # exported uniforms (replay): flags follow u < 0.5 exactly
+    st = g.ParticleFilterState(model.bind(xs), 64, seed=3)
+    u = np.random.default_rng(5).random((64, n))
+    st.set_replay(normals=np.zeros((64, 4)), uniforms=u)
+    st.init(ys)
+    packed = st.state()[4:].astype(np.uint64)
+    for i in (0, 31, 32, 199):
+        assert np.array_equal((packed[i >> 5] >> np.uint64(i & 31)) & np.uint64(1), (u[:, i] < 0.5).astype(np.uint64))
+    st.close()
+
+
+def test_uniform_continuous_on_device(gpu, orc):
+    """uniform_continuous.jl:12-23 on the device: sampler and logpdf (-Inf outside the support) inside an importance sampler."""
+    g = gpu
+    lo, hi, sd, y, ns = -1.0, 3.0, 0.7, 0.4, 200000
+    model = g.UniformNormal(lo, hi, sd)
+    obs = g.choicemap(("y", y))
+    traces, lnw, lml = g.importance_sampling(model, (), obs, ns, seed=1)
+    lat, lnw_o, lml_o = orc.importance_sampling(O.UNIFORM_NORMAL, [lo, hi, sd], [y], ns, seed=1)
+    assert same_bits(traces._state.state(), lat) and lml == pytest.approx(lml_o, rel=1e-12)
+    Phi = lambda v: 0.5 * (1 + math.erf(v / math.sqrt(2)))
+    assert lml == pytest.approx(math.log((Phi((hi - y) / sd) - Phi((lo - y) / sd)) / (hi - lo)), abs=0.01)
+    assert lat.min() >= lo and lat.max() <= hi
+    traces._state.close()
+    # a proposal wider than the prior: samples outside [lo, hi] get log weight -Inf (distributions.jl:215 edge case)
+    traces, lnw, lml2 = g.importance_sampling(model, (), obs, model.custom_proposal(-2.0, 2.0), (), ns, seed=1)
+    lat, lnw_o, lml2_o = orc.importance_sampling(O.UNIFORM_NORMAL, [lo, hi, sd], [y], ns, seed=1, proposal=1, prop_params=[-2.0, 2.0])
+    assert same_bits(traces._state.state(), lat) and lml2 == pytest.approx(lml2_o, rel=1e-12)
+    assert np.array_equal(np.isinf(lnw), np.isinf(lnw_o)) and np.isinf(lnw).sum() > ns // 5
+    assert np.array_equal(np.isinf(lnw), lat[0] < lo)
+    traces._state.close()

@@ -276,3 +276,30 @@ def test_golden_fixtures(orc):
                 assert list(got[key]) == val, (case["spec"], key)
             else:
                 assert got[key] == pytest.approx(val, rel=1e-13, abs=1e-13), (case["spec"], key)
+
+
+def test_bernoulli_uniform_families(orc):
+    """The two importance-sampling families that put bernoulli.jl:10-19 and uniform_continuous.jl:12-23 on the path."""
+    lo, hi, sd, y = -1.0, 3.0, 0.7, 0.4
+    lat, lnw, lml = orc.importance_sampling(O.UNIFORM_NORMAL, [lo, hi, sd], [y], 200000, seed=1)
+    Phi = lambda v: 0.5 * (1 + math.erf(v / math.sqrt(2)))
+    assert lml == pytest.approx(math.log((Phi((hi - y) / sd) - Phi((lo - y) / sd)) / (hi - lo)), abs=0.01)
+    u = orc.uniforms(1, 1, O.STREAM_UNIFORM, 0, 5)
+    assert np.array_equal(lat[0, :5], u * (hi - lo) + lo)                        # random = rand() * (high - low) + low
+    assert orc.L.orc_logpdf_uniform(3.5, lo, hi) == -math.inf and orc.L.orc_logpdf_uniform(3.0, lo, hi) == -math.log(4.0)
+    assert orc.L.orc_logpdf_bernoulli(1, 0.3) == math.log(0.3) and orc.L.orc_logpdf_bernoulli(0, 0.3) == math.log(1. - 0.3)
+    n, ns = 40, 3000
+    xs = np.linspace(-5, 5, n)
+    ys = -xs + 2 + 0.3 * np.sin(7 * xs)
+    lat, lnw, lml = orc.importance_sampling(O.OUTLIER_REGRESSION, np.concatenate([[n, 0.5, 2.0], xs]), ys, ns, seed=2)
+    assert abs(orc.logsumexp(lnw)) < 1e-12 and np.isfinite(lml)
+    z = orc.normals(2, 1, 0, 8)
+    assert np.array_equal(lat[:4, 0], 2.0 * z[:4]) and np.array_equal(lat[:4, 1], 2.0 * z[4:8])
+    u = orc.uniforms(2, 1, O.STREAM_UNIFORM, 0, 2 * n).reshape(2, n)
+    for s in range(2):
+        flags = [(int(lat[4 + (i >> 5), s]) >> (i & 31)) & 1 for i in range(n)]
+        assert flags == [int(v < 0.5) for v in u[s]]
+        # weight = sum of the constrained :y logpdfs with std = ifelse(z, inlier_std, outlier_std) (static_model.jl:6)
+        stds = np.where(np.array(flags) == 1, math.exp(lat[0, s]), math.exp(lat[1, s]))
+        w = sum(orc.L.orc_logpdf_normal(float(ys[i]), float(xs[i] * lat[2, s] + lat[3, s]), float(stds[i])) for i in range(n))
+        assert lnw[s] + (lml + math.log(ns)) == pytest.approx(w, rel=1e-9)
