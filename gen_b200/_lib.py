@@ -73,6 +73,7 @@ SIGNATURES = {
     "gsmc_get_log_weights": (C.c_int, [_H, _dp, C.c_size_t]),
     "gsmc_get_log_weights_device": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "gsmc_get_state": (C.c_int, [_H, C.c_int64, _dp, C.c_size_t]),
+    "gsmc_get_observation": (C.c_int, [_H, C.c_int64, _dp, C.c_size_t]),
     "gsmc_get_trajectories": (C.c_int, [_H, _ip, C.c_size_t, _dp, C.c_size_t]),
     "gsmc_get_ancestors": (C.c_int, [_H, _ip, C.c_size_t]),
     "gsmc_sample_unweighted": (C.c_int, [_H, C.c_uint64, _ip]),

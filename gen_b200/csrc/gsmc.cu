@@ -223,6 +223,9 @@ struct gsmc_filter {
   double fuse_thr = -1.0;
   bool use_nccl_scalars = false;  // GSMC_NCCL_SCALARS=1: exchange the per-step scalars with ncclAllGather instead
   size_t bytes_state = 0, bytes_anc = 0, bytes_lw = 0, bytes_cdf = 0;
+  // unobserved steps: sampled observation choices, Real[cap][n_pad], allocated by the first unobserved step
+  void* obs_slab = nullptr;
+  std::vector<char> unobserved;   // per time step (index t-1): 1 = the observation choice was sampled
   // replay staging
   double* d_zrep = nullptr; size_t zrep_n = 0, zrep_cap = 0;
   double* d_urep = nullptr; size_t urep_n = 0, urep_cap = 0;
@@ -416,6 +419,7 @@ static void free_buffers(gsmc_filter* f) {
   pool_free(f->device, f->partials, partials_bytes(f)); pool_free(f->device, f->ds, sizeof(DevScalars));
   pool_free(f->device, f->resampled, (size_t)f->flag_mod * sizeof(int));
   pinned_free(f->h_ds);
+  pool_free(f->device, f->obs_slab, (size_t)f->cap * f->n_pad * real_size(f)); f->obs_slab = nullptr;
   f->state_slab = nullptr; f->anc_slab = nullptr; f->lw = nullptr; f->cdf = nullptr; f->cc = nullptr;
   f->seg_a = f->seg_b = f->seg_e = f->tile_e = f->raw0 = f->raw1 = nullptr; f->gap = nullptr; f->win = nullptr; f->partials = nullptr; f->ds = nullptr; f->h_ds = nullptr;
   f->resampled = nullptr;
@@ -531,6 +535,14 @@ static int launch_propagate_r(gsmc_filter* f, ModelArgs& a, bool init, int prop,
 static int fill_model_args(gsmc_filter* f, ModelArgs& a, const double* obs, size_t n_obs, int prop, const double* pp, size_t npp) {
   memset(&a, 0, sizeof a);
   const int need = expected_obs(f);
+  static const double dummy_obs[1] = {1.0};
+  if (!obs && n_obs == 0) {
+    // Unobserved step (the reference samples the unconstrained observation choice, static_ir/generate.jl:36-42)
+    if (model_is_importance(f->model)) return fail(GSMC_E_BADARG, "importance sampling needs the observations");
+    if (prop != GSMC_PROPOSAL_DEFAULT) return fail(GSMC_E_BADARG, "the catalogue's custom proposals condition on the observation: an unobserved step takes the default proposal");
+    a.unobserved = 1;
+    obs = dummy_obs; n_obs = 1;
+  }
   if (!obs || (int)n_obs != need) return fail(GSMC_E_BADARG, "model %d needs %d observation value(s) per step, got %zu", f->model, need, n_obs);
   if (npp > 8) return fail(GSMC_E_BADARG, "at most 8 proposal parameters");
   if (prop != GSMC_PROPOSAL_DEFAULT && prop != GSMC_PROPOSAL_CUSTOM) return fail(GSMC_E_BADARG, "bad proposal id %d", prop);
@@ -555,10 +567,34 @@ static int fill_model_args(gsmc_filter* f, ModelArgs& a, const double* obs, size
     return fail(GSMC_E_BADARG, "normal-normal proposal params: [mu_q, sd_q]");
   if (f->model == GSMC_MODEL_UNIFORM_NORMAL && prop == GSMC_PROPOSAL_CUSTOM && (npp != 2 || !(pp[1] > pp[0])))
     return fail(GSMC_E_BADARG, "uniform-normal proposal params: [low_q, high_q] with high_q > low_q");
-  if (f->model == GSMC_MODEL_HMM) {
+  if (f->model == GSMC_MODEL_HMM && !a.unobserved) {
     const int V = (int)f->params[1];
     if (!(obs[0] >= 1 && obs[0] <= V) || obs[0] != (double)(int)obs[0]) return fail(GSMC_E_BADARG, "HMM observation must be an integer in 1..%d", V);
   }
+  return GSMC_OK;
+}
+
+// the sampled observation choice of the step that launch_propagate has just produced (column of step f->T + 1)
+template <typename Real>
+static int launch_sample_obs(gsmc_filter* f, const ModelArgs& a) {
+  const size_t rs = real_size(f);
+  if (!f->obs_slab) {
+    CK(pool_alloc(f->device, &f->obs_slab, (size_t)f->cap * f->n_pad * rs));
+    CK(cudaMemsetAsync(f->obs_slab, 0, (size_t)f->cap * f->n_pad * rs, f->stream));
+  }
+  const int64_t step = f->T + 1;
+  const Real* state = (const Real*)state_col(f, f->state_slab, step);
+  Real* col = (Real*)((char*)f->obs_slab + (size_t)((step - 1) % f->cap) * f->n_pad * rs);
+  const int grid = (int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK);
+  ProfScope ps(f, KC_OTHER);
+  switch (f->model) {
+    case GSMC_MODEL_HMM: sample_obs_kernel<HmmModel, Real><<<grid, GSMC_BLOCK, 0, f->stream>>>(a, state, col, f->n, f->n_pad, (uint64_t)f->first, f->cfg.seed, (uint32_t)step); break;
+    case GSMC_MODEL_LGSSM: sample_obs_kernel<LgssmModel, Real><<<grid, GSMC_BLOCK, 0, f->stream>>>(a, state, col, f->n, f->n_pad, (uint64_t)f->first, f->cfg.seed, (uint32_t)step); break;
+    case GSMC_MODEL_SV: sample_obs_kernel<SvModel, Real><<<grid, GSMC_BLOCK, 0, f->stream>>>(a, state, col, f->n, f->n_pad, (uint64_t)f->first, f->cfg.seed, (uint32_t)step); break;
+    case GSMC_MODEL_BEARINGS: sample_obs_kernel<BearingsModel, Real><<<grid, GSMC_BLOCK, 0, f->stream>>>(a, state, col, f->n, f->n_pad, (uint64_t)f->first, f->cfg.seed, (uint32_t)step); break;
+    default: return fail(GSMC_E_UNSUPPORTED, "model %d has no sampler for its observation choice", f->model);
+  }
+  CK(cudaGetLastError());
   return GSMC_OK;
 }
 
@@ -568,6 +604,11 @@ static int launch_propagate(gsmc_filter* f, bool init, const double* obs, size_t
   if (f->cfg.keep_history && f->T + 1 > f->cap) return fail(GSMC_E_BADARG, "history_capacity (%lld steps) exceeded", (long long)f->cap);
   int rc = f->f32 ? launch_propagate_r<float>(f, a, init, prop, use_anc) : launch_propagate_r<double>(f, a, init, prop, use_anc);
   f->zrep_n = 0; f->urep_n = 0;
+  if (rc == GSMC_OK) {
+    if ((int64_t)f->unobserved.size() < f->T + 1) f->unobserved.resize(f->T + 1, 0);
+    f->unobserved[f->T] = (char)a.unobserved;
+    if (a.unobserved) rc = f->f32 ? launch_sample_obs<float>(f, a) : launch_sample_obs<double>(f, a);
+  }
   return rc;
 }
 
@@ -848,6 +889,7 @@ GSMC_API int gsmc_reset(gsmc_handle f) {
   CK(cudaSetDevice(f->device));
   f->T = 0; f->decided_since_step = false; f->pending = false; f->stats_fresh = false;
   f->last_resample_step = 0; f->n_sample_calls = 0; f->zrep_n = 0; f->urep_n = 0;
+  f->unobserved.clear();
   CKRC(peer_barrier(f));
   if (f->ds) {
     CK(cudaMemsetAsync(f->ds, 0, offsetof(DevScalars, xseq), f->stream));   // the exchange sequence number and the mailboxes keep their tags
@@ -1068,6 +1110,33 @@ GSMC_API int gsmc_get_state(gsmc_handle f, int64_t t, double* host_dst, size_t n
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(host_dst, f->d_f64, n_values * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CK(cudaStreamSynchronize(f->stream));
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_get_observation(gsmc_handle f, int64_t t, double* host_dst, size_t n) {
+  if (!f || !host_dst) return fail(GSMC_E_BADARG, "null argument");
+  if (f->T < 1) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (t == 0) t = f->T;
+  if (t < 1 || t > f->T) return fail(GSMC_E_BADARG, "time step %lld out of range 1..%lld", (long long)t, (long long)f->T);
+  if ((int64_t)f->unobserved.size() < t || !f->unobserved[t - 1] || !f->obs_slab)
+    return fail(GSMC_E_BADARG, "time step %lld was observed: its observation is the constraint the caller passed", (long long)t);
+  if (t != f->T && !f->cfg.keep_history) return fail(GSMC_E_BADARG, "earlier time steps need keep_history=1");
+  if (f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "sampled observation choices are read back on unsharded filters only");
+  if (n != (size_t)f->n) return fail(GSMC_E_BADARG, "expected a buffer of %lld values", (long long)f->n);
+  CK(cudaSetDevice(f->device));
+  CKRC(ensure_f64(f, n));
+  const int grid = (int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK);
+  {
+    // the ancestor walk of get_state over the one-column observation slab
+    ProfScope ps(f, KC_OTHER);
+    if (f->f32) { HistView<float> h = make_hist_view<float>(f); h.slab[0] = (const float*)f->obs_slab; h.D = 1;
+                  get_state_kernel<float><<<grid, GSMC_BLOCK, 0, f->stream>>>(h, f->rank, f->n, t, f->T, f->pending ? 1 : 0, f->d_f64); }
+    else { HistView<double> h = make_hist_view<double>(f); h.slab[0] = (const double*)f->obs_slab; h.D = 1;
+           get_state_kernel<double><<<grid, GSMC_BLOCK, 0, f->stream>>>(h, f->rank, f->n, t, f->T, f->pending ? 1 : 0, f->d_f64); }
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host_dst, f->d_f64, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   CK(cudaStreamSynchronize(f->stream));
   return GSMC_OK;
 }
@@ -1497,6 +1566,7 @@ static int read_dev(FILE* fp, gsmc_filter* f, void* dev, size_t bytes, std::vect
 GSMC_API int gsmc_save(gsmc_handle f, const char* path) {
   if (!f || !path) return fail(GSMC_E_BADARG, "null argument");
   if (f->T < 1 || !f->state_slab) return fail(GSMC_E_BADARG, "filter is not initialised");
+  if (f->obs_slab) return fail(GSMC_E_UNSUPPORTED, "checkpoints of filters with unobserved steps (sampled observation choices) are not supported");
   CK(cudaSetDevice(f->device));
   CK(cudaStreamSynchronize(f->stream));
   FILE* fp = fopen(path, "wb");

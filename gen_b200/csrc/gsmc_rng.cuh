@@ -14,6 +14,7 @@
 //   uniforms (stream 1,3): element e -> call e>>1; (e odd ? b : a)>>11 * 2^-53   in [0,1)
 //   resampling draws (stream 2): output slot k -> call k>>2, 32-bit word k&3 (out0..out3); u = (w+.5)2^-32 places
 //                        the draw inside its group's interval (see "grouped order statistics" below)
+//   observation choices of unobserved steps (stream 5): particle i -> element i (a normal, or a uniform for discrete emissions)
 //   group gaps (stream 4): Marsaglia-Tsang Gamma variate of group j, attempt a: normal = cos branch of call
 //                        (j<<5 | 2a), uniform = ((word a of call (j<<5 | 2a+1)) >> 11 + .5) 2^-53
 // Particle i's j-th normal at a step that needs nz normals per particle is element i*nz + j.
@@ -23,7 +24,7 @@
 #include <stdint.h>
 #include "gsmc_math.h"
 
-enum { GSMC_STREAM_NORMAL = 0, GSMC_STREAM_UNIFORM = 1, GSMC_STREAM_RESAMPLE = 2, GSMC_STREAM_SAMPLE = 3, GSMC_STREAM_GAP = 4 };
+enum { GSMC_STREAM_NORMAL = 0, GSMC_STREAM_UNIFORM = 1, GSMC_STREAM_RESAMPLE = 2, GSMC_STREAM_SAMPLE = 3, GSMC_STREAM_GAP = 4, GSMC_STREAM_OBS = 5 };
 
 struct PhiloxOut { uint64_t a, b; };
 
@@ -69,8 +70,9 @@ __device__ __forceinline__ PhiloxOut philox_call(const PhiloxKeys& K, uint64_t c
 }
 
 // two standard normals from one call
-__host__ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t call, uint32_t t, const double* ltab, double* z0, double* z1) {
-  const PhiloxOut o = philox_call(seed, call, t, GSMC_STREAM_NORMAL);
+__host__ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t call, uint32_t t, const double* ltab, double* z0, double* z1,
+                                                      uint32_t stream = GSMC_STREAM_NORMAL) {
+  const PhiloxOut o = philox_call(seed, call, t, stream);
   const double u1 = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
   const double u2 = (double)(o.b >> 11) * 0x1p-53;
   const double r = sqrt(-2.0 * gm_log_unit(u1, ltab));   // u1 in (0,1): log <= 0

@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
       w0 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u], zz[u], uu[u], out0);
       w1 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u + 1], zz[u] + NZ, uu[u] + NU, out1);
     }
+    if (a.unobserved) { w0 = 0.0; w1 = 0.0; }     // no constrained choice at this step (static_ir/generate.jl:36-42)
     const Real r0 = (Real)(INIT ? w0 : lwv[2 * u] + w0), r1 = (Real)(INIT ? w1 : lwv[2 * u + 1] + w1);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -549,6 +550,31 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
       }
     }
   }
+}
+
+// Unobserved step: the observation choice is sampled from the model given the particle's NEW latent
+// (static_ir/generate.jl:36-42: an unconstrained choice is random(dist, args...), weight unchanged). One draw per
+// particle from Philox stream GSMC_STREAM_OBS (element = global particle index). A rare path: one thread per particle.
+template <class Model, typename Real>
+__global__ void __launch_bounds__(GSMC_BLOCK) sample_obs_kernel(const ModelArgs a, const Real* state, Real* obs_col, int64_t n, int64_t stride,
+                                                                uint64_t first_global, uint64_t seed, uint32_t t) {
+  const int64_t i = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  double lat[Model::D];
+#pragma unroll
+  for (int d = 0; d < Model::D; ++d) lat[d] = (double)state[d * stride + i];
+  const uint64_t e = first_global + (uint64_t)i;
+  double draw;
+  if (Model::OBS_DRAW_UNIFORM) {
+    double u0, u1;
+    uniform_pair(seed, e >> 1, t, GSMC_STREAM_OBS, &u0, &u1);
+    draw = (e & 1) ? u1 : u0;
+  } else {
+    double z0, z1;
+    normal_pair(seed, e >> 1, t, gm_logtab64_g, &z0, &z1, GSMC_STREAM_OBS);
+    draw = (e & 1) ? z1 : z0;
+  }
+  obs_col[i] = (Real)Model::sample_obs(a, lat, draw);
 }
 
 // ------------------------------------------------------------------------------------------------

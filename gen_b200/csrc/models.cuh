@@ -29,6 +29,7 @@ struct ModelArgs {
   const double* p_dev;
   const double* obs_dev;
   int n_p, n_obs;
+  int unobserved;                     // this step has no constraint: the weight increment is 0 (the observation choice is sampled)
 };
 
 // normal.jl:56-60 with var = std*std hoisted:  -(diff*diff)/(2.0*var) - 0.5*log(2.0*pi*var)
@@ -94,6 +95,9 @@ struct LgssmModel {
       a.k[9] = sd * sd; a.k[10] = r * r;
     }
   }
+  // the observation choice of an unobserved step: y ~ normal(c*x, r)
+  static constexpr bool OBS_DRAW_UNIFORM = false;
+  __device__ __forceinline__ static double sample_obs(const ModelArgs& a, const double* lat, double z) { return random_normal(a.p[5] * lat[0], a.p[6], z); }
   template <bool INIT, int PROP>
   __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
   template <bool INIT, int PROP>
@@ -137,6 +141,8 @@ struct SvModel {
     const double phi = a.p[1], sigma = a.p[2];
     a.k[0] = init ? sigma / sqrt(1.0 - phi * phi) : sigma;
   }
+  static constexpr bool OBS_DRAW_UNIFORM = false;       // y ~ normal(0, exp(h/2))
+  __device__ __forceinline__ static double sample_obs(const ModelArgs&, const double* lat, double z) { return random_normal(0.0, gm_exp(lat[0] / 2.0), z); }
   template <bool INIT, int PROP>
   __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
   template <bool INIT, int PROP>
@@ -166,6 +172,8 @@ struct BearingsModel {
     a.nc[0] = make_normc(st); a.nc[1] = make_normc(sw);
     a.k[4] = sw * sw; a.k[5] = st * st;
   }
+  static constexpr bool OBS_DRAW_UNIFORM = false;       // bearing ~ normal(atan(y, x), sigma_theta)
+  __device__ __forceinline__ static double sample_obs(const ModelArgs& a, const double* lat, double z) { return random_normal(gm_atan2(lat[2], lat[0]), a.p[9], z); }
   template <bool INIT, int PROP>
   __device__ __forceinline__ static void prologue(const ModelArgs&, double*) {}
   template <bool INIT, int PROP>
@@ -232,6 +240,16 @@ struct HmmModel {
   __host__ __device__ static constexpr int nu(bool, int) { return 1; }
   static bool has_proposal(int prop) { return prop == 0 || prop == 1; }
   static void prepare(ModelArgs&, bool, int) {}
+  static constexpr bool OBS_DRAW_UNIFORM = true;        // x ~ categorical(emission_dists[:, z]): linear scan with one uniform
+  __device__ __forceinline__ static double sample_obs(const ModelArgs& a, const double* lat, double u) {
+    const double* p = a.p_dev;
+    const int K = (int)p[0], V = (int)p[1];
+    const double* e = p + 2 + K + K * K + ((int)lat[0] - 1) * V;
+    double cp = e[0];
+    int i = 1;
+    while (cp <= u && i < V) { cp += e[i]; i += 1; }
+    return (double)i;
+  }
   template <bool INIT, int PROP>
   __device__ __forceinline__ static void prologue(const ModelArgs& a, double* sm) {
     const double* p = a.p_dev;

@@ -89,6 +89,15 @@ class ParticleFilterState:
     def _propagate(self, fn, obs, proposal):
         # per-step hot path of the host loop: short observation vectors go through a preallocated ctypes buffer
         # (no numpy array + pointer cast per call); the library copies what it needs before returning
+        if obs is None:                      # unobserved step: the observation choice is sampled on the device
+            if proposal is not None:
+                raise _lib.GsmcError(_lib.E_BADARG, "an unobserved step takes the default proposal")
+            rc = fn(self.handle, None, 0, _lib.PROPOSAL_DEFAULT, None, 0)
+            if rc:
+                _lib.check(rc, self.handle)
+            self.T += 1
+            self.observations.append(None)
+            return
         n = len(obs)
         if n <= 16:
             buf = self.__dict__.get("_obs_buf")
@@ -160,6 +169,12 @@ class ParticleFilterState:
         _lib.check(self.lib.gsmc_get_state(self.handle, int(t), _lib.dptr(out), out.size), self.handle)
         return out
 
+    def sampled_observation(self, t=0):
+        """Observation choices the device sampled at UNOBSERVED step t (1-based; 0 = current), current particle order."""
+        out = np.empty(self.num_local, dtype=np.float64)
+        _lib.check(self.lib.gsmc_get_observation(self.handle, int(t), _lib.dptr(out), out.size), self.handle)
+        return out
+
     def trajectories(self, idx, local=False):
         """Trajectories of particles given by GLOBAL index (local=True: indices into this rank's shard)."""
         idx = np.ascontiguousarray(idx, dtype=np.int64)
@@ -227,7 +242,15 @@ class DeviceTrace:
                 cm[m.latent_address(t, name)] = int(v) if m.family == _lib.MODEL_HMM else float(v)
             if t - 1 < len(st.observations):
                 obs = st.observations[t - 1]
-                if isinstance(m, LinearRegression):
+                if obs is None:              # unobserved step: the choice this particle's trace sampled
+                    key = (st.T, t)
+                    cache = st.__dict__.setdefault("_sampled_obs_cache", {})
+                    if key not in cache:
+                        cache.clear()
+                        cache[key] = st.sampled_observation(t)
+                    v = cache[key][self.index]
+                    cm[m.obs_address(t)] = int(v) if m.family == _lib.MODEL_HMM else float(v)
+                elif isinstance(m, LinearRegression):
                     for i, y in enumerate(obs):
                         cm["y-%d" % (i + 1)] = float(y)
                 else:

@@ -43,11 +43,13 @@ class DeviceModel:
         """Observation vector of time step T out of a ChoiceMap; like the reference, constraints at
         addresses the model does not visit are an error (src/dynamic/update.jl:191-193)."""
         addr = self.obs_address(T)
-        if addr not in observations:
-            raise _lib.GsmcError(_lib.E_BADARG, "observations must constrain %r" % (addr,))
         extra = [k for k in observations.keys() if k != addr]
         if extra:
             raise _lib.GsmcError(_lib.E_BADARG, "constraints at addresses the model does not visit at this step: %r" % (extra,))
+        if addr not in observations:
+            # an empty choice map: nothing is constrained at this step, the reference samples the observation choice
+            # (static_ir/generate.jl:36-42) and the weight does not change
+            return None
         return np.array([float(observations[addr])], dtype=np.float64)
 
     def custom_proposal(self, *params):

@@ -166,6 +166,12 @@ GSMC_API int gsmc_get_log_weights_device(gsmc_handle h, void** dev_ptr);
  * latent of time step t (1-based; 0 = current) for this rank's particles in their current
  * order, column-major [D][n_local], f64. t < current needs keep_history (walks ancestors). */
 GSMC_API int gsmc_get_state(gsmc_handle h, int64_t t, double* host_dst, size_t n_values);
+/* An UNOBSERVED step: gsmc_init / gsmc_step with obs == NULL and n_obs == 0 (default proposal only). As the reference
+ * does for an unconstrained choice (src/static_ir/generate.jl:36-42, src/modeling_library/unfold/update.jl:54-78), the
+ * latent is sampled as usual, the observation choice is sampled from the model given the new latent, and the weight is
+ * unchanged. gsmc_get_observation returns the sampled observation choice of unobserved step t (1-based; 0 = current)
+ * for this handle's particles in their current order (walks ancestors like gsmc_get_state); it fails for observed steps. */
+GSMC_API int gsmc_get_observation(gsmc_handle h, int64_t t, double* host_dst, size_t n);
 /* full trajectories of selected particles: out[s][t][d], t = 1..num_steps. idx holds GLOBAL particle indices
  * (= local indices on an unsharded filter). Rows owned by other ranks of a sharded filter are read through the
  * NVLink peer mappings; a call that asks for such rows is collective (every rank passes the same indices). */

@@ -367,6 +367,7 @@ struct orc_pf {
   double* cur;          /* D x N column-major current latent */
   double* nxt;
   double** hist;        /* hist[t-1] = D x N, physically permuted at every resample */
+  double** obs_hist;    /* obs_hist[t-1] = N sampled observation choices of an UNOBSERVED step (NULL if it was observed); permuted alike */
   int64_t hist_cap;
   double* lw;
   double log_ml_est;
@@ -642,17 +643,35 @@ orc_pf* orc_pf_create(int family, const double* params, int n_params, int64_t N,
 void orc_pf_destroy(orc_pf* pf) {
   if (!pf) return;
   for (int64_t t = 0; t < pf->T && pf->hist; ++t) free(pf->hist[t]);
+  for (int64_t t = 0; t < pf->T && pf->obs_hist; ++t) free(pf->obs_hist[t]);
+  free(pf->obs_hist);
   free(pf->hist); free(pf->cur); free(pf->nxt); free(pf->lw); free(pf->parents); free(pf);
 }
-static void push_history(orc_pf* pf) {
-  if (!pf->keep_history) return;
+static void push_history(orc_pf* pf, double* sampled_obs) {
+  if (!pf->keep_history) { free(sampled_obs); return; }
   if (pf->T > pf->hist_cap) {
     pf->hist_cap = pf->hist_cap ? pf->hist_cap * 2 : 16;
     if (pf->hist_cap < pf->T) pf->hist_cap = pf->T;
     pf->hist = (double**)realloc(pf->hist, sizeof(double*) * pf->hist_cap);
+    pf->obs_hist = (double**)realloc(pf->obs_hist, sizeof(double*) * pf->hist_cap);
   }
   pf->hist[pf->T - 1] = (double*)malloc(sizeof(double) * pf->D * pf->N);
   memcpy(pf->hist[pf->T - 1], pf->cur, sizeof(double) * pf->D * pf->N);
+  pf->obs_hist[pf->T - 1] = sampled_obs;
+}
+/* The observation choice of an UNOBSERVED step: static_ir/generate.jl:36-42 / dynamic/generate.jl:26-33 sample an
+ * unconstrained choice with random(dist, args...) and add nothing to the weight. One draw per particle from Philox
+ * stream ORC_STREAM_OBS of the step (element = particle index): a normal for the continuous families, a uniform for the
+ * HMM's categorical emission. lat = the particle's NEW latent (D values, stride N). */
+static double sample_observation(const orc_pf* pf, const double* lat, int64_t stride, double draw) {
+  const double* p = pf->params;
+  switch (pf->family) {
+    case ORC_LGSSM: return random_normal(p[5] * lat[0], p[6], draw);                       /* y ~ normal(c*x, r) */
+    case ORC_SV: return random_normal(0.0, orc_exp(lat[0] / 2.0), draw);                    /* y ~ normal(0, exp(h/2)) */
+    case ORC_BEARINGS: return random_normal(orc_atan2(lat[2 * stride], lat[0]), p[9], draw);  /* bearing ~ normal(atan(y, x), sigma_theta) */
+    case ORC_HMM: { hmm_t h = hmm_view(p); return (double)random_categorical(h.emis + ((int64_t)lat[0] - 1) * h.V, h.V, draw); }
+  }
+  return 0.0;
 }
 
 /* one pass of `for i=1:num_particles` for init (particle_filter.jl:84-88,103-105) or
@@ -661,7 +680,13 @@ static int propagate(orc_pf* pf, int is_init, const double* obs, int n_obs, int 
                      const double* zrep, const double* urep) {
   const int64_t N = pf->N; const int D = pf->D;
   const int nz = family_normals(pf->family, proposal, is_init), nu = family_uniforms(pf->family, proposal, is_init);
-  if (n_obs < 1 || !obs) ORC_FAIL("an observation is required at every step");
+  const int unobserved = (n_obs < 1 || !obs);
+  const double dummy_obs[1] = {1.0};
+  if (unobserved) {
+    /* no constraint at this step: the latent is sampled as usual, the observation choice is sampled too, weight += 0 */
+    if (proposal != ORC_PROPOSAL_DEFAULT) ORC_FAIL("the catalogue's custom proposals condition on the observation");
+    obs = dummy_obs;
+  }
   if (proposal != ORC_PROPOSAL_DEFAULT && pf->family == ORC_SV) ORC_FAIL("no custom proposal for this family");
   const uint32_t t = (uint32_t)(pf->T + 1);
   double* Z = NULL; double* U = NULL;
@@ -703,15 +728,27 @@ static int propagate(orc_pf* pf, int is_init, const double* obs, int n_obs, int 
         for (int d = 0; d < 4; ++d) pf->nxt[d * N + i] = so[d];
       } break;
     }
+    if (unobserved) w = 0.0;               /* generate/update weight = sum over CONSTRAINED choices: none */
     if (is_init) pf->lw[i] = w;            /* particle_filter.jl:87,104 */
     else pf->lw[i] += w;                   /* :145,171 */
   }
   (void)D;
   if (nz && !zrep) free(Z);
   if (nu && !urep) free(U);
+  double* sampled = NULL;
+  if (unobserved) {
+    sampled = (double*)malloc(sizeof(double) * N);
+    for (int64_t i = 0; i < N; ++i) {
+      uint64_t a, b; double z0, z1, draw;
+      philox_pair(pf->seed, (uint64_t)i >> 1, t, ORC_STREAM_OBS, &a, &b);
+      if (pf->family == ORC_HMM) draw = (double)(((i & 1) ? b : a) >> 11) * 0x1p-53;
+      else { box_muller(a, b, &z0, &z1); draw = (i & 1) ? z1 : z0; }
+      sampled[i] = sample_observation(pf, pf->nxt + i, N, draw);
+    }
+  }
   double* tmp = pf->cur; pf->cur = pf->nxt; pf->nxt = tmp;   /* swap references, :148-151,174-177 */
   pf->T += 1;
-  push_history(pf);
+  push_history(pf, sampled);
   return 0;
 }
 
@@ -796,6 +833,13 @@ int orc_pf_maybe_resample(orc_pf* pf, double ess_threshold, int scheme, const do
         for (int64_t i = 0; i < N; ++i) tmp[d * N + i] = h[d * N + anc[i]];
       memcpy(h, tmp, sizeof(double) * D * N);
       free(tmp);
+      double* o = pf->obs_hist[t];
+      if (o) {
+        double* tmo = (double*)malloc(sizeof(double) * N);
+        for (int64_t i = 0; i < N; ++i) tmo[i] = o[anc[i]];
+        memcpy(o, tmo, sizeof(double) * N);
+        free(tmo);
+      }
     }
   }
   for (int64_t i = 0; i < N; ++i) pf->lw[i] = 0.;
@@ -817,6 +861,15 @@ int orc_pf_history(const orc_pf* pf, int64_t t, double* out) {
   if (!pf->keep_history) ORC_FAIL("history not kept");
   if (t < 1 || t > pf->T) ORC_FAIL("t out of range");
   memcpy(out, pf->hist[t - 1], sizeof(double) * pf->D * pf->N);
+  return 0;
+}
+
+/* sampled observation choices of unobserved step t (in the particles' current order); fails if step t was observed */
+int orc_pf_sampled_observation(const orc_pf* pf, int64_t t, double* out) {
+  if (!pf->keep_history) ORC_FAIL("history not kept");
+  if (t < 1 || t > pf->T) ORC_FAIL("t out of range");
+  if (!pf->obs_hist[t - 1]) ORC_FAIL("step %lld was observed", (long long)t);
+  memcpy(out, pf->obs_hist[t - 1], sizeof(double) * pf->N);
   return 0;
 }
 

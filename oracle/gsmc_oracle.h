@@ -48,7 +48,7 @@ enum { ORC_HMM = 1, ORC_LGSSM = 2, ORC_SV = 3, ORC_BEARINGS = 4, ORC_REGRESSION 
 enum { ORC_PROPOSAL_DEFAULT = 0, ORC_PROPOSAL_CUSTOM = 1 };
 enum { ORC_RESAMPLE_MULTINOMIAL = 0, ORC_RESAMPLE_RESIDUAL = 1 };
 /* Philox stream ids (counter word 3) */
-enum { ORC_STREAM_NORMAL = 0, ORC_STREAM_UNIFORM = 1, ORC_STREAM_RESAMPLE = 2, ORC_STREAM_SAMPLE = 3, ORC_STREAM_GAP = 4 };
+enum { ORC_STREAM_NORMAL = 0, ORC_STREAM_UNIFORM = 1, ORC_STREAM_RESAMPLE = 2, ORC_STREAM_SAMPLE = 3, ORC_STREAM_GAP = 4, ORC_STREAM_OBS = 5 };
 
 typedef struct orc_pf orc_pf;
 
@@ -96,6 +96,8 @@ orc_pf* orc_pf_create(int family, const double* params, int n_params, int64_t nu
                       uint64_t seed, int keep_history, int num_threads);
 void orc_pf_destroy(orc_pf* pf);
 int orc_pf_state_dim(const orc_pf* pf);
+/* init/step with obs == NULL (n_obs == 0): an UNOBSERVED step -- the observation choice is sampled, the weight is unchanged */
+int orc_pf_sampled_observation(const orc_pf* pf, int64_t t, double* out);
 int orc_pf_num_normals(const orc_pf* pf, int proposal, int is_init);
 int orc_pf_num_uniforms(const orc_pf* pf, int proposal, int is_init);
 /* initialize_particle_filter. obs: family-specific observation vector (may be NULL = no constraint).

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HMM, LGSSM, SV, BEARINGS, REGRESSION, NORMAL_NORMAL, OUTLIER_REGRESSION, UNIFORM_NORMAL = 1, 2, 3, 4, 5, 6, 7, 8
 PROPOSAL_DEFAULT, PROPOSAL_CUSTOM = 0, 1
 MULTINOMIAL, RESIDUAL = 0, 1
-STREAM_NORMAL, STREAM_UNIFORM, STREAM_RESAMPLE, STREAM_SAMPLE = 0, 1, 2, 3
+STREAM_NORMAL, STREAM_UNIFORM, STREAM_RESAMPLE, STREAM_SAMPLE, STREAM_GAP, STREAM_OBS = 0, 1, 2, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int64)
@@ -109,6 +109,7 @@ class Oracle:
         L.orc_pf_state.restype = _dp
         L.orc_pf_state.argtypes = [C.c_void_p]
         L.orc_pf_history.argtypes = [C.c_void_p, C.c_int64, _dp]
+        L.orc_pf_sampled_observation.argtypes = [C.c_void_p, C.c_int64, _dp]
         L.orc_pf_num_steps.restype = C.c_int64
         L.orc_pf_num_steps.argtypes = [C.c_void_p]
         L.orc_pf_sample_unweighted.argtypes = [C.c_void_p, C.c_int64, _dp, _ip]
@@ -224,8 +225,12 @@ class OraclePF:
             self.h = None
 
     def _prop(self, fn, obs, proposal, z, u):
-        obs, z, u = _d(np.atleast_1d(obs)), _d(z), _d(u)
-        rc = fn(self.h, _ptr(obs), obs.size, proposal, None, 0, _ptr(z), _ptr(u))
+        z, u = _d(z), _d(u)
+        if obs is None:                       # unobserved step: the observation choice is sampled, weight += 0
+            rc = fn(self.h, None, 0, proposal, None, 0, _ptr(z), _ptr(u))
+        else:
+            obs = _d(np.atleast_1d(obs))
+            rc = fn(self.h, _ptr(obs), obs.size, proposal, None, 0, _ptr(z), _ptr(u))
         if rc:
             raise RuntimeError(self.o.err())
 
@@ -270,6 +275,13 @@ class OraclePF:
     def history(self, t):
         out = np.empty((self.D, self.N), dtype=np.float64)
         if self.L.orc_pf_history(self.h, t, _ptr(out)):
+            raise RuntimeError(self.o.err())
+        return out
+
+    def sampled_observation(self, t):
+        """Sampled observation choices of UNOBSERVED step t, in the particles' current order."""
+        out = np.empty(self.N, dtype=np.float64)
+        if self.L.orc_pf_sampled_observation(self.h, t, _ptr(out)):
             raise RuntimeError(self.o.err())
         return out
 

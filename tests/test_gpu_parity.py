@@ -749,3 +749,51 @@ def test_uniform_continuous_on_device(gpu, orc):
     assert np.array_equal(np.isinf(lnw), np.isinf(lnw_o)) and np.isinf(lnw).sum() > ns // 5
     assert np.array_equal(np.isinf(lnw), lat[0] < lo)
     traces._state.close()
+
+
+@pytest.mark.parametrize("fam", [O.LGSSM, O.SV, O.BEARINGS, O.HMM])
+def test_unobserved_steps_sample_the_observation_choice(gpu, orc, fam):
+    """A step without a constraint (empty choice map): the reference samples the observation choice and leaves the
+    weight alone (static_ir/generate.jl:36-42, unfold/update.jl:54-78). Latents, log weights, ancestors and the
+    sampled observation choices (followed through two resamples) are bit-exact against the oracle."""
+    g = gpu
+    N, T = 5000, 10
+    model, params, ys = make_model(g, fam)
+    st = g.ParticleFilterState(model, N, seed=17, keep_history=True, history_capacity=T)
+    pf = orc.particle_filter(fam, params, N, seed=17, keep_history=True)
+    unobs = {3, 4, 7}                       # 1-based time steps without an observation
+    st.init([ys[0]])
+    pf.init([ys[0]])
+    n_res = 0
+    for t in range(2, T + 1):
+        dg, do = st.maybe_resample(N * 0.9), pf.maybe_resample(N * 0.9)
+        assert dg == do
+        n_res += dg
+        if dg:
+            assert np.array_equal(st.ancestors(), pf.parents())
+        if t in unobs:
+            if t == 3:                      # through the mirrored API: an empty choice map
+                g.particle_filter_step_b(st, (t,), (g.UnknownChange(),), g.choicemap())
+            else:
+                st.step(None)
+            pf.step(None)
+        else:
+            st.step([ys[t - 1]])
+            pf.step([ys[t - 1]])
+        assert same_bits(st.log_weights(), pf.log_weights()) and same_bits(st.state(), pf.state()), t
+    assert n_res >= 2
+    for t in sorted(unobs):
+        assert same_bits(st.sampled_observation(t), pf.sampled_observation(t)), "sampled observation of step %d" % t
+    with pytest.raises(g.GsmcError):
+        st.sampled_observation(2)           # step 2 was observed
+    assert st.log_ml_estimate() == pytest.approx(pf.log_ml_estimate(), rel=1e-12)
+    # the trace of a particle exposes its sampled choice under the reference's address
+    ch = g.get_traces(st)[5].get_choices()
+    want = pf.sampled_observation(4)[5]
+    assert ch[model.obs_address(4)] == (int(want) if fam == O.HMM else want)
+    assert ch[model.obs_address(2)] == (int(ys[1]) if fam == O.HMM else ys[1])
+    if fam != O.SV:
+        with pytest.raises(g.GsmcError):    # the catalogue's custom proposals condition on the observation
+            st.lib  # noqa: B018
+            g.particle_filter_step_b(st, (T + 1,), (g.UnknownChange(),), g.choicemap(), model.custom_proposal())
+    st.close()
