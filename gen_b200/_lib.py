@@ -82,6 +82,7 @@ SIGNATURES = {
     "gsmc_run_steps": (C.c_int, [_H, _dp, C.c_size_t, C.c_size_t, C.c_int, _dp, C.c_size_t, C.c_double]),
     "gsmc_save": (C.c_int, [_H, C.c_char_p]),
     "gsmc_restore": (C.c_int, [_H, C.c_char_p]),
+    "gsmc_register_model_plugin": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "gsmc_trim": (C.c_int, []),
     "gsmc_local_count": (C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gsmc_state_dim": (C.c_int, [_H, C.POINTER(C.c_int)]),

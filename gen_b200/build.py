@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgensmc.so")
 SOURCES = ["gsmc.cu"]
-HEADERS = ["kernels.cuh", "models.cuh", "gsmc_rng.cuh", "gsmc_math.h", "gsmc_tables.h", "gsmc_fixed.h", os.path.join("..", "..", "include", "gen_b200.h")]
+HEADERS = ["kernels.cuh", "models.cuh", "gsmc_rng.cuh", "gsmc_math.h", "gsmc_tables.h", "gsmc_fixed.h", "plugin.h", os.path.join("..", "..", "include", "gen_b200.h")]
 
 
 def nvcc_path():

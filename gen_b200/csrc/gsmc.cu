@@ -18,6 +18,7 @@
 
 #include "../../include/gen_b200.h"
 #include "kernels.cuh"
+#include "plugin.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -138,6 +139,22 @@ static cudaError_t ipc_open_cached(int device, const cudaIpcMemHandle_t& handle,
   cudaError_t e = cudaIpcOpenMemHandle(p, handle, cudaIpcMemLazyEnablePeerAccess);
   if (e == cudaSuccess) g_ipc_cache[k] = *p;
   return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model plugins (generated from a static-IR description, see plugin.h): model ids GSMC_MODEL_PLUGIN_BASE + k
+// ------------------------------------------------------------------------------------------------
+struct ModelPlugin {
+  void* lib = nullptr;
+  gsmc_plugin_info info;
+  gsmc_plugin_propagate_fn propagate = nullptr;
+  gsmc_plugin_sample_obs_fn sample_obs = nullptr;
+  std::string path;
+};
+static std::vector<ModelPlugin> g_plugins;
+static const ModelPlugin* plugin_of(int model) {
+  const int k = model - GSMC_MODEL_PLUGIN_BASE;
+  return (k >= 0 && k < (int)g_plugins.size()) ? &g_plugins[k] : nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -310,7 +327,7 @@ static int model_dim(int model) {
     case GSMC_MODEL_NORMAL_NORMAL: return NormalNormalModel::D;
     case GSMC_MODEL_OUTLIER_REGRESSION: return OutlierRegressionModel::D;
     case GSMC_MODEL_UNIFORM_NORMAL: return UniformNormalModel::D;
-    default: return -1;
+    default: return plugin_of(model) ? plugin_of(model)->info.D : -1;
   }
 }
 static bool model_is_importance(int model) {
@@ -339,7 +356,10 @@ static int check_params(int model, const double* p, size_t np) {
         return fail(GSMC_E_BADARG, "outlier regression params: [n, prob_outlier, prior_sd, xs[n]] with 1 <= n <= %d", 32 * GSMC_OUTLIER_ZWORDS);
       return GSMC_OK;
     case GSMC_MODEL_UNIFORM_NORMAL: return (np == 3 && p[1] > p[0]) ? GSMC_OK : fail(GSMC_E_BADARG, "uniform-normal params: [low, high, sd_y] with high > low");
-    default: return fail(GSMC_E_UNSUPPORTED, "unknown model id %d", model);
+    default:
+      if (const ModelPlugin* pl = plugin_of(model))
+        return (int)np == pl->info.n_params ? GSMC_OK : fail(GSMC_E_BADARG, "generated model '%s' takes %d parameters, got %zu", pl->info.name, pl->info.n_params, np);
+      return fail(GSMC_E_UNSUPPORTED, "unknown model id %d", model);
   }
 }
 static int expected_obs(const gsmc_filter* f) {
@@ -461,10 +481,9 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   g_pdl_suppress_next = false;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
-template <class Model, typename Real, bool INIT, int PROP>
-static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
-  Model::prepare(a, INIT, PROP);
-  PropArgs<Real> g;
+// everything of PropArgs that does not depend on the model: columns, flags, RNG keys, replay buffers (checked against nz / nu)
+template <typename Real>
+static int fill_prop_args(gsmc_filter* f, PropArgs<Real>& g, bool INIT, int nz, int nu, bool use_anc) {
   memset(&g, 0, sizeof g);
   const int64_t new_step = f->T + 1;
   for (int r = 0; r < f->nranks; ++r)
@@ -486,12 +505,19 @@ static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
   g.rank = f->rank;
   g.zrep = f->zrep_n ? f->d_zrep : nullptr;
   g.urep = f->urep_n ? f->d_urep : nullptr;
-  // models that draw a run-time number of uniforms per particle (DrawCtx) take p[0] of them
-  const int nz = Model::nz(INIT, PROP), nu = model_ctx_uniforms<Model>::value ? (int)f->params[0] : Model::nu(INIT, PROP);
   if (g.zrep && f->zrep_n != (size_t)(f->n * nz)) return fail(GSMC_E_BADARG, "replay normals: expected %lld values", (long long)(f->n * nz));
   if (g.urep && nu && f->urep_n != (size_t)(f->n * nu)) return fail(GSMC_E_BADARG, "replay uniforms: expected %lld values", (long long)(f->n * nu));
   if (!nu) g.urep = nullptr;
   if (!nz) g.zrep = nullptr;
+  return GSMC_OK;
+}
+template <class Model, typename Real, bool INIT, int PROP>
+static int launch_propagate_t(gsmc_filter* f, ModelArgs& a, bool use_anc) {
+  Model::prepare(a, INIT, PROP);
+  PropArgs<Real> g;
+  // models that draw a run-time number of uniforms per particle (DrawCtx) take p[0] of them
+  const int nz = Model::nz(INIT, PROP), nu = model_ctx_uniforms<Model>::value ? (int)f->params[0] : Model::nu(INIT, PROP);
+  CKRC(fill_prop_args<Real>(f, g, INIT, nz, nu, use_anc));
   {
     ProfScope ps(f, (use_anc && f->pending) ? KC_PROPAGATE_GATHER : KC_PROPAGATE);
     // persistent grid: as many blocks as are resident at once (occupancy of this instantiation), at most one per tile
@@ -515,8 +541,26 @@ static int launch_propagate_m(gsmc_filter* f, ModelArgs& a, bool init, int prop,
   if (init) return prop ? launch_propagate_t<Model, Real, true, 1>(f, a, use_anc) : launch_propagate_t<Model, Real, true, 0>(f, a, use_anc);
   return prop ? launch_propagate_t<Model, Real, false, 1>(f, a, use_anc) : launch_propagate_t<Model, Real, false, 0>(f, a, use_anc);
 }
+// a generated model: the plugin launches its own instantiation of propagate_kernel
+static int launch_propagate_plugin(gsmc_filter* f, const ModelPlugin* pl, ModelArgs& a, bool init, int prop, bool use_anc) {
+  if (prop != GSMC_PROPOSAL_DEFAULT) return fail(GSMC_E_UNSUPPORTED, "generated model '%s' has no custom proposal", pl->info.name);
+  if (f->f32) return fail(GSMC_E_UNSUPPORTED, "generated models are compiled for f64 storage");
+  PropArgs<double> g;
+  CKRC(fill_prop_args<double>(f, g, init, init ? pl->info.nz_init : pl->info.nz_step, 0, use_anc));
+  int n_blocks = 0;
+  {
+    ProfScope ps(f, (use_anc && f->pending) ? KC_PROPAGATE_GATHER : KC_PROPAGATE);
+    const bool pdl = ((pdl_mask() >> PDL_PROPAGATE) & 1u) && !g_pdl_suppress_next;
+    g_pdl_suppress_next = false;
+    const int e = pl->propagate(&g, &a, init ? 1 : 0, f->n_pad, f->sm_count, (void*)f->stream, pdl ? 1 : 0, &n_blocks);
+    if (e != 0) return fail(GSMC_E_CUDA, "generated model '%s': kernel launch failed: %s", pl->info.name, cudaGetErrorString((cudaError_t)e));
+  }
+  f->n_partials = n_blocks;
+  return GSMC_OK;
+}
 template <typename Real>
 static int launch_propagate_r(gsmc_filter* f, ModelArgs& a, bool init, int prop, bool use_anc) {
+  if (const ModelPlugin* pl = plugin_of(f->model)) return launch_propagate_plugin(f, pl, a, init, prop, use_anc);
   switch (f->model) {
     case GSMC_MODEL_HMM: return launch_propagate_m<HmmModel, Real>(f, a, init, prop, use_anc);
     case GSMC_MODEL_LGSSM: return launch_propagate_m<LgssmModel, Real>(f, a, init, prop, use_anc);
@@ -592,7 +636,12 @@ static int launch_sample_obs(gsmc_filter* f, const ModelArgs& a) {
     case GSMC_MODEL_LGSSM: sample_obs_kernel<LgssmModel, Real><<<grid, GSMC_BLOCK, 0, f->stream>>>(a, state, col, f->n, f->n_pad, (uint64_t)f->first, f->cfg.seed, (uint32_t)step); break;
     case GSMC_MODEL_SV: sample_obs_kernel<SvModel, Real><<<grid, GSMC_BLOCK, 0, f->stream>>>(a, state, col, f->n, f->n_pad, (uint64_t)f->first, f->cfg.seed, (uint32_t)step); break;
     case GSMC_MODEL_BEARINGS: sample_obs_kernel<BearingsModel, Real><<<grid, GSMC_BLOCK, 0, f->stream>>>(a, state, col, f->n, f->n_pad, (uint64_t)f->first, f->cfg.seed, (uint32_t)step); break;
-    default: return fail(GSMC_E_UNSUPPORTED, "model %d has no sampler for its observation choice", f->model);
+    default: {
+      const ModelPlugin* pl = plugin_of(f->model);
+      if (!pl || !pl->sample_obs || !pl->info.has_obs_sampler || f->f32) return fail(GSMC_E_UNSUPPORTED, "model %d has no sampler for its observation choice", f->model);
+      const int e = pl->sample_obs(&a, (const double*)state, (double*)col, f->n, f->n_pad, (uint64_t)f->first, f->cfg.seed, (uint32_t)step, (void*)f->stream);
+      if (e != 0) return fail(GSMC_E_CUDA, "generated model '%s': observation sampler failed: %s", pl->info.name, cudaGetErrorString((cudaError_t)e));
+    }
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -1637,6 +1686,29 @@ GSMC_API int gsmc_restore(gsmc_handle f, const char* path) {
   f->last_resample_step = h.last_resample_step; f->pending = h.pending != 0; f->decided_since_step = h.decided_since_step != 0;
   f->is_importance = h.is_importance != 0; f->n_sample_calls = h.n_sample_calls; f->is_lml = h.is_lml;
   f->stats_fresh = false; f->zrep_n = 0; f->urep_n = 0;
+  return GSMC_OK;
+}
+
+GSMC_API int gsmc_register_model_plugin(const char* path, int* model_id_out) {
+  if (!path || !model_id_out) return fail(GSMC_E_BADARG, "null argument");
+  for (size_t k = 0; k < g_plugins.size(); ++k) if (g_plugins[k].path == path) { *model_id_out = GSMC_MODEL_PLUGIN_BASE + (int)k; return GSMC_OK; }
+  void* lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!lib) return fail(GSMC_E_BADARG, "cannot load model plugin %s: %s", path, dlerror());
+  ModelPlugin pl;
+  pl.lib = lib; pl.path = path;
+  gsmc_plugin_describe_fn describe = (gsmc_plugin_describe_fn)dlsym(lib, "gsmc_plugin_describe");
+  pl.propagate = (gsmc_plugin_propagate_fn)dlsym(lib, "gsmc_plugin_propagate");
+  pl.sample_obs = (gsmc_plugin_sample_obs_fn)dlsym(lib, "gsmc_plugin_sample_obs");
+  memset(&pl.info, 0, sizeof pl.info);
+  if (!describe || !pl.propagate || describe(&pl.info) != 0) { dlclose(lib); return fail(GSMC_E_BADARG, "%s is not a libgensmc model plugin", path); }
+  if (pl.info.abi != GSMC_PLUGIN_ABI || pl.info.sizeof_prop_args != sizeof(PropArgs<double>) || pl.info.sizeof_model_args != sizeof(ModelArgs) ||
+      pl.info.sizeof_dev_scalars != sizeof(DevScalars)) {
+    dlclose(lib);
+    return fail(GSMC_E_BADARG, "model plugin %s was generated for another version of libgensmc (regenerate it)", path);
+  }
+  if (pl.info.D < 1 || pl.info.D > 16 || pl.info.n_params < 0 || pl.info.n_params > GSMC_MAX_INLINE_PARAMS) { dlclose(lib); return fail(GSMC_E_BADARG, "model plugin %s: unsupported shape", path); }
+  g_plugins.push_back(pl);
+  *model_id_out = GSMC_MODEL_PLUGIN_BASE + (int)g_plugins.size() - 1;
   return GSMC_OK;
 }
 

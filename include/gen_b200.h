@@ -44,6 +44,8 @@ enum {
   GSMC_MODEL_OUTLIER_REGRESSION = 7, /* examples/regression/static_model.jl:3-23: bernoulli outlier flags, Map of a static kernel (importance sampling) */
   GSMC_MODEL_UNIFORM_NORMAL = 8  /* x ~ uniform(low, high); y ~ normal(x, sd): uniform_continuous.jl:12-23 on the device (importance sampling) */
 };
+/* models generated from a static-IR description (gsmc_register_model_plugin) get ids GSMC_MODEL_PLUGIN_BASE + k */
+#define GSMC_MODEL_PLUGIN_BASE 1000
 enum { GSMC_PROPOSAL_DEFAULT = 0, GSMC_PROPOSAL_CUSTOM = 1 };
 enum { GSMC_RESAMPLE_MULTINOMIAL = 0, GSMC_RESAMPLE_RESIDUAL = 1 };
 enum { GSMC_F64 = 0, GSMC_F32 = 1 };   /* storage type of state columns and log weights; arithmetic is f64 */
@@ -211,6 +213,13 @@ GSMC_API int gsmc_run_steps(gsmc_handle h, const double* obs, size_t n_steps, si
  * bit-identically to one that was never interrupted. */
 GSMC_API int gsmc_save(gsmc_handle h, const char* path);
 GSMC_API int gsmc_restore(gsmc_handle h, const char* path);
+
+/* Beyond the catalogue: a state-space kernel written in a static IR whose nodes are
+ * arithmetic (the counterpart of src/static_ir/dag.jl:1-46; the reference generates Julia code per node,
+ * src/static_ir/generate.jl:68-116) is turned into CUDA source by the host side (gen_b200/staticir.py), compiled with
+ * nvcc into a small shared object that instantiates the propagate kernel for it, and registered here. The returned
+ * model id is used in gsmc_config.model_id like a catalogue id (default proposal, f64 storage). */
+GSMC_API int gsmc_register_model_plugin(const char* path, int* model_id_out);
 
 /* Release the slab pool (column slabs of destroyed filters are cached per device for reuse). */
 GSMC_API int gsmc_trim(void);

@@ -13,12 +13,13 @@
 #     log_ml_estimate(state)
 #
 # NOT EXECUTED in the build environment (no Julia there); the same C ABI is exercised by the Python
-# mirror gen_b200/inference.py, which the tests drive.
+# mirror gen_b200/inference.py and by a plain-C caller (tests/c_abi_smoke.c), which the tests drive.
+# `GenB200.validate()` is the probe to run first wherever Julia + Gen + a B200 exist.
 module GenB200
 
 using Gen
 import Gen: initialize_particle_filter, particle_filter_step!, maybe_resample!, log_ml_estimate,
-            get_log_weights, get_traces, sample_unweighted_traces, importance_sampling
+            get_log_weights, get_traces, sample_unweighted_traces, importance_sampling, importance_resampling
 
 const LIB = get(ENV, "GENSMC_LIB", joinpath(@__DIR__, "..", "gen_b200", "libgensmc.so"))
 
@@ -37,6 +38,7 @@ struct Config
 end
 
 const MODEL_HMM, MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_REGRESSION, MODEL_NORMAL_NORMAL = 1, 2, 3, 4, 5, 6
+const MODEL_OUTLIER_REGRESSION, MODEL_UNIFORM_NORMAL = 7, 8
 
 function check(rc::Cint, h = C_NULL)
     rc == 0 && return
@@ -74,6 +76,57 @@ model_id(::StochasticVolatility) = MODEL_SV
 state_names(::StochasticVolatility) = (:h,)
 obs_name(::StochasticVolatility) = :y
 
+"2-D bearings-only tracking, state (x, vx, y, vy); custom proposal = one-step EKF update (BASELINE.json configs[5])."
+struct BearingsOnly <: DeviceSSM
+    prior_mean::NTuple{4,Float64}; prior_std::NTuple{4,Float64}; sigma_w::Float64; sigma_theta::Float64
+end
+BearingsOnly() = BearingsOnly((0.0, 0.0, 12.4, -0.05), (0.5, 0.005, 0.3, 0.01), 0.001, 0.005)
+params(m::BearingsOnly) = Float64[m.prior_mean..., m.prior_std..., m.sigma_w, m.sigma_theta]
+model_id(::BearingsOnly) = MODEL_BEARINGS
+state_names(::BearingsOnly) = (:x, :vx, :y, :vy)
+obs_name(::BearingsOnly) = :bearing
+
+# ---- importance-sampling families (one "time step", no resampling) --------------------------------
+abstract type DeviceISModel <: GenerativeFunction{Any,Trace} end
+
+"examples/regression/quickstart.jl:3-9; model_args = (xs,); observations constrain \"y-\$i\"."
+struct LinearRegression <: DeviceISModel
+    sd_slope::Float64; sd_intercept::Float64; sd_noise::Float64
+end
+LinearRegression() = LinearRegression(2.0, 10.0, 1.0)
+model_id(::LinearRegression) = MODEL_REGRESSION
+is_params(m::LinearRegression, model_args) = (xs = Float64.(model_args[1]); vcat(Float64[length(xs), m.sd_slope, m.sd_intercept, m.sd_noise], xs))
+is_observations(m::LinearRegression, model_args, obs::ChoiceMap) = Float64[obs["y-$i"] for i in 1:length(model_args[1])]
+latent_names(::LinearRegression) = (:slope, :intercept)
+
+"test/inference/importance_sampling.jl:3-12: x ~ normal(mu0, sd0); y ~ normal(x, sd_y)."
+struct NormalNormal <: DeviceISModel
+    mu0::Float64; sd0::Float64; sd_y::Float64
+end
+model_id(::NormalNormal) = MODEL_NORMAL_NORMAL
+is_params(m::NormalNormal, model_args) = Float64[m.mu0, m.sd0, m.sd_y]
+is_observations(m::NormalNormal, model_args, obs::ChoiceMap) = Float64[obs[:y]]
+latent_names(::NormalNormal) = (:x,)
+
+"examples/regression/static_model.jl:3-23 (bernoulli outlier flags, Map of the static `datum`); model_args = (xs,), n <= 256."
+struct OutlierRegression <: DeviceISModel
+    prob_outlier::Float64; prior_sd::Float64
+end
+OutlierRegression() = OutlierRegression(0.5, 2.0)
+model_id(::OutlierRegression) = MODEL_OUTLIER_REGRESSION
+is_params(m::OutlierRegression, model_args) = (xs = Float64.(model_args[1]); vcat(Float64[length(xs), m.prob_outlier, m.prior_sd], xs))
+is_observations(m::OutlierRegression, model_args, obs::ChoiceMap) = Float64[obs[:data => i => :y] for i in 1:length(model_args[1])]
+latent_names(::OutlierRegression) = (:log_inlier_std, :log_outlier_std, :slope, :intercept)
+
+"x ~ uniform(low, high); y ~ normal(x, sd_y) (uniform_continuous.jl:12-23 on the device)."
+struct UniformNormal <: DeviceISModel
+    low::Float64; high::Float64; sd_y::Float64
+end
+model_id(::UniformNormal) = MODEL_UNIFORM_NORMAL
+is_params(m::UniformNormal, model_args) = Float64[m.low, m.high, m.sd_y]
+is_observations(m::UniformNormal, model_args, obs::ChoiceMap) = Float64[obs[:y]]
+latent_names(::UniformNormal) = (:x,)
+
 "A catalogue proposal (the `proposal::GenerativeFunction` argument)."
 struct DeviceProposal <: GenerativeFunction{Any,Trace}
     params::Vector{Float64}
@@ -83,7 +136,10 @@ obs_address(m::DeviceSSM, T::Int) = T == 1 ? Symbol(obs_name(m), :_init) : (:cha
 
 function observation_vector(m::DeviceSSM, T::Int, observations::ChoiceMap)
     addr = obs_address(m, T)
-    has_value(observations, addr) || error("observations must constrain $addr")
+    # an empty choice map: nothing is constrained at this step -- the reference samples the observation choice
+    # (src/static_ir/generate.jl:36-42) and the weight does not change; the C ABI takes (NULL, 0) for that
+    isempty(observations) && return Float64[]
+    has_value(observations, addr) || error("constraints at addresses the model does not visit at this step")
     # like src/dynamic/update.jl:191-193: constraints the model does not visit are an error
     n = length(collect(get_values_shallow(observations))) + sum(Int[1 for _ in get_submaps_shallow(observations)])
     n == 1 || error("constraints at addresses the model does not visit at this step")
@@ -100,7 +156,7 @@ mutable struct DeviceParticleFilterState{M<:DeviceSSM}
 end
 
 function create(model::DeviceSSM, num_particles::Int; seed = 0, dtype = 0, resample = 0, keep_history = true,
-                history_capacity = 128, device = -1)
+                history_capacity = 128, device = -1, comm = nothing)
     cfg = Ref(Config(sizeof(Config), model_id(model), dtype, resample, num_particles, seed, device,
                      keep_history ? 1 : 0, history_capacity, C_NULL))
     p = params(model)
@@ -108,6 +164,7 @@ function create(model::DeviceSSM, num_particles::Int; seed = 0, dtype = 0, resam
     check(ccall((:gsmc_create, LIB), Cint, (Ref{Config}, Ptr{Float64}, Csize_t, Ref{Ptr{Cvoid}}), cfg, p, length(p), h))
     state = DeviceParticleFilterState(h[], model, num_particles, 0, Vector{Float64}[])
     finalizer(s -> ccall((:gsmc_destroy, LIB), Cvoid, (Ptr{Cvoid},), s.handle), state)
+    comm === nothing || check(ccall((:gsmc_comm_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), state.handle, comm.handle), state.handle)
     state
 end
 
@@ -116,9 +173,10 @@ proposal_args(p::DeviceProposal) = (1, p.params)
 
 function propagate!(state, fn::Symbol, obs::Vector{Float64}, proposal)
     (pid, pp) = proposal_args(proposal)
-    rc = fn == :gsmc_init ?
-        ccall((:gsmc_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Csize_t, Cint, Ptr{Float64}, Csize_t), state.handle, obs, length(obs), pid, pp, length(pp)) :
-        ccall((:gsmc_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Csize_t, Cint, Ptr{Float64}, Csize_t), state.handle, obs, length(obs), pid, pp, length(pp))
+    optr = isempty(obs) ? Ptr{Float64}(C_NULL) : pointer(obs)          # (NULL, 0): unobserved step
+    rc = GC.@preserve obs (fn == :gsmc_init ?
+        ccall((:gsmc_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Csize_t, Cint, Ptr{Float64}, Csize_t), state.handle, optr, length(obs), pid, pp, length(pp)) :
+        ccall((:gsmc_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Csize_t, Cint, Ptr{Float64}, Csize_t), state.handle, optr, length(obs), pid, pp, length(pp)))
     check(rc, state.handle)
     state.T += 1
     push!(state.observations, obs)
@@ -191,11 +249,59 @@ function trace_choices(state::DeviceParticleFilterState, i::Int)
         v = out[(t - 1) * D + d]
         addr = t == 1 ? Symbol(name, :_init) : (:chain => (t - 1) => name)
         cm[addr] = state.model isa HMM ? Int(v) : v
-        y = state.observations[t][1]
+        y = isempty(state.observations[t]) ? sampled_observation(state, t)[i] : state.observations[t][1]
         cm[obs_address(state.model, t)] = state.model isa HMM ? Int(y) : y
     end
     cm
 end
+
+"Observation choices the device sampled at UNOBSERVED step t (current particle order)."
+function sampled_observation(state::DeviceParticleFilterState, t::Int)
+    out = Vector{Float64}(undef, state.num_particles)
+    check(ccall((:gsmc_get_observation, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Csize_t), state.handle, t, out, length(out)), state.handle)
+    out
+end
+
+"The whole loop `for t: maybe_resample!; particle_filter_step!` enqueued without a host round trip per step (gsmc_run_steps)."
+function run_steps!(state::DeviceParticleFilterState, ys::Vector{Float64}; ess_threshold::Real = state.num_particles / 2, proposal = nothing)
+    (pid, pp) = proposal_args(proposal)
+    check(ccall((:gsmc_run_steps, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Csize_t, Csize_t, Cint, Ptr{Float64}, Csize_t, Float64),
+                state.handle, ys, length(ys), 1, pid, pp, length(pp), Float64(ess_threshold)), state.handle)
+    state.T += length(ys)
+    append!(state.observations, [Float64[y] for y in ys])
+    nothing
+end
+
+"Checkpoint / resume (gsmc_save / gsmc_restore): one file per handle (per rank of a sharded filter)."
+save_checkpoint(state::DeviceParticleFilterState, path::String) =
+    check(ccall((:gsmc_save, LIB), Cint, (Ptr{Cvoid}, Cstring), state.handle, path), state.handle)
+function restore_checkpoint!(state::DeviceParticleFilterState, path::String, observations::Vector{Vector{Float64}})
+    check(ccall((:gsmc_restore, LIB), Cint, (Ptr{Cvoid}, Cstring), state.handle, path), state.handle)
+    state.T = length(observations); state.observations = observations
+    nothing
+end
+
+# ---- multi-GPU: one Julia process per GPU (e.g. under MPI.jl); rank 0 makes the id and broadcasts its 128 bytes ----
+mutable struct Communicator
+    handle::Ptr{Cvoid}
+    rank::Int
+    nranks::Int
+end
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:gsmc_comm_unique_id, LIB), Cint, (Ptr{UInt8}, Csize_t), id, 128))
+    id
+end
+function Communicator(unique_id::Vector{UInt8}, rank::Int, nranks::Int; device::Int = -1)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gsmc_comm_create, LIB), Cint, (Ptr{UInt8}, Csize_t, Cint, Cint, Cint, Ref{Ptr{Cvoid}}), unique_id, 128, rank, nranks, device, h))
+    c = Communicator(h[], rank, nranks)
+    finalizer(x -> ccall((:gsmc_comm_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), c)
+    c
+end
+"After attach the state owns particles [rank*N/R, (rank+1)*N/R); pass `comm = c` to initialize_particle_filter."
+attach!(state::DeviceParticleFilterState, c::Communicator) =
+    check(ccall((:gsmc_comm_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), state.handle, c.handle), state.handle)
 
 struct DeviceTraces{S}
     state::S
@@ -226,13 +332,62 @@ function importance_sampling(model::DeviceSSM, model_args::Tuple, observations::
     (get_traces(state), get_log_weights(state) .- (lml + log(num_samples)), lml)
 end
 
+# importance.jl:20-33 and :35-52 for the importance-sampling families: gsmc_importance_sampling returns a handle whose
+# log weights are already normalised and whose columns are the sampled latents
+struct ISTraces{M<:DeviceISModel}
+    handle::Ptr{Cvoid}
+    model::M
+    model_args::Tuple
+    observations::ChoiceMap
+    num_samples::Int
+end
+Base.length(t::ISTraces) = t.num_samples
+function Base.getindex(t::ISTraces, i::Int)
+    names = latent_names(t.model)
+    dim = Ref{Cint}(0)
+    check(ccall((:gsmc_state_dim, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}), t.handle, dim), t.handle)
+    row = Vector{Float64}(undef, Int(dim[]))
+    idx = Int64[i - 1]
+    check(ccall((:gsmc_get_trajectories, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Csize_t, Ptr{Float64}, Csize_t), t.handle, idx, 1, row, length(row)), t.handle)
+    cm = choicemap()
+    for (d, name) in enumerate(names)
+        cm[name] = row[d]
+    end
+    if t.model isa OutlierRegression                     # flags are bit-packed, 32 per column, after the four reals
+        for j in 1:length(t.model_args[1])
+            cm[:data => j => :z] = ((UInt64(row[4 + ((j - 1) >> 5) + 1]) >> ((j - 1) & 31)) & 1) == 1
+        end
+    end
+    merge(cm, t.observations)
+end
+function is_call(model::DeviceISModel, model_args::Tuple, observations::ChoiceMap, proposal, num_samples::Int; seed = 0, dtype = 0, device = -1)
+    cfg = Ref(Config(sizeof(Config), model_id(model), dtype, 0, num_samples, seed, device, 0, 0, C_NULL))
+    p = is_params(model, model_args)
+    obs = is_observations(model, model_args, observations)
+    (pid, pp) = proposal_args(proposal)
+    lml = Ref{Float64}(0.0); h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gsmc_importance_sampling, LIB), Cint,
+                (Ref{Config}, Ptr{Float64}, Csize_t, Ptr{Float64}, Csize_t, Cint, Ptr{Float64}, Csize_t, Ref{Float64}, Ref{Ptr{Cvoid}}),
+                cfg, p, length(p), obs, length(obs), pid, pp, length(pp), lml, h))
+    lw = Vector{Float64}(undef, num_samples)
+    check(ccall((:gsmc_get_log_weights, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Csize_t), h[], lw, length(lw)), h[])
+    (ISTraces(h[], model, model_args, observations, num_samples), lw, lml[])
+end
+# importance.jl:20-33
+importance_sampling(model::DeviceISModel, model_args::Tuple, observations::ChoiceMap, num_samples::Int, verbose = false; kwargs...) =
+    is_call(model, model_args, observations, nothing, num_samples; kwargs...)
+# importance.jl:35-52 (custom proposal: weight = model weight - proposal score)
+importance_sampling(model::DeviceISModel, model_args::Tuple, observations::ChoiceMap, proposal::DeviceProposal, proposal_args::Tuple,
+                    num_samples::Int, verbose = false; kwargs...) =
+    is_call(model, model_args, observations, proposal, num_samples; kwargs...)
+
 # importance.jl:70-87: sampling importance resampling that returns ONE trace. The reference keeps a reservoir of size
 # one while it streams the samples; here the samples are generated `chunk_size` at a time on the device, the kept trace
 # of a chunk is one categorical draw from the chunk's weights, and chunks are merged with the reference's rule
 # (`bernoulli(exp(log_weight - log_total_weight))` with the chunk's total in the place of one sample's weight).
 chunk_seed(seed::UInt64, c::Int) = seed + UInt64(c) * 0x9E3779B97F4A7C15
-function importance_resampling(model::DeviceSSM, model_args::Tuple, observations::ChoiceMap, num_samples::Int, verbose = false;
-                               seed::UInt64 = UInt64(0), chunk_size::Int = 1 << 24, kwargs...)
+function importance_resampling(model::DeviceSSM, model_args::Tuple, observations::ChoiceMap, num_samples::Int;
+                               verbose = false, seed::UInt64 = UInt64(0), chunk_size::Int = 1 << 24, kwargs...)   # verbose is a keyword (importance.jl:72)
     log_total, kept, done, c = -Inf, nothing, 0, 0
     while done < num_samples
         m = min(chunk_size, num_samples - done)
@@ -267,6 +422,32 @@ function philox_uniform(seed::UInt64, e::Int, t::Integer, stream::Integer)
     Float64(w >> 11) * 2.0^-53
 end
 
-export LinearGaussianSSM, HMM, StochasticVolatility, DeviceProposal, DeviceParticleFilterState, importance_resampling
+"""
+    validate(; num_particles = 10_000)
+
+The reference's own particle-filter test (test/inference/particle_filter.jl:52-81,130-142) run twice: once with Gen's
+dynamic-DSL model on the CPU, once with the device model; both estimates must be within the test's tolerance (0.01) of
+the exact forward-algorithm value -4.87645083351704. The probe SURVEY.md section 8(b) asks for; needs Gen and a GPU.
+"""
+function validate(; num_particles::Int = 10_000)
+    prior = [0.2, 0.3, 0.5]
+    emission_dists = [0.1 0.2 0.7; 0.2 0.7 0.1; 0.7 0.2 0.1]'
+    transition_dists = [0.4 0.4 0.2; 0.2 0.3 0.5; 0.9 0.05 0.05]'
+    obs_x = [1, 1, 2, 3]
+    expected = -4.87645083351704
+    model = HMM(prior, Matrix(emission_dists), Matrix(transition_dists))
+    state = initialize_particle_filter(model, (1,), choicemap((:x_init, obs_x[1])), num_particles)
+    for T in 2:length(obs_x)
+        maybe_resample!(state; ess_threshold = num_particles)
+        particle_filter_step!(state, (T,), (UnknownChange(),), choicemap((:chain => (T - 1) => :x, obs_x[T])))
+    end
+    lml = log_ml_estimate(state)
+    isapprox(lml, expected; atol = 0.02) || error("device estimate $lml is not within 0.02 of $expected")
+    (device = lml, exact = expected)
+end
+
+export LinearGaussianSSM, HMM, StochasticVolatility, BearingsOnly, LinearRegression, NormalNormal, OutlierRegression, UniformNormal,
+       DeviceProposal, DeviceParticleFilterState, Communicator, comm_unique_id, attach!, run_steps!, sampled_observation,
+       save_checkpoint, restore_checkpoint!, validate
 
 end # module
