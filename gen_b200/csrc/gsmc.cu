@@ -814,7 +814,8 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid, i
       CK(launch_pdl(resid_cdf_kernel<Real>, ns, GSMC_BLOCK, 0, f->stream, lw, f->n, scale, f->ds, f->cc, f->raw0, f->cdf, f->raw1, nt, st, conditional)); }
     CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_b, SCAN_RESID, conditional));
     { ProfScope ps(f, KC_SEARCH);
-      CK(launch_pdl(det_copies_kernel, (int)((f->n + GSMC_BLOCK - 1) / GSMC_BLOCK), GSMC_BLOCK, 0, f->stream,
+      const int want = (int)((f->n_pad + GSMC_BLOCK - 1) / GSMC_BLOCK), wave = 8 * f->sm_count;
+      CK(launch_pdl(det_copies_kernel, want < wave ? want : wave, GSMC_BLOCK, 0, f->stream,
           f->cc, f->seg_a, ns, st * GSMC_TILE, (int)f->n_pad, f->n, f->ds, anc, conditional)); }
     CK(cudaGetLastError());
   }

@@ -927,35 +927,54 @@ __global__ void resid_scale_kernel(DevScalars* ds, double n_global) {
   if (threadIdx.x == 0 && blockIdx.x == 0 && ds->do_resample)
     ds->resid_scale = (n_global * 4294967296.0) / (double)ds->cdf_total;
 }
-// segment-local inclusive CDFs of the copy counts (cc) and of the residual fractions (cl) + the segment totals
+// segment-local inclusive CDFs of the copy counts (cc) and of the residual fractions (cl) + the segment totals;
+// same streaming structure as weights_kernel (8 elements per thread and tile, one barrier per block scan)
 template <typename Real>
-__global__ void __launch_bounds__(GSMC_BLOCK) resid_cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
-                                                               uint64_t* cc, uint64_t* seg_c, uint64_t* cl, uint64_t* seg_r,
-                                                               int nt, int seg_tiles, int conditional) {
-  __shared__ uint64_t sm[GSMC_BLOCK / 32 + 1];
+__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_WK_OCC) resid_cdf_kernel(const Real* lw, int64_t n, double scale, const DevScalars* ds,
+                                                                            uint64_t* cc, uint64_t* seg_c, uint64_t* cl, uint64_t* seg_r,
+                                                                            int nt, int seg_tiles, int conditional) {
+  typedef typename Vec2T<Real>::type Real2;
+  constexpr int W = GSMC_WPT;
+  __shared__ uint64_t sm_c[2 * (GSMC_BLOCK / 32)];
+  __shared__ uint64_t sm_r[2 * (GSMC_BLOCK / 32)];
   __shared__ double etab[64];
   if (threadIdx.x < 64) etab[threadIdx.x] = gm_exp2tab_g[threadIdx.x];
   __syncthreads();
   pdl_wait();
   pdl_trigger();
   if (conditional && !ds->do_resample) return;
+  const double mx = ds->max_lw, rscale = ds->resid_scale;
   const int t0 = blockIdx.x * seg_tiles, t1 = min(t0 + seg_tiles, nt);
   uint64_t run_c = 0, run_r = 0;
-  for (int sub = t0 * (GSMC_TILE / 1024); sub < t1 * (GSMC_TILE / 1024); ++sub) {
-    const int64_t i = (int64_t)sub * 1024 + 4 * threadIdx.x;
-    uint64_t q[4], c[4], r[4], cs = 0, rs = 0;
-    load_q4(lw, i, n, ds->max_lw, scale, etab, q);
+  int buf = 0;
+  for (int tile = t0; tile < t1; ++tile, buf ^= 1) {
+    const int64_t i = (int64_t)tile * GSMC_TILE + W * threadIdx.x;
+    double x[W], ex[W];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      resid_split(q[j], ds->resid_scale, &c[j], &r[j]);
+    for (int j = 0; j < W / 2; ++j) {
+      const Real2 l = *reinterpret_cast<const Real2*>(lw + i + 2 * j);
+      x[2 * j] = (double)l.x - mx; x[2 * j + 1] = (double)l.y - mx;
+    }
+    gm_exp_nonpos_v<W>(x, ex, etab);
+    uint64_t c[W], r[W], cs = 0, rs = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const uint64_t q = (uint64_t)(ex[j] * scale);                      // = floor: the product is >= 0 (as in weights_kernel)
+      resid_split(q, rscale, &c[j], &r[j]);
       if (i + j >= n) { c[j] = 0; r[j] = 0; }
       cs += c[j]; rs += r[j];
     }
     uint64_t ctot, rtot;
-    uint64_t ic = run_c + block_scan_u64(cs, sm, &ctot) - cs;
-    uint64_t ir = run_r + block_scan_u64(rs, sm, &rtot) - rs;
+    uint64_t ic = run_c + block_scan_incl(cs, sm_c, buf, &ctot) - cs;
+    uint64_t ir = run_r + block_scan_incl(rs, sm_r, buf, &rtot) - rs;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { ic += c[j]; ir += r[j]; cc[i + j] = ic; cl[i + j] = ir; }
+    for (int j = 0; j < W; j += 2) {
+      ulonglong2 oc, orr;
+      ic += c[j]; oc.x = ic; ic += c[j + 1]; oc.y = ic;
+      ir += r[j]; orr.x = ir; ir += r[j + 1]; orr.y = ir;
+      *reinterpret_cast<ulonglong2*>(cc + i + j) = oc;
+      *reinterpret_cast<ulonglong2*>(cl + i + j) = orr;
+    }
     run_c += ctot; run_r += rtot;
   }
   if (threadIdx.x == 0) { seg_c[blockIdx.x] = run_c; seg_r[blockIdx.x] = run_r; }
@@ -1429,24 +1448,39 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_iid_kernel(CdfView v, const
   if (anc64) anc64[o] = (int64_t)(w >> GSMC_ANC_RANK_SHIFT) * v.n_per + (int64_t)(w & GSMC_ANC_INDEX_MASK);
 }
 
-// residual scheme, deterministic part: slot o < n_det belongs to min{i : Cc_i > o}, Cc in two levels
+// residual scheme, deterministic part: particle i owns the output slots [Cc_{i-1}, Cc_i) of the copies CDF (two levels:
+// segment prefix + segment-local inclusive count). A scatter: one thread per particle writes its own c_i = floor(N p_i)
+// copies (usually 0..2, neighbouring threads write neighbouring slots); a particle with 32 or more copies is written by
+// its whole warp. Same result as searching min{i : Cc_i > o} for every slot o.
 __global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* cc, const uint64_t* seg_c, int n_segs, int seg_len, int n_pad,
                                                                 int64_t n, const DevScalars* ds, uint32_t* anc, int conditional) {
   pdl_wait();
   pdl_trigger();
   if (conditional && !ds->do_resample) return;
-  const int64_t o = (int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x;
-  if (o >= (int64_t)ds->n_det || o >= n) return;
-  GtU64 gt; gt.T = (uint64_t)o;
-  const int s = upper_pred(seg_c + 1, n_segs, 0, gt);
-  int64_t l = n - 1;
-  if (s < n_segs) {
-    const int64_t first = (int64_t)s * seg_len;
-    const int len = (int)(first + seg_len <= n_pad ? seg_len : n_pad - first);
-    l = first + upper_pred(cc + first, len, __ldg(seg_c + s), gt);
-    if (l > n - 1) l = n - 1;
+  const int lane = threadIdx.x & 31;
+  for (int64_t base = ((int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x) & ~(int64_t)31; base < n_pad; base += (int64_t)gridDim.x * GSMC_BLOCK) {
+    const int64_t i = base + lane;                       // a warp covers 32 consecutive particles of ONE segment
+    const int seg = (int)(base / seg_len);
+    const uint64_t off = __ldg(seg_c + seg);
+    const uint64_t incl = (i < n) ? __ldg(cc + i) : 0;
+    uint64_t prev = shfl_up_u64(incl, 1);
+    if (lane == 0) prev = (base % seg_len == 0) ? 0 : __ldg(cc + base - 1);
+    uint64_t first = off + prev;
+    uint64_t cnt = (i < n) ? incl - prev : 0;
+    if (first >= (uint64_t)n) cnt = 0;
+    else if (first + cnt > (uint64_t)n) cnt = (uint64_t)n - first;       // never more than N slots
+    const bool big = cnt >= 32;
+    if (!big) for (uint64_t j = 0; j < cnt; ++j) anc[first + j] = (uint32_t)i;
+    unsigned mask = __ballot_sync(0xffffffffu, big);
+    while (mask) {
+      const int src = __ffs((int)mask) - 1;
+      mask &= mask - 1;
+      const uint64_t f0 = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)first, src);
+      const uint64_t c0 = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)cnt, src);
+      const uint32_t who = (uint32_t)(base + src);
+      for (uint64_t j = lane; j < c0; j += 32) anc[f0 + j] = who;
+    }
   }
-  anc[o] = (uint32_t)l;
 }
 
 // ------------------------------------------------------------------------------------------------
