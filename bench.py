@@ -307,6 +307,17 @@ def run_ours(args):
                                "accounting": "SURVEY 8(d): (2S+16) B per particle-step + (2S+36) B per particle per resample"},
         "kernel_ms_profile_pass": kernel_ms, "kernel_share_propagate": ms_prop / total_kernel_ms if total_kernel_ms else None,
     }
+    # second roofline entry: the resampling path (weights/CDF pass + partition + ancestor search) on the events that fired.
+    # scan reads lw (8) and writes the CDF (8), search reads the CDF (8) and writes the ancestors (4) = 28 B
+    # per particle and event in fp64 (the gather and the zeroed weights are booked with the propagate launch that follows)
+    ms_res = prof["ms_scan"] + prof["ms_spacings"] + prof["ms_search"]
+    if n_gather and ms_res > 0:
+        res_bytes = n_per * (2 * LW + 8 + 4)
+        line["roofline_resample"] = {"bound": "hbm", "kernels": "weights_kernel + partition_kernel + search_sorted_kernel",
+                                     "achieved": res_bytes * n_gather / (ms_res * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": res_bytes * n_gather / (ms_res * 1e-3) / 1e9 / peak, "events": n_gather,
+                                     "algorithmic_bytes_per_event": res_bytes, "avg_event_ms": ms_res / n_gather,
+                                     "note": "conditional launches of the steps that did not resample are booked under 'other'"}
     if world > 1:
         line["nvlink"] = {"remote_rows_per_resample_max_rank": remote_rows, "rows_per_rank": n_per,
                           "bytes_per_resample_est": (remote_rows or 0) * (S + 8),
@@ -317,6 +328,8 @@ def run_ours(args):
         n_l = max(1, n_plain + n_gather)
         line["roofline"]["traffic"] = (n_plain * tr["propagate_plain_bytes"] + n_gather * tr["propagate_gather_bytes"]) / n_l
         line["roofline"]["traffic_source"] = tr.get("source")
+        if "roofline_resample" in line and "weights_bytes" in tr:
+            line["roofline_resample"]["traffic"] = tr["weights_bytes"] + tr.get("partition_bytes", 0) + tr["search_bytes"]
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(1, args.cpu_log2n, T, ys, args.config)
     emit(args.out_fd, line)

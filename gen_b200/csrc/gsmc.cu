@@ -1075,8 +1075,14 @@ GSMC_API int gsmc_maybe_resample(gsmc_handle f, double ess_threshold, int* did_r
   // exported uniforms are being replayed, the resampling kernels are enqueued right away in their conditional form
   // (they exit at once when no resample was decided), so the GPU never idles while the host reads the Bool.
   CKRC(launch_finalize(f, ess_threshold, true));
+  const size_t ev0 = f->prof_live.size();
   if (!replay) CKRC(launch_resample(f, 1, false));
   CKRC(wait_decision(f));
+  // profiling: the conditional launches of a step that did not resample exited at once; book them as "other" so that
+  // the scan / search classes time resampling events only
+  if (f->profiling && !f->h_ds->do_resample)
+    for (size_t k = ev0; k < f->prof_live.size(); ++k)
+      if (f->prof_live[k].cls == KC_SCAN || f->prof_live[k].cls == KC_SEARCH || f->prof_live[k].cls == KC_SPACINGS) f->prof_live[k].cls = KC_OTHER;
   f->stats_fresh = true;
   f->decided_since_step = true;
   if (f->h_ds->error) {

@@ -12,5 +12,5 @@ $CMD > gpurun_out/plain_short.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/plain_short2.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"propagate_kernel|finalize|weights_kernel|partition|search_sorted" -s 60 -c 12 -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"propagate_kernel|finalize|weights_kernel|partition|search_sorted" -s 60 -c 14 -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -2 gpurun_out/ncu_full.log; ls -la gpurun_out/*.ncu-rep
