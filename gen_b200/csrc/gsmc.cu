@@ -206,7 +206,7 @@ struct gsmc_filter {
   uint64_t* cdf = nullptr;    // u64[n_pad] segment-local inclusive CDF of the integer weights, followed by seg_a
   uint64_t* cc = nullptr;     // residual: segment-local inclusive counts of deterministic copies
   uint64_t* seg_a = nullptr;  // u64[n_segs+1] segment totals / exclusive prefixes of the weights (inside the cdf allocation: peers read it)
-  uint64_t* seg_b = nullptr;  // u64[n_segs+1] residual scheme: segment prefixes of the residual fractions
+  uint64_t* seg_b = nullptr;  // u64[n_segs+1] residual scheme: segment prefixes of the residual fractions (inside the cdf allocation too)
   uint64_t* seg_e = nullptr;  // u64[n_segs+1] exclusive prefixes of the group gaps
   uint64_t* raw0 = nullptr;   // u64[n_segs] raw segment totals written by the streaming passes (weights; residual: copies)
   uint64_t* raw1 = nullptr;   // u64[n_segs] raw segment totals (group gaps; residual: fractions)
@@ -387,14 +387,15 @@ static int alloc_buffers(gsmc_filter* f) {
   f->seg_tiles = (f->n_tiles + max_segs - 1) / max_segs;
   f->n_segs = (f->n_tiles + f->seg_tiles - 1) / f->seg_tiles;
   const size_t seg_words = GSMC_MAX_SEGS + 16;
-  f->bytes_lw = f->n_pad * rs; f->bytes_cdf = (f->n_pad + seg_words) * sizeof(uint64_t);
+  // the CDF column is followed by two arrays of segment prefixes (weights / copies, residual fractions): peers read all three
+  f->bytes_lw = f->n_pad * rs; f->bytes_cdf = (f->n_pad + 2 * seg_words) * sizeof(uint64_t);
   CK(pool_alloc(f->device, &f->state_slab, f->bytes_state));
   CK(pool_alloc(f->device, (void**)&f->anc_slab, f->bytes_anc));
   CK(pool_alloc(f->device, &f->lw, f->bytes_lw));
   CK(pool_alloc(f->device, (void**)&f->cdf, f->bytes_cdf));
   if (f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL) CK(pool_alloc(f->device, (void**)&f->cc, f->n_pad * sizeof(uint64_t)));
   f->seg_a = f->cdf + f->n_pad;
-  CK(pool_alloc(f->device, (void**)&f->seg_b, seg_words * sizeof(uint64_t)));
+  f->seg_b = f->seg_a + seg_words;
   CK(pool_alloc(f->device, (void**)&f->seg_e, seg_words * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->raw0, seg_words * sizeof(uint64_t)));
   CK(pool_alloc(f->device, (void**)&f->raw1, seg_words * sizeof(uint64_t)));
@@ -432,7 +433,7 @@ static void free_buffers(gsmc_filter* f) {
   pool_free(f->device, f->state_slab, f->bytes_state); pool_free(f->device, f->anc_slab, f->bytes_anc);
   pool_free(f->device, f->lw, f->bytes_lw); pool_free(f->device, f->cdf, f->bytes_cdf); pool_free(f->device, f->cc, f->n_pad * sizeof(uint64_t));
   const size_t seg_words = GSMC_MAX_SEGS + 16;
-  pool_free(f->device, f->seg_b, seg_words * sizeof(uint64_t)); pool_free(f->device, f->seg_e, seg_words * sizeof(uint64_t));
+  pool_free(f->device, f->seg_e, seg_words * sizeof(uint64_t));
   pool_free(f->device, f->raw0, seg_words * sizeof(uint64_t)); pool_free(f->device, f->raw1, seg_words * sizeof(uint64_t));
   pool_free(f->device, f->tile_e, (size_t)f->n_tiles * sizeof(uint64_t));
   pool_free(f->device, f->gap, (size_t)(f->n_pad / GSMC_GROUP) * sizeof(uint64_t)); pool_free(f->device, f->win, (size_t)(f->n_tiles + 1) * sizeof(uint32_t));
@@ -727,14 +728,23 @@ static int fetch_scalars(gsmc_filter* f) {
 static CdfView make_cdf_view(const gsmc_filter* f, bool residual_fractions) {
   CdfView v;
   memset(&v, 0, sizeof v);
-  for (int r = 0; r < f->nranks; ++r) { v.seg[r] = f->peer_cdf[r]; v.sp[r] = f->peer_cdf[r] + f->n_pad; }
-  if (residual_fractions) v.sp[f->rank] = f->seg_b;      // single rank: the CDF of the residual fractions
+  const size_t seg_words = GSMC_MAX_SEGS + 16;
+  // residual scheme: the searched CDF is the one of the residual fractions, whose segment prefixes are the second array
+  for (int r = 0; r < f->nranks; ++r) { v.seg[r] = f->peer_cdf[r]; v.sp[r] = f->peer_cdf[r] + f->n_pad + (residual_fractions ? seg_words : 0); }
   v.n_per = f->n;
   v.n_pad = (int)f->n_pad;
   v.seg_len = f->seg_tiles * GSMC_TILE;
   v.n_segs = f->n_segs;
   v.nranks = f->nranks;
   return v;
+}
+// the ancestor column of the step being produced on every rank (for the remote stores of the sharded residual scheme)
+static AncOut make_anc_out(const gsmc_filter* f, int64_t step) {
+  AncOut a;
+  memset(&a, 0, sizeof a);
+  for (int r = 0; r < f->nranks; ++r) a.col[r] = anc_col(f, f->peer_anc[r], step);
+  a.n_per = f->n; a.nranks = f->nranks;
+  return a;
 }
 static double weight_scale(const gsmc_filter* f) {
   int lg = 0;
@@ -745,25 +755,30 @@ static double weight_scale(const gsmc_filter* f) {
 // One-block scan of the raw segment totals in0/in1 into the prefix arrays out0/out1 + exchange of this rank's
 // totals + the event's totals (see kernels.cuh). phases: bit 0 = the scan (fused exchange included), bit 1 = what
 // follows it when the exchange is not fused (ncclAllGather, or the direct peer reads of the shard emulation).
-enum { PH_LOCAL = 1, PH_GLOBAL = 2, PH_ALL = 3 };
+// Every exchange of per-rank scalars separates two phases; the multinomial scheme has one (PH_LOCAL | PH_GLOBAL), the
+// residual scheme three (weights totals; copy and fraction totals; gap totals): PH_LOCAL, PH_R1, PH_R2, PH_GLOBAL.
+enum { PH_LOCAL = 1, PH_R1 = 2, PH_R2 = 4, PH_GLOBAL = 8, PH_ALL = 15 };
 static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint64_t* in1, uint64_t* out0, uint64_t* out1, int what, int conditional,
-                       int phases = PH_ALL) {
+                       bool do_local = true, bool do_global = true) {
   const bool multi = f->nranks > 1;
   const int xm = xmode(f);
   const bool fused = multi && xm == XMODE_LL;
-  if (phases & PH_LOCAL) {
+  if (do_local) {
     ProfScope ps(f, cls);
     CK(launch_pdl(scan_segments_kernel, 1, 1024, 0, f->stream, in0, in1, out0, out1, f->n_segs, f->ds, what, f->cfg.seed, (uint64_t)f->N, conditional,
                   peer_scalars(f), f->rank, f->nranks, fused ? 1 : 0));
     CK(cudaGetLastError());
   }
-  if ((phases & PH_GLOBAL) && multi && !fused) {
+  if (do_global && multi && !fused) {
     if (xm == XMODE_LOCAL) {
       ProfScope ps(f, KC_OTHER);
-      peer_copy_kernel<<<1, 32, 0, f->stream>>>(peer_scalars(f), f->ds, f->rank, f->nranks, ((what & SCAN_Q) ? PEER_COPY_CDF : 0) | ((what & SCAN_E) ? PEER_COPY_GAP : 0), conditional);
+      peer_copy_kernel<<<1, 32, 0, f->stream>>>(peer_scalars(f), f->ds, f->rank, f->nranks,
+          ((what & SCAN_Q) ? PEER_COPY_CDF : 0) | ((what & SCAN_E) ? PEER_COPY_GAP : 0) | ((what & SCAN_RESID) ? PEER_COPY_DET : 0), conditional);
     } else {
       if (what & SCAN_Q) NK(g_nccl.AllGather((const char*)(f->ds->cdf_rank_total + f->rank), f->ds->cdf_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+      if (what & SCAN_RESID) NK(g_nccl.AllGather((const char*)(f->ds->frac_rank_total + f->rank), f->ds->frac_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
       if (what & SCAN_E) NK(g_nccl.AllGather((const char*)(f->ds->gap_rank_total + f->rank), f->ds->gap_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
+      if (what & SCAN_RESID) NK(g_nccl.AllGather((const char*)(f->ds->det_rank_total + f->rank), f->ds->det_rank_total, sizeof(uint64_t), NCCL_UINT8, f->comm, f->stream));
     }
     ProfScope ps(f, KC_OTHER);
     totals_kernel<<<1, 1024, 0, f->stream>>>(out0, out1, f->n_segs, f->ds, f->nranks, f->rank, f->cfg.seed, (uint64_t)f->N, what, conditional);
@@ -776,22 +791,25 @@ static int launch_scan(gsmc_filter* f, int cls, const uint64_t* in0, const uint6
 //   multinomial, Philox draws:         weights + group-gaps pass -> partition (scan and the ranks' exchange fused) -> search   (3 launches)
 //   exported uniforms (replay): weights pass -> scan -> iid search
 //   residual: + the copy counts / residual fractions pass and the deterministic copies
-// phases: PH_LOCAL = everything up to (and including) this rank's own totals, PH_GLOBAL = everything that needs the
-// other ranks' totals. A filter on its own runs both in one go; the shard emulation runs PH_LOCAL on every rank first.
+// phases: see PH_* above. A filter on its own runs all of them in one go; the shard emulation runs each phase on every
+// rank before the next one (a phase may read what the previous phase produced on ANY rank).
 template <typename Real>
 static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid, int phases) {
   const Real* lw = (const Real*)f->lw;
   const double scale = weight_scale(f);
   const int nt = f->n_tiles, ns = f->n_segs, st = f->seg_tiles;
   const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
+  const bool multi = f->nranks > 1;
   uint32_t* anc = anc_col(f, f->anc_slab, f->T + 1);
-  if (residual && f->nranks > 1) return fail(GSMC_E_UNSUPPORTED, "residual resampling is single-GPU in this version");
-  const uint64_t k_first = residual ? 0 : (uint64_t)f->first;
+  if (residual && multi && replay_iid) return fail(GSMC_E_UNSUPPORTED, "exported uniforms with residual resampling on a sharded filter");
+  // draws are indexed globally; rank r generates (and, multinomial scheme, owns the output slots of) draws [r n, (r+1) n)
+  const uint64_t k_first = (uint64_t)f->first;
   const bool fuse_spacings = !residual && !replay_iid;
   // the partition kernel scans the segment totals itself and, on a sharded filter, exchanges the ranks' totals
   // over the peer mailboxes; with GSMC_NCCL_SCALARS=1 (and in the shard emulation) the separate scan + gather path is used
-  const bool fuse_scan = fuse_spacings && (f->nranks == 1 || xmode(f) == XMODE_LL);
-  if (phases & PH_LOCAL) {
+  const bool fuse_scan = fuse_spacings && (!multi || xmode(f) == XMODE_LL);
+  const bool L = phases & PH_LOCAL, G = phases & PH_GLOBAL;
+  if (L) {
     // 1. integer weights -> segment-local CDF + segment totals (and, fused, the group gaps of the N sorted draws)
     if (fuse_spacings) {
       ProfScope ps(f, KC_SCAN);
@@ -805,20 +823,33 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid, i
     CK(cudaGetLastError());
   }
   // 2. segment prefixes and the totals of the event
-  if (fuse_spacings) { if (!fuse_scan) CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional, phases)); }
-  else CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, residual ? SCAN_Q : (SCAN_Q | SCAN_SET_DRAWS), conditional, phases));
-  if (!(phases & PH_GLOBAL)) return GSMC_OK;
+  if (fuse_spacings) { if (!fuse_scan) CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_e, SCAN_Q | SCAN_SET_DRAWS | SCAN_E, conditional, L, G)); }
+  else if (!residual) CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q | SCAN_SET_DRAWS, conditional, L, G));
+  else CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q, conditional, L, (phases & PH_R1) != 0));
   if (residual) {
-    { ProfScope ps(f, KC_OTHER); CK(launch_pdl(resid_scale_kernel, 1, 32, 0, f->stream, f->ds, (double)f->N)); }
-    { ProfScope ps(f, KC_SCAN);
-      CK(launch_pdl(resid_cdf_kernel<Real>, ns, GSMC_BLOCK, 0, f->stream, lw, f->n, scale, f->ds, f->cc, f->raw0, f->cdf, f->raw1, nt, st, conditional)); }
-    CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_b, SCAN_RESID, conditional));
-    { ProfScope ps(f, KC_SEARCH);
-      const int want = (int)((f->n_pad + GSMC_BLOCK - 1) / GSMC_BLOCK), wave = 8 * f->sm_count;
-      CK(launch_pdl(det_copies_kernel, want < wave ? want : wave, GSMC_BLOCK, 0, f->stream,
-          f->cc, f->seg_a, ns, st * GSMC_TILE, (int)f->n_pad, f->n, f->ds, anc, conditional)); }
-    CK(cudaGetLastError());
+    if (phases & PH_R1) {
+      { ProfScope ps(f, KC_OTHER); CK(launch_pdl(resid_scale_kernel, 1, 32, 0, f->stream, f->ds, (double)f->N)); }
+      { ProfScope ps(f, KC_SCAN);
+        CK(launch_pdl(resid_cdf_kernel<Real>, ns, GSMC_BLOCK, 0, f->stream, lw, f->n, scale, f->ds, f->cc, f->raw0, f->cdf, f->raw1, nt, st, conditional)); }
+    }
+    // copy and fraction totals of all ranks -> n_det, M, the total of the fractions
+    CKRC(launch_scan(f, KC_SCAN, f->raw0, f->raw1, f->seg_a, f->seg_b, SCAN_RESID, conditional, (phases & PH_R1) != 0, (phases & PH_R2) != 0));
+    if (phases & PH_R2) {
+      { ProfScope ps(f, KC_SEARCH);
+        const int want = (int)((f->n_pad + GSMC_BLOCK - 1) / GSMC_BLOCK), wave = 8 * f->sm_count;
+        CK(launch_pdl(det_copies_kernel, want < wave ? want : wave, GSMC_BLOCK, 0, f->stream,
+            f->cc, f->seg_a, ns, st * GSMC_TILE, (int)f->n_pad, f->n, f->N, f->rank, f->ds, make_anc_out(f, f->T + 1), conditional)); }
+      CK(cudaGetLastError());
+      if (!replay_iid) {
+        // the number of draws M is only known now: group gaps of this rank's share [r n, (r+1) n) of the M sorted draws
+        ProfScope ps(f, KC_SPACINGS);
+        CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, false, true>, ns, GSMC_BLOCK, 0, f->stream,
+            lw, f->n, scale, f->ds, (uint64_t*)nullptr, (uint64_t*)nullptr, f->cfg.seed, k_first, (uint64_t)0, f->gap, f->tile_e, f->raw1, nt, st, conditional));
+      }
+    }
+    if (!replay_iid) CKRC(launch_scan(f, KC_SPACINGS, f->raw1, nullptr, f->seg_e, nullptr, SCAN_E, conditional, (phases & PH_R2) != 0, G));
   }
+  if (!G) return GSMC_OK;
   const CdfView v = make_cdf_view(f, residual);
   if (replay_iid) {
     // one exported uniform per output slot (per multinomial draw in the residual scheme)
@@ -828,13 +859,6 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid, i
         v, f->ds, f->d_urep, 0, 0, 0, f->n, residual ? 1 : 0, anc, nullptr, conditional);
     f->urep_n = 0;
   } else {
-    if (residual) {
-      // the number of draws M is only known now: group gaps of the M sorted draws
-      { ProfScope ps(f, KC_SPACINGS);
-        CK(launch_pdl<PDL_WEIGHTS>(weights_kernel<Real, false, true>, ns, GSMC_BLOCK, 0, f->stream,
-            lw, f->n, scale, f->ds, (uint64_t*)nullptr, (uint64_t*)nullptr, f->cfg.seed, k_first, (uint64_t)0, f->gap, f->tile_e, f->raw1, nt, st, conditional)); }
-      CKRC(launch_scan(f, KC_SPACINGS, f->raw1, nullptr, f->seg_e, nullptr, SCAN_E, conditional));
-    }
     // 3. ancestors
     uint64_t* sp_q = residual ? f->seg_b : f->seg_a;
     { ProfScope ps(f, KC_SEARCH);
@@ -853,7 +877,14 @@ static int launch_resample_t(gsmc_filter* f, int conditional, bool replay_iid, i
       const uint32_t magic = st > 1 ? (uint32_t)(0x100000000ULL / (uint64_t)st) + 1u : 0u;
       ProfScope ps(f, KC_SEARCH);
       CK(launch_pdl<PDL_SEARCH>(search_sorted_kernel, grid, GSMC_BLOCK, GSMC_SEARCH_SMEM, f->stream,
-          v, k_first, f->ds, f->tile_e, f->gap, (uint32_t)st, magic, make_philox_keys(f->cfg.seed), f->win, anc, f->n, nt, residual ? 1 : 0, conditional, f->rank)); }
+          v, k_first, f->ds, f->tile_e, f->gap, (uint32_t)st, magic, make_philox_keys(f->cfg.seed), f->win, anc, f->n, nt, residual ? 1 : 0, conditional, f->rank,
+          make_anc_out(f, f->T + 1))); }
+    // sharded residual scheme: deterministic copies and draws were stored into the ranks that own the slots -- nobody
+    // gathers through its ancestor column before every rank's stores have landed
+    if (residual && multi && !f->group) {
+      ProfScope ps(f, KC_OTHER);
+      peer_fence_kernel<<<1, 32, 0, f->stream>>>(peer_scalars(f), f->ds, f->rank, f->nranks, conditional);
+    }
   }
   CK(cudaGetLastError());
   return GSMC_OK;
@@ -1269,7 +1300,7 @@ static int sample_unweighted_impl(gsmc_filter* f, uint64_t num_samples, int64_t*
           (const double*)f->lw, f->n, scale, f->ds, f->cdf, f->raw0, 0, 0, 0, nullptr, nullptr, nullptr, f->n_tiles, f->seg_tiles, 0); }
     CK(cudaGetLastError());
   }
-  CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q, 0, phases));
+  CKRC(launch_scan(f, KC_SCAN, f->raw0, nullptr, f->seg_a, nullptr, SCAN_Q, 0, (phases & PH_LOCAL) != 0, (phases & PH_GLOBAL) != 0));
   if (!(phases & PH_GLOBAL)) return GSMC_OK;
   const double* urep = f->urep_n ? f->d_urep : nullptr;
   { ProfScope ps(f, KC_SEARCH);
@@ -1389,7 +1420,7 @@ static int run_steps_graph(gsmc_filter* f, const double* obs, size_t n_steps, si
   static int env_all = getenv("GSMC_GRAPH") ? 1 : 0;
   const bool residual = f->cfg.resample_scheme == GSMC_RESAMPLE_RESIDUAL;
   if (env_off || (!residual && !env_all) || f->graph_disabled || f->profiling || f->group || (f->nranks > 1 && xmode(f) != XMODE_LL) || n_steps < 2 ||
-      model_obs_on_device(f->model) || (residual && f->nranks > 1)) return GSMC_OK;
+      model_obs_on_device(f->model) || false) return GSMC_OK;
   uint64_t key = 0xcbf29ce484222325ULL;
   const int64_t t0 = f->T;
   key = fnv1a(key, &t0, sizeof t0); key = fnv1a(key, &n_steps, sizeof n_steps); key = fnv1a(key, &n_obs, sizeof n_obs);
@@ -1549,8 +1580,8 @@ GSMC_API int gsmc_group_maybe_resample(gsmc_group g, double ess_threshold, int* 
   const int R = g->nranks;
   for (int r = 0; r < R; ++r) CKRC(launch_finalize(g->member[r], ess_threshold, true));
   if (!replay) {
-    for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 1, false, PH_LOCAL));
-    for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 1, false, PH_GLOBAL));
+    for (int ph = PH_LOCAL; ph <= PH_GLOBAL; ph <<= 1)
+      for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 1, false, ph));
   }
   int did = 0;
   for (int r = 0; r < R; ++r) {
@@ -1563,8 +1594,8 @@ GSMC_API int gsmc_group_maybe_resample(gsmc_group g, double ess_threshold, int* 
   }
   if (did) {
     if (replay) {
-      for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 0, true, PH_LOCAL));
-      for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 0, true, PH_GLOBAL));
+      for (int ph = PH_LOCAL; ph <= PH_GLOBAL; ph <<= 1)
+        for (int r = 0; r < R; ++r) CKRC(launch_resample(g->member[r], 0, true, ph));
     }
     for (int r = 0; r < R; ++r) { g->member[r]->pending = true; g->member[r]->last_resample_step = g->member[r]->T + 1; }
   }

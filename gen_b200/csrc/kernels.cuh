@@ -74,6 +74,9 @@ struct DevScalars {
   LseTriple triples[GSMC_MAX_RANKS];
   uint64_t cdf_rank_total[GSMC_MAX_RANKS];      // per-rank integer weight totals (allgathered)
   uint64_t gap_rank_total[GSMC_MAX_RANKS];      // per-rank totals of the group gaps (allgathered)
+  uint64_t det_rank_total[GSMC_MAX_RANKS];      // residual scheme: per-rank totals of the deterministic copies (allgathered)
+  uint64_t frac_rank_total[GSMC_MAX_RANKS];     // residual scheme: per-rank totals of the residual fractions (allgathered; they
+                                                // replace cdf_rank_total once every rank's are known)
   // Sequence number of the peer exchanges, kept ON THE DEVICE (identical on every rank: all ranks run the same
   // exchanges in the same order), so that a captured / replayed launch sequence never reuses a tag. The exchange of the
   // logsumexp triples (and every other one-block exchange) advances it by 2 and uses the new value; the exchange of the
@@ -93,6 +96,14 @@ struct DevScalars {
 // skips (the logsumexp triples), so a rank is never more than two exchanges ahead of a peer that has not read
 // its words yet. The spin is bounded (~2 s) so a lost peer cannot hang the GPU.
 struct PeerScalars { DevScalars* ds[GSMC_MAX_RANKS]; };
+// Output column of a resampling event on every rank (peer-mapped): the sharded residual scheme stores ancestors into the
+// rank that owns the output slot.
+struct AncOut { uint32_t* col[GSMC_MAX_RANKS]; int64_t n_per; int nranks; };
+__device__ __forceinline__ void anc_store(const AncOut& a, uint64_t slot, uint32_t word) {
+  if (a.nranks == 1) { a.col[0][slot] = word; return; }
+  const uint64_t r = slot / (uint64_t)a.n_per;
+  a.col[r][slot - r * (uint64_t)a.n_per] = word;
+}
 __device__ __forceinline__ void ll_send(DevScalars* peer, int my_rank, uint32_t seq, const uint32_t* words, int n) {
   volatile unsigned long long* box = peer->mbox[seq & 3][my_rank];
   for (int w = 0; w < n; ++w) box[w] = (unsigned long long)words[w] | ((unsigned long long)seq << 32);
@@ -446,7 +457,8 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
       DrawCtx c0, c1;
       c0.seed = c1.seed = g.seed; c0.t = c1.t = g.t;
       c0.global_index = g.first_global + (uint64_t)i; c1.global_index = c0.global_index + 1;
-      c0.urep = g.urep ? g.urep + i * nu_rt : nullptr; c1.urep = g.urep ? g.urep + (i + 1) * nu_rt : nullptr;
+      // pad lanes (i >= n) have no replayed values: they draw from Philox like everybody else (results are discarded)
+      c0.urep = (g.urep && i < g.n) ? g.urep + i * nu_rt : nullptr; c1.urep = (g.urep && i + 1 < g.n) ? g.urep + (i + 1) * nu_rt : nullptr;
       w0 = Model::template particle_ctx<INIT, PROP>(a, dyn_sm, prev[2 * u], zz[u], c0, out0);
       w1 = Model::template particle_ctx<INIT, PROP>(a, dyn_sm, prev[2 * u + 1], zz[u] + NZ, c1, out1);
     } else {
@@ -631,8 +643,21 @@ __global__ void peer_barrier_kernel(PeerScalars peers, DevScalars* ds, int rank,
   __syncthreads();
   ll_allgather_u64(peers, ds, rank, nranks, s_seq, mine, 1, got);
 }
+// the same inside a stream of conditional kernels: the stores every rank issued before it (system-wide fence) are visible
+// to every rank after it; skipped by everybody when no resample was decided (the sequence number then does not advance)
+__global__ void peer_fence_kernel(PeerScalars peers, DevScalars* ds, int rank, int nranks, int conditional) {
+  __shared__ uint64_t mine[1];
+  __shared__ uint64_t got[GSMC_MAX_RANKS];
+  __shared__ uint32_t s_seq;
+  pdl_wait();
+  if (conditional && !ds->do_resample) return;
+  if (threadIdx.x == 0) { __threadfence_system(); s_seq = (ds->xseq += 2); mine[0] = s_seq; }
+  __syncthreads();
+  ll_allgather_u64(peers, ds, rank, nranks, s_seq, mine, 1, got);
+  __threadfence_system();
+}
 // shard emulation (XMODE_LOCAL): copy the peers' own entries of the per-rank scalars into this rank's arrays
-enum { PEER_COPY_TRIPLES = 1, PEER_COPY_CDF = 2, PEER_COPY_GAP = 4 };
+enum { PEER_COPY_TRIPLES = 1, PEER_COPY_CDF = 2, PEER_COPY_GAP = 4, PEER_COPY_DET = 8 };
 __global__ void peer_copy_kernel(PeerScalars peers, DevScalars* ds, int rank, int nranks, int what, int conditional) {
   if (conditional && !ds->do_resample) return;
   const int r = threadIdx.x;
@@ -640,6 +665,7 @@ __global__ void peer_copy_kernel(PeerScalars peers, DevScalars* ds, int rank, in
   if (what & PEER_COPY_TRIPLES) ds->triples[r] = peers.ds[r]->triples[r];
   if (what & PEER_COPY_CDF) ds->cdf_rank_total[r] = peers.ds[r]->cdf_rank_total[r];
   if (what & PEER_COPY_GAP) ds->gap_rank_total[r] = peers.ds[r]->gap_rank_total[r];
+  if (what & PEER_COPY_DET) { ds->det_rank_total[r] = peers.ds[r]->det_rank_total[r]; ds->frac_rank_total[r] = peers.ds[r]->frac_rank_total[r]; }
 }
 
 // multi-rank: runs after the allgather of ds->triples
@@ -805,14 +831,16 @@ enum { SCAN_Q = 1, SCAN_SET_DRAWS = 2, SCAN_E = 4, SCAN_RESID = 8 };
 // Totals of a resampling event once every rank's totals are known (thread 0 of one block):
 //   SCAN_Q      cdf_total = sum of the ranks' integer weight totals  [SCAN_SET_DRAWS: M = N draws, no copies]
 //   SCAN_E      S_tot = head gap + all ranks' gap totals, and the threshold ratio
-//   SCAN_RESID  (single rank) n_det = sum c, M = N - n_det, cdf_total = sum of the residual fractions
+//   SCAN_RESID  n_det = sum c over all ranks, M = N - n_det, cdf_total = sum of the residual fractions
 __device__ __forceinline__ void finish_totals(DevScalars* ds, int nranks, uint64_t seed, uint64_t n_global, int what,
                                               uint64_t total0, uint64_t total1) {
   if (what & SCAN_RESID) {
-    ds->n_det = total0;
-    ds->n_draws = n_global - total0;
-    ds->cdf_total = total1;
-    ds->cdf_rank_total[0] = total1;
+    if (nranks == 1) { ds->det_rank_total[0] = total0; ds->frac_rank_total[0] = total1; }
+    uint64_t d = 0, c = 0;
+    for (int r = 0; r < nranks; ++r) { d += ds->det_rank_total[r]; c += ds->frac_rank_total[r]; ds->cdf_rank_total[r] = ds->frac_rank_total[r]; }
+    ds->n_det = d;
+    ds->n_draws = n_global - d;
+    ds->cdf_total = c;
   }
   if (what & SCAN_Q) {
     uint64_t s = 0;
@@ -882,7 +910,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
   pdl_wait();
   pdl_trigger();
   const bool skip = conditional && !ds->do_resample;
-  const int n64 = ((what & SCAN_Q) ? 1 : 0) + ((what & SCAN_E) ? 1 : 0);
+  const int n64 = (what & SCAN_RESID) ? 2 : ((what & SCAN_Q) ? 1 : 0) + ((what & SCAN_E) ? 1 : 0);
   uint64_t totals[2] = {0, 0};
   if (!skip) scan_segments_block(in0, in1, n_segs, out0, out1, sm, totals);
   __threadfence_system();                            // the (rank-local) prefixes are visible to the peers before the totals are sent
@@ -891,6 +919,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
     int k = 0;
     if (what & SCAN_Q) { ds->cdf_rank_total[rank] = totals[0]; mine[k++] = totals[0]; }
     if (what & SCAN_E) { const uint64_t t = (what & SCAN_Q) ? totals[1] : totals[0]; ds->gap_rank_total[rank] = t; mine[k++] = t; }
+    if (what & SCAN_RESID) { ds->det_rank_total[rank] = totals[0]; ds->frac_rank_total[rank] = totals[1]; mine[0] = totals[0]; mine[1] = totals[1]; }
     if (nranks > 1 && exchange && n64) s_seq = (ds->xseq += 2);
   }
   __syncthreads();
@@ -904,6 +933,7 @@ __global__ void __launch_bounds__(1024) scan_segments_kernel(const uint64_t* in0
         int k = 0;
         if (what & SCAN_Q) ds->cdf_rank_total[r] = got[r * n64 + k++];
         if (what & SCAN_E) ds->gap_rank_total[r] = got[r * n64 + k++];
+        if (what & SCAN_RESID) { ds->det_rank_total[r] = got[r * n64]; ds->frac_rank_total[r] = got[r * n64 + 1]; }
       }
     }
   }
@@ -1261,7 +1291,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
                                                                       const uint64_t* tile_e, const uint64_t* gap, uint32_t seg_tiles,
                                                                       uint32_t seg_magic, const PhiloxKeys keys, const uint32_t* win,
                                                                       uint32_t* anc, int64_t n_out, int nt, int det_offset,
-                                                                      int conditional, int rank) {
+                                                                      int conditional, int rank, AncOut anc_all) {
   extern __shared__ __align__(16) uint64_t cwin[];                 // GSMC_WIN_CAP + 4
   __shared__ uint64_t mbar;
   __shared__ int s_pos[GSMC_GPT + 1];                              // window positions of the order statistics that bracket the tile's groups
@@ -1414,14 +1444,21 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
       for (int j = 0; j < GSMC_SEARCH_TPT; ++j)
         a[j] = draw_global(v, ds, (uint32_t)br, (j == 0 && lane == 0) ? (uint32_t)br : (uint32_t)(br >> 32), TL_abs, r32, wd[j]);
     }
-    // output slot of draw k: (k - k_first) [+ n_det for the residual scheme]
-    const int64_t o = o_local + (det_offset ? (int64_t)ds->n_det : 0);
-    if (!det_offset && k + GSMC_SEARCH_TPT <= m_draws && o + GSMC_SEARCH_TPT <= n_out) {
-      *reinterpret_cast<uint4*>(anc + o) = make_uint4(a[0], a[1], a[2], a[3]);
-      *reinterpret_cast<uint4*>(anc + o + 4) = make_uint4(a[4], a[5], a[6], a[7]);
-    } else {
+    // output slot of draw k: k - k_first (multinomial: this rank's own slots); residual scheme: GLOBAL slot n_det + k,
+    // stored into the rank that owns it
+    if (!det_offset) {
+      const int64_t o = o_local;
+      if (k + GSMC_SEARCH_TPT <= m_draws && o + GSMC_SEARCH_TPT <= n_out) {
+        *reinterpret_cast<uint4*>(anc + o) = make_uint4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<uint4*>(anc + o + 4) = make_uint4(a[4], a[5], a[6], a[7]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (k + j < m_draws && o + j < n_out) anc[o + j] = a[j];
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (k + j < m_draws && o + j < n_out) anc[o + j] = a[j];
+      }
+    } else {
+      const uint64_t og = ds->n_det + k;
+#pragma unroll
+      for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (k + j < m_draws) anc_store(anc_all, og + j, a[j]);
     }
     __syncthreads();                                     // everybody is done with the window before the next tile's copy lands
   }
@@ -1452,33 +1489,38 @@ __global__ void __launch_bounds__(GSMC_BLOCK) search_iid_kernel(CdfView v, const
 // segment prefix + segment-local inclusive count). A scatter: one thread per particle writes its own c_i = floor(N p_i)
 // copies (usually 0..2, neighbouring threads write neighbouring slots); a particle with 32 or more copies is written by
 // its whole warp. Same result as searching min{i : Cc_i > o} for every slot o.
+// Sharded filter: the copies of rank r's particles start at global slot D_r = copies of the lower ranks, and a slot is
+// stored into the ancestor column of the rank that owns it (peer memory); the word names the owner rank of the particle.
 __global__ void __launch_bounds__(GSMC_BLOCK) det_copies_kernel(const uint64_t* cc, const uint64_t* seg_c, int n_segs, int seg_len, int n_pad,
-                                                                int64_t n, const DevScalars* ds, uint32_t* anc, int conditional) {
+                                                                int64_t n, int64_t n_global, int rank, const DevScalars* ds, AncOut anc, int conditional) {
   pdl_wait();
   pdl_trigger();
   if (conditional && !ds->do_resample) return;
   const int lane = threadIdx.x & 31;
+  uint64_t rank_off = 0;
+  for (int q = 0; q < rank; ++q) rank_off += ds->det_rank_total[q];
+  const uint32_t rank_word = (uint32_t)rank << GSMC_ANC_RANK_SHIFT;
   for (int64_t base = ((int64_t)blockIdx.x * GSMC_BLOCK + threadIdx.x) & ~(int64_t)31; base < n_pad; base += (int64_t)gridDim.x * GSMC_BLOCK) {
     const int64_t i = base + lane;                       // a warp covers 32 consecutive particles of ONE segment
     const int seg = (int)(base / seg_len);
-    const uint64_t off = __ldg(seg_c + seg);
+    const uint64_t off = rank_off + __ldg(seg_c + seg);
     const uint64_t incl = (i < n) ? __ldg(cc + i) : 0;
     uint64_t prev = shfl_up_u64(incl, 1);
     if (lane == 0) prev = (base % seg_len == 0) ? 0 : __ldg(cc + base - 1);
     uint64_t first = off + prev;
     uint64_t cnt = (i < n) ? incl - prev : 0;
-    if (first >= (uint64_t)n) cnt = 0;
-    else if (first + cnt > (uint64_t)n) cnt = (uint64_t)n - first;       // never more than N slots
+    if (first >= (uint64_t)n_global) cnt = 0;
+    else if (first + cnt > (uint64_t)n_global) cnt = (uint64_t)n_global - first;       // never more than N slots
     const bool big = cnt >= 32;
-    if (!big) for (uint64_t j = 0; j < cnt; ++j) anc[first + j] = (uint32_t)i;
+    if (!big) for (uint64_t j = 0; j < cnt; ++j) anc_store(anc, first + j, rank_word | (uint32_t)i);
     unsigned mask = __ballot_sync(0xffffffffu, big);
     while (mask) {
       const int src = __ffs((int)mask) - 1;
       mask &= mask - 1;
       const uint64_t f0 = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)first, src);
       const uint64_t c0 = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)cnt, src);
-      const uint32_t who = (uint32_t)(base + src);
-      for (uint64_t j = lane; j < c0; j += 32) anc[f0 + j] = who;
+      const uint32_t who = rank_word | (uint32_t)(base + src);
+      for (uint64_t j = lane; j < c0; j += 32) anc_store(anc, f0 + j, who);
     }
   }
 }

@@ -1,10 +1,13 @@
+# kernel-parameter sweep: every variants/*.so (built with other -DGSMC_* values) through the bench
 mkdir -p gpurun_out
+cp gen_b200/libgensmc.so /tmp/head.so
 for v in variants/*.so; do
   cp $v gen_b200/libgensmc.so
-  python bench.py --no-cpu-baseline --steps 5 --warmup 3 > gpurun_out/var.json 2>/dev/null
+  python bench.py --no-cpu-baseline --steps 8 --warmup 3 > gpurun_out/var.json 2>/dev/null
   python - <<PY
 import json
 d=json.load(open('gpurun_out/var.json')); k=d['kernel_ms_profile_pass']
-print("$v", round(d['ms_per_step'],2), 'search', round(k['search'],2), 'scan', round(k['scan'],2), 'spac', round(k['spacings'],2), 'prop', round(k['propagate']+k['propagate_gather'],2), 'lml', d['log_ml'])
+print("$v", round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), 'search', round(k['search'],2), 'scan', round(k['scan'],2), 'prop', round(k['propagate'],2), round(k['propagate_gather'],2), 'lml', d['log_ml'])
 PY
 done
+cp /tmp/head.so gen_b200/libgensmc.so

@@ -35,18 +35,22 @@ def main():
     SVP = [-1.0, 0.97, 0.2]
     big = int(os.environ.get("GSMC_MGPU_BIG_LOG2", "20"))          # particles per rank of the large cases
     cases = [
-        (O.LGSSM, g.LinearGaussianSSM(*LG), LG, cf.simulate_lgssm(16, LG, 3), 0, 1024 * 16, 12, 0.8),
-        (O.BEARINGS, g.BearingsOnly(), cf.BEARINGS_PARAMS, cf.simulate_bearings(16), 1, 1024 * 16, 12, 0.8),
-        (O.SV, g.StochasticVolatility(*SVP), SVP, cf.simulate_sv(16, SVP, 0), 0, 1024 * 16, 12, 0.8),
-        (O.HMM, g.HMM(cf.HMM_PRIOR, cf.HMM_EMISSION, cf.HMM_TRANSITION), list(cf.hmm_params()), np.array(cf.HMM_OBS * 4, dtype=float), 0, 1024 * 16, 12, 0.8),
+        (O.LGSSM, g.LinearGaussianSSM(*LG), LG, cf.simulate_lgssm(16, LG, 3), 0, 1024 * 16, 12, 0.8, "multinomial"),
+        (O.BEARINGS, g.BearingsOnly(), cf.BEARINGS_PARAMS, cf.simulate_bearings(16), 1, 1024 * 16, 12, 0.8, "multinomial"),
+        (O.SV, g.StochasticVolatility(*SVP), SVP, cf.simulate_sv(16, SVP, 0), 0, 1024 * 16, 12, 0.8, "multinomial"),
+        (O.HMM, g.HMM(cf.HMM_PRIOR, cf.HMM_EMISSION, cf.HMM_TRANSITION), list(cf.hmm_params()), np.array(cf.HMM_OBS * 4, dtype=float), 0, 1024 * 16, 12, 0.8, "multinomial"),
         # 2^20 particles per rank: many tiles per segment, windows across segment and rank boundaries, skewed weights
-        (O.LGSSM, g.LinearGaussianSSM(*LG), LG, cf.simulate_lgssm(16, LG, 3), 0, 1 << big, 7, 0.4),
+        (O.LGSSM, g.LinearGaussianSSM(*LG), LG, cf.simulate_lgssm(16, LG, 3), 0, 1 << big, 7, 0.4, "multinomial"),
         # the cfg-5 shape (bearings-only, custom proposal, D = 4 rows gathered across shard boundaries) at 2^18 per rank
-        (O.BEARINGS, g.BearingsOnly(), cf.BEARINGS_PARAMS, cf.simulate_bearings(16), 1, 1 << (big - 2), 7, 0.5),
+        (O.BEARINGS, g.BearingsOnly(), cf.BEARINGS_PARAMS, cf.simulate_bearings(16), 1, 1 << (big - 2), 7, 0.5, "multinomial"),
+        # residual resampling on a sharded filter (the cfg-4 shape): copies and draws are stored into the rank that owns the slot
+        (O.SV, g.StochasticVolatility(*SVP), SVP, cf.simulate_sv(16, SVP, 0), 0, 1024 * 16, 12, 0.8, "residual"),
+        (O.LGSSM, g.LinearGaussianSSM(*LG), LG, cf.simulate_lgssm(16, LG, 3), 0, 1 << (big - 1), 7, 0.4, "residual"),
     ]
-    for fam, model, params, ys, prop, n_per, T, thr in cases:
+    for fam, model, params, ys, prop, n_per, T, thr, scheme in cases:
         N = n_per * world
-        st = g.ParticleFilterState(model, N, seed=5, keep_history=True, history_capacity=T, device=local, comm=comm)
+        oscheme = 1 if scheme == "residual" else 0
+        st = g.ParticleFilterState(model, N, seed=5, resample=scheme, keep_history=True, history_capacity=T, device=local, comm=comm)
         n, first = st.num_local, st.first_global
         assert n == N // world and first == rank * n
         pf = orc.particle_filter(fam, params, N, seed=5, keep_history=True)
@@ -58,7 +62,7 @@ def main():
         same(st.state(), pf.state()[:, sl], "init state")
         n_res = 0
         for t in range(1, T):
-            dg, do = st.maybe_resample(N * thr), pf.maybe_resample(N * thr)
+            dg, do = st.maybe_resample(N * thr), pf.maybe_resample(N * thr, scheme=oscheme)
             assert dg == do, (t, st.last_ess, pf.last_ess)
             assert abs(st.last_ess - pf.last_ess) <= 1e-10 * pf.last_ess
             if dg:
@@ -86,7 +90,7 @@ def main():
         trs = g.sample_unweighted_traces(st, 7)
         assert len(trs) == 7
         # the sync-free loop gives the same answer
-        st2 = g.ParticleFilterState(model, N, seed=5, keep_history=False, device=local, comm=comm)
+        st2 = g.ParticleFilterState(model, N, seed=5, resample=scheme, keep_history=False, device=local, comm=comm)
         st2.init([ys[0]], proposal)
         st2.run_steps(ys[1:T], N * thr, proposal)
         assert st2.log_ml_estimate() == a
@@ -95,7 +99,7 @@ def main():
         st2.close()
         dist.barrier()
         if rank == 0:
-            print("family %d (N = %d x %d, T = %d) ok on %d ranks: log_ml %.12f, %d resamples" % (fam, world, n_per, T, world, a, n_res), flush=True)
+            print("family %d %s (N = %d x %d, T = %d) ok on %d ranks: log_ml %.12f, %d resamples" % (fam, scheme, world, n_per, T, world, a, n_res), flush=True)
     comm.close()
     dist.destroy_process_group()
 

@@ -28,7 +28,7 @@ def test_sharded_filter_matches_oracle(world):
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mgpu_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert res.stdout.count(" ok on %d ranks" % world) == 6, res.stdout[-2000:]
+    assert res.stdout.count(" ok on %d ranks" % world) == 8, res.stdout[-2000:]
 
 
 @pytest.mark.gpu
@@ -40,7 +40,7 @@ def test_sharded_filter_with_nccl_scalar_exchanges():
            "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tests", "mgpu_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, GSMC_NCCL_SCALARS="1", GSMC_MGPU_BIG_LOG2="16"))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert res.stdout.count(" ok on 2 ranks") == 6, res.stdout[-2000:]
+    assert res.stdout.count(" ok on 2 ranks") == 8, res.stdout[-2000:]
 
 
 def _gloo_worker(rank, world, port, N, T, ret):

@@ -30,10 +30,11 @@ def families():
     }
 
 
-def run_group(orc, fam, model, params, ys, prop, world, n_per, T, thr_frac, dtype="f64", skew=None):
+def run_group(orc, fam, model, params, ys, prop, world, n_per, T, thr_frac, dtype="f64", scheme="multinomial"):
     N = n_per * world
+    oscheme = 1 if scheme == "residual" else 0
     grp = LocalShardGroup(world)
-    shards = [g.ParticleFilterState(model, N, seed=5, dtype=dtype, keep_history=True, history_capacity=T, comm=grp.rank(r)) for r in range(world)]
+    shards = [g.ParticleFilterState(model, N, seed=5, dtype=dtype, resample=scheme, keep_history=True, history_capacity=T, comm=grp.rank(r)) for r in range(world)]
     pf = orc.particle_filter(fam, params, N, seed=5, keep_history=True)
     proposal = model.custom_proposal() if prop else None
     for r, st in enumerate(shards):
@@ -46,7 +47,7 @@ def run_group(orc, fam, model, params, ys, prop, world, n_per, T, thr_frac, dtyp
         assert np.array_equal(bits(st.state()), bits(pf.state()[:, sl]))
     n_res, remote = 0, 0
     for t in range(1, T):
-        dg, do = grp.maybe_resample(N * thr_frac), pf.maybe_resample(N * thr_frac)
+        dg, do = grp.maybe_resample(N * thr_frac), pf.maybe_resample(N * thr_frac, scheme=oscheme)
         assert dg == do, (t, shards[0].last_ess, pf.last_ess)
         assert abs(shards[0].last_ess - pf.last_ess) <= 1e-10 * pf.last_ess
         if dg:
@@ -87,6 +88,24 @@ def test_emulated_shards_match_oracle(orc, world, family):
     tr = shards[world - 1].trajectories(ig[:64])
     for t in (1, T // 2, T):
         assert np.array_equal(bits(tr[:, t - 1, :].T), bits(pf.history(t)[:, io[:64]]))
+    grp.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("family", ["sv", "lgssm", "bearings"])
+def test_emulated_shards_residual_resampling(orc, world, family):
+    """Residual resampling on a sharded filter (BASELINE.json configs[3] names the scheme): the deterministic copies of a
+    rank's particles and its share of the multinomial draws land in output slots that other ranks own."""
+    fam, model, params, ys, prop = families()[family]
+    grp, shards, pf, n_res, remote = run_group(orc, fam, model, params, ys, prop, world, 2048 * 4, 12, 0.8, scheme="residual")
+    assert n_res >= 2 and remote > 0
+    grp.close()
+
+
+def test_emulated_shards_residual_large(orc):
+    fam, model, params, ys, prop = families()["lgssm"]
+    grp, shards, pf, n_res, remote = run_group(orc, fam, model, params, cf.simulate_lgssm(8, LG, 3), prop, 4, 1 << 19, 8, 0.4, scheme="residual")
+    assert n_res >= 1 and remote > 0
     grp.close()
 
 
