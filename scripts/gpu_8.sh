@@ -14,3 +14,4 @@ for f in ('gpurun_out/${TAG}_bench_${N}gpu.json', 'gpurun_out/${TAG}_bench_cfg5_
             d=json.loads(line); print({k:d[k] for k in ('n_gpus','value','ms_per_step','log_ml','log_ml_e2e','gpu_launches')}); print('e2e',d['e2e']['value'],d['e2e']['ms_per_step'], 'roofline', d['roofline']['frac'], d['roofline_whole_run']['frac']); print(d['kernel_ms_profile_pass']); print(d.get('nvlink'))
 PY
 grep -v "^W\|^\[W\|^$\|\*\*\*\|OMP_NUM" gpurun_out/${TAG}_bench_cfg5_${N}gpu.err | tail -5
+timeout 300 $RUN --master-port 29515 scripts/mgpu_breakdown.py 2>&1 | grep "^R=" | tee gpurun_out/${TAG}_breakdown_${N}gpu.txt
