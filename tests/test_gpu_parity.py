@@ -833,3 +833,51 @@ def test_cfg4_full_length_agreement(gpu):
     other, _ = run(1 << 22, 1)
     quarter, _ = run(1 << 20, 2)
     assert abs(big[0][0] - other[0][0]) < 0.05 and abs(big[0][0] - quarter[0][0]) < 0.1, (big[0], other[0], quarter[0])
+
+
+def test_baseline_configs_at_full_size(gpu):
+    """BASELINE.json configs 2, 3 and 5 (one GPU's shard) at their full sizes, where the oracle is too slow: size-independent
+    properties. cfg 3: log-ML within Monte-Carlo error of the Kalman filter, bit-reproducible, ancestors of the last
+    resample in group order with every slot filled; cfg 2: 10^7 importance samples, normalised weights sum to one, log-ML
+    near the conjugate closed form; cfg 5 shape: two independent 2^22-particle runs agree."""
+    g = gpu
+    # cfg 3: 1-D LG-SSM, T = 100, N = 2^24
+    N, T = 1 << 24, 100
+    model = g.LinearGaussianSSM(*LG)
+    ys = cf.simulate_lgssm(T, LG, 0)
+    st = g.ParticleFilterState(model, N, seed=0, keep_history=True, history_capacity=T)
+    vals = []
+    for rep in range(2):
+        st.reset()
+        st.init([ys[0]])
+        st.run_steps(ys[1:], N / 2)
+        vals.append((st.log_ml_estimate(), st.stats()["num_resamples"]))
+    assert vals[0] == vals[1] and 30 <= vals[0][1] <= 80
+    assert vals[0][0] == pytest.approx(cf.kalman_log_ml(ys, *LG), abs=0.01)
+    anc = st.ancestors()
+    assert anc.min() >= 0 and anc.max() < N and grouped_order(anc)
+    counts = np.bincount(anc, minlength=N)
+    assert counts.sum() == N and counts.max() < 64
+    x_last, x_mid = st.state(), st.state(T // 2)                   # history walk through ~50 ancestor columns at full size
+    assert np.isfinite(x_last).all() and np.isfinite(x_mid).all() and abs(float(x_mid.mean())) < 10
+    st.close()
+    # cfg 2: Bayesian linear regression, 10^7 samples
+    reg = g.LinearRegression()
+    obs = g.choicemap(*[("y-%d" % (i + 1), y) for i, y in enumerate(cf.QUICKSTART_YS)])
+    traces, lnw, lml = g.importance_sampling(reg, (cf.QUICKSTART_XS,), obs, 10 ** 7, seed=0)
+    m = lnw.max()
+    assert abs(m + math.log(np.exp(lnw - m).sum())) < 1e-9 and len(traces) == 10 ** 7
+    assert lml == pytest.approx(cf.QUICKSTART_LOG_ML, abs=0.1)
+    traces._state.close()
+    # cfg 5 shape: bearings-only, custom proposal, T = 200
+    bm = g.BearingsOnly()
+    yb = cf.simulate_bearings(200)
+    lm = []
+    for seed in (0, 1):
+        sb = g.ParticleFilterState(bm, 1 << 22, seed=seed, keep_history=False)
+        sb.init([yb[0]], bm.custom_proposal())
+        sb.run_steps(yb[1:], (1 << 22) / 2, bm.custom_proposal())
+        lm.append(sb.log_ml_estimate())
+        assert sb.stats()["num_resamples"] >= 5
+        sb.close()
+    assert abs(lm[0] - lm[1]) < 0.2, lm
