@@ -95,6 +95,15 @@ def main():
         st2.run_steps(ys[1:T], N * thr, proposal)
         assert st2.log_ml_estimate() == a
         assert np.array_equal(bits(st2.log_weights()), bits(st.log_weights()))
+        if scheme == "residual":
+            # a repeated run shape is captured into a CUDA graph (conditional node per step) on its second occurrence:
+            # every rank replays its own graph, the exchanges inside carry device-side sequence numbers
+            for rep in range(3):
+                st2.reset()
+                st2.init([ys[0]], proposal)
+                st2.run_steps(ys[1:T], N * thr, proposal)
+                assert st2.log_ml_estimate() == a and np.array_equal(bits(st2.log_weights()), bits(st.log_weights())), rep
+            assert st2.stats()["graph_replays"] == 2
         st.close()
         st2.close()
         dist.barrier()
