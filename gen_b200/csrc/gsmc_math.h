@@ -376,6 +376,101 @@ GM_HD double gm_log_unit(double x, const double* tab) {
   return l > 0.0 ? 0.0 : l;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 pieces of the Box-Muller transform behind the per-particle normal draws (gsmc_rng.cuh, normal_quad): the radius
+// and angle come from 32-bit Philox words, so the transform is evaluated in IEEE fp32 (+ - * fma sqrt and bit casts
+// only: the same bits on the host and on the device) and the two normals are widened to fp64 afterwards. All MODEL
+// arithmetic (transition, logpdf, logsumexp) stays in fp64; only the resolution of the random numbers is 32 bits,
+// as in cuRAND's Philox normal generator.
+//   gm_nlog_u32f(w)   = -ln((w + 1/2) 2^-32), w a 32-bit word: v = 2w + 1 = 2^n m (m in [1, 2), kept to 32 bits), so
+//                       -ln x = lz ln2 + [ln2 - ln m] with lz = 32 - n. The top 6 mantissa bits pick a centre c_i from
+//                       a 64-entry table {ic = fl(1/c_i), fl(ln(2 ic))}; r = m ic - 1 (|r| <= 2^-7), log1p(r) by three
+//                       terms (truncation < 1e-9), -ln x = fma(lz, ln2, ln(2 ic)) - log1p(r). Next to x = 1 the 24-bit
+//                       mantissa would quantise the result at 6e-8 absolute, so x > 1 - 2^-7 (0.8% of the words) goes
+//                       through the complement, -log1p(-(1 - x)). Relative error < 1e-5 everywhere (2e-7 typical).
+//   gm_sincos_u32f(a) = (sin, cos)(2 pi a 2^-32): a = 2^25 j + d, |d| <= 2^24 (exactly a float), table (S, C) =
+//                       (sin, cos)(pi j/64), x = d pi 2^-31 (|x| <= pi/128), sin x and cos x - 1 by two terms each and the
+//                       angle addition written around the table values (as gm_sincospi_t). Absolute error < 1e-7.
+// ------------------------------------------------------------------------------------------------
+static const float gm_logtabf_h[128] = GM_LOGTABF_VALUES;
+static const float gm_sincostabf_h[256] = GM_SINCOSTABF_VALUES;
+#if defined(__CUDACC__)
+static __device__ __align__(16) const float gm_logtabf_g[128] = GM_LOGTABF_VALUES;
+static __device__ __align__(16) const float gm_sincostabf_g[256] = GM_SINCOSTABF_VALUES;
+#endif
+#if defined(__CUDA_ARCH__)
+#define GM_LOGTABF gm_logtabf_g
+#define GM_SINCOSTABF gm_sincostabf_g
+#else
+#define GM_LOGTABF gm_logtabf_h
+#define GM_SINCOSTABF gm_sincostabf_h
+#endif
+GM_HD float gm_f32_from_bits(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(b);
+#else
+  float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+/* the two adjacent float table entries tab[2i], tab[2i+1] with one 8-byte load on the device */
+GM_HD void gm_tab_pairf(const float* tab, uint32_t i, float* a, float* b) {
+#if defined(__CUDA_ARCH__)
+  const float2 v = *reinterpret_cast<const float2*>(tab + 2 * i);
+  *a = v.x; *b = v.y;
+#else
+  *a = tab[2 * i]; *b = tab[2 * i + 1];
+#endif
+}
+GM_HD float gm_nlog_u32f(uint32_t w, const float* tab) {
+  if (w >= 0xfe000000u) {
+    /* x > 1 - 2^-7: the 24-bit mantissa of x would quantise -ln x at 6e-8 ABSOLUTE; the complement y = 1 - x =
+       (~w + 1/2) 2^-32 <= 2^-7 is (nearly) exact instead, -ln x = -log1p(-y) = y (1 + y/2 + y^2/3 + y^3/4) */
+    const float y = ((float)(~w) + 0.5f) * 2.32830644e-10f;
+    float q = fmaf(0.25f, y, 0.333333343f);
+    q = fmaf(q, y, 0.5f);
+    q = fmaf(q, y, 1.0f);
+    return q * y;
+  }
+  /* t = the top 32 bits (leading one included) of the 33-bit odd integer 2w + 1: m = t 2^-31 in [1, 2) */
+#if defined(__CUDA_ARCH__)
+  const int lz = __clz((int)w);                                   /* 32 for w = 0 */
+  const uint32_t t = __funnelshift_lc(0x80000000u, w, (uint32_t)lz);
+#else
+  const int lz = w ? __builtin_clz(w) : 32;
+  const uint32_t t = (uint32_t)(((2 * (uint64_t)w + 1) << lz) >> 1);
+#endif
+  const float m = gm_f32_from_bits(0x3f800000u | ((t >> 8) & 0x007fffffu));
+  float ic, t2;
+  gm_tab_pairf(tab, (t >> 25) & 63u, &ic, &t2);
+  const float r = fmaf(m, ic, -1.0f);
+  float q = fmaf(0.333333343f, r, -0.5f);
+  q = fmaf(q, r, 1.0f);
+  const float base = fmaf((float)lz, GM_LN2F, t2);
+  const float l = fmaf(-q, r, base);
+  return l < 0.0f ? 0.0f : l;
+}
+GM_HD void gm_sincos_u32f(uint32_t a, const float* tab, float* sn, float* cs) {
+  const uint32_t b = a + 0x01000000u;                              /* wraps with the full turn */
+  const int32_t d = (int32_t)(b & 0x01ffffffu) - 0x01000000;
+  const float x = (float)d * GM_PI_64_2M25F;
+  const float z = x * x;
+  const float sx = fmaf(x * z, -0.166666672f, x);                  /* sin x */
+  const float cm = z * fmaf(z, 0.0416666679f, -0.5f);              /* cos x - 1 */
+  float S, C;
+  gm_tab_pairf(tab, b >> 25, &S, &C);
+  *sn = S + fmaf(S, cm, C * sx);
+  *cs = C + fmaf(C, cm, -(S * sx));
+}
+/* two standard normals (cos branch, sin branch) from a radius word and an angle word */
+GM_HD void gm_box_muller_u32(uint32_t wr, uint32_t wa, const float* ltab, const float* sctab, double* z0, double* z1) {
+  const float l = gm_nlog_u32f(wr, ltab);
+  const float r = sqrtf(l + l);
+  float sn, cs;
+  gm_sincos_u32f(wa, sctab, &sn, &cs);
+  *z0 = (double)(r * cs);
+  *z1 = (double)(r * sn);
+}
+
 #if defined(__cplusplus)
 // ------------------------------------------------------------------------------------------------
 // Batch forms: K independent evaluations with the coefficient loop outside and the element loop

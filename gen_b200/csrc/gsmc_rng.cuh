@@ -9,12 +9,15 @@
 // Layout (shared with the oracle's independent restatement, oracle/gsmc_oracle.c):
 //   call c of (seed, t, stream)    = Philox(ctr = {lo32(c), hi32(c), t, stream}, key = {lo32(seed), hi32(seed)})
 //   word a = out0 | out1<<32, word b = out2 | out3<<32
-//   normals  (stream 0): element e -> call e>>1; Box-Muller u1=((a>>11)+.5)2^-53, u2=(b>>11)2^-53,
-//                        r=sqrt(-2 gm_log_unit(u1)); e even -> r cos(2 pi u2), e odd -> r sin(2 pi u2)
+//   normals  (stream 0): element e -> call e>>2, pair (e>>1)&1 of the call: radius word out[2 pair], angle word
+//                        out[2 pair + 1]; Box-Muller in fp32 on the 32-bit words (gsmc_math.h, gm_box_muller_u32):
+//                        r = sqrtf(-2 ln((wr+.5)2^-32)); e even -> r cos(2 pi wa 2^-32), e odd -> r sin(...); widened to
+//                        fp64. One call feeds FOUR consecutive elements (a thread owns quads of neighbouring particles).
 //   uniforms (stream 1,3): element e -> call e>>1; (e odd ? b : a)>>11 * 2^-53   in [0,1)
 //   resampling draws (stream 2): output slot k -> call k>>2, 32-bit word k&3 (out0..out3); u = (w+.5)2^-32 places
 //                        the draw inside its group's interval (see "grouped order statistics" below)
-//   observation choices of unobserved steps (stream 5): particle i -> element i (a normal, or a uniform for discrete emissions)
+//   observation choices of unobserved steps (stream 5): particle i -> element i (a normal by the 53-bit fp64 Box-Muller
+//                        below, normal_pair: element e -> call e>>1; or a uniform for discrete emissions)
 //   group gaps (stream 4): Marsaglia-Tsang Gamma variate of group j, attempt a: normal = cos branch of call
 //                        (j<<5 | 2a), uniform = ((word a of call (j<<5 | 2a+1)) >> 11 + .5) 2^-53
 // Particle i's j-th normal at a step that needs nz normals per particle is element i*nz + j.
@@ -69,7 +72,8 @@ __device__ __forceinline__ PhiloxOut philox_call(const PhiloxKeys& K, uint64_t c
   return o;
 }
 
-// two standard normals from one call
+// two standard normals from one call, 53-bit uniforms and fp64 Box-Muller: the Gamma gaps of the resampler (stream 4)
+// and the observation choices of unobserved steps (stream 5). The per-particle draws of the models use normal_quad.
 __host__ __device__ __forceinline__ void normal_pair(uint64_t seed, uint64_t call, uint32_t t, const double* ltab, double* z0, double* z1,
                                                       uint32_t stream = GSMC_STREAM_NORMAL) {
   const PhiloxOut o = philox_call(seed, call, t, stream);
@@ -150,25 +154,18 @@ __host__ __device__ __forceinline__ uint64_t threshold_u64(double x, double rati
   return T < cn ? T : cn - 1;
 }
 
-// Batch forms (same bits as the scalar functions, see gsmc_math.h "Batch forms").
-// K Philox calls -> 2K standard normals z[2m] (cos branch), z[2m+1] (sin branch)
+// four standard normals (elements 4 call .. 4 call + 3 of the step's virtual normal array) from one call
+template <class Key>
+__host__ __device__ __forceinline__ void normal_quad(const Key& seed, uint64_t call, uint32_t t, const float* ltab, const float* sctab, double* z) {
+  const PhiloxOut o = philox_call(seed, call, t, GSMC_STREAM_NORMAL);
+  gm_box_muller_u32((uint32_t)o.a, (uint32_t)(o.a >> 32), ltab, sctab, z, z + 1);
+  gm_box_muller_u32((uint32_t)o.b, (uint32_t)(o.b >> 32), ltab, sctab, z + 2, z + 3);
+}
+// K calls -> 4K standard normals, z[4m .. 4m+3] from calls[m] (same bits as normal_quad; the K independent
+// evaluations are written one after the other and interleaved by the compiler)
 template <int K, class Key>
-__host__ __device__ __forceinline__ void normal_pairs_v(const Key& seed, const uint64_t* calls, uint32_t t, const double* ltab, const double* sctab, double* z) {
-  double u1[K], t2[K], l[K], sn[K], cs[K];
+__device__ __forceinline__ void normal_quads_v(const Key& seed, const uint64_t* calls, uint32_t t, const float* ltab, const float* sctab, double* z) {
 #pragma unroll
-  for (int m = 0; m < K; ++m) {
-    const PhiloxOut o = philox_call(seed, calls[m], t, GSMC_STREAM_NORMAL);
-    u1[m] = ((double)(o.a >> 11) + 0.5) * 0x1p-53;
-    const double u2 = (double)(o.b >> 11) * 0x1p-53;
-    t2[m] = 2.0 * u2;
-  }
-  gm_log_unit_v<K>(u1, ltab, l);
-  gm_sincospi_v<K>(t2, sn, cs, sctab);
-#pragma unroll
-  for (int m = 0; m < K; ++m) {
-    const double r = sqrt(-2.0 * l[m]);
-    z[2 * m] = r * cs[m];
-    z[2 * m + 1] = r * sn[m];
-  }
+  for (int m = 0; m < K; ++m) normal_quad(seed, calls[m], t, ltab, sctab, z + 4 * m);
 }
 #endif

@@ -1,8 +1,9 @@
 // kernels.cuh -- hand-written sm_100a kernels of the SMC / importance-sampling hot path.
 //
 // All kernels are streaming passes over structure-of-arrays particle columns (no tensor cores: nothing here is a
-// dense contraction). One thread owns PAIRS of neighbouring particles so that every global access is a 16-byte vector
-// access, a warp touches 512 contiguous bytes per column, and one Philox call feeds both particles of a pair. The hot
+// dense contraction). In propagate one thread owns QUADS of neighbouring particles: every column access is a 32-byte
+// vector access (LDG/STG.256), a warp touches 1 KB contiguous per column, and one Philox call feeds the four particles of
+// a quad; the resampling kernels work on pairs / octets with 16- and 32-byte accesses. The hot
 // kernels are persistent (one resident wave of blocks looping over 2048-particle tiles) and are launched with
 // programmatic dependent launch (pdl_wait / pdl_trigger below).
 //
@@ -30,8 +31,8 @@
 #include "models.cuh"
 
 #define GSMC_BLOCK 256
-#ifndef GSMC_PROP_PAIRS
-#define GSMC_PROP_PAIRS 4
+#ifndef GSMC_PROP_QUADS
+#define GSMC_PROP_QUADS 2
 #endif
 #ifndef GSMC_PROP_OCC
 #define GSMC_PROP_OCC 3
@@ -194,16 +195,30 @@ __device__ __forceinline__ uint64_t block_scan_u64(uint64_t v, uint64_t* sm, uin
 // Shared-memory copies of the lookup tables of gsmc_math.h (lanes index them divergently), staged with
 // coalesced loads from their global-memory copies.
 struct __align__(16) SmemTabs {
-  double sincos[256];   // (sin, cos)(pi j/64)
-  double log64[128];    // gm_log_unit
   double exp2[64];      // 2^(j/64)
+  float sincosf[256];   // (sin, cos)(pi j/64), fp32 Box-Muller
+  float logf[128];      // gm_nlog_u32f
 };
 __device__ __forceinline__ void load_tabs(SmemTabs& t, bool normals) {
   for (int i = threadIdx.x; i < 64; i += blockDim.x) t.exp2[i] = gm_exp2tab_g[i];
   if (normals) {
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) t.log64[i] = gm_logtab64_g[i];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) t.sincos[i] = gm_sincostab_g[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) t.logf[i] = gm_logtabf_g[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) t.sincosf[i] = gm_sincostabf_g[i];
   }
+}
+// 32-byte vector accesses (sm_100: LDG/STG.256) of four consecutive column entries, widened to / narrowed from fp64
+__device__ __forceinline__ void load4(const double* p, double* o) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
+__device__ __forceinline__ void load4(const float* p, double* o) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = (double)v.x; o[1] = (double)v.y; o[2] = (double)v.z; o[3] = (double)v.w;
+}
+__device__ __forceinline__ void store4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void store4(float* p, double a, double b, double c, double d) {
+  *reinterpret_cast<float4*>(p) = make_float4((float)a, (float)b, (float)c, (float)d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -237,10 +252,11 @@ struct PropArgs {
   const double* urep;                // replay uniforms [n][nu] or NULL
 };
 
-// pairs of particles per thread: 4 (2048-particle tile) for 1-2 column models, 2 for wider states
+// quads of neighbouring particles per thread: 2 (2048-particle tile) for 1-2 column models, 1 for wider states. One
+// Philox call yields the four normals of four consecutive elements of the step's virtual normal array.
 template <class Model> struct PropTile {
-  static constexpr int PAIRS = Model::D <= 2 ? GSMC_PROP_PAIRS : 2;
-  static constexpr int TILE = 2 * GSMC_BLOCK * PAIRS;
+  static constexpr int QUADS = Model::D <= 2 ? GSMC_PROP_QUADS : 1;
+  static constexpr int TILE = 4 * GSMC_BLOCK * QUADS;
 };
 
 __device__ __forceinline__ LseTriple lse_merge(LseTriple a, LseTriple b) {
@@ -333,7 +349,7 @@ template <class Model, typename Real, bool INIT, int PROP>
 __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
   typedef typename Vec2T<Real>::type Real2;
   constexpr int D = Model::D;
-  constexpr int PAIRS = PropTile<Model>::PAIRS, NP = 2 * PAIRS, TILE = PropTile<Model>::TILE;
+  constexpr int QUADS = PropTile<Model>::QUADS, NP = 4 * QUADS, TILE = PropTile<Model>::TILE;
   constexpr int NZ = Model::nz(INIT, PROP), NU = Model::nu(INIT, PROP);
   constexpr int NZA = NZ > 0 ? NZ : 1, NUA = NU > 0 ? NU : 1;
   extern __shared__ double dyn_sm[];
@@ -349,44 +365,35 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
   pdl_trigger();
   const bool gather = !INIT && g.use_anc && (*g.resampled_flag != 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // Persistent blocks: block b handles tiles b, b + gridDim.x, ...; thread 0 carries the block's running
-  // (max, s1, s2) over its tiles, so one partial, one fence and one atomic per BLOCK (not per tile) are left.
+  // Persistent blocks: block b handles tiles b, b + gridDim.x, ...; every thread carries a running (max, s1, s2)
+  // over its own particles, so one block reduction, one partial, one fence and one atomic per BLOCK (not per tile) are left.
   LseTriple run; run.m = -gm_inf(); run.s1 = 0.0; run.s2 = 0.0;
+  double tm = -gm_inf(), t1 = 0.0, t2 = 0.0;
+  const bool unobserved = a.unobserved != 0;
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-  const int64_t tile0 = (int64_t)tile * TILE + 2 * threadIdx.x;
+  // particle j of this thread: quad q = j >> 2, position tile0 + q * 4 * GSMC_BLOCK + (j & 3)
+  const int64_t tile0 = (int64_t)tile * TILE + 4 * threadIdx.x;
   // Only the last tile can hold pad lanes (the columns are padded to the tile): they are loaded, computed and
   // stored like real particles (harmless garbage; the pad words of the ancestor columns are zero) and only
   // masked out of the logsumexp partial. `lim` = real particles of this tile, block-uniform.
   const int64_t lim64 = g.n - (int64_t)tile * TILE;
   const int lim = lim64 < TILE ? (int)lim64 : TILE;
 
-  // Stage A: previous state and log weights of all pairs (all loads in flight together).
+  // Stage A: previous state and log weights of all quads (all loads in flight together).
   double prev[NP][D], lwv[NP];
   if (!INIT) {
     if (gather) {
-      uint2 aw[PAIRS];
+      uint4 aw[QUADS];
 #pragma unroll
-      for (int u = 0; u < PAIRS; ++u) aw[u] = *reinterpret_cast<const uint2*>(g.anc + tile0 + (int64_t)u * 2 * GSMC_BLOCK);
-      if (g.nranks == 1) {
-        const Real* cur = g.cur[0];
+      for (int q = 0; q < QUADS; ++q) aw[q] = *reinterpret_cast<const uint4*>(g.anc + tile0 + (int64_t)q * 4 * GSMC_BLOCK);
 #pragma unroll
-        for (int u = 0; u < PAIRS; ++u) {
+      for (int q = 0; q < QUADS; ++q) {
+        const uint32_t w[4] = {aw[q].x, aw[q].y, aw[q].z, aw[q].w};
 #pragma unroll
-          for (int d = 0; d < D; ++d) {
-            prev[2 * u][d] = (double)__ldg(cur + d * g.stride + aw[u].x);
-            prev[2 * u + 1][d] = (double)__ldg(cur + d * g.stride + aw[u].y);
-          }
-        }
-      } else {
+        for (int k = 0; k < 4; ++k) {
+          const Real* c = (g.nranks == 1) ? g.cur[0] + w[k] : g.cur[w[k] >> GSMC_ANC_RANK_SHIFT] + (w[k] & GSMC_ANC_INDEX_MASK);
 #pragma unroll
-        for (int u = 0; u < PAIRS; ++u) {
-          const Real* c0 = g.cur[aw[u].x >> GSMC_ANC_RANK_SHIFT] + (aw[u].x & GSMC_ANC_INDEX_MASK);
-          const Real* c1 = g.cur[aw[u].y >> GSMC_ANC_RANK_SHIFT] + (aw[u].y & GSMC_ANC_INDEX_MASK);
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            prev[2 * u][d] = (double)__ldg(c0 + d * g.stride);
-            prev[2 * u + 1][d] = (double)__ldg(c1 + d * g.stride);
-          }
+          for (int d = 0; d < D; ++d) prev[4 * q + k][d] = (double)__ldg(c + d * g.stride);
         }
       }
 #pragma unroll
@@ -394,45 +401,46 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
     } else {
       const Real* cur = g.cur[g.rank];
 #pragma unroll
-      for (int u = 0; u < PAIRS; ++u) {
-        const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
+      for (int q = 0; q < QUADS; ++q) {
+        const int64_t i = tile0 + (int64_t)q * 4 * GSMC_BLOCK;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          const Real2 x = *reinterpret_cast<const Real2*>(cur + d * g.stride + i);
-          prev[2 * u][d] = (double)x.x; prev[2 * u + 1][d] = (double)x.y;
+          double x[4];
+          load4(cur + d * g.stride + i, x);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) prev[4 * q + k][d] = x[k];
         }
-        const Real2 l = *reinterpret_cast<const Real2*>(g.lw + i);
-        lwv[2 * u] = (double)l.x; lwv[2 * u + 1] = (double)l.y;
+        load4(g.lw + i, &lwv[4 * q]);
       }
     }
   }
 
-  // Stage B: draws. Pair u needs elements [(first_global+i)*NZ, +2NZ) of the step's virtual normal
-  // array = NZ Philox calls; all PAIRS*NZ Box-Muller transforms are evaluated as one batch.
-  double zz[PAIRS][2 * NZA], uu[PAIRS][2 * NUA];
+  // Stage B: draws. Quad q needs elements [(first_global+i)*NZ, +4NZ) of the step's virtual normal
+  // array = NZ Philox calls of four normals each.
+  double zz[QUADS][4 * NZA], uu[2 * QUADS][2 * NUA];
   if (NZ > 0) {
     if (g.zrep) {
 #pragma unroll
-      for (int u = 0; u < PAIRS; ++u) {
-        const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
+      for (int q = 0; q < QUADS; ++q) {
+        const int64_t i = tile0 + (int64_t)q * 4 * GSMC_BLOCK;
 #pragma unroll
-        for (int j = 0; j < 2 * NZ; ++j) zz[u][j] = (i * NZ + j < g.n * NZ) ? g.zrep[i * NZ + j] : 0.0;
+        for (int j = 0; j < 4 * NZ; ++j) zz[q][j] = (i * NZ + j < g.n * NZ) ? g.zrep[i * NZ + j] : 0.0;
       }
     } else {
-      uint64_t calls[PAIRS * NZA];
+      uint64_t calls[QUADS * NZA];
 #pragma unroll
-      for (int u = 0; u < PAIRS; ++u) {
-        const uint64_t c0 = ((g.first_global + (uint64_t)(tile0 + (int64_t)u * 2 * GSMC_BLOCK)) * (uint64_t)NZ) >> 1;
+      for (int q = 0; q < QUADS; ++q) {
+        const uint64_t c0 = ((g.first_global + (uint64_t)(tile0 + (int64_t)q * 4 * GSMC_BLOCK)) * (uint64_t)NZ) >> 2;
 #pragma unroll
-        for (int m = 0; m < NZ; ++m) calls[u * NZ + m] = c0 + m;
+        for (int m = 0; m < NZ; ++m) calls[q * NZ + m] = c0 + m;
       }
-      normal_pairs_v<PAIRS * NZA>(g.keys, calls, g.t, tabs.log64, tabs.sincos, &zz[0][0]);
+      normal_quads_v<QUADS * NZA>(g.keys, calls, g.t, tabs.logf, tabs.sincosf, &zz[0][0]);
     }
   }
   if (NU > 0) {
 #pragma unroll
-    for (int u = 0; u < PAIRS; ++u) {
-      const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
+    for (int u = 0; u < 2 * QUADS; ++u) {             // pair u: particles 2u, 2u+1 of this thread
+      const int64_t i = tile0 + (int64_t)(u >> 1) * 4 * GSMC_BLOCK + 2 * (u & 1);
       if (g.urep) {
 #pragma unroll
         for (int j = 0; j < 2 * NU; ++j) uu[u][j] = (i * NU + j < g.n * NU) ? g.urep[i * NU + j] : 0.0;
@@ -447,88 +455,95 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(co
   // Stage C: the model, per particle. log_weights[i] = weight (init) / += increment (step).
   // Stage D: vector stores of the new state and log weights.
 #pragma unroll
-  for (int u = 0; u < PAIRS; ++u) {
-    const int64_t i = tile0 + (int64_t)u * 2 * GSMC_BLOCK;
-    double out0[D], out1[D];
-    double w0, w1;
-    if constexpr (model_ctx_uniforms<Model>::value) {
-      // run-time number of uniforms per particle: the model draws them itself from the same virtual array
-      const int nu_rt = (int)a.p[0];
-      DrawCtx c0, c1;
-      c0.seed = c1.seed = g.seed; c0.t = c1.t = g.t;
-      c0.global_index = g.first_global + (uint64_t)i; c1.global_index = c0.global_index + 1;
-      // pad lanes (i >= n) have no replayed values: they draw from Philox like everybody else (results are discarded)
-      c0.urep = (g.urep && i < g.n) ? g.urep + i * nu_rt : nullptr; c1.urep = (g.urep && i + 1 < g.n) ? g.urep + (i + 1) * nu_rt : nullptr;
-      w0 = Model::template particle_ctx<INIT, PROP>(a, dyn_sm, prev[2 * u], zz[u], c0, out0);
-      w1 = Model::template particle_ctx<INIT, PROP>(a, dyn_sm, prev[2 * u + 1], zz[u] + NZ, c1, out1);
-    } else {
-      w0 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u], zz[u], uu[u], out0);
-      w1 = Model::template particle<INIT, PROP>(a, dyn_sm, prev[2 * u + 1], zz[u] + NZ, uu[u] + NU, out1);
-    }
-    if (a.unobserved) { w0 = 0.0; w1 = 0.0; }     // no constrained choice at this step (static_ir/generate.jl:36-42)
-    const Real r0 = (Real)(INIT ? w0 : lwv[2 * u] + w0), r1 = (Real)(INIT ? w1 : lwv[2 * u + 1] + w1);
+  for (int q = 0; q < QUADS; ++q) {
+    const int64_t i = tile0 + (int64_t)q * 4 * GSMC_BLOCK;
+    double out[4][D], w[4];
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      Real2 o; o.x = (Real)out0[d]; o.y = (Real)out1[d];
-      *reinterpret_cast<Real2*>(g.nxt + d * g.stride + i) = o;
+    for (int k = 0; k < 4; ++k) {
+      const int j = 4 * q + k;
+      if constexpr (model_ctx_uniforms<Model>::value) {
+        // run-time number of uniforms per particle: the model draws them itself from the same virtual array
+        const int nu_rt = (int)a.p[0];
+        DrawCtx c;
+        c.seed = g.seed; c.t = g.t;
+        c.global_index = g.first_global + (uint64_t)(i + k);
+        // pad lanes (i >= n) have no replayed values: they draw from Philox like everybody else (results are discarded)
+        c.urep = (g.urep && i + k < g.n) ? g.urep + (i + k) * nu_rt : nullptr;
+        w[k] = Model::template particle_ctx<INIT, PROP>(a, dyn_sm, prev[j], &zz[q][k * NZ], c, out[k]);
+      } else {
+        w[k] = Model::template particle<INIT, PROP>(a, dyn_sm, prev[j], &zz[q][k * NZ], &uu[j >> 1][(k & 1) * NU], out[k]);
+      }
+      if (unobserved) w[k] = 0.0;                     // no constrained choice at this step (static_ir/generate.jl:36-42)
     }
-    Real2 l; l.x = r0; l.y = r1;
-    *reinterpret_cast<Real2*>(g.lw + i) = l;
-    lwv[2 * u] = (double)r0; lwv[2 * u + 1] = (double)r1;
+    Real r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = (Real)(INIT ? w[k] : lwv[4 * q + k] + w[k]);
+#pragma unroll
+    for (int d = 0; d < D; ++d) store4(g.nxt + d * g.stride + i, out[0][d], out[1][d], out[2][d], out[3][d]);
+    store4(g.lw + i, (double)r[0], (double)r[1], (double)r[2], (double)r[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lwv[4 * q + k] = (double)r[k];
   }
   if (lim < TILE) {                                            // last tile only: pad lanes drop out of the reduction
 #pragma unroll
-    for (int u = 0; u < PAIRS; ++u) {
-      const int o = 2 * (int)threadIdx.x + u * 2 * GSMC_BLOCK;
-      if (o >= lim) lwv[2 * u] = -gm_inf();
-      if (o + 1 >= lim) lwv[2 * u + 1] = -gm_inf();
+    for (int j = 0; j < NP; ++j) {
+      const int o = 4 * (int)threadIdx.x + (j >> 2) * 4 * GSMC_BLOCK + (j & 3);
+      if (o >= lim) lwv[j] = -gm_inf();
     }
   }
 
-  // Stage E: block partial of (max, sum exp(lw-max), sum exp(2(lw-max))); NaN log weights poison s1/s2 on purpose.
-  // max_nn drops NaNs, so the max needs no NaN test; a NaN log weight then turns into a NaN exp below.
-  // Pairwise tree (independent compares) rather than one dependent chain.
-  double mt[NP];
+  // Stage E: this THREAD's running (max, sum exp(lw-max), sum exp(2(lw-max))) over all its particles of all tiles: no
+  // shuffle, barrier or shared-memory traffic per tile; the block combines its threads' triples once, after the tile
+  // loop. NaN log weights poison s1/s2 on purpose: max_nn drops NaNs (the accumulator never is NaN), so the max needs
+  // no NaN test, and a NaN log weight turns into a NaN exp below. Two chains of compares rather than one.
+  double ma = max_nn(-gm_inf(), lwv[0]), mb = max_nn(-gm_inf(), lwv[NP / 2]);
 #pragma unroll
-  for (int j = 0; j < NP; ++j) mt[j] = max_nn(-gm_inf(), lwv[j]);
+  for (int j = 1; j < NP / 2; ++j) { ma = max_nn(ma, lwv[j]); mb = max_nn(mb, lwv[NP / 2 + j]); }
+  const double mn = max_nn(max_nn(tm, ma), mb);
+  if (mn > -gm_inf()) {
+    double x[NP + 1], e[NP + 1];
 #pragma unroll
-  for (int w = NP / 2; w >= 1; w >>= 1) {
+    for (int j = 0; j < NP; ++j) x[j] = lwv[j] - mn;             // -inf for pad lanes -> exp = 0
+    x[NP] = tm - mn;                                             // rescales the sums so far (-inf the first time: they are 0)
+    gm_exp_nonpos_v<NP + 1>(x, e, tabs.exp2);
+    double a1 = 0.0, a2 = 0.0;
 #pragma unroll
-    for (int j = 0; j < w; ++j) mt[j] = max_nn(mt[j], mt[j + w]);
-  }
-  double m = warp_max(mt[0]);
-  if (lane == 0) red[warp] = m;
-  __syncthreads();
-  // block max: every group of 8 lanes loads the 8 warp maxima and folds them with a 3-step butterfly
-  double bm = red[lane & (GSMC_BLOCK / 32 - 1)];
-#pragma unroll
-  for (int o = GSMC_BLOCK / 64; o > 0; o >>= 1) bm = max_nn(bm, __shfl_xor_sync(0xffffffffu, bm, o));
-  double s1 = 0.0, s2 = 0.0;
-  if (bm > -gm_inf()) {
-    double x[NP], e[NP];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) x[j] = lwv[j] - bm;           // -inf for pad lanes -> exp = 0
-    gm_exp_nonpos_v<NP>(x, e, tabs.exp2);
-#pragma unroll
-    for (int j = 0; j < NP; ++j) { s1 += e[j]; s2 += e[j] * e[j]; }
+    for (int j = 0; j < NP; ++j) { a1 += e[j]; a2 += e[j] * e[j]; }
+    t1 = t1 * e[NP] + a1;
+    t2 = t2 * (e[NP] * e[NP]) + a2;
+    tm = mn;
   } else {
-    // a tile of -inf / NaN log weights only: no exp is evaluated, so look for the NaNs explicitly
+    // -inf / NaN log weights only so far: no exp is evaluated, so look for the NaNs explicitly
     bool any_nan = false;
 #pragma unroll
     for (int j = 0; j < NP; ++j) any_nan = any_nan || (lwv[j] != lwv[j]);
-    if (any_nan) { s1 = gm_nan(); s2 = gm_nan(); }
-  }
-  s1 = warp_sum(s1); s2 = warp_sum(s2);
-  if (lane == 0) { red[32 + warp] = s1; red[64 + warp] = s2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-    for (int w = 0; w < GSMC_BLOCK / 32; ++w) { t1 += red[32 + w]; t2 += red[64 + w]; }
-    LseTriple tr; tr.m = bm; tr.s1 = t1; tr.s2 = t2;
-    run = (tile == (int)blockIdx.x) ? tr : lse_merge_t(run, tr, tabs.exp2);
+    if (any_nan) { t1 = gm_nan(); t2 = gm_nan(); }
   }
   }  // tiles
+  // The block's triple from its threads' triples: block max, one exp per thread, two block sums.
+  {
+    const double m = warp_max(tm);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    // every group of 8 lanes loads the 8 warp maxima and folds them with a 3-step butterfly
+    double bm = red[lane & (GSMC_BLOCK / 32 - 1)];
+#pragma unroll
+    for (int o = GSMC_BLOCK / 64; o > 0; o >>= 1) bm = max_nn(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+    double s1 = t1, s2 = t2;                                     // (all -inf: 0, or NaN when a NaN log weight was seen)
+    if (bm > -gm_inf()) {
+      const double e = gm_exp_nonpos_t(tm - bm, tabs.exp2);
+      s1 = t1 * e; s2 = t2 * (e * e);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { red[32 + warp] = s1; red[64 + warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < GSMC_BLOCK / 32; ++w) { b1 += red[32 + w]; b2 += red[64 + w]; }
+      run.m = bm; run.s1 = b1; run.s2 = b2;
+    }
+  }
   if (threadIdx.x == 0) {
     g.partials[blockIdx.x] = run;
     // The last block to publish its partial reduces all of them (replaces a separate one-block launch).
@@ -1223,15 +1238,26 @@ __device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
   return v;
 }
 
-// Key of a CDF entry inside a group's bracket [TL, TH): the largest 32-bit word that still selects a particle at or
-// before it, min(trunc((double)(C - TL) * 2^32 / (double)(TH - TL)), 2^32 - 1) (the conversion saturates).
-// (double)(u64) as fma(hi, 2^32, lo): one rounding of the exact value, i.e. the same bits as the direct conversion, with
-// two 32-bit conversions instead of the multi-instruction 64-bit one.
-__device__ __forceinline__ uint32_t bracket_key(uint64_t c_minus_tl, double r32) {
-  const double d = fma((double)(uint32_t)(c_minus_tl >> 32), 4294967296.0, (double)(uint32_t)c_minus_tl);
-  return __double2uint_rz(d * r32);
+// Key of a CDF entry inside a group's bracket [TL, TH): (nearly) the largest 32-bit word that still selects a particle
+// at or before it, i.e. (C - TL) 2^32 / (TH - TL), in integer arithmetic (no int<->fp64 conversion per entry): with
+// D = TH - TL normalised to 32 bits, Dn = top 32 bits of D << clz(D) (in [2^31, 2^32)), the multiplier
+// M = trunc((2^63 - 2^10) / Dn) (in [2^31, 2^32), one fp64 division per group) and c' = top 32 bits of (C - TL) << clz(D)
+// (<= Dn), the key is (c' M) >> 31 < 2^32: non-decreasing in C, off the exact quotient by a few units of 2^-32.
+struct BracketScale { uint32_t lz, mul; };
+__device__ __forceinline__ BracketScale bracket_scale(uint64_t tl, uint64_t th) {
+  BracketScale b; b.lz = 0; b.mul = 0;                          // TH <= TL: every key is 0
+  if (th > tl) {
+    const uint64_t d = th - tl;
+    b.lz = (uint32_t)__clzll((long long)d);
+    const uint32_t dn = (uint32_t)((d << b.lz) >> 32);
+    b.mul = __double2uint_rz(9223372036854774784.0 / (double)dn);
+  }
+  return b;
 }
-__device__ __forceinline__ double bracket_ratio(uint64_t tl, uint64_t th) { return th > tl ? 4294967296.0 / (double)(th - tl) : 0.0; }
+__device__ __forceinline__ uint32_t bracket_key(uint64_t c_minus_tl, BracketScale b) {
+  const uint32_t cn = (uint32_t)((c_minus_tl << b.lz) >> 32);
+  return (uint32_t)(((uint64_t)cn * b.mul) >> 31);
+}
 // global CDF value of the particle behind an ancestor word
 __device__ __forceinline__ uint64_t cdf_at(const CdfView& v, const DevScalars* ds, uint32_t word) {
   const int r = (int)(word >> GSMC_ANC_RANK_SHIFT);
@@ -1243,6 +1269,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+// one step of a branch-free binary search over 4-byte keys in shared memory: if (key[ad + probe] < w) ad += step, as a
+// load, a compare and a PREDICATED add (the compiler's own choice is compare + select + add)
+__device__ __forceinline__ void search_step(uint32_t& ad, uint32_t probe, uint32_t step, uint32_t w) {
+  asm("{\n .reg .pred p;\n .reg .u32 k, a;\n add.u32 a, %0, %1;\n ld.shared.u32 k, [a];\n setp.lt.u32 p, k, %2;\n @p add.u32 %0, %0, %3;\n}"
+      : "+r"(ad) : "r"(probe), "r"(w), "r"(step));
+}
 // Bracket of a group on the global CDF, as global positions (rank * n_per + index): low word p_lo, high word p_hi.
 __device__ __noinline__ uint64_t bracket_global(const CdfView& v, const DevScalars* ds, uint64_t tl, uint64_t th) {
   GtU64 g_lo; g_lo.T = tl;
@@ -1253,7 +1285,7 @@ __device__ __noinline__ uint64_t bracket_global(const CdfView& v, const DevScala
   return p_lo | (p_hi << 32);
 }
 // Ancestor word of the draw with Philox word w in the bracket [p_lo, p_hi): p_lo + #{p : K_p < w}, keys evaluated per probe.
-__device__ __noinline__ uint32_t draw_global(const CdfView& v, const DevScalars* ds, uint32_t p_lo, uint32_t p_hi, uint64_t tl, double r32, uint32_t w) {
+__device__ __noinline__ uint32_t draw_global(const CdfView& v, const DevScalars* ds, uint32_t p_lo, uint32_t p_hi, uint64_t tl, BracketScale r32, uint32_t w) {
   uint32_t l = p_lo, h = p_hi;
   const uint32_t n_per = (uint32_t)v.n_per;
   while (l < h) {
@@ -1398,7 +1430,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
       int p_hi = s_pos[warp + 1];
       p_hi = p_hi < len - 1 ? p_hi : len - 1;
       // keys of the bracket, in place (low word of each 8-byte entry); brackets of different warps are disjoint
-      const double r32 = bracket_ratio(TL, TH);
+      const BracketScale r32 = bracket_scale(TL, TH);
       for (int p = p_lo + lane; p < p_hi; p += 32) {
         const uint32_t key = bracket_key(cw[p] - TL, r32);
         *reinterpret_cast<uint32_t*>(cw + p) = key;
@@ -1413,17 +1445,17 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
       for (int j = 0; j < GSMC_SEARCH_TPT; ++j) ad[j] = cw_base + (uint32_t)p_lo * 8u;
       // (halving by n/2, n/4, ... rather than a power-of-two ladder with immediate offsets: power-of-two strides put
       // every lane's probe into the same shared-memory bank, measured 143 us against 107 us)
-      const int n_search = p_hi - p_lo;
+      const int n_search = __shfl_sync(0xffffffffu, p_hi - p_lo, 0);     // warp-uniform (broadcast: lets the loop control run on the uniform datapath)
       for (int rem = n_search; rem > 1;) {
         const int half = rem >> 1;
         const uint32_t probe = (uint32_t)(half - 1) * 8u, step = (uint32_t)half * 8u;
 #pragma unroll
-        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (lds_u32(ad[j] + probe) < wd[j]) ad[j] += step;
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) search_step(ad[j], probe, step, wd[j]);
         rem -= half;
       }
       if (n_search > 0) {
 #pragma unroll
-        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) if (lds_u32(ad[j]) < wd[j]) ad[j] += 8u;
+        for (int j = 0; j < GSMC_SEARCH_TPT; ++j) search_step(ad[j], 0u, 8u, wd[j]);
       }
       if (lane == 0) ad[0] = cw_base + (uint32_t)p_lo * 8u;        // the order statistic that opens the group
       if (len_b == 0) {                                    // the usual case (block-uniform): the window lies in one rank
@@ -1439,7 +1471,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
     } else {
       // same definition on the global CDF (out of line: rare, and the hot loop stays small)
       const uint64_t br = bracket_global(v, ds, TL_abs, TH_abs);
-      const double r32 = bracket_ratio(TL_abs, TH_abs);
+      const BracketScale r32 = bracket_scale(TL_abs, TH_abs);
 #pragma unroll
       for (int j = 0; j < GSMC_SEARCH_TPT; ++j)
         a[j] = draw_global(v, ds, (uint32_t)br, (j == 0 && lane == 0) ? (uint32_t)br : (uint32_t)(br >> 32), TL_abs, r32, wd[j]);

@@ -123,7 +123,8 @@ static void philox_pair(uint64_t seed, uint64_t call, uint32_t t, uint32_t strea
   *b = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
 }
 
-/* Box-Muller: call c yields normals for elements 2c (cos branch) and 2c+1 (sin branch). */
+/* fp64 Box-Muller on 53-bit uniforms: the Gamma gaps of the resampler and the observation choices of unobserved steps
+ * (call c yields elements 2c (cos branch) and 2c+1 (sin branch) of those streams). */
 static void box_muller(uint64_t a, uint64_t b, double* z0, double* z1) {
   const double u1 = ((double)(a >> 11) + 0.5) * 0x1p-53;   /* (0,1) */
   const double u2 = (double)(b >> 11) * 0x1p-53;           /* [0,1) */
@@ -134,14 +135,25 @@ static void box_muller(uint64_t a, uint64_t b, double* z0, double* z1) {
   *z1 = r * s;
 }
 
+/* Per-particle normal draws (stream 0): call c yields elements 4c .. 4c+3; pair 0 = (radius word out[0], angle word
+ * out[1]), pair 1 = (out[2], out[3]); cos branch first. The transform is evaluated in fp32 on the 32-bit words
+ * (gm_box_muller_u32 of the shared gsmc_math.h, also under -DORC_USE_LIBM: its accuracy is checked directly against
+ * glibc in tests/test_math.py) and widened to fp64. */
 void orc_fill_normals(uint64_t seed, uint32_t t, uint64_t first, uint64_t count, double* out) {
   for (uint64_t e = first; e < first + count; ++e) {
-    uint64_t a, b; double z0, z1;
-    philox_pair(seed, e >> 1, t, ORC_STREAM_NORMAL, &a, &b);
-    box_muller(a, b, &z0, &z1);
+    uint32_t ctr[4] = { (uint32_t)(e >> 2), (uint32_t)((e >> 2) >> 32), t, ORC_STREAM_NORMAL };
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t o[4];
+    double z0, z1;
+    orc_philox4x32_10(ctr, key, o);
+    const int pair = (int)((e >> 1) & 1);
+    gm_box_muller_u32(o[2 * pair], o[2 * pair + 1], gm_logtabf_h, gm_sincostabf_h, &z0, &z1);
     out[e - first] = (e & 1) ? z1 : z0;
   }
 }
+/* pieces of the fp32 transform for tests/test_math.py */
+float orc_nlog_u32f(uint32_t w) { return gm_nlog_u32f(w, gm_logtabf_h); }
+void orc_sincos_u32f(uint32_t a, float* s, float* c) { gm_sincos_u32f(a, gm_sincostabf_h, s, c); }
 
 void orc_fill_uniforms(uint64_t seed, uint32_t t, uint32_t stream, uint64_t first, uint64_t count, double* out) {
   for (uint64_t e = first; e < first + count; ++e) {
@@ -301,16 +313,29 @@ void orc_search_iid(const uint64_t* cdf, int64_t n, const double* u, int64_t m, 
  *   any other slot: w_k = 32-bit word (k & 3) of Philox call k >> 2 of stream ORC_STREAM_RESAMPLE places the draw at
  *                   TL + w_k (TH - TL) / 2^32; compared in the domain of the 32-bit words:
  *                   anc_k = p_lo + #{p in [p_lo, p_hi) : K_p < w_k},
- *                   K_p = min(trunc((double)(C_p - TL) * (2^32 / (double)(TH - TL))), 2^32 - 1)
- * (K_p is the largest word that still selects a particle <= p; it is non-decreasing in p, so the count is a binary
- * search. No per-draw floating-point arithmetic is left: one conversion per CDF entry of the bracket.) */
+ *                   K_p = (C_p - TL) 2^32 / (TH - TL) in integer arithmetic: with D = TH - TL, lz = clz64(D),
+ *                   Dn = (D << lz) >> 32 (the top 32 bits, in [2^31, 2^32)), M = trunc((2^63 - 2^10) / (double)Dn) and
+ *                   c' = ((C_p - TL) << lz) >> 32 (<= Dn):  K_p = (c' * M) >> 31  (< 2^32; all keys 0 when TH <= TL)
+ * (K_p is, up to a few units of 2^-32, the largest word that still selects a particle <= p; it is non-decreasing in
+ * p, so the count is a binary search. No per-draw arithmetic is left: two integer multiplies per CDF entry.) */
 static uint64_t thr_of(uint64_t x, double ratio, uint64_t total) {
   uint64_t T = (uint64_t)((double)x * ratio);
   return T < total ? T : total - 1;
 }
-uint32_t orc_bracket_key(uint64_t c_minus_tl, double r32) {
-  const double x = (double)c_minus_tl * r32;
-  return x >= 4294967295.0 ? 0xffffffffu : (uint32_t)x;
+/* scale of a bracket: lz in the high word, M in the low word; 0 when TH <= TL */
+uint64_t orc_bracket_scale(uint64_t tl, uint64_t th) {
+  if (th <= tl) return 0;
+  const uint64_t d = th - tl;
+  const int lz = __builtin_clzll(d);
+  const uint32_t dn = (uint32_t)((d << lz) >> 32);
+  const uint32_t mul = (uint32_t)(9223372036854774784.0 / (double)dn);      /* 2^63 - 2^10, exactly a double */
+  return ((uint64_t)lz << 32) | mul;
+}
+uint32_t orc_bracket_key(uint64_t c_minus_tl, uint64_t scale) {
+  const int lz = (int)(scale >> 32);
+  const uint32_t mul = (uint32_t)scale;
+  const uint32_t cn = (uint32_t)((c_minus_tl << lz) >> 32);
+  return (uint32_t)(((uint64_t)cn * mul) >> 31);
 }
 void orc_search_sorted(const uint64_t* cdf, int64_t n, uint64_t seed, uint32_t rho, int64_t m, int64_t* anc) {
   const uint64_t total = cdf[n - 1];
@@ -327,7 +352,7 @@ void orc_search_sorted(const uint64_t* cdf, int64_t n, uint64_t seed, uint32_t r
     const int64_t p_lo = upper_bound_u64(cdf, n, TL);
     int64_t p_hi = upper_bound_u64(cdf, n, TH);
     if (p_hi > n - 1) p_hi = n - 1;
-    const double r32 = TH > TL ? 4294967296.0 / (double)(TH - TL) : 0.0;
+    const uint64_t r32 = orc_bracket_scale(TL, TH);
     for (int64_t k = j * ORC_GROUP; k < (j + 1) * ORC_GROUP && k < m; ++k) {
       int64_t pos = p_lo;
       if (k > j * ORC_GROUP) {

@@ -66,6 +66,8 @@ uint64_t orc_gap_head(uint64_t seed, uint32_t rho, uint64_t m);
 double orc_div_inv(double x, double c);
 double orc_log_pos(double x);
 double orc_exp_nonpos(double x);
+float orc_nlog_u32f(uint32_t w);                       /* -ln((w + 1/2) 2^-32) in fp32: radius of the per-particle normals */
+void orc_sincos_u32f(uint32_t a, float* s, float* c);  /* (sin, cos)(2 pi a 2^-32) in fp32 */
 double orc_log_unit(double x);   /* gm_log_unit: log of a uniform in (0,1), Box-Muller radius */
 int64_t orc_muldiv_mismatches(uint64_t seed, int64_t n);
 int64_t orc_div_inv_mismatches(uint64_t seed, int64_t n);
@@ -88,7 +90,8 @@ void orc_quantise_weights(const double* lw, int64_t n, uint64_t n_global, uint64
 void orc_search_iid(const uint64_t* cdf, int64_t n, const double* u, int64_t m, int64_t* anc);
 /* grouped-order-statistics search of the m draws of event rho (0-based ancestors): the slot that opens a group takes
  * the group's lower bracket position; every other slot counts the 32-bit bracket keys below its Philox word */
-uint32_t orc_bracket_key(uint64_t c_minus_tl, double r32);   /* min(trunc((double)(C_p - TL) * r32), 2^32 - 1) */
+uint64_t orc_bracket_scale(uint64_t tl, uint64_t th);              /* (clz64(TH - TL) << 32) | M, 0 when TH <= TL */
+uint32_t orc_bracket_key(uint64_t c_minus_tl, uint64_t scale);    /* ((((C_p - TL) << lz) >> 32) * M) >> 31 */
 void orc_search_sorted(const uint64_t* cdf, int64_t n, uint64_t seed, uint32_t rho, int64_t m, int64_t* anc);
 
 /* ---- particle filter ---- */

@@ -53,6 +53,10 @@ class Oracle:
         L.orc_log_pos.argtypes = [C.c_double]
         L.orc_exp_nonpos.restype = C.c_double
         L.orc_exp_nonpos.argtypes = [C.c_double]
+        L.orc_nlog_u32f.restype = C.c_float
+        L.orc_nlog_u32f.argtypes = [C.c_uint32]
+        L.orc_sincos_u32f.restype = None
+        L.orc_sincos_u32f.argtypes = [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_log_unit.restype = C.c_double
         L.orc_log_unit.argtypes = [C.c_double]
         L.orc_muldiv_mismatches.restype = C.c_int64
@@ -88,7 +92,9 @@ class Oracle:
         L.orc_quantise_weights.argtypes = [_dp, C.c_int64, C.c_uint64, _up, _dp]
         L.orc_search_iid.argtypes = [_up, C.c_int64, _dp, C.c_int64, _ip]
         L.orc_bracket_key.restype = C.c_uint32
-        L.orc_bracket_key.argtypes = [C.c_uint64, C.c_double]
+        L.orc_bracket_key.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_bracket_scale.restype = C.c_uint64
+        L.orc_bracket_scale.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_search_sorted.argtypes = [_up, C.c_int64, C.c_uint64, C.c_uint32, C.c_int64, _ip]
         L.orc_pf_create.restype = C.c_void_p
         L.orc_pf_create.argtypes = [C.c_int, _dp, C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int]

@@ -36,10 +36,49 @@ def test_sincospi_atan2_accuracy(orc):
         assert ulps(math.atan2(y, x), orc.L.orc_atan2(float(y), float(x))) <= 4.0
 
 
+def test_fp32_box_muller_pieces_against_glibc(orc):
+    """gm_nlog_u32f / gm_sincos_u32f (the fp32 transform behind the per-particle normals, shared by device and oracle)
+    against glibc in double: -ln((w + 1/2) 2^-32) to 1e-5 relative over the whole range (next to 1 through the
+    complement), always positive; (sin, cos)(2 pi a 2^-32) to 1e-7 absolute."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    ws = np.concatenate([rng.integers(0, 2 ** 32, 60000, dtype=np.uint64), rng.integers(2 ** 32 - 2 ** 26, 2 ** 32, 20000, dtype=np.uint64),
+                         np.arange(0, 2000, dtype=np.uint64), 2 ** 32 - 1 - np.arange(0, 2000, dtype=np.uint64),
+                         np.uint64(1) << np.arange(0, 32, dtype=np.uint64), (np.uint64(1) << np.arange(1, 32, dtype=np.uint64)) - np.uint64(1),
+                         np.array([0xfe000000 - 1, 0xfe000000, 0xfe000001], dtype=np.uint64)])
+    worst = 0.0
+    for w in ws:
+        w = int(w)
+        got, ref = float(orc.L.orc_nlog_u32f(w)), -math.log1p(-(2 ** 32 - w - 0.5) * 2.0 ** -32)
+        assert got > 0.0
+        worst = max(worst, abs(got - ref) / ref)
+    assert worst < 1e-5, worst
+    s, c = C.c_float(), C.c_float()
+    worst = 0.0
+    j = np.arange(0, 128, dtype=np.uint64) << np.uint64(25)
+    for a in np.concatenate([rng.integers(0, 2 ** 32, 60000, dtype=np.uint64), np.arange(0, 1000, dtype=np.uint64), j, j + np.uint64((1 << 24) - 1), j + np.uint64(1 << 24)]):
+        a = int(a) & 0xffffffff
+        orc.L.orc_sincos_u32f(a, C.byref(s), C.byref(c))
+        th = 2 * math.pi * a / 2 ** 32
+        worst = max(worst, abs(s.value - math.sin(th)), abs(c.value - math.cos(th)))
+    assert worst < 1e-7, worst
+    orc.L.orc_sincos_u32f(0, C.byref(s), C.byref(c))
+    assert (s.value, c.value) == (0.0, 1.0)
+    orc.L.orc_sincos_u32f(1 << 30, C.byref(s), C.byref(c))
+    assert (s.value, c.value) == (1.0, 0.0)
+
+
 def test_box_muller_normals_are_standard(orc):
     z = orc.normals(12345, 7, 0, 400000)
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
     assert abs(np.mean(z ** 3)) < 0.03 and abs(np.mean(z ** 4) - 3) < 0.06
+    # the normals are fp32 values widened to fp64; Kolmogorov-Smirnov against the normal CDF (1% critical value) and
+    # no correlation between the cos and sin branches or between neighbouring calls
+    from scipy import stats
+    assert np.array_equal(z, z.astype(np.float32).astype(np.float64))
+    assert stats.kstest(z, "norm").statistic < 1.63 / math.sqrt(len(z))
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 0.01 and abs(np.corrcoef(z[0::4], z[2::4])[0, 1]) < 0.01
+    assert abs(np.mean(np.abs(z) > 3.0) - 0.0026998) < 0.0005
     assert np.array_equal(orc.normals(12345, 7, 1000, 10), z[1000:1010])          # counter-based: any slice
     u = orc.uniforms(1, 2, 1, 0, 100000)
     assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01

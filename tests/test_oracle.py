@@ -201,9 +201,15 @@ def test_resampling_arithmetic(orc):
         TL, TH = thr(A), thr(A + g[j])
         p_lo = int(np.searchsorted(cdf, np.uint64(TL), side="right"))
         p_hi = min(int(np.searchsorted(cdf, np.uint64(TH), side="right")), N - 1)
-        r32 = 4294967296.0 / float(TH - TL) if TH > TL else 0.0
-        keys = [min(int(float(cl[p] - TL) * r32), 2 ** 32 - 1) for p in range(p_lo, p_hi)]
-        assert keys == sorted(keys) and all(orc.L.orc_bracket_key(cl[p] - TL, r32) == k for p, k in zip(range(p_lo, p_hi), keys))
+        # keys (C_p - TL) 2^32 / (TH - TL) in integer arithmetic: D normalised to its top 32 bits, one 32-bit multiplier
+        D = TH - TL
+        lz = 64 - D.bit_length() if D > 0 else 0
+        mul = int(9223372036854774784.0 / float((D << lz) >> 32)) if D > 0 else 0
+        keys = [((((cl[p] - TL) << lz) >> 32) * mul) >> 31 for p in range(p_lo, p_hi)]
+        scale = orc.L.orc_bracket_scale(TL, TH)
+        assert scale == (lz << 32) | mul and all(0 <= k < 2 ** 32 for k in keys)
+        assert keys == sorted(keys) and all(orc.L.orc_bracket_key(cl[p] - TL, scale) == k for p, k in zip(range(p_lo, p_hi), keys))
+        assert all(abs(k - (cl[p] - TL) * 2 ** 32 // D) <= 8 for p, k in zip(range(p_lo, p_hi), keys) if D > 0)
         for k in range(256 * j, min(256 * (j + 1), M)):
             if k == 256 * j:
                 exp_anc.append(p_lo)
