@@ -37,6 +37,9 @@
 #ifndef GSMC_PROP_OCC
 #define GSMC_PROP_OCC 3
 #endif
+#ifndef GSMC_PROP_OCC_WIDE
+#define GSMC_PROP_OCC_WIDE 3
+#endif
 #define GSMC_TILE 2048            // particles (or thresholds) per block iteration of the scan / search kernels
 #define GSMC_TILE_SHIFT 11
 #define GSMC_PAD 2048             // local columns are padded to this many particles
@@ -257,6 +260,7 @@ struct PropArgs {
 template <class Model> struct PropTile {
   static constexpr int QUADS = Model::D <= 2 ? GSMC_PROP_QUADS : 1;
   static constexpr int TILE = 4 * GSMC_BLOCK * QUADS;
+  static constexpr int OCC = Model::D <= 2 ? GSMC_PROP_OCC : GSMC_PROP_OCC_WIDE;   // resident blocks per SM asked of the compiler
 };
 
 __device__ __forceinline__ LseTriple lse_merge(LseTriple a, LseTriple b) {
@@ -346,7 +350,7 @@ template <class M, class = void> struct model_ctx_uniforms { static constexpr bo
 template <class M> struct model_ctx_uniforms<M, decltype((void)M::CTX_UNIFORMS)> { static constexpr bool value = M::CTX_UNIFORMS; };
 
 template <class Model, typename Real, bool INIT, int PROP>
-__global__ void __launch_bounds__(GSMC_BLOCK, GSMC_PROP_OCC) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
+__global__ void __launch_bounds__(GSMC_BLOCK, PropTile<Model>::OCC) propagate_kernel(const PropArgs<Real> g, const ModelArgs a) {
   typedef typename Vec2T<Real>::type Real2;
   constexpr int D = Model::D;
   constexpr int QUADS = PropTile<Model>::QUADS, NP = 4 * QUADS, TILE = PropTile<Model>::TILE;
