@@ -1123,9 +1123,11 @@ __global__ void __launch_bounds__(1024) partition_kernel(CdfView v, uint64_t k_f
   __shared__ uint64_t s_draws, s_cn, s_head;
   __shared__ uint64_t off_q[GSMC_MAX_RANKS + 1], off_e[GSMC_MAX_RANKS + 1];   // exclusive prefixes of the ranks' totals, [R] = sum
   __shared__ uint64_t tot_q[GSMC_MAX_RANKS], tot_e[GSMC_MAX_RANKS];
+  // The decision was final before the weights pass of this event triggered this launch (it waited for the deciding kernel
+  // first), so a step that does not resample leaves WITHOUT waiting for the previous kernel to drain.
+  if (conditional && !ds->do_resample) { pdl_trigger(); return; }   // every rank takes the same decision: nobody sends, nobody waits
   pdl_wait();
   pdl_trigger();
-  if (conditional && !ds->do_resample) return;          // every rank takes the same decision: nobody sends, nobody waits
   const int n_segs = v.n_segs, R = v.nranks;
   if (FUSED_SCAN) {
     const uint32_t seq = ds->xseq + 1;                    // the totals exchange of this step (see DevScalars::xseq)
@@ -1331,9 +1333,9 @@ __global__ void __launch_bounds__(GSMC_BLOCK, GSMC_SEARCH_OCC) search_sorted_ker
   extern __shared__ __align__(16) uint64_t cwin[];                 // GSMC_WIN_CAP + 4
   __shared__ uint64_t mbar;
   __shared__ int s_pos[GSMC_GPT + 1];                              // window positions of the order statistics that bracket the tile's groups
+  if (conditional && !ds->do_resample) { pdl_trigger(); return; }   // (see partition_kernel: no wait on a step that does not resample)
   pdl_wait();
   pdl_trigger();
-  if (conditional && !ds->do_resample) return;
   const uint64_t m_draws = ds->n_draws, cn = ds->cdf_total;
   const double ratio = ds->thr_ratio;
   const uint32_t rho = ds->rho;
