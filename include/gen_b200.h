@@ -67,7 +67,9 @@ typedef struct gsmc_config {
   int32_t dtype;             /* GSMC_F64 | GSMC_F32 */
   int32_t resample_scheme;   /* GSMC_RESAMPLE_* */
   uint64_t num_particles;    /* global particle count N (all ranks together) */
-  uint64_t seed;             /* Philox key */
+  uint64_t seed;             /* Philox4x32-10 key. Every draw is a function of (seed, global particle index, time step): the
+                              * result does not depend on the GPU count. Standard normals have the resolution of their two
+                              * 32-bit words (Box-Muller evaluated in fp32, widened to fp64); all model arithmetic is fp64. */
   int32_t device;            /* CUDA device ordinal, -1 = current device */
   int32_t keep_history;      /* 1: keep every step's state + ancestor columns (get_traces semantics) */
   int64_t history_capacity;  /* number of time steps to preallocate when keep_history (0 = 128) */
