@@ -460,11 +460,12 @@ static int ensure_f64(gsmc_filter* f, size_t n) {
 // Hot-path kernels are launched with programmatic stream serialization (see pdl_wait in kernels.cuh): the
 // launch latency and the prologue of kernel k+1 overlap the tail of kernel k. GSMC_NO_PDL=1 turns it off.
 // GSMC_PDL_MASK=<bits> selects the kernel classes that may start early (bit 0 propagate, 1 finalize, 2 weights,
-// 3 partition, 4 search, 5 everything else). Default 0x3e: everything but propagate -- measured on B200 (cfg 3, ms per
-// run): all classes 24.97, none 23.02, all but propagate 22.38 (profiles/r2_pdl_masks.txt).
+// 3 partition, 4 search, 5 everything else). Default 0x3f: every class. Measured on B200 (cfg 3, ms per run): while
+// search_sorted_kernel triggered its dependents early, all classes 20.47, all but propagate 19.84, none 20.70; with the
+// trigger of the search kernel left to block exit, all classes 19.52 (profiles/r2_pdl_masks.txt).
 enum { PDL_PROPAGATE = 0, PDL_FINALIZE, PDL_WEIGHTS, PDL_PARTITION, PDL_SEARCH, PDL_OTHER };
 static unsigned pdl_mask() {
-  static unsigned mask = getenv("GSMC_NO_PDL") ? 0u : (getenv("GSMC_PDL_MASK") ? (unsigned)strtoul(getenv("GSMC_PDL_MASK"), nullptr, 0) : 0x3eu);
+  static unsigned mask = getenv("GSMC_NO_PDL") ? 0u : (getenv("GSMC_PDL_MASK") ? (unsigned)strtoul(getenv("GSMC_PDL_MASK"), nullptr, 0) : 0x3fu);
   return mask;
 }
 // While a run is being captured into a graph, the kernel that follows a conditional node (and the first kernel of a

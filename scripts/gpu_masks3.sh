@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+cp gen_b200/libgensmc.so /tmp/head.so
+for v in variants/*.so; do cp $v gen_b200/libgensmc.so
+for M in 0x3e 0x3f; do
+  GSMC_PDL_MASK=$M python bench.py --no-cpu-baseline --steps 10 > gpurun_out/bench_mask.json 2>/dev/null
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_mask.json')); print('$v mask $M ms_per_step %.3f e2e %.3f' % (d['ms_per_step'], d['e2e']['ms_per_step']))"
+done; done
+cp /tmp/head.so gen_b200/libgensmc.so
