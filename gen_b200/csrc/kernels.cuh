@@ -8,17 +8,19 @@
 // programmatic dependent launch (pdl_wait / pdl_trigger below).
 //
 //   propagate_kernel   particle_filter.jl:84-88,103-105 (init), :143-146,165-172 (step) fused with the ancestor gather
-//                      of :202-205 and with logsumexp/ESS: per-tile partials -> per-block running triple -> the last
-//                      block to finish reduces the block partials into this rank's (max, sum e, sum e^2)
+//                      of :202-205 and with logsumexp/ESS: every thread carries a running (max, sum e, sum e^2) over its
+//                      particles, the block combines them once, the last block to finish reduces the block partials into
+//                      this rank's triple and (gsmc_run_steps) takes the next maybe_resample! decision itself
 //   finalize_kernel    inference.jl:3-6 + particle_filter.jl:3-12 (normalize_weights, ESS): merge of the ranks' triples
 //                      (fused NVLink mailbox exchange), the `ess < ess_threshold` decision and
 //                      `log_ml_est += log_total - log N` of :194,201; the Bool goes to the host through a pinned mirror
 //   weights_kernel     `weights = exp.(lnw)` + the CDF behind Categorical(weights/sum(weights)), :199-200, in 64-bit fixed
 //                      point so the prefix sum is associative (order/shard independent), as a two-level CDF; fused: the
-//                      exponential spacings of the sorted uniforms (the N iid draws of :200, generated already sorted so
-//                      that search + gather stream through memory)
+//                      Gamma gaps of the groups of sorted draws (the N iid draws of :200 are generated as grouped order
+//                      statistics, so that search + gather stream through memory)
 //   partition_kernel   scan of the segment totals (+ exchange of the ranks' totals) and the CDF window of every tile
-//   search_sorted_kernel  parents[i] (:200): TMA-staged CDF window, binary search + walks in shared memory
+//   search_sorted_kernel  parents[i] (:200): TMA-staged CDF window, per-group bracket, integer keys, binary searches over
+//                      4-byte keys in shared memory
 //   search_iid_kernel  replay / sample_unweighted_traces (:62-70); resid_* / det_copies: the residual scheme
 #ifndef GSMC_KERNELS_CUH
 #define GSMC_KERNELS_CUH
