@@ -153,3 +153,15 @@ def test_table_log_of_the_box_muller_radius(orc):
         assert got <= 0.0
         worst = max(worst, abs(got - ref) / max(1.0, abs(ref)))
     assert worst < 4e-16, worst
+
+
+def test_lookup_tables_are_the_generated_ones():
+    """gen_b200/csrc/gsmc_tables.h (exp2, sin/cos, and the fp32 log / sin-cos tables of the normal generator) is what
+    scripts/gen_math_tables.py generates with mpmath: correctly rounded entries, no hand edits."""
+    import os
+    import subprocess
+    import sys
+    pytest.importorskip("mpmath")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_math_tables.py")], capture_output=True, text=True, check=True).stdout
+    assert out.strip() == open(os.path.join(root, "gen_b200", "csrc", "gsmc_tables.h")).read().strip()
