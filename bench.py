@@ -288,6 +288,9 @@ def run_ours(args):
                                "multinomial resampling at ESS<N/2, trace history %s" % (wl["name"], args.log2n, wl["proposal_name"], "dropped" if args.no_history else "kept"),
                    "particles_total": N, "time_steps": T, "resamples_per_run": n_resamples,
                    "parallelism": "particles sharded over %d GPU(s)" % world,
+                   "arithmetic": "all model arithmetic (transition, logpdf, weights, logsumexp, ESS) in fp64; random numbers: "
+                                 "Philox4x32-10, standard normals by a Box-Muller transform evaluated in fp32 on 32-bit words "
+                                 "(cuRAND-like resolution) and widened to fp64",
                    "l2": "inputs larger than L2: each step streams >=3 columns of %d MiB (126 MB L2), history columns are never re-read" % (n_per * S >> 20)},
         "log_ml": lml, "log_ml_kalman": wl["kalman"], "log_ml_e2e": lml_e2e,
         "clocks": clocks,
