@@ -265,23 +265,30 @@ template <class Model> struct PropTile {
   static constexpr int OCC = Model::D <= 2 ? GSMC_PROP_OCC : GSMC_PROP_OCC_WIDE;   // resident blocks per SM asked of the compiler
 };
 
-__device__ __forceinline__ LseTriple lse_merge(LseTriple a, LseTriple b) {
-  if (!(b.m > -gm_inf()) && b.s1 == b.s1) return a;
-  if (!(a.m > -gm_inf()) && a.s1 == a.s1) return b;
-  LseTriple r;
-  r.m = fmax(a.m, b.m);
-  const double ea = gm_exp(a.m - r.m), eb = gm_exp(b.m - r.m);
-  r.s1 = a.s1 * ea + b.s1 * eb;
-  r.s2 = a.s2 * (ea * ea) + b.s2 * (eb * eb);
+// Merge of the ranks' (max, s1, s2) triples by ONE WARP (all 32 lanes call it): lane r < R evaluates its own rescaling
+// factor exp(m_r - M) against the maximum over the ranks -- one exp per lane in parallel instead of a chain of 2 (R - 1)
+// on one thread, which sat on the critical path of every step of a sharded filter -- and the products are added in rank
+// order on every lane. All ranks run the same code on the same eight triples: identical bits everywhere. One rank: the
+// triple itself (exp(0) = 1 exactly). NaN sums propagate (0 * NaN), empty triples
+// (max = -inf, sums 0) drop out.
+__device__ __forceinline__ LseTriple merge_ranks_warp(const DevScalars* ds, int nranks) {
+  const int lane = threadIdx.x & 31;
+  LseTriple t; t.m = -gm_inf(); t.s1 = 0.0; t.s2 = 0.0;
+  if (lane < nranks) t = ds->triples[lane];
+  double M = t.m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(0xffffffffu, M, o); M = y > M ? y : M; }
+  const double e = (t.m > -gm_inf()) ? gm_exp(t.m - M) : 0.0;
+  const double p1 = t.s1 * e, p2 = t.s2 * (e * e);
+  LseTriple r; r.m = M; r.s1 = 0.0; r.s2 = 0.0;
+  for (int q = 0; q < nranks; ++q) { r.s1 += __shfl_sync(0xffffffffu, p1, q); r.s2 += __shfl_sync(0xffffffffu, p2, q); }
   return r;
 }
 
-// Combine the per-rank triples in rank order and take the maybe_resample! decision.
+// The maybe_resample! decision from the merged triple t (one thread).
 // ess_threshold < 0: statistics only. resampled_flag_out: flag slot of the NEXT step.
-__device__ __forceinline__ void combine_and_decide(DevScalars* ds, int nranks, double ess_threshold,
+__device__ __forceinline__ void combine_and_decide(DevScalars* ds, LseTriple t, double ess_threshold,
                                                    double n_global, int* resampled_flag_out, int64_t next_step) {
-  LseTriple t = ds->triples[0];
-  for (int r = 1; r < nranks; ++r) t = lse_merge(t, ds->triples[r]);
   const bool empty = !(t.m > -gm_inf()) && t.s1 == t.s1;
   const double log_total = empty ? -gm_inf() : t.m + gm_log(t.s1);       // inference.jl:3-6
   // particle_filter.jl:3-12 literally: lnw = lw - log_total; ess = exp(-logsumexp(2 lnw)) with
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(GSMC_BLOCK, PropTile<Model>::OCC) propagate_ke
     if (threadIdx.x == 0) {
       g.ds->triples[g.rank] = tr; g.ds->blocks_done = 0;
       if (g.fuse_decide && g.nranks == 1) {
-        combine_and_decide(g.ds, 1, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
+        combine_and_decide(g.ds, tr, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
         if (g.cond_handle) cudaGraphSetConditional(g.cond_handle, g.ds->do_resample ? 1u : 0u);
       }
     }
@@ -577,9 +584,12 @@ __global__ void __launch_bounds__(GSMC_BLOCK, PropTile<Model>::OCC) propagate_ke
       __syncthreads();
       ll_allgather_u64(g.peers, g.ds, g.rank, g.nranks, s_seq, s_mine, 3, reinterpret_cast<uint64_t*>(g.ds->triples));
       __syncthreads();
-      if (threadIdx.x == 0) {
-        combine_and_decide(g.ds, g.nranks, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
-        if (g.cond_handle) cudaGraphSetConditional(g.cond_handle, g.ds->do_resample ? 1u : 0u);
+      if (threadIdx.x < 32) {
+        const LseTriple all = merge_ranks_warp(g.ds, g.nranks);
+        if (threadIdx.x == 0) {
+          combine_and_decide(g.ds, all, g.fuse_threshold, g.n_global, g.next_flag, (int64_t)g.t + 1);
+          if (g.cond_handle) cudaGraphSetConditional(g.cond_handle, g.ds->do_resample ? 1u : 0u);
+        }
       }
     }
   }
@@ -646,13 +656,15 @@ __global__ void __launch_bounds__(32) finalize_kernel(DevScalars* ds, int rank, 
     __syncwarp();
     ll_allgather_u64(peers, ds, rank, nranks, seq, mine, 3, reinterpret_cast<uint64_t*>(ds->triples));
     __syncwarp();
-    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
+    const LseTriple all = merge_ranks_warp(ds, nranks);
+    if (threadIdx.x == 0) { combine_and_decide(ds, all, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
   } else if (nranks > 1 && xmode == XMODE_LOCAL) {
     if ((int)threadIdx.x < nranks && (int)threadIdx.x != rank) ds->triples[threadIdx.x] = peers.ds[threadIdx.x]->triples[threadIdx.x];
     __syncwarp();
-    if (threadIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
+    const LseTriple all = merge_ranks_warp(ds, nranks);
+    if (threadIdx.x == 0) { combine_and_decide(ds, all, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
   } else if (nranks == 1) {
-    if (threadIdx.x == 0) { combine_and_decide(ds, 1, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
+    if (threadIdx.x == 0) { combine_and_decide(ds, ds->triples[0], ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); if (cond_handle) cudaGraphSetConditional(cond_handle, ds->do_resample ? 1u : 0u); }
   }
 }
 // cross-GPU barrier (peer-memory exchange of one word): nobody passes until every rank has arrived
@@ -692,7 +704,9 @@ __global__ void peer_copy_kernel(PeerScalars peers, DevScalars* ds, int rank, in
 // multi-rank: runs after the allgather of ds->triples
 __global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, double n_global, int* resampled_flag_out,
                               int64_t next_step, DevScalars* host, uint32_t token) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { combine_and_decide(ds, nranks, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const LseTriple all = merge_ranks_warp(ds, nranks);
+  if (threadIdx.x == 0) { combine_and_decide(ds, all, ess_threshold, n_global, resampled_flag_out, next_step); publish_decision(ds, host, token); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -702,9 +716,9 @@ __global__ void decide_kernel(DevScalars* ds, int nranks, double ess_threshold, 
 // so that C_i = (rank offset) + sp[segment(i)] + cl[i]. A segment is a run of seg_tiles consecutive
 // 2048-particle tiles owned by ONE block of the streaming pass, which carries the running sum in a
 // register: no inter-block dependency, no look-back, and only n_segs (a few hundred) totals are left to
-// scan. The global CDF is never materialised (lw is read once, exp evaluated once). The exponential
-// spacings of the sorted uniforms are generated by the same pass and kept as 4-byte values (plus their
-// segment-local tile prefixes), so the search pass neither re-runs Philox nor the log.
+// scan. The global CDF is never materialised (lw is read once, exp evaluated once). The Gamma gaps of the
+// groups of sorted draws (one per 256 output slots) and their segment-local tile prefixes are generated by
+// the same pass.
 // ------------------------------------------------------------------------------------------------
 template <typename Real>
 __device__ __forceinline__ void q_from_lw(typename Vec2T<Real>::type a, typename Vec2T<Real>::type b, int64_t i, int64_t n,
