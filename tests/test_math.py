@@ -165,3 +165,98 @@ def test_lookup_tables_are_the_generated_ones():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_math_tables.py")], capture_output=True, text=True, check=True).stdout
     assert out.strip() == open(os.path.join(root, "gen_b200", "csrc", "gsmc_tables.h")).read().strip()
+
+
+def test_fp32_box_muller_independent_restatement(orc):
+    """The definition of the per-particle normals, restated here with exact rational arithmetic and ONE correct rounding
+    to float32 per operation (no C, no shared header, tables recomputed with mpmath), must give the bits of the
+    shared gm_box_muller_u32: radius, angle, and whole draws taken from Philox words (element e -> call e >> 2, pair
+    (e >> 1) & 1, cos / sin branch e & 1)."""
+    import ctypes as C
+    import struct
+    from fractions import Fraction as Fr
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+
+    def rn32(x):
+        """exact rational (or mpf) -> nearest float32 (ties to even), as an exact Fraction; normal range only"""
+        if not isinstance(x, Fr):                           # an mpmath value (200 bits): far finer than any float32 tie
+            x = Fr(int(mp.nint(mp.mpf(x) * mp.mpf(2) ** 300)), 2 ** 300)
+        if x == 0:
+            return Fr(0)
+        s, a = (1 if x > 0 else -1), abs(x)
+        e = a.numerator.bit_length() - a.denominator.bit_length()
+        if Fr(2) ** e > a:
+            e -= 1                                          # 2^e <= a < 2^(e+1)
+        assert e >= -126
+        scaled = a / Fr(2) ** (e - 23)                     # in [2^23, 2^24)
+        n, rem = divmod(scaled.numerator, scaled.denominator)
+        twice = 2 * rem
+        if twice > scaled.denominator or (twice == scaled.denominator and (n & 1)):
+            n += 1
+        return s * Fr(n) * Fr(2) ** (e - 23)
+
+    def bits32(x):
+        return struct.unpack("<I", struct.pack("<f", float(x)))[0]      # x is exactly a float32: float() is exact
+
+    c = lambda v: Fr(np.float32(v).item())                              # the float32 constant the C source spells
+    ln2f, kpi = rn32(mp.log(2)), rn32(mp.pi / 64 / 2 ** 25)
+    ltab = []
+    for i in range(64):
+        ic = rn32(1 / (1 + (mp.mpf(i) + mp.mpf(1) / 2) / 64))
+        ltab.append((ic, rn32(mp.log(2 * mp.mpf(ic.numerator) / mp.mpf(ic.denominator)))))
+    sctab = [(rn32(mp.sin(mp.pi * j / 64)) if j % 64 else Fr(0), rn32(mp.cos(mp.pi * j / 64)) if (j - 32) % 64 else Fr(0)) for j in range(128)]
+
+    def nlog(w):
+        if w >= 0xfe000000:
+            y = rn32(rn32(rn32(Fr((~w) & 0xffffffff)) + Fr(1, 2)) * c(2.32830644e-10))
+            q = rn32(c(0.25) * y + c(0.333333343))
+            q = rn32(q * y + Fr(1, 2))
+            q = rn32(q * y + 1)
+            return rn32(q * y)
+        v = 2 * w + 1
+        lz = 33 - v.bit_length()
+        t = (v << lz) >> 1
+        m = 1 + Fr((t >> 8) & 0x7fffff, 2 ** 23)
+        ic, t2 = ltab[(t >> 25) & 63]
+        r = rn32(m * ic - 1)
+        q = rn32(c(0.333333343) * r - Fr(1, 2))
+        q = rn32(q * r + 1)
+        base = rn32(lz * ln2f + t2)
+        l = rn32(-q * r + base)
+        return l if l > 0 else Fr(0)
+
+    def sincos(a):
+        b = (a + 0x01000000) & 0xffffffff
+        d = (b & 0x01ffffff) - 0x01000000
+        x = rn32(Fr(d) * kpi)
+        z = rn32(x * x)
+        sx = rn32(rn32(x * z) * c(-0.166666672) + x)
+        cm = rn32(z * rn32(z * c(0.0416666679) - Fr(1, 2)))
+        S, Cc = sctab[b >> 25]
+        sn = rn32(S + rn32(S * cm + rn32(Cc * sx)))
+        cs = rn32(Cc + rn32(Cc * cm - rn32(S * sx)))
+        return sn, cs
+
+    def box(wr, wa):
+        l = nlog(wr)
+        l2 = rn32(l + l)
+        r = rn32(mp.sqrt(mp.mpf(l2.numerator) / mp.mpf(l2.denominator))) if l2 > 0 else Fr(0)
+        sn, cs = sincos(wa)
+        return float(rn32(r * cs)), float(rn32(r * sn))
+
+    rng = np.random.default_rng(11)
+    words = [int(w) for w in rng.integers(0, 2 ** 32, 1500, dtype=np.uint64)] + [0, 1, 2, 2 ** 31, 2 ** 32 - 1, 0xfe000000 - 1, 0xfe000000,
+                                                                                   0xffffff00, 2 ** 24, 2 ** 24 - 1, 0x80000001, 0x7fffffff]
+    s, cc = C.c_float(), C.c_float()
+    for w in words:
+        assert bits32(nlog(w)) == bits32(Fr(float(orc.L.orc_nlog_u32f(w)))), hex(w)
+        orc.L.orc_sincos_u32f(w, C.byref(s), C.byref(cc))
+        sn, cs = sincos(w)
+        assert (bits32(sn), bits32(cs)) == (bits32(Fr(s.value)), bits32(Fr(cc.value))), hex(w)
+    seed, t = 0x0123456789abcdef, 9
+    z = orc.normals(seed, t, 0, 400)
+    for call in range(100):
+        o = orc.philox([call, 0, t, 0], [seed & 0xffffffff, seed >> 32])
+        exp = box(o[0], o[1]) + box(o[2], o[3])
+        assert [float(v) for v in z[4 * call: 4 * call + 4]] == list(exp), call
